@@ -1,0 +1,141 @@
+/*
+ * ofdg.h -- C ABI of the B200-native on-the-fly optical-flow data generator.
+ *
+ * This is the drop-in boundary for the reference's render path: every entry point names the
+ * reference interface it stands in for (paths relative to /root/reference). Plain pointers and
+ * sizes only; no C++ or torch types. Every function that can fail returns 0 on success and a
+ * nonzero code otherwise, with a message available from ofdg_last_error() (thread-local).
+ * No exception crosses this boundary. A generator handle is bound to one CUDA device and is not
+ * thread-safe: use one handle per GPU / per producer thread.
+ *
+ * There is no CPU fallback: every render entry point fails with OFDG_ERR_CUDA when no sm_100
+ * device is usable.
+ */
+#ifndef OFDG_OFDG_H_
+#define OFDG_OFDG_H_
+
+#include <stdint.h>
+
+#include "ofdg/scene.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFDG_VERSION 100
+
+enum {
+  OFDG_OK = 0,
+  OFDG_ERR_ARG = 1,     /* bad argument / descriptor the reference would also reject (std::runtime_error there) */
+  OFDG_ERR_CUDA = 2,    /* CUDA runtime error, or no usable device */
+  OFDG_ERR_STATE = 3    /* call order (e.g. render before textures were uploaded) */
+};
+
+typedef struct ofdg_generator ofdg_generator; /* replaces DataGenerator::DataGenerator, include/caffe/data_generation/DataGenerator.h:449-500 */
+typedef struct ofdg_params ofdg_params;       /* replaces ObjectParametersGenerator, DataGenerator.h:508-588 */
+typedef struct ofdg_tasks ofdg_tasks;         /* an owned, growable ofdg_task_batch (std::queue<TaskBucket*> m_undone_tasks) */
+typedef struct ofdg_prepared ofdg_prepared;   /* a flattened batch resident in HBM */
+
+/* data_generation_param / data_param subset + the compile-time size of the reference
+ * (src/caffe/proto/caffe.proto:6-12, DataGenerator.h:55-56). */
+typedef struct ofdg_config {
+  int32_t device;            /* CUDA device ordinal */
+  int32_t width, height;     /* DGEN_WIDTH, DGEN_HEIGHT (512 x 384); width % 4 == 0 */
+  int32_t mode;              /* 1..13 */
+  int32_t use_antialiasing;  /* default 1 */
+  int32_t max_batch;         /* largest batch a single render call may carry */
+  int32_t reserved[8];       /* zero */
+} ofdg_config;
+
+const char* ofdg_last_error(void);
+int32_t ofdg_version(void);
+
+/* ---- host parameter stream ------------------------------------------------------------------ */
+/* ObjectParametersGenerator ctor (src/caffe/DataGenerator.cpp:1358-2054): 45 engines seeded
+ * seed_offset+0..44. n_fields > 0 makes mode 9 assign field-pool ids. fg_override > 0 forces
+ * the number of foreground objects (stress config only; 0 = the mode's own distribution). */
+int ofdg_params_create(int32_t mode, int32_t width, int32_t height, int32_t seed_offset, int32_t n_fields,
+                       int32_t fg_override, ofdg_params** out);
+void ofdg_params_destroy(ofdg_params* p);
+/* The commission loop of load_batch (src/caffe/layers/data_generation_layer.cpp:197-214):
+ * appends n_tasks freshly drawn tasks to `out`. */
+int ofdg_params_generate(ofdg_params* p, int32_t n_tasks, ofdg_tasks* out);
+int ofdg_params_skip(ofdg_params* p, uint64_t n_tasks);          /* checkpoint/resume: fast-forward */
+uint64_t ofdg_params_tasks_generated(const ofdg_params* p);
+uint64_t ofdg_params_draws(const ofdg_params* p, int32_t slot);  /* draws made by engine `slot` so far */
+const char* ofdg_params_slot_name(int32_t slot);
+
+int ofdg_tasks_create(ofdg_tasks** out);
+void ofdg_tasks_destroy(ofdg_tasks* t);
+void ofdg_tasks_clear(ofdg_tasks* t);
+/* Borrowed view; valid until the next mutation of `t`. */
+int ofdg_tasks_view(const ofdg_tasks* t, ofdg_task_batch* out);
+/* Deep-copies a caller-built batch (tests, foreign producers). */
+int ofdg_tasks_assign(ofdg_tasks* t, const ofdg_task_batch* src);
+
+/* ---- host geometry (exposed for known-answer tests) ------------------------------------------- */
+/* Vertices the rasteriser is fed for an ellipse / polygon under matrix m[6] = {sx,shy,shx,sy,tx,ty}
+ * (conv_transform + conv_curve + iround(v*256); DataGenerator.cpp:465-534). Writes up to `cap`
+ * (x,y) int32 pairs, returns the count (or -1). */
+int32_t ofdg_flatten_ellipse(double rx, double ry, const double* m, int32_t* xy, int32_t cap);
+int32_t ofdg_flatten_polygon(const int32_t* seg_type, const float* seg_x, const float* seg_y, int32_t n,
+                             const double* m, int32_t* xy, int32_t cap);
+
+/* ---- generator ------------------------------------------------------------------------------------ */
+int ofdg_create(const ofdg_config* cfg, ofdg_generator** out);   /* DataGenerator ctor + Start(), DataGenerator.cpp:990-1030 */
+void ofdg_destroy(ofdg_generator* g);                            /* Stop() + dtor */
+
+/* TextureCollection ctor (DataGenerator.cpp:117-149) minus the image-file decoding: `planar` is
+ * n x 3 x h x w uint8 in the channel order the reference holds after its R<->B swap. One-time
+ * upload into the HBM-resident pool. All textures share one size, >= 2*width x 2*height. */
+int ofdg_upload_textures(ofdg_generator* g, const uint8_t* planar, int32_t n, int32_t w, int32_t h);
+/* Fills the pool with n procedural textures generated on the device (no texture database is
+ * available offline); bit-identical to ofdg_b200.synth_textures() in numpy. */
+int ofdg_synth_textures(ofdg_generator* g, int32_t n, int32_t w, int32_t h, uint64_t seed);
+int ofdg_download_texture(ofdg_generator* g, int32_t index, uint8_t* planar_out);
+
+/* Mode 9: inject the pool of (flow, iflow) crops the reference takes from
+ * WarpFields::CropGenerator::get_crop (src/caffe/WarpFields.cpp:516-538). fields is
+ * n x 2 x 2 x (height+1) x (width+1) float: [field][flow|iflow][channel][y][x]. */
+int ofdg_set_fields(ofdg_generator* g, const float* fields, int32_t n);
+
+/* Process_TaskBucket (DataGenerator.cpp:1175-1254) for a whole batch, writing straight into the
+ * caller's DEVICE blobs: img0/img1 = batch x 3 x H x W, flow = batch x 2 x H x W, float32.
+ * `stream` is a cudaStream_t (NULL = the generator's own stream; then the call synchronises). */
+int ofdg_render(ofdg_generator* g, const ofdg_task_batch* tasks, float* d_img0, float* d_img1, float* d_flow,
+                void* stream);
+/* Same with HOST blobs (pinned or pageable): scene upload, kernels and the device-to-host copy of
+ * the three blobs all inside the call -- what Forward_cpu delivers (data_generation_layer.cpp:266-282). */
+int ofdg_render_host(ofdg_generator* g, const ofdg_task_batch* tasks, float* h_img0, float* h_img1, float* h_flow);
+
+/* Parity instrumentation: additionally returns (to HOST buffers, any may be NULL)
+ *   masks: batch x max_objs x 4 x H x W uint8 -- per top-level foreground object in z-order
+ *          [AA frame0, AA frame1, noAA frame0, noAA frame1]   (MovingObjectBase::m_masks_*)
+ *   id0/id1: batch x H x W uint32                              (RenderCore::index_image0/1)
+ *   frames8: batch x 2 x 3 x H x W uint8                       (RenderCore::frame0/1) */
+int ofdg_render_debug(ofdg_generator* g, const ofdg_task_batch* tasks, float* h_img0, float* h_img1, float* h_flow,
+                      uint8_t* masks, int32_t max_objs, uint32_t* id0, uint32_t* id1, uint8_t* frames8);
+/* The prepared 2W x 2H background texture of every task (Texture::getRandomizedCrop(2W,2H,...),
+ * DataGenerator.cpp:1186-1192), planar batch x 3 x 2H x 2W uint8; pixels outside the region the
+ * renderer needs are 0 and `need` (batch x 4: x0,y0,x1,y1) reports that region. */
+int ofdg_debug_background(ofdg_generator* g, const ofdg_task_batch* tasks, uint8_t* planar_out, int32_t* need);
+
+/* Flatten + upload once, render many times (throughput measurement with inputs resident in HBM). */
+int ofdg_prepare(ofdg_generator* g, const ofdg_task_batch* tasks, ofdg_prepared** out);
+void ofdg_prepared_destroy(ofdg_prepared* p);
+int ofdg_render_prepared(ofdg_generator* g, const ofdg_prepared* p, float* d_img0, float* d_img1, float* d_flow,
+                         void* stream);
+
+/* One-call producer used by the layer: draws `batch` tasks from `p` and renders them into device blobs. */
+int ofdg_generate(ofdg_generator* g, ofdg_params* p, int32_t batch, float* d_img0, float* d_img1, float* d_flow,
+                  void* stream);
+
+/* Number of kernel launches issued by this generator so far (bench.py's gpu_launches). */
+uint64_t ofdg_launch_count(const ofdg_generator* g);
+/* Events-based duration (ms) of the main render kernel of the last render call on this generator. */
+float ofdg_last_render_kernel_ms(const ofdg_generator* g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFDG_OFDG_H_ */

@@ -1,0 +1,553 @@
+// C-ABI implementation (include/ofdg/ofdg.h): handle management, uploads, launches.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "host/flatten.hpp"
+#include "host/params.hpp"
+#include "ofdg/ofdg.h"
+#include "render.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+
+struct CudaError : std::runtime_error {
+  explicit CudaError(const std::string& m) : std::runtime_error(m) {}
+};
+struct ArgError : std::runtime_error {
+  explicit ArgError(const std::string& m) : std::runtime_error(m) {}
+};
+struct StateError : std::runtime_error {
+  explicit StateError(const std::string& m) : std::runtime_error(m) {}
+};
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(e_));                        \
+  } while (0)
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return OFDG_OK;
+  } catch (const CudaError& e) {
+    g_error = e.what();
+    return OFDG_ERR_CUDA;
+  } catch (const StateError& e) {
+    g_error = e.what();
+    return OFDG_ERR_STATE;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return OFDG_ERR_ARG;
+  }
+}
+
+// Device buffer that only ever grows.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) CK(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    CK(cudaMalloc(&p, bytes));
+    cap = bytes;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) CK(cudaFreeHost(p));
+    p = nullptr;
+    cap = 0;
+    CK(cudaMallocHost(&p, bytes));
+    cap = bytes;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// A flattened batch resident on the device.
+struct DeviceScene {
+  DevBuf samples, objects, shapes, verts;
+  int batch = 0;
+  void release() { samples.release(); objects.release(); shapes.release(); verts.release(); }
+};
+
+}  // namespace
+
+struct ofdg_params {
+  std::unique_ptr<ofdg::ParamStream> ps;
+};
+struct ofdg_tasks {
+  ofdg::TaskBatch tb;
+};
+struct ofdg_prepared {
+  DeviceScene scene;
+  int device = 0;
+};
+
+struct ofdg_generator {
+  ofdg_config cfg{};
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // texture pool
+  DevBuf pool;
+  int n_tex = 0, tex_w = 0, tex_h = 0;
+  // mode 9 fields
+  DevBuf fields;
+  int n_fields = 0;
+  // per-call scene staging + scratch
+  DeviceScene scene;
+  PinnedBuf staging;
+  DevBuf bg, pos_x, alpha_x, pos_y, alpha_y;
+  DevBuf out0, out1, outf;  // device blobs for the *_host entry points
+  DevBuf dbg_masks, dbg_id0, dbg_id1, dbg_frames8, dbg_planar;
+  ofdg::FlatBatch flat;
+  ofdg::TaskBatch gen_tasks;
+  uint64_t launches = 0;
+  float last_kernel_ms = 0.f;
+
+  void use() const { CK(cudaSetDevice(cfg.device)); }
+};
+
+namespace {
+
+void check_batch(const ofdg_generator* g, int n) {
+  if (n <= 0) throw ArgError("empty task batch");
+  if (n > g->cfg.max_batch) throw ArgError("batch larger than ofdg_config.max_batch");
+  if (g->n_tex <= 0) throw StateError("no textures uploaded (ofdg_upload_textures / ofdg_synth_textures)");
+}
+
+void upload_scene(ofdg_generator* g, const ofdg::FlatBatch& fb, DeviceScene& ds, cudaStream_t s) {
+  const size_t b0 = fb.samples.size() * sizeof(ofdg::FlatSample), b1 = fb.objects.size() * sizeof(ofdg::FlatObject),
+               b2 = fb.shapes.size() * sizeof(ofdg::FlatShape), b3 = fb.verts.size() * sizeof(ofdg::FlatVertex);
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  g->staging.reserve(al(b0) + al(b1) + al(b2) + al(b3) + 256);
+  char* st = (char*)g->staging.p;
+  size_t o0 = 0, o1 = al(b0), o2 = o1 + al(b1), o3 = o2 + al(b2);
+  std::memcpy(st + o0, fb.samples.data(), b0);
+  std::memcpy(st + o1, fb.objects.data(), b1);
+  std::memcpy(st + o2, fb.shapes.data(), b2);
+  std::memcpy(st + o3, fb.verts.data(), b3);
+  ds.samples.reserve(b0 + 256); ds.objects.reserve(b1 + 256); ds.shapes.reserve(b2 + 256); ds.verts.reserve(b3 + 256);
+  CK(cudaMemcpyAsync(ds.samples.p, st + o0, b0, cudaMemcpyHostToDevice, s));
+  if (b1) CK(cudaMemcpyAsync(ds.objects.p, st + o1, b1, cudaMemcpyHostToDevice, s));
+  if (b2) CK(cudaMemcpyAsync(ds.shapes.p, st + o2, b2, cudaMemcpyHostToDevice, s));
+  if (b3) CK(cudaMemcpyAsync(ds.verts.p, st + o3, b3, cudaMemcpyHostToDevice, s));
+  ds.batch = (int)fb.samples.size();
+}
+
+void flatten_tasks(ofdg_generator* g, const ofdg_task_batch* tasks) {
+  ofdg::FlattenConfig fc;
+  fc.W = g->cfg.width; fc.H = g->cfg.height;
+  fc.tex_w = g->tex_w; fc.tex_h = g->tex_h; fc.n_tex = g->n_tex;
+  fc.mode = g->cfg.mode;
+  g->flat.clear();
+  ofdg::flatten(*tasks, fc, g->flat);
+}
+
+void ensure_scratch(ofdg_generator* g, int batch) {
+  const size_t W = g->cfg.width, H = g->cfg.height;
+  g->bg.reserve((size_t)batch * 4 * W * H * sizeof(uchar4));
+  g->pos_x.reserve((size_t)batch * 2 * W * sizeof(int));
+  g->alpha_x.reserve((size_t)batch * 2 * W * sizeof(double));
+  g->pos_y.reserve((size_t)batch * 2 * H * sizeof(int));
+  g->alpha_y.reserve((size_t)batch * 2 * H * sizeof(double));
+}
+
+ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, float* d1, float* df) {
+  ofdg::RenderArgs a{};
+  a.samples = (const ofdg::FlatSample*)ds.samples.p;
+  a.objects = (const ofdg::FlatObject*)ds.objects.p;
+  a.shapes = (const ofdg::FlatShape*)ds.shapes.p;
+  a.verts = (const ofdg::FlatVertex*)ds.verts.p;
+  a.batch = ds.batch;
+  a.W = g->cfg.width; a.H = g->cfg.height;
+  a.use_aa = g->cfg.use_antialiasing;
+  a.pool = (const uchar4*)g->pool.p;
+  a.tex_w = g->tex_w; a.tex_h = g->tex_h;
+  a.bg = (uchar4*)g->bg.p;
+  a.pos_x = (int*)g->pos_x.p; a.alpha_x = (double*)g->alpha_x.p;
+  a.pos_y = (int*)g->pos_y.p; a.alpha_y = (double*)g->alpha_y.p;
+  a.fields = (const float*)g->fields.p;
+  a.n_fields = g->n_fields;
+  a.img0 = d0; a.img1 = d1; a.flow = df;
+  return a;
+}
+
+// bg prep + render on stream s; times the render kernel with events on that stream.
+void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s) {
+  g->launches += ofdg::launch_background_prep(a, s);
+  CK(cudaEventRecord(g->ev0, s));
+  g->launches += ofdg::launch_render(a, s);
+  CK(cudaEventRecord(g->ev1, s));
+  CK(cudaGetLastError());
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ofdg_last_error(void) { return g_error.c_str(); }
+int32_t ofdg_version(void) { return OFDG_VERSION; }
+
+// ---- parameter stream ---------------------------------------------------------------------------
+int ofdg_params_create(int32_t mode, int32_t width, int32_t height, int32_t seed_offset, int32_t n_fields,
+                       int32_t fg_override, ofdg_params** out) {
+  return guarded([&] {
+    if (!out) throw ArgError("null output pointer");
+    if (width <= 0 || height <= 0) throw ArgError("bad output size");
+    std::unique_ptr<ofdg_params> p(new ofdg_params);
+    p->ps.reset(new ofdg::ParamStream(mode, width, height, seed_offset, n_fields, fg_override));
+    *out = p.release();
+  });
+}
+void ofdg_params_destroy(ofdg_params* p) { delete p; }
+int ofdg_params_generate(ofdg_params* p, int32_t n_tasks, ofdg_tasks* out) {
+  return guarded([&] {
+    if (!p || !out || n_tasks < 0) throw ArgError("bad arguments");
+    for (int i = 0; i < n_tasks; ++i) p->ps->next_task(out->tb);
+  });
+}
+int ofdg_params_skip(ofdg_params* p, uint64_t n_tasks) {
+  return guarded([&] {
+    if (!p) throw ArgError("null stream");
+    p->ps->skip(n_tasks);
+  });
+}
+uint64_t ofdg_params_tasks_generated(const ofdg_params* p) { return p ? p->ps->tasks_generated() : 0; }
+uint64_t ofdg_params_draws(const ofdg_params* p, int32_t slot) {
+  return (p && slot >= 0 && slot < ofdg::kNumSlots) ? p->ps->draws(slot) : 0;
+}
+const char* ofdg_params_slot_name(int32_t slot) { return ofdg::slot_name(slot); }
+
+int ofdg_tasks_create(ofdg_tasks** out) {
+  return guarded([&] {
+    if (!out) throw ArgError("null output pointer");
+    *out = new ofdg_tasks;
+  });
+}
+void ofdg_tasks_destroy(ofdg_tasks* t) { delete t; }
+void ofdg_tasks_clear(ofdg_tasks* t) {
+  if (t) t->tb.clear();
+}
+int ofdg_tasks_view(const ofdg_tasks* t, ofdg_task_batch* out) {
+  return guarded([&] {
+    if (!t || !out) throw ArgError("null pointer");
+    *out = t->tb.view();
+  });
+}
+int ofdg_tasks_assign(ofdg_tasks* t, const ofdg_task_batch* s) {
+  return guarded([&] {
+    if (!t || !s) throw ArgError("null pointer");
+    t->tb.task_begin.assign(s->task_begin, s->task_begin + s->n_tasks + 1);
+    t->tb.blueprints.assign(s->blueprints, s->blueprints + s->n_blueprints);
+    t->tb.seg_type.assign(s->seg_type, s->seg_type + s->n_segments);
+    t->tb.seg_x.assign(s->seg_x, s->seg_x + s->n_segments);
+    t->tb.seg_y.assign(s->seg_y, s->seg_y + s->n_segments);
+  });
+}
+
+// ---- host geometry ---------------------------------------------------------------------------------
+int32_t ofdg_flatten_ellipse(double rx, double ry, const double* m, int32_t* xy, int32_t cap) {
+  try {
+    std::vector<ofdg::FlatVertex> v;
+    ofdg::flatten_ellipse(rx, ry, m, v);
+    const int n = (int)v.size();
+    for (int i = 0; i < n && i < cap; ++i) { xy[2 * i] = v[i].x; xy[2 * i + 1] = v[i].y; }
+    return n;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return -1;
+  }
+}
+int32_t ofdg_flatten_polygon(const int32_t* seg_type, const float* seg_x, const float* seg_y, int32_t n,
+                             const double* m, int32_t* xy, int32_t cap) {
+  try {
+    std::vector<ofdg::FlatVertex> v;
+    ofdg::flatten_polygon(seg_type, seg_x, seg_y, n, m, v);
+    const int k = (int)v.size();
+    for (int i = 0; i < k && i < cap; ++i) { xy[2 * i] = v[i].x; xy[2 * i + 1] = v[i].y; }
+    return k;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return -1;
+  }
+}
+
+// ---- generator ---------------------------------------------------------------------------------------
+int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
+  return guarded([&] {
+    if (!cfg || !out) throw ArgError("null pointer");
+    if (cfg->width <= 0 || cfg->height <= 0 || cfg->width % 4) throw ArgError("width/height must be positive and width a multiple of 4");
+    if (cfg->mode < 1 || cfg->mode > 13) throw ArgError("BAD MODE");
+    if (cfg->max_batch <= 0 || cfg->max_batch > 65535) throw ArgError("max_batch must be in 1..65535");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      throw CudaError(std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) throw ArgError("bad device ordinal");
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) throw CudaError("this library carries sm_100a code only; found sm_" + std::to_string(prop.major * 10 + prop.minor));
+    std::unique_ptr<ofdg_generator> g(new ofdg_generator);
+    g->cfg = *cfg;
+    CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&g->ev0));
+    CK(cudaEventCreate(&g->ev1));
+    *out = g.release();
+  });
+}
+
+void ofdg_destroy(ofdg_generator* g) {
+  if (!g) return;
+  cudaSetDevice(g->cfg.device);
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  DevBuf* bufs[] = {&g->pool, &g->fields, &g->bg, &g->pos_x, &g->alpha_x, &g->pos_y, &g->alpha_y, &g->out0, &g->out1,
+                    &g->outf, &g->dbg_masks, &g->dbg_id0, &g->dbg_id1, &g->dbg_frames8, &g->dbg_planar};
+  for (DevBuf* b : bufs) b->release();
+  g->scene.release();
+  g->staging.release();
+  if (g->ev0) cudaEventDestroy(g->ev0);
+  if (g->ev1) cudaEventDestroy(g->ev1);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+}
+
+int ofdg_upload_textures(ofdg_generator* g, const uint8_t* planar, int32_t n, int32_t w, int32_t h) {
+  return guarded([&] {
+    if (!g || !planar || n <= 0) throw ArgError("bad arguments");
+    if (w < 2 * g->cfg.width || h < 2 * g->cfg.height) throw ArgError("textures must be at least 2*width x 2*height");
+    g->use();
+    const size_t plane = (size_t)w * h;
+    g->pool.reserve(plane * n * sizeof(uchar4));
+    DevBuf tmp;
+    const int chunk = 16;
+    tmp.reserve(plane * 3 * chunk);
+    for (int i = 0; i < n; i += chunk) {
+      const int m = std::min(chunk, n - i);
+      CK(cudaMemcpyAsync(tmp.p, planar + (size_t)i * 3 * plane, plane * 3 * m, cudaMemcpyHostToDevice, g->stream));
+      ofdg::launch_planar_to_rgbx((const uint8_t*)tmp.p, (uchar4*)g->pool.p + (size_t)i * plane, m, w, h, g->stream);
+      ++g->launches;
+      CK(cudaStreamSynchronize(g->stream));
+    }
+    tmp.release();
+    g->n_tex = n; g->tex_w = w; g->tex_h = h;
+  });
+}
+
+int ofdg_synth_textures(ofdg_generator* g, int32_t n, int32_t w, int32_t h, uint64_t seed) {
+  return guarded([&] {
+    if (!g || n <= 0) throw ArgError("bad arguments");
+    if (w < 2 * g->cfg.width || h < 2 * g->cfg.height) throw ArgError("textures must be at least 2*width x 2*height");
+    g->use();
+    const size_t plane = (size_t)w * h;
+    g->pool.reserve(plane * n * sizeof(uchar4));
+    const int chunk = 64;
+    for (int i = 0; i < n; i += chunk) {
+      ofdg::launch_synth_textures((uchar4*)g->pool.p + (size_t)i * plane, std::min(chunk, n - i), w, h, seed, i, g->stream);
+      ++g->launches;
+    }
+    CK(cudaStreamSynchronize(g->stream));
+    CK(cudaGetLastError());
+    g->n_tex = n; g->tex_w = w; g->tex_h = h;
+  });
+}
+
+int ofdg_download_texture(ofdg_generator* g, int32_t index, uint8_t* planar_out) {
+  return guarded([&] {
+    if (!g || !planar_out || index < 0 || index >= g->n_tex) throw ArgError("bad arguments");
+    g->use();
+    const size_t plane = (size_t)g->tex_w * g->tex_h;
+    g->dbg_planar.reserve(plane * 3);
+    ofdg::launch_rgbx_to_planar((const uchar4*)g->pool.p + (size_t)index * plane, (uint8_t*)g->dbg_planar.p, g->tex_w, g->tex_h, g->stream);
+    ++g->launches;
+    CK(cudaMemcpyAsync(planar_out, g->dbg_planar.p, plane * 3, cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+  });
+}
+
+int ofdg_set_fields(ofdg_generator* g, const float* fields, int32_t n) {
+  return guarded([&] {
+    if (!g || !fields || n <= 0) throw ArgError("bad arguments");
+    g->use();
+    const size_t per = (size_t)2 * 2 * (g->cfg.height + 1) * (g->cfg.width + 1) * sizeof(float);
+    g->fields.reserve(per * n);
+    CK(cudaMemcpy(g->fields.p, fields, per * n, cudaMemcpyHostToDevice));
+    g->n_fields = n;
+  });
+}
+
+int ofdg_render(ofdg_generator* g, const ofdg_task_batch* tasks, float* d_img0, float* d_img1, float* d_flow, void* stream) {
+  return guarded([&] {
+    if (!g || !tasks || !d_img0 || !d_img1 || !d_flow) throw ArgError("null pointer");
+    check_batch(g, tasks->n_tasks);
+    g->use();
+    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+    flatten_tasks(g, tasks);
+    ensure_scratch(g, tasks->n_tasks);
+    // the pinned staging area is reused by the next call: wait for the previous upload
+    CK(cudaStreamSynchronize(s));
+    upload_scene(g, g->flat, g->scene, s);
+    run_kernels(g, make_args(g, g->scene, d_img0, d_img1, d_flow), s);
+    if (!stream) CK(cudaStreamSynchronize(s));
+  });
+}
+
+int ofdg_render_host(ofdg_generator* g, const ofdg_task_batch* tasks, float* h_img0, float* h_img1, float* h_flow) {
+  return guarded([&] {
+    if (!g || !tasks || !h_img0 || !h_img1 || !h_flow) throw ArgError("null pointer");
+    check_batch(g, tasks->n_tasks);
+    g->use();
+    const size_t P = (size_t)g->cfg.width * g->cfg.height, n = tasks->n_tasks;
+    g->out0.reserve(n * 3 * P * sizeof(float)); g->out1.reserve(n * 3 * P * sizeof(float)); g->outf.reserve(n * 2 * P * sizeof(float));
+    cudaStream_t s = g->stream;
+    flatten_tasks(g, tasks);
+    ensure_scratch(g, tasks->n_tasks);
+    upload_scene(g, g->flat, g->scene, s);
+    run_kernels(g, make_args(g, g->scene, (float*)g->out0.p, (float*)g->out1.p, (float*)g->outf.p), s);
+    CK(cudaMemcpyAsync(h_img0, g->out0.p, n * 3 * P * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_img1, g->out1.p, n * 3 * P * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_flow, g->outf.p, n * 2 * P * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  });
+}
+
+int ofdg_render_debug(ofdg_generator* g, const ofdg_task_batch* tasks, float* h_img0, float* h_img1, float* h_flow,
+                      uint8_t* masks, int32_t max_objs, uint32_t* id0, uint32_t* id1, uint8_t* frames8) {
+  return guarded([&] {
+    if (!g || !tasks) throw ArgError("null pointer");
+    check_batch(g, tasks->n_tasks);
+    g->use();
+    const size_t P = (size_t)g->cfg.width * g->cfg.height, n = tasks->n_tasks;
+    g->out0.reserve(n * 3 * P * sizeof(float)); g->out1.reserve(n * 3 * P * sizeof(float)); g->outf.reserve(n * 2 * P * sizeof(float));
+    cudaStream_t s = g->stream;
+    flatten_tasks(g, tasks);
+    ensure_scratch(g, tasks->n_tasks);
+    CK(cudaMemsetAsync(g->bg.p, 0, n * 4 * P * sizeof(uchar4), s));
+    upload_scene(g, g->flat, g->scene, s);
+    ofdg::RenderArgs a = make_args(g, g->scene, (float*)g->out0.p, (float*)g->out1.p, (float*)g->outf.p);
+    if (masks && max_objs > 0) {
+      g->dbg_masks.reserve(n * max_objs * 4 * P);
+      CK(cudaMemsetAsync(g->dbg_masks.p, 0, n * max_objs * 4 * P, s));
+      a.dbg_masks = (uint8_t*)g->dbg_masks.p;
+      a.dbg_max_objs = max_objs;
+    }
+    if (id0 || id1) {
+      g->dbg_id0.reserve(n * P * 4); g->dbg_id1.reserve(n * P * 4);
+      a.dbg_id0 = (uint32_t*)g->dbg_id0.p; a.dbg_id1 = (uint32_t*)g->dbg_id1.p;
+    }
+    if (frames8) {
+      g->dbg_frames8.reserve(n * 6 * P);
+      a.dbg_frames8 = (uint8_t*)g->dbg_frames8.p;
+    }
+    run_kernels(g, a, s);
+    if (h_img0) CK(cudaMemcpyAsync(h_img0, g->out0.p, n * 3 * P * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (h_img1) CK(cudaMemcpyAsync(h_img1, g->out1.p, n * 3 * P * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (h_flow) CK(cudaMemcpyAsync(h_flow, g->outf.p, n * 2 * P * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (a.dbg_masks) CK(cudaMemcpyAsync(masks, a.dbg_masks, n * max_objs * 4 * P, cudaMemcpyDeviceToHost, s));
+    if (id0) CK(cudaMemcpyAsync(id0, a.dbg_id0, n * P * 4, cudaMemcpyDeviceToHost, s));
+    if (id1) CK(cudaMemcpyAsync(id1, a.dbg_id1, n * P * 4, cudaMemcpyDeviceToHost, s));
+    if (frames8) CK(cudaMemcpyAsync(frames8, a.dbg_frames8, n * 6 * P, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  });
+}
+
+int ofdg_debug_background(ofdg_generator* g, const ofdg_task_batch* tasks, uint8_t* planar_out, int32_t* need) {
+  return guarded([&] {
+    if (!g || !tasks || !planar_out) throw ArgError("null pointer");
+    check_batch(g, tasks->n_tasks);
+    g->use();
+    const size_t P4 = (size_t)g->cfg.width * g->cfg.height * 4, n = tasks->n_tasks;
+    cudaStream_t s = g->stream;
+    flatten_tasks(g, tasks);
+    ensure_scratch(g, tasks->n_tasks);
+    CK(cudaMemsetAsync(g->bg.p, 0, n * P4 * sizeof(uchar4), s));
+    upload_scene(g, g->flat, g->scene, s);
+    ofdg::RenderArgs a = make_args(g, g->scene, nullptr, nullptr, nullptr);
+    g->launches += ofdg::launch_background_prep(a, s);
+    g->dbg_planar.reserve(n * 3 * P4);
+    ofdg::launch_bg_to_planar((const uchar4*)g->bg.p, (uint8_t*)g->dbg_planar.p, (int)n, 2 * g->cfg.width, 2 * g->cfg.height, s);
+    g->launches += n;
+    CK(cudaMemcpyAsync(planar_out, g->dbg_planar.p, n * 3 * P4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (need)
+      for (size_t i = 0; i < n; ++i) std::memcpy(need + 4 * i, g->flat.samples[i].prep.need, 4 * sizeof(int32_t));
+  });
+}
+
+int ofdg_prepare(ofdg_generator* g, const ofdg_task_batch* tasks, ofdg_prepared** out) {
+  return guarded([&] {
+    if (!g || !tasks || !out) throw ArgError("null pointer");
+    check_batch(g, tasks->n_tasks);
+    g->use();
+    flatten_tasks(g, tasks);
+    std::unique_ptr<ofdg_prepared> p(new ofdg_prepared);
+    p->device = g->cfg.device;
+    upload_scene(g, g->flat, p->scene, g->stream);
+    CK(cudaStreamSynchronize(g->stream));
+    *out = p.release();
+  });
+}
+void ofdg_prepared_destroy(ofdg_prepared* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  p->scene.release();
+  delete p;
+}
+int ofdg_render_prepared(ofdg_generator* g, const ofdg_prepared* p, float* d_img0, float* d_img1, float* d_flow, void* stream) {
+  return guarded([&] {
+    if (!g || !p || !d_img0 || !d_img1 || !d_flow) throw ArgError("null pointer");
+    check_batch(g, p->scene.batch);
+    g->use();
+    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+    ensure_scratch(g, p->scene.batch);
+    run_kernels(g, make_args(g, p->scene, d_img0, d_img1, d_flow), s);
+    if (!stream) CK(cudaStreamSynchronize(s));
+  });
+}
+
+int ofdg_generate(ofdg_generator* g, ofdg_params* p, int32_t batch, float* d_img0, float* d_img1, float* d_flow, void* stream) {
+  if (!g || !p) { g_error = "null pointer"; return OFDG_ERR_ARG; }
+  int rc = guarded([&] {
+    g->gen_tasks.clear();
+    for (int i = 0; i < batch; ++i) p->ps->next_task(g->gen_tasks);
+  });
+  if (rc) return rc;
+  ofdg_task_batch v = g->gen_tasks.view();
+  return ofdg_render(g, &v, d_img0, d_img1, d_flow, stream);
+}
+
+uint64_t ofdg_launch_count(const ofdg_generator* g) { return g ? g->launches : 0; }
+float ofdg_last_render_kernel_ms(const ofdg_generator* g) {
+  if (!g) return 0.f;
+  float ms = 0.f;
+  if (cudaEventSynchronize(g->ev1) != cudaSuccess) return 0.f;
+  if (cudaEventElapsedTime(&ms, g->ev0, g->ev1) != cudaSuccess) return 0.f;
+  return ms;
+}
+
+}  // extern "C"

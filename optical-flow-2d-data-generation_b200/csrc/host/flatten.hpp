@@ -1,0 +1,42 @@
+// Host geometry stage: blueprints -> fixed-point outlines + per-object matrices.
+// Everything here is IEEE-double arithmetic in the order AGG 2.4 performs it, because the
+// results are rounded to 24.8 fixed point and must land on the same sub-pixel as the
+// reference's. Replaces, per object,
+//   setIntrinsicTransform / setMotion / addBackgroundMotion   DataGenerator.cpp:302-335
+//   setEllipse + conv_transform<ellipse>                       DataGenerator.cpp:459-476
+//   path_storage + conv_transform + conv_curve                 DataGenerator.cpp:491-531
+//   RealizeObjectBlueprint's object construction               DataGenerator.cpp:1065-1173
+// and, per sample, the parameter side of Texture::getRandomizedCrop (DataGenerator.cpp:87-109).
+#pragma once
+#include <vector>
+
+#include "../flat_scene.h"
+#include "ofdg/scene.h"
+
+namespace ofdg {
+
+struct FlatBatch {
+  std::vector<FlatSample> samples;
+  std::vector<FlatObject> objects;
+  std::vector<FlatShape> shapes;
+  std::vector<FlatVertex> verts;
+  void clear() { samples.clear(); objects.clear(); shapes.clear(); verts.clear(); }
+};
+
+struct FlattenConfig {
+  int W = 512, H = 384;      // output size (DGEN_WIDTH / DGEN_HEIGHT)
+  int tex_w = 0, tex_h = 0;  // pool texture size
+  int n_tex = 0;             // pool size
+  int mode = 1;              // only mode 9 attaches warp fields
+};
+
+// Appends the flattened form of every task in `tb` to `out`.
+// Throws std::runtime_error on descriptors the reference would also reject.
+void flatten(const ofdg_task_batch& tb, const FlattenConfig& cfg, FlatBatch& out);
+
+// Exposed for the known-answer tests.
+void flatten_ellipse(double rx, double ry, const double m[6], std::vector<FlatVertex>& out);
+void flatten_polygon(const int32_t* seg_type, const float* seg_x, const float* seg_y, int n,
+                     const double m[6], std::vector<FlatVertex>& out);
+
+}  // namespace ofdg

@@ -1,0 +1,672 @@
+// sm_100a kernels of the generator's render path. Build with --fmad=false: every float/double
+// expression below is meant to round exactly like the reference's x86-64 (SSE, no FMA) build.
+//
+// What each kernel replaces in /root/reference/src/caffe/DataGenerator.cpp ("DG.cpp"):
+//   bg_tables_kernel / bg_prep_kernel  Texture::getRandomizedCrop(2W,2H,..) for the background
+//                                      (DG.cpp:87-109, 1186-1192; CImg shift/rotate/crop/resize)
+//   render_kernel                      per 128x8-pixel tile, everything else of Process_TaskBucket:
+//       raster   MovingObjectBase::draw<> = AGG scanline cell/cover accumulation  (DG.cpp:351-368)
+//       combine  MovingObjectComposite::renderMasks                                  (DG.cpp:591-646)
+//       warp     getTransformedTexture = AGG span bilinear filter, reflect wrap      (DG.cpp:168-231)
+//       blit     RenderCore::blitObject = object ids + CImg draw_image blend         (DG.cpp:762-799)
+//       flow     RenderCore::computeFlowImage / getPointFlow                          (DG.cpp:801-818, 388-407, 692-718)
+//       write    uint8 -> float conversion into the output blobs                      (DG.cpp:1229-1245)
+#include "render.cuh"
+
+namespace ofdg {
+
+namespace {
+
+constexpr int TW = 128;   // tile width  = 32 lanes x 4 pixels (one 128-bit store per lane and plane)
+constexpr int TH = 8;     // tile height = 8 warps
+constexpr int RENDER_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------
+// small integer helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int floordiv(int a, int b) {  // b > 0
+  int q = a / b, r = a % b;
+  return r < 0 ? q - 1 : q;
+}
+__device__ __forceinline__ long long floordiv64(long long a, long long b) {  // b > 0
+  long long q = a / b, r = a % b;
+  return r < 0 ? q - 1 : q;
+}
+__device__ __forceinline__ int iround_d(double v) { return int((v < 0.0) ? v - 0.5 : v + 0.5); }
+
+// agg::wrap_mode_reflect
+__device__ __forceinline__ int reflect(int v, int size) {
+  if ((unsigned)v < (unsigned)size) return v;
+  unsigned size2 = 2u * (unsigned)size;
+  unsigned add = size2 * (0x3FFFFFFFu / size2);
+  unsigned m = ((unsigned)v + add) % size2;
+  return (int)(m >= (unsigned)size ? size2 - m - 1 : m);
+}
+// CImg mirror boundary: cimg::mod(i, 2n), then fold
+__device__ __forceinline__ int mirror(int i, int n) {
+  if ((unsigned)i < (unsigned)n) return i;
+  int n2 = 2 * n;
+  int m = i % n2;
+  if (m < 0) m += n2;
+  return m < n ? m : n2 - m - 1;
+}
+
+// dda2_line_interpolator in closed form: value after i increments
+struct Dda2 {
+  int v1, lft, rem, n;
+  __device__ __forceinline__ void init(int a, int b, int count) {
+    n = count;
+    int d = b - a;
+    lft = d / n;
+    rem = d % n;
+    if (rem <= 0) { rem += n; lft--; }
+    v1 = a;
+  }
+  __device__ __forceinline__ int at(int i) const { return v1 + i * lft + ((i + 1) * rem + n - 1) / n - 1; }
+};
+
+// One row of agg::span_interpolator_linear + span_image_filter_rgb_bilinear over an RGBX image
+// addressed as img[(oy + r(y)) * pitch + ox + r(x)], r = reflect over (sw, sh).
+struct RowWarp {
+  Dda2 dx, dy;
+  __device__ __forceinline__ void init(const double* m, double y, int n) {
+    // begin(0.5, y + 0.5, n): endpoints through the inverse matrix, iround(256 * .)
+    double tx = 0.5, ty = y + 0.5;
+    double ax = tx * m[0] + ty * m[2] + m[4];
+    double ay = tx * m[1] + ty * m[3] + m[5];
+    int X1 = iround_d(ax * 256.0), Y1 = iround_d(ay * 256.0);
+    tx = 0.5 + n;
+    double bx = tx * m[0] + ty * m[2] + m[4];
+    double by = tx * m[1] + ty * m[3] + m[5];
+    int X2 = iround_d(bx * 256.0), Y2 = iround_d(by * 256.0);
+    dx.init(X1, X2, n);
+    dy.init(Y1, Y2, n);
+  }
+};
+
+__device__ __forceinline__ uint32_t ld_px(const uchar4* p) { return *reinterpret_cast<const uint32_t*>(p); }
+
+__device__ __forceinline__ uint32_t bilinear_rgbx(const uchar4* img, int pitch, int ox, int oy, int sw, int sh,
+                                                  const RowWarp& rw, int i) {
+  int x_hr = rw.dx.at(i) - 128, y_hr = rw.dy.at(i) - 128;
+  int x_lr = x_hr >> 8, y_lr = y_hr >> 8;
+  unsigned fx = x_hr & 255, fy = y_hr & 255;
+  int xa = reflect(x_lr, sw), xb = reflect(x_lr + 1, sw), ya = reflect(y_lr, sh), yb = reflect(y_lr + 1, sh);
+  const uchar4* r0 = img + (size_t)(oy + ya) * pitch + ox;
+  const uchar4* r1 = img + (size_t)(oy + yb) * pitch + ox;
+  uint32_t p00 = ld_px(r0 + xa), p10 = ld_px(r0 + xb), p01 = ld_px(r1 + xa), p11 = ld_px(r1 + xb);
+  unsigned w00 = (256 - fx) * (256 - fy), w10 = fx * (256 - fy), w01 = (256 - fx) * fy, w11 = fx * fy;
+  uint32_t out = 0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    unsigned s = 32768u + w00 * ((p00 >> (8 * c)) & 255u) + w10 * ((p10 >> (8 * c)) & 255u) +
+                 w01 * ((p01 >> (8 * c)) & 255u) + w11 * ((p11 >> (8 * c)) & 255u);
+    out |= (s >> 16) << (8 * c);
+  }
+  return out;
+}
+
+// CImg draw_image(sprite, mask, 1, 255) per channel == floor((m*t + f*(255-m)) / 255)  
+__device__ __forceinline__ uint32_t blend_rgbx(uint32_t f, uint32_t t, unsigned m) {
+  uint32_t out = 0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    unsigned fv = (f >> (8 * c)) & 255u, tv = (t >> (8 * c)) & 255u;
+    out |= ((m * tv + fv * (255u - m)) / 255u) << (8 * c);
+  }
+  return out;
+}
+
+// MovingObjectComposite::renderMasks, strict float (DG.cpp:606, 626)
+__device__ __forceinline__ unsigned comp_add(unsigned u, unsigned v) {
+  return (unsigned)(unsigned char)(255.f * (1.f - (1.f - (float)(int)u / 255.f) * (1.f - (float)(int)v / 255.f)));
+}
+__device__ __forceinline__ unsigned comp_sub(unsigned u, unsigned v) {
+  return (unsigned)(unsigned char)(255.f * (((float)(int)u / 255.f) * (1.f - (float)(int)v / 255.f)));
+}
+
+// pixfmt_gray8 blend of colour 255 over a cleared buffer
+__device__ __forceinline__ unsigned graylut(unsigned c) {
+  return c == 255u ? 255u : (255u * ((255u * (c + 1u)) >> 8)) >> 8;
+}
+
+// ------------------------------------------------------------------------------------------------
+// AGG cell accumulation for one edge restricted to one tile (closed forms of H1)
+// ------------------------------------------------------------------------------------------------
+// render_hline(ey, x1, y1, x2, y2) with the cells scattered into the tile's cover/area arrays;
+// cells left of the tile only add to the row's carry-in cover, cells right of it are dropped.
+__device__ __forceinline__ void tile_hline(int* cover, int* area, int* carry, int tx0, int x1, int y1, int x2, int y2) {
+  if (y1 == y2) return;
+  int ex1 = x1 >> 8, ex2 = x2 >> 8, fx1 = x1 & 255, fx2 = x2 & 255;
+  const int dyv = y2 - y1;
+  if (ex1 == ex2) {
+    int c = ex1 - tx0;
+    if (c < 0) atomicAdd(carry, dyv);
+    else if (c < TW) { atomicAdd(cover + c, dyv); atomicAdd(area + c, (fx1 + fx2) * dyv); }
+    return;
+  }
+  int dx = x2 - x1, p0, incr, first;
+  if (dx > 0) { p0 = (256 - fx1) * dyv; incr = 1; first = 256; }
+  else { p0 = fx1 * dyv; incr = -1; first = 0; dx = -dx; }
+  const int ncell = (ex2 - ex1) * incr;  // >= 1: cells j = 0..ncell along the walk
+  // cumulative y after leaving cell j: C(j) = floor((p0 + 256*j*dy) / dx), j < ncell; C(ncell) = dy
+  auto C = [&](int j) { return j >= ncell ? dyv : floordiv(p0 + 256 * j * dyv, dx); };
+  // walk cells; j-th cell is ex1 + incr*j
+  int jlo, jhi;  // range of j whose cell lies inside the tile
+  if (incr > 0) { jlo = max(0, tx0 - ex1); jhi = min(ncell, tx0 + TW - 1 - ex1); }
+  else { jlo = max(0, ex1 - (tx0 + TW - 1)); jhi = min(ncell, ex1 - tx0); }
+  // cover of all cells left of the tile (telescoping sum)
+  if (incr > 0) {
+    if (ex1 < tx0) { int jl = min(ncell + 1, tx0 - ex1); atomicAdd(carry, jl > ncell ? dyv : C(jl - 1)); }
+  } else {
+    if (ex2 < tx0) { int jf = max(0, ex1 - tx0 + 1); atomicAdd(carry, dyv - (jf > 0 ? C(jf - 1) : 0)); }
+  }
+  if (jlo > jhi) return;
+  int prev = jlo > 0 ? C(jlo - 1) : 0;
+  for (int j = jlo; j <= jhi; ++j) {
+    int cur = C(j);
+    int d = cur - prev;
+    prev = cur;
+    int a;
+    if (j == 0) a = (fx1 + first) * d;
+    else if (j == ncell) a = (fx2 + 256 - first) * d;
+    else a = 256 * d;
+    int c = ex1 + incr * j - tx0;
+    if (d | a) { atomicAdd(cover + c, d); atomicAdd(area + c, a); }
+  }
+}
+
+// rasterizer_cells_aa::line(x1,y1,x2,y2) restricted to tile rows [ty0, ty0+TH) and columns [tx0, tx0+TW)
+__device__ __forceinline__ void tile_edge(int* cover, int* area, int* carry, int tx0, int ty0, int xa, int ya, int xb, int yb) {
+  if (ya == yb) return;
+  const int ey1 = ya >> 8, ey2 = yb >> 8;
+  const int rlo = max(min(ey1, ey2), ty0), rhi = min(max(ey1, ey2), ty0 + TH - 1);
+  if (rlo > rhi) return;
+  if ((min(xa, xb) >> 8) >= tx0 + TW) return;
+  const int fy1 = ya & 255, fy2 = yb & 255;
+  const long long dx = (long long)xb - xa;
+  if (ey1 == ey2) {
+    const int r = ey1 - ty0;
+    tile_hline(cover + r * TW, area + r * TW, carry + r, tx0, xa, fy1, xb, fy2);
+    return;
+  }
+  if (yb > ya) {
+    const long long dy = (long long)yb - ya;
+    // x at the bottom boundary of row ey1 + j
+    auto X = [&](int j) { return xa + (int)floordiv64(((256 - fy1) + 256LL * j) * dx, dy); };
+    for (int r = rlo; r <= rhi; ++r) {
+      const int j = r - ey1;
+      const int xs = j == 0 ? xa : X(j - 1), ys = j == 0 ? fy1 : 0;
+      const int xe = r == ey2 ? xb : X(j), ye = r == ey2 ? fy2 : 256;
+      tile_hline(cover + (r - ty0) * TW, area + (r - ty0) * TW, carry + (r - ty0), tx0, xs, ys, xe, ye);
+    }
+  } else {
+    const long long dy = (long long)ya - yb;
+    // x at the top boundary of row ey1 - j
+    auto X = [&](int j) { return xa + (int)floordiv64((fy1 + 256LL * j) * dx, dy); };
+    for (int r = rhi; r >= rlo; --r) {
+      const int j = ey1 - r;
+      const int xs = j == 0 ? xa : X(j - 1), ys = j == 0 ? fy1 : 256;
+      const int xe = r == ey2 ? xb : X(j), ye = r == ey2 ? fy2 : 0;
+      tile_hline(cover + (r - ty0) * TW, area + (r - ty0) * TW, carry + (r - ty0), tx0, xs, ys, xe, ye);
+    }
+  }
+}
+
+__device__ __forceinline__ bool box_hits_tile(const int32_t* b, int tx0, int ty0) {
+  // cells right of the tile never matter; cells left of it feed the carry-in
+  return b[1] <= ty0 + TH - 1 && b[3] >= ty0 && b[0] <= tx0 + TW - 1 && b[2] >= tx0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// render kernel: one CTA per (tile, sample); warp = tile row, lane = 4 consecutive pixels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RENDER_THREADS) render_kernel(RenderArgs a) {
+  __shared__ int s_cover[2][TH][TW];
+  __shared__ int s_area[2][TH][TW];
+  __shared__ int s_carry[2][TH];
+
+  const int W = a.W, H = a.H;
+  const int tiles_x = (W + TW - 1) / TW;
+  const int tx0 = (blockIdx.x % tiles_x) * TW, ty0 = (blockIdx.x / tiles_x) * TH;
+  const int sample = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int y = ty0 + warp, x0 = tx0 + lane * 4;
+  const bool live = (y < H) && (x0 < W);
+  const FlatSample& smp = a.samples[sample];
+  const size_t P = (size_t)W * H;
+
+  uint32_t col0[4], col1[4];
+  unsigned id0[4] = {0, 0, 0, 0}, id1[4] = {0, 0, 0, 0};  // 0 = background, k+1 = k-th foreground object
+
+  // ---- background: masks are all 255 (DG.cpp:684-690); frame 0 = centre window of the prepared
+  //      texture, frame 1 = that texture warped by I^-1*M*I on the 2W x 2H canvas (DG.cpp:665-682)
+  {
+    const uchar4* bg = a.bg + (size_t)sample * (4 * P);
+    const int W2 = 2 * W, H2 = 2 * H;
+    if (live) {
+      const uchar4* row = bg + (size_t)(y + H / 2) * W2 + (x0 + W / 2);
+      RowWarp rw;
+      rw.init(smp.bg_tex_inv, (double)(y + H / 2), W2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        col0[i] = ld_px(row + i) & 0xFFFFFFu;
+        col1[i] = bilinear_rgbx(bg, W2, 0, 0, W2, H2, rw, x0 + i + W / 2);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) col0[i] = col1[i] = 0;
+    }
+  }
+
+  // ---- foreground objects in z-order
+  const int tex_ox = a.tex_w / 2 - W / 2, tex_oy = a.tex_h / 2 - H / 2;  // centre crop, DG.cpp:99-102 with defaults
+  for (int k = 0; k < smp.obj_count; ++k) {
+    const FlatObject& obj = a.objects[smp.obj_begin + k];
+    const bool hit0 = box_hits_tile(obj.bbox[0], tx0, ty0), hit1 = box_hits_tile(obj.bbox[1], tx0, ty0);
+    if (!hit0 && !hit1) continue;
+
+    // u[frame][aa?]: 4 pixels packed one byte each
+    unsigned aa[2][4], na[2][4];
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) aa[f][i] = na[f][i] = 0;
+
+    for (int si = 0; si < obj.shape_count; ++si) {
+      const FlatShape& sh = a.shapes[obj.shape_begin + si];
+      const bool sh0 = box_hits_tile(sh.bbox[0], tx0, ty0), sh1 = box_hits_tile(sh.bbox[1], tx0, ty0);
+      unsigned vaa[2][4], vna[2][4];
+#pragma unroll
+      for (int f = 0; f < 2; ++f)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) vaa[f][i] = vna[f][i] = 0;
+      if (sh0 || sh1) {
+        __syncthreads();  // previous readers are done with the accumulators
+        for (int i = tid; i < 2 * TH * TW; i += RENDER_THREADS) { (&s_cover[0][0][0])[i] = 0; (&s_area[0][0][0])[i] = 0; }
+        if (tid < 2 * TH) (&s_carry[0][0])[tid] = 0;
+        __syncthreads();
+        const int n0 = sh0 ? sh.vcount[0] : 0, n1 = sh1 ? sh.vcount[1] : 0;
+        for (int e = tid; e < n0 + n1; e += RENDER_THREADS) {
+          const int f = e >= n0 ? 1 : 0;
+          const int ei = f ? e - n0 : e;
+          const int n = sh.vcount[f];
+          const FlatVertex* v = a.verts + sh.vbegin[f];
+          const FlatVertex p = v[ei], q = v[ei + 1 == n ? 0 : ei + 1];
+          tile_edge(&s_cover[f][0][0], &s_area[f][0][0], &s_carry[f][0], tx0, ty0, p.x, p.y, q.x, q.y);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          if (!(f ? sh1 : sh0)) continue;
+          const int4 c4 = *reinterpret_cast<const int4*>(&s_cover[f][warp][lane * 4]);
+          const int4 a4 = *reinterpret_cast<const int4*>(&s_area[f][warp][lane * 4]);
+          int c[4] = {c4.x, c4.y, c4.z, c4.w}, ar[4] = {a4.x, a4.y, a4.z, a4.w};
+          c[1] += c[0]; c[2] += c[1]; c[3] += c[2];
+          int tot = c[3];  // warp-level inclusive prefix sum over the lanes' cover totals
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            int o = __shfl_up_sync(0xffffffffu, tot, d);
+            if (lane >= d) tot += o;
+          }
+          const int base = tot - c[3] + s_carry[f][warp];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            // sweep_scanline + calculate_alpha: arithmetic shift before abs, non-zero rule, clamp
+            int cv = (((base + c[i]) << 9) - ar[i]) >> 9;
+            if (cv < 0) cv = -cv;
+            if (cv > 255) cv = 255;
+            vaa[f][i] = graylut((unsigned)cv);            // gamma_none
+            vna[f][i] = cv >= 128 ? 255u : 0u;            // gamma_threshold(0.5), then graylut(255) = 255
+          }
+        }
+      }
+      if (obj.composite) {
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (sh.additive) { aa[f][i] = comp_add(aa[f][i], vaa[f][i]); na[f][i] = comp_add(na[f][i], vna[f][i]); }
+            else { aa[f][i] = comp_sub(aa[f][i], vaa[f][i]); na[f][i] = comp_sub(na[f][i], vna[f][i]); }
+          }
+      } else {
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { aa[f][i] = vaa[f][i]; na[f][i] = vna[f][i]; }
+      }
+    }
+
+    if (!live) continue;
+    if (a.dbg_masks && k < a.dbg_max_objs) {
+      uint8_t* mb = a.dbg_masks + ((size_t)sample * a.dbg_max_objs + k) * 4 * P + (size_t)y * W + x0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        mb[0 * P + i] = (uint8_t)aa[0][i]; mb[1 * P + i] = (uint8_t)aa[1][i];
+        mb[2 * P + i] = (uint8_t)na[0][i]; mb[3 * P + i] = (uint8_t)na[1][i];
+      }
+    }
+    // blit: ids from the non-AA masks, colour through the AA (or non-AA) masks
+    const uchar4* tex = a.pool + (size_t)obj.tex * a.tex_w * a.tex_h;
+    unsigned any1 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (na[0][i] == 255u) id0[i] = k + 1;
+      if (na[1][i] == 255u) id1[i] = k + 1;
+      const unsigned m0 = a.use_aa ? aa[0][i] : na[0][i];
+      if (m0) {
+        uint32_t t = ld_px(tex + (size_t)(y + tex_oy) * a.tex_w + (x0 + i + tex_ox)) & 0xFFFFFFu;  // identity warp == copy
+        col0[i] = blend_rgbx(col0[i], t, m0);
+      }
+      any1 |= a.use_aa ? aa[1][i] : na[1][i];
+    }
+    if (any1) {
+      RowWarp rw;
+      rw.init(obj.tex_inv, (double)y, W);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const unsigned m1 = a.use_aa ? aa[1][i] : na[1][i];
+        if (m1) col1[i] = blend_rgbx(col1[i], bilinear_rgbx(tex, a.tex_w, tex_ox, tex_oy, W, H, rw, x0 + i), m1);
+      }
+    }
+  }
+
+  if (!live) return;
+
+  // ---- flow of the top-most frame-0 object, f64 -> f32 (DG.cpp:388-401, 692-712)
+  float fxv[4], fyv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float xf = (float)(x0 + i), yf = (float)y;
+    if (id0[i] == 0) {
+      double ix = xf + (float)(W / 2), iy = yf + (float)(H / 2);
+      const float save_x = (float)ix, save_y = (float)iy;
+      ix = ix - (double)W; iy = iy - (double)H;  // I^-1 = T(-W,-H)
+      const double* m = smp.bg_motion;
+      double tmp = ix;
+      ix = tmp * m[0] + iy * m[2] + m[4];
+      iy = tmp * m[1] + iy * m[3] + m[5];
+      ix = ix + (double)W; iy = iy + (double)H;  // I = T(W,H)
+      fxv[i] = (float)(ix - save_x);
+      fyv[i] = (float)(iy - save_y);
+    } else {
+      const double* m = a.objects[smp.obj_begin + id0[i] - 1].motion;
+      double ix = xf, iy = yf;
+      double tmp = ix;
+      ix = tmp * m[0] + iy * m[2] + m[4];
+      iy = tmp * m[1] + iy * m[3] + m[5];
+      fxv[i] = (float)(ix - xf);
+      fyv[i] = (float)(iy - yf);
+    }
+  }
+
+  // ---- write the three blobs (NCHW float): 8 planes x one 128-bit store per lane
+  const size_t pix = (size_t)y * W + x0;
+  float* o0 = a.img0 + (size_t)sample * 3 * P + pix;
+  float* o1 = a.img1 + (size_t)sample * 3 * P + pix;
+  float* of = a.flow + (size_t)sample * 2 * P + pix;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float4 v0 = make_float4((float)((col0[0] >> (8 * c)) & 255u), (float)((col0[1] >> (8 * c)) & 255u),
+                            (float)((col0[2] >> (8 * c)) & 255u), (float)((col0[3] >> (8 * c)) & 255u));
+    float4 v1 = make_float4((float)((col1[0] >> (8 * c)) & 255u), (float)((col1[1] >> (8 * c)) & 255u),
+                            (float)((col1[2] >> (8 * c)) & 255u), (float)((col1[3] >> (8 * c)) & 255u));
+    __stcs(reinterpret_cast<float4*>(o0 + c * P), v0);
+    __stcs(reinterpret_cast<float4*>(o1 + c * P), v1);
+  }
+  __stcs(reinterpret_cast<float4*>(of), make_float4(fxv[0], fxv[1], fxv[2], fxv[3]));
+  __stcs(reinterpret_cast<float4*>(of + P), make_float4(fyv[0], fyv[1], fyv[2], fyv[3]));
+
+  if (a.dbg_id0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const unsigned o0id = id0[i] ? (unsigned)a.objects[smp.obj_begin + id0[i] - 1].obj_id : 1u;
+      const unsigned o1id = id1[i] ? (unsigned)a.objects[smp.obj_begin + id1[i] - 1].obj_id : 1u;
+      a.dbg_id0[(size_t)sample * P + pix + i] = o0id;
+      if (a.dbg_id1) a.dbg_id1[(size_t)sample * P + pix + i] = o1id;
+    }
+  }
+  if (a.dbg_frames8) {
+    uint8_t* fb = a.dbg_frames8 + (size_t)sample * 6 * P + pix;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        fb[c * P + i] = (uint8_t)((col0[i] >> (8 * c)) & 255u);
+        fb[(3 + c) * P + i] = (uint8_t)((col1[i] >> (8 * c)) & 255u);
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// background texture preparation (CImg chain)
+// ------------------------------------------------------------------------------------------------
+// Linear-resize tables of CImg::get_resize (interpolation 3, growing axis): the source position is
+// accumulated by repeated double additions, so it is produced sequentially, one thread per axis.
+__global__ void bg_tables_kernel(RenderArgs a) {
+  const int sample = blockIdx.x;
+  const BgPrep& p = a.samples[sample].prep;
+  const int axis = threadIdx.x;  // 0 = x, 1 = y
+  if (axis > 1) return;
+  const int n = axis == 0 ? 2 * a.W : 2 * a.H;
+  const int len = axis == 0 ? p.crop_w : p.crop_h;
+  if (!(len < n) || len <= 1) return;  // only the growing, linear case reads the tables
+  int* pos = (axis == 0 ? a.pos_x : a.pos_y) + (size_t)sample * n;
+  double* alpha = (axis == 0 ? a.alpha_x : a.alpha_y) + (size_t)sample * n;
+  const double f = n > 1 ? (len - 1.0) / (n - 1) : 0;
+  double curr = 0, old = 0;
+  unsigned q = 0;
+  for (int i = 0; i < n; ++i) {
+    alpha[i] = curr - (unsigned int)curr;
+    pos[i] = (int)q;
+    old = curr;
+    curr = fmin(len - 1.0, curr + f);
+    q += (unsigned int)curr - (unsigned int)old;
+  }
+}
+
+constexpr int PT = 32;        // prepared-texture tile edge
+constexpr int PS = 46;        // source tile edge: ceil(32 * 1.25) + slack  (zoom >= 0.8 => crop <= 1.25 * 2W)
+constexpr int PREP_THREADS = 256;
+
+__device__ __forceinline__ float cimg_mod_f(float x, float m) {
+  const double dx = (double)x, dm = (double)m;
+  return (float)(dx - dm * floor(dx / dm));
+}
+
+// pixel (x, y) of get_shift(sx, sy, 0, 0, mirror) of the pool texture
+__device__ __forceinline__ uint32_t shifted_px(const uchar4* tex, int w, int h, int sx, int sy, int x, int y) {
+  return ld_px(tex + (size_t)mirror(y - sy, h) * w + mirror(x - sx, w)) & 0xFFFFFFu;
+}
+
+// pixel (x, y) of rotate(angle, linear, mirror) of the shifted texture
+__device__ __forceinline__ uint32_t rotated_px(const uchar4* tex, int w, int h, const BgPrep& p, int x, int y) {
+  if (p.rot_identity) return shifted_px(tex, w, h, p.shift_x, p.shift_y, x, y);
+  const float ww = 2.0f * w, hh = 2.0f * h;
+  const float xc = x - p.rw2, yc = y - p.rh2;
+  const float mx = cimg_mod_f(p.w2 + xc * p.ca + yc * p.sa, ww), my = cimg_mod_f(p.h2 - xc * p.sa + yc * p.ca, hh);
+  const float fx = mx < w ? mx : ww - mx - 1, fy = my < h ? my : hh - my - 1;
+  // _linear_atXY (Neumann)
+  const float nfx = fx <= 0 ? 0 : (fx >= w - 1 ? (float)(w - 1) : fx), nfy = fy <= 0 ? 0 : (fy >= h - 1 ? (float)(h - 1) : fy);
+  const unsigned int ix = (unsigned int)nfx, iy = (unsigned int)nfy;
+  const float dx = nfx - ix, dy = nfy - iy;
+  const unsigned int nx = dx > 0 ? ix + 1 : ix, ny = dy > 0 ? iy + 1 : iy;
+  const uint32_t pcc = shifted_px(tex, w, h, p.shift_x, p.shift_y, ix, iy), pnc = shifted_px(tex, w, h, p.shift_x, p.shift_y, nx, iy),
+                 pcn = shifted_px(tex, w, h, p.shift_x, p.shift_y, ix, ny), pnn = shifted_px(tex, w, h, p.shift_x, p.shift_y, nx, ny);
+  uint32_t out = 0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float Icc = (float)((pcc >> (8 * c)) & 255u), Inc = (float)((pnc >> (8 * c)) & 255u),
+                Icn = (float)((pcn >> (8 * c)) & 255u), Inn = (float)((pnn >> (8 * c)) & 255u);
+    const float v = Icc + dx * (Inc - Icc + dy * (Icc + Inn - Icn - Inc)) + dy * (Icn - Icc);
+    out |= ((uint32_t)(unsigned char)v) << (8 * c);
+  }
+  return out;
+}
+
+// One resize pass (CImg get_resize interpolation 3; shrinking axes use the moving average)
+// evaluated at output index t from a line of source pixels src[(s - s0) * stride].
+__device__ __forceinline__ uint32_t resize_at(const uint32_t* src, int stride, int s0, int len, int n, int t,
+                                              const int* pos, const double* alpha) {
+  if (len == n) return src[(t - s0) * stride];
+  uint32_t out = 0;
+  if (len > n) {  // moving average over the exact rational overlap
+    const long long lo = (long long)t * len, hi = lo + len;
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (int s = (int)(lo / n); (long long)s * n < hi; ++s) {
+      const long long b = max((long long)s * n, lo), e = min((long long)(s + 1) * n, hi);
+      const float d = (float)(unsigned int)(e - b);
+      const uint32_t p = src[(s - s0) * stride];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] += (float)((p >> (8 * c)) & 255u) * d;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out |= ((uint32_t)(unsigned char)(acc[c] / (float)(unsigned int)len)) << (8 * c);
+    return out;
+  }
+  const int q = pos[t];
+  const double al = alpha[t];
+  const uint32_t p1 = src[(q - s0) * stride], p2 = q < len - 1 ? src[(q + 1 - s0) * stride] : p1;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double v = (1 - al) * (double)(int)((p1 >> (8 * c)) & 255u) + al * (double)(int)((p2 >> (8 * c)) & 255u);
+    out |= ((uint32_t)(unsigned char)v) << (8 * c);
+  }
+  return out;
+}
+
+__device__ __forceinline__ void source_range(int len, int n, int t0, int t1, const int* pos, int& s0, int& s1) {
+  if (len == n) { s0 = t0; s1 = t1; }
+  else if (len > n) { s0 = (int)(((long long)t0 * len) / n); s1 = (int)((((long long)(t1 + 1) * len) - 1) / n); }
+  else { s0 = pos[t0]; s1 = min(pos[t1] + 1, len - 1); }
+}
+
+__global__ void __launch_bounds__(PREP_THREADS) bg_prep_kernel(RenderArgs a) {
+  __shared__ uint32_t sA[PS][PS];  // rotated + cropped source pixels
+  __shared__ uint32_t sB[PS][PT];  // after the x pass
+  const int sample = blockIdx.z;
+  const BgPrep& p = a.samples[sample].prep;
+  const int W2 = 2 * a.W, H2 = 2 * a.H;
+  const int X0 = p.need[0] + blockIdx.x * PT, Y0 = p.need[1] + blockIdx.y * PT;
+  if (X0 > p.need[2] || Y0 > p.need[3]) return;
+  const int X1 = min(X0 + PT - 1, p.need[2]), Y1 = min(Y0 + PT - 1, p.need[3]);
+  const int* pos_x = a.pos_x + (size_t)sample * W2;
+  const double* alpha_x = a.alpha_x + (size_t)sample * W2;
+  const int* pos_y = a.pos_y + (size_t)sample * H2;
+  const double* alpha_y = a.alpha_y + (size_t)sample * H2;
+  int cx0, cx1, cy0, cy1;
+  source_range(p.crop_w, W2, X0, X1, pos_x, cx0, cx1);
+  source_range(p.crop_h, H2, Y0, Y1, pos_y, cy0, cy1);
+  const int cw = cx1 - cx0 + 1, ch = cy1 - cy0 + 1;  // <= PS by construction
+  const uchar4* tex = a.pool + (size_t)p.tex * a.tex_w * a.tex_h;
+  // A: crop(x0, y0, .., mirror) of the rotated image
+  for (int i = threadIdx.x; i < cw * ch; i += PREP_THREADS) {
+    const int lx = i % cw, ly = i / cw;
+    sA[ly][lx] = rotated_px(tex, a.tex_w, a.tex_h, p, mirror(p.crop_x0 + cx0 + lx, p.rw), mirror(p.crop_y0 + cy0 + ly, p.rh));
+  }
+  __syncthreads();
+  // B: resize along x
+  const int tw = X1 - X0 + 1, th = Y1 - Y0 + 1;
+  for (int i = threadIdx.x; i < tw * ch; i += PREP_THREADS) {
+    const int lx = i % tw, ly = i / tw;
+    sB[ly][lx] = resize_at(&sA[ly][0], 1, cx0, p.crop_w, W2, X0 + lx, pos_x, alpha_x);
+  }
+  __syncthreads();
+  // P: resize along y
+  uchar4* out = a.bg + (size_t)sample * W2 * H2;
+  for (int i = threadIdx.x; i < tw * th; i += PREP_THREADS) {
+    const int lx = i % tw, ly = i / tw;
+    const uint32_t v = resize_at(&sB[0][lx], PT, cy0, p.crop_h, H2, Y0 + ly, pos_y, alpha_y);
+    *reinterpret_cast<uint32_t*>(out + (size_t)(Y0 + ly) * W2 + X0 + lx) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// texture pool helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void planar_to_rgbx_kernel(const uint8_t* planar, uchar4* out, size_t n_px, size_t plane) {
+  // planar: [tex][3][plane]; out: [tex][plane]
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_px; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t t = i / plane, r = i % plane;
+    const uint8_t* src = planar + t * 3 * plane + r;
+    out[i] = make_uchar4(src[0], src[plane], src[2 * plane], 0);
+  }
+}
+__global__ void rgbx_to_planar_kernel(const uchar4* in, uint8_t* planar, size_t plane) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
+    const uchar4 v = in[i];
+    planar[i] = v.x; planar[plane + i] = v.y; planar[2 * plane + i] = v.z;
+  }
+}
+
+__device__ __forceinline__ uint32_t synth_hash8(uint64_t key, uint32_t gx, uint32_t gy, uint32_t o) {
+  uint64_t z = key + (uint64_t)gx * 0xBF58476D1CE4E5B9ull + (uint64_t)gy * 0x94D049BB133111EBull + (uint64_t)o * 0xD6E8FEB86659FD93ull;
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z & 255u);
+}
+// Integer-only procedural texture: 4 octaves of value noise + a triangle-wave stripe + a checker.
+// Mirrors ofdg_b200.synth_textures() (numpy) bit for bit.
+__global__ void synth_textures_kernel(uchar4* out, int n, int w, int h, uint64_t seed, int first_index) {
+  const size_t plane = (size_t)w * h, total = plane * n;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t t = (uint32_t)(i / plane) + (uint32_t)first_index;
+    const uint32_t r = (uint32_t)(i % plane), x = r % w, y = r / w;
+    uint32_t px[3];
+    const uint64_t tkey = seed ^ ((uint64_t)(t + 1) * 0x9E3779B97F4A7C15ull);
+    const uint32_t sax = synth_hash8(tkey, 1, 2, 77) % 17, say = synth_hash8(tkey, 3, 4, 77) % 17;  // stripe direction
+    const uint32_t phase = (x * sax + y * say) & 255u;
+    const uint32_t tri = (phase < 128u ? phase : 255u - phase) * 2u;  // 0..254
+    const uint32_t checker = ((x >> 5) ^ (y >> 5)) & 1u;
+    for (uint32_t c = 0; c < 3; ++c) {
+      const uint64_t key = tkey + (uint64_t)(c + 1) * 0xA24BAED4963EE407ull;
+      uint32_t acc = 0;
+      for (uint32_t o = 0; o < 4; ++o) {
+        const uint32_t cell = 64u >> o;
+        const uint32_t gx = x / cell, gy = y / cell, fx = (x % cell) * 256u / cell, fy = (y % cell) * 256u / cell;
+        const uint32_t v00 = synth_hash8(key, gx, gy, o), v10 = synth_hash8(key, gx + 1, gy, o),
+                       v01 = synth_hash8(key, gx, gy + 1, o), v11 = synth_hash8(key, gx + 1, gy + 1, o);
+        const uint32_t top = v00 * (256u - fx) + v10 * fx, bot = v01 * (256u - fx) + v11 * fx;
+        const uint32_t val = (top * (256u - fy) + bot * fy) >> 16;
+        acc += val << (3u - o);
+      }
+      uint32_t v = (acc / 15u) * 3u / 4u + tri / 4u + (checker ? 24u : 0u) + c * 5u;
+      px[c] = v > 255u ? 255u : v;
+    }
+    out[i] = make_uchar4((unsigned char)px[0], (unsigned char)px[1], (unsigned char)px[2], 0);
+  }
+}
+
+}  // namespace
+
+int launch_background_prep(const RenderArgs& a, cudaStream_t s) {
+  bg_tables_kernel<<<a.batch, 32, 0, s>>>(a);
+  dim3 grid((2 * a.W + PT - 1) / PT, (2 * a.H + PT - 1) / PT, a.batch);
+  bg_prep_kernel<<<grid, PREP_THREADS, 0, s>>>(a);
+  return 2;
+}
+
+int launch_render(const RenderArgs& a, cudaStream_t s) {
+  const int tiles_x = (a.W + TW - 1) / TW, tiles_y = (a.H + TH - 1) / TH;
+  dim3 grid(tiles_x * tiles_y, a.batch);
+  render_kernel<<<grid, RENDER_THREADS, 0, s>>>(a);
+  return 1;
+}
+
+void launch_planar_to_rgbx(const uint8_t* planar, uchar4* out, int n, int w, int h, cudaStream_t s) {
+  const size_t plane = (size_t)w * h;
+  planar_to_rgbx_kernel<<<1184, 256, 0, s>>>(planar, out, plane * n, plane);
+}
+void launch_rgbx_to_planar(const uchar4* in, uint8_t* planar, int w, int h, cudaStream_t s) {
+  rgbx_to_planar_kernel<<<592, 256, 0, s>>>(in, planar, (size_t)w * h);
+}
+void launch_synth_textures(uchar4* out, int n, int w, int h, uint64_t seed, int first_index, cudaStream_t s) {
+  synth_textures_kernel<<<2368, 256, 0, s>>>(out, n, w, h, seed, first_index);
+}
+void launch_bg_to_planar(const uchar4* bg, uint8_t* planar, int batch, int w2, int h2, cudaStream_t s) {
+  const size_t plane = (size_t)w2 * h2;
+  for (int b = 0; b < batch; ++b) rgbx_to_planar_kernel<<<592, 256, 0, s>>>(bg + b * plane, planar + b * 3 * plane, plane);
+}
+
+}  // namespace ofdg

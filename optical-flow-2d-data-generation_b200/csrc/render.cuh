@@ -1,0 +1,52 @@
+// Kernel-side parameter block and launch entry points of the sm_100a render path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "flat_scene.h"
+
+namespace ofdg {
+
+// Everything the kernels of one render call need (passed by value).
+struct RenderArgs {
+  const FlatSample* samples;
+  const FlatObject* objects;
+  const FlatShape* shapes;
+  const FlatVertex* verts;
+  int batch;
+  int W, H;          // output size
+  int use_aa;
+  // texture pool: RGBX8 interleaved, [n][tex_h][tex_w]
+  const uchar4* pool;
+  int tex_w, tex_h;
+  // per-sample prepared background texture, RGBX8 [batch][2H][2W], and linear-resize tables
+  uchar4* bg;
+  int* pos_x;        // [batch][2W]
+  double* alpha_x;   // [batch][2W]
+  int* pos_y;        // [batch][2H]
+  double* alpha_y;   // [batch][2H]
+  // mode 9
+  const float* fields;  // [n][2][2][H+1][W+1]
+  int n_fields;
+  // outputs (device): NCHW float blobs
+  float* img0;
+  float* img1;
+  float* flow;
+  // parity instrumentation (device, may be null)
+  uint8_t* dbg_masks;   // [batch][max_objs][4][H][W]
+  int dbg_max_objs;
+  uint32_t* dbg_id0;    // [batch][H][W]
+  uint32_t* dbg_id1;
+  uint8_t* dbg_frames8; // [batch][2][3][H][W]
+};
+
+// Launchers; each returns the number of kernels it launched.
+int launch_background_prep(const RenderArgs& a, cudaStream_t s);
+int launch_render(const RenderArgs& a, cudaStream_t s);
+
+void launch_planar_to_rgbx(const uint8_t* planar, uchar4* out, int n, int w, int h, cudaStream_t s);
+void launch_rgbx_to_planar(const uchar4* in, uint8_t* planar, int w, int h, cudaStream_t s);
+void launch_synth_textures(uchar4* out, int n, int w, int h, uint64_t seed, int first_index, cudaStream_t s);
+void launch_bg_to_planar(const uchar4* bg, uint8_t* planar, int batch, int w2, int h2, cudaStream_t s);
+
+}  // namespace ofdg
