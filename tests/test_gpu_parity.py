@@ -1,0 +1,110 @@
+"""GPU parity: the sm_100a render path (through the C ABI) against the CPU oracle on identical
+task batches and textures. Thresholds (BASELINE.json north_star / SURVEY 8d):
+  coverage masks and object-id images bit-exact; uint8 images within 1 LSB; flow within 1e-3 px."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FLOW_TOL = 1e-3
+IMG_TOL = 1  # LSB
+
+
+def _gen(ofdg, mode, n_tex=8, max_batch=16, **kw):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return ofdg.Generator(device=0, mode=mode, max_batch=max_batch, **kw)
+
+
+def _compare(gpu, cpu, n_objs_max=24):
+    assert np.array_equal(gpu["id0"], cpu["id0"]), "object-id image (frame 0) differs"
+    assert np.array_equal(gpu["id1"], cpu["id1"]), "object-id image (frame 1) differs"
+    assert np.array_equal(gpu["masks"], cpu["masks"]), "coverage masks differ"
+    d = np.abs(gpu["frames8"].astype(np.int32) - cpu["frames8"].astype(np.int32)).max()
+    assert d <= IMG_TOL, f"uint8 frames differ by {d} LSB"
+    assert np.abs(gpu["img0"] - cpu["img0"]).max() <= IMG_TOL
+    assert np.abs(gpu["img1"] - cpu["img1"]).max() <= IMG_TOL
+    assert np.abs(gpu["flow"] - cpu["flow"]).max() <= FLOW_TOL
+    return int(d)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 5, 7])
+def test_mode_parity_batch8(ofdg, oracle, textures8, mode):
+    g = _gen(ofdg, mode)
+    g.upload_textures(textures8)
+    tasks = ofdg.ParamStream(mode).generate(8)
+    gpu = g.render_debug(tasks)
+    cpu = oracle.render(tasks.struct(), textures8, mode=mode, debug=True)
+    d = _compare(gpu, cpu)
+    # the float blobs are the uint8 frames converted, channel-major (NCHW)
+    assert np.array_equal(gpu["img0"], gpu["frames8"][:, 0].astype(np.float32))
+    assert np.array_equal(gpu["img1"], gpu["frames8"][:, 1].astype(np.float32))
+    print(f"mode {mode}: max image diff {d} LSB")
+    g.close()
+
+
+def test_no_antialiasing(ofdg, oracle, textures8):
+    g = _gen(ofdg, 7, use_antialiasing=False)
+    g.upload_textures(textures8)
+    tasks = ofdg.ParamStream(7).generate(4)
+    gpu = g.render_debug(tasks)
+    cpu = oracle.render(tasks.struct(), textures8, mode=7, use_aa=False, debug=True)
+    _compare(gpu, cpu)
+    g.close()
+
+
+def test_background_preparation(ofdg, oracle, textures8):
+    """Texture::getRandomizedCrop(2W, 2H, rot, zoom, shift) for the background, inside the region the renderer reads."""
+    g = _gen(ofdg, 7)
+    g.upload_textures(textures8)
+    tasks = ofdg.ParamStream(7).generate(8)
+    a = tasks.arrays()
+    bg, need = g.debug_background(tasks)
+    zooms = []
+    for t in range(8):
+        b = a["blueprints"][a["task_begin"][t]]
+        ref = oracle.randomized_crop(textures8[b["tex_id"] % 8], 1024, 768, float(b["tex_rot"]), float(b["tex_scale"]),
+                                     int(b["tex_shift_x"]), int(b["tex_shift_y"]))
+        x0, y0, x1, y1 = need[t]
+        assert np.array_equal(bg[t][:, y0:y1 + 1, x0:x1 + 1], ref[:, y0:y1 + 1, x0:x1 + 1]), f"task {t} zoom {b['tex_scale']}"
+        zooms.append(float(b["tex_scale"]))
+    assert min(zooms) < 1 < max(zooms), "both the shrinking (moving average) and growing (linear) resize paths must be hit"
+    g.close()
+
+
+def test_synth_textures_match_numpy(ofdg):
+    g = _gen(ofdg, 1)
+    g.synth_textures(3, 1024, 768, seed=5)
+    ref = ofdg.synth_textures(3, 1024, 768, seed=5)
+    for i in range(3):
+        assert np.array_equal(g.download_texture(i), ref[i])
+    g.close()
+
+
+def test_upload_roundtrip(ofdg, textures8):
+    g = _gen(ofdg, 1)
+    g.upload_textures(textures8)
+    assert np.array_equal(g.download_texture(5), textures8[5])
+    g.close()
+
+
+def test_device_blobs_and_prepared(ofdg, oracle, textures8):
+    """ofdg_render into torch device tensors == ofdg_render_host == ofdg_render_prepared."""
+    import torch
+    g = _gen(ofdg, 5)
+    g.upload_textures(textures8)
+    tasks = ofdg.ParamStream(5).generate(8)
+    i0 = torch.empty((8, 3, 384, 512), device="cuda"); i1 = torch.empty_like(i0)
+    fl = torch.empty((8, 2, 384, 512), device="cuda")
+    g.render(tasks, i0, i1, fl)
+    h0, h1, hf = g.render_host(tasks)
+    assert np.array_equal(i0.cpu().numpy(), h0) and np.array_equal(i1.cpu().numpy(), h1) and np.array_equal(fl.cpu().numpy(), hf)
+    p = g.prepare(tasks)
+    j0 = torch.zeros_like(i0); j1 = torch.zeros_like(i1); jf = torch.zeros_like(fl)
+    g.render_prepared(p, j0, j1, jf)
+    torch.cuda.synchronize()
+    assert torch.equal(i0, j0) and torch.equal(i1, j1) and torch.equal(fl, jf)
+    cpu = oracle.render(tasks.struct(), textures8, mode=5)
+    assert np.abs(h0 - cpu["img0"]).max() <= IMG_TOL and np.abs(hf - cpu["flow"]).max() <= FLOW_TOL
+    assert g.launch_count() > 0
+    g.close()
