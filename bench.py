@@ -1,0 +1,308 @@
+#!/usr/bin/env python3
+"""Throughput benchmark of the generator's hot path (BASELINE.json metric: image-pair + flow
+samples/s at 1/2/4/8 B200, achieved HBM GB/s against the measured peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one batch of `--batch` (default 64) samples per GPU rendered by the hot path
+(background preparation + tile render kernels) from scenes already flattened and resident in HBM;
+`value` is whole-job samples/s over all ranks (weak scaling: per-GPU batch fixed, per-GPU seed
+offset 45*rank). `e2e` is the same metric through the C-ABI call with HOST blobs: host parameter
+draw + geometry flattening + scene upload + kernels + device-to-host copy of the three blobs, all
+inside the timed region. `--impl reference` times the CPU generator (the oracle port of the
+reference, all host threads) on bounded samples of the same workload.
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_512x384 = 7471104  # 6,291,456 B blobs written + 1,179,648 B texels read per sample
+
+
+def algo_bytes(W, H):
+    return 2 * 3 * H * W * 4 + 2 * H * W * 4 + 2 * H * W * 3
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks/throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for l in self.proc.stdout:
+            self.lines.append((time.time(), l.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    sm.append(float(f[1]))
+                    mx = float(f[2])
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_generator_rate(mode, W, H, n_samples, threads, tex, seed_offset=0, faithful=True):
+    """samples/s of the CPU generator (oracle port, reference structure: one worker thread per task)."""
+    import ofdg_b200 as o
+    from oracle import binding as ob
+    tasks = o.ParamStream(mode, W, H, seed_offset).generate(n_samples)
+    t0 = time.time()
+    ob.render(tasks.struct(), tex, W=W, H=H, mode=mode, n_threads=threads, faithful=faithful)
+    dt = time.time() - t0
+    return n_samples / dt, dt
+
+
+def run_reference(args):
+    """The reference arm: the CPU generator on this box's host cores, same workload/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    import ofdg_b200 as o
+    from oracle import binding as ob
+    ob.build()
+    cores = os.cpu_count() or 1
+    W, H, mode = args.width, args.height, args.mode
+    tex = o.synth_textures(16, 2 * W, 2 * H, seed=args.seed)  # a small pool: pool size does not change CPU cost
+    # calibrate, then size the per-step sample so the whole run stays within ~3 minutes
+    rate, _ = cpu_generator_rate(mode, W, H, min(cores, 16), min(cores, 16), tex)
+    per_step = int(max(1, min(2 * cores, rate * 150.0 / (args.steps + args.warmup))))
+    threads = min(cores, per_step)
+    ps = o.ParamStream(mode, W, H, 0)
+    tasks = o.Tasks()
+
+    def step():
+        tasks.clear()
+        ps.generate(per_step, tasks)  # parameter draws are part of the reference's per-batch work too
+        ob.render(tasks.struct(), tex, W=W, H=H, mode=mode, n_threads=threads, faithful=True)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step()
+    dt = time.time() - t0
+    v = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "img-pair+flow samples/sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": f"{per_step} samples per step x {args.steps} steps, mode {mode}, {W}x{H}, oracle/liboracle.so "
+                                   f"with the reference's whole-image copies, {threads} worker threads of {cores} host cores"},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"mode {args.mode} (example prototxt) {args.width}x{args.height}, batch {args.batch} per GPU per step, "
+                        f"{args.textures}-texture procedural pool resident in HBM, host-RNG parameter stream",
+            "global_batch": args.batch * args.gpus, "mode": args.mode, "textures": args.textures,
+            "l2": "inputs+outputs larger than L2 (403 MB of blobs written per step per GPU; distinct scene batches cycled)",
+            "parallelism": f"sample-sharded x{args.gpus}, seed offset 45*rank, no collective"}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import ofdg_b200 as o
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py needs a B200 (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, H, B, mode = args.width, args.height, args.batch, args.mode
+    g = o.Generator(device=local, width=W, height=H, mode=mode, max_batch=B)
+    g.synth_textures(args.textures, 2 * W, 2 * H, seed=args.seed)
+    ps = o.ParamStream(mode, W, H, seed_offset=45 * rank)
+    n_sets = 4
+    prepared = [g.prepare(ps.generate(B)) for _ in range(n_sets)]
+    img0 = torch.empty((B, 3, H, W), device="cuda", dtype=torch.float32)
+    img1 = torch.empty_like(img0)
+    flow = torch.empty((B, 2, H, W), device="cuda", dtype=torch.float32)
+    tstream = torch.cuda.Stream()  # a non-default stream: torch events and our launches share it
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for i in range(args.warmup):
+        g.render_prepared(prepared[i % n_sets], img0, img1, flow, stream)
+    barrier()
+    g.kernel_times()
+    launches0 = g.launch_count()
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start = time.time()
+    e0.record()
+    for i in range(args.steps):
+        g.render_prepared(prepared[i % n_sets], img0, img1, flow, stream)
+    e1.record()
+    barrier()
+    t_end = time.time()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_start, t_end) if sampler else None
+    launches = g.launch_count() - launches0
+    prep_ms, render_ms, calls = g.kernel_times()
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with host blobs (pinned), copies inside the timed region
+    h0 = torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory()
+    h1 = torch.empty_like(h0).pin_memory()
+    hf = torch.empty((B, 2, H, W), dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    tasks = o.Tasks()
+    for _ in range(2):
+        tasks.clear(); ps.generate(B, tasks); g.render_host(tasks, h0, h1, hf)
+    barrier()
+    t0 = time.time()
+    h2d = 0
+    for _ in range(e2e_steps):
+        tasks.clear()
+        ps.generate(B, tasks)
+        g.render_host(tasks, h0, h1, hf)
+        h2d += g.last_upload_bytes()
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    if dist is not None:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = world * B * e2e_steps / dt
+    checksum = float(h0[0, 0, 0, 0]) + float(hf[0, 0, 0, 0])
+    g.kernel_times()
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    ab = algo_bytes(W, H) * B
+    kern_ms = render_ms / max(calls, 1)
+    achieved = ab / (kern_ms * 1e-3) / 1e9
+    line = {
+        "metric": "img-pair+flow samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args),
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d // e2e_steps,
+                "d2h_bytes_per_step": B * (2 * 3 + 2) * H * W * 4, "steps": e2e_steps, "checksum": checksum},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "render_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": args.traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": ab, "kernel_ms": kern_ms,
+                     "bg_prep_ms": prep_ms / max(calls, 1), "step_share": render_ms / max(render_ms + prep_ms, 1e-9)},
+    }
+    # CPU generator next to it (N=1 only): bounded sample on this box's host cores
+    if world == 1 and not args.no_cpu:
+        from oracle import binding as ob
+        ob.build()
+        cores = os.cpu_count() or 1
+        tex = o.synth_textures(16, 2 * W, 2 * H, seed=args.seed)
+        n = int(max(8, min(64, 2 * cores)))
+        rate, dt_cpu = cpu_generator_rate(mode, W, H, n, min(cores, n), tex)
+        line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": min(cores, n), "kind": "port",
+                                "sample": f"{n} samples of the same workload in {dt_cpu:.1f} s (oracle/liboracle.so, reference structure "
+                                          f"with its whole-image copies), {min(cores, n)} worker threads of {cores} host cores"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--mode", type=int, default=7)
+    ap.add_argument("--width", type=int, default=512)
+    ap.add_argument("--height", type=int, default=384)
+    ap.add_argument("--textures", type=int, default=1000)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture (profiles/)")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and args.impl == "ours":
+        if world == 1 and args.gpus > 1:
+            # relaunch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -120,6 +120,10 @@ int ofdg_render_debug(ofdg_generator* g, const ofdg_task_batch* tasks, float* h_
  * renderer needs are 0 and `need` (batch x 4: x0,y0,x1,y1) reports that region. */
 int ofdg_debug_background(ofdg_generator* g, const ofdg_task_batch* tasks, uint8_t* planar_out, int32_t* need);
 
+/* The two 256x256 composite-mask tables [u][v] exactly as the render kernel evaluates
+ * MovingObjectComposite::renderMasks' float rules (DataGenerator.cpp:606, 626). */
+int ofdg_debug_composite_luts(ofdg_generator* g, uint8_t* add_lut, uint8_t* sub_lut);
+
 /* Flatten + upload once, render many times (throughput measurement with inputs resident in HBM). */
 int ofdg_prepare(ofdg_generator* g, const ofdg_task_batch* tasks, ofdg_prepared** out);
 void ofdg_prepared_destroy(ofdg_prepared* p);
@@ -132,8 +136,12 @@ int ofdg_generate(ofdg_generator* g, ofdg_params* p, int32_t batch, float* d_img
 
 /* Number of kernel launches issued by this generator so far (bench.py's gpu_launches). */
 uint64_t ofdg_launch_count(const ofdg_generator* g);
-/* Events-based duration (ms) of the main render kernel of the last render call on this generator. */
-float ofdg_last_render_kernel_ms(const ofdg_generator* g);
+/* Device time, measured with CUDA events on the launching stream, spent in the background
+ * preparation kernels and in the render kernel over the render calls made since the previous
+ * call of this function (synchronises; resets the accumulation). */
+int ofdg_kernel_times(ofdg_generator* g, double* prep_ms, double* render_ms, int32_t* calls);
+/* Bytes of flattened scene data the last render/prepare call copied host-to-device. */
+uint64_t ofdg_last_upload_bytes(const ofdg_generator* g);
 
 #ifdef __cplusplus
 }

@@ -57,8 +57,8 @@ EXPORTS = [
     "ofdg_tasks_create", "ofdg_tasks_destroy", "ofdg_tasks_clear", "ofdg_tasks_view", "ofdg_tasks_assign",
     "ofdg_flatten_ellipse", "ofdg_flatten_polygon", "ofdg_create", "ofdg_destroy", "ofdg_upload_textures",
     "ofdg_synth_textures", "ofdg_download_texture", "ofdg_set_fields", "ofdg_render", "ofdg_render_host",
-    "ofdg_render_debug", "ofdg_debug_background", "ofdg_prepare", "ofdg_prepared_destroy",
-    "ofdg_render_prepared", "ofdg_generate", "ofdg_launch_count", "ofdg_last_render_kernel_ms",
+    "ofdg_render_debug", "ofdg_debug_background", "ofdg_debug_composite_luts", "ofdg_prepare", "ofdg_prepared_destroy",
+    "ofdg_render_prepared", "ofdg_generate", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_upload_bytes",
 ]
 
 
@@ -79,8 +79,9 @@ def lib():
         L.ofdg_params_draws.argtypes = [C.c_void_p, C.c_int32]
         L.ofdg_launch_count.restype = C.c_uint64
         L.ofdg_launch_count.argtypes = [C.c_void_p]
-        L.ofdg_last_render_kernel_ms.restype = C.c_float
-        L.ofdg_last_render_kernel_ms.argtypes = [C.c_void_p]
+        L.ofdg_last_upload_bytes.restype = C.c_uint64
+        L.ofdg_last_upload_bytes.argtypes = [C.c_void_p]
+        L.ofdg_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         L.ofdg_params_create.argtypes = [C.c_int32] * 6 + [C.POINTER(C.c_void_p)]
         L.ofdg_params_destroy.argtypes = [C.c_void_p]
         L.ofdg_params_generate.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
@@ -102,6 +103,7 @@ def lib():
         L.ofdg_render_host.argtypes = [C.c_void_p, C.POINTER(TaskBatchStruct)] + [C.c_void_p] * 3
         L.ofdg_render_debug.argtypes = [C.c_void_p, C.POINTER(TaskBatchStruct)] + [C.c_void_p] * 4 + [C.c_int32] + [C.c_void_p] * 3
         L.ofdg_debug_background.argtypes = [C.c_void_p, C.POINTER(TaskBatchStruct), C.c_void_p, C.c_void_p]
+        L.ofdg_debug_composite_luts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ofdg_prepare.argtypes = [C.c_void_p, C.POINTER(TaskBatchStruct), C.POINTER(C.c_void_p)]
         L.ofdg_prepared_destroy.argtypes = [C.c_void_p]
         L.ofdg_render_prepared.argtypes = [C.c_void_p] * 6
@@ -225,7 +227,7 @@ class ParamStream:
             self._h = None
 
     def generate(self, n, out=None):
-        out = out or Tasks()
+        out = Tasks() if out is None else out
         _check(lib().ofdg_params_generate(self._h, n, out._h))
         return out
 
@@ -345,6 +347,12 @@ class Generator:
         _check(lib().ofdg_debug_background(self._h, C.byref(s), _ptr(out), _ptr(need)))
         return out, need
 
+    def debug_composite_luts(self):
+        a = np.empty((256, 256), np.uint8)
+        s = np.empty((256, 256), np.uint8)
+        _check(lib().ofdg_debug_composite_luts(self._h, _ptr(a), _ptr(s)))
+        return a, s
+
     def prepare(self, tasks):
         s = tasks.struct()
         h = C.c_void_p()
@@ -360,8 +368,14 @@ class Generator:
     def launch_count(self):
         return int(lib().ofdg_launch_count(self._h))
 
-    def last_render_kernel_ms(self):
-        return float(lib().ofdg_last_render_kernel_ms(self._h))
+    def kernel_times(self):
+        """(prep_ms, render_ms, calls) accumulated since the last call; CUDA events on the launching stream."""
+        p, r, n = C.c_double(), C.c_double(), C.c_int32()
+        _check(lib().ofdg_kernel_times(self._h, C.byref(p), C.byref(r), C.byref(n)))
+        return p.value, r.value, n.value
+
+    def last_upload_bytes(self):
+        return int(lib().ofdg_last_upload_bytes(self._h))
 
 
 class Prepared:

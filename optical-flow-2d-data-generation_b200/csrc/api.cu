@@ -110,7 +110,10 @@ struct ofdg_prepared {
 struct ofdg_generator {
   ofdg_config cfg{};
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // ring of event pairs bracketing the render kernel of each call (roofline timing)
+  std::vector<cudaEvent_t> evs;
+  size_t ev_used = 0;
+  size_t last_upload_bytes = 0;
   // texture pool
   DevBuf pool;
   int n_tex = 0, tex_w = 0, tex_h = 0;
@@ -156,6 +159,7 @@ void upload_scene(ofdg_generator* g, const ofdg::FlatBatch& fb, DeviceScene& ds,
   if (b2) CK(cudaMemcpyAsync(ds.shapes.p, st + o2, b2, cudaMemcpyHostToDevice, s));
   if (b3) CK(cudaMemcpyAsync(ds.verts.p, st + o3, b3, cudaMemcpyHostToDevice, s));
   ds.batch = (int)fb.samples.size();
+  g->last_upload_bytes = b0 + b1 + b2 + b3;
 }
 
 void flatten_tasks(ofdg_generator* g, const ofdg_task_batch* tasks) {
@@ -198,10 +202,18 @@ ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, 
 
 // bg prep + render on stream s; times the render kernel with events on that stream.
 void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s) {
+  if (g->ev_used + 3 > g->evs.size()) {
+    if (g->evs.size() >= 3 * 8192) g->ev_used = 0;  // wrap: only the most recent calls are kept
+    else
+      for (int i = 0; i < 3; ++i) { cudaEvent_t e; CK(cudaEventCreate(&e)); g->evs.push_back(e); }
+  }
+  cudaEvent_t e0 = g->evs[g->ev_used], e1 = g->evs[g->ev_used + 1], e2 = g->evs[g->ev_used + 2];
+  g->ev_used += 3;
+  CK(cudaEventRecord(e0, s));
   g->launches += ofdg::launch_background_prep(a, s);
-  CK(cudaEventRecord(g->ev0, s));
+  CK(cudaEventRecord(e1, s));
   g->launches += ofdg::launch_render(a, s);
-  CK(cudaEventRecord(g->ev1, s));
+  CK(cudaEventRecord(e2, s));
   CK(cudaGetLastError());
 }
 
@@ -315,8 +327,6 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
     std::unique_ptr<ofdg_generator> g(new ofdg_generator);
     g->cfg = *cfg;
     CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&g->ev0));
-    CK(cudaEventCreate(&g->ev1));
     *out = g.release();
   });
 }
@@ -330,8 +340,7 @@ void ofdg_destroy(ofdg_generator* g) {
   for (DevBuf* b : bufs) b->release();
   g->scene.release();
   g->staging.release();
-  if (g->ev0) cudaEventDestroy(g->ev0);
-  if (g->ev1) cudaEventDestroy(g->ev1);
+  for (cudaEvent_t e : g->evs) cudaEventDestroy(e);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
 }
@@ -499,6 +508,21 @@ int ofdg_debug_background(ofdg_generator* g, const ofdg_task_batch* tasks, uint8
   });
 }
 
+int ofdg_debug_composite_luts(ofdg_generator* g, uint8_t* add_lut, uint8_t* sub_lut) {
+  return guarded([&] {
+    if (!g || !add_lut || !sub_lut) throw ArgError("null pointer");
+    g->use();
+    g->dbg_planar.reserve(2 * 65536);
+    uint8_t* d = (uint8_t*)g->dbg_planar.p;
+    ofdg::launch_composite_luts(d, d + 65536, g->stream);
+    ++g->launches;
+    CK(cudaMemcpyAsync(add_lut, d, 65536, cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaMemcpyAsync(sub_lut, d + 65536, 65536, cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    CK(cudaGetLastError());
+  });
+}
+
 int ofdg_prepare(ofdg_generator* g, const ofdg_task_batch* tasks, ofdg_prepared** out) {
   return guarded([&] {
     if (!g || !tasks || !out) throw ArgError("null pointer");
@@ -542,12 +566,25 @@ int ofdg_generate(ofdg_generator* g, ofdg_params* p, int32_t batch, float* d_img
 }
 
 uint64_t ofdg_launch_count(const ofdg_generator* g) { return g ? g->launches : 0; }
-float ofdg_last_render_kernel_ms(const ofdg_generator* g) {
-  if (!g) return 0.f;
-  float ms = 0.f;
-  if (cudaEventSynchronize(g->ev1) != cudaSuccess) return 0.f;
-  if (cudaEventElapsedTime(&ms, g->ev0, g->ev1) != cudaSuccess) return 0.f;
-  return ms;
+int ofdg_kernel_times(ofdg_generator* g, double* prep_ms, double* render_ms, int32_t* calls) {
+  return guarded([&] {
+    if (!g) throw ArgError("null pointer");
+    g->use();
+    double p = 0, r = 0;
+    const size_t n = g->ev_used / 3;
+    for (size_t i = 0; i < n; ++i) {
+      float a = 0.f, b = 0.f;
+      CK(cudaEventSynchronize(g->evs[3 * i + 2]));
+      CK(cudaEventElapsedTime(&a, g->evs[3 * i], g->evs[3 * i + 1]));
+      CK(cudaEventElapsedTime(&b, g->evs[3 * i + 1], g->evs[3 * i + 2]));
+      p += a; r += b;
+    }
+    g->ev_used = 0;
+    if (prep_ms) *prep_ms = p;
+    if (render_ms) *render_ms = r;
+    if (calls) *calls = (int32_t)n;
+  });
 }
+uint64_t ofdg_last_upload_bytes(const ofdg_generator* g) { return g ? g->last_upload_bytes : 0; }
 
 }  // extern "C"

@@ -37,6 +37,8 @@ __device__ __forceinline__ int iround_d(double v) { return int((v < 0.0) ? v - 0
 // agg::wrap_mode_reflect
 __device__ __forceinline__ int reflect(int v, int size) {
   if ((unsigned)v < (unsigned)size) return v;
+  if (v < 0 && v >= -size) return -v - 1;          // one fold covers every tap near the image
+  if (v >= size && v < 2 * size) return 2 * size - v - 1;
   unsigned size2 = 2u * (unsigned)size;
   unsigned add = size2 * (0x3FFFFFFFu / size2);
   unsigned m = ((unsigned)v + add) % size2;
@@ -115,14 +117,6 @@ __device__ __forceinline__ uint32_t blend_rgbx(uint32_t f, uint32_t t, unsigned 
     out |= ((m * tv + fv * (255u - m)) / 255u) << (8 * c);
   }
   return out;
-}
-
-// MovingObjectComposite::renderMasks, strict float (DG.cpp:606, 626)
-__device__ __forceinline__ unsigned comp_add(unsigned u, unsigned v) {
-  return (unsigned)(unsigned char)(255.f * (1.f - (1.f - (float)(int)u / 255.f) * (1.f - (float)(int)v / 255.f)));
-}
-__device__ __forceinline__ unsigned comp_sub(unsigned u, unsigned v) {
-  return (unsigned)(unsigned char)(255.f * (((float)(int)u / 255.f) * (1.f - (float)(int)v / 255.f)));
 }
 
 // pixfmt_gray8 blend of colour 255 over a cleared buffer
@@ -221,10 +215,47 @@ __device__ __forceinline__ bool box_hits_tile(const int32_t* b, int tx0, int ty0
 // ------------------------------------------------------------------------------------------------
 // render kernel: one CTA per (tile, sample); warp = tile row, lane = 4 consecutive pixels
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RENDER_THREADS) render_kernel(RenderArgs a) {
-  __shared__ int s_cover[2][TH][TW];
-  __shared__ int s_area[2][TH][TW];
-  __shared__ int s_carry[2][TH];
+constexpr int NLAYER = 4;      // cover/area accumulator layers that are filled between two barriers
+constexpr int MAX_HITS = 64;   // objects touching the tile handled per pass
+constexpr int MAX_JOBS = 128;  // shapes (outlines) handled per pass
+
+struct HitObject {             // what the per-pixel stage needs of a FlatObject, staged in shared memory
+  int obj;                     // index within the sample (z-order)
+  int shape_begin, shape_count;
+  int tex;
+  int composite;
+};
+struct Job {                   // one outline of a hit object
+  int vbegin[2], vcount[2];
+  short hit;                   // index into the hit table
+  signed char slot[2];         // accumulator layer per frame, -1: the outline misses the tile (coverage 0)
+  unsigned char flags;         // 1 additive | 2 first outline of its object | 4 last outline | 8 a chunk ends after this job
+};
+
+// MovingObjectComposite::renderMasks (DG.cpp:606, 626) with the trivial cases folded: the strict-float
+// formulas give ADD[u][255] = 255, SUB[u][255] = 0, SUB[0][v] = 0 and ADD[0][0] = 0 exactly; everything
+// else goes through the float expression (u/255.f and v/255.f come from a table of those quotients).
+__device__ __forceinline__ unsigned comp_add(unsigned u, unsigned v, const float* q255) {
+  if (v == 255u) return 255u;
+  if ((u | v) == 0u) return 0u;
+  return (unsigned)(unsigned char)(255.f * (1.f - (1.f - q255[u]) * (1.f - q255[v])));
+}
+__device__ __forceinline__ unsigned comp_sub(unsigned u, unsigned v, const float* q255) {
+  if (v == 255u || u == 0u) return 0u;
+  return (unsigned)(unsigned char)(255.f * ((q255[u]) * (1.f - q255[v])));
+}
+
+__global__ void __launch_bounds__(RENDER_THREADS, 2) render_kernel(RenderArgs a) {
+  __shared__ int s_cover[NLAYER][TH][TW];
+  __shared__ int s_area[NLAYER][TH][TW];
+  __shared__ int s_carry[NLAYER][TH];
+  __shared__ float s_q255[256];
+  __shared__ HitObject s_hit[MAX_HITS];
+  __shared__ Job s_job[MAX_JOBS];
+  __shared__ int s_jobbase[MAX_HITS + 1];
+  __shared__ unsigned s_ballot[RENDER_THREADS / 32];
+  __shared__ int s_nhit, s_njob, s_hits_done, s_next_obj;
+  __shared__ int s_seg_begin[NLAYER], s_seg_count[NLAYER + 1];
 
   const int W = a.W, H = a.H;
   const int tiles_x = (W + TW - 1) / TW;
@@ -235,6 +266,10 @@ __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(RenderArgs a) {
   const bool live = (y < H) && (x0 < W);
   const FlatSample& smp = a.samples[sample];
   const size_t P = (size_t)W * H;
+  const int n_obj = smp.obj_count, obj_begin = smp.obj_begin;
+
+  s_q255[tid] = (float)tid / 255.f;
+  if (tid == 0) s_next_obj = 0;
 
   uint32_t col0[4], col1[4];
   unsigned id0[4] = {0, 0, 0, 0}, id1[4] = {0, 0, 0, 0};  // 0 = background, k+1 = k-th foreground object
@@ -259,48 +294,137 @@ __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(RenderArgs a) {
     }
   }
 
-  // ---- foreground objects in z-order
   const int tex_ox = a.tex_w / 2 - W / 2, tex_oy = a.tex_h / 2 - H / 2;  // centre crop, DG.cpp:99-102 with defaults
-  for (int k = 0; k < smp.obj_count; ++k) {
-    const FlatObject& obj = a.objects[smp.obj_begin + k];
-    const bool hit0 = box_hits_tile(obj.bbox[0], tx0, ty0), hit1 = box_hits_tile(obj.bbox[1], tx0, ty0);
-    if (!hit0 && !hit1) continue;
+  unsigned aa[2][4], na[2][4];  // masks of the object being assembled: [frame][pixel]
 
-    // u[frame][aa?]: 4 pixels packed one byte each
-    unsigned aa[2][4], na[2][4];
-#pragma unroll
-    for (int f = 0; f < 2; ++f)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) aa[f][i] = na[f][i] = 0;
+  // ---- foreground objects in z-order, in passes of at most MAX_HITS objects / MAX_JOBS outlines
+  for (;;) {
+    __syncthreads();
+    const int obj0 = s_next_obj;
+    if (obj0 >= n_obj) break;
+    // (1) objects whose boxes touch the tile -> ordered hit table
+    if (tid == 0) s_nhit = 0;
+    int scanned = obj0;
+    for (; scanned < n_obj; scanned += RENDER_THREADS) {
+      __syncthreads();
+      const int nh = s_nhit;
+      if (nh >= MAX_HITS) break;
+      const int o = scanned + tid;
+      bool hit = false;
+      const FlatObject* ob = nullptr;
+      if (o < n_obj) {
+        ob = a.objects + obj_begin + o;
+        hit = box_hits_tile(ob->bbox[0], tx0, ty0) || box_hits_tile(ob->bbox[1], tx0, ty0);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) s_ballot[warp] = bal;
+      __syncthreads();
+      int pos = nh, total = nh;
+      for (int w = 0; w < RENDER_THREADS / 32; ++w) {
+        const int c = __popc(s_ballot[w]);
+        if (w < warp) pos += c;
+        total += c;
+      }
+      pos += __popc(bal & ((1u << lane) - 1u));
+      if (hit && pos < MAX_HITS) {
+        HitObject h;
+        h.obj = o; h.shape_begin = ob->shape_begin; h.shape_count = ob->shape_count; h.tex = ob->tex; h.composite = ob->composite;
+        s_hit[pos] = h;
+      }
+      if (tid == 0) {
+        // objects past the table's capacity are rescanned by the next pass
+        if (total > MAX_HITS) { s_nhit = MAX_HITS; } else { s_nhit = total; }
+      }
+      if (total > MAX_HITS) { scanned += RENDER_THREADS; break; }
+    }
+    __syncthreads();
+    // (2) outline jobs of the hit objects
+    if (tid == 0) {
+      int nj = 0, h = 0;
+      const int nh = s_nhit;
+      for (; h < nh; ++h) {
+        if (nj + s_hit[h].shape_count > MAX_JOBS && h > 0) break;
+        s_jobbase[h] = nj;
+        nj += min(s_hit[h].shape_count, MAX_JOBS);
+      }
+      s_jobbase[h] = nj;
+      s_hits_done = h;
+      s_njob = nj;
+      // next pass starts after the last object fully handled here
+      s_next_obj = (h == nh && nh < MAX_HITS) ? n_obj : s_hit[h - 1].obj + 1;
+      if (nh == 0) s_next_obj = n_obj;
+    }
+    __syncthreads();
+    const int njob = s_njob, nhd = s_hits_done;
+    if (njob == 0) continue;
+    if (tid < njob) {
+      int h = 0;
+      while (h + 1 < nhd && s_jobbase[h + 1] <= tid) ++h;
+      const int si = tid - s_jobbase[h];
+      const HitObject ho = s_hit[h];
+      const FlatShape& sh = a.shapes[ho.shape_begin + si];
+      Job j;
+      j.hit = (short)h;
+      const bool h0 = box_hits_tile(sh.bbox[0], tx0, ty0), h1 = box_hits_tile(sh.bbox[1], tx0, ty0);
+      j.vbegin[0] = sh.vbegin[0]; j.vbegin[1] = sh.vbegin[1];
+      j.vcount[0] = h0 ? sh.vcount[0] : 0; j.vcount[1] = h1 ? sh.vcount[1] : 0;
+      j.slot[0] = h0 ? 0 : -1; j.slot[1] = h1 ? 0 : -1;
+      j.flags = (unsigned char)((sh.additive ? 1 : 0) | (si == 0 ? 2 : 0) | (si == ho.shape_count - 1 ? 4 : 0));
+      s_job[tid] = j;
+    }
+    __syncthreads();
+    if (tid == 0) {  // accumulator layers and chunk boundaries
+      int used = 0;
+      for (int j = 0; j < njob; ++j) {
+        const int need = (s_job[j].slot[0] >= 0) + (s_job[j].slot[1] >= 0);
+        if (used + need > NLAYER) { s_job[j - 1].flags |= 8; used = 0; }
+        if (s_job[j].slot[0] >= 0) s_job[j].slot[0] = (signed char)used++;
+        if (s_job[j].slot[1] >= 0) s_job[j].slot[1] = (signed char)used++;
+      }
+      s_job[njob - 1].flags |= 8;
+    }
+    __syncthreads();
 
-    for (int si = 0; si < obj.shape_count; ++si) {
-      const FlatShape& sh = a.shapes[obj.shape_begin + si];
-      const bool sh0 = box_hits_tile(sh.bbox[0], tx0, ty0), sh1 = box_hits_tile(sh.bbox[1], tx0, ty0);
-      unsigned vaa[2][4], vna[2][4];
-#pragma unroll
-      for (int f = 0; f < 2; ++f)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) vaa[f][i] = vna[f][i] = 0;
-      if (sh0 || sh1) {
-        __syncthreads();  // previous readers are done with the accumulators
-        for (int i = tid; i < 2 * TH * TW; i += RENDER_THREADS) { (&s_cover[0][0][0])[i] = 0; (&s_area[0][0][0])[i] = 0; }
-        if (tid < 2 * TH) (&s_carry[0][0])[tid] = 0;
-        __syncthreads();
-        const int n0 = sh0 ? sh.vcount[0] : 0, n1 = sh1 ? sh.vcount[1] : 0;
-        for (int e = tid; e < n0 + n1; e += RENDER_THREADS) {
-          const int f = e >= n0 ? 1 : 0;
-          const int ei = f ? e - n0 : e;
-          const int n = sh.vcount[f];
-          const FlatVertex* v = a.verts + sh.vbegin[f];
+    // (3) chunks: zero -> accumulate edges -> per-pixel masks, combine, blit
+    int j0 = 0;
+    while (j0 < njob) {
+      int j1 = j0;
+      while (!(s_job[j1].flags & 8)) ++j1;
+      ++j1;  // jobs [j0, j1)
+      if (tid == 0) {
+        for (int l = 0; l < NLAYER; ++l) { s_seg_begin[l] = 0; s_seg_count[l] = 0; }
+        for (int j = j0; j < j1; ++j)
+          for (int f = 0; f < 2; ++f)
+            if (s_job[j].slot[f] >= 0) { s_seg_begin[s_job[j].slot[f]] = s_job[j].vbegin[f]; s_seg_count[s_job[j].slot[f]] = s_job[j].vcount[f]; }
+      }
+      for (int i = tid; i < NLAYER * TH * TW; i += RENDER_THREADS) { (&s_cover[0][0][0])[i] = 0; (&s_area[0][0][0])[i] = 0; }
+      if (tid < NLAYER * TH) (&s_carry[0][0])[tid] = 0;
+      __syncthreads();
+      {
+        const int c0 = s_seg_count[0], c1 = c0 + s_seg_count[1], c2 = c1 + s_seg_count[2], c3 = c2 + s_seg_count[3];
+        for (int e = tid; e < c3; e += RENDER_THREADS) {
+          const int l = e < c0 ? 0 : (e < c1 ? 1 : (e < c2 ? 2 : 3));
+          const int ei = e - (l == 0 ? 0 : (l == 1 ? c0 : (l == 2 ? c1 : c2)));
+          const int n = s_seg_count[l];
+          const FlatVertex* v = a.verts + s_seg_begin[l];
           const FlatVertex p = v[ei], q = v[ei + 1 == n ? 0 : ei + 1];
-          tile_edge(&s_cover[f][0][0], &s_area[f][0][0], &s_carry[f][0], tx0, ty0, p.x, p.y, q.x, q.y);
+          tile_edge(&s_cover[l][0][0], &s_area[l][0][0], &s_carry[l][0], tx0, ty0, p.x, p.y, q.x, q.y);
         }
-        __syncthreads();
+      }
+      __syncthreads();
+      for (int j = j0; j < j1; ++j) {
+        const Job jb = s_job[j];
+        unsigned vaa[2][4], vna[2][4];
 #pragma unroll
         for (int f = 0; f < 2; ++f) {
-          if (!(f ? sh1 : sh0)) continue;
-          const int4 c4 = *reinterpret_cast<const int4*>(&s_cover[f][warp][lane * 4]);
-          const int4 a4 = *reinterpret_cast<const int4*>(&s_area[f][warp][lane * 4]);
+          if (jb.slot[f] < 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) vaa[f][i] = vna[f][i] = 0;
+            continue;
+          }
+          const int l = jb.slot[f];
+          const int4 c4 = *reinterpret_cast<const int4*>(&s_cover[l][warp][lane * 4]);
+          const int4 a4 = *reinterpret_cast<const int4*>(&s_area[l][warp][lane * 4]);
           int c[4] = {c4.x, c4.y, c4.z, c4.w}, ar[4] = {a4.x, a4.y, a4.z, a4.w};
           c[1] += c[0]; c[2] += c[1]; c[3] += c[2];
           int tot = c[3];  // warp-level inclusive prefix sum over the lanes' cover totals
@@ -309,65 +433,75 @@ __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(RenderArgs a) {
             int o = __shfl_up_sync(0xffffffffu, tot, d);
             if (lane >= d) tot += o;
           }
-          const int base = tot - c[3] + s_carry[f][warp];
+          const int base = tot - c[3] + s_carry[l][warp];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             // sweep_scanline + calculate_alpha: arithmetic shift before abs, non-zero rule, clamp
-            int cv = (((base + c[i]) << 9) - ar[i]) >> 9;
+            int cv = ((base + c[i]) * 512 - ar[i]) >> 9;
             if (cv < 0) cv = -cv;
             if (cv > 255) cv = 255;
-            vaa[f][i] = graylut((unsigned)cv);            // gamma_none
-            vna[f][i] = cv >= 128 ? 255u : 0u;            // gamma_threshold(0.5), then graylut(255) = 255
+            vaa[f][i] = graylut((unsigned)cv);  // gamma_none
+            vna[f][i] = cv >= 128 ? 255u : 0u;  // gamma_threshold(0.5), then graylut(255) = 255
+          }
+        }
+        const HitObject ho = s_hit[jb.hit];
+        if (ho.composite) {
+          if (jb.flags & 2) {
+#pragma unroll
+            for (int f = 0; f < 2; ++f)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) aa[f][i] = na[f][i] = 0;
+          }
+#pragma unroll
+          for (int f = 0; f < 2; ++f)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (jb.flags & 1) { aa[f][i] = comp_add(aa[f][i], vaa[f][i], s_q255); na[f][i] = comp_add(na[f][i], vna[f][i], s_q255); }
+              else { aa[f][i] = comp_sub(aa[f][i], vaa[f][i], s_q255); na[f][i] = comp_sub(na[f][i], vna[f][i], s_q255); }
+            }
+        } else {
+#pragma unroll
+          for (int f = 0; f < 2; ++f)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { aa[f][i] = vaa[f][i]; na[f][i] = vna[f][i]; }
+        }
+        if (!(jb.flags & 4) || !live) continue;
+
+        // the object's masks are complete: ids from the non-AA masks, colour through the AA (or non-AA) masks
+        const int k = ho.obj;
+        if (a.dbg_masks && k < a.dbg_max_objs) {
+          uint8_t* mb = a.dbg_masks + ((size_t)sample * a.dbg_max_objs + k) * 4 * P + (size_t)y * W + x0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            mb[0 * P + i] = (uint8_t)aa[0][i]; mb[1 * P + i] = (uint8_t)aa[1][i];
+            mb[2 * P + i] = (uint8_t)na[0][i]; mb[3 * P + i] = (uint8_t)na[1][i];
+          }
+        }
+        const uchar4* tex = a.pool + (size_t)ho.tex * a.tex_w * a.tex_h;
+        unsigned any1 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (na[0][i] == 255u) id0[i] = k + 1;
+          if (na[1][i] == 255u) id1[i] = k + 1;
+          const unsigned m0 = a.use_aa ? aa[0][i] : na[0][i];
+          if (m0) {
+            uint32_t t = ld_px(tex + (size_t)(y + tex_oy) * a.tex_w + (x0 + i + tex_ox)) & 0xFFFFFFu;  // identity warp == copy
+            col0[i] = blend_rgbx(col0[i], t, m0);
+          }
+          any1 |= a.use_aa ? aa[1][i] : na[1][i];
+        }
+        if (any1) {
+          RowWarp rw;
+          rw.init(a.objects[obj_begin + k].tex_inv, (double)y, W);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const unsigned m1 = a.use_aa ? aa[1][i] : na[1][i];
+            if (m1) col1[i] = blend_rgbx(col1[i], bilinear_rgbx(tex, a.tex_w, tex_ox, tex_oy, W, H, rw, x0 + i), m1);
           }
         }
       }
-      if (obj.composite) {
-#pragma unroll
-        for (int f = 0; f < 2; ++f)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (sh.additive) { aa[f][i] = comp_add(aa[f][i], vaa[f][i]); na[f][i] = comp_add(na[f][i], vna[f][i]); }
-            else { aa[f][i] = comp_sub(aa[f][i], vaa[f][i]); na[f][i] = comp_sub(na[f][i], vna[f][i]); }
-          }
-      } else {
-#pragma unroll
-        for (int f = 0; f < 2; ++f)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { aa[f][i] = vaa[f][i]; na[f][i] = vna[f][i]; }
-      }
-    }
-
-    if (!live) continue;
-    if (a.dbg_masks && k < a.dbg_max_objs) {
-      uint8_t* mb = a.dbg_masks + ((size_t)sample * a.dbg_max_objs + k) * 4 * P + (size_t)y * W + x0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        mb[0 * P + i] = (uint8_t)aa[0][i]; mb[1 * P + i] = (uint8_t)aa[1][i];
-        mb[2 * P + i] = (uint8_t)na[0][i]; mb[3 * P + i] = (uint8_t)na[1][i];
-      }
-    }
-    // blit: ids from the non-AA masks, colour through the AA (or non-AA) masks
-    const uchar4* tex = a.pool + (size_t)obj.tex * a.tex_w * a.tex_h;
-    unsigned any1 = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (na[0][i] == 255u) id0[i] = k + 1;
-      if (na[1][i] == 255u) id1[i] = k + 1;
-      const unsigned m0 = a.use_aa ? aa[0][i] : na[0][i];
-      if (m0) {
-        uint32_t t = ld_px(tex + (size_t)(y + tex_oy) * a.tex_w + (x0 + i + tex_ox)) & 0xFFFFFFu;  // identity warp == copy
-        col0[i] = blend_rgbx(col0[i], t, m0);
-      }
-      any1 |= a.use_aa ? aa[1][i] : na[1][i];
-    }
-    if (any1) {
-      RowWarp rw;
-      rw.init(obj.tex_inv, (double)y, W);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const unsigned m1 = a.use_aa ? aa[1][i] : na[1][i];
-        if (m1) col1[i] = blend_rgbx(col1[i], bilinear_rgbx(tex, a.tex_w, tex_ox, tex_oy, W, H, rw, x0 + i), m1);
-      }
+      j0 = j1;
+      __syncthreads();  // the accumulators are rewritten by the next chunk
     }
   }
 
@@ -390,7 +524,7 @@ __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(RenderArgs a) {
       fxv[i] = (float)(ix - save_x);
       fyv[i] = (float)(iy - save_y);
     } else {
-      const double* m = a.objects[smp.obj_begin + id0[i] - 1].motion;
+      const double* m = a.objects[obj_begin + id0[i] - 1].motion;
       double ix = xf, iy = yf;
       double tmp = ix;
       ix = tmp * m[0] + iy * m[2] + m[4];
@@ -420,8 +554,8 @@ __global__ void __launch_bounds__(RENDER_THREADS) render_kernel(RenderArgs a) {
   if (a.dbg_id0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const unsigned o0id = id0[i] ? (unsigned)a.objects[smp.obj_begin + id0[i] - 1].obj_id : 1u;
-      const unsigned o1id = id1[i] ? (unsigned)a.objects[smp.obj_begin + id1[i] - 1].obj_id : 1u;
+      const unsigned o0id = id0[i] ? (unsigned)a.objects[obj_begin + id0[i] - 1].obj_id : 1u;
+      const unsigned o1id = id1[i] ? (unsigned)a.objects[obj_begin + id1[i] - 1].obj_id : 1u;
       a.dbg_id0[(size_t)sample * P + pix + i] = o0id;
       if (a.dbg_id1) a.dbg_id1[(size_t)sample * P + pix + i] = o1id;
     }
@@ -638,7 +772,21 @@ __global__ void synth_textures_kernel(uchar4* out, int n, int w, int h, uint64_t
   }
 }
 
+// Exhaustive table of the composite-mask rules as the render kernel evaluates them (parity check)
+__global__ void composite_lut_kernel(uint8_t* add_lut, uint8_t* sub_lut) {
+  __shared__ float q[256];
+  q[threadIdx.x] = (float)threadIdx.x / 255.f;
+  __syncthreads();
+  const unsigned u = blockIdx.x, v = threadIdx.x;
+  add_lut[u * 256 + v] = (uint8_t)comp_add(u, v, q);
+  sub_lut[u * 256 + v] = (uint8_t)comp_sub(u, v, q);
+}
+
 }  // namespace
+
+void launch_composite_luts(uint8_t* add_lut, uint8_t* sub_lut, cudaStream_t s) {
+  composite_lut_kernel<<<256, 256, 0, s>>>(add_lut, sub_lut);
+}
 
 int launch_background_prep(const RenderArgs& a, cudaStream_t s) {
   bg_tables_kernel<<<a.batch, 32, 0, s>>>(a);

@@ -47,6 +47,7 @@ int launch_render(const RenderArgs& a, cudaStream_t s);
 void launch_planar_to_rgbx(const uint8_t* planar, uchar4* out, int n, int w, int h, cudaStream_t s);
 void launch_rgbx_to_planar(const uchar4* in, uint8_t* planar, int w, int h, cudaStream_t s);
 void launch_synth_textures(uchar4* out, int n, int w, int h, uint64_t seed, int first_index, cudaStream_t s);
+void launch_composite_luts(uint8_t* add_lut, uint8_t* sub_lut, cudaStream_t s);
 void launch_bg_to_planar(const uchar4* bg, uint8_t* planar, int batch, int w2, int h2, cudaStream_t s);
 
 }  // namespace ofdg

@@ -108,3 +108,23 @@ def test_device_blobs_and_prepared(ofdg, oracle, textures8):
     assert np.abs(h0 - cpu["img0"]).max() <= IMG_TOL and np.abs(hf - cpu["flow"]).max() <= FLOW_TOL
     assert g.launch_count() > 0
     g.close()
+
+
+def test_composite_rules_exhaustive(ofdg, oracle):
+    """All 2 x 65536 (u, v) pairs of the composite-mask float rules, device vs the reference's expression."""
+    g = _gen(ofdg, 7)
+    ga, gs = g.debug_composite_luts()
+    ca, cs = oracle.composite_luts()
+    assert np.array_equal(ga, ca) and np.array_equal(gs, cs)
+    g.close()
+
+
+def test_many_objects_per_tile(ofdg, oracle, textures8):
+    """More objects than one pass of the tile kernel holds (stress config: forced object count)."""
+    g = _gen(ofdg, 7, max_batch=2)
+    g.upload_textures(textures8)
+    tasks = ofdg.ParamStream(7, fg_override=160).generate(2)
+    gpu = g.render_debug(tasks, max_objs=160)
+    cpu = oracle.render(tasks.struct(), textures8, mode=7, debug=True, max_objs=160)
+    _compare(gpu, cpu)
+    g.close()
