@@ -81,6 +81,12 @@ int32_t ofdg_flatten_ellipse(double rx, double ry, const double* m, int32_t* xy,
 int32_t ofdg_flatten_polygon(const int32_t* seg_type, const float* seg_x, const float* seg_y, int32_t n,
                              const double* m, int32_t* xy, int32_t cap);
 
+/* The render kernel's tile rasteriser executed on the HOST (same source, csrc/raster_tile.h) for a
+ * closed outline of n 24.8 fixed-point vertices; writes the W x H gray8 mask draw() would produce
+ * (aa != 0: gamma_none, else gamma_threshold(0.5)). Lets the CPU test-suite check the closed-form
+ * cell arithmetic against the oracle's sequential AGG port without a GPU. */
+int ofdg_debug_raster_host(const int32_t* xy, int32_t n, int32_t W, int32_t H, int32_t aa, uint8_t* mask);
+
 /* ---- generator ------------------------------------------------------------------------------------ */
 int ofdg_create(const ofdg_config* cfg, ofdg_generator** out);   /* DataGenerator ctor + Start(), DataGenerator.cpp:990-1030 */
 void ofdg_destroy(ofdg_generator* g);                            /* Stop() + dtor */

@@ -55,7 +55,7 @@ EXPORTS = [
     "ofdg_last_error", "ofdg_version", "ofdg_params_create", "ofdg_params_destroy", "ofdg_params_generate",
     "ofdg_params_skip", "ofdg_params_tasks_generated", "ofdg_params_draws", "ofdg_params_slot_name",
     "ofdg_tasks_create", "ofdg_tasks_destroy", "ofdg_tasks_clear", "ofdg_tasks_view", "ofdg_tasks_assign",
-    "ofdg_flatten_ellipse", "ofdg_flatten_polygon", "ofdg_create", "ofdg_destroy", "ofdg_upload_textures",
+    "ofdg_flatten_ellipse", "ofdg_flatten_polygon", "ofdg_debug_raster_host", "ofdg_create", "ofdg_destroy", "ofdg_upload_textures",
     "ofdg_synth_textures", "ofdg_download_texture", "ofdg_set_fields", "ofdg_render", "ofdg_render_host",
     "ofdg_render_debug", "ofdg_debug_background", "ofdg_debug_composite_luts", "ofdg_prepare", "ofdg_prepared_destroy",
     "ofdg_render_prepared", "ofdg_generate", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_upload_bytes",
@@ -93,6 +93,7 @@ def lib():
         L.ofdg_tasks_assign.argtypes = [C.c_void_p, C.POINTER(TaskBatchStruct)]
         L.ofdg_flatten_ellipse.argtypes = [C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int32]
         L.ofdg_flatten_polygon.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
+        L.ofdg_debug_raster_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
         L.ofdg_create.argtypes = [C.POINTER(ConfigStruct), C.POINTER(C.c_void_p)]
         L.ofdg_destroy.argtypes = [C.c_void_p]
         L.ofdg_upload_textures.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
@@ -264,6 +265,14 @@ def flatten_polygon(seg_type, seg_x, seg_y, m):
     if n < 0:
         raise OfdgError(lib().ofdg_last_error().decode())
     return xy[:n].copy()
+
+
+def raster_host(xy, W, H, aa=True):
+    """The render kernel's tile rasteriser run on the host (csrc/raster_tile.h)."""
+    xy = np.ascontiguousarray(xy, dtype=np.int32)
+    mask = np.empty((H, W), np.uint8)
+    _check(lib().ofdg_debug_raster_host(_ptr(xy), len(xy), W, H, int(aa), _ptr(mask)))
+    return mask
 
 
 class Generator:

@@ -11,6 +11,7 @@
 #include "host/flatten.hpp"
 #include "host/params.hpp"
 #include "ofdg/ofdg.h"
+#include "raster_tile.h"
 #include "render.cuh"
 
 namespace {
@@ -306,6 +307,34 @@ int32_t ofdg_flatten_polygon(const int32_t* seg_type, const float* seg_x, const 
     g_error = e.what();
     return -1;
   }
+}
+
+// The tile rasteriser of the render kernel (raster_tile.h) run on the host over every tile of a
+// W x H frame: same code path as the device, atomics replaced by plain adds.
+int ofdg_debug_raster_host(const int32_t* xy, int32_t n, int32_t W, int32_t H, int32_t aa, uint8_t* mask) {
+  return guarded([&] {
+    if (!xy || !mask || n < 1 || W <= 0 || H <= 0) throw ArgError("bad arguments");
+    using namespace ofdg;
+    std::vector<int> cover(TH * TW), area(TH * TW), carry(TH);
+    for (int ty0 = 0; ty0 < H; ty0 += TH)
+      for (int tx0 = 0; tx0 < W; tx0 += TW) {
+        std::fill(cover.begin(), cover.end(), 0);
+        std::fill(area.begin(), area.end(), 0);
+        std::fill(carry.begin(), carry.end(), 0);
+        for (int e = 0; e < n; ++e) {
+          const int e2 = e + 1 == n ? 0 : e + 1;
+          tile_edge<false>(cover.data(), area.data(), carry.data(), tx0, ty0, xy[2 * e], xy[2 * e + 1], xy[2 * e2], xy[2 * e2 + 1]);
+        }
+        for (int r = 0; r < TH && ty0 + r < H; ++r) {
+          int cum = carry[r];
+          for (int c = 0; c < TW && tx0 + c < W; ++c) {
+            cum += cover[r * TW + c];
+            const int cv = coverage_alpha(cum, area[r * TW + c]);
+            mask[(size_t)(ty0 + r) * W + tx0 + c] = (uint8_t)(aa ? graylut((unsigned)cv) : (cv >= 128 ? 255u : 0u));
+          }
+        }
+      }
+  });
 }
 
 // ---- generator ---------------------------------------------------------------------------------------

@@ -13,25 +13,17 @@
 //       write    uint8 -> float conversion into the output blobs                      (DG.cpp:1229-1245)
 #include "render.cuh"
 
+#include "raster_tile.h"
+
 namespace ofdg {
 
 namespace {
 
-constexpr int TW = 128;   // tile width  = 32 lanes x 4 pixels (one 128-bit store per lane and plane)
-constexpr int TH = 8;     // tile height = 8 warps
-constexpr int RENDER_THREADS = 256;
+constexpr int RENDER_THREADS = 256;  // TH warps; lane = 4 consecutive pixels (one 128-bit store per lane and plane)
 
 // ------------------------------------------------------------------------------------------------
 // small integer helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int floordiv(int a, int b) {  // b > 0
-  int q = a / b, r = a % b;
-  return r < 0 ? q - 1 : q;
-}
-__device__ __forceinline__ long long floordiv64(long long a, long long b) {  // b > 0
-  long long q = a / b, r = a % b;
-  return r < 0 ? q - 1 : q;
-}
 __device__ __forceinline__ int iround_d(double v) { return int((v < 0.0) ? v - 0.5 : v + 0.5); }
 
 // agg::wrap_mode_reflect
@@ -47,6 +39,8 @@ __device__ __forceinline__ int reflect(int v, int size) {
 // CImg mirror boundary: cimg::mod(i, 2n), then fold
 __device__ __forceinline__ int mirror(int i, int n) {
   if ((unsigned)i < (unsigned)n) return i;
+  if (i < 0 && i >= -n) return -i - 1;
+  if (i >= n && i < 2 * n) return 2 * n - i - 1;
   int n2 = 2 * n;
   int m = i % n2;
   if (m < 0) m += n2;
@@ -55,16 +49,20 @@ __device__ __forceinline__ int mirror(int i, int n) {
 
 // dda2_line_interpolator in closed form: value after i increments
 struct Dda2 {
-  int v1, lft, rem, n;
+  int v1, lft, rem, n, sh;
   __device__ __forceinline__ void init(int a, int b, int count) {
     n = count;
+    sh = (count & (count - 1)) == 0 ? 31 - __clz(count) : -1;  // 512 / 1024 wide frames: shift instead of divide
     int d = b - a;
     lft = d / n;
     rem = d % n;
     if (rem <= 0) { rem += n; lft--; }
     v1 = a;
   }
-  __device__ __forceinline__ int at(int i) const { return v1 + i * lft + ((i + 1) * rem + n - 1) / n - 1; }
+  __device__ __forceinline__ int at(int i) const {
+    const int t = (i + 1) * rem + n - 1;  // > 0
+    return v1 + i * lft + (sh >= 0 ? (t >> sh) : t / n) - 1;
+  }
 };
 
 // One row of agg::span_interpolator_linear + span_image_filter_rgb_bilinear over an RGBX image
@@ -97,13 +95,17 @@ __device__ __forceinline__ uint32_t bilinear_rgbx(const uchar4* img, int pitch, 
   const uchar4* r0 = img + (size_t)(oy + ya) * pitch + ox;
   const uchar4* r1 = img + (size_t)(oy + yb) * pitch + ox;
   uint32_t p00 = ld_px(r0 + xa), p10 = ld_px(r0 + xb), p01 = ld_px(r1 + xa), p11 = ld_px(r1 + xb);
-  unsigned w00 = (256 - fx) * (256 - fy), w10 = fx * (256 - fy), w01 = (256 - fx) * fy, w11 = fx * fy;
+  // sum w_k p_k = [p00 (256-fx) + p10 fx] (256-fy) + [p01 (256-fx) + p11 fx] fy, exact in integers;
+  // the horizontal pair is one dp4a: bytes {p00_c, p10_c, p00_c, 0} . {255-fx, fx, 1, 0}
+  const unsigned wx = (255u - fx) | (fx << 8) | (1u << 16);
   uint32_t out = 0;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    unsigned s = 32768u + w00 * ((p00 >> (8 * c)) & 255u) + w10 * ((p10 >> (8 * c)) & 255u) +
-                 w01 * ((p01 >> (8 * c)) & 255u) + w11 * ((p11 >> (8 * c)) & 255u);
-    out |= (s >> 16) << (8 * c);
+    const unsigned sel = (unsigned)c | ((4u + c) << 4) | ((unsigned)c << 8) | (3u << 12);
+    const unsigned top = __dp4a(__byte_perm(p00, p10, sel) & 0xFFFFFFu, wx, 0u);
+    const unsigned bot = __dp4a(__byte_perm(p01, p11, sel) & 0xFFFFFFu, wx, 0u);
+    const unsigned sacc = 32768u + top * (256u - fy) + bot * fy;
+    out |= (sacc >> 16) << (8 * c);
   }
   return out;
 }
@@ -117,94 +119,6 @@ __device__ __forceinline__ uint32_t blend_rgbx(uint32_t f, uint32_t t, unsigned 
     out |= ((m * tv + fv * (255u - m)) / 255u) << (8 * c);
   }
   return out;
-}
-
-// pixfmt_gray8 blend of colour 255 over a cleared buffer
-__device__ __forceinline__ unsigned graylut(unsigned c) {
-  return c == 255u ? 255u : (255u * ((255u * (c + 1u)) >> 8)) >> 8;
-}
-
-// ------------------------------------------------------------------------------------------------
-// AGG cell accumulation for one edge restricted to one tile (closed forms of H1)
-// ------------------------------------------------------------------------------------------------
-// render_hline(ey, x1, y1, x2, y2) with the cells scattered into the tile's cover/area arrays;
-// cells left of the tile only add to the row's carry-in cover, cells right of it are dropped.
-__device__ __forceinline__ void tile_hline(int* cover, int* area, int* carry, int tx0, int x1, int y1, int x2, int y2) {
-  if (y1 == y2) return;
-  int ex1 = x1 >> 8, ex2 = x2 >> 8, fx1 = x1 & 255, fx2 = x2 & 255;
-  const int dyv = y2 - y1;
-  if (ex1 == ex2) {
-    int c = ex1 - tx0;
-    if (c < 0) atomicAdd(carry, dyv);
-    else if (c < TW) { atomicAdd(cover + c, dyv); atomicAdd(area + c, (fx1 + fx2) * dyv); }
-    return;
-  }
-  int dx = x2 - x1, p0, incr, first;
-  if (dx > 0) { p0 = (256 - fx1) * dyv; incr = 1; first = 256; }
-  else { p0 = fx1 * dyv; incr = -1; first = 0; dx = -dx; }
-  const int ncell = (ex2 - ex1) * incr;  // >= 1: cells j = 0..ncell along the walk
-  // cumulative y after leaving cell j: C(j) = floor((p0 + 256*j*dy) / dx), j < ncell; C(ncell) = dy
-  auto C = [&](int j) { return j >= ncell ? dyv : floordiv(p0 + 256 * j * dyv, dx); };
-  // walk cells; j-th cell is ex1 + incr*j
-  int jlo, jhi;  // range of j whose cell lies inside the tile
-  if (incr > 0) { jlo = max(0, tx0 - ex1); jhi = min(ncell, tx0 + TW - 1 - ex1); }
-  else { jlo = max(0, ex1 - (tx0 + TW - 1)); jhi = min(ncell, ex1 - tx0); }
-  // cover of all cells left of the tile (telescoping sum)
-  if (incr > 0) {
-    if (ex1 < tx0) { int jl = min(ncell + 1, tx0 - ex1); atomicAdd(carry, jl > ncell ? dyv : C(jl - 1)); }
-  } else {
-    if (ex2 < tx0) { int jf = max(0, ex1 - tx0 + 1); atomicAdd(carry, dyv - (jf > 0 ? C(jf - 1) : 0)); }
-  }
-  if (jlo > jhi) return;
-  int prev = jlo > 0 ? C(jlo - 1) : 0;
-  for (int j = jlo; j <= jhi; ++j) {
-    int cur = C(j);
-    int d = cur - prev;
-    prev = cur;
-    int a;
-    if (j == 0) a = (fx1 + first) * d;
-    else if (j == ncell) a = (fx2 + 256 - first) * d;
-    else a = 256 * d;
-    int c = ex1 + incr * j - tx0;
-    if (d | a) { atomicAdd(cover + c, d); atomicAdd(area + c, a); }
-  }
-}
-
-// rasterizer_cells_aa::line(x1,y1,x2,y2) restricted to tile rows [ty0, ty0+TH) and columns [tx0, tx0+TW)
-__device__ __forceinline__ void tile_edge(int* cover, int* area, int* carry, int tx0, int ty0, int xa, int ya, int xb, int yb) {
-  if (ya == yb) return;
-  const int ey1 = ya >> 8, ey2 = yb >> 8;
-  const int rlo = max(min(ey1, ey2), ty0), rhi = min(max(ey1, ey2), ty0 + TH - 1);
-  if (rlo > rhi) return;
-  if ((min(xa, xb) >> 8) >= tx0 + TW) return;
-  const int fy1 = ya & 255, fy2 = yb & 255;
-  const long long dx = (long long)xb - xa;
-  if (ey1 == ey2) {
-    const int r = ey1 - ty0;
-    tile_hline(cover + r * TW, area + r * TW, carry + r, tx0, xa, fy1, xb, fy2);
-    return;
-  }
-  if (yb > ya) {
-    const long long dy = (long long)yb - ya;
-    // x at the bottom boundary of row ey1 + j
-    auto X = [&](int j) { return xa + (int)floordiv64(((256 - fy1) + 256LL * j) * dx, dy); };
-    for (int r = rlo; r <= rhi; ++r) {
-      const int j = r - ey1;
-      const int xs = j == 0 ? xa : X(j - 1), ys = j == 0 ? fy1 : 0;
-      const int xe = r == ey2 ? xb : X(j), ye = r == ey2 ? fy2 : 256;
-      tile_hline(cover + (r - ty0) * TW, area + (r - ty0) * TW, carry + (r - ty0), tx0, xs, ys, xe, ye);
-    }
-  } else {
-    const long long dy = (long long)ya - yb;
-    // x at the top boundary of row ey1 - j
-    auto X = [&](int j) { return xa + (int)floordiv64((fy1 + 256LL * j) * dx, dy); };
-    for (int r = rhi; r >= rlo; --r) {
-      const int j = ey1 - r;
-      const int xs = j == 0 ? xa : X(j - 1), ys = j == 0 ? fy1 : 256;
-      const int xe = r == ey2 ? xb : X(j), ye = r == ey2 ? fy2 : 0;
-      tile_hline(cover + (r - ty0) * TW, area + (r - ty0) * TW, carry + (r - ty0), tx0, xs, ys, xe, ye);
-    }
-  }
 }
 
 __device__ __forceinline__ bool box_hits_tile(const int32_t* b, int tx0, int ty0) {
@@ -245,7 +159,7 @@ __device__ __forceinline__ unsigned comp_sub(unsigned u, unsigned v, const float
   return (unsigned)(unsigned char)(255.f * ((q255[u]) * (1.f - q255[v])));
 }
 
-__global__ void __launch_bounds__(RENDER_THREADS, 2) render_kernel(RenderArgs a) {
+__global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a) {
   __shared__ int s_cover[NLAYER][TH][TW];
   __shared__ int s_area[NLAYER][TH][TW];
   __shared__ int s_carry[NLAYER][TH];
@@ -408,7 +322,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 2) render_kernel(RenderArgs a)
           const int n = s_seg_count[l];
           const FlatVertex* v = a.verts + s_seg_begin[l];
           const FlatVertex p = v[ei], q = v[ei + 1 == n ? 0 : ei + 1];
-          tile_edge(&s_cover[l][0][0], &s_area[l][0][0], &s_carry[l][0], tx0, ty0, p.x, p.y, q.x, q.y);
+          tile_edge<true>(&s_cover[l][0][0], &s_area[l][0][0], &s_carry[l][0], tx0, ty0, p.x, p.y, q.x, q.y);
         }
       }
       __syncthreads();
@@ -436,10 +350,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 2) render_kernel(RenderArgs a)
           const int base = tot - c[3] + s_carry[l][warp];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            // sweep_scanline + calculate_alpha: arithmetic shift before abs, non-zero rule, clamp
-            int cv = ((base + c[i]) * 512 - ar[i]) >> 9;
-            if (cv < 0) cv = -cv;
-            if (cv > 255) cv = 255;
+            const int cv = coverage_alpha(base + c[i], ar[i]);
             vaa[f][i] = graylut((unsigned)cv);  // gamma_none
             vna[f][i] = cv >= 128 ? 255u : 0u;  // gamma_threshold(0.5), then graylut(255) = 255
           }
@@ -603,8 +514,12 @@ constexpr int PT = 32;        // prepared-texture tile edge
 constexpr int PS = 46;        // source tile edge: ceil(32 * 1.25) + slack  (zoom >= 0.8 => crop <= 1.25 * 2W)
 constexpr int PREP_THREADS = 256;
 
+// cimg::mod(float x, float m) = (float)(dx - dm * floor(dx / dm)) in double. For 0 <= x < m the quotient's
+// floor is 0 and the result is x itself; for -m <= x < 0 it is -1 and the result is (float)(dx + dm).
 __device__ __forceinline__ float cimg_mod_f(float x, float m) {
+  if (x >= 0.f && x < m) return x;
   const double dx = (double)x, dm = (double)m;
+  if (x < 0.f && x >= -m) return (float)(dx + dm);
   return (float)(dx - dm * floor(dx / dm));
 }
 
@@ -645,12 +560,12 @@ __device__ __forceinline__ uint32_t resize_at(const uint32_t* src, int stride, i
   if (len == n) return src[(t - s0) * stride];
   uint32_t out = 0;
   if (len > n) {  // moving average over the exact rational overlap
-    const long long lo = (long long)t * len, hi = lo + len;
+    const unsigned lo = (unsigned)t * (unsigned)len, hi = lo + (unsigned)len;  // < 2^31 for any supported size
     float acc[3] = {0.f, 0.f, 0.f};
-    for (int s = (int)(lo / n); (long long)s * n < hi; ++s) {
-      const long long b = max((long long)s * n, lo), e = min((long long)(s + 1) * n, hi);
-      const float d = (float)(unsigned int)(e - b);
-      const uint32_t p = src[(s - s0) * stride];
+    for (unsigned s = lo / (unsigned)n; s * (unsigned)n < hi; ++s) {
+      const unsigned b = max(s * (unsigned)n, lo), e = min((s + 1u) * (unsigned)n, hi);
+      const float d = (float)(e - b);
+      const uint32_t p = src[((int)s - s0) * stride];
 #pragma unroll
       for (int c = 0; c < 3; ++c) acc[c] += (float)((p >> (8 * c)) & 255u) * d;
     }
@@ -694,25 +609,24 @@ __global__ void __launch_bounds__(PREP_THREADS) bg_prep_kernel(RenderArgs a) {
   const int cw = cx1 - cx0 + 1, ch = cy1 - cy0 + 1;  // <= PS by construction
   const uchar4* tex = a.pool + (size_t)p.tex * a.tex_w * a.tex_h;
   // A: crop(x0, y0, .., mirror) of the rotated image
-  for (int i = threadIdx.x; i < cw * ch; i += PREP_THREADS) {
-    const int lx = i % cw, ly = i / cw;
-    sA[ly][lx] = rotated_px(tex, a.tex_w, a.tex_h, p, mirror(p.crop_x0 + cx0 + lx, p.rw), mirror(p.crop_y0 + cy0 + ly, p.rh));
-  }
+  const int lane_x = threadIdx.x & 31, lane_y = threadIdx.x >> 5;
+  for (int ly = lane_y; ly < ch; ly += PREP_THREADS / 32)
+    for (int lx = lane_x; lx < cw; lx += 32)
+      sA[ly][lx] = rotated_px(tex, a.tex_w, a.tex_h, p, mirror(p.crop_x0 + cx0 + lx, p.rw), mirror(p.crop_y0 + cy0 + ly, p.rh));
   __syncthreads();
   // B: resize along x
   const int tw = X1 - X0 + 1, th = Y1 - Y0 + 1;
-  for (int i = threadIdx.x; i < tw * ch; i += PREP_THREADS) {
-    const int lx = i % tw, ly = i / tw;
-    sB[ly][lx] = resize_at(&sA[ly][0], 1, cx0, p.crop_w, W2, X0 + lx, pos_x, alpha_x);
-  }
+  if (lane_x < tw)
+    for (int ly = lane_y; ly < ch; ly += PREP_THREADS / 32)
+      sB[ly][lane_x] = resize_at(&sA[ly][0], 1, cx0, p.crop_w, W2, X0 + lane_x, pos_x, alpha_x);
   __syncthreads();
   // P: resize along y
   uchar4* out = a.bg + (size_t)sample * W2 * H2;
-  for (int i = threadIdx.x; i < tw * th; i += PREP_THREADS) {
-    const int lx = i % tw, ly = i / tw;
-    const uint32_t v = resize_at(&sB[0][lx], PT, cy0, p.crop_h, H2, Y0 + ly, pos_y, alpha_y);
-    *reinterpret_cast<uint32_t*>(out + (size_t)(Y0 + ly) * W2 + X0 + lx) = v;
-  }
+  if (lane_x < tw)
+    for (int ly = lane_y; ly < th; ly += PREP_THREADS / 32) {
+      const uint32_t v = resize_at(&sB[0][lane_x], PT, cy0, p.crop_h, H2, Y0 + ly, pos_y, alpha_y);
+      *reinterpret_cast<uint32_t*>(out + (size_t)(Y0 + ly) * W2 + X0 + lane_x) = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
