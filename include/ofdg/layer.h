@@ -1,0 +1,32 @@
+/*
+ * ofdg/layer.h -- C entry points that drive the Caffe-style DataGenerationLayer
+ * (optical-flow-2d-data-generation_b200/csrc/host/layer.hpp) from a host that cannot include C++
+ * headers. A C++ host uses caffe::DataGenerationLayer<float> directly, exactly like the reference's
+ * /root/reference/include/caffe/layers/data_generation_layer.hpp:37-89.
+ * All functions return 0 on success; message via ofdg_layer_last_error().
+ */
+#ifndef OFDG_LAYER_H_
+#define OFDG_LAYER_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* ofdg_layer_last_error(void);
+/* Parses a prototxt `layer { ... }` block (the reference's example-prototxt/train.prototxt is accepted verbatim).
+ * ints[7] = {batch_size, prefetch, mode, first_level_threads, second_level_threads, use_antialiasing, top_size}. */
+int ofdg_layer_parse_prototxt(const char* text, int32_t* ints, char* texture_db, int32_t cap, char* type, int32_t type_cap);
+/* DataGenerationLayer(const LayerParameter&) on the current CUDA device. texture_db_override (may be NULL)
+ * replaces texture_dbases(0): either a list file of binary PPM paths or "synthetic:<count>[:<seed>]". */
+int ofdg_layer_create(const char* prototxt, const char* texture_db_override, int32_t solver_rank, void** out);
+void ofdg_layer_destroy(void* layer);
+int ofdg_layer_setup(void* layer);                               /* Layer::SetUp -> LayerSetUp: starts prefetching, shapes the 3 tops */
+int ofdg_layer_top_shape(void* layer, int32_t i, int32_t* shape4);
+int ofdg_layer_forward(void* layer, int32_t gpu);                /* Forward_gpu (1) / Forward_cpu (0) */
+const float* ofdg_layer_top_data(void* layer, int32_t i, int32_t gpu); /* top[i]->gpu_data() / cpu_data() */
+const char* ofdg_layer_type(void* layer);                        /* "DataGeneration" */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -60,6 +60,11 @@ EXPORTS = [
     "ofdg_render_debug", "ofdg_debug_background", "ofdg_debug_composite_luts", "ofdg_prepare", "ofdg_prepared_destroy",
     "ofdg_render_prepared", "ofdg_generate", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_upload_bytes",
 ]
+# include/ofdg/layer.h
+LAYER_EXPORTS = [
+    "ofdg_layer_last_error", "ofdg_layer_parse_prototxt", "ofdg_layer_create", "ofdg_layer_destroy", "ofdg_layer_setup",
+    "ofdg_layer_top_shape", "ofdg_layer_forward", "ofdg_layer_top_data", "ofdg_layer_type",
+]
 
 
 def lib():
@@ -109,6 +114,17 @@ def lib():
         L.ofdg_prepared_destroy.argtypes = [C.c_void_p]
         L.ofdg_render_prepared.argtypes = [C.c_void_p] * 6
         L.ofdg_generate.argtypes = [C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 4
+        L.ofdg_layer_last_error.restype = C.c_char_p
+        L.ofdg_layer_type.restype = C.c_char_p
+        L.ofdg_layer_type.argtypes = [C.c_void_p]
+        L.ofdg_layer_parse_prototxt.argtypes = [C.c_char_p, C.c_void_p, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32]
+        L.ofdg_layer_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
+        L.ofdg_layer_destroy.argtypes = [C.c_void_p]
+        L.ofdg_layer_setup.argtypes = [C.c_void_p]
+        L.ofdg_layer_top_shape.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.ofdg_layer_forward.argtypes = [C.c_void_p, C.c_int32]
+        L.ofdg_layer_top_data.restype = C.c_void_p
+        L.ofdg_layer_top_data.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         _lib = L
     return _lib
 
@@ -447,3 +463,70 @@ def synth_textures(n, w=1024, h=768, seed=0, first_index=0):
             v = (acc // np.uint32(15)) * np.uint32(3) // np.uint32(4) + tri // np.uint32(4) + checker * np.uint32(24) + np.uint32(c * 5)
             out[ti, c] = np.minimum(v, 255).astype(np.uint8)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Caffe-style layer surface (csrc/host/layer.hpp): prototxt in, three top blobs out.
+# ---------------------------------------------------------------------------------------------------
+def parse_prototxt(text):
+    """Fields of a prototxt `layer { ... }` block as the layer sees them."""
+    ints = (C.c_int32 * 7)()
+    db = C.create_string_buffer(4096)
+    ty = C.create_string_buffer(256)
+    if lib().ofdg_layer_parse_prototxt(text.encode(), ints, db, 4096, ty, 256):
+        raise OfdgError(lib().ofdg_layer_last_error().decode())
+    keys = ["batch_size", "prefetch", "mode", "first_level_threads", "second_level_threads", "use_antialiasing", "top_size"]
+    d = dict(zip(keys, [int(v) for v in ints]))
+    d["use_antialiasing"] = bool(d["use_antialiasing"])
+    d["texture_dbases"] = db.value.decode()
+    d["type"] = ty.value.decode()
+    return d
+
+
+class DataGenerationLayer:
+    """caffe::DataGenerationLayer<float> (type "DataGeneration", 0 bottoms, 3 tops) driven from Python.
+
+    layer = DataGenerationLayer(prototxt_text, texture_db="synthetic:64"); layer.LayerSetUp()
+    layer.Forward_gpu(); img0, img1, flow = layer.top_tensors()   # torch views of the device blobs
+    """
+
+    def __init__(self, prototxt, texture_db=None, solver_rank=0):
+        self._h = C.c_void_p()
+        if lib().ofdg_layer_create(prototxt.encode(), (texture_db or "").encode(), solver_rank, C.byref(self._h)):
+            raise OfdgError(lib().ofdg_layer_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.ofdg_layer_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def type(self):
+        return lib().ofdg_layer_type(self._h).decode()
+
+    def LayerSetUp(self):
+        if lib().ofdg_layer_setup(self._h):
+            raise OfdgError(lib().ofdg_layer_last_error().decode())
+
+    def top_shape(self, i):
+        s = (C.c_int32 * 4)()
+        if lib().ofdg_layer_top_shape(self._h, i, s):
+            raise OfdgError(lib().ofdg_layer_last_error().decode())
+        return tuple(int(v) for v in s)
+
+    def Forward_gpu(self):
+        if lib().ofdg_layer_forward(self._h, 1):
+            raise OfdgError(lib().ofdg_layer_last_error().decode())
+
+    def Forward_cpu(self):
+        if lib().ofdg_layer_forward(self._h, 0):
+            raise OfdgError(lib().ofdg_layer_last_error().decode())
+
+    def top_cpu(self, i):
+        shape = self.top_shape(i)
+        ptr = lib().ofdg_layer_top_data(self._h, i, 0)
+        if not ptr:
+            raise OfdgError(lib().ofdg_layer_last_error().decode())
+        n = int(np.prod(shape))
+        return np.frombuffer((C.c_float * n).from_address(ptr), dtype=np.float32).reshape(shape).copy()

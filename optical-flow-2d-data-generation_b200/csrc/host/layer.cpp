@@ -1,0 +1,469 @@
+// See layer.hpp / caffe_shim.hpp.
+#include "layer.hpp"
+
+#include <cuda_runtime.h>
+
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+
+namespace caffe {
+
+#define SHIM_CUDA(expr)                                                                              \
+  do {                                                                                               \
+    cudaError_t e_ = (expr);                                                                         \
+    if (e_ != cudaSuccess) throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+// ---- Blob -------------------------------------------------------------------------------------------
+template <typename Dtype>
+Blob<Dtype>::~Blob() {
+  if (cpu_) cudaFreeHost(cpu_);
+  if (gpu_) cudaFree(gpu_);
+}
+template <typename Dtype>
+void Blob<Dtype>::Reshape(const std::vector<int>& shape) {
+  shape_ = shape;
+  size_t n = 1;
+  for (int d : shape) n *= (size_t)d;
+  count_ = (int)n;
+  if (n > capacity_) {
+    if (cpu_) cudaFreeHost(cpu_);
+    if (gpu_) cudaFree(gpu_);
+    cpu_ = nullptr; gpu_ = nullptr;
+    capacity_ = n;
+    head_ = UNINITIALIZED;
+  }
+}
+template <typename Dtype>
+void Blob<Dtype>::to_cpu() {
+  if (!cpu_) {
+    SHIM_CUDA(cudaMallocHost((void**)&cpu_, capacity_ * sizeof(Dtype)));
+    if (head_ == UNINITIALIZED) std::memset(cpu_, 0, capacity_ * sizeof(Dtype));
+  }
+  if (head_ == HEAD_AT_GPU) {
+    SHIM_CUDA(cudaMemcpy(cpu_, gpu_, (size_t)count_ * sizeof(Dtype), cudaMemcpyDeviceToHost));
+    head_ = SYNCED;
+  }
+}
+template <typename Dtype>
+void Blob<Dtype>::to_gpu() {
+  if (!gpu_) {
+    SHIM_CUDA(cudaMalloc((void**)&gpu_, capacity_ * sizeof(Dtype)));
+    if (head_ == UNINITIALIZED) SHIM_CUDA(cudaMemset(gpu_, 0, capacity_ * sizeof(Dtype)));
+  }
+  if (head_ == HEAD_AT_CPU) {
+    SHIM_CUDA(cudaMemcpy(gpu_, cpu_, (size_t)count_ * sizeof(Dtype), cudaMemcpyHostToDevice));
+    head_ = SYNCED;
+  }
+}
+template <typename Dtype>
+const Dtype* Blob<Dtype>::cpu_data() { to_cpu(); if (head_ == UNINITIALIZED) head_ = HEAD_AT_CPU; return cpu_; }
+template <typename Dtype>
+Dtype* Blob<Dtype>::mutable_cpu_data() { to_cpu(); head_ = HEAD_AT_CPU; return cpu_; }
+template <typename Dtype>
+const Dtype* Blob<Dtype>::gpu_data() { to_gpu(); if (head_ == UNINITIALIZED) head_ = HEAD_AT_GPU; return gpu_; }
+template <typename Dtype>
+Dtype* Blob<Dtype>::mutable_gpu_data() { to_gpu(); head_ = HEAD_AT_GPU; return gpu_; }
+template class Blob<float>;
+
+// ---- prototxt text parser -----------------------------------------------------------------------------
+namespace {
+struct Tok {
+  enum K { IDENT, STRING, NUMBER, LBRACE, RBRACE, COLON, END } k;
+  std::string s;
+};
+struct Lexer {
+  const std::string& t;
+  size_t i = 0;
+  explicit Lexer(const std::string& text) : t(text) {}
+  Tok next() {
+    for (;;) {
+      while (i < t.size() && std::isspace((unsigned char)t[i])) ++i;
+      if (i < t.size() && t[i] == '#') { while (i < t.size() && t[i] != '\n') ++i; continue; }
+      break;
+    }
+    if (i >= t.size()) return {Tok::END, ""};
+    char c = t[i];
+    if (c == '{') { ++i; return {Tok::LBRACE, "{"}; }
+    if (c == '}') { ++i; return {Tok::RBRACE, "}"}; }
+    if (c == ':') { ++i; return {Tok::COLON, ":"}; }
+    if (c == '"' || c == '\'') {
+      size_t j = ++i;
+      std::string out;
+      while (j < t.size() && t[j] != c) { if (t[j] == '\\' && j + 1 < t.size()) ++j; out += t[j++]; }
+      if (j >= t.size()) throw std::runtime_error("prototxt: unterminated string");
+      i = j + 1;
+      return {Tok::STRING, out};
+    }
+    size_t j = i;
+    while (j < t.size() && !std::isspace((unsigned char)t[j]) && t[j] != '{' && t[j] != '}' && t[j] != ':' && t[j] != '#') ++j;
+    std::string w = t.substr(i, j - i);
+    i = j;
+    bool num = !w.empty() && (std::isdigit((unsigned char)w[0]) || w[0] == '-' || w[0] == '+' || w[0] == '.');
+    return {num ? Tok::NUMBER : Tok::IDENT, w};
+  }
+};
+int to_int(const Tok& v, const std::string& f) {
+  if (v.k != Tok::NUMBER) throw std::runtime_error("prototxt: field '" + f + "' expects an integer");
+  return std::atoi(v.s.c_str());
+}
+bool to_bool(const Tok& v, const std::string& f) {
+  if (v.s == "true" || v.s == "1") return true;
+  if (v.s == "false" || v.s == "0") return false;
+  throw std::runtime_error("prototxt: field '" + f + "' expects true/false");
+}
+std::string to_str(const Tok& v, const std::string& f) {
+  if (v.k != Tok::STRING) throw std::runtime_error("prototxt: field '" + f + "' expects a quoted string");
+  return v.s;
+}
+// parses `name: value` or `name { ... }` pairs until the closing brace
+template <class F>
+void parse_message(Lexer& lx, bool top_level, F&& field) {
+  for (;;) {
+    Tok name = lx.next();
+    if (name.k == Tok::END) { if (top_level) return; throw std::runtime_error("prototxt: missing '}'"); }
+    if (name.k == Tok::RBRACE) { if (top_level) throw std::runtime_error("prototxt: stray '}'"); return; }
+    if (name.k != Tok::IDENT) throw std::runtime_error("prototxt: expected a field name, got '" + name.s + "'");
+    Tok t = lx.next();
+    if (t.k == Tok::COLON) {
+      Tok v = lx.next();
+      if (v.k == Tok::LBRACE) field(name.s, nullptr, lx);
+      else field(name.s, &v, lx);
+    } else if (t.k == Tok::LBRACE) {
+      field(name.s, nullptr, lx);
+    } else {
+      throw std::runtime_error("prototxt: expected ':' or '{' after '" + name.s + "'");
+    }
+  }
+}
+void skip_message(Lexer& lx) {
+  parse_message(lx, false, [](const std::string&, const Tok* v, Lexer& l) { if (!v) skip_message(l); });
+}
+}  // namespace
+
+LayerParameter ParseLayerPrototxt(const std::string& text) {
+  LayerParameter p;
+  Lexer lx(text);
+  bool seen_layer = false, seen_mode = false;
+  auto layer_fields = [&](const std::string& n, const Tok* v, Lexer& l) {
+    if (n == "name") p.name_ = to_str(*v, n);
+    else if (n == "type") p.type_ = to_str(*v, n);
+    else if (n == "top") p.top_.push_back(to_str(*v, n));
+    else if (n == "bottom") p.bottom_.push_back(to_str(*v, n));
+    else if (n == "data_param") {
+      if (v) throw std::runtime_error("prototxt: data_param is a message");
+      parse_message(l, false, [&](const std::string& f, const Tok* fv, Lexer&) {
+        if (!fv) throw std::runtime_error("prototxt: unexpected message '" + f + "' in data_param");
+        if (f == "batch_size") p.data_param_.batch_size_ = to_int(*fv, f);
+        else if (f == "prefetch") p.data_param_.prefetch_ = to_int(*fv, f);
+        else if (f == "block_size") p.data_param_.block_size_ = to_int(*fv, f);
+        else if (f == "verbose") p.data_param_.verbose_ = to_bool(*fv, f);
+        else if (f == "sample") p.data_param_.sample_.push_back(fv->s);
+        else throw std::runtime_error("prototxt: unknown data_param field '" + f + "'");
+      });
+    } else if (n == "data_generation_param") {
+      if (v) throw std::runtime_error("prototxt: data_generation_param is a message");
+      parse_message(l, false, [&](const std::string& f, const Tok* fv, Lexer&) {
+        if (!fv) throw std::runtime_error("prototxt: unexpected message '" + f + "' in data_generation_param");
+        DataGenerationParameter& g = p.data_generation_param_;
+        if (f == "mode") { g.mode_ = to_int(*fv, f); seen_mode = true; }
+        else if (f == "texture_dbases") g.texture_dbases_.push_back(to_str(*fv, f));
+        else if (f == "first_level_threads") g.first_level_threads_ = to_int(*fv, f);
+        else if (f == "second_level_threads") g.second_level_threads_ = to_int(*fv, f);
+        else if (f == "use_antialiasing") g.use_antialiasing_ = to_bool(*fv, f);
+        else throw std::runtime_error("prototxt: unknown data_generation_param field '" + f + "'");
+      });
+    } else if (n == "include" || n == "exclude" || n == "phase") {
+      if (!v) skip_message(l);  // net-level plumbing, irrelevant to the layer itself
+    } else {
+      throw std::runtime_error("prototxt: unknown layer field '" + n + "'");
+    }
+  };
+  parse_message(lx, true, [&](const std::string& n, const Tok* v, Lexer& l) {
+    if (n != "layer" && n != "layers") throw std::runtime_error("prototxt: expected a 'layer { ... }' block, got '" + n + "'");
+    if (v) throw std::runtime_error("prototxt: 'layer' is a message");
+    if (seen_layer) throw std::runtime_error("prototxt: more than one layer block");
+    seen_layer = true;
+    parse_message(l, false, layer_fields);
+  });
+  if (!seen_layer) throw std::runtime_error("prototxt: no layer block found");
+  (void)seen_mode;  // `required` in the .proto but carries a default; protobuf text format would insist, Caffe users rely on the default
+  return p;
+}
+
+// ---- DataGenerationLayer ----------------------------------------------------------------------------------
+#define OFDG_CHECK(expr)                                                                 \
+  do {                                                                                   \
+    if ((expr) != OFDG_OK) throw std::runtime_error(std::string(ofdg_last_error()));     \
+  } while (0)
+
+template <typename Dtype>
+int DataGenerationLayer<Dtype>::solver_rank_ = 0;
+
+namespace {
+// Loads a texture list: one binary PPM (P6, maxval 255) path per line, like the reference's
+// TextureCollection ctor (DataGenerator.cpp:117-149) including its R<->B swap. Other image formats
+// need an image decoder the reference gets from CImg; they are rejected with a clear message.
+void load_ppm_list(const std::string& listfile, std::vector<unsigned char>& planar, int& n, int& w, int& h) {
+  std::ifstream infile(listfile);
+  if (infile.bad() || !infile.is_open()) throw std::runtime_error("Could not open texture collection");  // DataGenerator.cpp:121
+  std::string path;
+  n = 0; w = h = 0;
+  while (std::getline(infile, path)) {
+    if (path.empty()) continue;
+    std::ifstream f(path, std::ios::binary);
+    if (!f.is_open()) throw std::runtime_error("Could not open texture " + path);
+    std::string magic;
+    f >> magic;
+    if (magic != "P6") throw std::runtime_error("texture " + path + ": only binary PPM (P6) textures can be decoded without CImg");
+    auto next_int = [&]() {
+      for (;;) {
+        int c = f.peek();
+        if (c == '#') { std::string skip; std::getline(f, skip); }
+        else if (std::isspace(c)) f.get();
+        else break;
+      }
+      int v; f >> v; return v;
+    };
+    int tw = next_int(), th = next_int(), maxv = next_int();
+    f.get();
+    if (maxv != 255) throw std::runtime_error("texture " + path + ": maxval must be 255");
+    if (n == 0) { w = tw; h = th; }
+    else if (tw != w || th != h) throw std::runtime_error("texture " + path + ": all pool textures must share one size");
+    std::vector<unsigned char> rgb((size_t)tw * th * 3);
+    f.read((char*)rgb.data(), rgb.size());
+    if (!f) throw std::runtime_error("texture " + path + ": truncated file");
+    const size_t plane = (size_t)tw * th;
+    planar.resize((size_t)(n + 1) * 3 * plane);
+    unsigned char* dst = planar.data() + (size_t)n * 3 * plane;
+    for (size_t i = 0; i < plane; ++i) {
+      dst[0 * plane + i] = rgb[3 * i + 2];  // std::swap(c0, c2): the reference holds textures as B,G,R planes
+      dst[1 * plane + i] = rgb[3 * i + 1];
+      dst[2 * plane + i] = rgb[3 * i + 0];
+    }
+    ++n;
+  }
+  if (n == 0) throw std::runtime_error("texture collection is empty");
+}
+}  // namespace
+
+template <typename Dtype>
+DataGenerationLayer<Dtype>::DataGenerationLayer(const LayerParameter& param) : Layer<Dtype>(param) {
+  const DataGenerationParameter& gp = param.data_generation_param();
+  if (param.data_param().batch_size() <= 0) throw std::runtime_error("data_param.batch_size must be positive");
+  if (gp.texture_dbases_size() < 1) throw std::runtime_error("data_generation_param.texture_dbases(0) is required");  // DataGenerator.cpp:992
+  prefetch_depth_ = (size_t)std::max(1, std::min(param.data_param().prefetch(), 64));
+  SHIM_CUDA(cudaGetDevice(&device_));
+  ofdg_config cfg{};
+  cfg.device = device_;
+  cfg.width = 512; cfg.height = 384;  // DGEN_WIDTH / DGEN_HEIGHT, DataGenerator.h:55-56
+  cfg.mode = gp.mode();
+  cfg.use_antialiasing = gp.use_antialiasing() ? 1 : 0;
+  cfg.max_batch = param.data_param().batch_size();
+  OFDG_CHECK(ofdg_create(&cfg, &generator_));
+  const std::string& db = gp.texture_dbases(0);
+  if (db.compare(0, 10, "synthetic:") == 0) {  // "synthetic:<count>[:<seed>]": procedural pool generated on the device
+    int count = 0; unsigned long long seed = 0;
+    if (std::sscanf(db.c_str() + 10, "%d:%llu", &count, &seed) < 1 || count <= 0) throw std::runtime_error("bad synthetic texture spec: " + db);
+    OFDG_CHECK(ofdg_synth_textures(generator_, count, 2 * cfg.width, 2 * cfg.height, seed));
+  } else {
+    std::vector<unsigned char> planar;
+    int n, w, h;
+    load_ppm_list(db, planar, n, w, h);
+    OFDG_CHECK(ofdg_upload_textures(generator_, planar.data(), n, w, h));
+  }
+  OFDG_CHECK(ofdg_params_create(gp.mode(), cfg.width, cfg.height, 45 * solver_rank_, 0, 0, &params_));
+  OFDG_CHECK(ofdg_tasks_create(&tasks_));
+}
+
+template <typename Dtype>
+DataGenerationLayer<Dtype>::~DataGenerationLayer() {
+  StopInternalThread();
+  for (ofdg_prepared* p : prefetch_full_) ofdg_prepared_destroy(p);
+  if (tasks_) ofdg_tasks_destroy(tasks_);
+  if (params_) ofdg_params_destroy(params_);
+  if (generator_) ofdg_destroy(generator_);
+}
+
+template <typename Dtype>
+void DataGenerationLayer<Dtype>::LayerSetUp(const std::vector<Blob<Dtype>*>& bottom, const std::vector<Blob<Dtype>*>& top) {
+  if (!bottom.empty()) throw std::runtime_error("DataGeneration takes no bottom blobs");
+  if (top.size() < 3) throw std::runtime_error("DataGeneration needs 3 top blobs (first image, second image, flow)");  // the reference indexes top[0..2]
+  const int batch_size = this->layer_param_.data_param().batch_size();
+  StartInternalThread();
+  top[0]->Reshape({batch_size, 3, 384, 512});  // data_generation_layer.cpp:128-130
+  top[1]->Reshape({batch_size, 3, 384, 512});
+  top[2]->Reshape({batch_size, 2, 384, 512});
+}
+
+template <typename Dtype>
+void DataGenerationLayer<Dtype>::StartInternalThread() {
+  if (thread_.joinable()) return;
+  must_stop_ = false;
+  thread_ = std::thread([this] { this->InternalThreadEntry(); });
+}
+template <typename Dtype>
+void DataGenerationLayer<Dtype>::StopInternalThread() {
+  {
+    std::lock_guard<std::mutex> l(mutex_);
+    must_stop_ = true;
+  }
+  cv_free_.notify_all();
+  cv_full_.notify_all();
+  if (thread_.joinable()) thread_.join();
+}
+
+// Draws batch_size tasks in commission order, flattens them and uploads the scene (load_batch,
+// data_generation_layer.cpp:183-216; the retrieval half of the reference's load_batch is now the
+// kernel launch in Forward).
+template <typename Dtype>
+void DataGenerationLayer<Dtype>::load_batch(ofdg_prepared** out) {
+  const int batch_size = this->layer_param_.data_param().batch_size();
+  std::lock_guard<std::mutex> g(generator_mutex_);
+  ofdg_tasks_clear(tasks_);
+  OFDG_CHECK(ofdg_params_generate(params_, batch_size, tasks_));
+  ofdg_task_batch view;
+  OFDG_CHECK(ofdg_tasks_view(tasks_, &view));
+  OFDG_CHECK(ofdg_prepare(generator_, &view, out));
+}
+
+template <typename Dtype>
+void DataGenerationLayer<Dtype>::InternalThreadEntry() {
+  cudaSetDevice(device_);
+  try {
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> l(mutex_);
+        cv_free_.wait(l, [this] { return must_stop_ || prefetch_full_.size() < prefetch_depth_; });
+        if (must_stop_) return;
+      }
+      ofdg_prepared* p = nullptr;
+      load_batch(&p);
+      {
+        std::lock_guard<std::mutex> l(mutex_);
+        prefetch_full_.push_back(p);
+      }
+      cv_full_.notify_one();
+    }
+  } catch (const std::exception& e) {
+    std::lock_guard<std::mutex> l(mutex_);
+    producer_error_ = e.what();
+    cv_full_.notify_all();
+  }
+}
+
+template <typename Dtype>
+void DataGenerationLayer<Dtype>::Forward_gpu(const std::vector<Blob<Dtype>*>& bottom, const std::vector<Blob<Dtype>*>& top) {
+  ofdg_prepared* p = nullptr;
+  {
+    std::unique_lock<std::mutex> l(mutex_);  // prefetch_full_.pop("Data layer prefetch queue empty")
+    cv_full_.wait(l, [this] { return !prefetch_full_.empty() || !producer_error_.empty() || must_stop_; });
+    if (!producer_error_.empty()) throw std::runtime_error(producer_error_);
+    if (prefetch_full_.empty()) throw std::runtime_error("Data layer prefetch queue empty");
+    p = prefetch_full_.front();
+    prefetch_full_.pop_front();
+  }
+  cv_free_.notify_one();
+  const int batch_size = this->layer_param_.data_param().batch_size();
+  top[0]->Reshape({batch_size, 3, 384, 512});
+  top[1]->Reshape({batch_size, 3, 384, 512});
+  top[2]->Reshape({batch_size, 2, 384, 512});
+  int rc;
+  {
+    std::lock_guard<std::mutex> g(generator_mutex_);
+    rc = ofdg_render_prepared(generator_, p, top[0]->mutable_gpu_data(), top[1]->mutable_gpu_data(), top[2]->mutable_gpu_data(), nullptr);
+  }
+  ofdg_prepared_destroy(p);
+  if (rc != OFDG_OK) throw std::runtime_error(ofdg_last_error());
+}
+
+template <typename Dtype>
+void DataGenerationLayer<Dtype>::Forward_cpu(const std::vector<Blob<Dtype>*>& bottom, const std::vector<Blob<Dtype>*>& top) {
+  // There is no CPU generator any more: the blobs are produced on the device and become visible to
+  // cpu_data() through the usual synced-memory copy.
+  Forward_gpu(bottom, top);
+  for (size_t i = 0; i < 3; ++i) top[i]->cpu_data();
+}
+
+template <typename Dtype>
+uint64_t DataGenerationLayer<Dtype>::tasks_commissioned() const { return ofdg_params_tasks_generated(params_); }
+
+template class DataGenerationLayer<float>;
+
+}  // namespace caffe
+
+// ---- C wrappers so the layer can be driven through the C ABI (tests, foreign hosts) --------------------
+namespace {
+thread_local std::string g_layer_error;
+struct LayerBox {
+  std::unique_ptr<caffe::DataGenerationLayer<float>> layer;
+  std::vector<std::unique_ptr<caffe::Blob<float>>> tops;
+  std::vector<caffe::Blob<float>*> top_ptrs, bottom_ptrs;
+  caffe::LayerParameter param;
+};
+template <class F>
+int layer_guard(F&& f) {
+  try { f(); return 0; } catch (const std::exception& e) { g_layer_error = e.what(); return 1; }
+}
+}  // namespace
+
+extern "C" {
+const char* ofdg_layer_last_error(void) { return g_layer_error.c_str(); }
+
+int ofdg_layer_parse_prototxt(const char* text, int32_t* ints /*[7]: batch,prefetch,mode,first,second,aa,n_top*/, char* texture_db, int32_t cap,
+                              char* type, int32_t type_cap) {
+  return layer_guard([&] {
+    caffe::LayerParameter p = caffe::ParseLayerPrototxt(text);
+    ints[0] = p.data_param().batch_size(); ints[1] = p.data_param().prefetch();
+    ints[2] = p.data_generation_param().mode(); ints[3] = p.data_generation_param().first_level_threads();
+    ints[4] = p.data_generation_param().second_level_threads(); ints[5] = p.data_generation_param().use_antialiasing();
+    ints[6] = p.top_size();
+    std::string db = p.data_generation_param().texture_dbases_size() ? p.data_generation_param().texture_dbases(0) : "";
+    std::snprintf(texture_db, cap, "%s", db.c_str());
+    std::snprintf(type, type_cap, "%s", p.type().c_str());
+  });
+}
+
+int ofdg_layer_create(const char* prototxt, const char* texture_db_override, int32_t solver_rank, void** out) {
+  return layer_guard([&] {
+    std::unique_ptr<LayerBox> b(new LayerBox);
+    b->param = caffe::ParseLayerPrototxt(prototxt);
+    if (b->param.type() != "DataGeneration") throw std::runtime_error("layer type must be \"DataGeneration\"");
+    if (texture_db_override && *texture_db_override) b->param.data_generation_param_.texture_dbases_ = {texture_db_override};
+    caffe::DataGenerationLayer<float>::set_solver_rank(solver_rank);
+    b->layer.reset(new caffe::DataGenerationLayer<float>(b->param));
+    for (int i = 0; i < std::max(3, b->param.top_size()); ++i) {
+      b->tops.emplace_back(new caffe::Blob<float>());
+      b->top_ptrs.push_back(b->tops.back().get());
+    }
+    *out = b.release();
+  });
+}
+void ofdg_layer_destroy(void* l) { delete (LayerBox*)l; }
+int ofdg_layer_setup(void* l) {
+  return layer_guard([&] { LayerBox* b = (LayerBox*)l; b->layer->SetUp(b->bottom_ptrs, b->top_ptrs); });
+}
+int ofdg_layer_top_shape(void* l, int32_t i, int32_t* shape4) {
+  return layer_guard([&] {
+    LayerBox* b = (LayerBox*)l;
+    const std::vector<int>& s = b->top_ptrs.at(i)->shape();
+    for (int k = 0; k < 4; ++k) shape4[k] = k < (int)s.size() ? s[k] : 0;
+  });
+}
+int ofdg_layer_forward(void* l, int32_t gpu) {
+  return layer_guard([&] {
+    LayerBox* b = (LayerBox*)l;
+    if (gpu) b->layer->Forward_gpu(b->bottom_ptrs, b->top_ptrs); else b->layer->Forward_cpu(b->bottom_ptrs, b->top_ptrs);
+  });
+}
+const float* ofdg_layer_top_data(void* l, int32_t i, int32_t gpu) {
+  LayerBox* b = (LayerBox*)l;
+  try { return gpu ? b->top_ptrs.at(i)->gpu_data() : b->top_ptrs.at(i)->cpu_data(); } catch (const std::exception& e) { g_layer_error = e.what(); return nullptr; }
+}
+const char* ofdg_layer_type(void* l) { return ((LayerBox*)l)->layer->type(); }
+}

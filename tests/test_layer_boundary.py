@@ -1,0 +1,74 @@
+"""Caffe-layer boundary: prototxt parsing (the reference's example file verbatim), blob contract."""
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_reference_example_prototxt_parses_verbatim(ofdg):
+    text = open(os.path.join(GOLDEN, "train.prototxt")).read()  # copy of example-prototxt/train.prototxt
+    p = ofdg.parse_prototxt(text)
+    assert p == {"batch_size": 8, "prefetch": 40, "mode": 7, "first_level_threads": 8, "second_level_threads": 3,
+                 "use_antialiasing": True, "top_size": 3, "type": "DataGeneration",
+                 "texture_dbases": "/misc/lmbraid18/mayern/CLUSTER/resources/random-textures-1000/database.txt"}
+
+
+def test_prototxt_defaults_and_errors(ofdg):
+    p = ofdg.parse_prototxt('layer { type: "DataGeneration" top: "a" data_param { batch_size: 2 } data_generation_param { texture_dbases: "x" } }')
+    assert p["mode"] == 1 and p["first_level_threads"] == 16 and p["second_level_threads"] == 1 and p["use_antialiasing"] is True
+    with pytest.raises(ofdg.OfdgError, match="unknown"):
+        ofdg.parse_prototxt('layer { type: "DataGeneration" data_generation_param { modee: 3 } }')
+    with pytest.raises(ofdg.OfdgError):
+        ofdg.parse_prototxt('layer { type: "DataGeneration" ')
+    with pytest.raises(ofdg.OfdgError, match="DataGeneration"):
+        ofdg.DataGenerationLayer('layer { type: "Data" top: "a" }')
+
+
+@pytest.mark.gpu
+def test_layer_blob_contract(ofdg, oracle):
+    import torch
+    text = open(os.path.join(GOLDEN, "train.prototxt")).read()
+    layer = ofdg.DataGenerationLayer(text, texture_db="synthetic:8:1")
+    assert layer.type() == "DataGeneration"
+    layer.LayerSetUp()
+    assert layer.top_shape(0) == (8, 3, 384, 512) and layer.top_shape(1) == (8, 3, 384, 512) and layer.top_shape(2) == (8, 2, 384, 512)
+    tex = ofdg.synth_textures(8, 1024, 768, seed=1)
+    ps = ofdg.ParamStream(7)
+    for it in range(3):  # consecutive batches follow the commission order of the parameter stream
+        if it % 2:
+            layer.Forward_cpu()
+        else:
+            layer.Forward_gpu()
+        got = [layer.top_cpu(i) for i in range(3)]
+        tasks = ps.generate(8)
+        ref = oracle.render(tasks.struct(), tex, mode=7)
+        assert np.abs(got[0] - ref["img0"]).max() <= 1 and np.abs(got[1] - ref["img1"]).max() <= 1
+        assert np.abs(got[2] - ref["flow"]).max() <= 1e-3
+        assert got[0].min() >= 0 and got[0].max() <= 255 and got[0].dtype == np.float32
+    layer.close()
+
+
+@pytest.mark.gpu
+def test_layer_ppm_texture_list(ofdg, oracle, tmp_path):
+    """texture_dbases as a list file of PPM images, with the reference's R<->B swap."""
+    rng = np.random.default_rng(0)
+    tex_rgb = ofdg.synth_textures(2, 1024, 768, seed=9)  # treat planes as R,G,B on disk
+    lines = []
+    for i in range(2):
+        path = tmp_path / f"t{i}.ppm"
+        with open(path, "wb") as f:
+            f.write(b"P6\n# comment\n1024 768\n255\n")
+            f.write(np.ascontiguousarray(tex_rgb[i].transpose(1, 2, 0)).tobytes())
+        lines.append(str(path))
+    (tmp_path / "db.txt").write_text("\n".join(lines) + "\n")
+    layer = ofdg.DataGenerationLayer('layer { type: "DataGeneration" top: "a" top: "b" top: "c" data_param { batch_size: 2 prefetch: 2 } '
+                                     'data_generation_param { mode: 5 texture_dbases: "%s" } }' % (tmp_path / "db.txt"))
+    layer.LayerSetUp()
+    layer.Forward_gpu()
+    got = [layer.top_cpu(i) for i in range(3)]
+    tasks = ofdg.ParamStream(5).generate(2)
+    ref = oracle.render(tasks.struct(), tex_rgb[:, ::-1].copy(), mode=5)  # planes held as B,G,R
+    assert np.abs(got[0] - ref["img0"]).max() <= 1 and np.abs(got[1] - ref["img1"]).max() <= 1
+    layer.close()
