@@ -1,7 +1,9 @@
 // C-ABI implementation (include/ofdg/ofdg.h): handle management, uploads, launches.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -90,9 +92,9 @@ struct PinnedBuf {
 
 // A flattened batch resident on the device.
 struct DeviceScene {
-  DevBuf samples, objects, shapes, verts;
-  int batch = 0;
-  void release() { samples.release(); objects.release(); shapes.release(); verts.release(); }
+  DevBuf samples, objects, shapes, verts, deform_shape, deform_field;
+  int batch = 0, n_deform = 0;
+  void release() { samples.release(); objects.release(); shapes.release(); verts.release(); deform_shape.release(); deform_field.release(); }
 };
 
 }  // namespace
@@ -119,8 +121,9 @@ struct ofdg_generator {
   DevBuf pool;
   int n_tex = 0, tex_w = 0, tex_h = 0;
   // mode 9 fields
-  DevBuf fields;
+  DevBuf fields, fpos_x, falpha_x, fpos_y, falpha_y, mask_raw, mask_warp;
   int n_fields = 0;
+  std::vector<int> field_reach;
   // per-call scene staging + scratch
   DeviceScene scene;
   PinnedBuf staging;
@@ -160,7 +163,15 @@ void upload_scene(ofdg_generator* g, const ofdg::FlatBatch& fb, DeviceScene& ds,
   if (b2) CK(cudaMemcpyAsync(ds.shapes.p, st + o2, b2, cudaMemcpyHostToDevice, s));
   if (b3) CK(cudaMemcpyAsync(ds.verts.p, st + o3, b3, cudaMemcpyHostToDevice, s));
   ds.batch = (int)fb.samples.size();
-  g->last_upload_bytes = b0 + b1 + b2 + b3;
+  ds.n_deform = (int)fb.deform_shape.size();
+  if (ds.n_deform) {  // mode 9 only; small, pageable copies are fine here
+    const size_t bd = (size_t)ds.n_deform * sizeof(int32_t);
+    ds.deform_shape.reserve(bd); ds.deform_field.reserve(bd);
+    CK(cudaMemcpyAsync(ds.deform_shape.p, fb.deform_shape.data(), bd, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ds.deform_field.p, fb.deform_field.data(), bd, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  g->last_upload_bytes = b0 + b1 + b2 + b3 + 2 * (size_t)ds.n_deform * sizeof(int32_t);
 }
 
 void flatten_tasks(ofdg_generator* g, const ofdg_task_batch* tasks) {
@@ -168,6 +179,8 @@ void flatten_tasks(ofdg_generator* g, const ofdg_task_batch* tasks) {
   fc.W = g->cfg.width; fc.H = g->cfg.height;
   fc.tex_w = g->tex_w; fc.tex_h = g->tex_h; fc.n_tex = g->n_tex;
   fc.mode = g->cfg.mode;
+  fc.n_fields = g->n_fields;
+  fc.field_reach = g->field_reach.empty() ? nullptr : g->field_reach.data();
   g->flat.clear();
   ofdg::flatten(*tasks, fc, g->flat);
 }
@@ -197,6 +210,18 @@ ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, 
   a.pos_y = (int*)g->pos_y.p; a.alpha_y = (double*)g->alpha_y.p;
   a.fields = (const float*)g->fields.p;
   a.n_fields = g->n_fields;
+  a.n_deform = ds.n_deform;
+  if (ds.n_deform) {
+    const size_t P = (size_t)g->cfg.width * g->cfg.height;
+    g->mask_raw.reserve((size_t)ds.n_deform * 2 * P);
+    g->mask_warp.reserve((size_t)ds.n_deform * 2 * P);
+  }
+  a.deform_shape = (const int*)ds.deform_shape.p;
+  a.deform_field = (const int*)ds.deform_field.p;
+  a.mask_raw = (uint8_t*)g->mask_raw.p;
+  a.mask_warp = (uint8_t*)g->mask_warp.p;
+  a.fpos_x = (const int*)g->fpos_x.p; a.falpha_x = (const double*)g->falpha_x.p;
+  a.fpos_y = (const int*)g->fpos_y.p; a.falpha_y = (const double*)g->falpha_y.p;
   a.img0 = d0; a.img1 = d1; a.flow = df;
   return a;
 }
@@ -211,6 +236,7 @@ void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s) {
   cudaEvent_t e0 = g->evs[g->ev_used], e1 = g->evs[g->ev_used + 1], e2 = g->evs[g->ev_used + 2];
   g->ev_used += 3;
   CK(cudaEventRecord(e0, s));
+  g->launches += ofdg::launch_deform_prepass(a, s);
   g->launches += ofdg::launch_background_prep(a, s);
   CK(cudaEventRecord(e1, s));
   g->launches += ofdg::launch_render(a, s);
@@ -364,7 +390,7 @@ void ofdg_destroy(ofdg_generator* g) {
   if (!g) return;
   cudaSetDevice(g->cfg.device);
   if (g->stream) cudaStreamSynchronize(g->stream);
-  DevBuf* bufs[] = {&g->pool, &g->fields, &g->bg, &g->pos_x, &g->alpha_x, &g->pos_y, &g->alpha_y, &g->out0, &g->out1,
+  DevBuf* bufs[] = {&g->pool, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->bg, &g->pos_x, &g->alpha_x, &g->pos_y, &g->alpha_y, &g->out0, &g->out1,
                     &g->outf, &g->dbg_masks, &g->dbg_id0, &g->dbg_id1, &g->dbg_frames8, &g->dbg_planar};
   for (DevBuf* b : bufs) b->release();
   g->scene.release();
@@ -435,6 +461,40 @@ int ofdg_set_fields(ofdg_generator* g, const float* fields, int32_t n) {
     g->fields.reserve(per * n);
     CK(cudaMemcpy(g->fields.p, fields, per * n, cudaMemcpyHostToDevice));
     g->n_fields = n;
+    // how far the inverse field can move a mask: widens the frame-1 boxes of warped outlines
+    const size_t plane2 = (size_t)2 * (g->cfg.height + 1) * (g->cfg.width + 1);
+    g->field_reach.assign(n, 0);
+    for (int i = 0; i < n; ++i) {
+      const float* ifl = fields + ((size_t)i * 2 + 1) * plane2;
+      float mx = 0.f;
+      for (size_t k = 0; k < plane2; ++k)
+        if (std::isfinite(ifl[k])) mx = std::max(mx, std::fabs(ifl[k]));
+      g->field_reach[i] = (int)std::ceil(std::min(mx, 1.0e6f));
+    }
+    // CImg linear-resize tables (W+1 -> 2W, H+1 -> 2H) used when the background carries a field
+    auto table = [](int len, int nout, std::vector<int>& pos, std::vector<double>& alpha) {
+      pos.resize(nout); alpha.resize(nout);
+      const double f = nout > 1 ? (len - 1.0) / (nout - 1) : 0;
+      double curr = 0, old = 0;
+      unsigned q = 0;
+      for (int i2 = 0; i2 < nout; ++i2) {
+        alpha[i2] = curr - (unsigned int)curr;
+        pos[i2] = (int)q;
+        old = curr;
+        curr = std::min(len - 1.0, curr + f);
+        q += (unsigned int)curr - (unsigned int)old;
+      }
+    };
+    std::vector<int> px, py;
+    std::vector<double> ax, ay;
+    table(g->cfg.width + 1, 2 * g->cfg.width, px, ax);
+    table(g->cfg.height + 1, 2 * g->cfg.height, py, ay);
+    g->fpos_x.reserve(px.size() * sizeof(int)); g->falpha_x.reserve(ax.size() * sizeof(double));
+    g->fpos_y.reserve(py.size() * sizeof(int)); g->falpha_y.reserve(ay.size() * sizeof(double));
+    CK(cudaMemcpy(g->fpos_x.p, px.data(), px.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(g->falpha_x.p, ax.data(), ax.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(g->fpos_y.p, py.data(), py.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(g->falpha_y.p, ay.data(), ay.size() * sizeof(double), cudaMemcpyHostToDevice));
   });
 }
 

@@ -15,7 +15,8 @@ struct FlatShape {
   int32_t vcount[2];
   int32_t bbox[2][4];   // [frame] {x0, y0, x1, y1} inclusive pixel range that can hold cells
   int32_t additive;     // composite op: 1 = add, 0 = subtract (DataGenerator.cpp:602-642)
-  int32_t pad;
+  int32_t deform;       // mode 9: slot of this outline's warped frame-1 masks in the deformation scratch, else -1
+  int32_t raw1[4];      // mode 9: frame-1 box before it was widened by the field's reach (what the pre-pass rasterises)
 };
 
 // One top-level foreground object, in z-order within its sample.

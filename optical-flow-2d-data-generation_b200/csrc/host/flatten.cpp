@@ -166,7 +166,7 @@ void prepare_background(const ofdg_blueprint& b, const FlattenConfig& cfg, const
 
 // One outline of blueprint `b` (an ellipse or a polygon), both frames.
 void realize_shape(const ofdg_task_batch& tb, const ofdg_blueprint& b, const Affine& bg_n,
-                   FlatBatch& out, Affine* motion_out) {
+                   FlatBatch& out, Affine* motion_out, int field, int reach) {
   Affine I = intrinsic_of(b.init_rot, b.init_trans_x, b.init_trans_y);
   Affine M = motion_of(b);
   M.then(bg_n);  // addBackgroundMotion, DG.cpp:324-335
@@ -193,6 +193,16 @@ void realize_shape(const ofdg_task_batch& tb, const ofdg_blueprint& b, const Aff
     }
     s.vcount[f] = (int32_t)out.verts.size() - s.vbegin[f];
     bbox_of(out.verts.data() + s.vbegin[f], s.vcount[f], s.bbox[f]);
+  }
+  s.deform = -1;
+  for (int i = 0; i < 4; ++i) s.raw1[i] = s.bbox[1][i];
+  if (field >= 0) {
+    // MovingObjectBase::renderMasks warps this outline's frame-1 masks by the inverse field (DG.cpp:370-386):
+    // out(x,y) = in((x,y) + iflow(x,y)) can be non-zero up to `reach` pixels away from the outline.
+    s.deform = (int32_t)out.deform_shape.size();
+    out.deform_shape.push_back((int32_t)out.shapes.size());
+    out.deform_field.push_back(field);
+    s.bbox[1][0] -= reach + 2; s.bbox[1][1] -= reach + 2; s.bbox[1][2] += reach + 2; s.bbox[1][3] += reach + 2;
   }
   out.shapes.push_back(s);
 }
@@ -270,6 +280,7 @@ void flatten(const ofdg_task_batch& tb, const FlattenConfig& cfg, FlatBatch& out
     bgM.store(smp.bg_motion);
     const bool bg_deformed = (cfg.mode == 9 && bg.do_warpfield_deformation && bg.field_id >= 0);
     smp.bg_field = bg_deformed ? bg.field_id : -1;
+    if (smp.bg_field >= cfg.n_fields) throw std::runtime_error("background refers to a warp field that was not injected (ofdg_set_fields)");
     prepare_background(bg, cfg, tex_inv, bg_deformed, smp.prep);
 
     // addBackgroundMotion's bracket T(-W/2,-H/2) * M_bg * T(W/2,H/2), DG.cpp:327-329
@@ -285,6 +296,8 @@ void flatten(const ofdg_task_batch& tb, const FlattenConfig& cfg, FlatBatch& out
       o.obj_id = b.obj_id;
       o.tex = (int32_t)((unsigned)b.tex_id % (unsigned)cfg.n_tex);
       o.field = (cfg.mode == 9 && b.do_warpfield_deformation && b.field_id >= 0) ? b.field_id : -1;
+      if (o.field >= cfg.n_fields) throw std::runtime_error("blueprint refers to a warp field that was not injected (ofdg_set_fields)");
+      const int reach = (o.field >= 0 && cfg.field_reach) ? cfg.field_reach[o.field] : 0;
       o.shape_begin = (int32_t)out.shapes.size();
       Affine M;
       if (b.obj_type == OFDG_OBJ_COMPOSITE) {
@@ -293,13 +306,14 @@ void flatten(const ofdg_task_batch& tb, const FlattenConfig& cfg, FlatBatch& out
           throw std::runtime_error("composite blueprint with a bad component range");
         for (int ci = 0; ci < b.comp_count; ++ci) {
           const ofdg_blueprint& c = tb.blueprints[b.comp_begin + ci];
-          realize_shape(tb, c, bg_n, out, nullptr);
+          // components carry the parent's field (DG.cpp:1157-1163)
+          realize_shape(tb, c, bg_n, out, nullptr, o.field, reach);
         }
         // the composite's own motion drives its texture and flow (DG.cpp:1151-1155)
         M = motion_of(b);
         M.then(bg_n);
       } else {
-        realize_shape(tb, b, bg_n, out, &M);
+        realize_shape(tb, b, bg_n, out, &M, o.field, reach);
       }
       o.shape_count = (int32_t)out.shapes.size() - o.shape_begin;
       M.store(o.motion);

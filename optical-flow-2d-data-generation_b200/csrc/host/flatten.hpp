@@ -20,7 +20,9 @@ struct FlatBatch {
   std::vector<FlatObject> objects;
   std::vector<FlatShape> shapes;
   std::vector<FlatVertex> verts;
-  void clear() { samples.clear(); objects.clear(); shapes.clear(); verts.clear(); }
+  // mode 9: per deformation-scratch slot, the outline it belongs to and the field that warps it
+  std::vector<int32_t> deform_shape, deform_field;
+  void clear() { samples.clear(); objects.clear(); shapes.clear(); verts.clear(); deform_shape.clear(); deform_field.clear(); }
 };
 
 struct FlattenConfig {
@@ -28,6 +30,8 @@ struct FlattenConfig {
   int tex_w = 0, tex_h = 0;  // pool texture size
   int n_tex = 0;             // pool size
   int mode = 1;              // only mode 9 attaches warp fields
+  int n_fields = 0;          // injected field pool
+  const int* field_reach = nullptr;  // per field: ceil(max |iflow|) over finite entries (how far a warped mask can move)
 };
 
 // Appends the flattened form of every task in `tb` to `out`.

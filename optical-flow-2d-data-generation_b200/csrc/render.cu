@@ -121,6 +121,68 @@ __device__ __forceinline__ uint32_t blend_rgbx(uint32_t f, uint32_t t, unsigned 
   return out;
 }
 
+// ------------------------------------------------------------------------------------------------
+// mode 9: non-rigid warp fields (consumer side, DG.cpp:237-252, 370-386, 403-406, 714-717)
+// ------------------------------------------------------------------------------------------------
+// CImg linear_atXY(fx, fy, z, c, out_value = 0) tap coordinates: x = (int)fx - (fx >= 0 ? 0 : 1) (not a
+// true floor for negative integers -- kept). Returns false when every tap is out of range anyway
+// (NaN / huge coordinates; the reference then produces NaN or 0, both of which store 0).
+__device__ __forceinline__ bool dirichlet_setup(float fx, float fy, int& ix, int& iy, float& dx, float& dy) {
+  if (!(fabsf(fx) < 1.0e9f) || !(fabsf(fy) < 1.0e9f)) return false;
+  ix = (int)fx - (fx >= 0 ? 0 : 1);
+  iy = (int)fy - (fy >= 0 ? 0 : 1);
+  dx = fx - ix;
+  dy = fy - iy;
+  return true;
+}
+__device__ __forceinline__ float cimg_lerp2(float Icc, float Inc, float Icn, float Inn, float dx, float dy) {
+  return Icc + dx * (Inc - Icc + dy * (Icc + Inn - Icn - Inc)) + dy * (Icn - Icc);
+}
+__device__ __forceinline__ unsigned dirichlet_u8(const uint8_t* img, int w, int h, float fx, float fy) {
+  int ix, iy;
+  float dx, dy;
+  if (!dirichlet_setup(fx, fy, ix, iy, dx, dy)) return 0u;
+  auto tap = [&](int x, int y) -> float { return (x < 0 || y < 0 || x >= w || y >= h) ? 0.f : (float)img[(size_t)y * w + x]; };
+  const float v = cimg_lerp2(tap(ix, iy), tap(ix + 1, iy), tap(ix, iy + 1), tap(ix + 1, iy + 1), dx, dy);
+  return (unsigned)(unsigned char)v;
+}
+// Same interpolation over three packed channels; taps come from a callable (px, py) -> RGBX, 0 outside.
+template <class Tap>
+__device__ __forceinline__ uint32_t dirichlet_rgbx(Tap tap, float fx, float fy) {
+  int ix, iy;
+  float dx, dy;
+  if (!dirichlet_setup(fx, fy, ix, iy, dx, dy)) return 0u;
+  const uint32_t pcc = tap(ix, iy), pnc = tap(ix + 1, iy), pcn = tap(ix, iy + 1), pnn = tap(ix + 1, iy + 1);
+  uint32_t out = 0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = cimg_lerp2((float)((pcc >> (8 * c)) & 255u), (float)((pnc >> (8 * c)) & 255u), (float)((pcn >> (8 * c)) & 255u),
+                               (float)((pnn >> (8 * c)) & 255u), dx, dy);
+    out |= ((uint32_t)(unsigned char)v) << (8 * c);
+  }
+  return out;
+}
+// CImg _linear_atXY (Neumann) over a callable (x, y) -> float
+template <class At>
+__device__ __forceinline__ float neumann_f(At at, int w, int h, float fx, float fy) {
+  const float nfx = fx <= 0 ? 0 : (fx >= w - 1 ? (float)(w - 1) : fx), nfy = fy <= 0 ? 0 : (fy >= h - 1 ? (float)(h - 1) : fy);
+  const unsigned int x = (unsigned int)nfx, y = (unsigned int)nfy;
+  const float dx = nfx - x, dy = nfy - y;
+  const unsigned int nx = dx > 0 ? x + 1 : x, ny = dy > 0 ? y + 1 : y;
+  return cimg_lerp2(at(x, y), at(nx, y), at(x, ny), at(nx, ny), dx, dy);
+}
+// Value at integer (X, Y) of a (W+1)x(H+1) field plane after CImg resize(2W, 2H, linear) and `*= 2.`
+// (DG.cpp:1197-1200): x pass then y pass, each in double, each stored as float.
+__device__ __forceinline__ float resized_field2(const float* f, int fw, int fh, int X, int Y, const RenderArgs& a) {
+  const int px = a.fpos_x[X], py = a.fpos_y[Y];
+  const double ax = a.falpha_x[X], ay = a.falpha_y[Y];
+  const int px2 = px < fw - 1 ? px + 1 : px, py2 = py < fh - 1 ? py + 1 : py;
+  const float r0 = (float)((1 - ax) * (double)f[(size_t)py * fw + px] + ax * (double)f[(size_t)py * fw + px2]);
+  const float r1 = (float)((1 - ax) * (double)f[(size_t)py2 * fw + px] + ax * (double)f[(size_t)py2 * fw + px2]);
+  const float v = (float)((1 - ay) * (double)r0 + ay * (double)r1);
+  return (float)(v * 2.);
+}
+
 __device__ __forceinline__ bool box_hits_tile(const int32_t* b, int tx0, int ty0) {
   // cells right of the tile never matter; cells left of it feed the carry-in
   return b[1] <= ty0 + TH - 1 && b[3] >= ty0 && b[0] <= tx0 + TW - 1 && b[2] >= tx0;
@@ -138,12 +200,14 @@ struct HitObject {             // what the per-pixel stage needs of a FlatObject
   int shape_begin, shape_count;
   int tex;
   int composite;
+  int field;                   // mode 9 field id or -1
 };
 struct Job {                   // one outline of a hit object
   int vbegin[2], vcount[2];
   short hit;                   // index into the hit table
   signed char slot[2];         // accumulator layer per frame, -1: the outline misses the tile (coverage 0)
   unsigned char flags;         // 1 additive | 2 first outline of its object | 4 last outline | 8 a chunk ends after this job
+  int deform;                  // mode 9: frame-1 masks come from this slot of the warped-mask scratch, else -1
 };
 
 // MovingObjectComposite::renderMasks (DG.cpp:606, 626) with the trivial cases folded: the strict-float
@@ -202,6 +266,24 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
         col0[i] = ld_px(row + i) & 0xFFFFFFu;
         col1[i] = bilinear_rgbx(bg, W2, 0, 0, W2, H2, rw, x0 + i + W / 2);
       }
+      if (smp.bg_field >= 0) {
+        // background with a warp field: the warped 2W x 2H texture is resampled through the resized,
+        // doubled inverse field before the centre crop (DG.cpp:670-681, 1194-1201)
+        const int fw = W + 1, fh = H + 1;
+        const float* ifl = a.fields + ((size_t)smp.bg_field * 2 + 1) * 2 * fw * fh;
+        const double* tinv = smp.bg_tex_inv;
+        auto tap = [&](int px, int py) -> uint32_t {
+          if (px < 0 || py < 0 || px >= W2 || py >= H2) return 0u;
+          RowWarp r2;
+          r2.init(tinv, (double)py, W2);
+          return bilinear_rgbx(bg, W2, 0, 0, W2, H2, r2, px);
+        };
+        for (int i = 0; i < 4; ++i) {
+          const int X = x0 + i + W / 2, Y = y + H / 2;
+          const float sx = X + resized_field2(ifl, fw, fh, X, Y, a), sy = Y + resized_field2(ifl + (size_t)fw * fh, fw, fh, X, Y, a);
+          col1[i] = dirichlet_rgbx(tap, sx, sy);
+        }
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i) col0[i] = col1[i] = 0;
@@ -242,7 +324,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
       pos += __popc(bal & ((1u << lane) - 1u));
       if (hit && pos < MAX_HITS) {
         HitObject h;
-        h.obj = o; h.shape_begin = ob->shape_begin; h.shape_count = ob->shape_count; h.tex = ob->tex; h.composite = ob->composite;
+        h.obj = o; h.shape_begin = ob->shape_begin; h.shape_count = ob->shape_count; h.tex = ob->tex; h.composite = ob->composite; h.field = ob->field;
         s_hit[pos] = h;
       }
       if (tid == 0) {
@@ -281,8 +363,10 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
       j.hit = (short)h;
       const bool h0 = box_hits_tile(sh.bbox[0], tx0, ty0), h1 = box_hits_tile(sh.bbox[1], tx0, ty0);
       j.vbegin[0] = sh.vbegin[0]; j.vbegin[1] = sh.vbegin[1];
-      j.vcount[0] = h0 ? sh.vcount[0] : 0; j.vcount[1] = h1 ? sh.vcount[1] : 0;
-      j.slot[0] = h0 ? 0 : -1; j.slot[1] = h1 ? 0 : -1;
+      j.deform = h1 ? sh.deform : -1;  // a warped outline's frame-1 masks were materialised by the pre-pass
+      const bool r1 = h1 && sh.deform < 0;
+      j.vcount[0] = h0 ? sh.vcount[0] : 0; j.vcount[1] = r1 ? sh.vcount[1] : 0;
+      j.slot[0] = h0 ? 0 : -1; j.slot[1] = r1 ? 0 : -1;
       j.flags = (unsigned char)((sh.additive ? 1 : 0) | (si == 0 ? 2 : 0) | (si == ho.shape_count - 1 ? 4 : 0));
       s_job[tid] = j;
     }
@@ -334,6 +418,12 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
           if (jb.slot[f] < 0) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) vaa[f][i] = vna[f][i] = 0;
+            if (f == 1 && jb.deform >= 0 && live) {
+              const uint8_t* mw = a.mask_warp + (size_t)jb.deform * 2 * P + (size_t)y * W + x0;
+              const uint32_t wa = *reinterpret_cast<const uint32_t*>(mw), wn = *reinterpret_cast<const uint32_t*>(mw + P);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { vaa[1][i] = (wa >> (8 * i)) & 255u; vna[1][i] = (wn >> (8 * i)) & 255u; }
+            }
             continue;
           }
           const int l = jb.slot[f];
@@ -401,13 +491,32 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
           }
           any1 |= a.use_aa ? aa[1][i] : na[1][i];
         }
-        if (any1) {
+        if (any1 && ho.field < 0) {
           RowWarp rw;
           rw.init(a.objects[obj_begin + k].tex_inv, (double)y, W);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const unsigned m1 = a.use_aa ? aa[1][i] : na[1][i];
             if (m1) col1[i] = blend_rgbx(col1[i], bilinear_rgbx(tex, a.tex_w, tex_ox, tex_oy, W, H, rw, x0 + i), m1);
+          }
+        } else if (any1) {
+          // applyWarpFieldToTexture(getTransformedTexture(tex0, M), iflow) evaluated where the mask is set:
+          // each of the 4 float-bilinear taps is itself one AGG span-bilinear pixel (DG.cpp:341-345)
+          const double* tinv = a.objects[obj_begin + k].tex_inv;
+          const int fw = W + 1, fh = H + 1;
+          const float* ifl = a.fields + ((size_t)ho.field * 2 + 1) * 2 * fw * fh;
+          auto tap = [&](int px, int py) -> uint32_t {
+            if (px < 0 || py < 0 || px >= W || py >= H) return 0u;
+            RowWarp rw;
+            rw.init(tinv, (double)py, W);
+            return bilinear_rgbx(tex, a.tex_w, tex_ox, tex_oy, W, H, rw, px);
+          };
+          for (int i = 0; i < 4; ++i) {
+            const unsigned m1 = a.use_aa ? aa[1][i] : na[1][i];
+            if (!m1) continue;
+            const int x = x0 + i;
+            const float sx = x + ifl[(size_t)y * fw + x], sy = y + ifl[(size_t)fw * fh + (size_t)y * fw + x];
+            col1[i] = blend_rgbx(col1[i], dirichlet_rgbx(tap, sx, sy), m1);
           }
         }
       }
@@ -434,6 +543,14 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
       ix = ix + (double)W; iy = iy + (double)H;  // I = T(W,H)
       fxv[i] = (float)(ix - save_x);
       fyv[i] = (float)(iy - save_y);
+      if (smp.bg_field >= 0 && ix >= 0 && ix < 2 * W && iy >= 0 && iy < 2 * H) {  // DG.cpp:714-717
+        const int fw = W + 1, fh = H + 1;
+        const float* fl = a.fields + ((size_t)smp.bg_field * 2 + 0) * 2 * fw * fh;
+        auto at0 = [&](unsigned X, unsigned Y) { return resized_field2(fl, fw, fh, (int)X, (int)Y, a); };
+        auto at1 = [&](unsigned X, unsigned Y) { return resized_field2(fl + (size_t)fw * fh, fw, fh, (int)X, (int)Y, a); };
+        fxv[i] += neumann_f(at0, 2 * W, 2 * H, (float)ix, (float)iy);
+        fyv[i] += neumann_f(at1, 2 * W, 2 * H, (float)ix, (float)iy);
+      }
     } else {
       const double* m = a.objects[obj_begin + id0[i] - 1].motion;
       double ix = xf, iy = yf;
@@ -442,6 +559,15 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
       iy = tmp * m[1] + iy * m[3] + m[5];
       fxv[i] = (float)(ix - xf);
       fyv[i] = (float)(iy - yf);
+      const int fld = a.objects[obj_begin + id0[i] - 1].field;
+      if (fld >= 0 && ix >= 0 && ix < W && iy >= 0 && iy < H) {  // DG.cpp:403-406
+        const int fw = W + 1, fh = H + 1;
+        const float* fl = a.fields + ((size_t)fld * 2 + 0) * 2 * fw * fh;
+        auto at0 = [&](unsigned X, unsigned Y) { return fl[(size_t)Y * fw + X]; };
+        auto at1 = [&](unsigned X, unsigned Y) { return fl[(size_t)fw * fh + (size_t)Y * fw + X]; };
+        fxv[i] += neumann_f(at0, fw, fh, (float)ix, (float)iy);
+        fyv[i] += neumann_f(at1, fw, fh, (float)ix, (float)iy);
+      }
     }
   }
 
@@ -481,6 +607,74 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
         fb[(3 + c) * P + i] = (uint8_t)((col1[i] >> (8 * c)) & 255u);
       }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mode 9 pre-pass: frame-1 masks of warped outlines (MovingObjectBase::renderMasks, DG.cpp:370-386)
+// ------------------------------------------------------------------------------------------------
+// (a) rasterise the outline's frame-1 AA / non-AA masks over the whole frame, tile by tile
+__global__ void __launch_bounds__(RENDER_THREADS) deform_raster_kernel(RenderArgs a) {
+  __shared__ int s_cover[TH][TW];
+  __shared__ int s_area[TH][TW];
+  __shared__ int s_carry[TH];
+  const int W = a.W, H = a.H;
+  const size_t P = (size_t)W * H;
+  const int tiles_x = (W + TW - 1) / TW;
+  const int tx0 = (blockIdx.x % tiles_x) * TW, ty0 = (blockIdx.x / tiles_x) * TH;
+  const int slot = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int y = ty0 + warp, x0 = tx0 + lane * 4;
+  const bool live = (y < H) && (x0 < W);
+  const FlatShape& sh = a.shapes[a.deform_shape[slot]];
+  uint8_t* out = a.mask_raw + (size_t)slot * 2 * P + (size_t)y * W + x0;
+  uint32_t paa = 0, pna = 0;
+  if (box_hits_tile(sh.raw1, tx0, ty0)) {
+    for (int i = tid; i < TH * TW; i += RENDER_THREADS) { (&s_cover[0][0])[i] = 0; (&s_area[0][0])[i] = 0; }
+    if (tid < TH) s_carry[tid] = 0;
+    __syncthreads();
+    const int n = sh.vcount[1];
+    const FlatVertex* v = a.verts + sh.vbegin[1];
+    for (int e = tid; e < n; e += RENDER_THREADS) {
+      const FlatVertex p = v[e], q = v[e + 1 == n ? 0 : e + 1];
+      tile_edge<true>(&s_cover[0][0], &s_area[0][0], &s_carry[0], tx0, ty0, p.x, p.y, q.x, q.y);
+    }
+    __syncthreads();
+    const int4 c4 = *reinterpret_cast<const int4*>(&s_cover[warp][lane * 4]);
+    const int4 a4 = *reinterpret_cast<const int4*>(&s_area[warp][lane * 4]);
+    int c[4] = {c4.x, c4.y, c4.z, c4.w}, ar[4] = {a4.x, a4.y, a4.z, a4.w};
+    c[1] += c[0]; c[2] += c[1]; c[3] += c[2];
+    int tot = c[3];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int o = __shfl_up_sync(0xffffffffu, tot, d);
+      if (lane >= d) tot += o;
+    }
+    const int base = tot - c[3] + s_carry[warp];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int cv = coverage_alpha(base + c[i], ar[i]);
+      paa |= graylut((unsigned)cv) << (8 * i);
+      pna |= (cv >= 128 ? 255u : 0u) << (8 * i);
+    }
+  }
+  if (live) {
+    *reinterpret_cast<uint32_t*>(out) = paa;
+    *reinterpret_cast<uint32_t*>(out + P) = pna;
+  }
+}
+// (b) applyWarpFieldToTexture(mask, iflow): out(x,y) = trunc(bilinear_0(mask, (x,y) + iflow(x,y)))
+__global__ void deform_warp_kernel(RenderArgs a) {
+  const int W = a.W, H = a.H;
+  const size_t P = (size_t)W * H;
+  const int slot = blockIdx.y >> 1, which = blockIdx.y & 1;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const int x = (int)(i % W), y = (int)(i / W);
+  const int fw = W + 1, fh = H + 1;
+  const float* ifl = a.fields + ((size_t)a.deform_field[slot] * 2 + 1) * 2 * fw * fh;
+  const float sx = x + ifl[(size_t)y * fw + x], sy = y + ifl[(size_t)fw * fh + (size_t)y * fw + x];
+  const uint8_t* src = a.mask_raw + ((size_t)slot * 2 + which) * P;
+  a.mask_warp[((size_t)slot * 2 + which) * P + i] = (uint8_t)dirichlet_u8(src, W, H, sx, sy);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -706,6 +900,15 @@ int launch_background_prep(const RenderArgs& a, cudaStream_t s) {
   bg_tables_kernel<<<a.batch, 32, 0, s>>>(a);
   dim3 grid((2 * a.W + PT - 1) / PT, (2 * a.H + PT - 1) / PT, a.batch);
   bg_prep_kernel<<<grid, PREP_THREADS, 0, s>>>(a);
+  return 2;
+}
+
+int launch_deform_prepass(const RenderArgs& a, cudaStream_t s) {
+  if (a.n_deform <= 0) return 0;
+  const int tiles_x = (a.W + TW - 1) / TW, tiles_y = (a.H + TH - 1) / TH;
+  deform_raster_kernel<<<dim3(tiles_x * tiles_y, a.n_deform), RENDER_THREADS, 0, s>>>(a);
+  const size_t P = (size_t)a.W * a.H;
+  deform_warp_kernel<<<dim3((unsigned)((P + 255) / 256), 2 * a.n_deform), 256, 0, s>>>(a);
   return 2;
 }
 

@@ -26,8 +26,17 @@ struct RenderArgs {
   int* pos_y;        // [batch][2H]
   double* alpha_y;   // [batch][2H]
   // mode 9
-  const float* fields;  // [n][2][2][H+1][W+1]
+  const float* fields;        // [n][flow|iflow][channel][H+1][W+1]
   int n_fields;
+  int n_deform;               // outlines whose frame-1 masks are warped (scratch slots)
+  const int* deform_shape;    // [n_deform] index into shapes
+  const int* deform_field;    // [n_deform] field id
+  uint8_t* mask_raw;          // [n_deform][AA|noAA][H][W] frame-1 masks before the warp
+  uint8_t* mask_warp;         // [n_deform][AA|noAA][H][W] after the warp
+  const int* fpos_x;          // CImg linear-resize tables (W+1 -> 2W, H+1 -> 2H) for the background's fields
+  const double* falpha_x;
+  const int* fpos_y;
+  const double* falpha_y;
   // outputs (device): NCHW float blobs
   float* img0;
   float* img1;
@@ -43,6 +52,7 @@ struct RenderArgs {
 // Launchers; each returns the number of kernels it launched.
 int launch_background_prep(const RenderArgs& a, cudaStream_t s);
 int launch_render(const RenderArgs& a, cudaStream_t s);
+int launch_deform_prepass(const RenderArgs& a, cudaStream_t s);  // mode 9 only; no-op when n_deform == 0
 
 void launch_planar_to_rgbx(const uint8_t* planar, uchar4* out, int n, int w, int h, cudaStream_t s);
 void launch_rgbx_to_planar(const uchar4* in, uint8_t* planar, int w, int h, cudaStream_t s);

@@ -112,3 +112,11 @@ def composite_luts():
     s = np.empty((256, 256), np.uint8)
     lib().oracle_composite_luts(_p(a), _p(s))
     return a, s
+
+
+def generate_fields(W=512, H=384, seed=1, n_fields=8):
+    """(n, 2, 2, H+1, W+1) float32 pool of (flow, iflow) crops, WarpFields::CropGenerator restated."""
+    out = np.empty((n_fields, 2, 2, H + 1, W + 1), np.float32)
+    rc = lib().oracle_generate_fields(C.c_int32(W), C.c_int32(H), C.c_uint32(seed), C.c_int32(n_fields), _p(out))
+    assert rc == 0
+    return out

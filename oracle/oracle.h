@@ -67,6 +67,10 @@ int oracle_randomized_crop(const uint8_t* tex, int32_t tw, int32_t th, int32_t o
 /* The two 256x256 composite-mask tables [u][v] (DataGenerator.cpp:606, 626). */
 void oracle_composite_luts(uint8_t* add_lut, uint8_t* sub_lut);
 
+/* Mode-9 field producer (WarpFields::CropGenerator restated, explicitly seeded): writes n_fields
+ * (flow, iflow) crops, layout n x 2 x 2 x (H+1) x (W+1) float. Values may be NaN near canvas borders. */
+int oracle_generate_fields(int32_t W, int32_t H, uint32_t seed, int32_t n_fields, float* out);
+
 const char* oracle_last_error(void);
 
 #ifdef __cplusplus

@@ -128,3 +128,33 @@ def test_many_objects_per_tile(ofdg, oracle, textures8):
     cpu = oracle.render(tasks.struct(), textures8, mode=7, debug=True, max_objs=160)
     _compare(gpu, cpu)
     g.close()
+
+
+@pytest.fixture(scope="module")
+def fields4(oracle):
+    f = oracle.generate_fields(512, 384, seed=1, n_fields=4)
+    # the reference's fields carry NaNs near the canvas border (WarpFields.cpp:389-398): plant some
+    f[3, :, :, 100:140, 200:260] = np.nan
+    return f
+
+
+def test_mode9_nonrigid_parity(ofdg, oracle, textures8, fields4):
+    """Mode 9: warped masks / textures / flow for flagged objects, composites and backgrounds."""
+    g = _gen(ofdg, 9)
+    g.upload_textures(textures8)
+    g.set_fields(fields4)
+    tasks = ofdg.ParamStream(9, n_fields=4).generate(8)
+    bp = tasks.arrays()["blueprints"]
+    flagged = bp[(bp["do_warpfield_deformation"] != 0) & (bp["parent"] < 0)]
+    assert (flagged["obj_id"] == 1).any(), "a deformed background must be part of the batch"
+    assert (flagged["obj_type"] == 3).any() and (flagged["obj_type"] == 1).any() and (flagged["obj_type"] == 2).any()
+    assert (flagged["field_id"] == 3).any(), "the field with NaNs must be in use"
+    gpu = g.render_debug(tasks)
+    cpu = oracle.render(tasks.struct(), textures8, mode=9, fields=fields4, debug=True)
+    assert np.array_equal(gpu["id0"], cpu["id0"]) and np.array_equal(gpu["id1"], cpu["id1"])
+    assert np.array_equal(gpu["masks"], cpu["masks"])
+    assert np.abs(gpu["frames8"].astype(int) - cpu["frames8"].astype(int)).max() <= IMG_TOL
+    ok = np.isfinite(cpu["flow"])
+    assert np.array_equal(ok, np.isfinite(gpu["flow"]))  # NaN flow where the field is NaN, exactly like the reference
+    assert np.abs(gpu["flow"][ok] - cpu["flow"][ok]).max() <= FLOW_TOL
+    g.close()
