@@ -214,16 +214,13 @@ def run_ours(args):
     h1 = torch.empty_like(h0).pin_memory()
     hf = torch.empty((B, 2, H, W), dtype=torch.float32).pin_memory()
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    tasks = o.Tasks()
     for _ in range(2):
-        tasks.clear(); ps.generate(B, tasks); g.render_host(tasks, h0, h1, hf)
+        g.generate_host(ps, B, h0, h1, hf)
     barrier()
     t0 = time.time()
     h2d = 0
     for _ in range(e2e_steps):
-        tasks.clear()
-        ps.generate(B, tasks)
-        g.render_host(tasks, h0, h1, hf)
+        g.generate_host(ps, B, h0, h1, hf)  # parameter draw + flatten + H2D + kernels + D2H, all inside
         h2d += g.last_upload_bytes()
     torch.cuda.synchronize()
     dt = time.time() - t0

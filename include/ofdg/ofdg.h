@@ -140,6 +140,10 @@ int ofdg_render_prepared(ofdg_generator* g, const ofdg_prepared* p, float* d_img
 int ofdg_generate(ofdg_generator* g, ofdg_params* p, int32_t batch, float* d_img0, float* d_img1, float* d_flow,
                   void* stream);
 
+/* Same, delivering into HOST blobs (what Forward_cpu hands to a CPU consumer): parameter draw, flattening,
+ * upload, kernels and the device-to-host copies are pipelined chunk by chunk inside the call. */
+int ofdg_generate_host(ofdg_generator* g, ofdg_params* p, int32_t batch, float* h_img0, float* h_img1, float* h_flow);
+
 /* Number of kernel launches issued by this generator so far (bench.py's gpu_launches). */
 uint64_t ofdg_launch_count(const ofdg_generator* g);
 /* Device time, measured with CUDA events on the launching stream, spent in the background

@@ -58,7 +58,7 @@ EXPORTS = [
     "ofdg_flatten_ellipse", "ofdg_flatten_polygon", "ofdg_debug_raster_host", "ofdg_create", "ofdg_destroy", "ofdg_upload_textures",
     "ofdg_synth_textures", "ofdg_download_texture", "ofdg_set_fields", "ofdg_render", "ofdg_render_host",
     "ofdg_render_debug", "ofdg_debug_background", "ofdg_debug_composite_luts", "ofdg_prepare", "ofdg_prepared_destroy",
-    "ofdg_render_prepared", "ofdg_generate", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_upload_bytes",
+    "ofdg_render_prepared", "ofdg_generate", "ofdg_generate_host", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_upload_bytes",
 ]
 # include/ofdg/layer.h
 LAYER_EXPORTS = [
@@ -113,6 +113,7 @@ def lib():
         L.ofdg_prepare.argtypes = [C.c_void_p, C.POINTER(TaskBatchStruct), C.POINTER(C.c_void_p)]
         L.ofdg_prepared_destroy.argtypes = [C.c_void_p]
         L.ofdg_render_prepared.argtypes = [C.c_void_p] * 6
+        L.ofdg_generate_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 3
         L.ofdg_generate.argtypes = [C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 4
         L.ofdg_layer_last_error.restype = C.c_char_p
         L.ofdg_layer_type.restype = C.c_char_p
@@ -389,6 +390,11 @@ class Generator:
 
     def generate(self, params, batch, img0, img1, flow, stream=None):
         _check(lib().ofdg_generate(self._h, params._h, batch, img0.data_ptr(), img1.data_ptr(), flow.data_ptr(), stream))
+
+    def generate_host(self, params, batch, img0, img1, flow):
+        """Draw + render `batch` samples into HOST blobs (numpy arrays or pinned torch tensors)."""
+        p = lambda a: a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+        _check(lib().ofdg_generate_host(self._h, params._h, batch, p(img0), p(img1), p(flow)))
 
     def launch_count(self):
         return int(lib().ofdg_launch_count(self._h))

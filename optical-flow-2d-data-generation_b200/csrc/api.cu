@@ -132,6 +132,12 @@ struct ofdg_generator {
   DevBuf dbg_masks, dbg_id0, dbg_id1, dbg_frames8, dbg_planar;
   ofdg::FlatBatch flat;
   ofdg::TaskBatch gen_tasks;
+  // host-blob pipeline: two scene/staging sets, a copy stream, events
+  DeviceScene pipe_scene[2];
+  PinnedBuf pipe_staging[2];
+  ofdg::FlatBatch pipe_flat[2];
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t pipe_uploaded[2] = {nullptr, nullptr}, pipe_rendered[2] = {nullptr, nullptr};
   uint64_t launches = 0;
   float last_kernel_ms = 0.f;
 
@@ -146,12 +152,12 @@ void check_batch(const ofdg_generator* g, int n) {
   if (g->n_tex <= 0) throw StateError("no textures uploaded (ofdg_upload_textures / ofdg_synth_textures)");
 }
 
-void upload_scene(ofdg_generator* g, const ofdg::FlatBatch& fb, DeviceScene& ds, cudaStream_t s) {
+void upload_scene(ofdg_generator* g, const ofdg::FlatBatch& fb, DeviceScene& ds, PinnedBuf& staging, cudaStream_t s) {
   const size_t b0 = fb.samples.size() * sizeof(ofdg::FlatSample), b1 = fb.objects.size() * sizeof(ofdg::FlatObject),
                b2 = fb.shapes.size() * sizeof(ofdg::FlatShape), b3 = fb.verts.size() * sizeof(ofdg::FlatVertex);
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  g->staging.reserve(al(b0) + al(b1) + al(b2) + al(b3) + 256);
-  char* st = (char*)g->staging.p;
+  staging.reserve(al(b0) + al(b1) + al(b2) + al(b3) + 256);
+  char* st = (char*)staging.p;
   size_t o0 = 0, o1 = al(b0), o2 = o1 + al(b1), o3 = o2 + al(b2);
   std::memcpy(st + o0, fb.samples.data(), b0);
   std::memcpy(st + o1, fb.objects.data(), b1);
@@ -174,15 +180,16 @@ void upload_scene(ofdg_generator* g, const ofdg::FlatBatch& fb, DeviceScene& ds,
   g->last_upload_bytes = b0 + b1 + b2 + b3 + 2 * (size_t)ds.n_deform * sizeof(int32_t);
 }
 
-void flatten_tasks(ofdg_generator* g, const ofdg_task_batch* tasks) {
+void flatten_tasks(ofdg_generator* g, const ofdg_task_batch* tasks, ofdg::FlatBatch* into = nullptr) {
+  ofdg::FlatBatch& flat = into ? *into : g->flat;
   ofdg::FlattenConfig fc;
   fc.W = g->cfg.width; fc.H = g->cfg.height;
   fc.tex_w = g->tex_w; fc.tex_h = g->tex_h; fc.n_tex = g->n_tex;
   fc.mode = g->cfg.mode;
   fc.n_fields = g->n_fields;
   fc.field_reach = g->field_reach.empty() ? nullptr : g->field_reach.data();
-  g->flat.clear();
-  ofdg::flatten(*tasks, fc, g->flat);
+  flat.clear();
+  ofdg::flatten(*tasks, fc, flat);
 }
 
 void ensure_scratch(ofdg_generator* g, int batch) {
@@ -382,6 +389,11 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
     std::unique_ptr<ofdg_generator> g(new ofdg_generator);
     g->cfg = *cfg;
     CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&g->pipe_uploaded[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&g->pipe_rendered[i], cudaEventDisableTiming));
+    }
     *out = g.release();
   });
 }
@@ -395,6 +407,13 @@ void ofdg_destroy(ofdg_generator* g) {
   for (DevBuf* b : bufs) b->release();
   g->scene.release();
   g->staging.release();
+  for (int i = 0; i < 2; ++i) {
+    g->pipe_scene[i].release();
+    g->pipe_staging[i].release();
+    if (g->pipe_uploaded[i]) cudaEventDestroy(g->pipe_uploaded[i]);
+    if (g->pipe_rendered[i]) cudaEventDestroy(g->pipe_rendered[i]);
+  }
+  if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
   for (cudaEvent_t e : g->evs) cudaEventDestroy(e);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
@@ -508,10 +527,53 @@ int ofdg_render(ofdg_generator* g, const ofdg_task_batch* tasks, float* d_img0, 
     ensure_scratch(g, tasks->n_tasks);
     // the pinned staging area is reused by the next call: wait for the previous upload
     CK(cudaStreamSynchronize(s));
-    upload_scene(g, g->flat, g->scene, s);
+    upload_scene(g, g->flat, g->scene, g->staging, s);
     run_kernels(g, make_args(g, g->scene, d_img0, d_img1, d_flow), s);
     if (!stream) CK(cudaStreamSynchronize(s));
   });
+}
+
+// Host-blob rendering, pipelined in up to 4 chunks: while chunk k's blobs travel device->host on
+// the copy stream, chunk k+1 is drawn/flattened on the host and rendered on the compute stream.
+static void render_host_pipelined(ofdg_generator* g, ofdg_params* params, const ofdg_task_batch* tasks, int n,
+                                  float* h_img0, float* h_img1, float* h_flow) {
+  const size_t P = (size_t)g->cfg.width * g->cfg.height;
+  g->out0.reserve((size_t)n * 3 * P * sizeof(float)); g->out1.reserve((size_t)n * 3 * P * sizeof(float)); g->outf.reserve((size_t)n * 2 * P * sizeof(float));
+  const int nchunk = n >= 32 ? 4 : (n >= 8 ? 2 : 1);
+  ensure_scratch(g, (n + nchunk - 1) / nchunk);
+  cudaStream_t A = g->stream, B = g->copy_stream;
+  size_t uploaded = 0;
+  for (int k = 0; k < nchunk; ++k) {
+    const int t0 = (int)((long long)n * k / nchunk), t1 = (int)((long long)n * (k + 1) / nchunk), set = k & 1;
+    if (k >= 2) CK(cudaEventSynchronize(g->pipe_uploaded[set]));  // the pinned staging area of this set is free again
+    ofdg_task_batch view;
+    if (params) {
+      g->gen_tasks.clear();
+      for (int i = t0; i < t1; ++i) params->ps->next_task(g->gen_tasks);
+      view = g->gen_tasks.view();
+    } else {
+      view = *tasks;
+      view.n_tasks = t1 - t0;
+      view.task_begin = tasks->task_begin + t0;  // blueprint indices stay absolute
+    }
+    flatten_tasks(g, &view, &g->pipe_flat[set]);
+    upload_scene(g, g->pipe_flat[set], g->pipe_scene[set], g->pipe_staging[set], A);
+    uploaded += g->last_upload_bytes;
+    CK(cudaEventRecord(g->pipe_uploaded[set], A));
+    float* d0 = (float*)g->out0.p + (size_t)t0 * 3 * P;
+    float* d1 = (float*)g->out1.p + (size_t)t0 * 3 * P;
+    float* df = (float*)g->outf.p + (size_t)t0 * 2 * P;
+    run_kernels(g, make_args(g, g->pipe_scene[set], d0, d1, df), A);
+    CK(cudaEventRecord(g->pipe_rendered[set], A));
+    CK(cudaStreamWaitEvent(B, g->pipe_rendered[set], 0));
+    const size_t c = (size_t)(t1 - t0);
+    CK(cudaMemcpyAsync(h_img0 + (size_t)t0 * 3 * P, d0, c * 3 * P * sizeof(float), cudaMemcpyDeviceToHost, B));
+    CK(cudaMemcpyAsync(h_img1 + (size_t)t0 * 3 * P, d1, c * 3 * P * sizeof(float), cudaMemcpyDeviceToHost, B));
+    CK(cudaMemcpyAsync(h_flow + (size_t)t0 * 2 * P, df, c * 2 * P * sizeof(float), cudaMemcpyDeviceToHost, B));
+  }
+  CK(cudaStreamSynchronize(B));
+  CK(cudaStreamSynchronize(A));
+  g->last_upload_bytes = uploaded;
 }
 
 int ofdg_render_host(ofdg_generator* g, const ofdg_task_batch* tasks, float* h_img0, float* h_img1, float* h_flow) {
@@ -519,17 +581,16 @@ int ofdg_render_host(ofdg_generator* g, const ofdg_task_batch* tasks, float* h_i
     if (!g || !tasks || !h_img0 || !h_img1 || !h_flow) throw ArgError("null pointer");
     check_batch(g, tasks->n_tasks);
     g->use();
-    const size_t P = (size_t)g->cfg.width * g->cfg.height, n = tasks->n_tasks;
-    g->out0.reserve(n * 3 * P * sizeof(float)); g->out1.reserve(n * 3 * P * sizeof(float)); g->outf.reserve(n * 2 * P * sizeof(float));
-    cudaStream_t s = g->stream;
-    flatten_tasks(g, tasks);
-    ensure_scratch(g, tasks->n_tasks);
-    upload_scene(g, g->flat, g->scene, s);
-    run_kernels(g, make_args(g, g->scene, (float*)g->out0.p, (float*)g->out1.p, (float*)g->outf.p), s);
-    CK(cudaMemcpyAsync(h_img0, g->out0.p, n * 3 * P * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(h_img1, g->out1.p, n * 3 * P * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(h_flow, g->outf.p, n * 2 * P * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    render_host_pipelined(g, nullptr, tasks, tasks->n_tasks, h_img0, h_img1, h_flow);
+  });
+}
+
+int ofdg_generate_host(ofdg_generator* g, ofdg_params* p, int32_t batch, float* h_img0, float* h_img1, float* h_flow) {
+  return guarded([&] {
+    if (!g || !p || !h_img0 || !h_img1 || !h_flow) throw ArgError("null pointer");
+    check_batch(g, batch);
+    g->use();
+    render_host_pipelined(g, p, nullptr, batch, h_img0, h_img1, h_flow);
   });
 }
 
@@ -545,7 +606,7 @@ int ofdg_render_debug(ofdg_generator* g, const ofdg_task_batch* tasks, float* h_
     flatten_tasks(g, tasks);
     ensure_scratch(g, tasks->n_tasks);
     CK(cudaMemsetAsync(g->bg.p, 0, n * 4 * P * sizeof(uchar4), s));
-    upload_scene(g, g->flat, g->scene, s);
+    upload_scene(g, g->flat, g->scene, g->staging, s);
     ofdg::RenderArgs a = make_args(g, g->scene, (float*)g->out0.p, (float*)g->out1.p, (float*)g->outf.p);
     if (masks && max_objs > 0) {
       g->dbg_masks.reserve(n * max_objs * 4 * P);
@@ -583,7 +644,7 @@ int ofdg_debug_background(ofdg_generator* g, const ofdg_task_batch* tasks, uint8
     flatten_tasks(g, tasks);
     ensure_scratch(g, tasks->n_tasks);
     CK(cudaMemsetAsync(g->bg.p, 0, n * P4 * sizeof(uchar4), s));
-    upload_scene(g, g->flat, g->scene, s);
+    upload_scene(g, g->flat, g->scene, g->staging, s);
     ofdg::RenderArgs a = make_args(g, g->scene, nullptr, nullptr, nullptr);
     g->launches += ofdg::launch_background_prep(a, s);
     g->dbg_planar.reserve(n * 3 * P4);
@@ -620,7 +681,7 @@ int ofdg_prepare(ofdg_generator* g, const ofdg_task_batch* tasks, ofdg_prepared*
     flatten_tasks(g, tasks);
     std::unique_ptr<ofdg_prepared> p(new ofdg_prepared);
     p->device = g->cfg.device;
-    upload_scene(g, g->flat, p->scene, g->stream);
+    upload_scene(g, g->flat, p->scene, g->staging, g->stream);
     CK(cudaStreamSynchronize(g->stream));
     *out = p.release();
   });

@@ -213,10 +213,21 @@ void realize_shape(const ofdg_task_batch& tb, const ofdg_blueprint& b, const Aff
 void flatten_ellipse(double rx, double ry, const double m6[6], std::vector<FlatVertex>& out) {
   const Affine m = from6(m6);
   const unsigned num = 100;  // setEllipse(0, 0, rx, ry, 100), DG.cpp:1080
+  // the 100 step angles do not depend on the ellipse: cos/sin evaluated once (same libm, same values)
+  static const struct Circle {
+    double c[100], s[100];
+    Circle() {
+      for (unsigned step = 0; step < 100; ++step) {
+        double angle = double(step) / double(100) * 2.0 * kPi;
+        c[step] = std::cos(angle);
+        s[step] = std::sin(angle);
+      }
+    }
+  } circle;
+  out.reserve(out.size() + num);
   for (unsigned step = 0; step < num; ++step) {
-    double angle = double(step) / double(num) * 2.0 * kPi;
-    double x = 0.0 + std::cos(angle) * rx;
-    double y = 0.0 + std::sin(angle) * ry;
+    double x = 0.0 + circle.c[step] * rx;
+    double y = 0.0 + circle.s[step] * ry;
     m.apply(&x, &y);
     out.push_back(to_fixed(x, y));
   }
@@ -330,6 +341,7 @@ void flatten(const ofdg_task_batch& tb, const FlattenConfig& cfg, FlatBatch& out
       out.objects.push_back(o);
     }
     smp.obj_count = (int32_t)out.objects.size() - smp.obj_begin;
+    if (smp.obj_count > 254) throw std::runtime_error("more than 254 foreground objects in one sample (object ids are tracked in one byte per pixel)");
     out.samples.push_back(smp);
   }
 }

@@ -222,7 +222,25 @@ __device__ __forceinline__ unsigned comp_sub(unsigned u, unsigned v, const float
   if (v == 255u || u == 0u) return 0u;
   return (unsigned)(unsigned char)(255.f * ((q255[u]) * (1.f - q255[v])));
 }
+// The same rules on four pixels packed one byte each.
+__device__ __forceinline__ uint32_t comp4(uint32_t u, uint32_t v, bool additive, const float* q255) {
+  if (additive) {
+    if (v == 0xFFFFFFFFu) return 0xFFFFFFFFu;
+    if ((u | v) == 0u) return 0u;
+  } else {
+    if (v == 0xFFFFFFFFu || u == 0u) return 0u;
+  }
+  uint32_t out = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const unsigned ub = (u >> (8 * i)) & 255u, vb = (v >> (8 * i)) & 255u;
+    out |= (additive ? comp_add(ub, vb, q255) : comp_sub(ub, vb, q255)) << (8 * i);
+  }
+  return out;
+}
 
+// kDeform = false compiles the mode-9 (warp field) branches out.
+template <bool kDeform>
 __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a) {
   __shared__ int s_cover[NLAYER][TH][TW];
   __shared__ int s_area[NLAYER][TH][TW];
@@ -231,9 +249,8 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
   __shared__ HitObject s_hit[MAX_HITS];
   __shared__ Job s_job[MAX_JOBS];
   __shared__ int s_jobbase[MAX_HITS + 1];
-  __shared__ unsigned s_ballot[RENDER_THREADS / 32];
-  __shared__ int s_nhit, s_njob, s_hits_done, s_next_obj;
-  __shared__ int s_seg_begin[NLAYER], s_seg_count[NLAYER + 1];
+  __shared__ int s_nhit, s_njob, s_hits_done, s_next_obj, s_scan_next;
+  __shared__ int s_seg_begin[NLAYER], s_seg_count[NLAYER];
 
   const int W = a.W, H = a.H;
   const int tiles_x = (W + TW - 1) / TW;
@@ -250,7 +267,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
   if (tid == 0) s_next_obj = 0;
 
   uint32_t col0[4], col1[4];
-  unsigned id0[4] = {0, 0, 0, 0}, id1[4] = {0, 0, 0, 0};  // 0 = background, k+1 = k-th foreground object
+  uint32_t id0 = 0, id1 = 0;  // four pixels, one byte each: 0 = background, k+1 = k-th foreground object (k < 255)
 
   // ---- background: masks are all 255 (DG.cpp:684-690); frame 0 = centre window of the prepared
   //      texture, frame 1 = that texture warped by I^-1*M*I on the 2W x 2H canvas (DG.cpp:665-682)
@@ -266,7 +283,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
         col0[i] = ld_px(row + i) & 0xFFFFFFu;
         col1[i] = bilinear_rgbx(bg, W2, 0, 0, W2, H2, rw, x0 + i + W / 2);
       }
-      if (smp.bg_field >= 0) {
+      if (kDeform && smp.bg_field >= 0) {
         // background with a warp field: the warped 2W x 2H texture is resampled through the resized,
         // doubled inverse field before the centre crop (DG.cpp:670-681, 1194-1201)
         const int fw = W + 1, fh = H + 1;
@@ -291,47 +308,38 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
   }
 
   const int tex_ox = a.tex_w / 2 - W / 2, tex_oy = a.tex_h / 2 - H / 2;  // centre crop, DG.cpp:99-102 with defaults
-  unsigned aa[2][4], na[2][4];  // masks of the object being assembled: [frame][pixel]
+  uint32_t uaa[2] = {0, 0}, una[2] = {0, 0};  // masks of the object being assembled: [frame], 4 pixels x 1 byte
 
   // ---- foreground objects in z-order, in passes of at most MAX_HITS objects / MAX_JOBS outlines
   for (;;) {
     __syncthreads();
     const int obj0 = s_next_obj;
     if (obj0 >= n_obj) break;
-    // (1) objects whose boxes touch the tile -> ordered hit table
-    if (tid == 0) s_nhit = 0;
-    int scanned = obj0;
-    for (; scanned < n_obj; scanned += RENDER_THREADS) {
-      __syncthreads();
-      const int nh = s_nhit;
-      if (nh >= MAX_HITS) break;
-      const int o = scanned + tid;
-      bool hit = false;
-      const FlatObject* ob = nullptr;
-      if (o < n_obj) {
-        ob = a.objects + obj_begin + o;
-        hit = box_hits_tile(ob->bbox[0], tx0, ty0) || box_hits_tile(ob->bbox[1], tx0, ty0);
+    // (1) warp 0: objects whose boxes touch the tile -> ordered hit table
+    if (warp == 0) {
+      int nh = 0, next = n_obj;
+      for (int o = obj0; o < n_obj; o += 32) {
+        const int idx = o + lane;
+        bool hit = false;
+        const FlatObject* ob = a.objects + obj_begin + idx;
+        if (idx < n_obj) hit = box_hits_tile(ob->bbox[0], tx0, ty0) || box_hits_tile(ob->bbox[1], tx0, ty0);
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        const int pos = nh + __popc(bal & ((1u << lane) - 1u));
+        if (hit && pos < MAX_HITS) {
+          HitObject h;
+          h.obj = idx; h.shape_begin = ob->shape_begin; h.shape_count = ob->shape_count; h.tex = ob->tex;
+          h.composite = ob->composite; h.field = ob->field;
+          s_hit[pos] = h;
+        }
+        const int cnt = __popc(bal);
+        if (nh + cnt > MAX_HITS) {  // table full: the next pass rescans from the first object left out
+          next = o + (int)__fns(bal, 0, MAX_HITS - nh + 1);
+          nh = MAX_HITS;
+          break;
+        }
+        nh += cnt;
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, hit);
-      if (lane == 0) s_ballot[warp] = bal;
-      __syncthreads();
-      int pos = nh, total = nh;
-      for (int w = 0; w < RENDER_THREADS / 32; ++w) {
-        const int c = __popc(s_ballot[w]);
-        if (w < warp) pos += c;
-        total += c;
-      }
-      pos += __popc(bal & ((1u << lane) - 1u));
-      if (hit && pos < MAX_HITS) {
-        HitObject h;
-        h.obj = o; h.shape_begin = ob->shape_begin; h.shape_count = ob->shape_count; h.tex = ob->tex; h.composite = ob->composite; h.field = ob->field;
-        s_hit[pos] = h;
-      }
-      if (tid == 0) {
-        // objects past the table's capacity are rescanned by the next pass
-        if (total > MAX_HITS) { s_nhit = MAX_HITS; } else { s_nhit = total; }
-      }
-      if (total > MAX_HITS) { scanned += RENDER_THREADS; break; }
+      if (lane == 0) { s_nhit = nh; s_scan_next = next; }
     }
     __syncthreads();
     // (2) outline jobs of the hit objects
@@ -346,9 +354,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
       s_jobbase[h] = nj;
       s_hits_done = h;
       s_njob = nj;
-      // next pass starts after the last object fully handled here
-      s_next_obj = (h == nh && nh < MAX_HITS) ? n_obj : s_hit[h - 1].obj + 1;
-      if (nh == 0) s_next_obj = n_obj;
+      s_next_obj = (h == nh) ? s_scan_next : s_hit[h].obj;  // first object not handled by this pass
     }
     __syncthreads();
     const int njob = s_njob, nhd = s_hits_done;
@@ -363,8 +369,8 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
       j.hit = (short)h;
       const bool h0 = box_hits_tile(sh.bbox[0], tx0, ty0), h1 = box_hits_tile(sh.bbox[1], tx0, ty0);
       j.vbegin[0] = sh.vbegin[0]; j.vbegin[1] = sh.vbegin[1];
-      j.deform = h1 ? sh.deform : -1;  // a warped outline's frame-1 masks were materialised by the pre-pass
-      const bool r1 = h1 && sh.deform < 0;
+      j.deform = (kDeform && h1) ? sh.deform : -1;  // a warped outline's frame-1 masks were materialised by the pre-pass
+      const bool r1 = h1 && j.deform < 0;
       j.vcount[0] = h0 ? sh.vcount[0] : 0; j.vcount[1] = r1 ? sh.vcount[1] : 0;
       j.slot[0] = h0 ? 0 : -1; j.slot[1] = r1 ? 0 : -1;
       j.flags = (unsigned char)((sh.additive ? 1 : 0) | (si == 0 ? 2 : 0) | (si == ho.shape_count - 1 ? 4 : 0));
@@ -389,13 +395,18 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
       int j1 = j0;
       while (!(s_job[j1].flags & 8)) ++j1;
       ++j1;  // jobs [j0, j1)
-      if (tid == 0) {
-        for (int l = 0; l < NLAYER; ++l) { s_seg_begin[l] = 0; s_seg_count[l] = 0; }
+      if (tid < NLAYER) {  // thread l publishes the edge list that feeds accumulator layer l
+        int b = 0, c = 0;
         for (int j = j0; j < j1; ++j)
           for (int f = 0; f < 2; ++f)
-            if (s_job[j].slot[f] >= 0) { s_seg_begin[s_job[j].slot[f]] = s_job[j].vbegin[f]; s_seg_count[s_job[j].slot[f]] = s_job[j].vcount[f]; }
+            if (s_job[j].slot[f] == tid) { b = s_job[j].vbegin[f]; c = s_job[j].vcount[f]; }
+        s_seg_begin[tid] = b;
+        s_seg_count[tid] = c;
       }
-      for (int i = tid; i < NLAYER * TH * TW; i += RENDER_THREADS) { (&s_cover[0][0][0])[i] = 0; (&s_area[0][0][0])[i] = 0; }
+      for (int i = tid; i < NLAYER * TH * TW / 4; i += RENDER_THREADS) {
+        reinterpret_cast<int4*>(&s_cover[0][0][0])[i] = make_int4(0, 0, 0, 0);
+        reinterpret_cast<int4*>(&s_area[0][0][0])[i] = make_int4(0, 0, 0, 0);
+      }
       if (tid < NLAYER * TH) (&s_carry[0][0])[tid] = 0;
       __syncthreads();
       {
@@ -412,23 +423,30 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
       __syncthreads();
       for (int j = j0; j < j1; ++j) {
         const Job jb = s_job[j];
-        unsigned vaa[2][4], vna[2][4];
+        uint32_t vaa[2] = {0, 0}, vna[2] = {0, 0};
 #pragma unroll
         for (int f = 0; f < 2; ++f) {
-          if (jb.slot[f] < 0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) vaa[f][i] = vna[f][i] = 0;
-            if (f == 1 && jb.deform >= 0 && live) {
+          const int l = jb.slot[f];
+          if (l < 0) {
+            if (kDeform && f == 1 && jb.deform >= 0 && live) {
               const uint8_t* mw = a.mask_warp + (size_t)jb.deform * 2 * P + (size_t)y * W + x0;
-              const uint32_t wa = *reinterpret_cast<const uint32_t*>(mw), wn = *reinterpret_cast<const uint32_t*>(mw + P);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) { vaa[1][i] = (wa >> (8 * i)) & 255u; vna[1][i] = (wn >> (8 * i)) & 255u; }
+              vaa[1] = *reinterpret_cast<const uint32_t*>(mw);
+              vna[1] = *reinterpret_cast<const uint32_t*>(mw + P);
             }
             continue;
           }
-          const int l = jb.slot[f];
           const int4 c4 = *reinterpret_cast<const int4*>(&s_cover[l][warp][lane * 4]);
           const int4 a4 = *reinterpret_cast<const int4*>(&s_area[l][warp][lane * 4]);
+          const int carry = s_carry[l][warp];
+          const bool cells = (c4.x | c4.y | c4.z | c4.w | a4.x | a4.y | a4.z | a4.w) != 0;
+          if (!__any_sync(0xffffffffu, cells)) {
+            // no outline crosses this row inside the tile: coverage is constant along it
+            if (carry == 0) continue;
+            const int cv = coverage_alpha(carry, 0);
+            vaa[f] = graylut((unsigned)cv) * 0x01010101u;
+            vna[f] = cv >= 128 ? 0xFFFFFFFFu : 0u;
+            continue;
+          }
           int c[4] = {c4.x, c4.y, c4.z, c4.w}, ar[4] = {a4.x, a4.y, a4.z, a4.w};
           c[1] += c[0]; c[2] += c[1]; c[3] += c[2];
           int tot = c[3];  // warp-level inclusive prefix sum over the lanes' cover totals
@@ -437,34 +455,27 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
             int o = __shfl_up_sync(0xffffffffu, tot, d);
             if (lane >= d) tot += o;
           }
-          const int base = tot - c[3] + s_carry[l][warp];
+          const int base = tot - c[3] + carry;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int cv = coverage_alpha(base + c[i], ar[i]);
-            vaa[f][i] = graylut((unsigned)cv);  // gamma_none
-            vna[f][i] = cv >= 128 ? 255u : 0u;  // gamma_threshold(0.5), then graylut(255) = 255
+            vaa[f] |= graylut((unsigned)cv) << (8 * i);        // gamma_none
+            vna[f] |= (cv >= 128 ? 255u : 0u) << (8 * i);      // gamma_threshold(0.5), then graylut(255) = 255
           }
         }
         const HitObject ho = s_hit[jb.hit];
         if (ho.composite) {
-          if (jb.flags & 2) {
+          if (jb.flags & 2) { uaa[0] = uaa[1] = una[0] = una[1] = 0; }
+          const bool add = jb.flags & 1;
 #pragma unroll
-            for (int f = 0; f < 2; ++f)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) aa[f][i] = na[f][i] = 0;
+          for (int f = 0; f < 2; ++f) {
+            uaa[f] = comp4(uaa[f], vaa[f], add, s_q255);
+            // non-AA masks stay in {0, 255} (the rules are closed on it) unless a warp field resampled them
+            if (kDeform) una[f] = comp4(una[f], vna[f], add, s_q255);
+            else una[f] = add ? (una[f] | vna[f]) : (una[f] & ~vna[f]);
           }
-#pragma unroll
-          for (int f = 0; f < 2; ++f)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (jb.flags & 1) { aa[f][i] = comp_add(aa[f][i], vaa[f][i], s_q255); na[f][i] = comp_add(na[f][i], vna[f][i], s_q255); }
-              else { aa[f][i] = comp_sub(aa[f][i], vaa[f][i], s_q255); na[f][i] = comp_sub(na[f][i], vna[f][i], s_q255); }
-            }
         } else {
-#pragma unroll
-          for (int f = 0; f < 2; ++f)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { aa[f][i] = vaa[f][i]; na[f][i] = vna[f][i]; }
+          uaa[0] = vaa[0]; uaa[1] = vaa[1]; una[0] = vna[0]; una[1] = vna[1];
         }
         if (!(jb.flags & 4) || !live) continue;
 
@@ -472,34 +483,33 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
         const int k = ho.obj;
         if (a.dbg_masks && k < a.dbg_max_objs) {
           uint8_t* mb = a.dbg_masks + ((size_t)sample * a.dbg_max_objs + k) * 4 * P + (size_t)y * W + x0;
+          *reinterpret_cast<uint32_t*>(mb + 0 * P) = uaa[0]; *reinterpret_cast<uint32_t*>(mb + 1 * P) = uaa[1];
+          *reinterpret_cast<uint32_t*>(mb + 2 * P) = una[0]; *reinterpret_cast<uint32_t*>(mb + 3 * P) = una[1];
+        }
+        const uint32_t kk = (uint32_t)(k + 1) * 0x01010101u;
+        const uint32_t e0 = __vcmpeq4(una[0], 0xFFFFFFFFu), e1 = __vcmpeq4(una[1], 0xFFFFFFFFu);
+        id0 = (id0 & ~e0) | (kk & e0);
+        id1 = (id1 & ~e1) | (kk & e1);
+        const uint32_t m0w = a.use_aa ? uaa[0] : una[0], m1w = a.use_aa ? uaa[1] : una[1];
+        if ((m0w | m1w) == 0u) continue;
+        const uchar4* tex = a.pool + (size_t)ho.tex * a.tex_w * a.tex_h;
+        if (m0w) {
+          const uchar4* trow = tex + (size_t)(y + tex_oy) * a.tex_w + (x0 + tex_ox);  // identity warp == copy
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            mb[0 * P + i] = (uint8_t)aa[0][i]; mb[1 * P + i] = (uint8_t)aa[1][i];
-            mb[2 * P + i] = (uint8_t)na[0][i]; mb[3 * P + i] = (uint8_t)na[1][i];
+            const unsigned m0 = (m0w >> (8 * i)) & 255u;
+            if (m0) col0[i] = blend_rgbx(col0[i], ld_px(trow + i) & 0xFFFFFFu, m0);
           }
         }
-        const uchar4* tex = a.pool + (size_t)ho.tex * a.tex_w * a.tex_h;
-        unsigned any1 = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (na[0][i] == 255u) id0[i] = k + 1;
-          if (na[1][i] == 255u) id1[i] = k + 1;
-          const unsigned m0 = a.use_aa ? aa[0][i] : na[0][i];
-          if (m0) {
-            uint32_t t = ld_px(tex + (size_t)(y + tex_oy) * a.tex_w + (x0 + i + tex_ox)) & 0xFFFFFFu;  // identity warp == copy
-            col0[i] = blend_rgbx(col0[i], t, m0);
-          }
-          any1 |= a.use_aa ? aa[1][i] : na[1][i];
-        }
-        if (any1 && ho.field < 0) {
+        if (m1w && (!kDeform || ho.field < 0)) {
           RowWarp rw;
           rw.init(a.objects[obj_begin + k].tex_inv, (double)y, W);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const unsigned m1 = a.use_aa ? aa[1][i] : na[1][i];
+            const unsigned m1 = (m1w >> (8 * i)) & 255u;
             if (m1) col1[i] = blend_rgbx(col1[i], bilinear_rgbx(tex, a.tex_w, tex_ox, tex_oy, W, H, rw, x0 + i), m1);
           }
-        } else if (any1) {
+        } else if (kDeform && m1w) {
           // applyWarpFieldToTexture(getTransformedTexture(tex0, M), iflow) evaluated where the mask is set:
           // each of the 4 float-bilinear taps is itself one AGG span-bilinear pixel (DG.cpp:341-345)
           const double* tinv = a.objects[obj_begin + k].tex_inv;
@@ -512,7 +522,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
             return bilinear_rgbx(tex, a.tex_w, tex_ox, tex_oy, W, H, rw, px);
           };
           for (int i = 0; i < 4; ++i) {
-            const unsigned m1 = a.use_aa ? aa[1][i] : na[1][i];
+            const unsigned m1 = (m1w >> (8 * i)) & 255u;
             if (!m1) continue;
             const int x = x0 + i;
             const float sx = x + ifl[(size_t)y * fw + x], sy = y + ifl[(size_t)fw * fh + (size_t)y * fw + x];
@@ -532,7 +542,8 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float xf = (float)(x0 + i), yf = (float)y;
-    if (id0[i] == 0) {
+    const unsigned oid = (id0 >> (8 * i)) & 255u;
+    if (oid == 0) {
       double ix = xf + (float)(W / 2), iy = yf + (float)(H / 2);
       const float save_x = (float)ix, save_y = (float)iy;
       ix = ix - (double)W; iy = iy - (double)H;  // I^-1 = T(-W,-H)
@@ -543,7 +554,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
       ix = ix + (double)W; iy = iy + (double)H;  // I = T(W,H)
       fxv[i] = (float)(ix - save_x);
       fyv[i] = (float)(iy - save_y);
-      if (smp.bg_field >= 0 && ix >= 0 && ix < 2 * W && iy >= 0 && iy < 2 * H) {  // DG.cpp:714-717
+      if (kDeform && smp.bg_field >= 0 && ix >= 0 && ix < 2 * W && iy >= 0 && iy < 2 * H) {  // DG.cpp:714-717
         const int fw = W + 1, fh = H + 1;
         const float* fl = a.fields + ((size_t)smp.bg_field * 2 + 0) * 2 * fw * fh;
         auto at0 = [&](unsigned X, unsigned Y) { return resized_field2(fl, fw, fh, (int)X, (int)Y, a); };
@@ -552,17 +563,17 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
         fyv[i] += neumann_f(at1, 2 * W, 2 * H, (float)ix, (float)iy);
       }
     } else {
-      const double* m = a.objects[obj_begin + id0[i] - 1].motion;
+      const FlatObject& fo = a.objects[obj_begin + oid - 1];
+      const double* m = fo.motion;
       double ix = xf, iy = yf;
       double tmp = ix;
       ix = tmp * m[0] + iy * m[2] + m[4];
       iy = tmp * m[1] + iy * m[3] + m[5];
       fxv[i] = (float)(ix - xf);
       fyv[i] = (float)(iy - yf);
-      const int fld = a.objects[obj_begin + id0[i] - 1].field;
-      if (fld >= 0 && ix >= 0 && ix < W && iy >= 0 && iy < H) {  // DG.cpp:403-406
+      if (kDeform && fo.field >= 0 && ix >= 0 && ix < W && iy >= 0 && iy < H) {  // DG.cpp:403-406
         const int fw = W + 1, fh = H + 1;
-        const float* fl = a.fields + ((size_t)fld * 2 + 0) * 2 * fw * fh;
+        const float* fl = a.fields + ((size_t)fo.field * 2 + 0) * 2 * fw * fh;
         auto at0 = [&](unsigned X, unsigned Y) { return fl[(size_t)Y * fw + X]; };
         auto at1 = [&](unsigned X, unsigned Y) { return fl[(size_t)fw * fh + (size_t)Y * fw + X]; };
         fxv[i] += neumann_f(at0, fw, fh, (float)ix, (float)iy);
@@ -591,8 +602,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
   if (a.dbg_id0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const unsigned o0id = id0[i] ? (unsigned)a.objects[obj_begin + id0[i] - 1].obj_id : 1u;
-      const unsigned o1id = id1[i] ? (unsigned)a.objects[obj_begin + id1[i] - 1].obj_id : 1u;
+      const unsigned b0 = (id0 >> (8 * i)) & 255u, b1 = (id1 >> (8 * i)) & 255u;
+      const unsigned o0id = b0 ? (unsigned)a.objects[obj_begin + b0 - 1].obj_id : 1u;
+      const unsigned o1id = b1 ? (unsigned)a.objects[obj_begin + b1 - 1].obj_id : 1u;
       a.dbg_id0[(size_t)sample * P + pix + i] = o0id;
       if (a.dbg_id1) a.dbg_id1[(size_t)sample * P + pix + i] = o1id;
     }
@@ -915,7 +927,8 @@ int launch_deform_prepass(const RenderArgs& a, cudaStream_t s) {
 int launch_render(const RenderArgs& a, cudaStream_t s) {
   const int tiles_x = (a.W + TW - 1) / TW, tiles_y = (a.H + TH - 1) / TH;
   dim3 grid(tiles_x * tiles_y, a.batch);
-  render_kernel<<<grid, RENDER_THREADS, 0, s>>>(a);
+  if (a.n_fields > 0) render_kernel<true><<<grid, RENDER_THREADS, 0, s>>>(a);
+  else render_kernel<false><<<grid, RENDER_THREADS, 0, s>>>(a);
   return 1;
 }
 
