@@ -16,8 +16,10 @@
 
 #if defined(__CUDACC__)
 #define OFDG_HD __host__ __device__ __forceinline__
+#define OFDG_HD_NOINLINE inline __host__ __device__ __noinline__
 #else
 #define OFDG_HD inline
+#define OFDG_HD_NOINLINE inline
 #endif
 
 namespace ofdg {
@@ -41,27 +43,46 @@ struct Acc<true> {
 OFDG_HD int rt_min(int a, int b) { return a < b ? a : b; }
 OFDG_HD int rt_max(int a, int b) { return a > b ? a : b; }
 
-// floor(a / b) and the matching non-negative remainder, b > 0
+// floor(a / b) and the matching non-negative remainder, b > 0. Out of line on the device (the emulated
+// integer divide is ~40 instructions and there are five call sites); results come back in registers.
+struct QuotRem {
+  int q, r;
+};
+OFDG_HD_NOINLINE QuotRem floordivmod_qr(int a, int b) {
+  QuotRem o;
+  o.q = a / b;
+  o.r = a - o.q * b;
+  if (o.r < 0) { --o.q; o.r += b; }
+  return o;
+}
 OFDG_HD void floordivmod(int a, int b, int& q, int& r) {
-  q = a / b;
-  r = a - q * b;
-  if (r < 0) { --q; r += b; }
+  const QuotRem o = floordivmod_qr(a, b);
+  q = o.q;
+  r = o.r;
 }
 // 64-bit numerator (|num| < 2^52), 32-bit positive divisor, quotient fits 32 bits. One correctly
 // rounded double division plus an exact integer fix-up replaces the emulated 64-bit divide.
-OFDG_HD void floordivmod64(long long num, int den, int& q, int& r) {
+OFDG_HD_NOINLINE QuotRem floordivmod64_qr(long long num, int den) {
   long long qq = (long long)((double)num / (double)den);
   long long rr = num - qq * den;
   if (rr < 0) { --qq; rr += den; }
   if (rr < 0) { --qq; rr += den; }
   if (rr >= den) { ++qq; rr -= den; }
-  q = (int)qq;
-  r = (int)rr;
+  QuotRem o;
+  o.q = (int)qq;
+  o.r = (int)rr;
+  return o;
+}
+OFDG_HD void floordivmod64(long long num, int den, int& q, int& r) {
+  const QuotRem o = floordivmod64_qr(num, den);
+  q = o.q;
+  r = o.r;
 }
 
-// render_hline(ey, x1, y1, x2, y2) scattered into one tile row.
+// render_hline(ey, x1, y1, x2, y2) scattered into one tile row. Out of line on the device: tile_edge
+// calls it from two places and the render kernel has to stay inside the instruction cache.
 template <bool kDevice>
-OFDG_HD void tile_hline(int* cover, int* area, int* carry, int tx0, int x1, int y1, int x2, int y2) {
+OFDG_HD_NOINLINE void tile_hline(int* cover, int* area, int* carry, int tx0, int x1, int y1, int x2, int y2) {
   if (y1 == y2) return;
   const int ex1 = x1 >> 8, ex2 = x2 >> 8, fx1 = x1 & 255, fx2 = x2 & 255;
   const int dyv = y2 - y1;

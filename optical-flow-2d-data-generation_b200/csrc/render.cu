@@ -26,15 +26,19 @@ constexpr int RENDER_THREADS = 256;  // TH warps; lane = 4 consecutive pixels (o
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int iround_d(double v) { return int((v < 0.0) ? v - 0.5 : v + 0.5); }
 
-// agg::wrap_mode_reflect
-__device__ __forceinline__ int reflect(int v, int size) {
-  if ((unsigned)v < (unsigned)size) return v;
-  if (v < 0 && v >= -size) return -v - 1;          // one fold covers every tap near the image
-  if (v >= size && v < 2 * size) return 2 * size - v - 1;
+// agg::wrap_mode_reflect. The generic modulo form is kept out of line: every tap near the image needs one fold at most,
+// and the render kernel must stay small enough for the instruction cache.
+__device__ __noinline__ int reflect_far(int v, int size) {
   unsigned size2 = 2u * (unsigned)size;
   unsigned add = size2 * (0x3FFFFFFFu / size2);
   unsigned m = ((unsigned)v + add) % size2;
   return (int)(m >= (unsigned)size ? size2 - m - 1 : m);
+}
+__device__ __forceinline__ int reflect(int v, int size) {
+  if ((unsigned)v < (unsigned)size) return v;
+  if (v < 0 && v >= -size) return -v - 1;
+  if (v >= size && v < 2 * size) return 2 * size - v - 1;
+  return reflect_far(v, size);
 }
 // CImg mirror boundary: cimg::mod(i, 2n), then fold
 __device__ __forceinline__ int mirror(int i, int n) {
@@ -54,8 +58,13 @@ struct Dda2 {
     n = count;
     sh = (count & (count - 1)) == 0 ? 31 - __clz(count) : -1;  // 512 / 1024 wide frames: shift instead of divide
     int d = b - a;
-    lft = d / n;
-    rem = d % n;
+    if (sh >= 0) {  // C division truncates toward zero
+      lft = (d + ((d >> 31) & (n - 1))) >> sh;
+      rem = d - (lft << sh);
+    } else {
+      lft = d / n;
+      rem = d % n;
+    }
     if (rem <= 0) { rem += n; lft--; }
     v1 = a;
   }
@@ -84,6 +93,11 @@ struct RowWarp {
   }
 };
 
+// byte c of a packed pixel as float without the (quarter-rate) I2F unit: 0x4B0000xx is 8388608 + xx exactly
+__device__ __forceinline__ float byte_to_float(uint32_t px, int c) {
+  return __uint_as_float(__byte_perm(px, 0x4B000000u, 0x7440u + (unsigned)c)) - 8388608.0f;
+}
+
 __device__ __forceinline__ uint32_t ld_px(const uchar4* p) { return *reinterpret_cast<const uint32_t*>(p); }
 
 __device__ __forceinline__ uint32_t bilinear_rgbx(const uchar4* img, int pitch, int ox, int oy, int sw, int sh,
@@ -108,6 +122,17 @@ __device__ __forceinline__ uint32_t bilinear_rgbx(const uchar4* img, int pitch, 
     out |= (sacc >> 16) << (8 * c);
   }
   return out;
+}
+
+// Out-of-line copy for the render kernel's eight call sites (keeps its code inside the instruction cache);
+// scalar arguments only, so that everything travels in registers. base = img + oy * pitch + ox.
+__device__ __noinline__ uint32_t bilinear_rgbx_call(const uchar4* base, int pitch, int sw, int sh, int n, int v1x, int lftx, int remx,
+                                                    int v1y, int lfty, int remy, int i) {
+  RowWarp rw;
+  const int shift = (n & (n - 1)) == 0 ? 31 - __clz(n) : -1;
+  rw.dx.v1 = v1x; rw.dx.lft = lftx; rw.dx.rem = remx; rw.dx.n = n; rw.dx.sh = shift;
+  rw.dy.v1 = v1y; rw.dy.lft = lfty; rw.dy.rem = remy; rw.dy.n = n; rw.dy.sh = shift;
+  return bilinear_rgbx(base, pitch, 0, 0, sw, sh, rw, i);
 }
 
 // CImg draw_image(sprite, mask, 1, 255) per channel == floor((m*t + f*(255-m)) / 255)  
@@ -156,8 +181,7 @@ __device__ __forceinline__ uint32_t dirichlet_rgbx(Tap tap, float fx, float fy) 
   uint32_t out = 0;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float v = cimg_lerp2((float)((pcc >> (8 * c)) & 255u), (float)((pnc >> (8 * c)) & 255u), (float)((pcn >> (8 * c)) & 255u),
-                               (float)((pnn >> (8 * c)) & 255u), dx, dy);
+    const float v = cimg_lerp2(byte_to_float(pcc, c), byte_to_float(pnc, c), byte_to_float(pcn, c), byte_to_float(pnn, c), dx, dy);
     out |= ((uint32_t)(unsigned char)v) << (8 * c);
   }
   return out;
@@ -222,14 +246,8 @@ __device__ __forceinline__ unsigned comp_sub(unsigned u, unsigned v, const float
   if (v == 255u || u == 0u) return 0u;
   return (unsigned)(unsigned char)(255.f * ((q255[u]) * (1.f - q255[v])));
 }
-// The same rules on four pixels packed one byte each.
-__device__ __forceinline__ uint32_t comp4(uint32_t u, uint32_t v, bool additive, const float* q255) {
-  if (additive) {
-    if (v == 0xFFFFFFFFu) return 0xFFFFFFFFu;
-    if ((u | v) == 0u) return 0u;
-  } else {
-    if (v == 0xFFFFFFFFu || u == 0u) return 0u;
-  }
+// The same rules on four pixels packed one byte each (out of line: only outline pixels of composites get here).
+__device__ __noinline__ uint32_t comp4_bytes(uint32_t u, uint32_t v, bool additive, const float* q255) {
   uint32_t out = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -237,6 +255,15 @@ __device__ __forceinline__ uint32_t comp4(uint32_t u, uint32_t v, bool additive,
     out |= (additive ? comp_add(ub, vb, q255) : comp_sub(ub, vb, q255)) << (8 * i);
   }
   return out;
+}
+__device__ __forceinline__ uint32_t comp4(uint32_t u, uint32_t v, bool additive, const float* q255) {
+  if (additive) {
+    if (v == 0xFFFFFFFFu) return 0xFFFFFFFFu;
+    if ((u | v) == 0u) return 0u;
+  } else {
+    if (v == 0xFFFFFFFFu || u == 0u) return 0u;
+  }
+  return comp4_bytes(u, v, additive, q255);
 }
 
 // kDeform = false compiles the mode-9 (warp field) branches out.
@@ -279,10 +306,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
       RowWarp rw;
       rw.init(smp.bg_tex_inv, (double)(y + H / 2), W2);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        col0[i] = ld_px(row + i) & 0xFFFFFFu;
-        col1[i] = bilinear_rgbx(bg, W2, 0, 0, W2, H2, rw, x0 + i + W / 2);
-      }
+      for (int i = 0; i < 4; ++i) col0[i] = ld_px(row + i) & 0xFFFFFFu;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) col1[i] = bilinear_rgbx_call(bg, W2, W2, H2, W2, rw.dx.v1, rw.dx.lft, rw.dx.rem, rw.dy.v1, rw.dy.lft, rw.dy.rem, x0 + i + W / 2);
       if (kDeform && smp.bg_field >= 0) {
         // background with a warp field: the warped 2W x 2H texture is resampled through the resized,
         // doubled inverse field before the centre crop (DG.cpp:670-681, 1194-1201)
@@ -507,7 +533,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const unsigned m1 = (m1w >> (8 * i)) & 255u;
-            if (m1) col1[i] = blend_rgbx(col1[i], bilinear_rgbx(tex, a.tex_w, tex_ox, tex_oy, W, H, rw, x0 + i), m1);
+            if (m1) col1[i] = blend_rgbx(col1[i], bilinear_rgbx_call(tex + (size_t)tex_oy * a.tex_w + tex_ox, a.tex_w, W, H, W, rw.dx.v1, rw.dx.lft, rw.dx.rem, rw.dy.v1, rw.dy.lft, rw.dy.rem, x0 + i), m1);
           }
         } else if (kDeform && m1w) {
           // applyWarpFieldToTexture(getTransformedTexture(tex0, M), iflow) evaluated where the mask is set:
@@ -543,37 +569,31 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
   for (int i = 0; i < 4; ++i) {
     const float xf = (float)(x0 + i), yf = (float)y;
     const unsigned oid = (id0 >> (8 * i)) & 255u;
-    if (oid == 0) {
-      double ix = xf + (float)(W / 2), iy = yf + (float)(H / 2);
-      const float save_x = (float)ix, save_y = (float)iy;
-      ix = ix - (double)W; iy = iy - (double)H;  // I^-1 = T(-W,-H)
-      const double* m = smp.bg_motion;
-      double tmp = ix;
-      ix = tmp * m[0] + iy * m[2] + m[4];
-      iy = tmp * m[1] + iy * m[3] + m[5];
-      ix = ix + (double)W; iy = iy + (double)H;  // I = T(W,H)
-      fxv[i] = (float)(ix - save_x);
-      fyv[i] = (float)(iy - save_y);
-      if (kDeform && smp.bg_field >= 0 && ix >= 0 && ix < 2 * W && iy >= 0 && iy < 2 * H) {  // DG.cpp:714-717
-        const int fw = W + 1, fh = H + 1;
-        const float* fl = a.fields + ((size_t)smp.bg_field * 2 + 0) * 2 * fw * fh;
-        auto at0 = [&](unsigned X, unsigned Y) { return resized_field2(fl, fw, fh, (int)X, (int)Y, a); };
-        auto at1 = [&](unsigned X, unsigned Y) { return resized_field2(fl + (size_t)fw * fh, fw, fh, (int)X, (int)Y, a); };
-        fxv[i] += neumann_f(at0, 2 * W, 2 * H, (float)ix, (float)iy);
-        fyv[i] += neumann_f(at1, 2 * W, 2 * H, (float)ix, (float)iy);
-      }
-    } else {
-      const FlatObject& fo = a.objects[obj_begin + oid - 1];
-      const double* m = fo.motion;
-      double ix = xf, iy = yf;
-      double tmp = ix;
-      ix = tmp * m[0] + iy * m[2] + m[4];
-      iy = tmp * m[1] + iy * m[3] + m[5];
-      fxv[i] = (float)(ix - xf);
-      fyv[i] = (float)(iy - yf);
-      if (kDeform && fo.field >= 0 && ix >= 0 && ix < W && iy >= 0 && iy < H) {  // DG.cpp:403-406
-        const int fw = W + 1, fh = H + 1;
-        const float* fl = a.fields + ((size_t)fo.field * 2 + 0) * 2 * fw * fh;
+    // background: the point goes through I^-1 = T(-W,-H), M, I = T(W,H) (DG.cpp:697-712); objects: through M alone.
+    // One code path: the translations are exact no-ops (+-0.0) for objects.
+    const FlatObject* fo = oid ? a.objects + obj_begin + oid - 1 : nullptr;
+    const double* m = oid ? fo->motion : smp.bg_motion;
+    const double pre_x = oid ? 0.0 : (double)W, pre_y = oid ? 0.0 : (double)H;
+    const float save_x = oid ? xf : xf + (float)(W / 2), save_y = oid ? yf : yf + (float)(H / 2);
+    double ix = (double)save_x - pre_x, iy = (double)save_y - pre_y;
+    const double tmp = ix;
+    ix = tmp * m[0] + iy * m[2] + m[4];
+    iy = tmp * m[1] + iy * m[3] + m[5];
+    ix = ix + pre_x; iy = iy + pre_y;
+    fxv[i] = (float)(ix - save_x);
+    fyv[i] = (float)(iy - save_y);
+    if (kDeform) {
+      const int fw = W + 1, fh = H + 1;
+      if (oid == 0) {
+        if (smp.bg_field >= 0 && ix >= 0 && ix < 2 * W && iy >= 0 && iy < 2 * H) {  // DG.cpp:714-717
+          const float* fl = a.fields + ((size_t)smp.bg_field * 2 + 0) * 2 * fw * fh;
+          auto at0 = [&](unsigned X, unsigned Y) { return resized_field2(fl, fw, fh, (int)X, (int)Y, a); };
+          auto at1 = [&](unsigned X, unsigned Y) { return resized_field2(fl + (size_t)fw * fh, fw, fh, (int)X, (int)Y, a); };
+          fxv[i] += neumann_f(at0, 2 * W, 2 * H, (float)ix, (float)iy);
+          fyv[i] += neumann_f(at1, 2 * W, 2 * H, (float)ix, (float)iy);
+        }
+      } else if (fo->field >= 0 && ix >= 0 && ix < W && iy >= 0 && iy < H) {  // DG.cpp:403-406
+        const float* fl = a.fields + ((size_t)fo->field * 2 + 0) * 2 * fw * fh;
         auto at0 = [&](unsigned X, unsigned Y) { return fl[(size_t)Y * fw + X]; };
         auto at1 = [&](unsigned X, unsigned Y) { return fl[(size_t)fw * fh + (size_t)Y * fw + X]; };
         fxv[i] += neumann_f(at0, fw, fh, (float)ix, (float)iy);
@@ -589,10 +609,8 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
   float* of = a.flow + (size_t)sample * 2 * P + pix;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    float4 v0 = make_float4((float)((col0[0] >> (8 * c)) & 255u), (float)((col0[1] >> (8 * c)) & 255u),
-                            (float)((col0[2] >> (8 * c)) & 255u), (float)((col0[3] >> (8 * c)) & 255u));
-    float4 v1 = make_float4((float)((col1[0] >> (8 * c)) & 255u), (float)((col1[1] >> (8 * c)) & 255u),
-                            (float)((col1[2] >> (8 * c)) & 255u), (float)((col1[3] >> (8 * c)) & 255u));
+    float4 v0 = make_float4(byte_to_float(col0[0], c), byte_to_float(col0[1], c), byte_to_float(col0[2], c), byte_to_float(col0[3], c));
+    float4 v1 = make_float4(byte_to_float(col1[0], c), byte_to_float(col1[1], c), byte_to_float(col1[2], c), byte_to_float(col1[3], c));
     __stcs(reinterpret_cast<float4*>(o0 + c * P), v0);
     __stcs(reinterpret_cast<float4*>(o1 + c * P), v1);
   }
@@ -751,8 +769,7 @@ __device__ __forceinline__ uint32_t rotated_px(const uchar4* tex, int w, int h, 
   uint32_t out = 0;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float Icc = (float)((pcc >> (8 * c)) & 255u), Inc = (float)((pnc >> (8 * c)) & 255u),
-                Icn = (float)((pcn >> (8 * c)) & 255u), Inn = (float)((pnn >> (8 * c)) & 255u);
+    const float Icc = byte_to_float(pcc, c), Inc = byte_to_float(pnc, c), Icn = byte_to_float(pcn, c), Inn = byte_to_float(pnn, c);
     const float v = Icc + dx * (Inc - Icc + dy * (Icc + Inn - Icn - Inc)) + dy * (Icn - Icc);
     out |= ((uint32_t)(unsigned char)v) << (8 * c);
   }
@@ -773,7 +790,7 @@ __device__ __forceinline__ uint32_t resize_at(const uint32_t* src, int stride, i
       const float d = (float)(e - b);
       const uint32_t p = src[((int)s - s0) * stride];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) acc[c] += (float)((p >> (8 * c)) & 255u) * d;
+      for (int c = 0; c < 3; ++c) acc[c] += byte_to_float(p, c) * d;
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) out |= ((uint32_t)(unsigned char)(acc[c] / (float)(unsigned int)len)) << (8 * c);
@@ -816,9 +833,15 @@ __global__ void __launch_bounds__(PREP_THREADS) bg_prep_kernel(RenderArgs a) {
   const uchar4* tex = a.pool + (size_t)p.tex * a.tex_w * a.tex_h;
   // A: crop(x0, y0, .., mirror) of the rotated image
   const int lane_x = threadIdx.x & 31, lane_y = threadIdx.x >> 5;
-  for (int ly = lane_y; ly < ch; ly += PREP_THREADS / 32)
-    for (int lx = lane_x; lx < cw; lx += 32)
+  {  // all lanes busy: walk the cw x ch source tile linearly, stepping (x, y) by 256 items without a divide per item
+    const int step_y = PREP_THREADS / cw, step_x = PREP_THREADS % cw;
+    int lx = (int)threadIdx.x % cw, ly = (int)threadIdx.x / cw;
+    while (ly < ch) {
       sA[ly][lx] = rotated_px(tex, a.tex_w, a.tex_h, p, mirror(p.crop_x0 + cx0 + lx, p.rw), mirror(p.crop_y0 + cy0 + ly, p.rh));
+      lx += step_x; ly += step_y;
+      if (lx >= cw) { lx -= cw; ++ly; }
+    }
+  }
   __syncthreads();
   // B: resize along x
   const int tw = X1 - X0 + 1, th = Y1 - Y0 + 1;

@@ -158,3 +158,16 @@ def test_mode9_nonrigid_parity(ofdg, oracle, textures8, fields4):
     assert np.array_equal(ok, np.isfinite(gpu["flow"]))  # NaN flow where the field is NaN, exactly like the reference
     assert np.abs(gpu["flow"][ok] - cpu["flow"][ok]).max() <= FLOW_TOL
     g.close()
+
+
+def test_double_resolution(ofdg, oracle):
+    """Stress config: 2x output resolution (runtime W, H; the reference only has #defines)."""
+    W, H = 1024, 768
+    tex = ofdg.synth_textures(3, 2 * W, 2 * H, seed=11)
+    g = ofdg.Generator(device=0, width=W, height=H, mode=7, max_batch=2)
+    g.upload_textures(tex)
+    tasks = ofdg.ParamStream(7, W, H, fg_override=40).generate(2)
+    gpu = g.render_debug(tasks, max_objs=40)
+    cpu = oracle.render(tasks.struct(), tex, W=W, H=H, mode=7, debug=True, max_objs=40)
+    _compare(gpu, cpu)
+    g.close()
