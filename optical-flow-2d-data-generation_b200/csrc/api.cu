@@ -113,10 +113,15 @@ struct ofdg_prepared {
 struct ofdg_generator {
   ofdg_config cfg{};
   cudaStream_t stream = nullptr;
-  // ring of event pairs bracketing the render kernel of each call (roofline timing)
-  std::vector<cudaEvent_t> evs;
-  size_t ev_used = 0;
+  // CUDA-event spans around every background-preparation / render launch (roofline timing)
+  struct Span { cudaEvent_t a, b; int kind; };  // kind 0 = background preparation, 1 = render
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_next = 0;
+  std::vector<Span> spans;
+  uint64_t timed_calls = 0;
   size_t last_upload_bytes = 0;
+  int scratch_batch = 0;
+  DevBuf rtab_pos_x, rtab_alpha_x, rtab_pos_y, rtab_alpha_y;  // CImg linear-resize tables for every source length
   // texture pool
   DevBuf pool;
   int n_tex = 0, tex_w = 0, tex_h = 0;
@@ -127,7 +132,7 @@ struct ofdg_generator {
   // per-call scene staging + scratch
   DeviceScene scene;
   PinnedBuf staging;
-  DevBuf bg, pos_x, alpha_x, pos_y, alpha_y;
+  DevBuf bg;
   DevBuf out0, out1, outf;  // device blobs for the *_host entry points
   DevBuf dbg_masks, dbg_id0, dbg_id1, dbg_frames8, dbg_planar;
   ofdg::FlatBatch flat;
@@ -193,12 +198,11 @@ void flatten_tasks(ofdg_generator* g, const ofdg_task_batch* tasks, ofdg::FlatBa
 }
 
 void ensure_scratch(ofdg_generator* g, int batch) {
+  if (batch <= g->scratch_batch) return;
+  CK(cudaDeviceSynchronize());  // growing the scratch while earlier launches may still read it: drain first
   const size_t W = g->cfg.width, H = g->cfg.height;
   g->bg.reserve((size_t)batch * 4 * W * H * sizeof(uchar4));
-  g->pos_x.reserve((size_t)batch * 2 * W * sizeof(int));
-  g->alpha_x.reserve((size_t)batch * 2 * W * sizeof(double));
-  g->pos_y.reserve((size_t)batch * 2 * H * sizeof(int));
-  g->alpha_y.reserve((size_t)batch * 2 * H * sizeof(double));
+  g->scratch_batch = batch;
 }
 
 ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, float* d1, float* df) {
@@ -213,8 +217,8 @@ ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, 
   a.pool = (const uchar4*)g->pool.p;
   a.tex_w = g->tex_w; a.tex_h = g->tex_h;
   a.bg = (uchar4*)g->bg.p;
-  a.pos_x = (int*)g->pos_x.p; a.alpha_x = (double*)g->alpha_x.p;
-  a.pos_y = (int*)g->pos_y.p; a.alpha_y = (double*)g->alpha_y.p;
+  a.pos_x = (const int*)g->rtab_pos_x.p; a.alpha_x = (const double*)g->rtab_alpha_x.p;
+  a.pos_y = (const int*)g->rtab_pos_y.p; a.alpha_y = (const double*)g->rtab_alpha_y.p;
   a.fields = (const float*)g->fields.p;
   a.n_fields = g->n_fields;
   a.n_deform = ds.n_deform;
@@ -233,21 +237,35 @@ ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, 
   return a;
 }
 
-// bg prep + render on stream s; times the render kernel with events on that stream.
-void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s) {
-  if (g->ev_used + 3 > g->evs.size()) {
-    if (g->evs.size() >= 3 * 8192) g->ev_used = 0;  // wrap: only the most recent calls are kept
-    else
-      for (int i = 0; i < 3; ++i) { cudaEvent_t e; CK(cudaEventCreate(&e)); g->evs.push_back(e); }
+cudaEvent_t timing_event(ofdg_generator* g) {
+  if (g->ev_next == g->ev_pool.size()) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    g->ev_pool.push_back(e);
   }
-  cudaEvent_t e0 = g->evs[g->ev_used], e1 = g->evs[g->ev_used + 1], e2 = g->evs[g->ev_used + 2];
-  g->ev_used += 3;
-  CK(cudaEventRecord(e0, s));
+  return g->ev_pool[g->ev_next++];
+}
+
+// Background preparation + render of one batch on stream s, every launch bracketed by events.
+// (Running the preparation of the next chunk on a second stream next to the render kernel was
+// measured and is slower: both kernels are issue-bound and the extra launches cost more than the
+// overlap gains -- profiles/README.md.)
+void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s) {
+  if (g->spans.size() > 60000) { g->spans.clear(); g->ev_next = 0; g->timed_calls = 0; }  // nobody is reading the timings
   g->launches += ofdg::launch_deform_prepass(a, s);
+  ofdg_generator::Span sp{timing_event(g), timing_event(g), 0};
+  CK(cudaEventRecord(sp.a, s));
   g->launches += ofdg::launch_background_prep(a, s);
-  CK(cudaEventRecord(e1, s));
-  g->launches += ofdg::launch_render(a, s);
-  CK(cudaEventRecord(e2, s));
+  CK(cudaEventRecord(sp.b, s));
+  g->spans.push_back(sp);
+  if (a.img0) {
+    ofdg_generator::Span sr{timing_event(g), timing_event(g), 1};
+    CK(cudaEventRecord(sr.a, s));
+    g->launches += ofdg::launch_render(a, s);
+    CK(cudaEventRecord(sr.b, s));
+    g->spans.push_back(sr);
+  }
+  ++g->timed_calls;
   CK(cudaGetLastError());
 }
 
@@ -390,6 +408,16 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
     g->cfg = *cfg;
     CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
+    {  // one-time: the resize tables for every possible crop length (they depend on nothing else)
+      const size_t W2 = 2 * (size_t)cfg->width, H2 = 2 * (size_t)cfg->height;
+      g->rtab_pos_x.reserve(W2 * W2 * sizeof(int)); g->rtab_alpha_x.reserve(W2 * W2 * sizeof(double));
+      g->rtab_pos_y.reserve(H2 * H2 * sizeof(int)); g->rtab_alpha_y.reserve(H2 * H2 * sizeof(double));
+      ofdg::launch_resize_tables((int*)g->rtab_pos_x.p, (double*)g->rtab_alpha_x.p, (int)W2, g->stream);
+      ofdg::launch_resize_tables((int*)g->rtab_pos_y.p, (double*)g->rtab_alpha_y.p, (int)H2, g->stream);
+      g->launches += 2;
+      CK(cudaStreamSynchronize(g->stream));
+      CK(cudaGetLastError());
+    }
     for (int i = 0; i < 2; ++i) {
       CK(cudaEventCreateWithFlags(&g->pipe_uploaded[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&g->pipe_rendered[i], cudaEventDisableTiming));
@@ -402,7 +430,7 @@ void ofdg_destroy(ofdg_generator* g) {
   if (!g) return;
   cudaSetDevice(g->cfg.device);
   if (g->stream) cudaStreamSynchronize(g->stream);
-  DevBuf* bufs[] = {&g->pool, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->bg, &g->pos_x, &g->alpha_x, &g->pos_y, &g->alpha_y, &g->out0, &g->out1,
+  DevBuf* bufs[] = {&g->pool, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->bg, &g->rtab_pos_x, &g->rtab_alpha_x, &g->rtab_pos_y, &g->rtab_alpha_y, &g->out0, &g->out1,
                     &g->outf, &g->dbg_masks, &g->dbg_id0, &g->dbg_id1, &g->dbg_frames8, &g->dbg_planar};
   for (DevBuf* b : bufs) b->release();
   g->scene.release();
@@ -414,7 +442,7 @@ void ofdg_destroy(ofdg_generator* g) {
     if (g->pipe_rendered[i]) cudaEventDestroy(g->pipe_rendered[i]);
   }
   if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
-  for (cudaEvent_t e : g->evs) cudaEventDestroy(e);
+  for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
 }
@@ -646,7 +674,7 @@ int ofdg_debug_background(ofdg_generator* g, const ofdg_task_batch* tasks, uint8
     CK(cudaMemsetAsync(g->bg.p, 0, n * P4 * sizeof(uchar4), s));
     upload_scene(g, g->flat, g->scene, g->staging, s);
     ofdg::RenderArgs a = make_args(g, g->scene, nullptr, nullptr, nullptr);
-    g->launches += ofdg::launch_background_prep(a, s);
+    run_kernels(g, a, s);
     g->dbg_planar.reserve(n * 3 * P4);
     ofdg::launch_bg_to_planar((const uchar4*)g->bg.p, (uint8_t*)g->dbg_planar.p, (int)n, 2 * g->cfg.width, 2 * g->cfg.height, s);
     g->launches += n;
@@ -720,19 +748,19 @@ int ofdg_kernel_times(ofdg_generator* g, double* prep_ms, double* render_ms, int
   return guarded([&] {
     if (!g) throw ArgError("null pointer");
     g->use();
-    double p = 0, r = 0;
-    const size_t n = g->ev_used / 3;
-    for (size_t i = 0; i < n; ++i) {
-      float a = 0.f, b = 0.f;
-      CK(cudaEventSynchronize(g->evs[3 * i + 2]));
-      CK(cudaEventElapsedTime(&a, g->evs[3 * i], g->evs[3 * i + 1]));
-      CK(cudaEventElapsedTime(&b, g->evs[3 * i + 1], g->evs[3 * i + 2]));
-      p += a; r += b;
+    CK(cudaDeviceSynchronize());
+    double t[2] = {0, 0};
+    for (const ofdg_generator::Span& sp : g->spans) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+      t[sp.kind] += ms;
     }
-    g->ev_used = 0;
-    if (prep_ms) *prep_ms = p;
-    if (render_ms) *render_ms = r;
-    if (calls) *calls = (int32_t)n;
+    if (prep_ms) *prep_ms = t[0];
+    if (render_ms) *render_ms = t[1];
+    if (calls) *calls = (int32_t)g->timed_calls;
+    g->spans.clear();
+    g->ev_next = 0;
+    g->timed_calls = 0;
   });
 }
 uint64_t ofdg_last_upload_bytes(const ofdg_generator* g) { return g ? g->last_upload_bytes : 0; }

@@ -116,8 +116,8 @@ __device__ __forceinline__ uint32_t bilinear_rgbx(const uchar4* img, int pitch, 
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const unsigned sel = (unsigned)c | ((4u + c) << 4) | ((unsigned)c << 8) | (3u << 12);
-    const unsigned top = __dp4a(__byte_perm(p00, p10, sel) & 0xFFFFFFu, wx, 0u);
-    const unsigned bot = __dp4a(__byte_perm(p01, p11, sel) & 0xFFFFFFu, wx, 0u);
+    const unsigned top = __dp4a(__byte_perm(p00, p10, sel), wx, 0u);
+    const unsigned bot = __dp4a(__byte_perm(p01, p11, sel), wx, 0u);
     const unsigned sacc = 32768u + top * (256u - fy) + bot * fy;
     out |= (sacc >> 16) << (8 * c);
   }
@@ -711,17 +711,13 @@ __global__ void deform_warp_kernel(RenderArgs a) {
 // background texture preparation (CImg chain)
 // ------------------------------------------------------------------------------------------------
 // Linear-resize tables of CImg::get_resize (interpolation 3, growing axis): the source position is
-// accumulated by repeated double additions, so it is produced sequentially, one thread per axis.
-__global__ void bg_tables_kernel(RenderArgs a) {
-  const int sample = blockIdx.x;
-  const BgPrep& p = a.samples[sample].prep;
-  const int axis = threadIdx.x;  // 0 = x, 1 = y
-  if (axis > 1) return;
-  const int n = axis == 0 ? 2 * a.W : 2 * a.H;
-  const int len = axis == 0 ? p.crop_w : p.crop_h;
-  if (!(len < n) || len <= 1) return;  // only the growing, linear case reads the tables
-  int* pos = (axis == 0 ? a.pos_x : a.pos_y) + (size_t)sample * n;
-  double* alpha = (axis == 0 ? a.alpha_x : a.alpha_y) + (size_t)sample * n;
+// accumulated by repeated double additions, so a table is a sequential chain -- but it depends on the
+// source length only. All tables (len = 2 .. n-1 -> n) are produced once at start-up, one thread each.
+__global__ void resize_tables_kernel(int* pos_all, double* alpha_all, int n) {
+  const int len = blockIdx.x * blockDim.x + threadIdx.x;
+  if (len < 2 || len >= n) return;
+  int* pos = pos_all + (size_t)len * n;
+  double* alpha = alpha_all + (size_t)len * n;
   const double f = n > 1 ? (len - 1.0) / (n - 1) : 0;
   double curr = 0, old = 0;
   unsigned q = 0;
@@ -822,10 +818,10 @@ __global__ void __launch_bounds__(PREP_THREADS) bg_prep_kernel(RenderArgs a) {
   const int X0 = p.need[0] + blockIdx.x * PT, Y0 = p.need[1] + blockIdx.y * PT;
   if (X0 > p.need[2] || Y0 > p.need[3]) return;
   const int X1 = min(X0 + PT - 1, p.need[2]), Y1 = min(Y0 + PT - 1, p.need[3]);
-  const int* pos_x = a.pos_x + (size_t)sample * W2;
-  const double* alpha_x = a.alpha_x + (size_t)sample * W2;
-  const int* pos_y = a.pos_y + (size_t)sample * H2;
-  const double* alpha_y = a.alpha_y + (size_t)sample * H2;
+  const int* pos_x = a.pos_x + (size_t)min(p.crop_w, W2 - 1) * W2;  // rows >= n are never read (no table needed when shrinking)
+  const double* alpha_x = a.alpha_x + (size_t)min(p.crop_w, W2 - 1) * W2;
+  const int* pos_y = a.pos_y + (size_t)min(p.crop_h, H2 - 1) * H2;
+  const double* alpha_y = a.alpha_y + (size_t)min(p.crop_h, H2 - 1) * H2;
   int cx0, cx1, cy0, cy1;
   source_range(p.crop_w, W2, X0, X1, pos_x, cx0, cx1);
   source_range(p.crop_h, H2, Y0, Y1, pos_y, cy0, cy1);
@@ -931,11 +927,14 @@ void launch_composite_luts(uint8_t* add_lut, uint8_t* sub_lut, cudaStream_t s) {
   composite_lut_kernel<<<256, 256, 0, s>>>(add_lut, sub_lut);
 }
 
+void launch_resize_tables(int* pos, double* alpha, int n, cudaStream_t s) {
+  resize_tables_kernel<<<(n + 63) / 64, 64, 0, s>>>(pos, alpha, n);
+}
+
 int launch_background_prep(const RenderArgs& a, cudaStream_t s) {
-  bg_tables_kernel<<<a.batch, 32, 0, s>>>(a);
   dim3 grid((2 * a.W + PT - 1) / PT, (2 * a.H + PT - 1) / PT, a.batch);
   bg_prep_kernel<<<grid, PREP_THREADS, 0, s>>>(a);
-  return 2;
+  return 1;
 }
 
 int launch_deform_prepass(const RenderArgs& a, cudaStream_t s) {

@@ -19,12 +19,13 @@ struct RenderArgs {
   // texture pool: RGBX8 interleaved, [n][tex_h][tex_w]
   const uchar4* pool;
   int tex_w, tex_h;
-  // per-sample prepared background texture, RGBX8 [batch][2H][2W], and linear-resize tables
+  // per-sample prepared background texture, RGBX8 [batch][2H][2W]
   uchar4* bg;
-  int* pos_x;        // [batch][2W]
-  double* alpha_x;   // [batch][2W]
-  int* pos_y;        // [batch][2H]
-  double* alpha_y;   // [batch][2H]
+  // CImg linear-resize tables for every source length: row `len` of pos_x/alpha_x ([2W][2W]) describes len -> 2W
+  const int* pos_x;
+  const double* alpha_x;
+  const int* pos_y;        // [2H][2H]
+  const double* alpha_y;
   // mode 9
   const float* fields;        // [n][flow|iflow][channel][H+1][W+1]
   int n_fields;
@@ -54,6 +55,7 @@ int launch_background_prep(const RenderArgs& a, cudaStream_t s);
 int launch_render(const RenderArgs& a, cudaStream_t s);
 int launch_deform_prepass(const RenderArgs& a, cudaStream_t s);  // mode 9 only; no-op when n_deform == 0
 
+void launch_resize_tables(int* pos, double* alpha, int n, cudaStream_t s);  // one-time, all lengths 1..n-1 -> n
 void launch_planar_to_rgbx(const uint8_t* planar, uchar4* out, int n, int w, int h, cudaStream_t s);
 void launch_rgbx_to_planar(const uchar4* in, uint8_t* planar, int w, int h, cudaStream_t s);
 void launch_synth_textures(uchar4* out, int n, int w, int h, uint64_t seed, int first_index, cudaStream_t s);
