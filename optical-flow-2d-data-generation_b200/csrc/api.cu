@@ -132,7 +132,7 @@ struct ofdg_generator {
   // per-call scene staging + scratch
   DeviceScene scene;
   PinnedBuf staging;
-  DevBuf bg;
+  DevBuf bg, tile_hits;
   DevBuf out0, out1, outf;  // device blobs for the *_host entry points
   DevBuf dbg_masks, dbg_id0, dbg_id1, dbg_frames8, dbg_planar;
   ofdg::FlatBatch flat;
@@ -202,6 +202,7 @@ void ensure_scratch(ofdg_generator* g, int batch) {
   CK(cudaDeviceSynchronize());  // growing the scratch while earlier launches may still read it: drain first
   const size_t W = g->cfg.width, H = g->cfg.height;
   g->bg.reserve((size_t)batch * 4 * W * H * sizeof(uchar4));
+  g->tile_hits.reserve(ofdg::tile_hits_bytes(batch, (int)W, (int)H));
   g->scratch_batch = batch;
 }
 
@@ -217,6 +218,7 @@ ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, 
   a.pool = (const uchar4*)g->pool.p;
   a.tex_w = g->tex_w; a.tex_h = g->tex_h;
   a.bg = (uchar4*)g->bg.p;
+  a.tile_hits = (uint8_t*)g->tile_hits.p;
   a.pos_x = (const int*)g->rtab_pos_x.p; a.alpha_x = (const double*)g->rtab_alpha_x.p;
   a.pos_y = (const int*)g->rtab_pos_y.p; a.alpha_y = (const double*)g->rtab_alpha_y.p;
   a.fields = (const float*)g->fields.p;
@@ -255,6 +257,7 @@ void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s) {
   g->launches += ofdg::launch_deform_prepass(a, s);
   ofdg_generator::Span sp{timing_event(g), timing_event(g), 0};
   CK(cudaEventRecord(sp.a, s));
+  g->launches += ofdg::launch_bin(a, s);
   g->launches += ofdg::launch_background_prep(a, s);
   CK(cudaEventRecord(sp.b, s));
   g->spans.push_back(sp);
@@ -430,7 +433,7 @@ void ofdg_destroy(ofdg_generator* g) {
   if (!g) return;
   cudaSetDevice(g->cfg.device);
   if (g->stream) cudaStreamSynchronize(g->stream);
-  DevBuf* bufs[] = {&g->pool, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->bg, &g->rtab_pos_x, &g->rtab_alpha_x, &g->rtab_pos_y, &g->rtab_alpha_y, &g->out0, &g->out1,
+  DevBuf* bufs[] = {&g->pool, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->bg, &g->tile_hits, &g->rtab_pos_x, &g->rtab_alpha_x, &g->rtab_pos_y, &g->rtab_alpha_y, &g->out0, &g->out1,
                     &g->outf, &g->dbg_masks, &g->dbg_id0, &g->dbg_id1, &g->dbg_frames8, &g->dbg_planar};
   for (DevBuf* b : bufs) b->release();
   g->scene.release();

@@ -213,6 +213,31 @@ __device__ __forceinline__ bool box_hits_tile(const int32_t* b, int tx0, int ty0
 }
 
 // ------------------------------------------------------------------------------------------------
+// binning: which objects touch which tile (so that background-only tiles never enter the object path)
+// ------------------------------------------------------------------------------------------------
+__global__ void bin_kernel(RenderArgs a) {
+  __shared__ int s_box[256][8];
+  const int sample = blockIdx.x;
+  const FlatSample& smp = a.samples[sample];
+  const int n_obj = smp.obj_count;
+  const int tiles_x = (a.W + TW - 1) / TW, tiles_y = (a.H + TH - 1) / TH, n_tiles = tiles_x * tiles_y;
+  for (int i = threadIdx.x; i < min(n_obj, 256) * 8; i += blockDim.x) s_box[i >> 3][i & 7] = (&a.objects[smp.obj_begin + (i >> 3)].bbox[0][0])[i & 7];
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+    const int tx0 = (t % tiles_x) * TW, ty0 = (t / tiles_x) * TH;
+    uint8_t* out = a.tile_hits + ((size_t)sample * n_tiles + t) * TILE_HIT_STRIDE;
+    int cnt = 0;
+    for (int o = 0; o < n_obj; ++o) {
+      if (box_hits_tile(&s_box[o][0], tx0, ty0) || box_hits_tile(&s_box[o][4], tx0, ty0)) {
+        if (cnt < TILE_HIT_STRIDE - 1) out[1 + cnt] = (uint8_t)o;
+        ++cnt;
+      }
+    }
+    out[0] = (uint8_t)(cnt <= TILE_HIT_STRIDE - 1 ? cnt : 255);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // render kernel: one CTA per (tile, sample); warp = tile row, lane = 4 consecutive pixels
 // ------------------------------------------------------------------------------------------------
 constexpr int NLAYER = 4;      // cover/area accumulator layers that are filled between two barriers
@@ -290,8 +315,11 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
   const size_t P = (size_t)W * H;
   const int n_obj = smp.obj_count, obj_begin = smp.obj_begin;
 
+  const uint8_t* bins = a.tile_hits + ((size_t)sample * gridDim.x + blockIdx.x) * TILE_HIT_STRIDE;
+  const int binned = bins[0];  // objects touching this tile (255: more than a bin entry lists)
+
   s_q255[tid] = (float)tid / 255.f;
-  if (tid == 0) s_next_obj = 0;
+  if (tid == 0) s_next_obj = binned ? 0 : n_obj;  // background-only tiles skip the object path entirely
 
   uint32_t col0[4], col1[4];
   uint32_t id0 = 0, id1 = 0;  // four pixels, one byte each: 0 = background, k+1 = k-th foreground object (k < 255)
@@ -341,29 +369,44 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
     __syncthreads();
     const int obj0 = s_next_obj;
     if (obj0 >= n_obj) break;
-    // (1) warp 0: objects whose boxes touch the tile -> ordered hit table
+    // (1) warp 0: objects whose boxes touch the tile -> ordered hit table (from the bin list, or by a scan
+    //     when the tile holds more objects than a bin entry can list)
     if (warp == 0) {
       int nh = 0, next = n_obj;
-      for (int o = obj0; o < n_obj; o += 32) {
-        const int idx = o + lane;
-        bool hit = false;
-        const FlatObject* ob = a.objects + obj_begin + idx;
-        if (idx < n_obj) hit = box_hits_tile(ob->bbox[0], tx0, ty0) || box_hits_tile(ob->bbox[1], tx0, ty0);
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        const int pos = nh + __popc(bal & ((1u << lane) - 1u));
-        if (hit && pos < MAX_HITS) {
+      if (binned <= TILE_HIT_STRIDE - 1) {
+        const int idx = lane < binned ? bins[1 + lane] : 0x7FFFFFFF;
+        // a later pass (more outlines than one pass holds) resumes behind the objects already done
+        const int skip = __popc(__ballot_sync(0xffffffffu, idx < obj0));
+        if (lane < binned && idx >= obj0) {
+          const FlatObject* ob = a.objects + obj_begin + idx;
           HitObject h;
           h.obj = idx; h.shape_begin = ob->shape_begin; h.shape_count = ob->shape_count; h.tex = ob->tex;
           h.composite = ob->composite; h.field = ob->field;
-          s_hit[pos] = h;
+          s_hit[lane - skip] = h;
         }
-        const int cnt = __popc(bal);
-        if (nh + cnt > MAX_HITS) {  // table full: the next pass rescans from the first object left out
-          next = o + (int)__fns(bal, 0, MAX_HITS - nh + 1);
-          nh = MAX_HITS;
-          break;
+        nh = binned - skip;
+      } else {
+        for (int o = obj0; o < n_obj; o += 32) {
+          const int idx = o + lane;
+          bool hit = false;
+          const FlatObject* ob = a.objects + obj_begin + idx;
+          if (idx < n_obj) hit = box_hits_tile(ob->bbox[0], tx0, ty0) || box_hits_tile(ob->bbox[1], tx0, ty0);
+          const unsigned bal = __ballot_sync(0xffffffffu, hit);
+          const int pos = nh + __popc(bal & ((1u << lane) - 1u));
+          if (hit && pos < MAX_HITS) {
+            HitObject h;
+            h.obj = idx; h.shape_begin = ob->shape_begin; h.shape_count = ob->shape_count; h.tex = ob->tex;
+            h.composite = ob->composite; h.field = ob->field;
+            s_hit[pos] = h;
+          }
+          const int cnt = __popc(bal);
+          if (nh + cnt > MAX_HITS) {  // table full: the next pass rescans from the first object left out
+            next = o + (int)__fns(bal, 0, MAX_HITS - nh + 1);
+            nh = MAX_HITS;
+            break;
+          }
+          nh += cnt;
         }
-        nh += cnt;
       }
       if (lane == 0) { s_nhit = nh; s_scan_next = next; }
     }
@@ -929,6 +972,14 @@ void launch_composite_luts(uint8_t* add_lut, uint8_t* sub_lut, cudaStream_t s) {
 
 void launch_resize_tables(int* pos, double* alpha, int n, cudaStream_t s) {
   resize_tables_kernel<<<(n + 63) / 64, 64, 0, s>>>(pos, alpha, n);
+}
+
+size_t tile_hits_bytes(int batch, int W, int H) {
+  return (size_t)batch * ((W + TW - 1) / TW) * ((H + TH - 1) / TH) * TILE_HIT_STRIDE;
+}
+int launch_bin(const RenderArgs& a, cudaStream_t s) {
+  bin_kernel<<<a.batch, 192, 0, s>>>(a);
+  return 1;
 }
 
 int launch_background_prep(const RenderArgs& a, cudaStream_t s) {

@@ -26,6 +26,8 @@ struct RenderArgs {
   const double* alpha_x;
   const int* pos_y;        // [2H][2H]
   const double* alpha_y;
+  // per-sample, per-tile lists of the objects whose boxes touch the tile (bin_kernel -> render_kernel)
+  uint8_t* tile_hits;         // [batch][tiles][TILE_HIT_STRIDE]: byte 0 = count (255: too many, rescan), then object indices in z-order
   // mode 9
   const float* fields;        // [n][flow|iflow][channel][H+1][W+1]
   int n_fields;
@@ -50,7 +52,11 @@ struct RenderArgs {
   uint8_t* dbg_frames8; // [batch][2][3][H][W]
 };
 
+constexpr int TILE_HIT_STRIDE = 32;  // 1 count byte + up to 31 object indices per tile
+
 // Launchers; each returns the number of kernels it launched.
+int launch_bin(const RenderArgs& a, cudaStream_t s);
+size_t tile_hits_bytes(int batch, int W, int H);
 int launch_background_prep(const RenderArgs& a, cudaStream_t s);
 int launch_render(const RenderArgs& a, cudaStream_t s);
 int launch_deform_prepass(const RenderArgs& a, cudaStream_t s);  // mode 9 only; no-op when n_deform == 0
