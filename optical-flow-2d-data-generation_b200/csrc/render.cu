@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
   __shared__ HitObject s_hit[MAX_HITS];
   __shared__ Job s_job[MAX_JOBS];
   __shared__ int s_jobbase[MAX_HITS + 1];
-  __shared__ int s_nhit, s_njob, s_hits_done, s_next_obj, s_scan_next;
+  __shared__ int s_njob, s_hits_done, s_next_obj;
   __shared__ int s_seg_begin[NLAYER], s_seg_count[NLAYER];
 
   const int W = a.W, H = a.H;
@@ -319,7 +319,97 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
   const int binned = bins[0];  // objects touching this tile (255: more than a bin entry lists)
 
   s_q255[tid] = (float)tid / 255.f;
-  if (tid == 0) s_next_obj = binned ? 0 : n_obj;  // background-only tiles skip the object path entirely
+
+  // ---- pass set-up, entirely inside warp 0 (the other warps fetch the background meanwhile):
+  //      hit table -> outline jobs -> accumulator layers and chunk boundaries
+  auto pass_setup = [&](int obj0) {
+    // (1) objects whose boxes touch the tile, in z-order: from the bin list, or by a scan when the tile
+    //     holds more objects than a bin entry can list
+    int nh = 0, next = n_obj;
+    if (binned <= TILE_HIT_STRIDE - 1) {
+      const int idx = lane < binned ? bins[1 + lane] : 0x7FFFFFFF;
+      // a later pass (more outlines than one pass holds) resumes behind the objects already done
+      const int skip = __popc(__ballot_sync(0xffffffffu, idx < obj0));
+      if (lane < binned && idx >= obj0) {
+        const FlatObject* ob = a.objects + obj_begin + idx;
+        HitObject h;
+        h.obj = idx; h.shape_begin = ob->shape_begin; h.shape_count = ob->shape_count; h.tex = ob->tex;
+        h.composite = ob->composite; h.field = ob->field;
+        s_hit[lane - skip] = h;
+      }
+      nh = binned - skip;
+    } else {
+      for (int o = obj0; o < n_obj; o += 32) {
+        const int idx = o + lane;
+        bool hit = false;
+        const FlatObject* ob = a.objects + obj_begin + idx;
+        if (idx < n_obj) hit = box_hits_tile(ob->bbox[0], tx0, ty0) || box_hits_tile(ob->bbox[1], tx0, ty0);
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        const int pos = nh + __popc(bal & ((1u << lane) - 1u));
+        if (hit && pos < MAX_HITS) {
+          HitObject h;
+          h.obj = idx; h.shape_begin = ob->shape_begin; h.shape_count = ob->shape_count; h.tex = ob->tex;
+          h.composite = ob->composite; h.field = ob->field;
+          s_hit[pos] = h;
+        }
+        const int cnt = __popc(bal);
+        if (nh + cnt > MAX_HITS) {  // table full: the next pass rescans from the first object left out
+          next = o + (int)__fns(bal, 0, MAX_HITS - nh + 1);
+          nh = MAX_HITS;
+          break;
+        }
+        nh += cnt;
+      }
+    }
+    __syncwarp();
+    // (2) job ranges of the hit objects (at most MAX_JOBS outlines per pass)
+    if (lane == 0) {
+      int nj = 0, h = 0;
+      for (; h < nh; ++h) {
+        if (nj + s_hit[h].shape_count > MAX_JOBS && h > 0) break;
+        s_jobbase[h] = nj;
+        nj += min(s_hit[h].shape_count, MAX_JOBS);
+      }
+      s_jobbase[h] = nj;
+      s_hits_done = h;
+      s_njob = nj;
+      s_next_obj = (h == nh) ? next : s_hit[h].obj;  // first object not handled by this pass
+    }
+    __syncwarp();
+    const int njob = s_njob, nhd = s_hits_done;
+    for (int jj = lane; jj < njob; jj += 32) {
+      int h = 0;
+      while (h + 1 < nhd && s_jobbase[h + 1] <= jj) ++h;
+      const int si = jj - s_jobbase[h];
+      const HitObject ho = s_hit[h];
+      const FlatShape& sh = a.shapes[ho.shape_begin + si];
+      Job j;
+      j.hit = (short)h;
+      const bool h0 = box_hits_tile(sh.bbox[0], tx0, ty0), h1 = box_hits_tile(sh.bbox[1], tx0, ty0);
+      j.vbegin[0] = sh.vbegin[0]; j.vbegin[1] = sh.vbegin[1];
+      j.deform = (kDeform && h1) ? sh.deform : -1;  // a warped outline's frame-1 masks were materialised by the pre-pass
+      const bool r1 = h1 && j.deform < 0;
+      j.vcount[0] = h0 ? sh.vcount[0] : 0; j.vcount[1] = r1 ? sh.vcount[1] : 0;
+      j.slot[0] = h0 ? 0 : -1; j.slot[1] = r1 ? 0 : -1;
+      j.flags = (unsigned char)((sh.additive ? 1 : 0) | (si == 0 ? 2 : 0) | (si == ho.shape_count - 1 ? 4 : 0));
+      s_job[jj] = j;
+    }
+    __syncwarp();
+    // (3) accumulator layers and chunk boundaries
+    if (lane == 0 && njob > 0) {
+      int used = 0;
+      for (int j = 0; j < njob; ++j) {
+        const int need = (s_job[j].slot[0] >= 0) + (s_job[j].slot[1] >= 0);
+        if (used + need > NLAYER) { s_job[j - 1].flags |= 8; used = 0; }
+        if (s_job[j].slot[0] >= 0) s_job[j].slot[0] = (signed char)used++;
+        if (s_job[j].slot[1] >= 0) s_job[j].slot[1] = (signed char)used++;
+      }
+      s_job[njob - 1].flags |= 8;
+    }
+  };
+
+  int obj0 = binned ? 0 : n_obj;  // background-only tiles skip the object path entirely
+  if (obj0 < n_obj && warp == 0) pass_setup(obj0);
 
   uint32_t col0[4], col1[4];
   uint32_t id0 = 0, id1 = 0;  // four pixels, one byte each: 0 = background, k+1 = k-th foreground object (k < 255)
@@ -365,98 +455,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
   uint32_t uaa[2] = {0, 0}, una[2] = {0, 0};  // masks of the object being assembled: [frame], 4 pixels x 1 byte
 
   // ---- foreground objects in z-order, in passes of at most MAX_HITS objects / MAX_JOBS outlines
-  for (;;) {
-    __syncthreads();
-    const int obj0 = s_next_obj;
-    if (obj0 >= n_obj) break;
-    // (1) warp 0: objects whose boxes touch the tile -> ordered hit table (from the bin list, or by a scan
-    //     when the tile holds more objects than a bin entry can list)
-    if (warp == 0) {
-      int nh = 0, next = n_obj;
-      if (binned <= TILE_HIT_STRIDE - 1) {
-        const int idx = lane < binned ? bins[1 + lane] : 0x7FFFFFFF;
-        // a later pass (more outlines than one pass holds) resumes behind the objects already done
-        const int skip = __popc(__ballot_sync(0xffffffffu, idx < obj0));
-        if (lane < binned && idx >= obj0) {
-          const FlatObject* ob = a.objects + obj_begin + idx;
-          HitObject h;
-          h.obj = idx; h.shape_begin = ob->shape_begin; h.shape_count = ob->shape_count; h.tex = ob->tex;
-          h.composite = ob->composite; h.field = ob->field;
-          s_hit[lane - skip] = h;
-        }
-        nh = binned - skip;
-      } else {
-        for (int o = obj0; o < n_obj; o += 32) {
-          const int idx = o + lane;
-          bool hit = false;
-          const FlatObject* ob = a.objects + obj_begin + idx;
-          if (idx < n_obj) hit = box_hits_tile(ob->bbox[0], tx0, ty0) || box_hits_tile(ob->bbox[1], tx0, ty0);
-          const unsigned bal = __ballot_sync(0xffffffffu, hit);
-          const int pos = nh + __popc(bal & ((1u << lane) - 1u));
-          if (hit && pos < MAX_HITS) {
-            HitObject h;
-            h.obj = idx; h.shape_begin = ob->shape_begin; h.shape_count = ob->shape_count; h.tex = ob->tex;
-            h.composite = ob->composite; h.field = ob->field;
-            s_hit[pos] = h;
-          }
-          const int cnt = __popc(bal);
-          if (nh + cnt > MAX_HITS) {  // table full: the next pass rescans from the first object left out
-            next = o + (int)__fns(bal, 0, MAX_HITS - nh + 1);
-            nh = MAX_HITS;
-            break;
-          }
-          nh += cnt;
-        }
-      }
-      if (lane == 0) { s_nhit = nh; s_scan_next = next; }
-    }
-    __syncthreads();
-    // (2) outline jobs of the hit objects
-    if (tid == 0) {
-      int nj = 0, h = 0;
-      const int nh = s_nhit;
-      for (; h < nh; ++h) {
-        if (nj + s_hit[h].shape_count > MAX_JOBS && h > 0) break;
-        s_jobbase[h] = nj;
-        nj += min(s_hit[h].shape_count, MAX_JOBS);
-      }
-      s_jobbase[h] = nj;
-      s_hits_done = h;
-      s_njob = nj;
-      s_next_obj = (h == nh) ? s_scan_next : s_hit[h].obj;  // first object not handled by this pass
-    }
-    __syncthreads();
-    const int njob = s_njob, nhd = s_hits_done;
-    if (njob == 0) continue;
-    if (tid < njob) {
-      int h = 0;
-      while (h + 1 < nhd && s_jobbase[h + 1] <= tid) ++h;
-      const int si = tid - s_jobbase[h];
-      const HitObject ho = s_hit[h];
-      const FlatShape& sh = a.shapes[ho.shape_begin + si];
-      Job j;
-      j.hit = (short)h;
-      const bool h0 = box_hits_tile(sh.bbox[0], tx0, ty0), h1 = box_hits_tile(sh.bbox[1], tx0, ty0);
-      j.vbegin[0] = sh.vbegin[0]; j.vbegin[1] = sh.vbegin[1];
-      j.deform = (kDeform && h1) ? sh.deform : -1;  // a warped outline's frame-1 masks were materialised by the pre-pass
-      const bool r1 = h1 && j.deform < 0;
-      j.vcount[0] = h0 ? sh.vcount[0] : 0; j.vcount[1] = r1 ? sh.vcount[1] : 0;
-      j.slot[0] = h0 ? 0 : -1; j.slot[1] = r1 ? 0 : -1;
-      j.flags = (unsigned char)((sh.additive ? 1 : 0) | (si == 0 ? 2 : 0) | (si == ho.shape_count - 1 ? 4 : 0));
-      s_job[tid] = j;
-    }
-    __syncthreads();
-    if (tid == 0) {  // accumulator layers and chunk boundaries
-      int used = 0;
-      for (int j = 0; j < njob; ++j) {
-        const int need = (s_job[j].slot[0] >= 0) + (s_job[j].slot[1] >= 0);
-        if (used + need > NLAYER) { s_job[j - 1].flags |= 8; used = 0; }
-        if (s_job[j].slot[0] >= 0) s_job[j].slot[0] = (signed char)used++;
-        if (s_job[j].slot[1] >= 0) s_job[j].slot[1] = (signed char)used++;
-      }
-      s_job[njob - 1].flags |= 8;
-    }
-    __syncthreads();
+  while (obj0 < n_obj) {
+    __syncthreads();  // warp 0's set-up (and s_q255) are visible
+    const int njob = s_njob;
 
     // (3) chunks: zero -> accumulate edges -> per-pixel masks, combine, blit
     int j0 = 0;
@@ -602,6 +603,10 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
       j0 = j1;
       __syncthreads();  // the accumulators are rewritten by the next chunk
     }
+    obj0 = s_next_obj;
+    if (obj0 >= n_obj) break;
+    __syncthreads();  // everybody has read the pass state before warp 0 rewrites it
+    if (warp == 0) pass_setup(obj0);
   }
 
   if (!live) return;
