@@ -127,56 +127,69 @@ OFDG_HD_NOINLINE void tile_hline(int* cover, int* area, int* carry, int tx0, int
   if (incr < 0 && ex2 < tx0) Acc<kDevice>::add(carry, dyv - prev);  // the cells left of the tile (walk goes left)
 }
 
+// Row range of edge (xa,ya)-(xb,yb) inside the tile: returns false when the edge cannot touch the tile's
+// accumulators at all; `left` is set when it lies entirely left of the tile (carry-in only, no divisions).
+OFDG_HD bool tile_edge_rows(int tx0, int ty0, int xa, int ya, int xb, int yb, int& rlo, int& rhi, bool& left) {
+  if (ya == yb) return false;
+  const int ey1 = ya >> 8, ey2 = yb >> 8;
+  rlo = rt_max(rt_min(ey1, ey2), ty0);
+  rhi = rt_min(rt_max(ey1, ey2), ty0 + TH - 1);
+  if (rlo > rhi) return false;
+  if ((rt_min(xa, xb) >> 8) >= tx0 + TW) return false;
+  left = (rt_max(xa, xb) >> 8) < tx0;
+  return true;
+}
+
+// The part of rasterizer_cells_aa::line(xa, ya, xb, yb) that falls into pixel row r (ty0 <= r < ty0+TH),
+// evaluated on its own: the x positions where the edge enters and leaves the row come from the closed form
+//   X(j) = xa + floor((p0 + 256*j) * dx / dy),   j = index of the row along the edge,
+// i.e. exactly the values AGG's remainder-carrying DDA reaches after j steps.
+template <bool kDevice>
+OFDG_HD void tile_edge_row(int* cover, int* area, int* carry, int tx0, int ty0, int r, int xa, int ya, int xb, int yb) {
+  const int ey1 = ya >> 8, ey2 = yb >> 8, fy1 = ya & 255, fy2 = yb & 255;
+  int* cv = cover + (r - ty0) * TW;
+  int* ar = area + (r - ty0) * TW;
+  int* cr = carry + (r - ty0);
+  if (ey1 == ey2) {
+    tile_hline<kDevice>(cv, ar, cr, tx0, xa, fy1, xb, fy2);
+    return;
+  }
+  const bool down = yb > ya;
+  const int ys = r == ey1 ? fy1 : (down ? 0 : 256), ye = r == ey2 ? fy2 : (down ? 256 : 0);
+  if ((rt_max(xa, xb) >> 8) < tx0) {  // entirely left of the tile: only the y extent matters
+    if (ye != ys) Acc<kDevice>::add(cr, ye - ys);
+    return;
+  }
+  const int dx = xb - xa, dy = down ? yb - ya : ya - yb;
+  const int p0 = down ? (256 - fy1) : fy1;
+  const int j = down ? r - ey1 : ey1 - r;
+  int xs = xa, xe = xb;
+  int q = 0, m = 0;
+  if (j > 0) {
+    floordivmod64((long long)(p0 + 256LL * (j - 1)) * dx, dy, q, m);
+    xs = xa + q;
+  }
+  if (r != ey2) {
+    if (j == 0) floordivmod64((long long)p0 * dx, dy, q, m);
+    else {
+      int lift, rem;
+      floordivmod(256 * dx, dy, lift, rem);
+      q += lift; m += rem;
+      if (m >= dy) { m -= dy; ++q; }
+    }
+    xe = xa + q;
+  }
+  tile_hline<kDevice>(cv, ar, cr, tx0, xs, ys, xe, ye);
+}
+
 // rasterizer_cells_aa::line(xa, ya, xb, yb) restricted to tile rows [ty0, ty0+TH) x columns [tx0, tx0+TW).
 // cover/area: TH x TW ints, carry: TH ints.
 template <bool kDevice>
 OFDG_HD void tile_edge(int* cover, int* area, int* carry, int tx0, int ty0, int xa, int ya, int xb, int yb) {
-  if (ya == yb) return;
-  const int ey1 = ya >> 8, ey2 = yb >> 8;
-  const int rlo = rt_max(rt_min(ey1, ey2), ty0), rhi = rt_min(rt_max(ey1, ey2), ty0 + TH - 1);
-  if (rlo > rhi) return;
-  if ((rt_min(xa, xb) >> 8) >= tx0 + TW) return;
-  const int fy1 = ya & 255, fy2 = yb & 255;
-  if (ey1 == ey2) {
-    const int r = ey1 - ty0;
-    tile_hline<kDevice>(cover + r * TW, area + r * TW, carry + r, tx0, xa, fy1, xb, fy2);
-    return;
-  }
-  const bool down = yb > ya;
-  if ((rt_max(xa, xb) >> 8) < tx0) {
-    // the whole edge lies left of the tile: each row only receives the edge's y extent in that row
-    for (int r = rlo; r <= rhi; ++r) {
-      const int ys = r == ey1 ? fy1 : (down ? 0 : 256), ye = r == ey2 ? fy2 : (down ? 256 : 0);
-      if (ye != ys) Acc<kDevice>::add(carry + (r - ty0), ye - ys);
-    }
-    return;
-  }
-  const int dx = xb - xa;
-  const int dy = down ? yb - ya : ya - yb;
-  // X(j) = xa + floor((p0 + 256*j*dx) / dy): x where the edge leaves its j-th row (j = 0 is row ey1)
-  const int p0 = down ? (256 - fy1) : fy1;  // times dx
-  int lift, rem;
-  floordivmod(256 * dx, dy, lift, rem);
-  const int rstart = down ? rlo : rhi;                  // first tile row along the walk
-  const int jstart = down ? rstart - ey1 : ey1 - rstart;  // its index along the edge
-  int q = 0, m = 0;                                     // DDA state: X(jstart - 1) = xa + q
-  if (jstart > 0) floordivmod64((long long)(p0 + 256LL * (jstart - 1)) * dx, dy, q, m);
-  const int nrows = rhi - rlo + 1;
-  for (int k = 0; k < nrows; ++k) {
-    const int r = down ? rstart + k : rstart - k;
-    const int j = jstart + k;
-    const int xs = j == 0 ? xa : xa + q;
-    const int ys = j == 0 ? fy1 : (down ? 0 : 256);
-    int xe, ye;
-    if (r == ey2) { xe = xb; ye = fy2; }
-    else {
-      if (j == 0) floordivmod64((long long)p0 * dx, dy, q, m);
-      else { q += lift; m += rem; if (m >= dy) { m -= dy; ++q; } }
-      xe = xa + q;
-      ye = down ? 256 : 0;
-    }
-    tile_hline<kDevice>(cover + (r - ty0) * TW, area + (r - ty0) * TW, carry + (r - ty0), tx0, xs, ys, xe, ye);
-  }
+  int rlo, rhi;
+  bool left;
+  if (!tile_edge_rows(tx0, ty0, xa, ya, xb, yb, rlo, rhi, left)) return;
+  for (int r = rlo; r <= rhi; ++r) tile_edge_row<kDevice>(cover, area, carry, tx0, ty0, r, xa, ya, xb, yb);
 }
 
 // sweep_scanline + calculate_alpha for one pixel: `cum` = cover summed over all cells at or left of

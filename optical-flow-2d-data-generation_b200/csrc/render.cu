@@ -243,6 +243,7 @@ __global__ void bin_kernel(RenderArgs a) {
 constexpr int NLAYER = 4;      // cover/area accumulator layers that are filled between two barriers
 constexpr int MAX_HITS = 64;   // objects touching the tile handled per pass
 constexpr int MAX_JOBS = 128;  // shapes (outlines) handled per pass
+constexpr int MAX_PAIRS = 1024;  // (edge, tile row) work items listed per chunk; the rest is handled in place
 
 struct HitObject {             // what the per-pixel stage needs of a FlatObject, staged in shared memory
   int obj;                     // index within the sample (z-order)
@@ -303,6 +304,8 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
   __shared__ int s_jobbase[MAX_HITS + 1];
   __shared__ int s_njob, s_hits_done, s_next_obj;
   __shared__ int s_seg_begin[NLAYER], s_seg_count[NLAYER];
+  __shared__ unsigned s_pairs[MAX_PAIRS];  // (layer, tile row, edge) work items of the current chunk
+  __shared__ int s_npairs;
 
   const int W = a.W, H = a.H;
   const int tiles_x = (W + TW - 1) / TW;
@@ -478,8 +481,10 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
         reinterpret_cast<int4*>(&s_area[0][0][0])[i] = make_int4(0, 0, 0, 0);
       }
       if (tid < NLAYER * TH) (&s_carry[0][0])[tid] = 0;
+      if (tid == 0) s_npairs = 0;
       __syncthreads();
       {
+        // (a) threads over edges: which tile rows does the edge cross? One work item per (edge, row).
         const int c0 = s_seg_count[0], c1 = c0 + s_seg_count[1], c2 = c1 + s_seg_count[2], c3 = c2 + s_seg_count[3];
         for (int e = tid; e < c3; e += RENDER_THREADS) {
           const int l = e < c0 ? 0 : (e < c1 ? 1 : (e < c2 ? 2 : 3));
@@ -487,7 +492,28 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
           const int n = s_seg_count[l];
           const FlatVertex* v = a.verts + s_seg_begin[l];
           const FlatVertex p = v[ei], q = v[ei + 1 == n ? 0 : ei + 1];
-          tile_edge<true>(&s_cover[l][0][0], &s_area[l][0][0], &s_carry[l][0], tx0, ty0, p.x, p.y, q.x, q.y);
+          int rlo, rhi;
+          bool left;
+          if (!tile_edge_rows(tx0, ty0, p.x, p.y, q.x, q.y, rlo, rhi, left)) continue;
+          const int nrows = rhi - rlo + 1;
+          const int base = left ? MAX_PAIRS : atomicAdd(&s_npairs, nrows);
+          for (int k = 0; k < nrows; ++k) {
+            if (base + k < MAX_PAIRS) s_pairs[base + k] = ((unsigned)l << 28) | ((unsigned)(rlo + k - ty0) << 24) | (unsigned)ei;
+            else tile_edge_row<true>(&s_cover[l][0][0], &s_area[l][0][0], &s_carry[l][0], tx0, ty0, rlo + k, p.x, p.y, q.x, q.y);  // cheap (left of the tile) or list full
+          }
+        }
+      }
+      __syncthreads();
+      {
+        // (b) threads over (edge, row) items: closed-form row segment -> cells
+        const int np = min(s_npairs, MAX_PAIRS);
+        for (int i = tid; i < np; i += RENDER_THREADS) {
+          const unsigned w = s_pairs[i];
+          const int l = (int)(w >> 28), r = ty0 + (int)((w >> 24) & 15u), ei = (int)(w & 0xFFFFFFu);
+          const int n = s_seg_count[l];
+          const FlatVertex* v = a.verts + s_seg_begin[l];
+          const FlatVertex p = v[ei], q = v[ei + 1 == n ? 0 : ei + 1];
+          tile_edge_row<true>(&s_cover[l][0][0], &s_area[l][0][0], &s_carry[l][0], tx0, ty0, r, p.x, p.y, q.x, q.y);
         }
       }
       __syncthreads();
