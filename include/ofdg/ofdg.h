@@ -60,6 +60,9 @@ void ofdg_params_destroy(ofdg_params* p);
 /* The commission loop of load_batch (src/caffe/layers/data_generation_layer.cpp:197-214):
  * appends n_tasks freshly drawn tasks to `out`. */
 int ofdg_params_generate(ofdg_params* p, int32_t n_tasks, ofdg_tasks* out);
+/* Colour/noise augmentation records for subsequently generated tasks (not in the reference; specification in
+ * ofdg/scene.h; drawn from five extra engines seeded seed_offset+45..49). Off by default. */
+int ofdg_params_enable_augmentation(ofdg_params* p, int32_t enable);
 int ofdg_params_skip(ofdg_params* p, uint64_t n_tasks);          /* checkpoint/resume: fast-forward */
 uint64_t ofdg_params_tasks_generated(const ofdg_params* p);
 uint64_t ofdg_params_draws(const ofdg_params* p, int32_t slot);  /* draws made by engine `slot` so far */

@@ -47,6 +47,23 @@ typedef struct ofdg_blueprint {
   int32_t field_id;               /* mode 9: index into the injected (flow, iflow) field pool, -1 = none */
 } ofdg_blueprint;
 
+/* Per-sample colour / noise augmentation. NOT part of the reference (it has no
+ * augmentation anywhere); this is this repository's own, deliberately simple specification so that
+ * the oracle reproduces it bit for bit: for frame f, channel c, pixel p with 8-bit value v,
+ *   y = contrast * (gain[c] * v - 127.5f) + 127.5f + brightness + noise_sigma * n(f, c, p)
+ *   out = min(max(y, 0), 255)                       (float32, one rounding per operation, no FMA)
+ * n = ((sum of the eight 16-bit halves of Philox4x32-10(key = noise_seed, counter = {p, 2*c + f, 0, 0}))
+ *      - 262140) * (1 / 53510.1f)                   (Irwin-Hall, approximately N(0,1), integer-exact)
+ * The flow is not touched. enabled == 0 leaves the sample exactly as the reference would produce it. */
+typedef struct ofdg_augment {
+  int32_t  enabled;
+  float    gain[3];
+  float    brightness;
+  float    contrast;
+  float    noise_sigma;
+  uint32_t noise_seed[2];
+} ofdg_augment;
+
 /* A batch of tasks as flat arrays (all owned by whoever built the batch).
  * Task t owns blueprints [task_begin[t], task_begin[t+1]); the first one is the
  * background; the top-level foreground objects are those with parent == -1, in
@@ -60,6 +77,7 @@ typedef struct ofdg_task_batch {
   const int32_t*        seg_type;      /* n_segments, OFDG_SEG_* */
   const float*          seg_x;         /* n_segments */
   const float*          seg_y;         /* n_segments */
+  const ofdg_augment*   augment;       /* n_tasks records, or NULL (= no augmentation) */
 } ofdg_task_batch;
 
 #ifdef __cplusplus

@@ -36,7 +36,13 @@ assert BLUEPRINT_DTYPE.itemsize == 100
 class TaskBatchStruct(C.Structure):
     _fields_ = [("n_tasks", C.c_int32), ("n_blueprints", C.c_int32), ("n_segments", C.c_int32),
                 ("task_begin", C.c_void_p), ("blueprints", C.c_void_p), ("seg_type", C.c_void_p),
-                ("seg_x", C.c_void_p), ("seg_y", C.c_void_p)]
+                ("seg_x", C.c_void_p), ("seg_y", C.c_void_p), ("augment", C.c_void_p)]
+
+
+# numpy view of ofdg_augment (include/ofdg/scene.h)
+AUGMENT_DTYPE = np.dtype([("enabled", "<i4"), ("gain", "<f4", (3,)), ("brightness", "<f4"), ("contrast", "<f4"),
+                          ("noise_sigma", "<f4"), ("noise_seed", "<u4", (2,))])
+assert AUGMENT_DTYPE.itemsize == 36
 
 
 class ConfigStruct(C.Structure):
@@ -53,7 +59,7 @@ _lib = None
 # every symbol include/ofdg/ofdg.h declares
 EXPORTS = [
     "ofdg_last_error", "ofdg_version", "ofdg_params_create", "ofdg_params_destroy", "ofdg_params_generate",
-    "ofdg_params_skip", "ofdg_params_tasks_generated", "ofdg_params_draws", "ofdg_params_slot_name",
+    "ofdg_params_skip", "ofdg_params_enable_augmentation", "ofdg_params_tasks_generated", "ofdg_params_draws", "ofdg_params_slot_name",
     "ofdg_tasks_create", "ofdg_tasks_destroy", "ofdg_tasks_clear", "ofdg_tasks_view", "ofdg_tasks_assign",
     "ofdg_flatten_ellipse", "ofdg_flatten_polygon", "ofdg_debug_raster_host", "ofdg_create", "ofdg_destroy", "ofdg_upload_textures",
     "ofdg_synth_textures", "ofdg_download_texture", "ofdg_set_fields", "ofdg_render", "ofdg_render_host",
@@ -91,6 +97,7 @@ def lib():
         L.ofdg_params_destroy.argtypes = [C.c_void_p]
         L.ofdg_params_generate.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ofdg_params_skip.argtypes = [C.c_void_p, C.c_uint64]
+        L.ofdg_params_enable_augmentation.argtypes = [C.c_void_p, C.c_int32]
         L.ofdg_tasks_create.argtypes = [C.POINTER(C.c_void_p)]
         L.ofdg_tasks_destroy.argtypes = [C.c_void_p]
         L.ofdg_tasks_clear.argtypes = [C.c_void_p]
@@ -178,6 +185,7 @@ class Tasks:
             "seg_type": cp(s.seg_type, s.n_segments, "<i4"),
             "seg_x": cp(s.seg_x, s.n_segments, "<f4"),
             "seg_y": cp(s.seg_y, s.n_segments, "<f4"),
+            "augment": cp(s.augment, s.n_tasks, AUGMENT_DTYPE) if s.augment else None,
         }
 
     @staticmethod
@@ -193,7 +201,7 @@ class Tasks:
 
 
 def struct_from_arrays(arrs):
-    keep = {k: np.ascontiguousarray(v) for k, v in arrs.items()}
+    keep = {k: np.ascontiguousarray(v) for k, v in arrs.items() if v is not None}
     s = TaskBatchStruct()
     s.n_tasks = len(keep["task_begin"]) - 1
     s.n_blueprints = len(keep["blueprints"])
@@ -203,6 +211,7 @@ def struct_from_arrays(arrs):
     s.seg_type = keep["seg_type"].ctypes.data
     s.seg_x = keep["seg_x"].ctypes.data
     s.seg_y = keep["seg_y"].ctypes.data
+    s.augment = keep["augment"].ctypes.data if "augment" in keep else None
     return s, keep
 
 
@@ -228,7 +237,8 @@ def select_tasks(arrs, idx):
         begin.append(nb)
     cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
     return {"task_begin": np.asarray(begin, "<i4"), "blueprints": cat(bps, BLUEPRINT_DTYPE),
-            "seg_type": cat(st, "<i4"), "seg_x": cat(sx, "<f4"), "seg_y": cat(sy, "<f4")}
+            "seg_type": cat(st, "<i4"), "seg_x": cat(sx, "<f4"), "seg_y": cat(sy, "<f4"),
+            "augment": None if arrs.get("augment") is None else arrs["augment"][list(idx)].copy()}
 
 
 class ParamStream:
@@ -251,6 +261,9 @@ class ParamStream:
 
     def skip(self, n):
         _check(lib().ofdg_params_skip(self._h, n))
+
+    def enable_augmentation(self, on=True):
+        _check(lib().ofdg_params_enable_augmentation(self._h, int(bool(on))))
 
     def tasks_generated(self):
         return int(lib().ofdg_params_tasks_generated(self._h))

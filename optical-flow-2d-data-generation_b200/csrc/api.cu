@@ -303,6 +303,12 @@ int ofdg_params_skip(ofdg_params* p, uint64_t n_tasks) {
     p->ps->skip(n_tasks);
   });
 }
+int ofdg_params_enable_augmentation(ofdg_params* p, int32_t enable) {
+  return guarded([&] {
+    if (!p) throw ArgError("null stream");
+    p->ps->enable_augmentation(enable != 0);
+  });
+}
 uint64_t ofdg_params_tasks_generated(const ofdg_params* p) { return p ? p->ps->tasks_generated() : 0; }
 uint64_t ofdg_params_draws(const ofdg_params* p, int32_t slot) {
   return (p && slot >= 0 && slot < ofdg::kNumSlots) ? p->ps->draws(slot) : 0;
@@ -333,6 +339,8 @@ int ofdg_tasks_assign(ofdg_tasks* t, const ofdg_task_batch* s) {
     t->tb.seg_type.assign(s->seg_type, s->seg_type + s->n_segments);
     t->tb.seg_x.assign(s->seg_x, s->seg_x + s->n_segments);
     t->tb.seg_y.assign(s->seg_y, s->seg_y + s->n_segments);
+    if (s->augment) t->tb.augment.assign(s->augment, s->augment + s->n_tasks);
+    else t->tb.augment.clear();
   });
 }
 
@@ -586,6 +594,7 @@ static void render_host_pipelined(ofdg_generator* g, ofdg_params* params, const 
       view = *tasks;
       view.n_tasks = t1 - t0;
       view.task_begin = tasks->task_begin + t0;  // blueprint indices stay absolute
+      if (view.augment) view.augment += t0;
     }
     flatten_tasks(g, &view, &g->pipe_flat[set]);
     upload_scene(g, g->pipe_flat[set], g->pipe_scene[set], g->pipe_staging[set], A);

@@ -6,6 +6,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "ofdg/scene.h"
+
 namespace ofdg {
 
 // One closed outline (a simple object, or one component of a composite), both frames.
@@ -53,6 +55,7 @@ struct FlatSample {
   double bg_tex_inv[6];              // inverse of I^-1 * M * I on the 2W x 2H canvas (DataGenerator.cpp:676-677)
   double bg_motion[6];               // M alone; the flow applies I^-1, M, I in turn (DataGenerator.cpp:692-712)
   BgPrep prep;
+  ofdg_augment aug;                  // colour/noise augmentation of this sample (enabled == 0: none)
 };
 
 struct FlatVertex {

@@ -293,6 +293,7 @@ void flatten(const ofdg_task_batch& tb, const FlattenConfig& cfg, FlatBatch& out
     smp.bg_field = bg_deformed ? bg.field_id : -1;
     if (smp.bg_field >= cfg.n_fields) throw std::runtime_error("background refers to a warp field that was not injected (ofdg_set_fields)");
     prepare_background(bg, cfg, tex_inv, bg_deformed, smp.prep);
+    if (tb.augment) smp.aug = tb.augment[t];
 
     // addBackgroundMotion's bracket T(-W/2,-H/2) * M_bg * T(W/2,H/2), DG.cpp:327-329
     Affine bg_n = Affine::translation(-W / 2., -H / 2.);

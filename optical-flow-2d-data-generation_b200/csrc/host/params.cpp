@@ -127,6 +127,7 @@ void TaskBatch::clear() {
   seg_type.clear();
   seg_x.clear();
   seg_y.clear();
+  augment.clear();
 }
 
 ofdg_task_batch TaskBatch::view() const {
@@ -139,6 +140,7 @@ ofdg_task_batch TaskBatch::view() const {
   v.seg_type = seg_type.data();
   v.seg_x = seg_x.data();
   v.seg_y = seg_y.data();
+  v.augment = (augment.size() == (size_t)n_tasks() && !augment.empty()) ? augment.data() : nullptr;
   return v;
 }
 
@@ -155,6 +157,7 @@ ParamStream::ParamStream(int mode, int W, int H, int seed_offset, int n_fields, 
   SlotSpec specs[kNumSlots];
   fill_mode_table(mode, W, H, specs);
   for (int i = 0; i < kNumSlots; ++i) eng_[i] = Engine(specs[i], seed_offset + i);  // RNG_SEED++, DG.cpp:1360
+  for (int i = 0; i < 5; ++i) aug_eng_[i] = std::mt19937((uint32_t)(seed_offset + kNumSlots + i));
 }
 
 // CropGenerator::get_crop serves every crop reuse_same+1 = 3 times before popping it
@@ -421,6 +424,19 @@ void ParamStream::next_task(TaskBatch& out) {  // data_generation_layer.cpp:197-
     foreground(out, idx, false);
   }
   out.task_begin.push_back((int32_t)out.blueprints.size());
+  if (augment_) {
+    ofdg_augment a{};
+    a.enabled = 1;
+    std::uniform_real_distribution<double> gain(0.8, 1.2), bright(-20.0, 20.0), contrast(0.7, 1.3), sigma(0.0, 10.0);
+    for (int c = 0; c < 3; ++c) a.gain[c] = (float)gain(aug_eng_[0]);
+    a.brightness = (float)bright(aug_eng_[1]);
+    a.contrast = (float)contrast(aug_eng_[2]);
+    a.noise_sigma = (float)sigma(aug_eng_[3]);
+    a.noise_seed[0] = aug_eng_[4]();
+    a.noise_seed[1] = aug_eng_[4]();
+    out.augment.resize(out.task_begin.size() - 2);  // earlier tasks generated without augmentation stay disabled
+    out.augment.push_back(a);
+  }
   ++tasks_;
 }
 

@@ -76,6 +76,7 @@ class TaskBatch {
   std::vector<ofdg_blueprint> blueprints;
   std::vector<int32_t> seg_type;
   std::vector<float> seg_x, seg_y;
+  std::vector<ofdg_augment> augment;  // empty, or one record per task
 };
 
 class ParamStream {
@@ -86,6 +87,9 @@ class ParamStream {
   // Appends one task (background + foreground objects) to `out`.
   void next_task(TaskBatch& out);
   void skip(uint64_t n_tasks);  // fast-forward (checkpoint/resume)
+  // Colour/noise augmentation (this repository's own spec, include/ofdg/scene.h): five extra engines seeded
+  // seed_offset + 45..49, so the reference's 45 streams are untouched. Off by default.
+  void enable_augmentation(bool on) { augment_ = on; }
   uint64_t tasks_generated() const { return tasks_; }
   uint64_t draws(int slot) const { return eng_[slot].draws; }
   int mode() const { return mode_; }
@@ -103,6 +107,8 @@ class ParamStream {
   int mode_, W_, H_, n_fields_, fg_override_;
   uint64_t tasks_ = 0, field_draws_ = 0;
   Engine eng_[kNumSlots];
+  bool augment_ = false;
+  std::mt19937 aug_eng_[5];
 };
 
 }  // namespace ofdg

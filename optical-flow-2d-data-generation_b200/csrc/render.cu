@@ -13,6 +13,7 @@
 //       write    uint8 -> float conversion into the output blobs                      (DG.cpp:1229-1245)
 #include "render.cuh"
 
+#include "ofdg/augment.h"
 #include "raster_tile.h"
 
 namespace ofdg {
@@ -681,10 +682,18 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
   float* o0 = a.img0 + (size_t)sample * 3 * P + pix;
   float* o1 = a.img1 + (size_t)sample * 3 * P + pix;
   float* of = a.flow + (size_t)sample * 2 * P + pix;
+  const bool augment = smp.aug.enabled != 0;  // this repository's own colour/noise augmentation (ofdg/augment.h); never set by the reference path
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float4 v0 = make_float4(byte_to_float(col0[0], c), byte_to_float(col0[1], c), byte_to_float(col0[2], c), byte_to_float(col0[3], c));
     float4 v1 = make_float4(byte_to_float(col1[0], c), byte_to_float(col1[1], c), byte_to_float(col1[2], c), byte_to_float(col1[3], c));
+    if (augment) {
+      const uint32_t p = (uint32_t)pix;
+      v0.x = ofdg_augment_value(&smp.aug, v0.x, c, 0, p); v0.y = ofdg_augment_value(&smp.aug, v0.y, c, 0, p + 1);
+      v0.z = ofdg_augment_value(&smp.aug, v0.z, c, 0, p + 2); v0.w = ofdg_augment_value(&smp.aug, v0.w, c, 0, p + 3);
+      v1.x = ofdg_augment_value(&smp.aug, v1.x, c, 1, p); v1.y = ofdg_augment_value(&smp.aug, v1.y, c, 1, p + 1);
+      v1.z = ofdg_augment_value(&smp.aug, v1.z, c, 1, p + 2); v1.w = ofdg_augment_value(&smp.aug, v1.w, c, 1, p + 3);
+    }
     __stcs(reinterpret_cast<float4*>(o0 + c * P), v0);
     __stcs(reinterpret_cast<float4*>(o1 + c * P), v1);
   }

@@ -14,6 +14,8 @@
 // double expressions are meant to round exactly like the reference's x86-64 SSE build.
 #include "oracle.h"
 
+#include "ofdg/augment.h"
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -1038,6 +1040,14 @@ static void process_task(const Ctx& c, const ofdg_task_batch& tb, int t, float* 
     }
   // copy results, DG.cpp:1229-1245
   for (size_t i = 0; i < 3 * P; ++i) { img0[i] = static_cast<float>(frame0.d[i]); img1[i] = static_cast<float>(frame1.d[i]); }
+  if (tb.augment && tb.augment[t].enabled) {  // not in the reference: this repository's augmentation spec (include/ofdg/scene.h)
+    const ofdg_augment* a = &tb.augment[t];
+    for (int ch = 0; ch < 3; ++ch)
+      for (size_t i = 0; i < P; ++i) {
+        img0[ch * P + i] = ofdg_augment_value(a, img0[ch * P + i], ch, 0, (uint32_t)i);
+        img1[ch * P + i] = ofdg_augment_value(a, img1[ch * P + i], ch, 1, (uint32_t)i);
+      }
+  }
   std::memcpy(flow, flow0.d.data(), 2 * P * sizeof(float));
   if (dbg) {
     if (dbg->id0) for (size_t i = 0; i < P; ++i) dbg->id0[(size_t)t * P + i] = (uint32_t)index0[i];

@@ -171,3 +171,24 @@ def test_double_resolution(ofdg, oracle):
     cpu = oracle.render(tasks.struct(), tex, W=W, H=H, mode=7, debug=True, max_objs=40)
     _compare(gpu, cpu)
     g.close()
+
+
+def test_augmentation_bit_exact(ofdg, oracle, textures8):
+    """Fused colour/noise augmentation (this repository's spec, not the reference's): integer Philox and
+    single-rounded float operations on both sides, so the float blobs must agree exactly."""
+    g = _gen(ofdg, 7)
+    g.upload_textures(textures8)
+    ps = ofdg.ParamStream(7)
+    ps.enable_augmentation(True)
+    tasks = ps.generate(8)
+    aug = tasks.arrays()["augment"]
+    assert aug is not None and np.all(aug["enabled"] == 1) and aug["noise_sigma"].max() > 1
+    i0, i1, fl = g.render_host(tasks)
+    cpu = oracle.render(tasks.struct(), textures8, mode=7)
+    assert np.array_equal(i0, cpu["img0"]) and np.array_equal(i1, cpu["img1"])
+    assert np.abs(fl - cpu["flow"]).max() <= FLOW_TOL
+    plain = oracle.render(ofdg.ParamStream(7).generate(8).struct(), textures8, mode=7)
+    assert np.array_equal(plain["flow"], cpu["flow"])          # geometry untouched
+    assert np.abs(plain["img0"] - cpu["img0"]).mean() > 3      # colours are not
+    assert i0.min() >= 0 and i0.max() <= 255
+    g.close()

@@ -150,3 +150,37 @@ def test_mode9_field_ids(ofdg):
 def test_bad_mode_rejected(ofdg):
     with pytest.raises(ofdg.OfdgError, match="BAD MODE"):
         ofdg.ParamStream(14)
+
+
+def test_augmentation_leaves_the_reference_stream_alone(ofdg, oracle, textures8):
+    a = ofdg.ParamStream(7).generate(5).arrays()
+    ps = ofdg.ParamStream(7)
+    ps.enable_augmentation(True)
+    b = ps.generate(5).arrays()
+    for k in ("task_begin", "blueprints", "seg_type", "seg_x", "seg_y"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["augment"] is None and len(b["augment"]) == 5
+    aug = b["augment"]
+    assert np.all((aug["gain"] >= 0.8) & (aug["gain"] <= 1.2)) and np.all(np.abs(aug["brightness"]) <= 20)
+    assert np.all((aug["contrast"] >= 0.7) & (aug["contrast"] <= 1.3)) and np.all((aug["noise_sigma"] >= 0) & (aug["noise_sigma"] <= 10))
+
+
+def test_augmentation_noise_statistics(ofdg, oracle, textures8):
+    """The Irwin-Hall/Philox noise of the augmentation spec is ~N(0, sigma) and differs per frame/channel."""
+    t = ofdg.ParamStream(1).generate(1)
+    arrs = t.arrays()
+    aug = np.zeros(1, ofdg.AUGMENT_DTYPE)
+    aug["enabled"], aug["gain"], aug["contrast"], aug["noise_sigma"], aug["noise_seed"] = 1, 1.0, 1.0, 5.0, (123, 456)
+    arrs["augment"] = aug
+    s, keep = ofdg.struct_from_arrays(arrs)
+    noisy = oracle.render(s, textures8, mode=1, n_threads=1)
+    arrs["augment"] = None
+    s2, keep2 = ofdg.struct_from_arrays(arrs)
+    clean = oracle.render(s2, textures8, mode=1, n_threads=1)
+    d = (noisy["img0"] - clean["img0"])[0]
+    inner = (clean["img0"][0] > 30) & (clean["img0"][0] < 225)  # away from the clamp
+    assert abs(d[inner].mean()) < 0.05 and abs(d[inner].std() - 5.0) < 0.1
+    d1 = (noisy["img1"] - clean["img1"])[0]
+    assert np.corrcoef(d[0].ravel()[:50000], d[1].ravel()[:50000])[0, 1] < 0.02  # channels independent
+    assert not np.array_equal(d[0], d1[0])
+    assert np.array_equal(noisy["flow"], clean["flow"])
