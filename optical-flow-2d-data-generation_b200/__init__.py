@@ -165,6 +165,7 @@ class Tasks:
     def struct(self):
         s = TaskBatchStruct()
         _check(lib().ofdg_tasks_view(self._h, C.byref(s)))
+        s._owner = self  # the view borrows this batch's memory: keep it alive as long as the view
         return s
 
     def __len__(self):
@@ -212,6 +213,7 @@ def struct_from_arrays(arrs):
     s.seg_x = keep["seg_x"].ctypes.data
     s.seg_y = keep["seg_y"].ctypes.data
     s.augment = keep["augment"].ctypes.data if "augment" in keep else None
+    s._owner = keep
     return s, keep
 
 
