@@ -147,6 +147,16 @@ int ofdg_generate(ofdg_generator* g, ofdg_params* p, int32_t batch, float* d_img
  * upload, kernels and the device-to-host copies are pipelined chunk by chunk inside the call. */
 int ofdg_generate_host(ofdg_generator* g, ofdg_params* p, int32_t batch, float* h_img0, float* h_img1, float* h_flow);
 
+/* Production mode: scene parameters are drawn ON THE DEVICE with counter-based Philox4x32-10
+ * from the same mode tables and branch structure as the host stream, flattened on the device and rendered --
+ * no host work, no upload. Sample i of the stream is a pure function of (mode, seed, first_sample + i), so any
+ * GPU reproduces any sample. Statistically, not bitwise, equivalent to the host stream; modes 1-8, 10-13. */
+int ofdg_generate_philox(ofdg_generator* g, uint64_t seed, uint64_t first_sample, int32_t batch, int32_t augment,
+                         float* d_img0, float* d_img1, float* d_flow, void* stream);
+/* The blueprints the device stream draws for those samples, downloaded into an ordinary task batch
+ * (inspection, and rendering the very same scenes through the host path / the oracle). */
+int ofdg_philox_tasks(ofdg_generator* g, uint64_t seed, uint64_t first_sample, int32_t batch, int32_t augment, ofdg_tasks* out);
+
 /* Number of kernel launches issued by this generator so far (bench.py's gpu_launches). */
 uint64_t ofdg_launch_count(const ofdg_generator* g);
 /* Device time, measured with CUDA events on the launching stream, spent in the background

@@ -64,7 +64,7 @@ EXPORTS = [
     "ofdg_flatten_ellipse", "ofdg_flatten_polygon", "ofdg_debug_raster_host", "ofdg_create", "ofdg_destroy", "ofdg_upload_textures",
     "ofdg_synth_textures", "ofdg_download_texture", "ofdg_set_fields", "ofdg_render", "ofdg_render_host",
     "ofdg_render_debug", "ofdg_debug_background", "ofdg_debug_composite_luts", "ofdg_prepare", "ofdg_prepared_destroy",
-    "ofdg_render_prepared", "ofdg_generate", "ofdg_generate_host", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_upload_bytes",
+    "ofdg_render_prepared", "ofdg_generate", "ofdg_generate_host", "ofdg_generate_philox", "ofdg_philox_tasks", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_upload_bytes",
 ]
 # include/ofdg/layer.h
 LAYER_EXPORTS = [
@@ -121,6 +121,8 @@ def lib():
         L.ofdg_prepared_destroy.argtypes = [C.c_void_p]
         L.ofdg_render_prepared.argtypes = [C.c_void_p] * 6
         L.ofdg_generate_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 3
+        L.ofdg_generate_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32] + [C.c_void_p] * 4
+        L.ofdg_philox_tasks.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]
         L.ofdg_generate.argtypes = [C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 4
         L.ofdg_layer_last_error.restype = C.c_char_p
         L.ofdg_layer_type.restype = C.c_char_p
@@ -410,6 +412,17 @@ class Generator:
         """Draw + render `batch` samples into HOST blobs (numpy arrays or pinned torch tensors)."""
         p = lambda a: a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
         _check(lib().ofdg_generate_host(self._h, params._h, batch, p(img0), p(img1), p(flow)))
+
+    def generate_philox(self, seed, first_sample, batch, img0, img1, flow, augment=False, stream=None):
+        """Production mode: parameters drawn and flattened on the device (Philox4x32), then rendered."""
+        _check(lib().ofdg_generate_philox(self._h, seed, first_sample, batch, int(bool(augment)), img0.data_ptr(), img1.data_ptr(),
+                                          flow.data_ptr(), stream))
+
+    def philox_tasks(self, seed, first_sample, batch, augment=False):
+        """The blueprints the device stream draws for these samples, as an ordinary task batch."""
+        t = Tasks()
+        _check(lib().ofdg_philox_tasks(self._h, seed, first_sample, batch, int(bool(augment)), t._h))
+        return t
 
     def launch_count(self):
         return int(lib().ofdg_launch_count(self._h))

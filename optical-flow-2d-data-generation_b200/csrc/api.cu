@@ -14,6 +14,7 @@
 #include "host/params.hpp"
 #include "ofdg/ofdg.h"
 #include "raster_tile.h"
+#include "philox.cuh"
 #include "render.cuh"
 
 namespace {
@@ -121,6 +122,10 @@ struct ofdg_generator {
   uint64_t timed_calls = 0;
   size_t last_upload_bytes = 0;
   int scratch_batch = 0;
+  // device-side (Philox) parameter stream
+  DevBuf ph_slots, ph_bp, ph_bp_count, ph_seg_type, ph_seg_x, ph_seg_y, ph_seg_count, ph_top, ph_ntop;
+  DeviceScene ph_scene;
+  int ph_batch = 0;
   DevBuf rtab_pos_x, rtab_alpha_x, rtab_pos_y, rtab_alpha_y;  // CImg linear-resize tables for every source length
   // texture pool
   DevBuf pool;
@@ -441,7 +446,8 @@ void ofdg_destroy(ofdg_generator* g) {
   if (!g) return;
   cudaSetDevice(g->cfg.device);
   if (g->stream) cudaStreamSynchronize(g->stream);
-  DevBuf* bufs[] = {&g->pool, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->bg, &g->tile_hits, &g->rtab_pos_x, &g->rtab_alpha_x, &g->rtab_pos_y, &g->rtab_alpha_y, &g->out0, &g->out1,
+  g->ph_scene.release();
+  DevBuf* bufs[] = {&g->ph_slots, &g->ph_bp, &g->ph_bp_count, &g->ph_seg_type, &g->ph_seg_x, &g->ph_seg_y, &g->ph_seg_count, &g->ph_top, &g->ph_ntop, &g->pool, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->bg, &g->tile_hits, &g->rtab_pos_x, &g->rtab_alpha_x, &g->rtab_pos_y, &g->rtab_alpha_y, &g->out0, &g->out1,
                     &g->outf, &g->dbg_masks, &g->dbg_id0, &g->dbg_id1, &g->dbg_frames8, &g->dbg_planar};
   for (DevBuf* b : bufs) b->release();
   g->scene.release();
@@ -710,6 +716,115 @@ int ofdg_debug_composite_luts(ofdg_generator* g, uint8_t* add_lut, uint8_t* sub_
     CK(cudaMemcpyAsync(sub_lut, d + 65536, 65536, cudaMemcpyDeviceToHost, g->stream));
     CK(cudaStreamSynchronize(g->stream));
     CK(cudaGetLastError());
+  });
+}
+
+namespace {
+void philox_run(ofdg_generator* g, uint64_t seed, uint64_t first_sample, int batch, int augment, int fg_override, cudaStream_t s) {
+  if (g->cfg.mode == 9) throw ArgError("the device-side parameter stream does not cover mode 9 (warp fields are injected through the host stream)");
+  if (g->n_tex <= 0) throw StateError("no textures uploaded (ofdg_upload_textures / ofdg_synth_textures)");
+  if (batch <= 0 || batch > g->cfg.max_batch) throw ArgError("bad batch size");
+  using namespace ofdg;
+  if (!g->ph_slots.p) {
+    SlotSpec specs[kNumSlots];
+    fill_mode_table(g->cfg.mode, g->cfg.width, g->cfg.height, specs);
+    std::vector<PhiloxSlot> ps(kPhiloxSlots);
+    for (int i = 0; i < kNumSlots; ++i) {
+      PhiloxSlot q{};
+      q.kind = specs[i].kind; q.n_opts = specs[i].n_opts;
+      for (int k = 0; k < 4; ++k) q.opts[k] = specs[i].opts[k];
+      q.ia = (int)specs[i].a; q.ib = (int)specs[i].b;
+      q.a = (float)specs[i].a; q.b = (float)specs[i].b; q.c = (float)specs[i].c; q.d = (float)specs[i].d;
+      ps[i] = q;
+    }
+    g->ph_slots.reserve(ps.size() * sizeof(PhiloxSlot));
+    CK(cudaMemcpy(g->ph_slots.p, ps.data(), ps.size() * sizeof(PhiloxSlot), cudaMemcpyHostToDevice));
+    double c[100], sn[100];
+    for (unsigned st = 0; st < 100; ++st) {  // the unit-circle table of agg::ellipse, from the host's libm (host/flatten.cpp)
+      const double angle = double(st) / double(100) * 2.0 * 3.14159265358979323846;
+      c[st] = std::cos(angle); sn[st] = std::sin(angle);
+    }
+    philox_upload_circle(c, sn);
+  }
+  if (batch > g->ph_batch) {
+    CK(cudaDeviceSynchronize());
+    const size_t n = batch;
+    g->ph_bp.reserve(n * kPhiloxMaxBp * sizeof(ofdg_blueprint)); g->ph_bp_count.reserve(n * sizeof(int));
+    g->ph_seg_type.reserve(n * kPhiloxMaxSeg * sizeof(int32_t)); g->ph_seg_x.reserve(n * kPhiloxMaxSeg * sizeof(float));
+    g->ph_seg_y.reserve(n * kPhiloxMaxSeg * sizeof(float)); g->ph_seg_count.reserve(n * sizeof(int));
+    g->ph_top.reserve(n * kPhiloxMaxObj * sizeof(int)); g->ph_ntop.reserve(n * sizeof(int));
+    g->ph_scene.samples.reserve(n * sizeof(FlatSample));
+    g->ph_scene.objects.reserve(n * kPhiloxMaxObj * sizeof(FlatObject));
+    g->ph_scene.shapes.reserve(n * kPhiloxMaxObj * kPhiloxMaxShapes * sizeof(FlatShape));
+    g->ph_scene.verts.reserve(n * kPhiloxMaxObj * (size_t)kPhiloxMaxVerts * sizeof(FlatVertex));
+    g->ph_batch = batch;
+  }
+  PhiloxArgs a{};
+  a.slots = (const PhiloxSlot*)g->ph_slots.p;
+  a.mode = g->cfg.mode; a.W = g->cfg.width; a.H = g->cfg.height;
+  a.seed = seed; a.first_sample = first_sample;
+  a.batch = batch; a.n_fields = 0; a.fg_override = fg_override; a.augment = augment;
+  a.n_tex = g->n_tex; a.tex_w = g->tex_w; a.tex_h = g->tex_h;
+  a.bp = (ofdg_blueprint*)g->ph_bp.p; a.bp_count = (int*)g->ph_bp_count.p;
+  a.seg_type = (int32_t*)g->ph_seg_type.p; a.seg_x = (float*)g->ph_seg_x.p; a.seg_y = (float*)g->ph_seg_y.p; a.seg_count = (int*)g->ph_seg_count.p;
+  a.top_index = (int*)g->ph_top.p; a.n_top = (int*)g->ph_ntop.p;
+  a.samples = (FlatSample*)g->ph_scene.samples.p; a.objects = (FlatObject*)g->ph_scene.objects.p;
+  a.shapes = (FlatShape*)g->ph_scene.shapes.p; a.verts = (FlatVertex*)g->ph_scene.verts.p;
+  g->launches += launch_philox(a, s);
+  g->ph_scene.batch = batch;
+  g->ph_scene.n_deform = 0;
+}
+}  // namespace
+
+int ofdg_generate_philox(ofdg_generator* g, uint64_t seed, uint64_t first_sample, int32_t batch, int32_t augment,
+                         float* d_img0, float* d_img1, float* d_flow, void* stream) {
+  return guarded([&] {
+    if (!g || !d_img0 || !d_img1 || !d_flow) throw ArgError("null pointer");
+    g->use();
+    cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
+    philox_run(g, seed, first_sample, batch, augment, 0, s);
+    ensure_scratch(g, batch);
+    run_kernels(g, make_args(g, g->ph_scene, d_img0, d_img1, d_flow), s);
+    if (!stream) CK(cudaStreamSynchronize(s));
+  });
+}
+
+int ofdg_philox_tasks(ofdg_generator* g, uint64_t seed, uint64_t first_sample, int32_t batch, int32_t augment, ofdg_tasks* out) {
+  return guarded([&] {
+    if (!g || !out) throw ArgError("null pointer");
+    g->use();
+    using namespace ofdg;
+    philox_run(g, seed, first_sample, batch, augment, 0, g->stream);
+    CK(cudaStreamSynchronize(g->stream));
+    std::vector<ofdg_blueprint> bp((size_t)batch * kPhiloxMaxBp);
+    std::vector<int32_t> st((size_t)batch * kPhiloxMaxSeg);
+    std::vector<float> sx(st.size()), sy(st.size());
+    std::vector<int> nbp(batch), nseg(batch);
+    std::vector<FlatSample> smp(batch);
+    CK(cudaMemcpy(bp.data(), g->ph_bp.p, bp.size() * sizeof(ofdg_blueprint), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(st.data(), g->ph_seg_type.p, st.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(sx.data(), g->ph_seg_x.p, sx.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(sy.data(), g->ph_seg_y.p, sy.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(nbp.data(), g->ph_bp_count.p, batch * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(nseg.data(), g->ph_seg_count.p, batch * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(smp.data(), g->ph_scene.samples.p, batch * sizeof(FlatSample), cudaMemcpyDeviceToHost));
+    // compact the fixed-stride device arrays into an ordinary task batch
+    TaskBatch& tb = out->tb;
+    tb.clear();
+    for (int s = 0; s < batch; ++s) {
+      const int bp0 = s * kPhiloxMaxBp, sg0 = s * kPhiloxMaxSeg;
+      const int new_bp0 = (int)tb.blueprints.size(), new_sg0 = (int)tb.seg_type.size();
+      for (int i = 0; i < nbp[s]; ++i) {
+        ofdg_blueprint b = bp[bp0 + i];
+        if (b.seg_count > 0) b.seg_begin = b.seg_begin - sg0 + new_sg0;
+        if (b.comp_count > 0) b.comp_begin = b.comp_begin - bp0 + new_bp0;
+        if (b.parent >= 0) b.parent = b.parent - bp0 + new_bp0;
+        tb.blueprints.push_back(b);
+      }
+      for (int i = 0; i < nseg[s]; ++i) { tb.seg_type.push_back(st[sg0 + i]); tb.seg_x.push_back(sx[sg0 + i]); tb.seg_y.push_back(sy[sg0 + i]); }
+      tb.task_begin.push_back((int32_t)tb.blueprints.size());
+      if (augment) tb.augment.push_back(smp[s].aug);
+    }
   });
 }
 

@@ -9,17 +9,23 @@
 #pragma once
 #include <cmath>
 
+#if defined(__CUDACC__)
+#define OFDG_AFFINE_FN __host__ __device__
+#else
+#define OFDG_AFFINE_FN
+#endif
+
 namespace ofdg {
 
 struct Affine {
   double sx = 1, shy = 0, shx = 0, sy = 1, tx = 0, ty = 0;
 
-  static Affine rotation(double a) { return Affine{std::cos(a), std::sin(a), -std::sin(a), std::cos(a), 0.0, 0.0}; }
-  static Affine scaling(double s) { return Affine{s, 0.0, 0.0, s, 0.0, 0.0}; }
-  static Affine translation(double x, double y) { return Affine{1.0, 0.0, 0.0, 1.0, x, y}; }
+  OFDG_AFFINE_FN static Affine rotation(double a) { return Affine{cos(a), sin(a), -sin(a), cos(a), 0.0, 0.0}; }
+  OFDG_AFFINE_FN static Affine scaling(double s) { return Affine{s, 0.0, 0.0, s, 0.0, 0.0}; }
+  OFDG_AFFINE_FN static Affine translation(double x, double y) { return Affine{1.0, 0.0, 0.0, 1.0, x, y}; }
 
   // trans_affine::multiply
-  Affine& then(const Affine& m) {
+  OFDG_AFFINE_FN Affine& then(const Affine& m) {
     double t0 = sx * m.sx + shy * m.shx;
     double t2 = shx * m.sx + sy * m.shx;
     double t4 = tx * m.sx + ty * m.shx + m.tx;
@@ -33,7 +39,7 @@ struct Affine {
   }
 
   // trans_affine::invert
-  Affine inverse() const {
+  OFDG_AFFINE_FN Affine inverse() const {
     Affine r = *this;
     double d = 1.0 / (r.sx * r.sy - r.shy * r.shx);
     double t0 = r.sy * d;
@@ -48,18 +54,18 @@ struct Affine {
   }
 
   // trans_affine::transform
-  void apply(double* x, double* y) const {
+  OFDG_AFFINE_FN void apply(double* x, double* y) const {
     double tmp = *x;
     *x = tmp * sx + *y * shx + tx;
     *y = tmp * shy + *y * sy + ty;
   }
 
-  void store(double out[6]) const {
+  OFDG_AFFINE_FN void store(double out[6]) const {
     out[0] = sx; out[1] = shy; out[2] = shx; out[3] = sy; out[4] = tx; out[5] = ty;
   }
 };
 
 // agg::iround
-static inline int iround(double v) { return int((v < 0.0) ? v - 0.5 : v + 0.5); }
+OFDG_AFFINE_FN static inline int iround(double v) { return int((v < 0.0) ? v - 0.5 : v + 0.5); }
 
 }  // namespace ofdg

@@ -1,0 +1,538 @@
+// Device-side ("production") scene generation: parameters drawn with counter-based Philox4x32-10 and
+// geometry flattened on the GPU, so that no host work is left on the path (the host-RNG
+// stream of host/params.cpp is the parity mode and stays the reference-comparable one).
+//
+//   philox_params_kernel    one thread per sample: ObjectParametersGenerator's logic
+//                           (/root/reference/src/caffe/DataGenerator.cpp:2105-2835, same mode tables, same
+//                           branch structure) with every engine replaced by Philox keyed on
+//                           (seed, sample index, slot, draw number) -> blueprints in the ABI's POD layout
+//   philox_flatten_kernel   one thread per (sample, top-level object): host/flatten.cpp on the device
+//
+// A sample is a pure function of (mode, seed, sample index): any GPU reproduces any sample. The streams
+// are statistically, not bitwise, equal to the host mode's (different engine, device libm).
+#include "philox.cuh"
+
+#include "host/affine.hpp"
+#include "ofdg/augment.h"
+
+namespace ofdg {
+
+namespace {
+
+__constant__ double c_circle_cos[100];
+__constant__ double c_circle_sin[100];
+
+// ---- Philox-backed engines ---------------------------------------------------------------------------
+struct Rng {
+  uint32_t k0, k1, s0, s1;
+  unsigned short ctr[kPhiloxSlots];
+  __device__ void init(uint64_t seed, uint64_t sample) {
+    k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); s0 = (uint32_t)sample; s1 = (uint32_t)(sample >> 32);
+    for (int i = 0; i < kPhiloxSlots; ++i) ctr[i] = 0;
+  }
+  __device__ void raw(int slot, uint32_t& a, uint32_t& b) {
+    uint32_t x0 = s0, x1 = s1, x2 = (uint32_t)slot, x3 = ctr[slot]++;
+    uint32_t ka = k0, kb = k1;
+    for (int r = 0; r < 10; ++r) {
+      const uint64_t p0 = (uint64_t)0xD2511F53u * x0, p1 = (uint64_t)0xCD9E8D57u * x2;
+      const uint32_t y0 = (uint32_t)(p1 >> 32) ^ x1 ^ ka, y1 = (uint32_t)p1, y2 = (uint32_t)(p0 >> 32) ^ x3 ^ kb, y3 = (uint32_t)p0;
+      x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+      ka += 0x9E3779B9u; kb += 0xBB67AE85u;
+    }
+    a = x0; b = x1;
+  }
+  __device__ float unit(int slot) {  // [0, 1)
+    uint32_t a, b;
+    raw(slot, a, b);
+    return (float)(a >> 8) * (1.0f / 16777216.0f);
+  }
+  __device__ float normal(int slot) {  // Box-Muller
+    uint32_t a, b;
+    raw(slot, a, b);
+    const float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f), u2 = (float)(b >> 8) * (1.0f / 16777216.0f);
+    return sqrtf(-2.0f * logf(u1)) * cosf(6.28318530717958647692f * u2);
+  }
+};
+
+struct Gen {
+  const PhiloxSlot* slots;
+  Rng rng;
+  int mode;
+  __device__ float base_gauss(float a, float b, float input, float normalize) {  // DG.cpp:828-831
+    const float sample = input * ((b + a) / 2.f - a) / normalize + (b + a) / 2.f;
+    return (a <= sample && sample <= b) ? sample : (b + a) / 2.f;
+  }
+  __device__ float real(int slot) {
+    const PhiloxSlot& s = slots[slot];
+    switch (s.kind) {
+      case 1: return s.a + (s.b - s.a) * rng.unit(slot);                                     // UREAL
+      case 5: { float t = rng.normal(slot); t = t > 0 ? t * t : -(t * t); return base_gauss(s.a, s.b, t, 6); }   // GAUSS_SQ
+      case 6: { float t = rng.normal(slot); return base_gauss(s.a, s.b, t * t * t, 10); }      // GAUSS_3
+      case 7: { float t = rng.normal(slot); const float q = t * t * t * t; return base_gauss(s.a, s.b, t > 0 ? q : -q, 15); }  // GAUSS_4
+      default: { float t = rng.normal(slot) * s.d + s.c; return (s.a <= t && t <= s.b) ? t : s.c; }  // GAUSS_MSR
+    }
+  }
+  __device__ int integer(int slot) {
+    const PhiloxSlot& s = slots[slot];
+    uint32_t a, b;
+    rng.raw(slot, a, b);
+    if (s.kind == 0) {  // UINT in [a, b]
+      const uint64_t range = (uint64_t)((long long)s.ib - (long long)s.ia) + 1ull;
+      return s.ia + (int)(((uint64_t)a * range) >> 32);
+    }
+    return s.opts[(int)(((uint64_t)a * (uint64_t)s.n_opts) >> 32)];  // CHOICE_*
+  }
+  __device__ bool trigger(int slot) {
+    const PhiloxSlot& s = slots[slot];
+    return s.a + (s.b - s.a) * rng.unit(slot) < s.c;
+  }
+};
+
+enum {  // slot indices, DataGenerator.h:524-587
+  BgTexID = 0, BgInitRot, BgInitTransX, BgInitTransY, BgRotTrigger, BgRot, BgTransX, BgTransY, BgScaleTrigger, BgInitScale,
+  BgScale, NumberOfFgObjects, ObjType, ObjTexID, ObjInitTransX, ObjInitTransY, ObjTransX, ObjTransY, ObjInitRot, ObjRotTrigger,
+  ObjRot, ObjInitScale, ObjScaleTrigger, ObjScale, ObjTexShiftX, ObjTexShiftY, ObjTexRot, ObjTexZoom, ElliObj_ScaleX,
+  ElliObj_ScaleY, PolyObj_spokes, PolyObj_dphi, PolyObj_r, PolyObj_ScaleX, PolyObj_ScaleY, PolyObj_CurveTrigger,
+  CompObjInitTransX, CompObjInitTransY, CompObiNumberOfComponents, ComponentIsAdditive, ComponentOffset, ObjIsExtraThin,
+  ObjDeformsNonrigidly, GenericUniform, GenericTrigger, AugGain, AugBrightness, AugContrast, AugSigma, AugSeed
+};
+
+struct SampleOut {  // this sample's slice of the blueprint arrays
+  ofdg_blueprint* bp;
+  int32_t* seg_type;
+  float* seg_x;
+  float* seg_y;
+  int nbp, nseg;
+  int bp_base, seg_base;  // absolute offsets (the batch is one ofdg_task_batch)
+};
+
+__device__ ofdg_blueprint blank_bp() {
+  ofdg_blueprint b;
+  memset(&b, 0, sizeof(b));
+  b.parent = -1;
+  b.field_id = -1;
+  return b;
+}
+
+__device__ void gen_polygon(Gen& g, SampleOut& o, ofdg_blueprint& b, bool curves) {
+  b.seg_begin = o.seg_base + o.nseg;
+  float* sx = o.seg_x + o.nseg;
+  float* sy = o.seg_y + o.nseg;
+  int32_t* st = o.seg_type + o.nseg;
+  if (g.mode == 1) {  // DG.cpp:2163-2183
+    const float radius = g.real(PolyObj_r);
+    const float xs = radius * g.real(PolyObj_ScaleX), ys = radius * g.real(PolyObj_ScaleY);
+    sx[0] = xs; sx[1] = xs; sx[2] = -xs; sx[3] = -xs;
+    sy[0] = -ys; sy[1] = ys; sy[2] = ys; sy[3] = -ys;
+    st[0] = OFDG_SEG_DUMMY; st[1] = st[2] = st[3] = OFDG_SEG_LINE;
+    b.seg_count = 4;
+    o.nseg += 4;
+    return;
+  }
+  const int spokes = g.integer(PolyObj_spokes);  // DG.cpp:2469-2495
+  for (int i = 0; i < spokes; ++i) {
+    const float phi = (float)((i * 360. / spokes + g.real(PolyObj_dphi)) * 3.14159265358979323846 / 180.);
+    const float r = g.real(PolyObj_r);
+    sx[i] = r * cosf(phi);  // scaled below, once ScaleX / ScaleY are drawn (same draw order as the reference)
+    sy[i] = r * sinf(phi);
+  }
+  const float xscale = g.real(PolyObj_ScaleX), yscale = g.real(PolyObj_ScaleY);
+  for (int i = 0; i < spokes; ++i) { sx[i] *= xscale; sy[i] *= yscale; st[i] = OFDG_SEG_LINE; }
+  st[0] = OFDG_SEG_DUMMY;
+  for (int i = 1; i < spokes; ++i) {
+    if (curves && (i < spokes - 1) && g.trigger(PolyObj_CurveTrigger)) {
+      st[i] = OFDG_SEG_CURVE3;
+      st[i + 1] = OFDG_SEG_DUMMY;
+      ++i;
+    }
+  }
+  b.seg_count = spokes;
+  o.nseg += spokes;
+}
+
+__device__ void shrink(SampleOut& o, ofdg_blueprint& c, float f) {
+  if (c.obj_type == OFDG_OBJ_ELLIPSE) { c.ellipse_scale_x *= f; c.ellipse_scale_y *= f; }
+  else for (int i = 0; i < c.seg_count; ++i) { o.seg_x[c.seg_begin - o.seg_base + i] *= f; o.seg_y[c.seg_begin - o.seg_base + i] *= f; }
+}
+
+// generateForegroundObject (DG.cpp:2145-2830); components are never composite, so one level of nesting suffices
+__device__ void gen_simple(Gen& g, SampleOut& o, int idx, bool is_component, int n_fields, int& field_draws) {
+  ofdg_blueprint b = o.bp[idx];
+  const bool redraw = (g.mode == 6 || g.mode == 7 || g.mode >= 9), thin_modes = (g.mode == 7 || g.mode >= 9);
+  do { b.obj_type = g.integer(ObjType); } while (redraw && is_component && b.obj_type == OFDG_OBJ_COMPOSITE);
+  b.init_rot = g.real(ObjInitRot);
+  b.init_trans_x = g.real(ObjInitTransX);
+  b.init_trans_y = g.real(ObjInitTransY);
+  b.rot = g.trigger(ObjRotTrigger) ? g.real(ObjRot) : 0.f;
+  b.scale = g.trigger(ObjScaleTrigger) ? g.real(ObjScale) : 1.f;
+  b.trans_x = g.real(ObjTransX);
+  b.trans_y = g.real(ObjTransY);
+  b.tex_id = g.integer(ObjTexID);
+  if (g.mode == 9) {
+    b.do_warpfield_deformation = g.trigger(ObjDeformsNonrigidly);
+    if (!is_component && b.do_warpfield_deformation && n_fields > 0) b.field_id = (field_draws++ / 3) % n_fields;
+  }
+  if (b.obj_type == OFDG_OBJ_ELLIPSE) {
+    b.ellipse_scale_x = g.real(ElliObj_ScaleX) * 50;
+    b.ellipse_scale_y = g.real(ElliObj_ScaleY) * 50;
+    if (thin_modes && !is_component && g.trigger(ObjIsExtraThin)) b.ellipse_scale_x *= 0.05f;
+  } else if (b.obj_type == OFDG_OBJ_POLYGON) {
+    gen_polygon(g, o, b, g.mode >= 4);
+    if (thin_modes && !is_component && g.trigger(ObjIsExtraThin))
+      for (int i = 0; i < b.seg_count; ++i) o.seg_x[b.seg_begin - o.seg_base + i] *= 0.05f;
+  }
+  o.bp[idx] = b;
+}
+
+__device__ void copy_placement(ofdg_blueprint& c, const ofdg_blueprint& b) {
+  c.init_rot = b.init_rot; c.init_trans_x = b.init_trans_x; c.init_trans_y = b.init_trans_y;
+  c.rot = b.rot; c.scale = b.scale; c.trans_x = b.trans_x; c.trans_y = b.trans_y;
+}
+
+__device__ void gen_object(Gen& g, SampleOut& o, int idx, int n_fields, int& field_draws) {
+  gen_simple(g, o, idx, false, n_fields, field_draws);
+  if (o.bp[idx].obj_type != OFDG_OBJ_COMPOSITE) return;
+  const bool thin_modes = (g.mode == 7 || g.mode >= 9);
+  ofdg_blueprint b = o.bp[idx];
+  b.comp_begin = o.bp_base + o.nbp;
+  if (thin_modes && g.trigger(ObjIsExtraThin)) {  // "outline": a shape minus a slightly smaller copy (DG.cpp:2504-2547)
+    const int i1 = o.nbp++;
+    o.bp[i1] = blank_bp();
+    o.bp[i1].obj_type = OFDG_OBJ_COMPOSITE;
+    gen_simple(g, o, i1, true, n_fields, field_draws);
+    ofdg_blueprint c1 = o.bp[i1];
+    c1.parent = o.bp_base + idx;
+    copy_placement(c1, b);
+    c1.is_additive_component = 1;
+    c1.do_warpfield_deformation = b.do_warpfield_deformation; c1.field_id = b.field_id;
+    o.bp[i1] = c1;
+    const int i2 = o.nbp++;
+    ofdg_blueprint c2 = c1;
+    if (c1.obj_type == OFDG_OBJ_POLYGON) {
+      c2.seg_begin = o.seg_base + o.nseg;
+      for (int i = 0; i < c1.seg_count; ++i) {
+        o.seg_type[o.nseg + i] = o.seg_type[c1.seg_begin - o.seg_base + i];
+        o.seg_x[o.nseg + i] = o.seg_x[c1.seg_begin - o.seg_base + i];
+        o.seg_y[o.nseg + i] = o.seg_y[c1.seg_begin - o.seg_base + i];
+      }
+      o.nseg += c1.seg_count;
+    }
+    if (c1.obj_type == OFDG_OBJ_ELLIPSE) {
+      if (g.trigger(GenericTrigger)) {
+        c2.init_trans_x = b.init_trans_x + g.real(CompObjInitTransX);
+        c2.init_trans_y = b.init_trans_y + g.real(CompObjInitTransY);
+      } else {
+        c2.ellipse_scale_x *= 0.9f; c2.ellipse_scale_y *= 0.9f;
+      }
+    } else {
+      shrink(o, c2, 0.9f);
+    }
+    c2.is_additive_component = 0;
+    o.bp[i2] = c2;
+    b.comp_count = 2;
+  } else {  // DG.cpp:2549-2591
+    const int parts = g.integer(CompObiNumberOfComponents);
+    for (int part = 0; part < parts; ++part) {
+      const int ci = o.nbp++;
+      o.bp[ci] = blank_bp();
+      o.bp[ci].obj_type = OFDG_OBJ_COMPOSITE;
+      gen_simple(g, o, ci, true, n_fields, field_draws);
+      ofdg_blueprint c = o.bp[ci];
+      c.parent = o.bp_base + idx;
+      copy_placement(c, b);
+      if (part == 0) {
+        c.is_additive_component = 1;
+      } else {
+        c.init_rot = g.real(ObjInitRot);
+        c.init_trans_x += g.real(ComponentOffset);
+        c.init_trans_y += g.real(ComponentOffset);
+        shrink(o, c, 0.2f);
+        c.is_additive_component = g.trigger(ComponentIsAdditive) ? 1 : 0;
+      }
+      c.do_warpfield_deformation = b.do_warpfield_deformation; c.field_id = b.field_id;
+      o.bp[ci] = c;
+    }
+    b.comp_count = parts;
+  }
+  o.bp[idx] = b;
+}
+
+__global__ void philox_params_kernel(PhiloxArgs a) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= a.batch) return;
+  Gen g;
+  g.slots = a.slots;
+  g.mode = a.mode;
+  g.rng.init(a.seed, a.first_sample + (uint64_t)s);
+  SampleOut o;
+  o.bp_base = s * kPhiloxMaxBp; o.seg_base = s * kPhiloxMaxSeg;
+  o.bp = a.bp + o.bp_base; o.seg_type = a.seg_type + o.seg_base; o.seg_x = a.seg_x + o.seg_base; o.seg_y = a.seg_y + o.seg_base;
+  o.nbp = 0; o.nseg = 0;
+  int field_draws = (int)((a.first_sample + (uint64_t)s) * 7 % 3000);  // decorrelates the field choice between samples
+  // generateBackground, DG.cpp:2105-2143
+  ofdg_blueprint bg = blank_bp();
+  bg.obj_id = 1;
+  bg.obj_type = OFDG_OBJ_POLYGON;
+  bg.rot = g.trigger(BgRotTrigger) ? g.real(BgRot) : 0.f;
+  bg.scale = g.trigger(BgScaleTrigger) ? g.real(BgScale) : 1.f;
+  const float ptx = g.real(BgTransX), pty = g.real(BgTransY);
+  bg.trans_x = cosf(-bg.rot) * ptx - sinf(-bg.rot) * pty;
+  bg.trans_y = sinf(-bg.rot) * ptx + cosf(-bg.rot) * pty;
+  bg.tex_id = g.integer(BgTexID);
+  bg.tex_rot = g.real(BgInitRot);
+  bg.tex_scale = g.real(BgInitScale);
+  bg.tex_shift_x = g.integer(BgInitTransX);
+  bg.tex_shift_y = g.integer(BgInitTransY);
+  bg.do_warpfield_deformation = g.trigger(ObjDeformsNonrigidly);
+  if (a.mode == 9 && bg.do_warpfield_deformation && a.n_fields > 0) bg.field_id = (field_draws++ / 3) % a.n_fields;
+  o.bp[o.nbp++] = bg;
+  int fg = a.fg_override > 0 ? a.fg_override : (int)g.real(NumberOfFgObjects);
+  if (fg > kPhiloxMaxObj) fg = kPhiloxMaxObj;
+  int* top = a.top_index + s * kPhiloxMaxObj;
+  for (int k = 0; k < fg; ++k) {
+    const int idx = o.nbp++;
+    o.bp[idx] = blank_bp();
+    o.bp[idx].obj_id = 10 + k;
+    top[k] = idx;
+    gen_object(g, o, idx, a.n_fields, field_draws);
+  }
+  a.n_top[s] = fg;
+  a.bp_count[s] = o.nbp;
+  a.seg_count[s] = o.nseg;
+  if (a.augment) {
+    ofdg_augment au;
+    au.enabled = 1;
+    for (int c = 0; c < 3; ++c) au.gain[c] = 0.8f + 0.4f * g.rng.unit(AugGain);
+    au.brightness = -20.f + 40.f * g.rng.unit(AugBrightness);
+    au.contrast = 0.7f + 0.6f * g.rng.unit(AugContrast);
+    au.noise_sigma = 10.f * g.rng.unit(AugSigma);
+    g.rng.raw(AugSeed, au.noise_seed[0], au.noise_seed[1]);
+    a.samples[s].aug = au;
+  } else {
+    a.samples[s].aug.enabled = 0;
+  }
+}
+
+// ---- device flatten (host/flatten.cpp restated for one thread per object) ------------------------------
+struct VertOut {
+  FlatVertex* v;
+  int n, cap;
+  int x0, y0, x1, y1;
+  __device__ void begin(FlatVertex* p, int c) { v = p; n = 0; cap = c; x0 = y0 = 0x7FFFFFFF; x1 = y1 = -0x7FFFFFFF; }
+  __device__ void push(double x, double y) {
+    const int fx = iround(x * 256.0), fy = iround(y * 256.0);
+    if (n < cap) { v[n].x = fx; v[n].y = fy; }
+    ++n;
+    x0 = min(x0, fx); x1 = max(x1, fx); y0 = min(y0, fy); y1 = max(y1, fy);
+  }
+};
+
+// agg::curve3_div::recursive_bezier without recursion: pending right halves wait on an explicit stack
+__device__ void subdivide(double x1, double y1, double x2, double y2, double x3, double y3, VertOut& out) {
+  struct Seg { double x1, y1, x2, y2, x3, y3; int level; };
+  Seg stack[34];
+  int sp = 0;
+  stack[sp++] = Seg{x1, y1, x2, y2, x3, y3, 0};
+  while (sp > 0) {
+    const Seg c = stack[--sp];
+    if (c.level > 32) continue;
+    const double x12 = (c.x1 + c.x2) / 2, y12 = (c.y1 + c.y2) / 2, x23 = (c.x2 + c.x3) / 2, y23 = (c.y2 + c.y3) / 2;
+    const double x123 = (x12 + x23) / 2, y123 = (y12 + y23) / 2;
+    const double dx = c.x3 - c.x1, dy = c.y3 - c.y1;
+    double d = fabs(((c.x2 - c.x3) * dy - (c.y2 - c.y3) * dx));
+    if (d > 1e-30) {
+      if (d * d <= 0.25 * (dx * dx + dy * dy)) { out.push(x123, y123); continue; }
+    } else {
+      const double da = dx * dx + dy * dy;
+      if (da == 0) d = (c.x2 - c.x1) * (c.x2 - c.x1) + (c.y2 - c.y1) * (c.y2 - c.y1);
+      else {
+        d = ((c.x2 - c.x1) * dx + (c.y2 - c.y1) * dy) / da;
+        if (d > 0 && d < 1) continue;
+        if (d <= 0) d = (c.x2 - c.x1) * (c.x2 - c.x1) + (c.y2 - c.y1) * (c.y2 - c.y1);
+        else if (d >= 1) d = (c.x3 - c.x2) * (c.x3 - c.x2) + (c.y3 - c.y2) * (c.y3 - c.y2);
+        else { const double ex = c.x1 + d * dx - c.x2, ey = c.y1 + d * dy - c.y2; d = ex * ex + ey * ey; }
+      }
+      if (d < 0.25) { out.push(c.x2, c.y2); continue; }
+    }
+    // left half first: push the right half, then the left one on top of it
+    stack[sp++] = Seg{x123, y123, x23, y23, c.x3, c.y3, c.level + 1};
+    stack[sp++] = Seg{c.x1, c.y1, x12, y12, x123, y123, c.level + 1};
+  }
+}
+
+__device__ void outline(const PhiloxArgs& a, const ofdg_blueprint& b, const Affine& m, VertOut& out) {
+  if (b.obj_type == OFDG_OBJ_ELLIPSE) {
+    for (int st = 0; st < 100; ++st) {
+      double x = 0.0 + c_circle_cos[st] * (double)b.ellipse_scale_x, y = 0.0 + c_circle_sin[st] * (double)b.ellipse_scale_y;
+      m.apply(&x, &y);
+      out.push(x, y);
+    }
+    return;
+  }
+  const int32_t* st = a.seg_type + b.seg_begin;
+  const float* sx = a.seg_x + b.seg_begin;
+  const float* sy = a.seg_y + b.seg_begin;
+  double lx = sx[0], ly = sy[0];
+  m.apply(&lx, &ly);
+  out.push(lx, ly);
+  for (int i = 1; i < b.seg_count; ++i) {
+    if (st[i] == OFDG_SEG_CURVE3 && i + 1 < b.seg_count) {
+      double cx = sx[i], cy = sy[i], ex = sx[i + 1], ey = sy[i + 1];
+      m.apply(&cx, &cy);
+      m.apply(&ex, &ey);
+      subdivide(lx, ly, cx, cy, ex, ey, out);
+      out.push(ex, ey);
+      lx = ex; ly = ey;
+      ++i;
+    } else {
+      lx = sx[i]; ly = sy[i];
+      m.apply(&lx, &ly);
+      out.push(lx, ly);
+    }
+  }
+}
+
+__device__ Affine motion_of(const ofdg_blueprint& b) {
+  Affine m;
+  m.then(Affine::rotation(b.rot));
+  m.then(Affine::scaling(b.scale));
+  m.then(Affine::translation(b.trans_x, b.trans_y));
+  return m;
+}
+
+__device__ float cimg_mod_dev(float x, float m) {
+  const double dx = (double)x, dm = (double)m;
+  return (float)(dx - dm * floor(dx / dm));
+}
+
+__device__ void prepare_bg(const PhiloxArgs& a, const ofdg_blueprint& b, const Affine& tex_inv, bool deformed, BgPrep& p) {
+  const int W = a.W, H = a.H, w = a.tex_w, h = a.tex_h, tw = 2 * W, th = 2 * H;
+  p.tex = (int)((unsigned)b.tex_id % (unsigned)a.n_tex);
+  p.shift_x = b.tex_shift_x; p.shift_y = b.tex_shift_y;
+  const float nangle = cimg_mod_dev(b.tex_rot, 360.0f);
+  p.rot_identity = (cimg_mod_dev(nangle, 90.0f) == 0) ? 1 : 0;
+  if (p.rot_identity) { p.ca = 1.f; p.sa = 0.f; p.rw = w; p.rh = h; }
+  else {
+    const float rad = (float)(nangle * 3.14159265358979323846 / 180.0);
+    p.ca = cosf(rad); p.sa = sinf(rad);
+    const float ux = fabsf((unsigned)(w - 1) * p.ca), uy = fabsf((unsigned)(w - 1) * p.sa), vx = fabsf((unsigned)(h - 1) * p.sa), vy = fabsf((unsigned)(h - 1) * p.ca);
+    p.rw = (int)floorf((1 + ux + vx) + 0.5f);
+    p.rh = (int)floorf((1 + uy + vy) + 0.5f);
+  }
+  p.w2 = 0.5f * (unsigned)(w - 1); p.h2 = 0.5f * (unsigned)(h - 1);
+  p.rw2 = 0.5f * (unsigned)(p.rw - 1); p.rh2 = 0.5f * (unsigned)(p.rh - 1);
+  const float zoom = b.tex_scale;
+  const int x0 = w / 2 - tw / 2, y0 = h / 2 - th / 2;
+  const int x1 = (int)(w / 2 - tw / 2 + tw / zoom - 1), y1 = (int)(h / 2 - th / 2 + th / zoom - 1);
+  p.crop_x0 = min(x0, x1); p.crop_y0 = min(y0, y1);
+  p.crop_w = abs(x1 - x0) + 1; p.crop_h = abs(y1 - y0) + 1;
+  int nx0 = W / 2, ny0 = H / 2, nx1 = W / 2 + W - 1, ny1 = H / 2 + H - 1;
+  if (deformed) { nx0 = 0; ny0 = 0; nx1 = tw - 1; ny1 = th - 1; }
+  else {
+    double fx0 = 1e300, fy0 = 1e300, fx1 = -1e300, fy1 = -1e300;
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j) {
+        double x = i ? W / 2 + W + 1.0 : W / 2 + 0.0, y = j ? H / 2 + H + 1.0 : H / 2 + 0.0;
+        tex_inv.apply(&x, &y);
+        fx0 = fmin(fx0, x); fx1 = fmax(fx1, x); fy0 = fmin(fy0, y); fy1 = fmax(fy1, y);
+      }
+    const int ax0 = (int)floor(fx0) - 3, ax1 = (int)ceil(fx1) + 3, ay0 = (int)floor(fy0) - 3, ay1 = (int)ceil(fy1) + 3;
+    if (ax0 < 0 || ax1 > tw - 1) { nx0 = 0; nx1 = tw - 1; } else { nx0 = min(nx0, ax0); nx1 = max(nx1, ax1); }
+    if (ay0 < 0 || ay1 > th - 1) { ny0 = 0; ny1 = th - 1; } else { ny0 = min(ny0, ay0); ny1 = max(ny1, ay1); }
+  }
+  p.need[0] = nx0; p.need[1] = ny0; p.need[2] = nx1; p.need[3] = ny1;
+}
+
+__global__ void philox_flatten_kernel(PhiloxArgs a) {
+  const int s = blockIdx.x, k = threadIdx.x;  // sample, top-level object (thread kPhiloxMaxObj: the background)
+  const int W = a.W, H = a.H;
+  const ofdg_blueprint* bp = a.bp;
+  const ofdg_blueprint& bg = bp[s * kPhiloxMaxBp];
+  const Affine bgM = motion_of(bg);
+  if (k == kPhiloxMaxObj) {
+    FlatSample smp = a.samples[s];  // keeps the augmentation record written by the parameter kernel
+    Affine bgI;
+    bgI.then(Affine::rotation(0.0));
+    bgI.then(Affine::translation((double)W, (double)H));
+    Affine tex_tf = bgI.inverse();
+    tex_tf.then(bgM);
+    tex_tf.then(bgI);
+    const Affine tex_inv = tex_tf.inverse();
+    tex_inv.store(smp.bg_tex_inv);
+    bgM.store(smp.bg_motion);
+    const bool deformed = false;  // see above: mode 9 is host-driven
+    smp.bg_field = -1;
+    prepare_bg(a, bg, tex_inv, deformed, smp.prep);
+    smp.obj_begin = s * kPhiloxMaxObj;
+    smp.obj_count = a.n_top[s];
+    a.samples[s] = smp;
+    return;
+  }
+  if (k >= a.n_top[s]) return;
+  const ofdg_blueprint& b = bp[s * kPhiloxMaxBp + a.top_index[s * kPhiloxMaxObj + k]];
+  Affine bg_n = Affine::translation(-W / 2., -H / 2.);
+  bg_n.then(bgM);
+  bg_n.then(Affine::translation(W / 2., H / 2.));
+  FlatObject o;
+  memset(&o, 0, sizeof(o));
+  o.obj_id = b.obj_id;
+  o.tex = (int)((unsigned)b.tex_id % (unsigned)a.n_tex);
+  o.field = -1;  // warp fields (mode 9) need the mask pre-pass bookkeeping of the host path: the device stream rejects mode 9
+  o.composite = b.obj_type == OFDG_OBJ_COMPOSITE;
+  const int obj_slot = s * kPhiloxMaxObj + k;
+  o.shape_begin = obj_slot * kPhiloxMaxShapes;
+  const int nshape = o.composite ? b.comp_count : 1;
+  o.shape_count = nshape;
+  FlatVertex* vbase = a.verts + (size_t)obj_slot * kPhiloxMaxVerts;
+  int vused = 0;
+  for (int f = 0; f < 2; ++f) { o.bbox[f][0] = o.bbox[f][1] = 0x7FFFFFFF; o.bbox[f][2] = o.bbox[f][3] = -0x7FFFFFFF; }
+  Affine M = motion_of(b);
+  M.then(bg_n);
+  for (int si = 0; si < nshape; ++si) {
+    const ofdg_blueprint& c = o.composite ? bp[b.comp_begin + si] : b;
+    Affine I;
+    I.then(Affine::rotation(c.init_rot));
+    I.then(Affine::translation(c.init_trans_x, c.init_trans_y));
+    Affine Mc = motion_of(c);
+    Mc.then(bg_n);
+    Affine IM = I;
+    IM.then(Mc);
+    FlatShape sh;
+    memset(&sh, 0, sizeof(sh));
+    sh.additive = c.is_additive_component ? 1 : 0;
+    sh.deform = -1;
+    for (int f = 0; f < 2; ++f) {
+      VertOut out;
+      out.begin(vbase + vused, max(0, kPhiloxMaxVerts - vused));
+      outline(a, c, f ? IM : I, out);
+      if (out.n > out.cap) out.n = 0;  // out of room: drop the outline rather than corrupt memory (never seen in practice)
+      sh.vbegin[f] = (int)(obj_slot * (size_t)kPhiloxMaxVerts + vused);
+      sh.vcount[f] = out.n;
+      vused += out.n;
+      if (out.n) { sh.bbox[f][0] = out.x0 >> 8; sh.bbox[f][1] = out.y0 >> 8; sh.bbox[f][2] = out.x1 >> 8; sh.bbox[f][3] = out.y1 >> 8; }
+      else { sh.bbox[f][0] = sh.bbox[f][1] = 0x7FFFFFF0; sh.bbox[f][2] = sh.bbox[f][3] = -0x7FFFFFF0; }
+      o.bbox[f][0] = min(o.bbox[f][0], sh.bbox[f][0]); o.bbox[f][1] = min(o.bbox[f][1], sh.bbox[f][1]);
+      o.bbox[f][2] = max(o.bbox[f][2], sh.bbox[f][2]); o.bbox[f][3] = max(o.bbox[f][3], sh.bbox[f][3]);
+    }
+    for (int i = 0; i < 4; ++i) sh.raw1[i] = sh.bbox[1][i];
+    a.shapes[o.shape_begin + si] = sh;
+  }
+  M.store(o.motion);
+  M.inverse().store(o.tex_inv);
+  a.objects[obj_slot] = o;
+}
+
+}  // namespace
+
+void philox_upload_circle(const double* c, const double* s) {
+  cudaMemcpyToSymbol(c_circle_cos, c, 100 * sizeof(double));
+  cudaMemcpyToSymbol(c_circle_sin, s, 100 * sizeof(double));
+}
+
+int launch_philox(const PhiloxArgs& a, cudaStream_t s) {
+  philox_params_kernel<<<(a.batch + 31) / 32, 32, 0, s>>>(a);
+  philox_flatten_kernel<<<a.batch, kPhiloxMaxObj + 1, 0, s>>>(a);
+  return 2;
+}
+
+}  // namespace ofdg
