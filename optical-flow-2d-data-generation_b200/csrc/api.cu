@@ -123,8 +123,16 @@ struct ofdg_generator {
   size_t last_upload_bytes = 0;
   int scratch_batch = 0;
   // device-side (Philox) parameter stream
-  DevBuf ph_slots, ph_bp, ph_bp_count, ph_seg_type, ph_seg_x, ph_seg_y, ph_seg_count, ph_top, ph_ntop;
-  DeviceScene ph_scene;
+  // (two sets: while batch k renders, batch k+1 is drawn and flattened on a side stream)
+  DevBuf ph_slots;
+  struct PhiloxSet {
+    DevBuf bp, seg_type, seg_x, seg_y, obj_nbp, obj_nseg, ntop;
+    DeviceScene scene;
+    cudaEvent_t ready = nullptr, consumed = nullptr;
+    bool used = false;
+  } ph[2];
+  cudaStream_t ph_stream = nullptr;
+  struct { bool valid = false; uint64_t seed = 0, first = 0; int batch = 0, augment = 0, set = 0; } ph_next;
   int ph_batch = 0;
   DevBuf rtab_pos_x, rtab_alpha_x, rtab_pos_y, rtab_alpha_y;  // CImg linear-resize tables for every source length
   // texture pool
@@ -424,6 +432,11 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
     g->cfg = *cfg;
     CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g->ph_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&g->ph[i].ready, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&g->ph[i].consumed, cudaEventDisableTiming));
+    }
     {  // one-time: the resize tables for every possible crop length (they depend on nothing else)
       const size_t W2 = 2 * (size_t)cfg->width, H2 = 2 * (size_t)cfg->height;
       g->rtab_pos_x.reserve(W2 * W2 * sizeof(int)); g->rtab_alpha_x.reserve(W2 * W2 * sizeof(double));
@@ -446,8 +459,16 @@ void ofdg_destroy(ofdg_generator* g) {
   if (!g) return;
   cudaSetDevice(g->cfg.device);
   if (g->stream) cudaStreamSynchronize(g->stream);
-  g->ph_scene.release();
-  DevBuf* bufs[] = {&g->ph_slots, &g->ph_bp, &g->ph_bp_count, &g->ph_seg_type, &g->ph_seg_x, &g->ph_seg_y, &g->ph_seg_count, &g->ph_top, &g->ph_ntop, &g->pool, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->bg, &g->tile_hits, &g->rtab_pos_x, &g->rtab_alpha_x, &g->rtab_pos_y, &g->rtab_alpha_y, &g->out0, &g->out1,
+  if (g->ph_stream) { cudaStreamSynchronize(g->ph_stream); cudaStreamDestroy(g->ph_stream); }
+  for (int i = 0; i < 2; ++i) {
+    ofdg_generator::PhiloxSet& q = g->ph[i];
+    q.scene.release();
+    DevBuf* qb[] = {&q.bp, &q.seg_type, &q.seg_x, &q.seg_y, &q.obj_nbp, &q.obj_nseg, &q.ntop};
+    for (DevBuf* b : qb) b->release();
+    if (q.ready) cudaEventDestroy(q.ready);
+    if (q.consumed) cudaEventDestroy(q.consumed);
+  }
+  DevBuf* bufs[] = {&g->ph_slots, &g->pool, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->bg, &g->tile_hits, &g->rtab_pos_x, &g->rtab_alpha_x, &g->rtab_pos_y, &g->rtab_alpha_y, &g->out0, &g->out1,
                     &g->outf, &g->dbg_masks, &g->dbg_id0, &g->dbg_id1, &g->dbg_frames8, &g->dbg_planar};
   for (DevBuf* b : bufs) b->release();
   g->scene.release();
@@ -720,10 +741,7 @@ int ofdg_debug_composite_luts(ofdg_generator* g, uint8_t* add_lut, uint8_t* sub_
 }
 
 namespace {
-void philox_run(ofdg_generator* g, uint64_t seed, uint64_t first_sample, int batch, int augment, int fg_override, cudaStream_t s) {
-  if (g->cfg.mode == 9) throw ArgError("the device-side parameter stream does not cover mode 9 (warp fields are injected through the host stream)");
-  if (g->n_tex <= 0) throw StateError("no textures uploaded (ofdg_upload_textures / ofdg_synth_textures)");
-  if (batch <= 0 || batch > g->cfg.max_batch) throw ArgError("bad batch size");
+void philox_run(ofdg_generator* g, int set, uint64_t seed, uint64_t first_sample, int batch, int augment, int fg_override, cudaStream_t s) {
   using namespace ofdg;
   if (!g->ph_slots.p) {
     SlotSpec specs[kNumSlots];
@@ -746,33 +764,47 @@ void philox_run(ofdg_generator* g, uint64_t seed, uint64_t first_sample, int bat
     }
     philox_upload_circle(c, sn);
   }
-  if (batch > g->ph_batch) {
-    CK(cudaDeviceSynchronize());
-    const size_t n = batch;
-    g->ph_bp.reserve(n * kPhiloxMaxBp * sizeof(ofdg_blueprint)); g->ph_bp_count.reserve(n * sizeof(int));
-    g->ph_seg_type.reserve(n * kPhiloxMaxSeg * sizeof(int32_t)); g->ph_seg_x.reserve(n * kPhiloxMaxSeg * sizeof(float));
-    g->ph_seg_y.reserve(n * kPhiloxMaxSeg * sizeof(float)); g->ph_seg_count.reserve(n * sizeof(int));
-    g->ph_top.reserve(n * kPhiloxMaxObj * sizeof(int)); g->ph_ntop.reserve(n * sizeof(int));
-    g->ph_scene.samples.reserve(n * sizeof(FlatSample));
-    g->ph_scene.objects.reserve(n * kPhiloxMaxObj * sizeof(FlatObject));
-    g->ph_scene.shapes.reserve(n * kPhiloxMaxObj * kPhiloxMaxShapes * sizeof(FlatShape));
-    g->ph_scene.verts.reserve(n * kPhiloxMaxObj * (size_t)kPhiloxMaxVerts * sizeof(FlatVertex));
-    g->ph_batch = batch;
-  }
+  ofdg_generator::PhiloxSet& q = g->ph[set];
   PhiloxArgs a{};
   a.slots = (const PhiloxSlot*)g->ph_slots.p;
   a.mode = g->cfg.mode; a.W = g->cfg.width; a.H = g->cfg.height;
   a.seed = seed; a.first_sample = first_sample;
   a.batch = batch; a.n_fields = 0; a.fg_override = fg_override; a.augment = augment;
   a.n_tex = g->n_tex; a.tex_w = g->tex_w; a.tex_h = g->tex_h;
-  a.bp = (ofdg_blueprint*)g->ph_bp.p; a.bp_count = (int*)g->ph_bp_count.p;
-  a.seg_type = (int32_t*)g->ph_seg_type.p; a.seg_x = (float*)g->ph_seg_x.p; a.seg_y = (float*)g->ph_seg_y.p; a.seg_count = (int*)g->ph_seg_count.p;
-  a.top_index = (int*)g->ph_top.p; a.n_top = (int*)g->ph_ntop.p;
-  a.samples = (FlatSample*)g->ph_scene.samples.p; a.objects = (FlatObject*)g->ph_scene.objects.p;
-  a.shapes = (FlatShape*)g->ph_scene.shapes.p; a.verts = (FlatVertex*)g->ph_scene.verts.p;
+  a.bp = (ofdg_blueprint*)q.bp.p;
+  a.seg_type = (int32_t*)q.seg_type.p; a.seg_x = (float*)q.seg_x.p; a.seg_y = (float*)q.seg_y.p;
+  a.obj_nbp = (int*)q.obj_nbp.p; a.obj_nseg = (int*)q.obj_nseg.p; a.n_top = (int*)q.ntop.p;
+  a.samples = (FlatSample*)q.scene.samples.p; a.objects = (FlatObject*)q.scene.objects.p;
+  a.shapes = (FlatShape*)q.scene.shapes.p; a.verts = (FlatVertex*)q.scene.verts.p;
   g->launches += launch_philox(a, s);
-  g->ph_scene.batch = batch;
-  g->ph_scene.n_deform = 0;
+  q.scene.batch = batch;
+  q.scene.n_deform = 0;
+}
+
+void philox_check(ofdg_generator* g, int batch) {
+  using namespace ofdg;
+  if (g->cfg.mode == 9) throw ArgError("the device-side parameter stream does not cover mode 9 (warp fields are injected through the host stream)");
+  if (g->n_tex <= 0) throw StateError("no textures uploaded (ofdg_upload_textures / ofdg_synth_textures)");
+  if (batch <= 0 || batch > g->cfg.max_batch) throw ArgError("bad batch size");
+  if (batch > g->ph_batch) {
+    CK(cudaDeviceSynchronize());
+    g->ph_next.valid = false;
+    const size_t n = batch;
+    for (int i = 0; i < 2; ++i) {
+      ofdg_generator::PhiloxSet& q = g->ph[i];
+      q.bp.reserve(n * kPhiloxMaxBp * sizeof(ofdg_blueprint));
+      q.seg_type.reserve(n * kPhiloxMaxSeg * sizeof(int32_t)); q.seg_x.reserve(n * kPhiloxMaxSeg * sizeof(float));
+      q.seg_y.reserve(n * kPhiloxMaxSeg * sizeof(float));
+      q.obj_nbp.reserve(n * kPhiloxMaxObj * sizeof(int)); q.obj_nseg.reserve(n * kPhiloxMaxObj * sizeof(int));
+      q.ntop.reserve(n * sizeof(int));
+      q.scene.samples.reserve(n * sizeof(FlatSample));
+      q.scene.objects.reserve(n * kPhiloxMaxObj * sizeof(FlatObject));
+      q.scene.shapes.reserve(n * kPhiloxMaxObj * kPhiloxMaxShapes * sizeof(FlatShape));
+      q.scene.verts.reserve(n * kPhiloxMaxObj * (size_t)kPhiloxMaxVerts * sizeof(FlatVertex));
+      q.used = false;
+    }
+    g->ph_batch = batch;
+  }
 }
 }  // namespace
 
@@ -781,10 +813,30 @@ int ofdg_generate_philox(ofdg_generator* g, uint64_t seed, uint64_t first_sample
   return guarded([&] {
     if (!g || !d_img0 || !d_img1 || !d_flow) throw ArgError("null pointer");
     g->use();
+    philox_check(g, batch);
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
-    philox_run(g, seed, first_sample, batch, augment, 0, s);
+    int set;
+    if (g->ph_next.valid && g->ph_next.seed == seed && g->ph_next.first == first_sample && g->ph_next.batch == batch &&
+        g->ph_next.augment == augment) {
+      set = g->ph_next.set;  // drawn and flattened on the side stream while the previous batch rendered
+      CK(cudaStreamWaitEvent(s, g->ph[set].ready, 0));
+    } else {
+      set = g->ph_next.valid ? (g->ph_next.set ^ 1) : 0;
+      if (g->ph_next.valid) CK(cudaStreamSynchronize(g->ph_stream));  // a speculative batch nobody asked for is still being written
+      if (g->ph[set].used) CK(cudaStreamWaitEvent(s, g->ph[set].consumed, 0));
+      philox_run(g, set, seed, first_sample, batch, augment, 0, s);
+    }
     ensure_scratch(g, batch);
-    run_kernels(g, make_args(g, g->ph_scene, d_img0, d_img1, d_flow), s);
+    run_kernels(g, make_args(g, g->ph[set].scene, d_img0, d_img1, d_flow), s);
+    CK(cudaEventRecord(g->ph[set].consumed, s));
+    g->ph[set].used = true;
+    // look ahead: the next batch of the same stream, on the side stream, into the other set
+    const int nset = set ^ 1;
+    if (g->ph[nset].used) CK(cudaStreamWaitEvent(g->ph_stream, g->ph[nset].consumed, 0));
+    philox_run(g, nset, seed, first_sample + (uint64_t)batch, batch, augment, 0, g->ph_stream);
+    CK(cudaEventRecord(g->ph[nset].ready, g->ph_stream));
+    g->ph_next.valid = true; g->ph_next.seed = seed; g->ph_next.first = first_sample + (uint64_t)batch;
+    g->ph_next.batch = batch; g->ph_next.augment = augment; g->ph_next.set = nset;
     if (!stream) CK(cudaStreamSynchronize(s));
   });
 }
@@ -794,34 +846,41 @@ int ofdg_philox_tasks(ofdg_generator* g, uint64_t seed, uint64_t first_sample, i
     if (!g || !out) throw ArgError("null pointer");
     g->use();
     using namespace ofdg;
-    philox_run(g, seed, first_sample, batch, augment, 0, g->stream);
+    philox_check(g, batch);
+    CK(cudaDeviceSynchronize());
+    g->ph_next.valid = false;
+    philox_run(g, 0, seed, first_sample, batch, augment, 0, g->stream);
     CK(cudaStreamSynchronize(g->stream));
     std::vector<ofdg_blueprint> bp((size_t)batch * kPhiloxMaxBp);
     std::vector<int32_t> st((size_t)batch * kPhiloxMaxSeg);
     std::vector<float> sx(st.size()), sy(st.size());
-    std::vector<int> nbp(batch), nseg(batch);
+    std::vector<int> onbp((size_t)batch * kPhiloxMaxObj), onseg((size_t)batch * kPhiloxMaxObj), ntop(batch);
     std::vector<FlatSample> smp(batch);
-    CK(cudaMemcpy(bp.data(), g->ph_bp.p, bp.size() * sizeof(ofdg_blueprint), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(st.data(), g->ph_seg_type.p, st.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(sx.data(), g->ph_seg_x.p, sx.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(sy.data(), g->ph_seg_y.p, sy.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(nbp.data(), g->ph_bp_count.p, batch * sizeof(int), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(nseg.data(), g->ph_seg_count.p, batch * sizeof(int), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(smp.data(), g->ph_scene.samples.p, batch * sizeof(FlatSample), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(bp.data(), g->ph[0].bp.p, bp.size() * sizeof(ofdg_blueprint), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(st.data(), g->ph[0].seg_type.p, st.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(sx.data(), g->ph[0].seg_x.p, sx.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(sy.data(), g->ph[0].seg_y.p, sy.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(onbp.data(), g->ph[0].obj_nbp.p, onbp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(onseg.data(), g->ph[0].obj_nseg.p, onseg.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ntop.data(), g->ph[0].ntop.p, batch * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(smp.data(), g->ph[0].scene.samples.p, batch * sizeof(FlatSample), cudaMemcpyDeviceToHost));
     // compact the fixed-stride device arrays into an ordinary task batch
     TaskBatch& tb = out->tb;
     tb.clear();
     for (int s = 0; s < batch; ++s) {
-      const int bp0 = s * kPhiloxMaxBp, sg0 = s * kPhiloxMaxSeg;
-      const int new_bp0 = (int)tb.blueprints.size(), new_sg0 = (int)tb.seg_type.size();
-      for (int i = 0; i < nbp[s]; ++i) {
-        ofdg_blueprint b = bp[bp0 + i];
-        if (b.seg_count > 0) b.seg_begin = b.seg_begin - sg0 + new_sg0;
-        if (b.comp_count > 0) b.comp_begin = b.comp_begin - bp0 + new_bp0;
-        if (b.parent >= 0) b.parent = b.parent - bp0 + new_bp0;
-        tb.blueprints.push_back(b);
+      tb.blueprints.push_back(bp[(size_t)s * kPhiloxMaxBp]);  // background
+      for (int k = 0; k < ntop[s]; ++k) {
+        const int bp0 = s * kPhiloxMaxBp + 1 + k * kPhiloxMaxShapes, sg0 = s * kPhiloxMaxSeg + k * kPhiloxMaxShapes * 20;
+        const int new_bp0 = (int)tb.blueprints.size(), new_sg0 = (int)tb.seg_type.size();
+        for (int i = 0; i < onbp[(size_t)s * kPhiloxMaxObj + k]; ++i) {
+          ofdg_blueprint b = bp[bp0 + i];
+          if (b.seg_count > 0) b.seg_begin = b.seg_begin - sg0 + new_sg0;
+          if (b.comp_count > 0) b.comp_begin = b.comp_begin - bp0 + new_bp0;
+          if (b.parent >= 0) b.parent = b.parent - bp0 + new_bp0;
+          tb.blueprints.push_back(b);
+        }
+        for (int i = 0; i < onseg[(size_t)s * kPhiloxMaxObj + k]; ++i) { tb.seg_type.push_back(st[sg0 + i]); tb.seg_x.push_back(sx[sg0 + i]); tb.seg_y.push_back(sy[sg0 + i]); }
       }
-      for (int i = 0; i < nseg[s]; ++i) { tb.seg_type.push_back(st[sg0 + i]); tb.seg_x.push_back(sx[sg0 + i]); tb.seg_y.push_back(sy[sg0 + i]); }
       tb.task_begin.push_back((int32_t)tb.blueprints.size());
       if (augment) tb.augment.push_back(smp[s].aug);
     }

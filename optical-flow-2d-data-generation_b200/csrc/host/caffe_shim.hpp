@@ -63,6 +63,11 @@ struct DataGenerationParameter {
   int first_level_threads_ = 16;        // accepted, unused: the CPU worker pools are gone
   int second_level_threads_ = 1;
   bool use_antialiasing_ = true;
+  // extensions of this implementation (optional, default off => the reference's behaviour):
+  bool device_params_ = false;          // draw the scene parameters on the GPU (Philox production mode)
+  unsigned long long seed_ = 0;         // seed of the device-side stream
+  bool device_params() const { return device_params_; }
+  unsigned long long seed() const { return seed_; }
   int mode() const { return mode_; }
   const std::string& texture_dbases(int i) const { return texture_dbases_.at(i); }
   int texture_dbases_size() const { return (int)texture_dbases_.size(); }

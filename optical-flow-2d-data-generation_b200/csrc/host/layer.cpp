@@ -176,6 +176,8 @@ LayerParameter ParseLayerPrototxt(const std::string& text) {
         else if (f == "first_level_threads") g.first_level_threads_ = to_int(*fv, f);
         else if (f == "second_level_threads") g.second_level_threads_ = to_int(*fv, f);
         else if (f == "use_antialiasing") g.use_antialiasing_ = to_bool(*fv, f);
+        else if (f == "device_params") g.device_params_ = to_bool(*fv, f);
+        else if (f == "seed") g.seed_ = std::strtoull(fv->s.c_str(), nullptr, 10);
         else throw std::runtime_error("prototxt: unknown data_generation_param field '" + f + "'");
       });
     } else if (n == "include" || n == "exclude" || n == "phase") {
@@ -295,7 +297,7 @@ void DataGenerationLayer<Dtype>::LayerSetUp(const std::vector<Blob<Dtype>*>& bot
   if (!bottom.empty()) throw std::runtime_error("DataGeneration takes no bottom blobs");
   if (top.size() < 3) throw std::runtime_error("DataGeneration needs 3 top blobs (first image, second image, flow)");  // the reference indexes top[0..2]
   const int batch_size = this->layer_param_.data_param().batch_size();
-  StartInternalThread();
+  if (!this->layer_param_.data_generation_param().device_params()) StartInternalThread();  // the device stream needs no producer
   top[0]->Reshape({batch_size, 3, 384, 512});  // data_generation_layer.cpp:128-130
   top[1]->Reshape({batch_size, 3, 384, 512});
   top[2]->Reshape({batch_size, 2, 384, 512});
@@ -359,6 +361,20 @@ void DataGenerationLayer<Dtype>::InternalThreadEntry() {
 
 template <typename Dtype>
 void DataGenerationLayer<Dtype>::Forward_gpu(const std::vector<Blob<Dtype>*>& bottom, const std::vector<Blob<Dtype>*>& top) {
+  const DataGenerationParameter& gp = this->layer_param_.data_generation_param();
+  if (gp.device_params()) {
+    // production mode: parameters drawn and flattened on the device, straight into the top blobs
+    const int bs = this->layer_param_.data_param().batch_size();
+    top[0]->Reshape({bs, 3, 384, 512});
+    top[1]->Reshape({bs, 3, 384, 512});
+    top[2]->Reshape({bs, 2, 384, 512});
+    const unsigned long long seed = gp.seed() ^ ((unsigned long long)solver_rank_ << 40);  // distinct streams per replica
+    if (ofdg_generate_philox(generator_, seed, device_batches_ * (unsigned long long)bs, bs, 0, top[0]->mutable_gpu_data(),
+                             top[1]->mutable_gpu_data(), top[2]->mutable_gpu_data(), nullptr) != OFDG_OK)
+      throw std::runtime_error(ofdg_last_error());
+    ++device_batches_;
+    return;
+  }
   ofdg_prepared* p = nullptr;
   {
     std::unique_lock<std::mutex> l(mutex_);  // prefetch_full_.pop("Data layer prefetch queue empty")

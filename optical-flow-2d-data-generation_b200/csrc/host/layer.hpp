@@ -61,6 +61,7 @@ class DataGenerationLayer : public Layer<Dtype> {
   std::condition_variable cv_full_, cv_free_;
   std::thread thread_;
   bool must_stop_ = false;
+  unsigned long long device_batches_ = 0;  // batches produced by the device-side stream (its sample counter)
   std::string producer_error_;
 };
 

@@ -2,11 +2,11 @@
 // geometry flattened on the GPU, so that no host work is left on the path (the host-RNG
 // stream of host/params.cpp is the parity mode and stays the reference-comparable one).
 //
-//   philox_params_kernel    one thread per sample: ObjectParametersGenerator's logic
+//   philox_params_kernel    one thread per (sample, object): ObjectParametersGenerator's logic
 //                           (/root/reference/src/caffe/DataGenerator.cpp:2105-2835, same mode tables, same
 //                           branch structure) with every engine replaced by Philox keyed on
-//                           (seed, sample index, slot, draw number) -> blueprints in the ABI's POD layout
-//   philox_flatten_kernel   one thread per (sample, top-level object): host/flatten.cpp on the device
+//                           (seed, sample index, object, slot, draw number) -> blueprints in the ABI's POD layout
+//   philox_flatten_kernel   one thread per (sample, object, outline, frame): host/flatten.cpp on the device
 //
 // A sample is a pure function of (mode, seed, sample index): any GPU reproduces any sample. The streams
 // are statistically, not bitwise, equal to the host mode's (different engine, device libm).
@@ -24,14 +24,15 @@ __constant__ double c_circle_sin[100];
 
 // ---- Philox-backed engines ---------------------------------------------------------------------------
 struct Rng {
-  uint32_t k0, k1, s0, s1;
-  unsigned short ctr[kPhiloxSlots];
-  __device__ void init(uint64_t seed, uint64_t sample) {
+  uint32_t k0, k1, s0, s1, obj;
+  unsigned char ctr[kPhiloxSlots];
+  __device__ void init(uint64_t seed, uint64_t sample, int object) {
     k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); s0 = (uint32_t)sample; s1 = (uint32_t)(sample >> 32);
+    obj = (uint32_t)object << 8;
     for (int i = 0; i < kPhiloxSlots; ++i) ctr[i] = 0;
   }
   __device__ void raw(int slot, uint32_t& a, uint32_t& b) {
-    uint32_t x0 = s0, x1 = s1, x2 = (uint32_t)slot, x3 = ctr[slot]++;
+    uint32_t x0 = s0, x1 = s1, x2 = (uint32_t)slot | obj, x3 = ctr[slot]++;
     uint32_t ka = k0, kb = k1;
     for (int r = 0; r < 10; ++r) {
       const uint64_t p0 = (uint64_t)0xD2511F53u * x0, p1 = (uint64_t)0xCD9E8D57u * x2;
@@ -258,59 +259,60 @@ __device__ void gen_object(Gen& g, SampleOut& o, int idx, int n_fields, int& fie
 }
 
 __global__ void philox_params_kernel(PhiloxArgs a) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= a.batch) return;
+  const int s = blockIdx.x, k = threadIdx.x;  // sample, object (thread kPhiloxMaxObj: background and sample-level draws)
   Gen g;
   g.slots = a.slots;
   g.mode = a.mode;
-  g.rng.init(a.seed, a.first_sample + (uint64_t)s);
-  SampleOut o;
-  o.bp_base = s * kPhiloxMaxBp; o.seg_base = s * kPhiloxMaxSeg;
-  o.bp = a.bp + o.bp_base; o.seg_type = a.seg_type + o.seg_base; o.seg_x = a.seg_x + o.seg_base; o.seg_y = a.seg_y + o.seg_base;
-  o.nbp = 0; o.nseg = 0;
-  int field_draws = (int)((a.first_sample + (uint64_t)s) * 7 % 3000);  // decorrelates the field choice between samples
-  // generateBackground, DG.cpp:2105-2143
-  ofdg_blueprint bg = blank_bp();
-  bg.obj_id = 1;
-  bg.obj_type = OFDG_OBJ_POLYGON;
-  bg.rot = g.trigger(BgRotTrigger) ? g.real(BgRot) : 0.f;
-  bg.scale = g.trigger(BgScaleTrigger) ? g.real(BgScale) : 1.f;
-  const float ptx = g.real(BgTransX), pty = g.real(BgTransY);
-  bg.trans_x = cosf(-bg.rot) * ptx - sinf(-bg.rot) * pty;
-  bg.trans_y = sinf(-bg.rot) * ptx + cosf(-bg.rot) * pty;
-  bg.tex_id = g.integer(BgTexID);
-  bg.tex_rot = g.real(BgInitRot);
-  bg.tex_scale = g.real(BgInitScale);
-  bg.tex_shift_x = g.integer(BgInitTransX);
-  bg.tex_shift_y = g.integer(BgInitTransY);
-  bg.do_warpfield_deformation = g.trigger(ObjDeformsNonrigidly);
-  if (a.mode == 9 && bg.do_warpfield_deformation && a.n_fields > 0) bg.field_id = (field_draws++ / 3) % a.n_fields;
-  o.bp[o.nbp++] = bg;
+  // the number of objects is a sample-level draw every thread of the sample repeats
+  g.rng.init(a.seed, a.first_sample + (uint64_t)s, kPhiloxMaxObj);
   int fg = a.fg_override > 0 ? a.fg_override : (int)g.real(NumberOfFgObjects);
   if (fg > kPhiloxMaxObj) fg = kPhiloxMaxObj;
-  int* top = a.top_index + s * kPhiloxMaxObj;
-  for (int k = 0; k < fg; ++k) {
-    const int idx = o.nbp++;
-    o.bp[idx] = blank_bp();
-    o.bp[idx].obj_id = 10 + k;
-    top[k] = idx;
-    gen_object(g, o, idx, a.n_fields, field_draws);
+  int field_draws = 0;
+  if (k == kPhiloxMaxObj) {
+    // generateBackground, DG.cpp:2105-2143
+    ofdg_blueprint bg = blank_bp();
+    bg.obj_id = 1;
+    bg.obj_type = OFDG_OBJ_POLYGON;
+    bg.rot = g.trigger(BgRotTrigger) ? g.real(BgRot) : 0.f;
+    bg.scale = g.trigger(BgScaleTrigger) ? g.real(BgScale) : 1.f;
+    const float ptx = g.real(BgTransX), pty = g.real(BgTransY);
+    bg.trans_x = cosf(-bg.rot) * ptx - sinf(-bg.rot) * pty;
+    bg.trans_y = sinf(-bg.rot) * ptx + cosf(-bg.rot) * pty;
+    bg.tex_id = g.integer(BgTexID);
+    bg.tex_rot = g.real(BgInitRot);
+    bg.tex_scale = g.real(BgInitScale);
+    bg.tex_shift_x = g.integer(BgInitTransX);
+    bg.tex_shift_y = g.integer(BgInitTransY);
+    bg.do_warpfield_deformation = g.trigger(ObjDeformsNonrigidly);
+    a.bp[s * kPhiloxMaxBp] = bg;
+    a.n_top[s] = fg;
+    if (a.augment) {
+      ofdg_augment au;
+      au.enabled = 1;
+      for (int c = 0; c < 3; ++c) au.gain[c] = 0.8f + 0.4f * g.rng.unit(AugGain);
+      au.brightness = -20.f + 40.f * g.rng.unit(AugBrightness);
+      au.contrast = 0.7f + 0.6f * g.rng.unit(AugContrast);
+      au.noise_sigma = 10.f * g.rng.unit(AugSigma);
+      g.rng.raw(AugSeed, au.noise_seed[0], au.noise_seed[1]);
+      a.samples[s].aug = au;
+    } else {
+      a.samples[s].aug.enabled = 0;
+    }
+    return;
   }
-  a.n_top[s] = fg;
-  a.bp_count[s] = o.nbp;
-  a.seg_count[s] = o.nseg;
-  if (a.augment) {
-    ofdg_augment au;
-    au.enabled = 1;
-    for (int c = 0; c < 3; ++c) au.gain[c] = 0.8f + 0.4f * g.rng.unit(AugGain);
-    au.brightness = -20.f + 40.f * g.rng.unit(AugBrightness);
-    au.contrast = 0.7f + 0.6f * g.rng.unit(AugContrast);
-    au.noise_sigma = 10.f * g.rng.unit(AugSigma);
-    g.rng.raw(AugSeed, au.noise_seed[0], au.noise_seed[1]);
-    a.samples[s].aug = au;
-  } else {
-    a.samples[s].aug.enabled = 0;
-  }
+  if (k >= fg) { a.obj_nbp[s * kPhiloxMaxObj + k] = 0; a.obj_nseg[s * kPhiloxMaxObj + k] = 0; return; }
+  // generateForegroundObject for object k: its own engines, its own slice of the arrays
+  g.rng.init(a.seed, a.first_sample + (uint64_t)s, k);
+  SampleOut o;
+  o.bp_base = s * kPhiloxMaxBp + 1 + k * kPhiloxMaxShapes;
+  o.seg_base = s * kPhiloxMaxSeg + k * (kPhiloxMaxShapes * 20);
+  o.bp = a.bp + o.bp_base; o.seg_type = a.seg_type + o.seg_base; o.seg_x = a.seg_x + o.seg_base; o.seg_y = a.seg_y + o.seg_base;
+  o.nbp = 1; o.nseg = 0;
+  o.bp[0] = blank_bp();
+  o.bp[0].obj_id = 10 + k;
+  gen_object(g, o, 0, 0, field_draws);
+  a.obj_nbp[s * kPhiloxMaxObj + k] = o.nbp;
+  a.obj_nseg[s * kPhiloxMaxObj + k] = o.nseg;
 }
 
 // ---- device flatten (host/flatten.cpp restated for one thread per object) ------------------------------
@@ -443,13 +445,17 @@ __device__ void prepare_bg(const PhiloxArgs& a, const ofdg_blueprint& b, const A
   p.need[0] = nx0; p.need[1] = ny0; p.need[2] = nx1; p.need[3] = ny1;
 }
 
-__global__ void philox_flatten_kernel(PhiloxArgs a) {
-  const int s = blockIdx.x, k = threadIdx.x;  // sample, top-level object (thread kPhiloxMaxObj: the background)
+constexpr int kFlatObjPerBlock = 8, kFlatLanes = 2 * kPhiloxMaxShapes;  // 16 (outline, frame) threads per object
+
+__global__ void __launch_bounds__(kFlatObjPerBlock * kFlatLanes) philox_flatten_kernel(PhiloxArgs a) {
+  __shared__ int s_box[kFlatObjPerBlock][2][4];
+  const int s = blockIdx.x;
   const int W = a.W, H = a.H;
   const ofdg_blueprint* bp = a.bp;
   const ofdg_blueprint& bg = bp[s * kPhiloxMaxBp];
   const Affine bgM = motion_of(bg);
-  if (k == kPhiloxMaxObj) {
+  if (blockIdx.y == kPhiloxMaxObj / kFlatObjPerBlock) {  // the extra block row: background / FlatSample
+    if (threadIdx.x != 0) return;
     FlatSample smp = a.samples[s];  // keeps the augmentation record written by the parameter kernel
     Affine bgI;
     bgI.then(Affine::rotation(0.0));
@@ -460,66 +466,70 @@ __global__ void philox_flatten_kernel(PhiloxArgs a) {
     const Affine tex_inv = tex_tf.inverse();
     tex_inv.store(smp.bg_tex_inv);
     bgM.store(smp.bg_motion);
-    const bool deformed = false;  // see above: mode 9 is host-driven
-    smp.bg_field = -1;
-    prepare_bg(a, bg, tex_inv, deformed, smp.prep);
+    smp.bg_field = -1;  // warp fields (mode 9) are host-driven: the device stream rejects mode 9
+    prepare_bg(a, bg, tex_inv, false, smp.prep);
     smp.obj_begin = s * kPhiloxMaxObj;
     smp.obj_count = a.n_top[s];
     a.samples[s] = smp;
     return;
   }
-  if (k >= a.n_top[s]) return;
-  const ofdg_blueprint& b = bp[s * kPhiloxMaxBp + a.top_index[s * kPhiloxMaxObj + k]];
+  const int lo = threadIdx.x / kFlatLanes, sf = threadIdx.x % kFlatLanes, si = sf >> 1, f = sf & 1;
+  const int k = blockIdx.y * kFlatObjPerBlock + lo;
+  if (sf < 8) s_box[lo][sf >> 2][sf & 3] = (sf & 2) ? -0x7FFFFFFF : 0x7FFFFFFF;
+  __syncthreads();
+  const bool active = k < a.n_top[s];
+  const int obj_slot = s * kPhiloxMaxObj + k;
+  const ofdg_blueprint& b = bp[s * kPhiloxMaxBp + 1 + k * kPhiloxMaxShapes];
+  const bool composite = active && b.obj_type == OFDG_OBJ_COMPOSITE;
+  const int nshape = !active ? 0 : (composite ? b.comp_count : 1);
   Affine bg_n = Affine::translation(-W / 2., -H / 2.);
   bg_n.then(bgM);
   bg_n.then(Affine::translation(W / 2., H / 2.));
-  FlatObject o;
-  memset(&o, 0, sizeof(o));
-  o.obj_id = b.obj_id;
-  o.tex = (int)((unsigned)b.tex_id % (unsigned)a.n_tex);
-  o.field = -1;  // warp fields (mode 9) need the mask pre-pass bookkeeping of the host path: the device stream rejects mode 9
-  o.composite = b.obj_type == OFDG_OBJ_COMPOSITE;
-  const int obj_slot = s * kPhiloxMaxObj + k;
-  o.shape_begin = obj_slot * kPhiloxMaxShapes;
-  const int nshape = o.composite ? b.comp_count : 1;
-  o.shape_count = nshape;
-  FlatVertex* vbase = a.verts + (size_t)obj_slot * kPhiloxMaxVerts;
-  int vused = 0;
-  for (int f = 0; f < 2; ++f) { o.bbox[f][0] = o.bbox[f][1] = 0x7FFFFFFF; o.bbox[f][2] = o.bbox[f][3] = -0x7FFFFFFF; }
-  Affine M = motion_of(b);
-  M.then(bg_n);
-  for (int si = 0; si < nshape; ++si) {
-    const ofdg_blueprint& c = o.composite ? bp[b.comp_begin + si] : b;
-    Affine I;
-    I.then(Affine::rotation(c.init_rot));
-    I.then(Affine::translation(c.init_trans_x, c.init_trans_y));
-    Affine Mc = motion_of(c);
-    Mc.then(bg_n);
-    Affine IM = I;
-    IM.then(Mc);
-    FlatShape sh;
-    memset(&sh, 0, sizeof(sh));
-    sh.additive = c.is_additive_component ? 1 : 0;
-    sh.deform = -1;
-    for (int f = 0; f < 2; ++f) {
-      VertOut out;
-      out.begin(vbase + vused, max(0, kPhiloxMaxVerts - vused));
-      outline(a, c, f ? IM : I, out);
-      if (out.n > out.cap) out.n = 0;  // out of room: drop the outline rather than corrupt memory (never seen in practice)
-      sh.vbegin[f] = (int)(obj_slot * (size_t)kPhiloxMaxVerts + vused);
-      sh.vcount[f] = out.n;
-      vused += out.n;
-      if (out.n) { sh.bbox[f][0] = out.x0 >> 8; sh.bbox[f][1] = out.y0 >> 8; sh.bbox[f][2] = out.x1 >> 8; sh.bbox[f][3] = out.y1 >> 8; }
-      else { sh.bbox[f][0] = sh.bbox[f][1] = 0x7FFFFFF0; sh.bbox[f][2] = sh.bbox[f][3] = -0x7FFFFFF0; }
-      o.bbox[f][0] = min(o.bbox[f][0], sh.bbox[f][0]); o.bbox[f][1] = min(o.bbox[f][1], sh.bbox[f][1]);
-      o.bbox[f][2] = max(o.bbox[f][2], sh.bbox[f][2]); o.bbox[f][3] = max(o.bbox[f][3], sh.bbox[f][3]);
+  if (si < nshape) {
+    const ofdg_blueprint& c = composite ? bp[b.comp_begin + si] : b;
+    Affine T;
+    T.then(Affine::rotation(c.init_rot));
+    T.then(Affine::translation(c.init_trans_x, c.init_trans_y));
+    if (f) {
+      Affine Mc = motion_of(c);
+      Mc.then(bg_n);
+      T.then(Mc);
     }
-    for (int i = 0; i < 4; ++i) sh.raw1[i] = sh.bbox[1][i];
-    a.shapes[o.shape_begin + si] = sh;
+    VertOut out;
+    const int cap = kPhiloxMaxVerts / kFlatLanes;
+    const size_t vb = (size_t)obj_slot * kPhiloxMaxVerts + (size_t)sf * cap;
+    out.begin(a.verts + vb, cap);
+    outline(a, c, T, out);
+    if (out.n > out.cap) out.n = 0;  // out of room: drop the outline rather than corrupt memory (never seen in practice)
+    FlatShape& sh = a.shapes[obj_slot * kPhiloxMaxShapes + si];
+    sh.vbegin[f] = (int)vb;
+    sh.vcount[f] = out.n;
+    int bx[4] = {0x7FFFFFF0, 0x7FFFFFF0, -0x7FFFFFF0, -0x7FFFFFF0};
+    if (out.n) { bx[0] = out.x0 >> 8; bx[1] = out.y0 >> 8; bx[2] = out.x1 >> 8; bx[3] = out.y1 >> 8; }
+    for (int i = 0; i < 4; ++i) sh.bbox[f][i] = bx[i];
+    if (f) { for (int i = 0; i < 4; ++i) sh.raw1[i] = bx[i]; }
+    else { sh.additive = c.is_additive_component ? 1 : 0; sh.deform = -1; }
+    atomicMin(&s_box[lo][f][0], bx[0]); atomicMin(&s_box[lo][f][1], bx[1]);
+    atomicMax(&s_box[lo][f][2], bx[2]); atomicMax(&s_box[lo][f][3], bx[3]);
   }
-  M.store(o.motion);
-  M.inverse().store(o.tex_inv);
-  a.objects[obj_slot] = o;
+  __syncthreads();
+  if (active && sf == 0) {
+    FlatObject o;
+    memset(&o, 0, sizeof(o));
+    o.obj_id = b.obj_id;
+    o.tex = (int)((unsigned)b.tex_id % (unsigned)a.n_tex);
+    o.field = -1;
+    o.composite = composite;
+    o.shape_begin = obj_slot * kPhiloxMaxShapes;
+    o.shape_count = nshape;
+    for (int ff = 0; ff < 2; ++ff)
+      for (int i = 0; i < 4; ++i) o.bbox[ff][i] = s_box[lo][ff][i];
+    Affine M = motion_of(b);
+    M.then(bg_n);
+    M.store(o.motion);
+    M.inverse().store(o.tex_inv);
+    a.objects[obj_slot] = o;
+  }
 }
 
 }  // namespace
@@ -530,8 +540,8 @@ void philox_upload_circle(const double* c, const double* s) {
 }
 
 int launch_philox(const PhiloxArgs& a, cudaStream_t s) {
-  philox_params_kernel<<<(a.batch + 31) / 32, 32, 0, s>>>(a);
-  philox_flatten_kernel<<<a.batch, kPhiloxMaxObj + 1, 0, s>>>(a);
+  philox_params_kernel<<<a.batch, kPhiloxMaxObj + 1, 0, s>>>(a);
+  philox_flatten_kernel<<<dim3(a.batch, kPhiloxMaxObj / kFlatObjPerBlock + 1), kFlatObjPerBlock * kFlatLanes, 0, s>>>(a);
   return 2;
 }
 

@@ -10,10 +10,10 @@ namespace ofdg {
 
 constexpr int kPhiloxSlots = 50;        // the 45 engines of a data mode + 5 augmentation engines
 constexpr int kPhiloxMaxObj = 32;       // top-level foreground objects per sample
-constexpr int kPhiloxMaxBp = 1 + kPhiloxMaxObj * 8;   // background + objects + up to 7 components each
-constexpr int kPhiloxMaxSeg = kPhiloxMaxObj * 8 * 20; // polygon segments per sample
-constexpr int kPhiloxMaxShapes = 8;     // outlines per object
-constexpr int kPhiloxMaxVerts = 4096;   // fixed-point vertices per object (all outlines, both frames)
+constexpr int kPhiloxMaxShapes = 8;     // blueprints per object (itself + up to 7 components) = outlines per object
+constexpr int kPhiloxMaxBp = 1 + kPhiloxMaxObj * kPhiloxMaxShapes;    // background, then 8 slots per object
+constexpr int kPhiloxMaxSeg = kPhiloxMaxObj * kPhiloxMaxShapes * 20;  // polygon segments per sample, 160 per object
+constexpr int kPhiloxMaxVerts = 8192;   // fixed-point vertices per object: 512 per (outline, frame)
 
 struct PhiloxSlot {  // one row of a mode table, narrowed to float like the reference's constructors do
   int kind;          // ofdg::SlotKind
@@ -30,14 +30,13 @@ struct PhiloxArgs {
   int batch, n_fields, fg_override, augment;
   int n_tex, tex_w, tex_h;
   // blueprints in the ABI layout, fixed strides per sample (downloadable for inspection / the oracle)
-  ofdg_blueprint* bp;   // [batch][kPhiloxMaxBp]
-  int* bp_count;        // [batch]
-  int32_t* seg_type;    // [batch][kPhiloxMaxSeg]
+  ofdg_blueprint* bp;   // [batch][kPhiloxMaxBp]: background, then kPhiloxMaxShapes slots per object
+  int32_t* seg_type;    // [batch][kPhiloxMaxSeg]: 160 per object
   float* seg_x;
   float* seg_y;
-  int* seg_count;       // [batch]
-  int* top_index;       // [batch][kPhiloxMaxObj] blueprint index (within the sample) of the k-th object
-  int* n_top;           // [batch]
+  int* obj_nbp;         // [batch][kPhiloxMaxObj] blueprints / segments object k actually uses
+  int* obj_nseg;
+  int* n_top;           // [batch] foreground objects
   // flattened scene, fixed strides
   FlatSample* samples;  // [batch]
   FlatObject* objects;  // [batch][kPhiloxMaxObj]

@@ -72,3 +72,25 @@ def test_layer_ppm_texture_list(ofdg, oracle, tmp_path):
     ref = oracle.render(tasks.struct(), tex_rgb[:, ::-1].copy(), mode=5)  # planes held as B,G,R
     assert np.abs(got[0] - ref["img0"]).max() <= 1 and np.abs(got[1] - ref["img1"]).max() <= 1
     layer.close()
+
+
+@pytest.mark.gpu
+def test_layer_device_params_mode(ofdg):
+    """Extension: device_params: true -> Philox production mode through the same layer surface."""
+    proto = ('layer { type: "DataGeneration" top: "a" top: "b" top: "c" data_param { batch_size: 4 prefetch: 2 } '
+             'data_generation_param { mode: 7 texture_dbases: "synthetic:8:1" device_params: true seed: 42 } }')
+    layer = ofdg.DataGenerationLayer(proto)
+    layer.LayerSetUp()
+    layer.Forward_gpu()
+    a = [layer.top_cpu(i) for i in range(3)]
+    layer.Forward_gpu()
+    b = [layer.top_cpu(i) for i in range(3)]
+    assert a[0].shape == (4, 3, 384, 512) and a[2].shape == (4, 2, 384, 512)
+    assert a[0].std() > 10 and not np.array_equal(a[0], b[0])
+    layer.close()
+    # a second layer with the same seed replays the same batches
+    layer2 = ofdg.DataGenerationLayer(proto)
+    layer2.LayerSetUp()
+    layer2.Forward_gpu()
+    assert np.array_equal(layer2.top_cpu(0), a[0])
+    layer2.close()
