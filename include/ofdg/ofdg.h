@@ -108,6 +108,12 @@ int ofdg_download_texture(ofdg_generator* g, int32_t index, uint8_t* planar_out)
  * n x 2 x 2 x (height+1) x (width+1) float: [field][flow|iflow][channel][y][x]. */
 int ofdg_set_fields(ofdg_generator* g, const float* fields, int32_t n);
 
+/* WarpFields::CropGenerator (src/caffe/WarpFields.cpp:469-641) on the GPU: draws the random displacer scene
+ * with std::mt19937(seed) (the reference: std::random_device), builds the forward/inverse fields on the
+ * 3*max(W,H) canvas with 17 self-compositions each and installs n crops as the generator's pool
+ * (like ofdg_set_fields). fields_out, if not NULL, receives a host copy (same layout as ofdg_set_fields). */
+int ofdg_generate_fields(ofdg_generator* g, uint32_t seed, int32_t n, float* fields_out);
+
 /* Process_TaskBucket (DataGenerator.cpp:1175-1254) for a whole batch, writing straight into the
  * caller's DEVICE blobs: img0/img1 = batch x 3 x H x W, flow = batch x 2 x H x W, float32.
  * `stream` is a cudaStream_t (NULL = the generator's own stream; then the call synchronises). */

@@ -62,7 +62,7 @@ EXPORTS = [
     "ofdg_params_skip", "ofdg_params_enable_augmentation", "ofdg_params_tasks_generated", "ofdg_params_draws", "ofdg_params_slot_name",
     "ofdg_tasks_create", "ofdg_tasks_destroy", "ofdg_tasks_clear", "ofdg_tasks_view", "ofdg_tasks_assign",
     "ofdg_flatten_ellipse", "ofdg_flatten_polygon", "ofdg_debug_raster_host", "ofdg_create", "ofdg_destroy", "ofdg_upload_textures",
-    "ofdg_synth_textures", "ofdg_download_texture", "ofdg_set_fields", "ofdg_render", "ofdg_render_host",
+    "ofdg_synth_textures", "ofdg_download_texture", "ofdg_set_fields", "ofdg_generate_fields", "ofdg_render", "ofdg_render_host",
     "ofdg_render_debug", "ofdg_debug_background", "ofdg_debug_composite_luts", "ofdg_prepare", "ofdg_prepared_destroy",
     "ofdg_render_prepared", "ofdg_generate", "ofdg_generate_host", "ofdg_generate_philox", "ofdg_philox_tasks", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_upload_bytes",
 ]
@@ -112,6 +112,7 @@ def lib():
         L.ofdg_synth_textures.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64]
         L.ofdg_download_texture.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ofdg_set_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        L.ofdg_generate_fields.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p]
         L.ofdg_render.argtypes = [C.c_void_p, C.POINTER(TaskBatchStruct)] + [C.c_void_p] * 4
         L.ofdg_render_host.argtypes = [C.c_void_p, C.POINTER(TaskBatchStruct)] + [C.c_void_p] * 3
         L.ofdg_render_debug.argtypes = [C.c_void_p, C.POINTER(TaskBatchStruct)] + [C.c_void_p] * 4 + [C.c_int32] + [C.c_void_p] * 3
@@ -351,6 +352,12 @@ class Generator:
         fields = np.ascontiguousarray(fields, dtype=np.float32)
         assert fields.shape[1:] == (2, 2, self.H + 1, self.W + 1), fields.shape
         _check(lib().ofdg_set_fields(self._h, _ptr(fields), fields.shape[0]))
+
+    def generate_fields(self, seed, n):
+        """Mode-9 field pool produced on the GPU and installed; returns a host copy (n, 2, 2, H+1, W+1)."""
+        out = np.empty((n, 2, 2, self.H + 1, self.W + 1), np.float32)
+        _check(lib().ofdg_generate_fields(self._h, seed, n, _ptr(out)))
+        return out
 
     # -- rendering
     def render(self, tasks, img0, img1, flow, stream=None):

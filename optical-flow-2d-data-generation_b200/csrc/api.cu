@@ -16,6 +16,7 @@
 #include "raster_tile.h"
 #include "philox.cuh"
 #include "render.cuh"
+#include "warpfields.cuh"
 
 namespace {
 
@@ -581,6 +582,26 @@ int ofdg_set_fields(ofdg_generator* g, const float* fields, int32_t n) {
     CK(cudaMemcpy(g->fpos_y.p, py.data(), py.size() * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(g->falpha_y.p, ay.data(), ay.size() * sizeof(double), cudaMemcpyHostToDevice));
   });
+}
+
+int ofdg_generate_fields(ofdg_generator* g, uint32_t seed, int32_t n, float* fields_out) {
+  if (!g || n <= 0) { g_error = "bad arguments"; return OFDG_ERR_ARG; }
+  std::vector<float> host;
+  int rc = guarded([&] {
+    g->use();
+    const size_t per = (size_t)2 * 2 * (g->cfg.height + 1) * (g->cfg.width + 1);
+    DevBuf tmp;
+    tmp.reserve(per * n * sizeof(float));
+    g->launches += ofdg::wf_generate(g->cfg.width, g->cfg.height, seed, n, (float*)tmp.p, g->stream);
+    CK(cudaStreamSynchronize(g->stream));
+    CK(cudaGetLastError());
+    host.resize(per * n);
+    CK(cudaMemcpy(host.data(), tmp.p, per * n * sizeof(float), cudaMemcpyDeviceToHost));
+    tmp.release();
+    if (fields_out) std::memcpy(fields_out, host.data(), per * n * sizeof(float));
+  });
+  if (rc) return rc;
+  return ofdg_set_fields(g, host.data(), n);  // install as the generator's pool (reach table, resize tables)
 }
 
 int ofdg_render(ofdg_generator* g, const ofdg_task_batch* tasks, float* d_img0, float* d_img1, float* d_flow, void* stream) {

@@ -192,3 +192,27 @@ def test_augmentation_bit_exact(ofdg, oracle, textures8):
     assert np.abs(plain["img0"] - cpu["img0"]).mean() > 3      # colours are not
     assert i0.min() >= 0 and i0.max() <= 255
     g.close()
+
+
+def test_gpu_field_producer_matches_the_cpu_restatement(ofdg, oracle, textures8):
+    """WarpFields::CropGenerator on the GPU vs oracle/warpfields.cpp, same seed (differences: device expf only)."""
+    g = _gen(ofdg, 9)
+    g.upload_textures(textures8)
+    gpu = g.generate_fields(seed=1, n=6)
+    cpu = oracle.generate_fields(512, 384, seed=1, n_fields=6)
+    assert gpu.shape == cpu.shape == (6, 2, 2, 385, 513)
+    assert np.array_equal(np.isnan(gpu), np.isnan(cpu))
+    ok = np.isfinite(cpu)
+    assert np.abs(gpu[ok] - cpu[ok]).max() < 2e-3 and np.abs(cpu[ok]).max() > 10
+    # forward and inverse fields undo each other: x + flow(x) + iflow(x + flow(x)) ~= x
+    f, fi = gpu[0, 0], gpu[0, 1]
+    ys, xs = np.mgrid[100:300:7, 100:400:7]
+    tx, ty = xs + f[0, ys, xs], ys + f[1, ys, xs]
+    ix, iy = np.clip(np.round(tx).astype(int), 0, 512), np.clip(np.round(ty).astype(int), 0, 384)
+    assert np.abs(tx + fi[0, iy, ix] - xs).max() < 1.5 and np.abs(ty + fi[1, iy, ix] - ys).max() < 1.5
+    # the installed pool renders (parity of the consumer side is covered by test_mode9_nonrigid_parity)
+    tasks = ofdg.ParamStream(9, n_fields=6).generate(2)
+    out = g.render_debug(tasks)
+    ref = oracle.render(tasks.struct(), textures8, mode=9, fields=gpu, debug=True)
+    assert np.array_equal(out["masks"], ref["masks"]) and np.abs(out["frames8"].astype(int) - ref["frames8"].astype(int)).max() <= 1
+    g.close()
