@@ -24,8 +24,11 @@
 
 namespace ofdg {
 
-constexpr int TW = 128;  // tile width  = 32 lanes x 4 pixels
-constexpr int TH = 8;    // tile height = 8 warps
+#ifndef OFDG_TILE_ROWS
+#define OFDG_TILE_ROWS 8
+#endif
+constexpr int TW = 128;             // tile width  = 32 lanes x 4 pixels
+constexpr int TH = OFDG_TILE_ROWS;  // tile height = one warp per row
 
 template <bool kDevice>
 struct Acc;

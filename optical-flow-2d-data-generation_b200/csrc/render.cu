@@ -20,7 +20,10 @@ namespace ofdg {
 
 namespace {
 
-constexpr int RENDER_THREADS = 256;  // TH warps; lane = 4 consecutive pixels (one 128-bit store per lane and plane)
+constexpr int RENDER_THREADS = 32 * TH;  // TH warps; lane = 4 consecutive pixels (one 128-bit store per lane and plane)
+#ifndef OFDG_RENDER_MIN_BLOCKS
+#define OFDG_RENDER_MIN_BLOCKS 3
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // small integer helpers
@@ -295,7 +298,7 @@ __device__ __forceinline__ uint32_t comp4(uint32_t u, uint32_t v, bool additive,
 
 // kDeform = false compiles the mode-9 (warp field) branches out.
 template <bool kDeform>
-__global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a) {
+__global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render_kernel(RenderArgs a) {
   __shared__ int s_cover[NLAYER][TH][TW];
   __shared__ int s_area[NLAYER][TH][TW];
   __shared__ int s_carry[NLAYER][TH];
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 3) render_kernel(RenderArgs a)
   const uint8_t* bins = a.tile_hits + ((size_t)sample * gridDim.x + blockIdx.x) * TILE_HIT_STRIDE;
   const int binned = bins[0];  // objects touching this tile (255: more than a bin entry lists)
 
-  s_q255[tid] = (float)tid / 255.f;
+  for (int i = tid; i < 256; i += RENDER_THREADS) s_q255[i] = (float)i / 255.f;
 
   // ---- pass set-up, entirely inside warp 0 (the other warps fetch the background meanwhile):
   //      hit table -> outline jobs -> accumulator layers and chunk boundaries
