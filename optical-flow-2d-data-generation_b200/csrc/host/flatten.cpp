@@ -140,6 +140,8 @@ void prepare_background(const ofdg_blueprint& b, const FlattenConfig& cfg, const
   p.crop_y0 = std::min(y0, y1);
   p.crop_w = std::abs(x1 - x0) + 1;
   p.crop_h = std::abs(y1 - y0) + 1;
+  if (p.crop_w * 10 > tw * 13 || p.crop_h * 10 > th * 13 || p.crop_w < 2 || p.crop_h < 2)
+    throw std::runtime_error("background texture zoom outside the supported range (crop must stay within 1.3x of 2W x 2H)");
 
   // Part of the prepared texture the renderer touches: the centre W x H window (frame 0)
   // plus the footprint of the frame-1 warp (4 taps around tex_inv * pixel centre).

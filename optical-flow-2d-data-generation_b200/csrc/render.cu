@@ -860,30 +860,54 @@ __device__ __forceinline__ uint32_t rotated_px(const uchar4* tex, int w, int h, 
 
 // One resize pass (CImg get_resize interpolation 3; shrinking axes use the moving average)
 // evaluated at output index t from a line of source pixels src[(s - s0) * stride].
-__device__ __forceinline__ uint32_t resize_at(const uint32_t* src, int stride, int s0, int len, int n, int t,
-                                              const int* pos, const double* alpha) {
-  if (len == n) return src[(t - s0) * stride];
-  uint32_t out = 0;
-  if (len > n) {  // moving average over the exact rational overlap
+// One output index of a resize pass (CImg get_resize interpolation 3; shrinking axes use the moving average)
+// reduced to its taps, so that the index arithmetic is done once per column / row instead of once per pixel.
+struct ResizeTaps {
+  int first;      // first source index
+  int count;      // 0: copy, 1..3: moving-average taps, -1: linear (first, first + 1 with weight alpha)
+  float w[3];     // moving average: overlap lengths, in accumulation order
+  double alpha;
+};
+__device__ __forceinline__ ResizeTaps make_taps(int len, int n, int t, const int* pos, const double* alpha) {
+  ResizeTaps r;
+  r.alpha = 0.0; r.w[0] = r.w[1] = r.w[2] = 0.f;
+  if (len == n) { r.first = t; r.count = 0; }
+  else if (len > n) {  // moving average over the exact rational overlap (at most 3 sources: len <= 1.3 n, checked on the host)
     const unsigned lo = (unsigned)t * (unsigned)len, hi = lo + (unsigned)len;  // < 2^31 for any supported size
-    float acc[3] = {0.f, 0.f, 0.f};
-    for (unsigned s = lo / (unsigned)n; s * (unsigned)n < hi; ++s) {
-      const unsigned b = max(s * (unsigned)n, lo), e = min((s + 1u) * (unsigned)n, hi);
-      const float d = (float)(e - b);
-      const uint32_t p = src[((int)s - s0) * stride];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) acc[c] += byte_to_float(p, c) * d;
+    unsigned s = lo / (unsigned)n;
+    r.first = (int)s;
+    int k = 0;
+    for (; s * (unsigned)n < hi && k < 3; ++s, ++k) {
+      const unsigned b0 = max(s * (unsigned)n, lo), e0 = min((s + 1u) * (unsigned)n, hi);
+      r.w[k] = (float)(e0 - b0);
     }
+    r.count = k;
+  } else { r.first = pos[t]; r.alpha = alpha[t]; r.count = -1; }
+  return r;
+}
+__device__ __forceinline__ uint32_t apply_taps(const uint32_t* src, int stride, int s0, int len, const ResizeTaps& r) {
+  const uint32_t* p0 = src + (r.first - s0) * stride;
+  if (r.count == 0) return p0[0];
+  uint32_t out = 0;
+  if (r.count > 0) {
+    float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int c = 0; c < 3; ++c) out |= ((uint32_t)(unsigned char)(acc[c] / (float)(unsigned int)len)) << (8 * c);
+    for (int k = 0; k < 3; ++k) {
+      if (k < r.count) {
+        const uint32_t p = p0[k * stride];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] += byte_to_float(p, c) * r.w[k];
+      }
+    }
+    const float flen = (float)(unsigned int)len;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out |= ((uint32_t)(unsigned char)(acc[c] / flen)) << (8 * c);
     return out;
   }
-  const int q = pos[t];
-  const double al = alpha[t];
-  const uint32_t p1 = src[(q - s0) * stride], p2 = q < len - 1 ? src[(q + 1 - s0) * stride] : p1;
+  const uint32_t p1 = p0[0], p2 = r.first < len - 1 ? p0[stride] : p1;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const double v = (1 - al) * (double)(int)((p1 >> (8 * c)) & 255u) + al * (double)(int)((p2 >> (8 * c)) & 255u);
+    const double v = (1 - r.alpha) * (double)(int)((p1 >> (8 * c)) & 255u) + r.alpha * (double)(int)((p2 >> (8 * c)) & 255u);
     out |= ((uint32_t)(unsigned char)v) << (8 * c);
   }
   return out;
@@ -898,6 +922,7 @@ __device__ __forceinline__ void source_range(int len, int n, int t0, int t1, con
 __global__ void __launch_bounds__(PREP_THREADS) bg_prep_kernel(RenderArgs a) {
   __shared__ uint32_t sA[PS][PS];  // rotated + cropped source pixels
   __shared__ uint32_t sB[PS][PT];  // after the x pass
+  __shared__ ResizeTaps sTy[PT];   // taps of the tile's output rows
   const int sample = blockIdx.z;
   const BgPrep& p = a.samples[sample].prep;
   const int W2 = 2 * a.W, H2 = 2 * a.H;
@@ -913,6 +938,8 @@ __global__ void __launch_bounds__(PREP_THREADS) bg_prep_kernel(RenderArgs a) {
   source_range(p.crop_h, H2, Y0, Y1, pos_y, cy0, cy1);
   const int cw = cx1 - cx0 + 1, ch = cy1 - cy0 + 1;  // <= PS by construction
   const uchar4* tex = a.pool + (size_t)p.tex * a.tex_w * a.tex_h;
+  const int tw = X1 - X0 + 1, th = Y1 - Y0 + 1;
+  if ((int)threadIdx.x < th) sTy[threadIdx.x] = make_taps(p.crop_h, H2, Y0 + (int)threadIdx.x, pos_y, alpha_y);  // visible after the barriers below
   // A: crop(x0, y0, .., mirror) of the rotated image
   const int lane_x = threadIdx.x & 31, lane_y = threadIdx.x >> 5;
   {  // all lanes busy: walk the cw x ch source tile linearly, stepping (x, y) by 256 items without a divide per item
@@ -925,17 +952,17 @@ __global__ void __launch_bounds__(PREP_THREADS) bg_prep_kernel(RenderArgs a) {
     }
   }
   __syncthreads();
-  // B: resize along x
-  const int tw = X1 - X0 + 1, th = Y1 - Y0 + 1;
-  if (lane_x < tw)
-    for (int ly = lane_y; ly < ch; ly += PREP_THREADS / 32)
-      sB[ly][lane_x] = resize_at(&sA[ly][0], 1, cx0, p.crop_w, W2, X0 + lane_x, pos_x, alpha_x);
+  // B: resize along x (one column per lane: its taps are computed once)
+  if (lane_x < tw) {
+    const ResizeTaps tx = make_taps(p.crop_w, W2, X0 + lane_x, pos_x, alpha_x);
+    for (int ly = lane_y; ly < ch; ly += PREP_THREADS / 32) sB[ly][lane_x] = apply_taps(&sA[ly][0], 1, cx0, p.crop_w, tx);
+  }
   __syncthreads();
   // P: resize along y
   uchar4* out = a.bg + (size_t)sample * W2 * H2;
   if (lane_x < tw)
     for (int ly = lane_y; ly < th; ly += PREP_THREADS / 32) {
-      const uint32_t v = resize_at(&sB[0][lane_x], PT, cy0, p.crop_h, H2, Y0 + ly, pos_y, alpha_y);
+      const uint32_t v = apply_taps(&sB[0][lane_x], PT, cy0, p.crop_h, sTy[ly]);
       *reinterpret_cast<uint32_t*>(out + (size_t)(Y0 + ly) * W2 + X0 + lane_x) = v;
     }
 }
