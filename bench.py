@@ -182,14 +182,21 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None
-    for i in range(args.warmup):
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    t_load = time.time()
+    # keep the GPU under the same load for at least ~0.5 s before timing, so that the clock samples
+    # (nvidia-smi polls every 100 ms) describe the timed region even when --steps is small
+    i = 0
+    while i < args.warmup or time.time() - t_load < 0.5:
         g.render_prepared(prepared[i % n_sets], img0, img1, flow, stream)
+        i += 1
+        if i % 50 == 0:
+            torch.cuda.synchronize()
     barrier()
     g.kernel_times()
     launches0 = g.launch_count()
-    if sampler:
-        sampler.start()
-        time.sleep(0.3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_start = time.time()
@@ -200,7 +207,7 @@ def run_ours(args):
     barrier()
     t_end = time.time()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop(t_start, t_end) if sampler else None
+    clocks = sampler.stop(t_load, t_end) if sampler else None
     launches = g.launch_count() - launches0
     prep_ms, render_ms, calls = g.kernel_times()
     if dist is not None:
