@@ -156,7 +156,9 @@ struct ofdg_generator {
   PinnedBuf pipe_staging[2];
   ofdg::FlatBatch pipe_flat[2];
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t pipe_uploaded[2] = {nullptr, nullptr}, pipe_rendered[2] = {nullptr, nullptr};
+  cudaEvent_t pipe_uploaded[2] = {nullptr, nullptr}, pipe_rendered[2] = {nullptr, nullptr}, render_done[2] = {nullptr, nullptr};
+  bool render_set_used[2] = {false, false};
+  uint64_t render_calls = 0;
   uint64_t launches = 0;
   float last_kernel_ms = 0.f;
 
@@ -451,6 +453,7 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
     for (int i = 0; i < 2; ++i) {
       CK(cudaEventCreateWithFlags(&g->pipe_uploaded[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&g->pipe_rendered[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&g->render_done[i], cudaEventDisableTiming));
     }
     *out = g.release();
   });
@@ -479,6 +482,7 @@ void ofdg_destroy(ofdg_generator* g) {
     g->pipe_staging[i].release();
     if (g->pipe_uploaded[i]) cudaEventDestroy(g->pipe_uploaded[i]);
     if (g->pipe_rendered[i]) cudaEventDestroy(g->pipe_rendered[i]);
+    if (g->render_done[i]) cudaEventDestroy(g->render_done[i]);
   }
   if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
   for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
@@ -610,12 +614,16 @@ int ofdg_render(ofdg_generator* g, const ofdg_task_batch* tasks, float* d_img0, 
     check_batch(g, tasks->n_tasks);
     g->use();
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
-    flatten_tasks(g, tasks);
+    // two scene/staging sets alternate, so that with a caller-provided stream the host flattening of the
+    // next call overlaps the kernels of this one; a set is reused only after its last render finished
+    const int set = (int)(g->render_calls++ & 1);
+    if (g->render_set_used[set]) CK(cudaEventSynchronize(g->render_done[set]));
+    flatten_tasks(g, tasks, &g->pipe_flat[set]);
     ensure_scratch(g, tasks->n_tasks);
-    // the pinned staging area is reused by the next call: wait for the previous upload
-    CK(cudaStreamSynchronize(s));
-    upload_scene(g, g->flat, g->scene, g->staging, s);
-    run_kernels(g, make_args(g, g->scene, d_img0, d_img1, d_flow), s);
+    upload_scene(g, g->pipe_flat[set], g->pipe_scene[set], g->pipe_staging[set], s);
+    run_kernels(g, make_args(g, g->pipe_scene[set], d_img0, d_img1, d_flow), s);
+    CK(cudaEventRecord(g->render_done[set], s));
+    g->render_set_used[set] = true;
     if (!stream) CK(cudaStreamSynchronize(s));
   });
 }
@@ -629,6 +637,8 @@ static void render_host_pipelined(ofdg_generator* g, ofdg_params* params, const 
   const int nchunk = n >= 32 ? 4 : (n >= 8 ? 2 : 1);
   ensure_scratch(g, (n + nchunk - 1) / nchunk);
   cudaStream_t A = g->stream, B = g->copy_stream;
+  for (int i = 0; i < 2; ++i)  // asynchronous ofdg_render calls share the two scene sets
+    if (g->render_set_used[i]) CK(cudaEventSynchronize(g->render_done[i]));
   size_t uploaded = 0;
   for (int k = 0; k < nchunk; ++k) {
     const int t0 = (int)((long long)n * k / nchunk), t1 = (int)((long long)n * (k + 1) / nchunk), set = k & 1;
