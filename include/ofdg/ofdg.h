@@ -89,6 +89,9 @@ int32_t ofdg_flatten_polygon(const int32_t* seg_type, const float* seg_x, const 
  * (aa != 0: gamma_none, else gamma_threshold(0.5)). Lets the CPU test-suite check the closed-form
  * cell arithmetic against the oracle's sequential AGG port without a GPU. */
 int ofdg_debug_raster_host(const int32_t* xy, int32_t n, int32_t W, int32_t H, int32_t aa, uint8_t* mask);
+/* Test hook (no GPU needed): the host routine that widens byte planes into float blobs for the
+ * host-blob entry points, dst[i] = (float)src[i]; `streaming` selects non-temporal stores. */
+int ofdg_debug_expand_host(const uint8_t* src, float* dst, uint64_t n, int32_t streaming);
 
 /* ---- generator ------------------------------------------------------------------------------------ */
 int ofdg_create(const ofdg_config* cfg, ofdg_generator** out);   /* DataGenerator ctor + Start(), DataGenerator.cpp:990-1030 */
@@ -171,6 +174,14 @@ uint64_t ofdg_launch_count(const ofdg_generator* g);
 int ofdg_kernel_times(ofdg_generator* g, double* prep_ms, double* render_ms, int32_t* calls);
 /* Bytes of flattened scene data the last render/prepare call copied host-to-device. */
 uint64_t ofdg_last_upload_bytes(const ofdg_generator* g);
+/* Bytes the last ofdg_render_host / ofdg_generate_host call copied device-to-host. The frames cross
+ * PCIe as bytes and are widened into the float blobs by host threads unless a sample carries the
+ * float augmentation. Environment knobs, read when the generator is created / first used:
+ *   OFDG_TRANSPORT=f32     float blobs cross PCIe as they are (no host widening)
+ *   OFDG_HOST_THREADS=N    worker threads of the host stages (default: half the cores, at most 16)
+ *   OFDG_HOST_CHUNKS=N     pipeline chunks per call (default: 4 samples per chunk, at most 16 chunks)
+ *   OFDG_TRACE_HOST=1      stage timestamps of every host-blob call on stderr */
+uint64_t ofdg_last_download_bytes(const ofdg_generator* g);
 
 #ifdef __cplusplus
 }

@@ -61,10 +61,10 @@ EXPORTS = [
     "ofdg_last_error", "ofdg_version", "ofdg_params_create", "ofdg_params_destroy", "ofdg_params_generate",
     "ofdg_params_skip", "ofdg_params_enable_augmentation", "ofdg_params_tasks_generated", "ofdg_params_draws", "ofdg_params_slot_name",
     "ofdg_tasks_create", "ofdg_tasks_destroy", "ofdg_tasks_clear", "ofdg_tasks_view", "ofdg_tasks_assign",
-    "ofdg_flatten_ellipse", "ofdg_flatten_polygon", "ofdg_debug_raster_host", "ofdg_create", "ofdg_destroy", "ofdg_upload_textures",
+    "ofdg_flatten_ellipse", "ofdg_flatten_polygon", "ofdg_debug_raster_host", "ofdg_debug_expand_host", "ofdg_create", "ofdg_destroy", "ofdg_upload_textures",
     "ofdg_synth_textures", "ofdg_download_texture", "ofdg_set_fields", "ofdg_generate_fields", "ofdg_render", "ofdg_render_host",
     "ofdg_render_debug", "ofdg_debug_background", "ofdg_debug_composite_luts", "ofdg_prepare", "ofdg_prepared_destroy",
-    "ofdg_render_prepared", "ofdg_generate", "ofdg_generate_host", "ofdg_generate_philox", "ofdg_philox_tasks", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_upload_bytes",
+    "ofdg_render_prepared", "ofdg_generate", "ofdg_generate_host", "ofdg_generate_philox", "ofdg_philox_tasks", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_upload_bytes", "ofdg_last_download_bytes",
 ]
 # include/ofdg/layer.h
 LAYER_EXPORTS = [
@@ -92,6 +92,8 @@ def lib():
         L.ofdg_launch_count.argtypes = [C.c_void_p]
         L.ofdg_last_upload_bytes.restype = C.c_uint64
         L.ofdg_last_upload_bytes.argtypes = [C.c_void_p]
+        L.ofdg_last_download_bytes.restype = C.c_uint64
+        L.ofdg_last_download_bytes.argtypes = [C.c_void_p]
         L.ofdg_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         L.ofdg_params_create.argtypes = [C.c_int32] * 6 + [C.POINTER(C.c_void_p)]
         L.ofdg_params_destroy.argtypes = [C.c_void_p]
@@ -106,6 +108,7 @@ def lib():
         L.ofdg_flatten_ellipse.argtypes = [C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int32]
         L.ofdg_flatten_polygon.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
         L.ofdg_debug_raster_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        L.ofdg_debug_expand_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int32]
         L.ofdg_create.argtypes = [C.POINTER(ConfigStruct), C.POINTER(C.c_void_p)]
         L.ofdg_destroy.argtypes = [C.c_void_p]
         L.ofdg_upload_textures.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
@@ -310,6 +313,14 @@ def raster_host(xy, W, H, aa=True):
     return mask
 
 
+def expand_host(src, dst, streaming=True):
+    """The host routine of the uint8 transport (csrc/host/expand.cpp): dst[i] = float(src[i]), in place into `dst`."""
+    assert src.dtype == np.uint8 and dst.dtype == np.float32 and src.size == dst.size
+    assert src.flags["C_CONTIGUOUS"] and dst.flags["C_CONTIGUOUS"]
+    _check(lib().ofdg_debug_expand_host(_ptr(src), _ptr(dst), src.size, int(streaming)))
+    return dst
+
+
 class Generator:
     """Device-side generator (DataGenerator::DataGenerator, DataGenerator.h:449-500): owns the HBM texture pool
     and renders task batches into caller-provided device blobs."""
@@ -442,6 +453,10 @@ class Generator:
 
     def last_upload_bytes(self):
         return int(lib().ofdg_last_upload_bytes(self._h))
+
+    def last_download_bytes(self):
+        """Bytes the last render_host / generate_host call copied device-to-host (uint8 frames + float flow by default)."""
+        return int(lib().ofdg_last_download_bytes(self._h))
 
 
 class Prepared:

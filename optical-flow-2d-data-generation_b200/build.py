@@ -15,9 +15,9 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libofdg.so")
 
-SOURCES = ["api.cu", "render.cu", "philox.cu", "warpfields.cu", "host/params.cpp", "host/flatten.cpp", "host/layer.cpp"]
+SOURCES = ["api.cu", "render.cu", "philox.cu", "warpfields.cu", "host/params.cpp", "host/flatten.cpp", "host/layer.cpp", "host/expand.cpp"]
 HEADERS = ["render.cuh", "philox.cuh", "warpfields.cuh", "raster_tile.h", "flat_scene.h", "host/params.hpp", "host/flatten.hpp", "host/affine.hpp",
-           "host/mode_tables.inc", "host/layer.hpp", "host/caffe_shim.hpp"]
+           "host/mode_tables.inc", "host/layer.hpp", "host/caffe_shim.hpp", "host/expand.hpp"]
 
 
 def _nvcc():

@@ -4,12 +4,19 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <thread>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
+#include "host/expand.hpp"
 #include "host/flatten.hpp"
 #include "host/params.hpp"
 #include "ofdg/ofdg.h"
@@ -74,20 +81,24 @@ struct DevBuf {
     cap = 0;
   }
 };
-struct PinnedBuf {
+struct PinnedBuf {  // pinned and mapped: kernels can read it through `dev`
   void* p = nullptr;
+  void* dev = nullptr;
   size_t cap = 0;
   void reserve(size_t bytes) {
     if (bytes <= cap) return;
     if (p) CK(cudaFreeHost(p));
     p = nullptr;
+    dev = nullptr;
     cap = 0;
-    CK(cudaMallocHost(&p, bytes));
+    CK(cudaHostAlloc(&p, bytes, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer(&dev, p, 0));
     cap = bytes;
   }
   void release() {
     if (p) cudaFreeHost(p);
     p = nullptr;
+    dev = nullptr;
     cap = 0;
   }
 };
@@ -121,7 +132,7 @@ struct ofdg_generator {
   size_t ev_next = 0;
   std::vector<Span> spans;
   uint64_t timed_calls = 0;
-  size_t last_upload_bytes = 0;
+  size_t last_upload_bytes = 0, last_download_bytes = 0;
   int scratch_batch = 0;
   // device-side (Philox) parameter stream
   // (two sets: while batch k renders, batch k+1 is drawn and flattened on a side stream)
@@ -148,6 +159,23 @@ struct ofdg_generator {
   PinnedBuf staging;
   DevBuf bg, tile_hits;
   DevBuf out0, out1, outf;  // device blobs for the *_host entry points
+  // uint8 transport of the host-blob path: byte frames on the device, their pinned landing area, the
+  // host threads that widen them into the caller's float blobs (host/expand.hpp), one event per chunk
+  static constexpr int kMaxChunks = 32;
+  DevBuf out8;
+  PinnedBuf host8;
+  std::unique_ptr<ofdg::HostPool> workers;
+  cudaEvent_t chunk_copied[kMaxChunks] = {};
+  // host stages of the pipeline: per-chunk task batches (parameter-stream flavour), one flattened part per sample
+  ofdg::TaskBatch chunk_tasks[kMaxChunks];
+  std::vector<ofdg::FlatBatch> sample_flat;
+  struct {
+    std::mutex mu;
+    std::condition_variable cv;
+    int done[kMaxChunks];
+    std::string error;
+  } host_sync;
+  bool transport_u8 = true;
   DevBuf dbg_masks, dbg_id0, dbg_id1, dbg_frames8, dbg_planar;
   ofdg::FlatBatch flat;
   ofdg::TaskBatch gen_tasks;
@@ -173,44 +201,83 @@ void check_batch(const ofdg_generator* g, int n) {
   if (g->n_tex <= 0) throw StateError("no textures uploaded (ofdg_upload_textures / ofdg_synth_textures)");
 }
 
-void upload_scene(ofdg_generator* g, const ofdg::FlatBatch& fb, DeviceScene& ds, PinnedBuf& staging, cudaStream_t s) {
-  const size_t b0 = fb.samples.size() * sizeof(ofdg::FlatSample), b1 = fb.objects.size() * sizeof(ofdg::FlatObject),
-               b2 = fb.shapes.size() * sizeof(ofdg::FlatShape), b3 = fb.verts.size() * sizeof(ofdg::FlatVertex);
-  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  staging.reserve(al(b0) + al(b1) + al(b2) + al(b3) + 256);
-  char* st = (char*)staging.p;
-  size_t o0 = 0, o1 = al(b0), o2 = o1 + al(b1), o3 = o2 + al(b2);
-  std::memcpy(st + o0, fb.samples.data(), b0);
-  std::memcpy(st + o1, fb.objects.data(), b1);
-  std::memcpy(st + o2, fb.shapes.data(), b2);
-  std::memcpy(st + o3, fb.verts.data(), b3);
-  ds.samples.reserve(b0 + 256); ds.objects.reserve(b1 + 256); ds.shapes.reserve(b2 + 256); ds.verts.reserve(b3 + 256);
-  CK(cudaMemcpyAsync(ds.samples.p, st + o0, b0, cudaMemcpyHostToDevice, s));
-  if (b1) CK(cudaMemcpyAsync(ds.objects.p, st + o1, b1, cudaMemcpyHostToDevice, s));
-  if (b2) CK(cudaMemcpyAsync(ds.shapes.p, st + o2, b2, cudaMemcpyHostToDevice, s));
-  if (b3) CK(cudaMemcpyAsync(ds.verts.p, st + o3, b3, cudaMemcpyHostToDevice, s));
-  ds.batch = (int)fb.samples.size();
-  ds.n_deform = (int)fb.deform_shape.size();
-  if (ds.n_deform) {  // mode 9 only; small, pageable copies are fine here
-    const size_t bd = (size_t)ds.n_deform * sizeof(int32_t);
-    ds.deform_shape.reserve(bd); ds.deform_field.reserve(bd);
-    CK(cudaMemcpyAsync(ds.deform_shape.p, fb.deform_shape.data(), bd, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ds.deform_field.p, fb.deform_field.data(), bd, cudaMemcpyHostToDevice, s));
-    CK(cudaStreamSynchronize(s));
+// Concatenates flattened parts (each with indices relative to itself) into the pinned staging area, rebasing
+// the indices, and starts the host-to-device copies on stream s.
+void upload_scene_parts(ofdg_generator* g, const ofdg::FlatBatch* parts, int n_parts, DeviceScene& ds, PinnedBuf& staging, cudaStream_t s) {
+  size_t ns = 0, no = 0, nsh = 0, nv = 0, nd = 0;
+  for (int i = 0; i < n_parts; ++i) {
+    ns += parts[i].samples.size(); no += parts[i].objects.size(); nsh += parts[i].shapes.size();
+    nv += parts[i].verts.size(); nd += parts[i].deform_shape.size();
   }
-  g->last_upload_bytes = b0 + b1 + b2 + b3 + 2 * (size_t)ds.n_deform * sizeof(int32_t);
+  const size_t b0 = ns * sizeof(ofdg::FlatSample), b1 = no * sizeof(ofdg::FlatObject), b2 = nsh * sizeof(ofdg::FlatShape),
+               b3 = nv * sizeof(ofdg::FlatVertex), bd = nd * sizeof(int32_t);
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o0 = 0, o1 = al(b0), o2 = o1 + al(b1), o3 = o2 + al(b2), o4 = o3 + al(b3), o5 = o4 + al(bd);
+  staging.reserve(o5 + al(bd) + 256);
+  char* st = (char*)staging.p;
+  ofdg::FlatSample* S = (ofdg::FlatSample*)(st + o0);
+  ofdg::FlatObject* O = (ofdg::FlatObject*)(st + o1);
+  ofdg::FlatShape* Sh = (ofdg::FlatShape*)(st + o2);
+  ofdg::FlatVertex* V = (ofdg::FlatVertex*)(st + o3);
+  int32_t* Ds = (int32_t*)(st + o4);
+  int32_t* Df = (int32_t*)(st + o5);
+  size_t is = 0, io = 0, ish = 0, iv = 0, id = 0;
+  for (int i = 0; i < n_parts; ++i) {
+    const ofdg::FlatBatch& fb = parts[i];
+    if (!fb.samples.empty()) std::memcpy(S + is, fb.samples.data(), fb.samples.size() * sizeof(ofdg::FlatSample));
+    if (!fb.objects.empty()) std::memcpy(O + io, fb.objects.data(), fb.objects.size() * sizeof(ofdg::FlatObject));
+    if (!fb.shapes.empty()) std::memcpy(Sh + ish, fb.shapes.data(), fb.shapes.size() * sizeof(ofdg::FlatShape));
+    if (!fb.verts.empty()) std::memcpy(V + iv, fb.verts.data(), fb.verts.size() * sizeof(ofdg::FlatVertex));
+    if (i > 0) {
+      for (size_t k = 0; k < fb.samples.size(); ++k) S[is + k].obj_begin += (int32_t)io;
+      for (size_t k = 0; k < fb.objects.size(); ++k) O[io + k].shape_begin += (int32_t)ish;
+      for (size_t k = 0; k < fb.shapes.size(); ++k) {
+        ofdg::FlatShape& sh = Sh[ish + k];
+        sh.vbegin[0] += (int32_t)iv; sh.vbegin[1] += (int32_t)iv;
+        if (sh.deform >= 0) sh.deform += (int32_t)id;
+      }
+    }
+    for (size_t k = 0; k < fb.deform_shape.size(); ++k) {
+      Ds[id + k] = fb.deform_shape[k] + (int32_t)ish;
+      Df[id + k] = fb.deform_field[k];
+    }
+    is += fb.samples.size(); io += fb.objects.size(); ish += fb.shapes.size(); iv += fb.verts.size(); id += fb.deform_shape.size();
+  }
+  ds.samples.reserve(b0 + 256); ds.objects.reserve(b1 + 256); ds.shapes.reserve(b2 + 256); ds.verts.reserve(b3 + 256);
+  if (nd) { ds.deform_shape.reserve(bd + 256); ds.deform_field.reserve(bd + 256); }  // mode 9 only
+  ds.batch = (int)ns;
+  ds.n_deform = (int)nd;
+  ofdg::UploadSegments u{};
+  const char* dv = (const char*)staging.dev;
+  auto seg = [&u, dv](void* dst, size_t off, size_t bytes) {
+    if (!bytes) return;
+    u.src[u.n] = dv + off; u.dst[u.n] = dst; u.n16[u.n] = (unsigned)((bytes + 15) / 16);
+    ++u.n;
+  };
+  seg(ds.samples.p, o0, b0); seg(ds.objects.p, o1, b1); seg(ds.shapes.p, o2, b2); seg(ds.verts.p, o3, b3);
+  if (nd) { seg(ds.deform_shape.p, o4, bd); seg(ds.deform_field.p, o5, bd); }
+  g->launches += ofdg::launch_scene_upload(u, s);
+  g->last_upload_bytes = b0 + b1 + b2 + b3 + 2 * bd;
 }
 
-void flatten_tasks(ofdg_generator* g, const ofdg_task_batch* tasks, ofdg::FlatBatch* into = nullptr) {
-  ofdg::FlatBatch& flat = into ? *into : g->flat;
+void upload_scene(ofdg_generator* g, const ofdg::FlatBatch& fb, DeviceScene& ds, PinnedBuf& staging, cudaStream_t s) {
+  upload_scene_parts(g, &fb, 1, ds, staging, s);
+}
+
+ofdg::FlattenConfig flatten_config(const ofdg_generator* g) {
   ofdg::FlattenConfig fc;
   fc.W = g->cfg.width; fc.H = g->cfg.height;
   fc.tex_w = g->tex_w; fc.tex_h = g->tex_h; fc.n_tex = g->n_tex;
   fc.mode = g->cfg.mode;
   fc.n_fields = g->n_fields;
   fc.field_reach = g->field_reach.empty() ? nullptr : g->field_reach.data();
+  return fc;
+}
+
+void flatten_tasks(ofdg_generator* g, const ofdg_task_batch* tasks, ofdg::FlatBatch* into = nullptr) {
+  ofdg::FlatBatch& flat = into ? *into : g->flat;
   flat.clear();
-  ofdg::flatten(*tasks, fc, flat);
+  ofdg::flatten(*tasks, flatten_config(g), flat);
 }
 
 void ensure_scratch(ofdg_generator* g, int batch) {
@@ -277,7 +344,7 @@ void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s) {
   g->launches += ofdg::launch_background_prep(a, s);
   CK(cudaEventRecord(sp.b, s));
   g->spans.push_back(sp);
-  if (a.img0) {
+  if (a.flow) {
     ofdg_generator::Span sr{timing_event(g), timing_event(g), 1};
     CK(cudaEventRecord(sr.a, s));
     g->launches += ofdg::launch_render(a, s);
@@ -415,6 +482,13 @@ int ofdg_debug_raster_host(const int32_t* xy, int32_t n, int32_t W, int32_t H, i
   });
 }
 
+int ofdg_debug_expand_host(const uint8_t* src, float* dst, uint64_t n, int32_t streaming) {
+  return guarded([&] {
+    if ((!src || !dst) && n) throw ArgError("null pointer");
+    ofdg::expand_u8_to_f32(src, dst, (size_t)n, streaming != 0);
+  });
+}
+
 // ---- generator ---------------------------------------------------------------------------------------
 int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
   return guarded([&] {
@@ -455,6 +529,8 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
       CK(cudaEventCreateWithFlags(&g->pipe_rendered[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&g->render_done[i], cudaEventDisableTiming));
     }
+    for (cudaEvent_t& e2 : g->chunk_copied) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming | cudaEventBlockingSync));
+    if (const char* t = std::getenv("OFDG_TRANSPORT")) g->transport_u8 = std::string(t) != "f32";  // "f32": float blobs cross PCIe as they are
     *out = g.release();
   });
 }
@@ -484,6 +560,10 @@ void ofdg_destroy(ofdg_generator* g) {
     if (g->pipe_rendered[i]) cudaEventDestroy(g->pipe_rendered[i]);
     if (g->render_done[i]) cudaEventDestroy(g->render_done[i]);
   }
+  g->workers.reset();
+  for (cudaEvent_t e2 : g->chunk_copied) if (e2) cudaEventDestroy(e2);
+  g->out8.release();
+  g->host8.release();
   if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
   for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
   if (g->stream) cudaStreamDestroy(g->stream);
@@ -628,50 +708,163 @@ int ofdg_render(ofdg_generator* g, const ofdg_task_batch* tasks, float* d_img0, 
   });
 }
 
-// Host-blob rendering, pipelined in up to 4 chunks: while chunk k's blobs travel device->host on
-// the copy stream, chunk k+1 is drawn/flattened on the host and rendered on the compute stream.
+// Host-blob rendering, pipelined in chunks over five stages that all overlap:
+//   draw the parameters (one pool job, sequential: the engines are streams) -> flatten (one pool job per sample)
+//   -> [this thread] upload + background preparation + render on the compute stream -> device-to-host copies on
+//   the copy stream -> widen the byte frames into the caller's float blobs (pool jobs).
+// Unless a sample carries this repository's float augmentation, the frames cross PCIe as bytes (2.3x fewer bytes
+// per sample than three float blobs) and host threads widen them -- what the reference does on the host as the
+// last step of Process_TaskBucket (/root/reference/src/caffe/DataGenerator.cpp:1228-1244). The flow blob is
+// float all the way.
 static void render_host_pipelined(ofdg_generator* g, ofdg_params* params, const ofdg_task_batch* tasks, int n,
                                   float* h_img0, float* h_img1, float* h_flow) {
   const size_t P = (size_t)g->cfg.width * g->cfg.height;
-  g->out0.reserve((size_t)n * 3 * P * sizeof(float)); g->out1.reserve((size_t)n * 3 * P * sizeof(float)); g->outf.reserve((size_t)n * 2 * P * sizeof(float));
-  const int nchunk = n >= 32 ? 4 : (n >= 8 ? 2 : 1);
+  bool bytes = g->transport_u8;
+  if (params && params->ps->augmentation_enabled()) bytes = false;
+  if (tasks && tasks->augment)
+    for (int i = 0; i < n && bytes; ++i) bytes = tasks->augment[i].enabled == 0;
+  // 4 samples per chunk: short chunks keep the pipeline's fill and drain short (measured: profiles/README.md)
+  int nchunk = std::max(1, std::min(n / 4, 16));
+  if (const char* t = std::getenv("OFDG_HOST_CHUNKS")) nchunk = std::max(1, std::min(std::min(std::atoi(t), n), (int)ofdg_generator::kMaxChunks));
+  if (bytes) {
+    g->out8.reserve((size_t)n * 6 * P);
+    g->host8.reserve((size_t)n * 6 * P);
+  } else {
+    g->out0.reserve((size_t)n * 3 * P * sizeof(float)); g->out1.reserve((size_t)n * 3 * P * sizeof(float));
+  }
+  g->outf.reserve((size_t)n * 2 * P * sizeof(float));
+  if (!g->workers) {
+    // widening is bound by host memory bandwidth, not by cores: more threads than this only slow the DMA down
+    int threads = std::min((int)std::thread::hardware_concurrency() / 2, 16);
+    if (const char* t = std::getenv("OFDG_HOST_THREADS")) threads = std::atoi(t);
+    g->workers.reset(new ofdg::HostPool(std::max(2, std::min(threads, 64)), g->cfg.device));
+  }
   ensure_scratch(g, (n + nchunk - 1) / nchunk);
   cudaStream_t A = g->stream, B = g->copy_stream;
   for (int i = 0; i < 2; ++i)  // asynchronous ofdg_render calls share the two scene sets
     if (g->render_set_used[i]) CK(cudaEventSynchronize(g->render_done[i]));
+
+  // ---- host stages: draw + flatten, running ahead of this thread
+  static const bool trace = std::getenv("OFDG_TRACE_HOST") != nullptr;  // stage timestamps of every call on stderr
+  const auto T0 = std::chrono::steady_clock::now();
+  auto now_ms = [T0] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count(); };
+  double t_ready[ofdg_generator::kMaxChunks] = {}, t_issued[ofdg_generator::kMaxChunks] = {};
+  auto& sync = g->host_sync;
+  for (int k = 0; k < nchunk; ++k) sync.done[k] = 0;
+  sync.error.clear();
+  if ((int)g->sample_flat.size() < n) g->sample_flat.resize(n);
+  const ofdg::FlattenConfig fc = flatten_config(g);
+  auto chunk_of = [n, nchunk](int k) { return (int)((long long)n * k / nchunk); };
+  auto fail = [g](const std::string& what) {
+    std::lock_guard<std::mutex> lk(g->host_sync.mu);
+    if (g->host_sync.error.empty()) g->host_sync.error = what.empty() ? std::string("host stage failed") : what;
+    g->host_sync.cv.notify_all();
+  };
+  auto submit_flatten = [g, fc, fail](ofdg_task_batch one, int sample, int chunk) {  // `one` views exactly one task
+    g->workers->submit([g, fc, fail, one, sample, chunk] {
+      try {
+        g->sample_flat[sample].clear();
+        ofdg::flatten(one, fc, g->sample_flat[sample]);
+      } catch (const std::exception& e) {
+        fail(e.what());
+      }
+      std::lock_guard<std::mutex> lk(g->host_sync.mu);
+      ++g->host_sync.done[chunk];
+      g->host_sync.cv.notify_all();
+    }, true);
+  };
+  auto one_task = [](const ofdg_task_batch& all, int i) {
+    ofdg_task_batch v = all;
+    v.n_tasks = 1;
+    v.task_begin = all.task_begin + i;  // blueprint indices stay absolute
+    if (v.augment) v.augment += i;
+    return v;
+  };
+  if (params) {
+    ofdg::ParamStream* ps = params->ps.get();
+    g->workers->submit([g, ps, nchunk, chunk_of, submit_flatten, one_task, fail] {
+      try {
+        for (int k = 0; k < nchunk; ++k) {
+          ofdg::TaskBatch& tb = g->chunk_tasks[k];
+          tb.clear();
+          const int t0 = chunk_of(k), t1 = chunk_of(k + 1);
+          for (int i = t0; i < t1; ++i) ps->next_task(tb);
+          const ofdg_task_batch all = tb.view();
+          for (int i = t0; i < t1; ++i) submit_flatten(one_task(all, i - t0), i, k);
+        }
+      } catch (const std::exception& e) {
+        fail(e.what());
+      }
+    }, true);
+  } else {
+    for (int k = 0; k < nchunk; ++k)
+      for (int i = chunk_of(k); i < chunk_of(k + 1); ++i) submit_flatten(one_task(*tasks, i), i, k);
+  }
+
   size_t uploaded = 0;
-  for (int k = 0; k < nchunk; ++k) {
-    const int t0 = (int)((long long)n * k / nchunk), t1 = (int)((long long)n * (k + 1) / nchunk), set = k & 1;
-    if (k >= 2) CK(cudaEventSynchronize(g->pipe_uploaded[set]));  // the pinned staging area of this set is free again
-    ofdg_task_batch view;
-    if (params) {
-      g->gen_tasks.clear();
-      for (int i = t0; i < t1; ++i) params->ps->next_task(g->gen_tasks);
-      view = g->gen_tasks.view();
-    } else {
-      view = *tasks;
-      view.n_tasks = t1 - t0;
-      view.task_begin = tasks->task_begin + t0;  // blueprint indices stay absolute
-      if (view.augment) view.augment += t0;
+  try {
+    for (int k = 0; k < nchunk; ++k) {
+      const int t0 = chunk_of(k), t1 = chunk_of(k + 1), set = k & 1;
+      {
+        std::unique_lock<std::mutex> lk(sync.mu);
+        sync.cv.wait(lk, [&] { return sync.done[k] == t1 - t0 || !sync.error.empty(); });
+        if (!sync.error.empty()) throw ArgError(sync.error);
+      }
+      t_ready[k] = now_ms();
+      if (k >= 2) CK(cudaEventSynchronize(g->pipe_uploaded[set]));  // the pinned staging area of this set is free again
+      upload_scene_parts(g, g->sample_flat.data() + t0, t1 - t0, g->pipe_scene[set], g->pipe_staging[set], A);
+      uploaded += g->last_upload_bytes;
+      CK(cudaEventRecord(g->pipe_uploaded[set], A));
+      float* d0 = bytes ? nullptr : (float*)g->out0.p + (size_t)t0 * 3 * P;
+      float* d1 = bytes ? nullptr : (float*)g->out1.p + (size_t)t0 * 3 * P;
+      float* df = (float*)g->outf.p + (size_t)t0 * 2 * P;
+      ofdg::RenderArgs a = make_args(g, g->pipe_scene[set], d0, d1, df);
+      if (bytes) a.frames8 = (uint8_t*)g->out8.p + (size_t)t0 * 6 * P;
+      run_kernels(g, a, A);
+      CK(cudaEventRecord(g->pipe_rendered[set], A));
+      CK(cudaStreamWaitEvent(B, g->pipe_rendered[set], 0));
+      const size_t c = (size_t)(t1 - t0);
+      if (bytes) {
+        uint8_t* h8 = (uint8_t*)g->host8.p + (size_t)t0 * 6 * P;
+        CK(cudaMemcpyAsync(h8, a.frames8, c * 6 * P, cudaMemcpyDeviceToHost, B));
+        CK(cudaEventRecord(g->chunk_copied[k], B));
+        CK(cudaMemcpyAsync(h_flow + (size_t)t0 * 2 * P, df, c * 2 * P * sizeof(float), cudaMemcpyDeviceToHost, B));
+        std::vector<std::function<void()>> widen;
+        widen.reserve(c * 6);
+        for (size_t i = 0; i < c; ++i)      // sample t0+i: planes 0-2 are frame 0, planes 3-5 frame 1; one job per plane
+          for (int pl = 0; pl < 6; ++pl) {
+            float* dst = (pl < 3 ? h_img0 : h_img1) + ((size_t)t0 + i) * 3 * P + (size_t)(pl % 3) * P;
+            widen.push_back(g->workers->expand_job(h8 + (i * 6 + pl) * P, dst, P));
+          }
+        g->workers->submit_after(g->chunk_copied[k], std::move(widen));
+      } else {
+        CK(cudaMemcpyAsync(h_img0 + (size_t)t0 * 3 * P, d0, c * 3 * P * sizeof(float), cudaMemcpyDeviceToHost, B));
+        CK(cudaMemcpyAsync(h_img1 + (size_t)t0 * 3 * P, d1, c * 3 * P * sizeof(float), cudaMemcpyDeviceToHost, B));
+        CK(cudaMemcpyAsync(h_flow + (size_t)t0 * 2 * P, df, c * 2 * P * sizeof(float), cudaMemcpyDeviceToHost, B));
+      }
+      t_issued[k] = now_ms();
     }
-    flatten_tasks(g, &view, &g->pipe_flat[set]);
-    upload_scene(g, g->pipe_flat[set], g->pipe_scene[set], g->pipe_staging[set], A);
-    uploaded += g->last_upload_bytes;
-    CK(cudaEventRecord(g->pipe_uploaded[set], A));
-    float* d0 = (float*)g->out0.p + (size_t)t0 * 3 * P;
-    float* d1 = (float*)g->out1.p + (size_t)t0 * 3 * P;
-    float* df = (float*)g->outf.p + (size_t)t0 * 2 * P;
-    run_kernels(g, make_args(g, g->pipe_scene[set], d0, d1, df), A);
-    CK(cudaEventRecord(g->pipe_rendered[set], A));
-    CK(cudaStreamWaitEvent(B, g->pipe_rendered[set], 0));
-    const size_t c = (size_t)(t1 - t0);
-    CK(cudaMemcpyAsync(h_img0 + (size_t)t0 * 3 * P, d0, c * 3 * P * sizeof(float), cudaMemcpyDeviceToHost, B));
-    CK(cudaMemcpyAsync(h_img1 + (size_t)t0 * 3 * P, d1, c * 3 * P * sizeof(float), cudaMemcpyDeviceToHost, B));
-    CK(cudaMemcpyAsync(h_flow + (size_t)t0 * 2 * P, df, c * 2 * P * sizeof(float), cudaMemcpyDeviceToHost, B));
+  } catch (...) {
+    // nothing of this call may still be running (drawing, flattening or writing into the caller's blobs) once it returns
+    try { g->workers->wait(); } catch (...) {}
+    cudaStreamSynchronize(B);
+    cudaStreamSynchronize(A);
+    throw;
   }
   CK(cudaStreamSynchronize(B));
   CK(cudaStreamSynchronize(A));
+  const double t_copied = now_ms();
+  g->workers->wait();
+  if (trace) {
+    std::string line = "[ofdg host pipeline] scenes ready / chunk issued (ms):";
+    char buf[64];
+    for (int k = 0; k < nchunk; ++k) { std::snprintf(buf, sizeof buf, " %.2f/%.2f", t_ready[k], t_issued[k]); line += buf; }
+    std::snprintf(buf, sizeof buf, "; copies done %.2f; widened %.2f\n", t_copied, now_ms());
+    line += buf;
+    std::fputs(line.c_str(), stderr);
+  }
   g->last_upload_bytes = uploaded;
+  g->last_download_bytes = bytes ? (size_t)n * (6 * P + 2 * P * sizeof(float)) : (size_t)n * 8 * P * sizeof(float);
 }
 
 int ofdg_render_host(ofdg_generator* g, const ofdg_task_batch* tasks, float* h_img0, float* h_img1, float* h_flow) {
@@ -718,7 +911,7 @@ int ofdg_render_debug(ofdg_generator* g, const ofdg_task_batch* tasks, float* h_
     }
     if (frames8) {
       g->dbg_frames8.reserve(n * 6 * P);
-      a.dbg_frames8 = (uint8_t*)g->dbg_frames8.p;
+      a.frames8 = (uint8_t*)g->dbg_frames8.p;
     }
     run_kernels(g, a, s);
     if (h_img0) CK(cudaMemcpyAsync(h_img0, g->out0.p, n * 3 * P * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -727,7 +920,7 @@ int ofdg_render_debug(ofdg_generator* g, const ofdg_task_batch* tasks, float* h_
     if (a.dbg_masks) CK(cudaMemcpyAsync(masks, a.dbg_masks, n * max_objs * 4 * P, cudaMemcpyDeviceToHost, s));
     if (id0) CK(cudaMemcpyAsync(id0, a.dbg_id0, n * P * 4, cudaMemcpyDeviceToHost, s));
     if (id1) CK(cudaMemcpyAsync(id1, a.dbg_id1, n * P * 4, cudaMemcpyDeviceToHost, s));
-    if (frames8) CK(cudaMemcpyAsync(frames8, a.dbg_frames8, n * 6 * P, cudaMemcpyDeviceToHost, s));
+    if (frames8) CK(cudaMemcpyAsync(frames8, a.frames8, n * 6 * P, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
   });
 }
@@ -981,5 +1174,6 @@ int ofdg_kernel_times(ofdg_generator* g, double* prep_ms, double* render_ms, int
   });
 }
 uint64_t ofdg_last_upload_bytes(const ofdg_generator* g) { return g ? g->last_upload_bytes : 0; }
+uint64_t ofdg_last_download_bytes(const ofdg_generator* g) { return g ? g->last_download_bytes : 0; }
 
 }  // extern "C"

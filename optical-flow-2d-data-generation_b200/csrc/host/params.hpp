@@ -90,6 +90,7 @@ class ParamStream {
   // Colour/noise augmentation (this repository's own spec, include/ofdg/scene.h): five extra engines seeded
   // seed_offset + 45..49, so the reference's 45 streams are untouched. Off by default.
   void enable_augmentation(bool on) { augment_ = on; }
+  bool augmentation_enabled() const { return augment_; }
   uint64_t tasks_generated() const { return tasks_; }
   uint64_t draws(int slot) const { return eng_[slot].draws; }
   int mode() const { return mode_; }

@@ -682,23 +682,25 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
 
   // ---- write the three blobs (NCHW float): 8 planes x one 128-bit store per lane
   const size_t pix = (size_t)y * W + x0;
-  float* o0 = a.img0 + (size_t)sample * 3 * P + pix;
-  float* o1 = a.img1 + (size_t)sample * 3 * P + pix;
   float* of = a.flow + (size_t)sample * 2 * P + pix;
-  const bool augment = smp.aug.enabled != 0;  // this repository's own colour/noise augmentation (ofdg/augment.h); never set by the reference path
+  if (a.img0) {
+    float* o0 = a.img0 + (size_t)sample * 3 * P + pix;
+    float* o1 = a.img1 + (size_t)sample * 3 * P + pix;
+    const bool augment = smp.aug.enabled != 0;  // this repository's own colour/noise augmentation (ofdg/augment.h); never set by the reference path
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float4 v0 = make_float4(byte_to_float(col0[0], c), byte_to_float(col0[1], c), byte_to_float(col0[2], c), byte_to_float(col0[3], c));
-    float4 v1 = make_float4(byte_to_float(col1[0], c), byte_to_float(col1[1], c), byte_to_float(col1[2], c), byte_to_float(col1[3], c));
-    if (augment) {
-      const uint32_t p = (uint32_t)pix;
-      v0.x = ofdg_augment_value(&smp.aug, v0.x, c, 0, p); v0.y = ofdg_augment_value(&smp.aug, v0.y, c, 0, p + 1);
-      v0.z = ofdg_augment_value(&smp.aug, v0.z, c, 0, p + 2); v0.w = ofdg_augment_value(&smp.aug, v0.w, c, 0, p + 3);
-      v1.x = ofdg_augment_value(&smp.aug, v1.x, c, 1, p); v1.y = ofdg_augment_value(&smp.aug, v1.y, c, 1, p + 1);
-      v1.z = ofdg_augment_value(&smp.aug, v1.z, c, 1, p + 2); v1.w = ofdg_augment_value(&smp.aug, v1.w, c, 1, p + 3);
+    for (int c = 0; c < 3; ++c) {
+      float4 v0 = make_float4(byte_to_float(col0[0], c), byte_to_float(col0[1], c), byte_to_float(col0[2], c), byte_to_float(col0[3], c));
+      float4 v1 = make_float4(byte_to_float(col1[0], c), byte_to_float(col1[1], c), byte_to_float(col1[2], c), byte_to_float(col1[3], c));
+      if (augment) {
+        const uint32_t p = (uint32_t)pix;
+        v0.x = ofdg_augment_value(&smp.aug, v0.x, c, 0, p); v0.y = ofdg_augment_value(&smp.aug, v0.y, c, 0, p + 1);
+        v0.z = ofdg_augment_value(&smp.aug, v0.z, c, 0, p + 2); v0.w = ofdg_augment_value(&smp.aug, v0.w, c, 0, p + 3);
+        v1.x = ofdg_augment_value(&smp.aug, v1.x, c, 1, p); v1.y = ofdg_augment_value(&smp.aug, v1.y, c, 1, p + 1);
+        v1.z = ofdg_augment_value(&smp.aug, v1.z, c, 1, p + 2); v1.w = ofdg_augment_value(&smp.aug, v1.w, c, 1, p + 3);
+      }
+      __stcs(reinterpret_cast<float4*>(o0 + c * P), v0);
+      __stcs(reinterpret_cast<float4*>(o1 + c * P), v1);
     }
-    __stcs(reinterpret_cast<float4*>(o0 + c * P), v0);
-    __stcs(reinterpret_cast<float4*>(o1 + c * P), v1);
   }
   __stcs(reinterpret_cast<float4*>(of), make_float4(fxv[0], fxv[1], fxv[2], fxv[3]));
   __stcs(reinterpret_cast<float4*>(of + P), make_float4(fyv[0], fyv[1], fyv[2], fyv[3]));
@@ -713,15 +715,16 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
       if (a.dbg_id1) a.dbg_id1[(size_t)sample * P + pix + i] = o1id;
     }
   }
-  if (a.dbg_frames8) {
-    uint8_t* fb = a.dbg_frames8 + (size_t)sample * 6 * P + pix;
+  if (a.frames8) {  // byte planes: channel c of the lane's four pixels is one 32-bit store
+    uint8_t* fb = a.frames8 + (size_t)sample * 6 * P + pix;
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        fb[c * P + i] = (uint8_t)((col0[i] >> (8 * c)) & 255u);
-        fb[(3 + c) * P + i] = (uint8_t)((col1[i] >> (8 * c)) & 255u);
-      }
+    for (int c = 0; c < 3; ++c) {
+      const unsigned sel = 0x40u + (unsigned)c * 0x11u;  // byte c of the first operand, byte c of the second
+      const uint32_t w0 = __byte_perm(__byte_perm(col0[0], col0[1], sel), __byte_perm(col0[2], col0[3], sel), 0x5410u);
+      const uint32_t w1 = __byte_perm(__byte_perm(col1[0], col1[1], sel), __byte_perm(col1[2], col1[3], sel), 0x5410u);
+      __stcs(reinterpret_cast<uint32_t*>(fb + c * P), w0);
+      __stcs(reinterpret_cast<uint32_t*>(fb + (3 + c) * P), w1);
+    }
   }
 }
 
@@ -1035,6 +1038,21 @@ __global__ void composite_lut_kernel(uint8_t* add_lut, uint8_t* sub_lut) {
 }
 
 }  // namespace
+
+namespace {
+__global__ void scene_upload_kernel(UploadSegments u) {
+  const int seg = blockIdx.y;
+  const uint4* src = static_cast<const uint4*>(u.src[seg]);
+  uint4* dst = static_cast<uint4*>(u.dst[seg]);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < u.n16[seg]; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+}  // namespace
+
+int launch_scene_upload(const UploadSegments& u, cudaStream_t s) {
+  if (u.n <= 0) return 0;
+  scene_upload_kernel<<<dim3(24, u.n), 256, 0, s>>>(u);
+  return 1;
+}
 
 void launch_composite_luts(uint8_t* add_lut, uint8_t* sub_lut, cudaStream_t s) {
   composite_lut_kernel<<<256, 256, 0, s>>>(add_lut, sub_lut);

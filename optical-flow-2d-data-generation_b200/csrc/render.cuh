@@ -49,7 +49,7 @@ struct RenderArgs {
   int dbg_max_objs;
   uint32_t* dbg_id0;    // [batch][H][W]
   uint32_t* dbg_id1;
-  uint8_t* dbg_frames8; // [batch][2][3][H][W]
+  uint8_t* frames8;     // [batch][2][3][H][W] the frames as bytes: uint8 transport of the host-blob path (img0/img1 may then be null) and parity checks
 };
 
 constexpr int TILE_HIT_STRIDE = 32;  // 1 count byte + up to 31 object indices per tile
@@ -62,6 +62,17 @@ int launch_render(const RenderArgs& a, cudaStream_t s);
 int launch_deform_prepass(const RenderArgs& a, cudaStream_t s);  // mode 9 only; no-op when n_deform == 0
 
 void launch_resize_tables(int* pos, double* alpha, int n, cudaStream_t s);  // one-time, all lengths 1..n-1 -> n
+// Scene upload without the copy engines: one kernel pulls the flattened arrays out of mapped pinned host memory.
+// (In the host-blob pipeline the copy engine is busy with large device-to-host copies; a small host-to-device
+// memcpy queued behind one of them stalls the compute stream for the length of that copy.)
+struct UploadSegments {
+  static constexpr int kMax = 6;
+  const void* src[kMax];  // device-visible address of the pinned source, 16-byte aligned
+  void* dst[kMax];        // 16-byte aligned, capacity rounded up to 16 bytes
+  unsigned n16[kMax];     // length in 16-byte units
+  int n;
+};
+int launch_scene_upload(const UploadSegments& u, cudaStream_t s);
 void launch_planar_to_rgbx(const uint8_t* planar, uchar4* out, int n, int w, int h, cudaStream_t s);
 void launch_rgbx_to_planar(const uchar4* in, uint8_t* planar, int w, int h, cudaStream_t s);
 void launch_synth_textures(uchar4* out, int n, int w, int h, uint64_t seed, int first_index, cudaStream_t s);

@@ -52,3 +52,19 @@ def test_product_never_imports_the_oracle():
                 assert not bad.search(text), f"{f} references the oracle"
     root_shim = open(os.path.join(ROOT, "ofdg_b200.py")).read()
     assert not bad.search(root_shim)
+
+
+def test_host_expand_routine_matches_numpy(ofdg):
+    """The host half of the uint8 transport (csrc/host/expand.cpp) for every head/tail alignment."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    src_all = rng.integers(0, 256, 5000, dtype=np.uint8)
+    dst_all = np.empty(5000 + 64, np.float32)
+    for streaming in (True, False):
+        for off in range(0, 17):
+            for n in (0, 1, 7, 15, 16, 17, 63, 64, 65, 1000, 4099):
+                dst_all[:] = -1
+                dst = dst_all[off:off + n]
+                ofdg.expand_host(src_all[3:3 + n], dst, streaming)
+                assert np.array_equal(dst, src_all[3:3 + n].astype(np.float32))
+                assert np.all(dst_all[:off] == -1) and np.all(dst_all[off + n:] == -1)

@@ -216,3 +216,53 @@ def test_gpu_field_producer_matches_the_cpu_restatement(ofdg, oracle, textures8)
     ref = oracle.render(tasks.struct(), textures8, mode=9, fields=gpu, debug=True)
     assert np.array_equal(out["masks"], ref["masks"]) and np.abs(out["frames8"].astype(int) - ref["frames8"].astype(int)).max() <= 1
     g.close()
+
+
+@pytest.mark.parametrize("n", [1, 5, 17, 64])
+def test_host_blobs_uint8_transport_equals_float_transport(ofdg, textures8, n, monkeypatch):
+    """The host-blob entry points move the frames over PCIe as bytes and widen them on the host; the float
+    blobs they deliver must be bit-identical to the plain float transfer, for every chunking of the batch and for
+    blobs that are not cache-line aligned."""
+    tasks = ofdg.ParamStream(7).generate(n)
+    monkeypatch.setenv("OFDG_TRANSPORT", "f32")
+    gf = _gen(ofdg, 7, max_batch=64)
+    monkeypatch.delenv("OFDG_TRANSPORT")
+    gb = _gen(ofdg, 7, max_batch=64)
+    P = 384 * 512
+    outs = []
+    for g in (gf, gb):
+        g.upload_textures(textures8)
+        raw = [np.full(n * c * P + 3, -7.0, np.float32) for c in (3, 3, 2)]
+        views = [r[3:].reshape(n, c, 384, 512) for r, c in zip(raw, (3, 3, 2))]   # 12 bytes off any 64-byte boundary
+        g.render_host(tasks, *views)
+        assert all(np.all(r[:3] == -7.0) for r in raw)
+        outs.append(views)
+    assert gf.last_download_bytes() == n * 8 * P * 4
+    assert gb.last_download_bytes() == n * (6 * P + 2 * P * 4)
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    # the parameter-stream flavour goes through the same pipeline
+    h = [np.empty((n, c, 384, 512), np.float32) for c in (3, 3, 2)]
+    gb.generate_host(ofdg.ParamStream(7), n, *h)
+    for a, b in zip(outs[1], h):
+        assert np.array_equal(a, b)
+    gf.close(); gb.close()
+
+
+def test_host_pipeline_reports_a_bad_task_and_recovers(ofdg, textures8):
+    """A descriptor the reference would reject (DataGenerator.cpp:1143) inside a later chunk: the call fails with the
+    flattening error, nothing keeps running behind it, and the generator stays usable."""
+    g = _gen(ofdg, 7, max_batch=64)
+    g.upload_textures(textures8)
+    good = ofdg.ParamStream(7).generate(20)
+    arrs = good.arrays()
+    first_fg = arrs["task_begin"][13] + 1
+    arrs["blueprints"]["obj_type"][first_fg] = 77
+    bad = ofdg.Tasks.from_arrays(arrs)
+    with pytest.raises(ofdg.OfdgError, match="Bad object type"):
+        g.render_host(bad)
+    a = g.render_host(good)
+    b = g.render_host(good)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    g.close()
