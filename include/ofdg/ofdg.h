@@ -166,6 +166,26 @@ int ofdg_generate_philox(ofdg_generator* g, uint64_t seed, uint64_t first_sample
  * (inspection, and rendering the very same scenes through the host path / the oracle). */
 int ofdg_philox_tasks(ofdg_generator* g, uint64_t seed, uint64_t first_sample, int32_t batch, int32_t augment, ofdg_tasks* out);
 
+/* Extra tops: the outputs RenderCore holds besides frames and forward flow
+ * (index_image0/1, flow1 = computeFlowImage(objects, true), DataGenerator.cpp:740-818), plus an occlusion
+ * mask derived from them. All are DEVICE float blobs for `max_batch` samples; any pointer may be NULL.
+ *   flow_bw    [N][2][H][W]  flow of frame 1's pixels back to frame 0: the inverse motion of the object
+ *                            index_image1 names (background: I^-1, M^-1, I), the forward field added in
+ *                            mode 9 exactly as getPointFlow(inverse = true) does
+ *   id0, id1   [N][1][H][W]  index images as float: 1 = background, 10 + k = k-th foreground object
+ *   occlusion  [N][1][H][W]  1.0 where frame 0's pixel p is not visible in frame 1, else 0.0. Not in the
+ *                            reference; defined here: t = p + flow(p) in float, q = floor(t + 0.5); p is
+ *                            occluded when t is NaN, q lies outside the frame, or id1(q) != id0(p).
+ * Sticky: applies to every later device-blob call (ofdg_render, ofdg_render_prepared, ofdg_generate,
+ * ofdg_generate_philox) until called again; pass NULL to switch the extra tops off. */
+typedef struct ofdg_extra_tops {
+  float* flow_bw;
+  float* id0;
+  float* id1;
+  float* occlusion;
+} ofdg_extra_tops;
+int ofdg_set_extra_tops(ofdg_generator* g, const ofdg_extra_tops* tops);
+
 /* Number of kernel launches issued by this generator so far (bench.py's gpu_launches). */
 uint64_t ofdg_launch_count(const ofdg_generator* g);
 /* Device time, measured with CUDA events on the launching stream, spent in the background

@@ -45,6 +45,10 @@ AUGMENT_DTYPE = np.dtype([("enabled", "<i4"), ("gain", "<f4", (3,)), ("brightnes
 assert AUGMENT_DTYPE.itemsize == 36
 
 
+class ExtraTopsStruct(C.Structure):
+    _fields_ = [("flow_bw", C.c_void_p), ("id0", C.c_void_p), ("id1", C.c_void_p), ("occlusion", C.c_void_p)]
+
+
 class ConfigStruct(C.Structure):
     _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("mode", C.c_int32),
                 ("use_antialiasing", C.c_int32), ("max_batch", C.c_int32), ("reserved", C.c_int32 * 8)]
@@ -64,7 +68,7 @@ EXPORTS = [
     "ofdg_flatten_ellipse", "ofdg_flatten_polygon", "ofdg_debug_raster_host", "ofdg_debug_expand_host", "ofdg_create", "ofdg_destroy", "ofdg_upload_textures",
     "ofdg_synth_textures", "ofdg_download_texture", "ofdg_set_fields", "ofdg_generate_fields", "ofdg_render", "ofdg_render_host",
     "ofdg_render_debug", "ofdg_debug_background", "ofdg_debug_composite_luts", "ofdg_prepare", "ofdg_prepared_destroy",
-    "ofdg_render_prepared", "ofdg_generate", "ofdg_generate_host", "ofdg_generate_philox", "ofdg_philox_tasks", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_upload_bytes", "ofdg_last_download_bytes",
+    "ofdg_render_prepared", "ofdg_generate", "ofdg_generate_host", "ofdg_generate_philox", "ofdg_philox_tasks", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_upload_bytes", "ofdg_last_download_bytes", "ofdg_set_extra_tops",
 ]
 # include/ofdg/layer.h
 LAYER_EXPORTS = [
@@ -116,6 +120,7 @@ def lib():
         L.ofdg_download_texture.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ofdg_set_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.ofdg_generate_fields.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p]
+        L.ofdg_set_extra_tops.argtypes = [C.c_void_p, C.c_void_p]
         L.ofdg_render.argtypes = [C.c_void_p, C.POINTER(TaskBatchStruct)] + [C.c_void_p] * 4
         L.ofdg_render_host.argtypes = [C.c_void_p, C.POINTER(TaskBatchStruct)] + [C.c_void_p] * 3
         L.ofdg_render_debug.argtypes = [C.c_void_p, C.POINTER(TaskBatchStruct)] + [C.c_void_p] * 4 + [C.c_int32] + [C.c_void_p] * 3
@@ -450,6 +455,19 @@ class Generator:
         p, r, n = C.c_double(), C.c_double(), C.c_int32()
         _check(lib().ofdg_kernel_times(self._h, C.byref(p), C.byref(r), C.byref(n)))
         return p.value, r.value, n.value
+
+    def set_extra_tops(self, flow_bw=None, id0=None, id1=None, occlusion=None):
+        """Register device float tensors that every later device-blob call also fills (ofdg_set_extra_tops):
+        backward flow (N,2,H,W), index images (N,1,H,W) and the occlusion mask (N,1,H,W). No arguments: off."""
+        t = ExtraTopsStruct()
+        keep = []
+        for name, v in (("flow_bw", flow_bw), ("id0", id0), ("id1", id1), ("occlusion", occlusion)):
+            if v is not None:
+                assert v.is_cuda and v.dtype.is_floating_point and v.element_size() == 4 and v.is_contiguous()
+                setattr(t, name, v.data_ptr())
+                keep.append(v)
+        self._extra_keep = keep
+        _check(lib().ofdg_set_extra_tops(self._h, C.byref(t) if keep else None))
 
     def last_upload_bytes(self):
         return int(lib().ofdg_last_upload_bytes(self._h))

@@ -159,6 +159,8 @@ struct ofdg_generator {
   PinnedBuf staging;
   DevBuf bg, tile_hits;
   DevBuf out0, out1, outf;  // device blobs for the *_host entry points
+  ofdg_extra_tops extra{};  // extra tops of the device-blob calls (ofdg_set_extra_tops)
+  DevBuf ids8;              // object ranks per pixel, scratch of the occlusion pass
   // uint8 transport of the host-blob path: byte frames on the device, their pinned landing area, the
   // host threads that widen them into the caller's float blobs (host/expand.hpp), one event per chunk
   static constexpr int kMaxChunks = 32;
@@ -319,6 +321,16 @@ ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, 
   a.fpos_x = (const int*)g->fpos_x.p; a.falpha_x = (const double*)g->falpha_x.p;
   a.fpos_y = (const int*)g->fpos_y.p; a.falpha_y = (const double*)g->falpha_y.p;
   a.img0 = d0; a.img1 = d1; a.flow = df;
+  return a;
+}
+
+// Device-blob calls also fill the extra tops the caller registered (ofdg_set_extra_tops).
+ofdg::RenderArgs with_extra_tops(ofdg_generator* g, ofdg::RenderArgs a) {
+  a.flow_bw = g->extra.flow_bw; a.top_id0 = g->extra.id0; a.top_id1 = g->extra.id1; a.occlusion = g->extra.occlusion;
+  if (a.occlusion) {
+    g->ids8.reserve((size_t)g->cfg.max_batch * 2 * g->cfg.width * g->cfg.height);
+    a.ids8 = (uint8_t*)g->ids8.p;
+  }
   return a;
 }
 
@@ -549,7 +561,7 @@ void ofdg_destroy(ofdg_generator* g) {
     if (q.consumed) cudaEventDestroy(q.consumed);
   }
   DevBuf* bufs[] = {&g->ph_slots, &g->pool, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->bg, &g->tile_hits, &g->rtab_pos_x, &g->rtab_alpha_x, &g->rtab_pos_y, &g->rtab_alpha_y, &g->out0, &g->out1,
-                    &g->outf, &g->dbg_masks, &g->dbg_id0, &g->dbg_id1, &g->dbg_frames8, &g->dbg_planar};
+                    &g->outf, &g->ids8, &g->dbg_masks, &g->dbg_id0, &g->dbg_id1, &g->dbg_frames8, &g->dbg_planar};
   for (DevBuf* b : bufs) b->release();
   g->scene.release();
   g->staging.release();
@@ -688,6 +700,15 @@ int ofdg_generate_fields(ofdg_generator* g, uint32_t seed, int32_t n, float* fie
   return ofdg_set_fields(g, host.data(), n);  // install as the generator's pool (reach table, resize tables)
 }
 
+int ofdg_set_extra_tops(ofdg_generator* g, const ofdg_extra_tops* tops) {
+  return guarded([&] {
+    if (!g) throw ArgError("null pointer");
+    g->use();
+    CK(cudaDeviceSynchronize());  // earlier launches may still be writing the previous set
+    g->extra = tops ? *tops : ofdg_extra_tops{};
+  });
+}
+
 int ofdg_render(ofdg_generator* g, const ofdg_task_batch* tasks, float* d_img0, float* d_img1, float* d_flow, void* stream) {
   return guarded([&] {
     if (!g || !tasks || !d_img0 || !d_img1 || !d_flow) throw ArgError("null pointer");
@@ -701,7 +722,7 @@ int ofdg_render(ofdg_generator* g, const ofdg_task_batch* tasks, float* d_img0, 
     flatten_tasks(g, tasks, &g->pipe_flat[set]);
     ensure_scratch(g, tasks->n_tasks);
     upload_scene(g, g->pipe_flat[set], g->pipe_scene[set], g->pipe_staging[set], s);
-    run_kernels(g, make_args(g, g->pipe_scene[set], d_img0, d_img1, d_flow), s);
+    run_kernels(g, with_extra_tops(g, make_args(g, g->pipe_scene[set], d_img0, d_img1, d_flow)), s);
     CK(cudaEventRecord(g->render_done[set], s));
     g->render_set_used[set] = true;
     if (!stream) CK(cudaStreamSynchronize(s));
@@ -736,6 +757,7 @@ static void render_host_pipelined(ofdg_generator* g, ofdg_params* params, const 
   if (!g->workers) {
     // widening is bound by host memory bandwidth, not by cores: more threads than this only slow the DMA down
     int threads = std::min((int)std::thread::hardware_concurrency() / 2, 16);
+    if (const char* lw = std::getenv("LOCAL_WORLD_SIZE")) threads /= std::max(1, std::atoi(lw));  // one process per GPU shares the host
     if (const char* t = std::getenv("OFDG_HOST_THREADS")) threads = std::atoi(t);
     g->workers.reset(new ofdg::HostPool(std::max(2, std::min(threads, 64)), g->cfg.device));
   }
@@ -1051,7 +1073,7 @@ int ofdg_generate_philox(ofdg_generator* g, uint64_t seed, uint64_t first_sample
       philox_run(g, set, seed, first_sample, batch, augment, 0, s);
     }
     ensure_scratch(g, batch);
-    run_kernels(g, make_args(g, g->ph[set].scene, d_img0, d_img1, d_flow), s);
+    run_kernels(g, with_extra_tops(g, make_args(g, g->ph[set].scene, d_img0, d_img1, d_flow)), s);
     CK(cudaEventRecord(g->ph[set].consumed, s));
     g->ph[set].used = true;
     // look ahead: the next batch of the same stream, on the side stream, into the other set
@@ -1137,7 +1159,7 @@ int ofdg_render_prepared(ofdg_generator* g, const ofdg_prepared* p, float* d_img
     g->use();
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
     ensure_scratch(g, p->scene.batch);
-    run_kernels(g, make_args(g, p->scene, d_img0, d_img1, d_flow), s);
+    run_kernels(g, with_extra_tops(g, make_args(g, p->scene, d_img0, d_img1, d_flow)), s);
     if (!stream) CK(cudaStreamSynchronize(s));
   });
 }

@@ -54,6 +54,7 @@ struct FlatSample {
   int32_t pad;
   double bg_tex_inv[6];              // inverse of I^-1 * M * I on the 2W x 2H canvas (DataGenerator.cpp:676-677)
   double bg_motion[6];               // M alone; the flow applies I^-1, M, I in turn (DataGenerator.cpp:692-712)
+  double bg_motion_inv[6];           // M^-1 (m_motion_inv): backward flow, getPointFlow(inverse = true)
   BgPrep prep;
   ofdg_augment aug;                  // colour/noise augmentation of this sample (enabled == 0: none)
 };

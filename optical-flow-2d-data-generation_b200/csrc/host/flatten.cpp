@@ -291,6 +291,7 @@ void flatten(const ofdg_task_batch& tb, const FlattenConfig& cfg, FlatBatch& out
     const Affine tex_inv = tex_tf.inverse();
     tex_inv.store(smp.bg_tex_inv);
     bgM.store(smp.bg_motion);
+    bgM.inverse().store(smp.bg_motion_inv);
     const bool bg_deformed = (cfg.mode == 9 && bg.do_warpfield_deformation && bg.field_id >= 0);
     smp.bg_field = bg_deformed ? bg.field_id : -1;
     if (smp.bg_field >= cfg.n_fields) throw std::runtime_error("background refers to a warp field that was not injected (ofdg_set_fields)");

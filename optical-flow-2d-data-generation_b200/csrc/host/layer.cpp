@@ -298,9 +298,32 @@ void DataGenerationLayer<Dtype>::LayerSetUp(const std::vector<Blob<Dtype>*>& bot
   if (top.size() < 3) throw std::runtime_error("DataGeneration needs 3 top blobs (first image, second image, flow)");  // the reference indexes top[0..2]
   const int batch_size = this->layer_param_.data_param().batch_size();
   if (!this->layer_param_.data_generation_param().device_params()) StartInternalThread();  // the device stream needs no producer
+  if (top.size() > 7) throw std::runtime_error("DataGeneration fills at most 7 top blobs");
   top[0]->Reshape({batch_size, 3, 384, 512});  // data_generation_layer.cpp:128-130
   top[1]->Reshape({batch_size, 3, 384, 512});
   top[2]->Reshape({batch_size, 2, 384, 512});
+  BindExtraTops(top);
+}
+
+// Tops beyond the reference's three (MinTopBlobs() = 1 leaves the count open):
+//   top[3] backward flow {N,2,H,W}   RenderCore::flow1 = computeFlowImage(objects, true), DataGenerator.cpp:801-818
+//   top[4] occlusion     {N,1,H,W}   include/ofdg/ofdg.h
+//   top[5], top[6]       {N,1,H,W}   RenderCore::index_image0 / index_image1 as float
+template <typename Dtype>
+void DataGenerationLayer<Dtype>::BindExtraTops(const std::vector<Blob<Dtype>*>& top) {
+  if (top.size() <= 3) return;
+  const int batch_size = this->layer_param_.data_param().batch_size();
+  ofdg_extra_tops t{};
+  top[3]->Reshape({batch_size, 2, 384, 512});
+  t.flow_bw = top[3]->mutable_gpu_data();
+  for (size_t i = 4; i < top.size(); ++i) top[i]->Reshape({batch_size, 1, 384, 512});
+  if (top.size() > 4) t.occlusion = top[4]->mutable_gpu_data();
+  if (top.size() > 5) t.id0 = top[5]->mutable_gpu_data();
+  if (top.size() > 6) t.id1 = top[6]->mutable_gpu_data();
+  if (t.flow_bw == extra_.flow_bw && t.occlusion == extra_.occlusion && t.id0 == extra_.id0 && t.id1 == extra_.id1) return;
+  std::lock_guard<std::mutex> g(generator_mutex_);
+  OFDG_CHECK(ofdg_set_extra_tops(generator_, &t));
+  extra_ = t;
 }
 
 template <typename Dtype>
@@ -368,6 +391,7 @@ void DataGenerationLayer<Dtype>::Forward_gpu(const std::vector<Blob<Dtype>*>& bo
     top[0]->Reshape({bs, 3, 384, 512});
     top[1]->Reshape({bs, 3, 384, 512});
     top[2]->Reshape({bs, 2, 384, 512});
+    BindExtraTops(top);
     const unsigned long long seed = gp.seed() ^ ((unsigned long long)solver_rank_ << 40);  // distinct streams per replica
     if (ofdg_generate_philox(generator_, seed, device_batches_ * (unsigned long long)bs, bs, 0, top[0]->mutable_gpu_data(),
                              top[1]->mutable_gpu_data(), top[2]->mutable_gpu_data(), nullptr) != OFDG_OK)
@@ -389,6 +413,7 @@ void DataGenerationLayer<Dtype>::Forward_gpu(const std::vector<Blob<Dtype>*>& bo
   top[0]->Reshape({batch_size, 3, 384, 512});
   top[1]->Reshape({batch_size, 3, 384, 512});
   top[2]->Reshape({batch_size, 2, 384, 512});
+  BindExtraTops(top);
   int rc;
   {
     std::lock_guard<std::mutex> g(generator_mutex_);
@@ -403,7 +428,7 @@ void DataGenerationLayer<Dtype>::Forward_cpu(const std::vector<Blob<Dtype>*>& bo
   // There is no CPU generator any more: the blobs are produced on the device and become visible to
   // cpu_data() through the usual synced-memory copy.
   Forward_gpu(bottom, top);
-  for (size_t i = 0; i < 3; ++i) top[i]->cpu_data();
+  for (size_t i = 0; i < top.size(); ++i) top[i]->cpu_data();
 }
 
 template <typename Dtype>

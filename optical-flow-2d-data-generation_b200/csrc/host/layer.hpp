@@ -48,6 +48,7 @@ class DataGenerationLayer : public Layer<Dtype> {
   virtual void load_batch(ofdg_prepared** out);       // draw + flatten + upload one batch
   void StartInternalThread();
   void StopInternalThread();
+  void BindExtraTops(const std::vector<Blob<Dtype>*>& top);  // top[3..6]: backward flow, occlusion, index images
 
   static int solver_rank_;
   int device_ = 0;
@@ -63,6 +64,7 @@ class DataGenerationLayer : public Layer<Dtype> {
   bool must_stop_ = false;
   unsigned long long device_batches_ = 0;  // batches produced by the device-side stream (its sample counter)
   std::string producer_error_;
+  ofdg_extra_tops extra_{};               // what the generator currently writes besides the three blobs
 };
 
 }  // namespace caffe

@@ -466,6 +466,7 @@ __global__ void __launch_bounds__(kFlatObjPerBlock * kFlatLanes) philox_flatten_
     const Affine tex_inv = tex_tf.inverse();
     tex_inv.store(smp.bg_tex_inv);
     bgM.store(smp.bg_motion);
+    bgM.inverse().store(smp.bg_motion_inv);
     smp.bg_field = -1;  // warp fields (mode 9) are host-driven: the device stream rejects mode 9
     prepare_bg(a, bg, tex_inv, false, smp.prep);
     smp.obj_begin = s * kPhiloxMaxObj;

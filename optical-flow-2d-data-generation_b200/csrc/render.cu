@@ -296,8 +296,8 @@ __device__ __forceinline__ uint32_t comp4(uint32_t u, uint32_t v, bool additive,
   return comp4_bytes(u, v, additive, q255);
 }
 
-// kDeform = false compiles the mode-9 (warp field) branches out.
-template <bool kDeform>
+// kDeform = false compiles the mode-9 (warp field) branches out; kExtra = false the extra tops (backward flow, ids).
+template <bool kDeform, bool kExtra>
 __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render_kernel(RenderArgs a) {
   __shared__ int s_cover[NLAYER][TH][TW];
   __shared__ int s_area[NLAYER][TH][TW];
@@ -641,16 +641,14 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
 
   if (!live) return;
 
-  // ---- flow of the top-most frame-0 object, f64 -> f32 (DG.cpp:388-401, 692-712)
-  float fxv[4], fyv[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  // ---- flow of the top-most object, f64 -> f32 (DG.cpp:388-401, 692-712). Forward: frame 0's ids through the motions;
+  //      backward (extra top, computeFlowImage(inverse = true)): frame 1's ids through the inverse motions.
+  auto point_flow = [&](unsigned oid, bool inverse, int i, float& fx, float& fy) {
     const float xf = (float)(x0 + i), yf = (float)y;
-    const unsigned oid = (id0 >> (8 * i)) & 255u;
     // background: the point goes through I^-1 = T(-W,-H), M, I = T(W,H) (DG.cpp:697-712); objects: through M alone.
     // One code path: the translations are exact no-ops (+-0.0) for objects.
     const FlatObject* fo = oid ? a.objects + obj_begin + oid - 1 : nullptr;
-    const double* m = oid ? fo->motion : smp.bg_motion;
+    const double* m = oid ? (inverse ? fo->tex_inv : fo->motion) : (inverse ? smp.bg_motion_inv : smp.bg_motion);
     const double pre_x = oid ? 0.0 : (double)W, pre_y = oid ? 0.0 : (double)H;
     const float save_x = oid ? xf : xf + (float)(W / 2), save_y = oid ? yf : yf + (float)(H / 2);
     double ix = (double)save_x - pre_x, iy = (double)save_y - pre_y;
@@ -658,27 +656,30 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
     ix = tmp * m[0] + iy * m[2] + m[4];
     iy = tmp * m[1] + iy * m[3] + m[5];
     ix = ix + pre_x; iy = iy + pre_y;
-    fxv[i] = (float)(ix - save_x);
-    fyv[i] = (float)(iy - save_y);
-    if (kDeform) {
+    fx = (float)(ix - save_x);
+    fy = (float)(iy - save_y);
+    if (kDeform) {  // the forward field is added in both directions (DG.cpp:403-406, 714-717)
       const int fw = W + 1, fh = H + 1;
       if (oid == 0) {
         if (smp.bg_field >= 0 && ix >= 0 && ix < 2 * W && iy >= 0 && iy < 2 * H) {  // DG.cpp:714-717
           const float* fl = a.fields + ((size_t)smp.bg_field * 2 + 0) * 2 * fw * fh;
           auto at0 = [&](unsigned X, unsigned Y) { return resized_field2(fl, fw, fh, (int)X, (int)Y, a); };
           auto at1 = [&](unsigned X, unsigned Y) { return resized_field2(fl + (size_t)fw * fh, fw, fh, (int)X, (int)Y, a); };
-          fxv[i] += neumann_f(at0, 2 * W, 2 * H, (float)ix, (float)iy);
-          fyv[i] += neumann_f(at1, 2 * W, 2 * H, (float)ix, (float)iy);
+          fx += neumann_f(at0, 2 * W, 2 * H, (float)ix, (float)iy);
+          fy += neumann_f(at1, 2 * W, 2 * H, (float)ix, (float)iy);
         }
       } else if (fo->field >= 0 && ix >= 0 && ix < W && iy >= 0 && iy < H) {  // DG.cpp:403-406
         const float* fl = a.fields + ((size_t)fo->field * 2 + 0) * 2 * fw * fh;
         auto at0 = [&](unsigned X, unsigned Y) { return fl[(size_t)Y * fw + X]; };
         auto at1 = [&](unsigned X, unsigned Y) { return fl[(size_t)fw * fh + (size_t)Y * fw + X]; };
-        fxv[i] += neumann_f(at0, fw, fh, (float)ix, (float)iy);
-        fyv[i] += neumann_f(at1, fw, fh, (float)ix, (float)iy);
+        fx += neumann_f(at0, fw, fh, (float)ix, (float)iy);
+        fy += neumann_f(at1, fw, fh, (float)ix, (float)iy);
       }
     }
-  }
+  };
+  float fxv[4], fyv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) point_flow((id0 >> (8 * i)) & 255u, false, i, fxv[i], fyv[i]);
 
   // ---- write the three blobs (NCHW float): 8 planes x one 128-bit store per lane
   const size_t pix = (size_t)y * W + x0;
@@ -704,6 +705,32 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
   }
   __stcs(reinterpret_cast<float4*>(of), make_float4(fxv[0], fxv[1], fxv[2], fxv[3]));
   __stcs(reinterpret_cast<float4*>(of + P), make_float4(fyv[0], fyv[1], fyv[2], fyv[3]));
+
+  if (kExtra) {
+    if (a.flow_bw) {
+      float bx[4], by[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) point_flow((id1 >> (8 * i)) & 255u, true, i, bx[i], by[i]);
+      float* ob = a.flow_bw + (size_t)sample * 2 * P + pix;
+      __stcs(reinterpret_cast<float4*>(ob), make_float4(bx[0], bx[1], bx[2], bx[3]));
+      __stcs(reinterpret_cast<float4*>(ob + P), make_float4(by[0], by[1], by[2], by[3]));
+    }
+    if (a.top_id0 || a.top_id1) {
+      float v0[4], v1[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const unsigned b0 = (id0 >> (8 * i)) & 255u, b1 = (id1 >> (8 * i)) & 255u;
+        v0[i] = (float)(b0 ? a.objects[obj_begin + b0 - 1].obj_id : 1);  // the background's ID is 1 (data_generation_layer.cpp:199)
+        v1[i] = (float)(b1 ? a.objects[obj_begin + b1 - 1].obj_id : 1);
+      }
+      if (a.top_id0) __stcs(reinterpret_cast<float4*>(a.top_id0 + (size_t)sample * P + pix), make_float4(v0[0], v0[1], v0[2], v0[3]));
+      if (a.top_id1) __stcs(reinterpret_cast<float4*>(a.top_id1 + (size_t)sample * P + pix), make_float4(v1[0], v1[1], v1[2], v1[3]));
+    }
+    if (a.ids8) {
+      *reinterpret_cast<uint32_t*>(a.ids8 + (size_t)sample * 2 * P + pix) = id0;
+      *reinterpret_cast<uint32_t*>(a.ids8 + (size_t)sample * 2 * P + P + pix) = id1;
+    }
+  }
 
   if (a.dbg_id0) {
 #pragma unroll
@@ -1085,12 +1112,42 @@ int launch_deform_prepass(const RenderArgs& a, cudaStream_t s) {
   return 2;
 }
 
+namespace {
+// Occlusion top (this repository's definition, include/ofdg/ofdg.h): frame 0's pixel p, carried by its forward flow
+// to the nearest frame-1 pixel q, is occluded when q lies outside the frame or shows another object there.
+__global__ void occlusion_kernel(RenderArgs a) {
+  const size_t P = (size_t)a.W * a.H;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int sample = blockIdx.y;
+  if (i >= P) return;
+  const int x = (int)(i % a.W), y = (int)(i / a.W);
+  const float* fl = a.flow + (size_t)sample * 2 * P;
+  const uint8_t* ids = a.ids8 + (size_t)sample * 2 * P;
+  const float tx = (float)x + fl[i], ty = (float)y + fl[P + i];
+  float occ = 1.f;
+  if (tx >= -0.5f && tx < (float)a.W - 0.5f && ty >= -0.5f && ty < (float)a.H - 0.5f) {  // false for NaN
+    const int qx = (int)floorf(tx + 0.5f), qy = (int)floorf(ty + 0.5f);
+    if (ids[P + (size_t)qy * a.W + qx] == ids[i]) occ = 0.f;
+  }
+  a.occlusion[(size_t)sample * P + i] = occ;
+}
+}  // namespace
+
 int launch_render(const RenderArgs& a, cudaStream_t s) {
   const int tiles_x = (a.W + TW - 1) / TW, tiles_y = (a.H + TH - 1) / TH;
   dim3 grid(tiles_x * tiles_y, a.batch);
-  if (a.n_fields > 0) render_kernel<true><<<grid, RENDER_THREADS, 0, s>>>(a);
-  else render_kernel<false><<<grid, RENDER_THREADS, 0, s>>>(a);
-  return 1;
+  const bool extra = a.flow_bw || a.top_id0 || a.top_id1 || a.ids8;
+  if (a.n_fields > 0) {
+    if (extra) render_kernel<true, true><<<grid, RENDER_THREADS, 0, s>>>(a);
+    else render_kernel<true, false><<<grid, RENDER_THREADS, 0, s>>>(a);
+  } else {
+    if (extra) render_kernel<false, true><<<grid, RENDER_THREADS, 0, s>>>(a);
+    else render_kernel<false, false><<<grid, RENDER_THREADS, 0, s>>>(a);
+  }
+  if (!a.occlusion) return 1;
+  const size_t P = (size_t)a.W * a.H;
+  occlusion_kernel<<<dim3((unsigned)((P + 255) / 256), a.batch), 256, 0, s>>>(a);
+  return 2;
 }
 
 void launch_planar_to_rgbx(const uint8_t* planar, uchar4* out, int n, int w, int h, cudaStream_t s) {

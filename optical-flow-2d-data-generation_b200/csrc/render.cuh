@@ -44,6 +44,12 @@ struct RenderArgs {
   float* img0;
   float* img1;
   float* flow;
+  // extra tops (device, each may be null): what the reference's RenderCore holds besides the three blobs
+  float* flow_bw;       // [batch][2][H][W] computeFlowImage(inverse = true): flow of frame 1's pixels back to frame 0
+  float* top_id0;       // [batch][1][H][W] index_image0 as float (1 = background, 10 + k = k-th foreground object)
+  float* top_id1;
+  float* occlusion;     // [batch][1][H][W] 1 where frame 0's pixel is not visible in frame 1 (include/ofdg/ofdg.h)
+  uint8_t* ids8;        // [batch][2][H][W] scratch: per-sample object ranks (0 = background, k + 1), feeds the occlusion pass
   // parity instrumentation (device, may be null)
   uint8_t* dbg_masks;   // [batch][max_objs][4][H][W]
   int dbg_max_objs;
@@ -58,7 +64,7 @@ constexpr int TILE_HIT_STRIDE = 32;  // 1 count byte + up to 31 object indices p
 int launch_bin(const RenderArgs& a, cudaStream_t s);
 size_t tile_hits_bytes(int batch, int W, int H);
 int launch_background_prep(const RenderArgs& a, cudaStream_t s);
-int launch_render(const RenderArgs& a, cudaStream_t s);
+int launch_render(const RenderArgs& a, cudaStream_t s);  // + the occlusion pass when a.occlusion is set
 int launch_deform_prepass(const RenderArgs& a, cudaStream_t s);  // mode 9 only; no-op when n_deform == 0
 
 void launch_resize_tables(int* pos, double* alpha, int n, cudaStream_t s);  // one-time, all lengths 1..n-1 -> n

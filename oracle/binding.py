@@ -19,7 +19,7 @@ class OracleConfig(C.Structure):
 
 class OracleDebug(C.Structure):
     _fields_ = [("id0", C.c_void_p), ("id1", C.c_void_p), ("masks", C.c_void_p), ("max_objs", C.c_int32),
-                ("frames8", C.c_void_p)]
+                ("frames8", C.c_void_p), ("flow_bw", C.c_void_p), ("occlusion", C.c_void_p)]
 
 
 def build(force=False):
@@ -61,7 +61,10 @@ def render(task_struct, textures, W=512, H=384, mode=1, use_aa=True, fields=None
         out["id1"] = np.empty((n, H, W), np.uint32)
         out["masks"] = np.zeros((n, max_objs, 4, H, W), np.uint8)
         out["frames8"] = np.empty((n, 2, 3, H, W), np.uint8)
-        dbg = OracleDebug(out["id0"].ctypes.data, out["id1"].ctypes.data, out["masks"].ctypes.data, max_objs, out["frames8"].ctypes.data)
+        out["flow_bw"] = np.empty((n, 2, H, W), np.float32)
+        out["occlusion"] = np.empty((n, 1, H, W), np.float32)
+        dbg = OracleDebug(out["id0"].ctypes.data, out["id1"].ctypes.data, out["masks"].ctypes.data, max_objs, out["frames8"].ctypes.data,
+                          out["flow_bw"].ctypes.data, out["occlusion"].ctypes.data)
     if fields is not None:
         fields = np.ascontiguousarray(fields, np.float32)
     rc = lib().oracle_render(C.byref(cfg), C.byref(task_struct), _p(textures), _p(fields), _p(out["img0"]), _p(out["img1"]),

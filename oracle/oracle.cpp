@@ -872,13 +872,14 @@ struct MovingObject {
       }
     }
   }
-  void get_point_flow(float* x, float* y) const {
+  void get_point_flow(float* x, float* y, bool inverse = false) const {
     const int W = ctx->W, H = ctx->H;
     if (is_bg) {  // DG.cpp:692-718
       double ix = *x + W / 2, iy = *y + H / 2;
       float save_x = ix, save_y = iy;
       intrinsic_inv.transform(&ix, &iy);
-      motion.transform(&ix, &iy);
+      if (inverse) motion_inv.transform(&ix, &iy);
+      else motion.transform(&ix, &iy);
       intrinsic.transform(&ix, &iy);
       *x = ix - save_x; *y = iy - save_y;
       if (has_fields && ix >= 0 && ix < 2 * W && iy >= 0 && iy < 2 * H) {
@@ -889,7 +890,8 @@ struct MovingObject {
     }
     double ix = *x, iy = *y;  // DG.cpp:388-407
     float save_x = ix, save_y = iy;
-    motion.transform(&ix, &iy);
+    if (inverse) motion_inv.transform(&ix, &iy);
+    else motion.transform(&ix, &iy);
     *x = ix - save_x; *y = iy - save_y;
     if (has_fields && ix >= 0 && ix < W && iy >= 0 && iy < H) {
       *x += cimg_linear_neumann(field, (float)ix, (float)iy, 0);
@@ -1049,6 +1051,33 @@ static void process_task(const Ctx& c, const ofdg_task_batch& tb, int t, float* 
       }
   }
   std::memcpy(flow, flow0.d.data(), 2 * P * sizeof(float));
+  if (dbg && dbg->flow_bw) {  // RenderCore::computeFlowImage(objects, true), DG.cpp:801-818
+    float* fb = dbg->flow_bw + (size_t)t * 2 * P;
+    std::fill(fb, fb + 2 * P, 0.f);
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        size_t idx = index1[(size_t)y * W + x];
+        if (idx == 0) continue;
+        float xf = x, yf = y;
+        objects[idx]->get_point_flow(&xf, &yf, true);
+        fb[(size_t)y * W + x] = xf;
+        fb[P + (size_t)y * W + x] = yf;
+      }
+  }
+  if (dbg && dbg->occlusion) {  // not in the reference: the product's occlusion top (include/ofdg/ofdg.h)
+    float* oc = dbg->occlusion + (size_t)t * P;
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        const size_t i = (size_t)y * W + x;
+        const float tx = (float)x + flow0.at(x, y, 0), ty = (float)y + flow0.at(x, y, 1);
+        float occ = 1.f;
+        if (tx >= -0.5f && tx < (float)W - 0.5f && ty >= -0.5f && ty < (float)H - 0.5f) {
+          const int qx = (int)std::floor(tx + 0.5f), qy = (int)std::floor(ty + 0.5f);
+          if (index1[(size_t)qy * W + qx] == index0[i]) occ = 0.f;
+        }
+        oc[i] = occ;
+      }
+  }
   if (dbg) {
     if (dbg->id0) for (size_t i = 0; i < P; ++i) dbg->id0[(size_t)t * P + i] = (uint32_t)index0[i];
     if (dbg->id1) for (size_t i = 0; i < P; ++i) dbg->id1[(size_t)t * P + i] = (uint32_t)index1[i];

@@ -36,13 +36,18 @@ typedef struct oracle_config {
  *   id0/id1:  n_tasks x H x W uint32, object id of the top-most non-AA-covered object
  *   masks:    n_tasks x max_objs x 4 x H x W uint8, per top-level foreground object k (z-order):
  *             [AA frame0, AA frame1, noAA frame0, noAA frame1]
- *   frames8:  n_tasks x 2 x 3 x H x W uint8 composited frames before the float conversion */
+ *   frames8:  n_tasks x 2 x 3 x H x W uint8 composited frames before the float conversion
+ *   flow_bw:  n_tasks x 2 x H x W float, RenderCore::computeFlowImage(objects, true) (DataGenerator.cpp:801-818): flow1
+ *   occlusion: n_tasks x H x W float; NOT a reference output -- the product's own definition (include/ofdg/ofdg.h),
+ *             restated here from flow0 and the two index images so that both sides can be compared */
 typedef struct oracle_debug {
   uint32_t* id0;
   uint32_t* id1;
   uint8_t* masks;
   int32_t max_objs;
   uint8_t* frames8;
+  float* flow_bw;
+  float* occlusion;
 } oracle_debug;
 
 /* Renders every task of the batch. img0/img1: n_tasks x 3 x H x W float, flow: n_tasks x 2 x H x W.

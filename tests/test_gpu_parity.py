@@ -266,3 +266,54 @@ def test_host_pipeline_reports_a_bad_task_and_recovers(ofdg, textures8):
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
     g.close()
+
+
+@pytest.mark.parametrize("mode", [7, 9])
+def test_extra_tops_backward_flow_ids_occlusion(ofdg, oracle, textures8, fields4, mode):
+    """SURVEY 8 f4 extra tops: index images and computeFlowImage(inverse=true) (DataGenerator.cpp:740-818) against the
+    oracle, plus this repository's occlusion mask against its restatement. The three standard blobs do not change."""
+    import torch
+    n = 6
+    g = _gen(ofdg, mode)
+    g.upload_textures(textures8)
+    if mode == 9:
+        g.set_fields(fields4)
+    tasks = ofdg.ParamStream(mode, n_fields=4 if mode == 9 else 0).generate(n)
+    dev = lambda c: torch.full((n, c, 384, 512), -5.0, device="cuda")
+    i0, i1, fl = dev(3), dev(3), dev(2)
+    g.render(tasks, i0, i1, fl)
+    torch.cuda.synchronize()
+    plain = [t.clone() for t in (i0, i1, fl)]
+    bw, id0, id1, occ = dev(2), dev(1), dev(1), dev(1)
+    g.set_extra_tops(flow_bw=bw, id0=id0, id1=id1, occlusion=occ)
+    g.render(tasks, i0, i1, fl)
+    torch.cuda.synchronize()
+    for a, b in zip(plain, (i0, i1, fl)):
+        assert torch.equal(a, b) or (mode == 9 and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b)))
+    cpu = oracle.render(tasks.struct(), textures8, mode=mode, fields=fields4 if mode == 9 else None, debug=True)
+    assert np.array_equal(id0.cpu().numpy()[:, 0], cpu["id0"].astype(np.float32))
+    assert np.array_equal(id1.cpu().numpy()[:, 0], cpu["id1"].astype(np.float32))
+    d = np.abs(bw.cpu().numpy() - cpu["flow_bw"])
+    assert np.nanmax(d) <= FLOW_TOL and np.array_equal(np.isnan(bw.cpu().numpy()), np.isnan(cpu["flow_bw"]))
+    o_gpu, o_cpu = occ.cpu().numpy(), cpu["occlusion"]
+    assert set(np.unique(o_gpu)) <= {0.0, 1.0}
+    # the mask is a function of flow (compared to 1e-3 px, not bitwise): allow disagreement only where a flow component
+    # sits within the tolerance of a rounding boundary
+    assert (o_gpu != o_cpu).mean() <= 1e-5
+    assert 0.001 < o_gpu.mean() < 0.6
+    # numpy restatement of the definition from the GPU's own tops: exact
+    f = fl.cpu().numpy(); a0 = id0.cpu().numpy()[:, 0]; a1 = id1.cpu().numpy()[:, 0]
+    ys, xs = np.mgrid[0:384, 0:512].astype(np.float32)
+    with np.errstate(invalid="ignore"):
+        tx, ty = xs + f[:, 0], ys + f[:, 1]
+        inside = (tx >= -0.5) & (tx < 511.5) & (ty >= -0.5) & (ty < 383.5)
+        qx = np.where(inside, np.floor(tx + np.float32(0.5)), 0).astype(np.int64)
+        qy = np.where(inside, np.floor(ty + np.float32(0.5)), 0).astype(np.int64)
+    same = a1[np.arange(n)[:, None, None], qy, qx] == a0
+    assert np.array_equal(o_gpu[:, 0], np.where(inside & same, 0.0, 1.0).astype(np.float32))
+    g.set_extra_tops()   # off again: the registered tensors are left alone
+    bw.fill_(-9.0)
+    g.render(tasks, i0, i1, fl)
+    torch.cuda.synchronize()
+    assert float(bw.min()) == -9.0
+    g.close()

@@ -94,3 +94,26 @@ def test_layer_device_params_mode(ofdg):
     layer2.Forward_gpu()
     assert np.array_equal(layer2.top_cpu(0), a[0])
     layer2.close()
+
+
+@pytest.mark.gpu
+def test_layer_extra_tops(ofdg, oracle):
+    """Seven tops: the reference's three, then backward flow, occlusion and the two index images."""
+    proto = ('layer { type: "DataGeneration" top: "img0" top: "img1" top: "flow" top: "flow_bw" top: "occ" top: "id0" top: "id1" '
+             'data_param { batch_size: 3 prefetch: 2 } data_generation_param { mode: 5 texture_dbases: "synthetic:8:1" } }')
+    layer = ofdg.DataGenerationLayer(proto)
+    layer.LayerSetUp()
+    assert [layer.top_shape(i)[1] for i in range(7)] == [3, 3, 2, 2, 1, 1, 1]
+    tex = ofdg.synth_textures(8, 1024, 768, seed=1)
+    ps = ofdg.ParamStream(5)
+    for it in range(2):
+        layer.Forward_cpu() if it else layer.Forward_gpu()
+        got = [layer.top_cpu(i) for i in range(7)]
+        ref = oracle.render(ps.generate(3).struct(), tex, mode=5, debug=True)
+        assert np.abs(got[2] - ref["flow"]).max() <= 1e-3 and np.abs(got[3] - ref["flow_bw"]).max() <= 1e-3
+        assert np.array_equal(got[5][:, 0], ref["id0"].astype(np.float32)) and np.array_equal(got[6][:, 0], ref["id1"].astype(np.float32))
+        assert (got[4] != ref["occlusion"]).mean() <= 1e-5
+    layer.close()
+    with pytest.raises(ofdg.OfdgError, match="at most 7"):
+        bad = ofdg.DataGenerationLayer(proto.replace('top: "id1"', 'top: "id1" top: "x"'))
+        bad.LayerSetUp()
