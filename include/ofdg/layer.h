@@ -17,7 +17,8 @@ const char* ofdg_layer_last_error(void);
  * ints[7] = {batch_size, prefetch, mode, first_level_threads, second_level_threads, use_antialiasing, top_size}. */
 int ofdg_layer_parse_prototxt(const char* text, int32_t* ints, char* texture_db, int32_t cap, char* type, int32_t type_cap);
 /* DataGenerationLayer(const LayerParameter&) on the current CUDA device. texture_db_override (may be NULL)
- * replaces texture_dbases(0): either a list file of binary PPM paths or "synthetic:<count>[:<seed>]". */
+ * replaces texture_dbases(0): either a list file of image paths (binary PPM, uncompressed BMP, 8-bit PNG; any
+ * mix of sizes) or "synthetic:<count>[:<seed>]". */
 int ofdg_layer_create(const char* prototxt, const char* texture_db_override, int32_t solver_rank, void** out);
 void ofdg_layer_destroy(void* layer);
 int ofdg_layer_setup(void* layer);                               /* Layer::SetUp -> LayerSetUp: starts prefetching, shapes the 3 tops */
@@ -25,6 +26,9 @@ int ofdg_layer_top_shape(void* layer, int32_t i, int32_t* shape4);
 int ofdg_layer_forward(void* layer, int32_t gpu);                /* Forward_gpu (1) / Forward_cpu (0) */
 const float* ofdg_layer_top_data(void* layer, int32_t i, int32_t gpu); /* top[i]->gpu_data() / cpu_data() */
 const char* ofdg_layer_type(void* layer);                        /* "DataGeneration" */
+/* The texture-file decoder the layer uses (TextureCollection ctor, DataGenerator.cpp:128-133): size of the image,
+ * and, when `planar_bgr` is non-NULL and `cap` >= 3*w*h, its pixels as 3 x h x w planes in B,G,R order. No GPU needed. */
+int ofdg_decode_texture_file(const char* path, int32_t* w, int32_t* h, uint8_t* planar_bgr, uint64_t cap);
 
 #ifdef __cplusplus
 }

@@ -99,12 +99,22 @@ void ofdg_destroy(ofdg_generator* g);                            /* Stop() + dto
 
 /* TextureCollection ctor (DataGenerator.cpp:117-149) minus the image-file decoding: `planar` is
  * n x 3 x h x w uint8 in the channel order the reference holds after its R<->B swap. One-time
- * upload into the HBM-resident pool. All textures share one size, >= 2*width x 2*height. */
+ * upload into the HBM-resident pool. ofdg_upload_textures replaces the pool; ofdg_add_textures
+ * appends, so a pool may mix sizes (one call per size), like the reference's texture lists.
+ * Any size from 2 x 2 works, with Texture::getRandomizedCrop's two branches (DataGenerator.cpp:87-109):
+ * foreground objects use the centre W x H window of a texture that is at least W x H, else the
+ * whole texture resized to W x H (resized once, here); the background crops textures that are at
+ * least 2W x 2H and resizes smaller ones whole. */
 int ofdg_upload_textures(ofdg_generator* g, const uint8_t* planar, int32_t n, int32_t w, int32_t h);
+int ofdg_add_textures(ofdg_generator* g, const uint8_t* planar, int32_t n, int32_t w, int32_t h);
+int ofdg_clear_textures(ofdg_generator* g);
 /* Fills the pool with n procedural textures generated on the device (no texture database is
  * available offline); bit-identical to ofdg_b200.synth_textures() in numpy. */
 int ofdg_synth_textures(ofdg_generator* g, int32_t n, int32_t w, int32_t h, uint64_t seed);
+int ofdg_texture_size(const ofdg_generator* g, int32_t index, int32_t* w, int32_t* h);
 int ofdg_download_texture(ofdg_generator* g, int32_t index, uint8_t* planar_out);
+/* The 3 x H x W foreground view of pool texture `index` as the renderer reads it (parity checks). */
+int ofdg_download_foreground_view(ofdg_generator* g, int32_t index, uint8_t* planar_out);
 
 /* Mode 9: inject the pool of (flow, iflow) crops the reference takes from
  * WarpFields::CropGenerator::get_crop (src/caffe/WarpFields.cpp:516-538). fields is

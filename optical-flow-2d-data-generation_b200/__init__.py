@@ -65,7 +65,7 @@ EXPORTS = [
     "ofdg_last_error", "ofdg_version", "ofdg_params_create", "ofdg_params_destroy", "ofdg_params_generate",
     "ofdg_params_skip", "ofdg_params_enable_augmentation", "ofdg_params_tasks_generated", "ofdg_params_draws", "ofdg_params_slot_name",
     "ofdg_tasks_create", "ofdg_tasks_destroy", "ofdg_tasks_clear", "ofdg_tasks_view", "ofdg_tasks_assign",
-    "ofdg_flatten_ellipse", "ofdg_flatten_polygon", "ofdg_debug_raster_host", "ofdg_debug_expand_host", "ofdg_create", "ofdg_destroy", "ofdg_upload_textures",
+    "ofdg_flatten_ellipse", "ofdg_flatten_polygon", "ofdg_debug_raster_host", "ofdg_debug_expand_host", "ofdg_create", "ofdg_destroy", "ofdg_upload_textures", "ofdg_add_textures", "ofdg_clear_textures", "ofdg_texture_size", "ofdg_download_foreground_view",
     "ofdg_synth_textures", "ofdg_download_texture", "ofdg_set_fields", "ofdg_generate_fields", "ofdg_render", "ofdg_render_host",
     "ofdg_render_debug", "ofdg_debug_background", "ofdg_debug_composite_luts", "ofdg_prepare", "ofdg_prepared_destroy",
     "ofdg_render_prepared", "ofdg_generate", "ofdg_generate_host", "ofdg_generate_philox", "ofdg_philox_tasks", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_upload_bytes", "ofdg_last_download_bytes", "ofdg_set_extra_tops",
@@ -73,7 +73,7 @@ EXPORTS = [
 # include/ofdg/layer.h
 LAYER_EXPORTS = [
     "ofdg_layer_last_error", "ofdg_layer_parse_prototxt", "ofdg_layer_create", "ofdg_layer_destroy", "ofdg_layer_setup",
-    "ofdg_layer_top_shape", "ofdg_layer_forward", "ofdg_layer_top_data", "ofdg_layer_type",
+    "ofdg_layer_top_shape", "ofdg_layer_forward", "ofdg_layer_top_data", "ofdg_layer_type", "ofdg_decode_texture_file",
 ]
 
 
@@ -116,6 +116,10 @@ def lib():
         L.ofdg_create.argtypes = [C.POINTER(ConfigStruct), C.POINTER(C.c_void_p)]
         L.ofdg_destroy.argtypes = [C.c_void_p]
         L.ofdg_upload_textures.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+        L.ofdg_add_textures.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+        L.ofdg_clear_textures.argtypes = [C.c_void_p]
+        L.ofdg_texture_size.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.ofdg_download_foreground_view.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ofdg_synth_textures.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64]
         L.ofdg_download_texture.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ofdg_set_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
@@ -318,6 +322,19 @@ def raster_host(xy, W, H, aa=True):
     return mask
 
 
+def decode_texture_file(path):
+    """The layer's texture-file decoder (binary PPM, uncompressed BMP, 8-bit PNG): (3, h, w) uint8, planes B,G,R."""
+    L = lib()
+    L.ofdg_decode_texture_file.argtypes = [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_uint64]
+    w, h = C.c_int32(), C.c_int32()
+    if L.ofdg_decode_texture_file(str(path).encode(), C.byref(w), C.byref(h), None, 0):
+        raise OfdgError(L.ofdg_layer_last_error().decode())
+    out = np.empty((3, h.value, w.value), np.uint8)
+    if L.ofdg_decode_texture_file(str(path).encode(), C.byref(w), C.byref(h), _ptr(out), out.size):
+        raise OfdgError(L.ofdg_layer_last_error().decode())
+    return out
+
+
 def expand_host(src, dst, streaming=True):
     """The host routine of the uint8 transport (csrc/host/expand.cpp): dst[i] = float(src[i]), in place into `dst`."""
     assert src.dtype == np.uint8 and dst.dtype == np.float32 and src.size == dst.size
@@ -348,20 +365,42 @@ class Generator:
 
     # -- texture pool
     def upload_textures(self, planar):
+        """Replace the pool. `planar`: (n, 3, h, w) uint8, or a list of (3, h, w) arrays of different sizes."""
+        if isinstance(planar, (list, tuple)):
+            _check(lib().ofdg_clear_textures(self._h))
+            for t in planar:
+                self.add_textures(np.asarray(t)[None])
+            return
         planar = np.ascontiguousarray(planar, dtype=np.uint8)
         n, c, h, w = planar.shape
         assert c == 3
         _check(lib().ofdg_upload_textures(self._h, _ptr(planar), n, w, h))
-        self.tex = (n, w, h)
+
+    def add_textures(self, planar):
+        """Append (n, 3, h, w) uint8 textures of one size to the pool (ofdg_add_textures)."""
+        planar = np.ascontiguousarray(planar, dtype=np.uint8)
+        n, c, h, w = planar.shape
+        assert c == 3
+        _check(lib().ofdg_add_textures(self._h, _ptr(planar), n, w, h))
 
     def synth_textures(self, n, w=1024, h=768, seed=0):
         _check(lib().ofdg_synth_textures(self._h, n, w, h, seed))
-        self.tex = (n, w, h)
+
+    def texture_size(self, i):
+        w, h = C.c_int32(), C.c_int32()
+        _check(lib().ofdg_texture_size(self._h, i, C.byref(w), C.byref(h)))
+        return w.value, h.value
 
     def download_texture(self, i):
-        n, w, h = self.tex
+        w, h = self.texture_size(i)
         out = np.empty((3, h, w), dtype=np.uint8)
         _check(lib().ofdg_download_texture(self._h, i, _ptr(out)))
+        return out
+
+    def download_foreground_view(self, i):
+        """The (3, H, W) view of pool texture i that foreground objects are textured from."""
+        out = np.empty((3, self.H, self.W), dtype=np.uint8)
+        _check(lib().ofdg_download_foreground_view(self._h, i, _ptr(out)))
         return out
 
     def set_fields(self, fields):

@@ -15,9 +15,9 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libofdg.so")
 
-SOURCES = ["api.cu", "render.cu", "philox.cu", "warpfields.cu", "host/params.cpp", "host/flatten.cpp", "host/layer.cpp", "host/expand.cpp"]
+SOURCES = ["api.cu", "render.cu", "philox.cu", "warpfields.cu", "host/params.cpp", "host/flatten.cpp", "host/layer.cpp", "host/expand.cpp", "host/texture_io.cpp"]
 HEADERS = ["render.cuh", "philox.cuh", "warpfields.cuh", "raster_tile.h", "flat_scene.h", "host/params.hpp", "host/flatten.hpp", "host/affine.hpp",
-           "host/mode_tables.inc", "host/layer.hpp", "host/caffe_shim.hpp", "host/expand.hpp"]
+           "host/mode_tables.inc", "host/layer.hpp", "host/caffe_shim.hpp", "host/expand.hpp", "host/texture_io.hpp"]
 
 
 def _nvcc():
@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "--fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-O2,-pthread", "-shared",
-           "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB + ".tmp"] + srcs
+           "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB + ".tmp"] + srcs + ["-lz"]
     cmd += [f for f in os.environ.get("OFDG_NVCC_FLAGS", "").split() if f]  # experiments: -DOFDG_TILE_ROWS=4 ...
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

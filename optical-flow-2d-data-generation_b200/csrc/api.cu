@@ -149,7 +149,10 @@ struct ofdg_generator {
   DevBuf rtab_pos_x, rtab_alpha_x, rtab_pos_y, rtab_alpha_y;  // CImg linear-resize tables for every source length
   // texture pool
   DevBuf pool;
-  int n_tex = 0, tex_w = 0, tex_h = 0;
+  int n_tex = 0;
+  size_t pool_px = 0;                    // pixels in use
+  std::vector<ofdg::TexInfo> tex_info;   // host copy of the table
+  DevBuf tex_info_dev;
   // mode 9 fields
   DevBuf fields, fpos_x, falpha_x, fpos_y, falpha_y, mask_raw, mask_warp;
   int n_fields = 0;
@@ -269,7 +272,7 @@ void upload_scene(ofdg_generator* g, const ofdg::FlatBatch& fb, DeviceScene& ds,
 ofdg::FlattenConfig flatten_config(const ofdg_generator* g) {
   ofdg::FlattenConfig fc;
   fc.W = g->cfg.width; fc.H = g->cfg.height;
-  fc.tex_w = g->tex_w; fc.tex_h = g->tex_h; fc.n_tex = g->n_tex;
+  fc.tex_info = g->tex_info.data(); fc.n_tex = g->n_tex;
   fc.mode = g->cfg.mode;
   fc.n_fields = g->n_fields;
   fc.field_reach = g->field_reach.empty() ? nullptr : g->field_reach.data();
@@ -301,7 +304,7 @@ ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, 
   a.W = g->cfg.width; a.H = g->cfg.height;
   a.use_aa = g->cfg.use_antialiasing;
   a.pool = (const uchar4*)g->pool.p;
-  a.tex_w = g->tex_w; a.tex_h = g->tex_h;
+  a.tex_info = (const ofdg::TexInfo*)g->tex_info_dev.p;
   a.bg = (uchar4*)g->bg.p;
   a.tile_hits = (uint8_t*)g->tile_hits.p;
   a.pos_x = (const int*)g->rtab_pos_x.p; a.alpha_x = (const double*)g->rtab_alpha_x.p;
@@ -560,7 +563,7 @@ void ofdg_destroy(ofdg_generator* g) {
     if (q.ready) cudaEventDestroy(q.ready);
     if (q.consumed) cudaEventDestroy(q.consumed);
   }
-  DevBuf* bufs[] = {&g->ph_slots, &g->pool, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->bg, &g->tile_hits, &g->rtab_pos_x, &g->rtab_alpha_x, &g->rtab_pos_y, &g->rtab_alpha_y, &g->out0, &g->out1,
+  DevBuf* bufs[] = {&g->ph_slots, &g->pool, &g->tex_info_dev, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->bg, &g->tile_hits, &g->rtab_pos_x, &g->rtab_alpha_x, &g->rtab_pos_y, &g->rtab_alpha_y, &g->out0, &g->out1,
                     &g->outf, &g->ids8, &g->dbg_masks, &g->dbg_id0, &g->dbg_id1, &g->dbg_frames8, &g->dbg_planar};
   for (DevBuf* b : bufs) b->release();
   g->scene.release();
@@ -582,35 +585,118 @@ void ofdg_destroy(ofdg_generator* g) {
   delete g;
 }
 
-int ofdg_upload_textures(ofdg_generator* g, const uint8_t* planar, int32_t n, int32_t w, int32_t h) {
+// ---- texture pool: textures of any size back to back, each with its foreground view (TexInfo) ---------
+namespace {
+
+// Nothing may still be reading the pool (or the look-ahead batch of the device stream) when it changes.
+void pool_quiesce(ofdg_generator* g) {
+  CK(cudaDeviceSynchronize());
+  g->ph_next.valid = false;
+}
+
+// Room for `extra_px` more pixels; keeps what is there.
+void pool_grow(ofdg_generator* g, size_t extra_px) {
+  const size_t need = (g->pool_px + extra_px) * sizeof(uchar4);
+  if (need <= g->pool.cap) return;
+  DevBuf bigger;
+  bigger.reserve(g->pool_px ? std::max(need, g->pool.cap + g->pool.cap / 2) : need);
+  if (g->pool_px) CK(cudaMemcpy(bigger.p, g->pool.p, g->pool_px * sizeof(uchar4), cudaMemcpyDeviceToDevice));
+  g->pool.release();
+  g->pool = bigger;
+}
+
+// Registers the texture whose w x h pixels already sit at pool offset `off`; appends its foreground view when the
+// texture is smaller than W x H (Texture::getRandomizedCrop's else branch, DataGenerator.cpp:103-107).
+void pool_register(ofdg_generator* g, size_t off, int w, int h) {
+  const int W = g->cfg.width, H = g->cfg.height;
+  ofdg::TexInfo ti{};
+  ti.off = off; ti.w = w; ti.h = h;
+  if (w >= W && h >= H) {  // centre crop: crop(w/2-W/2, h/2-H/2, ...) with zoom 1, DataGenerator.cpp:99-102
+    ti.fg_base = off + (size_t)(h / 2 - H / 2) * w + (size_t)(w / 2 - W / 2);
+    ti.fg_pitch = w;
+  } else {
+    const size_t P = (size_t)W * H;
+    pool_grow(g, P);
+    DevBuf tmp, pos, alpha;
+    tmp.reserve((size_t)W * h * sizeof(uint32_t));
+    pos.reserve((size_t)std::max(W, H) * sizeof(int)); alpha.reserve((size_t)std::max(W, H) * sizeof(double));
+    g->launches += ofdg::launch_fg_resize((const uchar4*)g->pool.p + off, w, h, W, H, (uchar4*)g->pool.p + g->pool_px, (uint32_t*)tmp.p,
+                                          (int*)pos.p, (double*)alpha.p, g->stream);
+    CK(cudaStreamSynchronize(g->stream));
+    CK(cudaGetLastError());
+    tmp.release(); pos.release(); alpha.release();
+    ti.fg_base = g->pool_px;
+    ti.fg_pitch = W;
+    g->pool_px += P;
+  }
+  g->tex_info.push_back(ti);
+}
+
+void pool_publish(ofdg_generator* g) {
+  g->n_tex = (int)g->tex_info.size();
+  g->tex_info_dev.reserve(g->tex_info.size() * sizeof(ofdg::TexInfo));
+  CK(cudaMemcpy(g->tex_info_dev.p, g->tex_info.data(), g->tex_info.size() * sizeof(ofdg::TexInfo), cudaMemcpyHostToDevice));
+}
+
+void check_texture_size(int n, int w, int h) {
+  if (n <= 0) throw ArgError("bad arguments");
+  if (w < 2 || h < 2 || w > 32768 || h > 32768) throw ArgError("texture sizes must be in 2..32768");
+}
+
+}  // namespace
+
+int ofdg_clear_textures(ofdg_generator* g) {
   return guarded([&] {
-    if (!g || !planar || n <= 0) throw ArgError("bad arguments");
-    if (w < 2 * g->cfg.width || h < 2 * g->cfg.height) throw ArgError("textures must be at least 2*width x 2*height");
+    if (!g) throw ArgError("null pointer");
     g->use();
+    pool_quiesce(g);
+    g->tex_info.clear();
+    g->pool_px = 0;
+    g->n_tex = 0;
+  });
+}
+
+int ofdg_add_textures(ofdg_generator* g, const uint8_t* planar, int32_t n, int32_t w, int32_t h) {
+  return guarded([&] {
+    if (!g || !planar) throw ArgError("bad arguments");
+    check_texture_size(n, w, h);
+    g->use();
+    pool_quiesce(g);
     const size_t plane = (size_t)w * h;
-    g->pool.reserve(plane * n * sizeof(uchar4));
+    pool_grow(g, plane * n);
     DevBuf tmp;
     const int chunk = 16;
     tmp.reserve(plane * 3 * chunk);
+    const size_t first = g->pool_px;
     for (int i = 0; i < n; i += chunk) {
       const int m = std::min(chunk, n - i);
       CK(cudaMemcpyAsync(tmp.p, planar + (size_t)i * 3 * plane, plane * 3 * m, cudaMemcpyHostToDevice, g->stream));
-      ofdg::launch_planar_to_rgbx((const uint8_t*)tmp.p, (uchar4*)g->pool.p + (size_t)i * plane, m, w, h, g->stream);
+      ofdg::launch_planar_to_rgbx((const uint8_t*)tmp.p, (uchar4*)g->pool.p + first + (size_t)i * plane, m, w, h, g->stream);
       ++g->launches;
       CK(cudaStreamSynchronize(g->stream));
     }
     tmp.release();
-    g->n_tex = n; g->tex_w = w; g->tex_h = h;
+    g->pool_px += plane * n;
+    for (int i = 0; i < n; ++i) pool_register(g, first + (size_t)i * plane, w, h);
+    pool_publish(g);
   });
+}
+
+int ofdg_upload_textures(ofdg_generator* g, const uint8_t* planar, int32_t n, int32_t w, int32_t h) {
+  const int rc = ofdg_clear_textures(g);
+  return rc ? rc : ofdg_add_textures(g, planar, n, w, h);
 }
 
 int ofdg_synth_textures(ofdg_generator* g, int32_t n, int32_t w, int32_t h, uint64_t seed) {
   return guarded([&] {
-    if (!g || n <= 0) throw ArgError("bad arguments");
-    if (w < 2 * g->cfg.width || h < 2 * g->cfg.height) throw ArgError("textures must be at least 2*width x 2*height");
+    if (!g) throw ArgError("bad arguments");
+    check_texture_size(n, w, h);
     g->use();
+    pool_quiesce(g);
+    g->tex_info.clear();
+    g->pool_px = 0;
     const size_t plane = (size_t)w * h;
-    g->pool.reserve(plane * n * sizeof(uchar4));
+    pool_grow(g, plane * n);
     const int chunk = 64;
     for (int i = 0; i < n; i += chunk) {
       ofdg::launch_synth_textures((uchar4*)g->pool.p + (size_t)i * plane, std::min(chunk, n - i), w, h, seed, i, g->stream);
@@ -618,7 +704,16 @@ int ofdg_synth_textures(ofdg_generator* g, int32_t n, int32_t w, int32_t h, uint
     }
     CK(cudaStreamSynchronize(g->stream));
     CK(cudaGetLastError());
-    g->n_tex = n; g->tex_w = w; g->tex_h = h;
+    g->pool_px = plane * n;
+    for (int i = 0; i < n; ++i) pool_register(g, (size_t)i * plane, w, h);
+    pool_publish(g);
+  });
+}
+
+int ofdg_texture_size(const ofdg_generator* g, int32_t index, int32_t* w, int32_t* h) {
+  return guarded([&] {
+    if (!g || !w || !h || index < 0 || index >= g->n_tex) throw ArgError("bad arguments");
+    *w = g->tex_info[index].w; *h = g->tex_info[index].h;
   });
 }
 
@@ -626,12 +721,33 @@ int ofdg_download_texture(ofdg_generator* g, int32_t index, uint8_t* planar_out)
   return guarded([&] {
     if (!g || !planar_out || index < 0 || index >= g->n_tex) throw ArgError("bad arguments");
     g->use();
-    const size_t plane = (size_t)g->tex_w * g->tex_h;
+    const ofdg::TexInfo& ti = g->tex_info[index];
+    const size_t plane = (size_t)ti.w * ti.h;
     g->dbg_planar.reserve(plane * 3);
-    ofdg::launch_rgbx_to_planar((const uchar4*)g->pool.p + (size_t)index * plane, (uint8_t*)g->dbg_planar.p, g->tex_w, g->tex_h, g->stream);
+    ofdg::launch_rgbx_to_planar((const uchar4*)g->pool.p + ti.off, (uint8_t*)g->dbg_planar.p, ti.w, ti.h, g->stream);
     ++g->launches;
     CK(cudaMemcpyAsync(planar_out, g->dbg_planar.p, plane * 3, cudaMemcpyDeviceToHost, g->stream));
     CK(cudaStreamSynchronize(g->stream));
+  });
+}
+
+// The W x H foreground view of a pool texture as the renderer sees it (parity checks).
+int ofdg_download_foreground_view(ofdg_generator* g, int32_t index, uint8_t* planar_out) {
+  return guarded([&] {
+    if (!g || !planar_out || index < 0 || index >= g->n_tex) throw ArgError("bad arguments");
+    g->use();
+    const ofdg::TexInfo& ti = g->tex_info[index];
+    const int W = g->cfg.width, H = g->cfg.height;
+    DevBuf rows;
+    rows.reserve((size_t)W * H * sizeof(uchar4));
+    CK(cudaMemcpy2D(rows.p, (size_t)W * sizeof(uchar4), (const uchar4*)g->pool.p + ti.fg_base, (size_t)ti.fg_pitch * sizeof(uchar4),
+                    (size_t)W * sizeof(uchar4), H, cudaMemcpyDeviceToDevice));
+    g->dbg_planar.reserve((size_t)W * H * 3);
+    ofdg::launch_rgbx_to_planar((const uchar4*)rows.p, (uint8_t*)g->dbg_planar.p, W, H, g->stream);
+    ++g->launches;
+    CK(cudaMemcpyAsync(planar_out, g->dbg_planar.p, (size_t)W * H * 3, cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    rows.release();
   });
 }
 
@@ -1016,7 +1132,7 @@ void philox_run(ofdg_generator* g, int set, uint64_t seed, uint64_t first_sample
   a.mode = g->cfg.mode; a.W = g->cfg.width; a.H = g->cfg.height;
   a.seed = seed; a.first_sample = first_sample;
   a.batch = batch; a.n_fields = 0; a.fg_override = fg_override; a.augment = augment;
-  a.n_tex = g->n_tex; a.tex_w = g->tex_w; a.tex_h = g->tex_h;
+  a.n_tex = g->n_tex; a.tex_info = (const ofdg::TexInfo*)g->tex_info_dev.p;
   a.bp = (ofdg_blueprint*)q.bp.p;
   a.seg_type = (int32_t*)q.seg_type.p; a.seg_x = (float*)q.seg_x.p; a.seg_y = (float*)q.seg_y.p;
   a.obj_nbp = (int*)q.obj_nbp.p; a.obj_nseg = (int*)q.obj_nseg.p; a.n_top = (int*)q.ntop.p;

@@ -34,6 +34,18 @@ struct FlatObject {
   int32_t pad[2];
 };
 
+// One texture of the HBM pool (RGBX8 pixels, textures of any size back to back; TextureCollection,
+// DataGenerator.cpp:117-161). Foreground objects see Texture::getRandomizedCrop(W, H) with its default
+// arguments (DataGenerator.cpp:87-109): the centre W x H window of a texture that is at least W x H,
+// else the whole texture resized to W x H -- that resized copy is made once at upload and lives in the pool too.
+struct TexInfo {
+  uint64_t off;        // first pixel of the raw texture
+  uint64_t fg_base;    // first pixel of the foreground view (W x H): raw + centre-crop origin, or the resized copy
+  int32_t w, h;        // raw size
+  int32_t fg_pitch;    // row pitch of the foreground view in pixels
+  int32_t pad;
+};
+
 // Background texture preparation = Texture::getRandomizedCrop(2W, 2H, rot, zoom, sx, sy)
 // (DataGenerator.cpp:87-109) restated as closed-form per-pixel parameters.
 struct BgPrep {
@@ -46,6 +58,8 @@ struct BgPrep {
   int32_t crop_x0, crop_y0;          // crop origin in the rotated image
   int32_t crop_w, crop_h;            // crop size (then resized to 2W x 2H)
   int32_t need[4];                   // {x0, y0, x1, y1}: part of the prepared texture the renderer reads
+  int32_t general;                   // the crop is more than 1.3x the prepared size on an axis (textures smaller than 2W x 2H
+  int32_t pad;                       //   skip the crop, DataGenerator.cpp:103-107): sub-tiled path with unbounded tap counts
 };
 
 struct FlatSample {

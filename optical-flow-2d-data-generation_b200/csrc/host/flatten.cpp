@@ -106,10 +106,9 @@ float cimg_modf(float x, float m) {
 
 void prepare_background(const ofdg_blueprint& b, const FlattenConfig& cfg, const Affine& tex_inv,
                         bool deformed, BgPrep& p) {
-  const int W = cfg.W, H = cfg.H, w = cfg.tex_w, h = cfg.tex_h, tw = 2 * W, th = 2 * H;
-  if (!(w >= tw && h >= th))
-    throw std::runtime_error("texture pool images must be at least 2W x 2H (the reference's small-texture branch is not supported)");
+  const int W = cfg.W, H = cfg.H, tw = 2 * W, th = 2 * H;
   p.tex = (int32_t)((unsigned)b.tex_id % (unsigned)cfg.n_tex);
+  const int w = cfg.tex_info[p.tex].w, h = cfg.tex_info[p.tex].h;
   p.shift_x = b.tex_shift_x;
   p.shift_y = b.tex_shift_y;
   // CImg get_rotate(angle, 1, 3): SURVEY App. B.5
@@ -131,17 +130,25 @@ void prepare_background(const ofdg_blueprint& b, const FlattenConfig& cfg, const
   p.h2 = 0.5f * (unsigned)(h - 1);
   p.rw2 = 0.5f * (unsigned)(p.rw - 1);
   p.rh2 = 0.5f * (unsigned)(p.rh - 1);
-  // crop(width/2-tex_w/2, height/2-tex_h/2, width/2-tex_w/2+tex_w/zoom-1, ..., 3), DG.cpp:99-102
-  const float zoom = b.tex_scale;
-  const int x0 = w / 2 - tw / 2, y0 = h / 2 - th / 2;
-  const int x1 = (int)(w / 2 - tw / 2 + tw / zoom - 1);
-  const int y1 = (int)(h / 2 - th / 2 + th / zoom - 1);
-  p.crop_x0 = std::min(x0, x1);
-  p.crop_y0 = std::min(y0, y1);
-  p.crop_w = std::abs(x1 - x0) + 1;
-  p.crop_h = std::abs(y1 - y0) + 1;
-  if (p.crop_w * 10 > tw * 13 || p.crop_h * 10 > th * 13 || p.crop_w < 2 || p.crop_h < 2)
-    throw std::runtime_error("background texture zoom outside the supported range (crop must stay within 1.3x of 2W x 2H)");
+  if (w >= tw && h >= th) {
+    // crop(width/2-tex_w/2, height/2-tex_h/2, width/2-tex_w/2+tex_w/zoom-1, ..., 3), DG.cpp:99-102
+    const float zoom = b.tex_scale;
+    const int x0 = w / 2 - tw / 2, y0 = h / 2 - th / 2;
+    const int x1 = (int)(w / 2 - tw / 2 + tw / zoom - 1);
+    const int y1 = (int)(h / 2 - th / 2 + th / zoom - 1);
+    p.crop_x0 = std::min(x0, x1);
+    p.crop_y0 = std::min(y0, y1);
+    p.crop_w = std::abs(x1 - x0) + 1;
+    p.crop_h = std::abs(y1 - y0) + 1;
+  } else {
+    // a texture smaller than 2W x 2H is not cropped: the whole rotated image is resized (DG.cpp:103-107)
+    p.crop_x0 = 0; p.crop_y0 = 0;
+    p.crop_w = p.rw; p.crop_h = p.rh;
+  }
+  if (p.crop_w < 2 || p.crop_h < 2) throw std::runtime_error("background texture crop degenerates to less than 2 pixels");
+  if (p.crop_w > 40 * tw || p.crop_h > 40 * th) throw std::runtime_error("background texture more than 40x larger than the prepared size");
+  p.general = (p.crop_w * 10 > tw * 13 || p.crop_h * 10 > th * 13) ? 1 : 0;
+  p.pad = 0;
 
   // Part of the prepared texture the renderer touches: the centre W x H window (frame 0)
   // plus the footprint of the frame-1 warp (4 taps around tex_inv * pixel centre).

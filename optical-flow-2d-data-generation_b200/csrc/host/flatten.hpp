@@ -27,7 +27,7 @@ struct FlatBatch {
 
 struct FlattenConfig {
   int W = 512, H = 384;      // output size (DGEN_WIDTH / DGEN_HEIGHT)
-  int tex_w = 0, tex_h = 0;  // pool texture size
+  const TexInfo* tex_info = nullptr;  // pool textures (sizes), n_tex entries
   int n_tex = 0;             // pool size
   int mode = 1;              // only mode 9 attaches warp fields
   int n_fields = 0;          // injected field pool

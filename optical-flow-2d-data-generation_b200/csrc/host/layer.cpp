@@ -1,5 +1,6 @@
 // See layer.hpp / caffe_shim.hpp.
 #include "layer.hpp"
+#include "texture_io.hpp"
 
 #include <cuda_runtime.h>
 
@@ -207,53 +208,6 @@ LayerParameter ParseLayerPrototxt(const std::string& text) {
 template <typename Dtype>
 int DataGenerationLayer<Dtype>::solver_rank_ = 0;
 
-namespace {
-// Loads a texture list: one binary PPM (P6, maxval 255) path per line, like the reference's
-// TextureCollection ctor (DataGenerator.cpp:117-149) including its R<->B swap. Other image formats
-// need an image decoder the reference gets from CImg; they are rejected with a clear message.
-void load_ppm_list(const std::string& listfile, std::vector<unsigned char>& planar, int& n, int& w, int& h) {
-  std::ifstream infile(listfile);
-  if (infile.bad() || !infile.is_open()) throw std::runtime_error("Could not open texture collection");  // DataGenerator.cpp:121
-  std::string path;
-  n = 0; w = h = 0;
-  while (std::getline(infile, path)) {
-    if (path.empty()) continue;
-    std::ifstream f(path, std::ios::binary);
-    if (!f.is_open()) throw std::runtime_error("Could not open texture " + path);
-    std::string magic;
-    f >> magic;
-    if (magic != "P6") throw std::runtime_error("texture " + path + ": only binary PPM (P6) textures can be decoded without CImg");
-    auto next_int = [&]() {
-      for (;;) {
-        int c = f.peek();
-        if (c == '#') { std::string skip; std::getline(f, skip); }
-        else if (std::isspace(c)) f.get();
-        else break;
-      }
-      int v; f >> v; return v;
-    };
-    int tw = next_int(), th = next_int(), maxv = next_int();
-    f.get();
-    if (maxv != 255) throw std::runtime_error("texture " + path + ": maxval must be 255");
-    if (n == 0) { w = tw; h = th; }
-    else if (tw != w || th != h) throw std::runtime_error("texture " + path + ": all pool textures must share one size");
-    std::vector<unsigned char> rgb((size_t)tw * th * 3);
-    f.read((char*)rgb.data(), rgb.size());
-    if (!f) throw std::runtime_error("texture " + path + ": truncated file");
-    const size_t plane = (size_t)tw * th;
-    planar.resize((size_t)(n + 1) * 3 * plane);
-    unsigned char* dst = planar.data() + (size_t)n * 3 * plane;
-    for (size_t i = 0; i < plane; ++i) {
-      dst[0 * plane + i] = rgb[3 * i + 2];  // std::swap(c0, c2): the reference holds textures as B,G,R planes
-      dst[1 * plane + i] = rgb[3 * i + 1];
-      dst[2 * plane + i] = rgb[3 * i + 0];
-    }
-    ++n;
-  }
-  if (n == 0) throw std::runtime_error("texture collection is empty");
-}
-}  // namespace
-
 template <typename Dtype>
 DataGenerationLayer<Dtype>::DataGenerationLayer(const LayerParameter& param) : Layer<Dtype>(param) {
   const DataGenerationParameter& gp = param.data_generation_param();
@@ -274,10 +228,12 @@ DataGenerationLayer<Dtype>::DataGenerationLayer(const LayerParameter& param) : L
     if (std::sscanf(db.c_str() + 10, "%d:%llu", &count, &seed) < 1 || count <= 0) throw std::runtime_error("bad synthetic texture spec: " + db);
     OFDG_CHECK(ofdg_synth_textures(generator_, count, 2 * cfg.width, 2 * cfg.height, seed));
   } else {
-    std::vector<unsigned char> planar;
-    int n, w, h;
-    load_ppm_list(db, planar, n, w, h);
-    OFDG_CHECK(ofdg_upload_textures(generator_, planar.data(), n, w, h));
+    // TextureCollection ctor, DataGenerator.cpp:117-149: every image the list names, whatever its size
+    OFDG_CHECK(ofdg_clear_textures(generator_));
+    for (const std::string& path : ofdg::read_texture_list(db)) {
+      const ofdg::TextureImage t = ofdg::load_texture_file(path);
+      OFDG_CHECK(ofdg_add_textures(generator_, t.planar_bgr.data(), 1, t.w, t.h));
+    }
   }
   OFDG_CHECK(ofdg_params_create(gp.mode(), cfg.width, cfg.height, 45 * solver_rank_, 0, 0, &params_));
   OFDG_CHECK(ofdg_tasks_create(&tasks_));
@@ -455,6 +411,18 @@ int layer_guard(F&& f) {
 
 extern "C" {
 const char* ofdg_layer_last_error(void) { return g_layer_error.c_str(); }
+
+int ofdg_decode_texture_file(const char* path, int32_t* w, int32_t* h, uint8_t* planar_bgr, uint64_t cap) {
+  return layer_guard([&] {
+    if (!path || !w || !h) throw std::runtime_error("null pointer");
+    const ofdg::TextureImage t = ofdg::load_texture_file(path);
+    *w = t.w; *h = t.h;
+    if (planar_bgr) {
+      if (cap < t.planar_bgr.size()) throw std::runtime_error("buffer too small");
+      std::memcpy(planar_bgr, t.planar_bgr.data(), t.planar_bgr.size());
+    }
+  });
+}
 
 int ofdg_layer_parse_prototxt(const char* text, int32_t* ints /*[7]: batch,prefetch,mode,first,second,aa,n_top*/, char* texture_db, int32_t cap,
                               char* type, int32_t type_cap) {

@@ -408,8 +408,9 @@ __device__ float cimg_mod_dev(float x, float m) {
 }
 
 __device__ void prepare_bg(const PhiloxArgs& a, const ofdg_blueprint& b, const Affine& tex_inv, bool deformed, BgPrep& p) {
-  const int W = a.W, H = a.H, w = a.tex_w, h = a.tex_h, tw = 2 * W, th = 2 * H;
+  const int W = a.W, H = a.H, tw = 2 * W, th = 2 * H;
   p.tex = (int)((unsigned)b.tex_id % (unsigned)a.n_tex);
+  const int w = a.tex_info[p.tex].w, h = a.tex_info[p.tex].h;
   p.shift_x = b.tex_shift_x; p.shift_y = b.tex_shift_y;
   const float nangle = cimg_mod_dev(b.tex_rot, 360.0f);
   p.rot_identity = (cimg_mod_dev(nangle, 90.0f) == 0) ? 1 : 0;
@@ -423,11 +424,18 @@ __device__ void prepare_bg(const PhiloxArgs& a, const ofdg_blueprint& b, const A
   }
   p.w2 = 0.5f * (unsigned)(w - 1); p.h2 = 0.5f * (unsigned)(h - 1);
   p.rw2 = 0.5f * (unsigned)(p.rw - 1); p.rh2 = 0.5f * (unsigned)(p.rh - 1);
-  const float zoom = b.tex_scale;
-  const int x0 = w / 2 - tw / 2, y0 = h / 2 - th / 2;
-  const int x1 = (int)(w / 2 - tw / 2 + tw / zoom - 1), y1 = (int)(h / 2 - th / 2 + th / zoom - 1);
-  p.crop_x0 = min(x0, x1); p.crop_y0 = min(y0, y1);
-  p.crop_w = abs(x1 - x0) + 1; p.crop_h = abs(y1 - y0) + 1;
+  if (w >= tw && h >= th) {
+    const float zoom = b.tex_scale;
+    const int x0 = w / 2 - tw / 2, y0 = h / 2 - th / 2;
+    const int x1 = (int)(w / 2 - tw / 2 + tw / zoom - 1), y1 = (int)(h / 2 - th / 2 + th / zoom - 1);
+    p.crop_x0 = min(x0, x1); p.crop_y0 = min(y0, y1);
+    p.crop_w = abs(x1 - x0) + 1; p.crop_h = abs(y1 - y0) + 1;
+  } else {  // smaller than 2W x 2H: the whole rotated image is resized (DG.cpp:103-107)
+    p.crop_x0 = 0; p.crop_y0 = 0; p.crop_w = p.rw; p.crop_h = p.rh;
+  }
+  p.crop_w = max(2, min(p.crop_w, 40 * tw)); p.crop_h = max(2, min(p.crop_h, 40 * th));  // the host path rejects these; stay in bounds here
+  p.general = (p.crop_w * 10 > tw * 13 || p.crop_h * 10 > th * 13) ? 1 : 0;
+  p.pad = 0;
   int nx0 = W / 2, ny0 = H / 2, nx1 = W / 2 + W - 1, ny1 = H / 2 + H - 1;
   if (deformed) { nx0 = 0; ny0 = 0; nx1 = tw - 1; ny1 = th - 1; }
   else {

@@ -28,7 +28,8 @@ struct PhiloxArgs {
   int mode, W, H;
   uint64_t seed, first_sample;
   int batch, n_fields, fg_override, augment;
-  int n_tex, tex_w, tex_h;
+  int n_tex;
+  const TexInfo* tex_info;  // device: pool texture sizes
   // blueprints in the ABI layout, fixed strides per sample (downloadable for inspection / the oracle)
   ofdg_blueprint* bp;   // [batch][kPhiloxMaxBp]: background, then kPhiloxMaxShapes slots per object
   int32_t* seg_type;    // [batch][kPhiloxMaxSeg]: 160 per object

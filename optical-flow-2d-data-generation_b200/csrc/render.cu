@@ -252,7 +252,8 @@ constexpr int MAX_PAIRS = 1024;  // (edge, tile row) work items listed per chunk
 struct HitObject {             // what the per-pixel stage needs of a FlatObject, staged in shared memory
   int obj;                     // index within the sample (z-order)
   int shape_begin, shape_count;
-  int tex;
+  int fg_pitch;                // foreground view of the object's texture (TexInfo): row pitch in pixels,
+  unsigned long long fg_base;  //   first pixel in the pool
   int composite;
   int field;                   // mode 9 field id or -1
 };
@@ -340,7 +341,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
       if (lane < binned && idx >= obj0) {
         const FlatObject* ob = a.objects + obj_begin + idx;
         HitObject h;
-        h.obj = idx; h.shape_begin = ob->shape_begin; h.shape_count = ob->shape_count; h.tex = ob->tex;
+        const TexInfo& ti = a.tex_info[ob->tex];
+        h.obj = idx; h.shape_begin = ob->shape_begin; h.shape_count = ob->shape_count;
+        h.fg_pitch = ti.fg_pitch; h.fg_base = ti.fg_base;
         h.composite = ob->composite; h.field = ob->field;
         s_hit[lane - skip] = h;
       }
@@ -355,7 +358,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
         const int pos = nh + __popc(bal & ((1u << lane) - 1u));
         if (hit && pos < MAX_HITS) {
           HitObject h;
-          h.obj = idx; h.shape_begin = ob->shape_begin; h.shape_count = ob->shape_count; h.tex = ob->tex;
+          const TexInfo& ti = a.tex_info[ob->tex];
+          h.obj = idx; h.shape_begin = ob->shape_begin; h.shape_count = ob->shape_count;
+          h.fg_pitch = ti.fg_pitch; h.fg_base = ti.fg_base;
           h.composite = ob->composite; h.field = ob->field;
           s_hit[pos] = h;
         }
@@ -458,7 +463,6 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
     }
   }
 
-  const int tex_ox = a.tex_w / 2 - W / 2, tex_oy = a.tex_h / 2 - H / 2;  // centre crop, DG.cpp:99-102 with defaults
   uint32_t uaa[2] = {0, 0}, una[2] = {0, 0};  // masks of the object being assembled: [frame], 4 pixels x 1 byte
 
   // ---- foreground objects in z-order, in passes of at most MAX_HITS objects / MAX_JOBS outlines
@@ -592,9 +596,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
         id1 = (id1 & ~e1) | (kk & e1);
         const uint32_t m0w = a.use_aa ? uaa[0] : una[0], m1w = a.use_aa ? uaa[1] : una[1];
         if ((m0w | m1w) == 0u) continue;
-        const uchar4* tex = a.pool + (size_t)ho.tex * a.tex_w * a.tex_h;
+        const uchar4* tex = a.pool + ho.fg_base;  // the W x H foreground view (centre crop, DG.cpp:99-102 with defaults, or the resized copy)
         if (m0w) {
-          const uchar4* trow = tex + (size_t)(y + tex_oy) * a.tex_w + (x0 + tex_ox);  // identity warp == copy
+          const uchar4* trow = tex + (size_t)y * ho.fg_pitch + x0;  // identity warp == copy
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const unsigned m0 = (m0w >> (8 * i)) & 255u;
@@ -607,7 +611,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const unsigned m1 = (m1w >> (8 * i)) & 255u;
-            if (m1) col1[i] = blend_rgbx(col1[i], bilinear_rgbx_call(tex + (size_t)tex_oy * a.tex_w + tex_ox, a.tex_w, W, H, W, rw.dx.v1, rw.dx.lft, rw.dx.rem, rw.dy.v1, rw.dy.lft, rw.dy.rem, x0 + i), m1);
+            if (m1) col1[i] = blend_rgbx(col1[i], bilinear_rgbx_call(tex, ho.fg_pitch, W, H, W, rw.dx.v1, rw.dx.lft, rw.dx.rem, rw.dy.v1, rw.dy.lft, rw.dy.rem, x0 + i), m1);
           }
         } else if (kDeform && m1w) {
           // applyWarpFieldToTexture(getTransformedTexture(tex0, M), iflow) evaluated where the mask is set:
@@ -619,7 +623,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
             if (px < 0 || py < 0 || px >= W || py >= H) return 0u;
             RowWarp rw;
             rw.init(tinv, (double)py, W);
-            return bilinear_rgbx(tex, a.tex_w, tex_ox, tex_oy, W, H, rw, px);
+            return bilinear_rgbx(tex, ho.fg_pitch, 0, 0, W, H, rw, px);
           };
           for (int i = 0; i < 4; ++i) {
             const unsigned m1 = (m1w >> (8 * i)) & 255u;
@@ -847,7 +851,7 @@ __global__ void resize_tables_kernel(int* pos_all, double* alpha_all, int n) {
 }
 
 constexpr int PT = 32;        // prepared-texture tile edge
-constexpr int PS = 46;        // source tile edge: ceil(32 * 1.25) + slack  (zoom >= 0.8 => crop <= 1.25 * 2W)
+constexpr int PS = 46;        // source tile edge: ceil(32 * 1.3) + slack  (zoom >= 0.8 => crop <= 1.25 * 2W; larger ratios: bg_prep_general)
 constexpr int PREP_THREADS = 256;
 
 // cimg::mod(float x, float m) = (float)(dx - dm * floor(dx / dm)) in double. For 0 <= x < m the quotient's
@@ -949,6 +953,73 @@ __device__ __forceinline__ void source_range(int len, int n, int t0, int t1, con
   else { s0 = pos[t0]; s1 = min(pos[t1] + 1, len - 1); }
 }
 
+// One output index of a resize pass with any number of taps (general path; the fast path hoists its <= 3 taps).
+__device__ __noinline__ uint32_t resize_general(const uint32_t* src, int stride, int s0, int len, int n, int t, const int* pos, const double* alpha) {
+  if (len == n) return src[(t - s0) * stride];
+  uint32_t out = 0;
+  if (len > n) {  // moving average: float accumulation in source order, then one division (CImg interpolation 2)
+    const unsigned lo = (unsigned)t * (unsigned)len, hi = lo + (unsigned)len;
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (unsigned sidx = lo / (unsigned)n; sidx * (unsigned)n < hi; ++sidx) {
+      const unsigned b0 = max(sidx * (unsigned)n, lo), e0 = min((sidx + 1u) * (unsigned)n, hi);
+      const float wgt = (float)(e0 - b0);
+      const uint32_t px = src[((int)sidx - s0) * stride];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] += byte_to_float(px, c) * wgt;
+    }
+    const float flen = (float)(unsigned int)len;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out |= ((uint32_t)(unsigned char)(acc[c] / flen)) << (8 * c);
+    return out;
+  }
+  const int first = pos[t];
+  const double al = alpha[t];
+  const uint32_t p1 = src[(first - s0) * stride], p2 = first < len - 1 ? src[(first + 1 - s0) * stride] : p1;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double v = (1 - al) * (double)(int)((p1 >> (8 * c)) & 255u) + al * (double)(int)((p2 >> (8 * c)) & 255u);
+    out |= ((uint32_t)(unsigned char)v) << (8 * c);
+  }
+  return out;
+}
+
+constexpr int PS_PITCH = PS;
+
+// General path of the background preparation: the 32 x 32 output tile is cut into sub-tiles small enough for their
+// source pixels to fit the shared staging area, whatever the resize ratio (textures smaller than 2W x 2H are resized
+// whole, DataGenerator.cpp:103-107; rotated, they can be several times larger than 2W x 2H along one axis).
+__device__ __noinline__ void bg_prep_general(const RenderArgs& a, const BgPrep& p, const uchar4* tex, int tex_w, int tex_h, int X0, int Y0, int X1, int Y1,
+                                             const int* pos_x, const double* alpha_x, const int* pos_y, const double* alpha_y,
+                                             uint32_t (*sA)[PS_PITCH], uint32_t (*sB)[PT], uchar4* out) {
+  const int W2 = 2 * a.W, H2 = 2 * a.H;
+  const int sub_w = p.crop_w > W2 ? max(1, min(PT, (int)(((long long)(PS - 2) * W2) / p.crop_w))) : PT;
+  const int sub_h = p.crop_h > H2 ? max(1, min(PT, (int)(((long long)(PS - 2) * H2) / p.crop_h))) : PT;
+  for (int ya = Y0; ya <= Y1; ya += sub_h)
+    for (int xa = X0; xa <= X1; xa += sub_w) {
+      const int xb = min(xa + sub_w - 1, X1), yb = min(ya + sub_h - 1, Y1);
+      int cx0, cx1, cy0, cy1;
+      source_range(p.crop_w, W2, xa, xb, pos_x, cx0, cx1);
+      source_range(p.crop_h, H2, ya, yb, pos_y, cy0, cy1);
+      const int cw = cx1 - cx0 + 1, ch = cy1 - cy0 + 1, tw = xb - xa + 1, th = yb - ya + 1;
+      __syncthreads();  // the previous sub-tile is done with the staging area
+      for (int i = threadIdx.x; i < cw * ch; i += PREP_THREADS) {
+        const int lx = i % cw, ly = i / cw;
+        sA[ly][lx] = rotated_px(tex, tex_w, tex_h, p, mirror(p.crop_x0 + cx0 + lx, p.rw), mirror(p.crop_y0 + cy0 + ly, p.rh));
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < tw * ch; i += PREP_THREADS) {
+        const int lx = i % tw, ly = i / tw;
+        sB[ly][lx] = resize_general(&sA[ly][0], 1, cx0, p.crop_w, W2, xa + lx, pos_x, alpha_x);
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < tw * th; i += PREP_THREADS) {
+        const int lx = i % tw, ly = i / tw;
+        const uint32_t v = resize_general(&sB[0][lx], PT, cy0, p.crop_h, H2, ya + ly, pos_y, alpha_y);
+        *reinterpret_cast<uint32_t*>(out + (size_t)(ya + ly) * W2 + xa + lx) = v;
+      }
+    }
+}
+
 __global__ void __launch_bounds__(PREP_THREADS) bg_prep_kernel(RenderArgs a) {
   __shared__ uint32_t sA[PS][PS];  // rotated + cropped source pixels
   __shared__ uint32_t sB[PS][PT];  // after the x pass
@@ -963,11 +1034,17 @@ __global__ void __launch_bounds__(PREP_THREADS) bg_prep_kernel(RenderArgs a) {
   const double* alpha_x = a.alpha_x + (size_t)min(p.crop_w, W2 - 1) * W2;
   const int* pos_y = a.pos_y + (size_t)min(p.crop_h, H2 - 1) * H2;
   const double* alpha_y = a.alpha_y + (size_t)min(p.crop_h, H2 - 1) * H2;
+  const TexInfo ti = a.tex_info[p.tex];
+  const uchar4* tex = a.pool + ti.off;
+  uchar4* out = a.bg + (size_t)sample * W2 * H2;
+  if (p.general) {
+    bg_prep_general(a, p, tex, ti.w, ti.h, X0, Y0, X1, Y1, pos_x, alpha_x, pos_y, alpha_y, sA, sB, out);
+    return;
+  }
   int cx0, cx1, cy0, cy1;
   source_range(p.crop_w, W2, X0, X1, pos_x, cx0, cx1);
   source_range(p.crop_h, H2, Y0, Y1, pos_y, cy0, cy1);
   const int cw = cx1 - cx0 + 1, ch = cy1 - cy0 + 1;  // <= PS by construction
-  const uchar4* tex = a.pool + (size_t)p.tex * a.tex_w * a.tex_h;
   const int tw = X1 - X0 + 1, th = Y1 - Y0 + 1;
   if ((int)threadIdx.x < th) sTy[threadIdx.x] = make_taps(p.crop_h, H2, Y0 + (int)threadIdx.x, pos_y, alpha_y);  // visible after the barriers below
   // A: crop(x0, y0, .., mirror) of the rotated image
@@ -976,7 +1053,7 @@ __global__ void __launch_bounds__(PREP_THREADS) bg_prep_kernel(RenderArgs a) {
     const int step_y = PREP_THREADS / cw, step_x = PREP_THREADS % cw;
     int lx = (int)threadIdx.x % cw, ly = (int)threadIdx.x / cw;
     while (ly < ch) {
-      sA[ly][lx] = rotated_px(tex, a.tex_w, a.tex_h, p, mirror(p.crop_x0 + cx0 + lx, p.rw), mirror(p.crop_y0 + cy0 + ly, p.rh));
+      sA[ly][lx] = rotated_px(tex, ti.w, ti.h, p, mirror(p.crop_x0 + cx0 + lx, p.rw), mirror(p.crop_y0 + cy0 + ly, p.rh));
       lx += step_x; ly += step_y;
       if (lx >= cw) { lx -= cw; ++ly; }
     }
@@ -989,12 +1066,39 @@ __global__ void __launch_bounds__(PREP_THREADS) bg_prep_kernel(RenderArgs a) {
   }
   __syncthreads();
   // P: resize along y
-  uchar4* out = a.bg + (size_t)sample * W2 * H2;
   if (lane_x < tw)
     for (int ly = lane_y; ly < th; ly += PREP_THREADS / 32) {
       const uint32_t v = apply_taps(&sB[0][lane_x], PT, cy0, p.crop_h, sTy[ly]);
       *reinterpret_cast<uint32_t*>(out + (size_t)(Y0 + ly) * W2 + X0 + lane_x) = v;
     }
+}
+
+// Foreground view of a texture smaller than W x H: the whole texture resized (getRandomizedCrop's else branch with
+// its default arguments, DataGenerator.cpp:103-107; shift 0 and angle 0 are copies). One-time, at upload.
+__global__ void resize_table_kernel(int* pos, double* alpha, int len, int n) {  // CImg linear-resize table len -> n (len < n)
+  if (threadIdx.x || blockIdx.x) return;
+  const double f = n > 1 ? (len - 1.0) / (n - 1) : 0;
+  double curr = 0, old = 0;
+  unsigned q = 0;
+  for (int i = 0; i < n; ++i) {
+    alpha[i] = curr - (unsigned int)curr;
+    pos[i] = (int)q;
+    old = curr;
+    curr = fmin(len - 1.0, curr + f);
+    q += (unsigned int)curr - (unsigned int)old;
+  }
+}
+__global__ void fg_resize_x_kernel(const uchar4* tex, int w, int h, int W, uint32_t* tmp, const int* pos, const double* alpha) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= W * h) return;
+  const int X = i % W, sy = i / W;
+  tmp[i] = resize_general(reinterpret_cast<const uint32_t*>(tex) + (size_t)sy * w, 1, 0, w, W, X, pos, alpha) & 0xFFFFFFu;
+}
+__global__ void fg_resize_y_kernel(const uint32_t* tmp, int h, int W, int H, uchar4* out, const int* pos, const double* alpha) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= W * H) return;
+  const int X = i % W, Y = i / W;
+  reinterpret_cast<uint32_t*>(out)[i] = resize_general(tmp + X, W, 0, h, H, Y, pos, alpha);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1083,6 +1187,16 @@ int launch_scene_upload(const UploadSegments& u, cudaStream_t s) {
 
 void launch_composite_luts(uint8_t* add_lut, uint8_t* sub_lut, cudaStream_t s) {
   composite_lut_kernel<<<256, 256, 0, s>>>(add_lut, sub_lut);
+}
+
+int launch_fg_resize(const uchar4* tex, int w, int h, int W, int H, uchar4* out, uint32_t* tmp, int* pos, double* alpha, cudaStream_t s) {
+  // tmp: W x h pixels; pos / alpha: max(W, H) entries each (reused by the two passes, stream-ordered)
+  int launches = 0;
+  if (w < W) { resize_table_kernel<<<1, 1, 0, s>>>(pos, alpha, w, W); ++launches; }
+  fg_resize_x_kernel<<<(W * h + 255) / 256, 256, 0, s>>>(tex, w, h, W, tmp, pos, alpha);
+  if (h < H) { resize_table_kernel<<<1, 1, 0, s>>>(pos, alpha, h, H); ++launches; }
+  fg_resize_y_kernel<<<(W * H + 255) / 256, 256, 0, s>>>(tmp, h, W, H, out, pos, alpha);
+  return launches + 2;
 }
 
 void launch_resize_tables(int* pos, double* alpha, int n, cudaStream_t s) {

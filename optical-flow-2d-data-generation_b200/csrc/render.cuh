@@ -16,9 +16,9 @@ struct RenderArgs {
   int batch;
   int W, H;          // output size
   int use_aa;
-  // texture pool: RGBX8 interleaved, [n][tex_h][tex_w]
+  // texture pool: RGBX8 interleaved, textures of any size back to back, described by tex_info[n]
   const uchar4* pool;
-  int tex_w, tex_h;
+  const TexInfo* tex_info;
   // per-sample prepared background texture, RGBX8 [batch][2H][2W]
   uchar4* bg;
   // CImg linear-resize tables for every source length: row `len` of pos_x/alpha_x ([2W][2W]) describes len -> 2W
@@ -67,6 +67,8 @@ int launch_background_prep(const RenderArgs& a, cudaStream_t s);
 int launch_render(const RenderArgs& a, cudaStream_t s);  // + the occlusion pass when a.occlusion is set
 int launch_deform_prepass(const RenderArgs& a, cudaStream_t s);  // mode 9 only; no-op when n_deform == 0
 
+// Foreground view (W x H) of a texture smaller than W x H, CImg linear resize; tmp holds W x h pixels, pos / alpha max(W, H) entries.
+int launch_fg_resize(const uchar4* tex, int w, int h, int W, int H, uchar4* out, uint32_t* tmp, int* pos, double* alpha, cudaStream_t s);
 void launch_resize_tables(int* pos, double* alpha, int n, cudaStream_t s);  // one-time, all lengths 1..n-1 -> n
 // Scene upload without the copy engines: one kernel pulls the flattened arrays out of mapped pinned host memory.
 // (In the host-blob pipeline the copy engine is busy with large device-to-host copies; a small host-to-device

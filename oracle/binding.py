@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "liboracle.so")
 class OracleConfig(C.Structure):
     _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("mode", C.c_int32), ("use_antialiasing", C.c_int32),
                 ("n_tex", C.c_int32), ("tex_w", C.c_int32), ("tex_h", C.c_int32), ("n_fields", C.c_int32),
-                ("n_threads", C.c_int32), ("faithful_copies", C.c_int32)]
+                ("n_threads", C.c_int32), ("faithful_copies", C.c_int32), ("tex_sizes", C.c_void_p), ("tex_offsets", C.c_void_p)]
 
 
 class OracleDebug(C.Structure):
@@ -48,10 +48,20 @@ def _p(a):
 
 def render(task_struct, textures, W=512, H=384, mode=1, use_aa=True, fields=None, n_threads=8, faithful=False,
            debug=False, max_objs=24):
-    """task_struct: ofdg_b200.TaskBatchStruct (same C layout). textures: n x 3 x th x tw uint8."""
-    textures = np.ascontiguousarray(textures, np.uint8)
-    n_tex, _, th, tw = textures.shape
-    cfg = OracleConfig(W, H, mode, int(use_aa), n_tex, tw, th, 0 if fields is None else fields.shape[0], n_threads, int(faithful))
+    """task_struct: ofdg_b200.TaskBatchStruct (same C layout). textures: n x 3 x th x tw uint8, or a list of
+    3 x h x w uint8 arrays of different sizes."""
+    sizes = offsets = None
+    if isinstance(textures, (list, tuple)):
+        parts = [np.ascontiguousarray(t, np.uint8) for t in textures]
+        sizes = np.array([[t.shape[2], t.shape[1]] for t in parts], np.int32)
+        offsets = np.cumsum([0] + [t.size for t in parts[:-1]]).astype(np.uint64)
+        textures = np.concatenate([t.ravel() for t in parts])
+        n_tex, th, tw = len(parts), 0, 0
+    else:
+        textures = np.ascontiguousarray(textures, np.uint8)
+        n_tex, _, th, tw = textures.shape
+    cfg = OracleConfig(W, H, mode, int(use_aa), n_tex, tw, th, 0 if fields is None else fields.shape[0], n_threads, int(faithful),
+                       None if sizes is None else sizes.ctypes.data, None if offsets is None else offsets.ctypes.data)
     n = task_struct.n_tasks
     out = {"img0": np.empty((n, 3, H, W), np.float32), "img1": np.empty((n, 3, H, W), np.float32),
            "flow": np.empty((n, 2, H, W), np.float32)}

@@ -903,6 +903,7 @@ struct MovingObject {
 static Img<u8> pool_texture(const Ctx& c, int raw_index) {  // TextureCollection::getTexturePtr, DG.cpp:158-161
   const oracle_config& g = *c.cfg;
   const size_t idx = (size_t)raw_index % (size_t)g.n_tex;
+  if (g.tex_sizes) return Img<u8>::wrap(c.textures + g.tex_offsets[idx], g.tex_sizes[2 * idx], g.tex_sizes[2 * idx + 1], 3);
   return Img<u8>::wrap(c.textures + idx * (size_t)g.tex_w * g.tex_h * 3, g.tex_w, g.tex_h, 3);
 }
 static void load_field(const Ctx& c, int id, Img<float>& flow, Img<float>& iflow) {
@@ -953,9 +954,10 @@ static std::unique_ptr<MovingObject> realize(const Ctx& c, const ofdg_task_batch
   }
   if (!parent || c.faithful) {  // components crop a texture they never use
     if (c.faithful) o->textures.push_back(randomized_crop(pool_texture(c, p.tex_id), c.W, c.H, 0.f, 1.f, 0, 0));
-    else {  // the default-argument chain is exactly the centre crop
+    else {  // the default-argument chain is exactly the centre crop when the texture is large enough
       Img<u8> t = pool_texture(c, p.tex_id);
-      o->textures.push_back(cimg_get_crop_mirror(t, t.w / 2 - c.W / 2, t.h / 2 - c.H / 2, t.w / 2 - c.W / 2 + c.W - 1, t.h / 2 - c.H / 2 + c.H - 1));
+      if (t.w < c.W || t.h < c.H) o->textures.push_back(randomized_crop(t, c.W, c.H, 0.f, 1.f, 0, 0));
+      else o->textures.push_back(cimg_get_crop_mirror(t, t.w / 2 - c.W / 2, t.h / 2 - c.H / 2, t.w / 2 - c.W / 2 + c.W - 1, t.h / 2 - c.H / 2 + c.H - 1));
     }
   }
   o->set_intrinsic(p.init_rot, p.init_trans_x, p.init_trans_y);

@@ -30,6 +30,11 @@ typedef struct oracle_config {
   int32_t n_fields;             /* mode 9: injected pool of (flow, iflow) pairs, each 2 x (H+1) x (W+1) float */
   int32_t n_threads;            /* first_level_threads */
   int32_t faithful_copies;      /* 1: also perform the reference's redundant whole-image copies (CPU-baseline timing) */
+  /* pools of mixed texture sizes (TextureCollection loads whatever the list names, DataGenerator.cpp:117-149):
+   * when tex_sizes is non-NULL it holds n_tex (w, h) pairs, tex_offsets the byte offset of each planar texture
+   * in `textures`, and tex_w / tex_h are ignored */
+  const int32_t* tex_sizes;
+  const uint64_t* tex_offsets;
 } oracle_config;
 
 /* Optional debug outputs (NULL to skip). Layouts:

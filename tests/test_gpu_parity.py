@@ -317,3 +317,51 @@ def test_extra_tops_backward_flow_ids_occlusion(ofdg, oracle, textures8, fields4
     torch.cuda.synchronize()
     assert float(bw.min()) == -9.0
     g.close()
+
+
+def _mixed_pool(ofdg):
+    """Textures of six sizes: every branch of Texture::getRandomizedCrop (DataGenerator.cpp:87-109) for 512 x 384 frames."""
+    sizes = [(1024, 768),   # >= 2W x 2H: background crop + resize, foreground centre crop
+             (300, 200),    # smaller than W x H: foreground resized up on both axes; background resized whole
+             (640, 480),    # >= W x H but < 2W x 2H: foreground crop, background resized whole (growing)
+             (1500, 500),   # wide and flat: background resized whole, shrinking along x (many taps), growing along y
+             (400, 900),    # narrow and tall: foreground x grows / y shrinks 2.3x; background likewise
+             (2600, 2000)]  # much larger than 2W x 2H: crop path with far-away origins
+    return [ofdg.synth_textures(1, w, h, seed=20 + i)[0] for i, (w, h) in enumerate(sizes)]
+
+
+def test_mixed_size_pool_views_and_backgrounds(ofdg, oracle):
+    g = _gen(ofdg, 7)
+    pool = _mixed_pool(ofdg)
+    g.upload_textures(pool)
+    for i, t in enumerate(pool):
+        assert g.texture_size(i) == (t.shape[2], t.shape[1])
+        assert np.array_equal(g.download_texture(i), t)
+        assert np.array_equal(g.download_foreground_view(i), oracle.randomized_crop(t, 512, 384)), f"foreground view of texture {i}"
+    # backgrounds: force every texture through the background path with the parameters the stream drew
+    tasks = ofdg.ParamStream(7).generate(12)
+    a = tasks.arrays()
+    for t in range(12):
+        a["blueprints"]["tex_id"][a["task_begin"][t]] = t % 6
+    tasks = ofdg.Tasks.from_arrays(a)
+    bg, need = g.debug_background(tasks)
+    for t in range(12):
+        b = a["blueprints"][a["task_begin"][t]]
+        ref = oracle.randomized_crop(pool[t % 6], 1024, 768, float(b["tex_rot"]), float(b["tex_scale"]), int(b["tex_shift_x"]), int(b["tex_shift_y"]))
+        x0, y0, x1, y1 = need[t]
+        assert np.array_equal(bg[t][:, y0:y1 + 1, x0:x1 + 1], ref[:, y0:y1 + 1, x0:x1 + 1]), f"task {t} texture {t % 6}"
+    g.close()
+
+
+def test_mixed_size_pool_render_parity(ofdg, oracle):
+    g = _gen(ofdg, 7)
+    pool = _mixed_pool(ofdg)
+    g.upload_textures(pool)
+    tasks = ofdg.ParamStream(7).generate(8)
+    a = tasks.arrays()
+    used = set(int(v) % 6 for v in a["blueprints"]["tex_id"][a["blueprints"]["parent"] < 0])
+    assert used == set(range(6)), "every pool texture must be in use"
+    gpu = g.render_debug(tasks)
+    cpu = oracle.render(tasks.struct(), pool, mode=7, debug=True)
+    assert _compare(gpu, cpu) <= IMG_TOL
+    g.close()

@@ -51,26 +51,27 @@ def test_layer_blob_contract(ofdg, oracle):
 
 
 @pytest.mark.gpu
-def test_layer_ppm_texture_list(ofdg, oracle, tmp_path):
-    """texture_dbases as a list file of PPM images, with the reference's R<->B swap."""
-    rng = np.random.default_rng(0)
-    tex_rgb = ofdg.synth_textures(2, 1024, 768, seed=9)  # treat planes as R,G,B on disk
-    lines = []
-    for i in range(2):
-        path = tmp_path / f"t{i}.ppm"
-        with open(path, "wb") as f:
-            f.write(b"P6\n# comment\n1024 768\n255\n")
-            f.write(np.ascontiguousarray(tex_rgb[i].transpose(1, 2, 0)).tobytes())
-        lines.append(str(path))
-    (tmp_path / "db.txt").write_text("\n".join(lines) + "\n")
-    layer = ofdg.DataGenerationLayer('layer { type: "DataGeneration" top: "a" top: "b" top: "c" data_param { batch_size: 2 prefetch: 2 } '
+def test_layer_texture_list_of_mixed_files(ofdg, oracle, tmp_path):
+    """texture_dbases as a list file (TextureCollection ctor, DataGenerator.cpp:117-149): a PPM, a PNG and a BMP of three
+    different sizes, with the reference's R<->B swap."""
+    import struct
+    tex = [ofdg.synth_textures(1, w, h, seed=9 + i)[0] for i, (w, h) in enumerate([(1024, 768), (700, 500), (320, 240)])]  # planes = R,G,B on disk
+    rgb = [np.ascontiguousarray(t.transpose(1, 2, 0)) for t in tex]
+    (tmp_path / "t0.ppm").write_bytes(b"P6\n# comment\n1024 768\n255\n" + rgb[0].tobytes())
+    (tmp_path / "t1.png").write_bytes(_png_bytes(rgb[1]))
+    rows = b"".join(rgb[2][y, :, ::-1].tobytes() for y in range(239, -1, -1))
+    (tmp_path / "t2.bmp").write_bytes(b"BM" + struct.pack("<IHHI", 54 + len(rows), 0, 0, 54) +
+                                      struct.pack("<IiiHHIIiiII", 40, 320, 240, 1, 24, 0, len(rows), 2835, 2835, 0, 0) + rows)
+    (tmp_path / "db.txt").write_text("".join(str(tmp_path / n) + "\n" for n in ("t0.ppm", "t1.png", "t2.bmp")))
+    layer = ofdg.DataGenerationLayer('layer { type: "DataGeneration" top: "a" top: "b" top: "c" data_param { batch_size: 4 prefetch: 2 } '
                                      'data_generation_param { mode: 5 texture_dbases: "%s" } }' % (tmp_path / "db.txt"))
     layer.LayerSetUp()
     layer.Forward_gpu()
     got = [layer.top_cpu(i) for i in range(3)]
-    tasks = ofdg.ParamStream(5).generate(2)
-    ref = oracle.render(tasks.struct(), tex_rgb[:, ::-1].copy(), mode=5)  # planes held as B,G,R
+    tasks = ofdg.ParamStream(5).generate(4)
+    ref = oracle.render(tasks.struct(), [t[::-1].copy() for t in tex], mode=5)  # planes held as B,G,R
     assert np.abs(got[0] - ref["img0"]).max() <= 1 and np.abs(got[1] - ref["img1"]).max() <= 1
+    assert np.abs(got[2] - ref["flow"]).max() <= 1e-3
     layer.close()
 
 
@@ -117,3 +118,77 @@ def test_layer_extra_tops(ofdg, oracle):
     with pytest.raises(ofdg.OfdgError, match="at most 7"):
         bad = ofdg.DataGenerationLayer(proto.replace('top: "id1"', 'top: "id1" top: "x"'))
         bad.LayerSetUp()
+
+
+def _png_bytes(rgb, filter_types=(0, 1, 2, 3, 4), alpha=False, palette=False):
+    """Minimal PNG writer (zlib + struct) exercising every scanline filter."""
+    import struct, zlib
+    h, w, _ = rgb.shape
+    if palette:
+        colours, idx = np.unique(rgb.reshape(-1, 3), axis=0, return_inverse=True)
+        assert len(colours) <= 256
+        px = idx.reshape(h, w, 1).astype(np.uint8)
+        ctype = 3
+    elif alpha:
+        px = np.concatenate([rgb, np.full((h, w, 1), 200, np.uint8)], axis=2)
+        ctype = 6
+    else:
+        px, ctype = rgb, 2
+    bpp = px.shape[2]
+    rows = px.reshape(h, w * bpp).astype(np.int32)
+    raw = bytearray()
+    prev = np.zeros(w * bpp, np.int32)
+    for y in range(h):
+        cur = rows[y]
+        ft = filter_types[y % len(filter_types)]
+        a = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]])
+        c = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]])
+        b = prev
+        if ft == 0: pred = 0
+        elif ft == 1: pred = a
+        elif ft == 2: pred = b
+        elif ft == 3: pred = (a + b) >> 1
+        else:
+            p = a + b - c
+            pa, pb, pc = np.abs(p - a), np.abs(p - b), np.abs(p - c)
+            pred = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, b, c))
+        raw.append(ft)
+        raw += ((cur - pred) & 255).astype(np.uint8).tobytes()
+        prev = cur
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    z = zlib.compress(bytes(raw), 6)
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ctype, 0, 0, 0))
+    if palette:
+        out += chunk(b"PLTE", colours.astype(np.uint8).tobytes())
+    out += chunk(b"IDAT", z[: len(z) // 2]) + chunk(b"IDAT", z[len(z) // 2:]) + chunk(b"IEND", b"")
+    return out
+
+
+def test_texture_file_decoders(ofdg, tmp_path):
+    """PPM / BMP / PNG files decode to the B,G,R planes the reference holds after its channel swap (DataGenerator.cpp:128-133)."""
+    import struct
+    rng = np.random.default_rng(3)
+    rgb = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    rgb[5:20, 7:30] = rgb[5, 7]  # flat area: the PNG predictors see zeros
+    want = np.ascontiguousarray(rgb[:, :, ::-1].transpose(2, 0, 1))
+    (tmp_path / "a.ppm").write_bytes(b"P6\n# c\n53 37\n255\n" + rgb.tobytes())
+    stride = (53 * 3 + 3) // 4 * 4
+    rows = b"".join(rgb[y, :, ::-1].tobytes() + b"\0" * (stride - 53 * 3) for y in range(36, -1, -1))
+    (tmp_path / "a.bmp").write_bytes(b"BM" + struct.pack("<IHHI", 54 + len(rows), 0, 0, 54) +
+                                     struct.pack("<IiiHHIIiiII", 40, 53, 37, 1, 24, 0, len(rows), 2835, 2835, 0, 0) + rows)
+    (tmp_path / "a.png").write_bytes(_png_bytes(rgb))
+    (tmp_path / "b.png").write_bytes(_png_bytes(rgb, alpha=True))
+    few = (rgb // 64) * 64
+    (tmp_path / "c.png").write_bytes(_png_bytes(few, palette=True))
+    for name in ("a.ppm", "a.bmp", "a.png", "b.png"):
+        assert np.array_equal(ofdg.decode_texture_file(tmp_path / name), want), name
+    assert np.array_equal(ofdg.decode_texture_file(tmp_path / "c.png"), np.ascontiguousarray(few[:, :, ::-1].transpose(2, 0, 1)))
+    (tmp_path / "x.jpg").write_bytes(b"\xff\xd8\xff\xe0" + b"\0" * 64)
+    with pytest.raises(ofdg.OfdgError, match="unsupported image format"):
+        ofdg.decode_texture_file(tmp_path / "x.jpg")
+    with pytest.raises(ofdg.OfdgError, match="Could not open"):
+        ofdg.decode_texture_file(tmp_path / "missing.png")
+    (tmp_path / "t.ppm").write_bytes(b"P6\n53 37\n255\n" + rgb.tobytes()[:100])
+    with pytest.raises(ofdg.OfdgError, match="truncated"):
+        ofdg.decode_texture_file(tmp_path / "t.ppm")
