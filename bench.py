@@ -139,7 +139,7 @@ def run_reference(args):
                                    f"with the reference's whole-image copies, {threads} worker threads of {cores} host cores"},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args):
@@ -307,10 +307,20 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": min(cores, n), "kind": "port",
                                 "sample": f"{n} samples of the same workload in {dt_cpu:.1f} s (oracle/liboracle.so, reference structure "
                                           f"with its whole-image copies), {min(cores, n)} worker threads of {cores} host cores"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_STDOUT_FD = None
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -336,6 +346,12 @@ def main():
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
             sys.exit(subprocess.call(cmd))
+    # stdout carries the JSON line and nothing else: libraries that write banners to fd 1 (NCCL prints its version
+    # there) are pointed at stderr until the line is printed
+    sys.stdout.flush()
+    global _STDOUT_FD
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -1,3 +1,4 @@
+"""Hottest source lines of a kernel in an ncu report: python tools/ncu_hot_lines.py REPORT KERNEL_REGEX [TOP] [inst]"""
 import csv,sys,subprocess
 rep,kern=sys.argv[1],sys.argv[2]
 top=int(sys.argv[3]) if len(sys.argv)>3 else 30

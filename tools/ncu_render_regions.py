@@ -1,3 +1,4 @@
+"""Per-region sampling summary of render_kernel from an ncu report: python tools/ncu_render_regions.py REPORT [render.cu as profiled]"""
 import csv,sys,subprocess
 rep=sys.argv[1]
 out=subprocess.run(['ncu','-i',rep,'--page','source','--csv','--print-source','cuda,sass','--kernel-name','regex:render_kernel'],capture_output=True,text=True).stdout
@@ -20,7 +21,7 @@ print('total inst',tot_i)
 def rng(f,a,b,name):
     s=sum(v[0] for k,v in lines.items() if k[0]==f and a<=k[1]<=b); i=sum(v[1] for k,v in lines.items() if k[0]==f and a<=k[1]<=b); t=sum(v[2] for k,v in lines.items() if k[0]==f and a<=k[1]<=b)
     print(f"{name:28s} {f}:{a}-{b}: samples {100*s/tot_s:5.1f}% inst {100*i/tot_i:5.1f}% lanes/inst {t/max(i,1):.1f}")
-src=open('/root/repo/optical-flow-2d-data-generation_b200/csrc/render.cu').read().split('\n')
+src=open(sys.argv[2] if len(sys.argv)>2 else '/root/repo/optical-flow-2d-data-generation_b200/csrc/render.cu').read().split('\n')  # the source the profiled binary was built from
 def find(pat):
     for n,l in enumerate(src,1):
         if pat in l: return n
