@@ -899,12 +899,12 @@ __device__ __forceinline__ uint32_t rotated_px(const uchar4* tex, int w, int h, 
 struct ResizeTaps {
   int first;      // first source index
   int count;      // 0: copy, 1..3: moving-average taps, -1: linear (first, first + 1 with weight alpha)
-  float w[3];     // moving average: overlap lengths, in accumulation order
+  unsigned w[3];  // moving average: overlap lengths, in accumulation order
   double alpha;
 };
 __device__ __forceinline__ ResizeTaps make_taps(int len, int n, int t, const int* pos, const double* alpha) {
   ResizeTaps r;
-  r.alpha = 0.0; r.w[0] = r.w[1] = r.w[2] = 0.f;
+  r.alpha = 0.0; r.w[0] = r.w[1] = r.w[2] = 0u;
   if (len == n) { r.first = t; r.count = 0; }
   else if (len > n) {  // moving average over the exact rational overlap (at most 3 sources: len <= 1.3 n, checked on the host)
     const unsigned lo = (unsigned)t * (unsigned)len, hi = lo + (unsigned)len;  // < 2^31 for any supported size
@@ -913,29 +913,33 @@ __device__ __forceinline__ ResizeTaps make_taps(int len, int n, int t, const int
     int k = 0;
     for (; s * (unsigned)n < hi && k < 3; ++s, ++k) {
       const unsigned b0 = max(s * (unsigned)n, lo), e0 = min((s + 1u) * (unsigned)n, hi);
-      r.w[k] = (float)(e0 - b0);
+      r.w[k] = e0 - b0;
     }
     r.count = k;
   } else { r.first = pos[t]; r.alpha = alpha[t]; r.count = -1; }
   return r;
 }
-__device__ __forceinline__ uint32_t apply_taps(const uint32_t* src, int stride, int s0, int len, const ResizeTaps& r) {
+// CImg's moving average accumulates byte * overlap in float and divides by the source length in float
+// (get_resize, interpolation 2). Every partial sum is an integer below 2^24, so the float sums are exact; the
+// quotient of two such integers is either an integer (exact in float) or at least 1/len away from the next one, far more
+// than the float rounding error at values <= 255 -- so trunc(float(acc) / float(len)) == acc / len in integers.
+// `magic` = floor(2^32 / len) + 1 turns that division into one multiply-high (exact for acc * len < 2^32).
+__device__ __forceinline__ uint32_t apply_taps(const uint32_t* src, int stride, int s0, int len, unsigned magic, const ResizeTaps& r) {
   const uint32_t* p0 = src + (r.first - s0) * stride;
   if (r.count == 0) return p0[0];
   uint32_t out = 0;
   if (r.count > 0) {
-    float acc[3] = {0.f, 0.f, 0.f};
+    unsigned acc[3] = {0u, 0u, 0u};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       if (k < r.count) {
         const uint32_t p = p0[k * stride];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) acc[c] += byte_to_float(p, c) * r.w[k];
+        for (int c = 0; c < 3; ++c) acc[c] += __byte_perm(p, 0u, 0x4440u + (unsigned)c) * r.w[k];
       }
     }
-    const float flen = (float)(unsigned int)len;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) out |= ((uint32_t)(unsigned char)(acc[c] / flen)) << (8 * c);
+    for (int c = 0; c < 3; ++c) out |= __umulhi(acc[c], magic) << (8 * c);
     return out;
   }
   const uint32_t p1 = p0[0], p2 = r.first < len - 1 ? p0[stride] : p1;
@@ -947,6 +951,12 @@ __device__ __forceinline__ uint32_t apply_taps(const uint32_t* src, int stride, 
   return out;
 }
 
+// fast path only (len <= 1.3 n): every product below 2^31
+__device__ __forceinline__ void source_range32(int len, int n, int t0, int t1, const int* pos, int& s0, int& s1) {
+  if (len == n) { s0 = t0; s1 = t1; }
+  else if (len > n) { s0 = (int)(((unsigned)t0 * (unsigned)len) / (unsigned)n); s1 = (int)((((unsigned)(t1 + 1) * (unsigned)len) - 1u) / (unsigned)n); }
+  else { s0 = pos[t0]; s1 = min(pos[t1] + 1, len - 1); }
+}
 __device__ __forceinline__ void source_range(int len, int n, int t0, int t1, const int* pos, int& s0, int& s1) {
   if (len == n) { s0 = t0; s1 = t1; }
   else if (len > n) { s0 = (int)(((long long)t0 * len) / n); s1 = (int)((((long long)(t1 + 1) * len) - 1) / n); }
@@ -1042,18 +1052,22 @@ __global__ void __launch_bounds__(PREP_THREADS) bg_prep_kernel(RenderArgs a) {
     return;
   }
   int cx0, cx1, cy0, cy1;
-  source_range(p.crop_w, W2, X0, X1, pos_x, cx0, cx1);
-  source_range(p.crop_h, H2, Y0, Y1, pos_y, cy0, cy1);
+  source_range32(p.crop_w, W2, X0, X1, pos_x, cx0, cx1);
+  source_range32(p.crop_h, H2, Y0, Y1, pos_y, cy0, cy1);
   const int cw = cx1 - cx0 + 1, ch = cy1 - cy0 + 1;  // <= PS by construction
   const int tw = X1 - X0 + 1, th = Y1 - Y0 + 1;
+  const unsigned magic_x = 0xFFFFFFFFu / (unsigned)p.crop_w + 1u, magic_y = 0xFFFFFFFFu / (unsigned)p.crop_h + 1u;
   if ((int)threadIdx.x < th) sTy[threadIdx.x] = make_taps(p.crop_h, H2, Y0 + (int)threadIdx.x, pos_y, alpha_y);  // visible after the barriers below
   // A: crop(x0, y0, .., mirror) of the rotated image
   const int lane_x = threadIdx.x & 31, lane_y = threadIdx.x >> 5;
   {  // all lanes busy: walk the cw x ch source tile linearly, stepping (x, y) by 256 items without a divide per item
     const int step_y = PREP_THREADS / cw, step_x = PREP_THREADS % cw;
     int lx = (int)threadIdx.x % cw, ly = (int)threadIdx.x / cw;
+    const int bx = p.crop_x0 + cx0, by = p.crop_y0 + cy0;
+    const bool inside = bx >= 0 && by >= 0 && bx + cw <= p.rw && by + ch <= p.rh;  // the crop's mirror boundary is not in play for this tile
     while (ly < ch) {
-      sA[ly][lx] = rotated_px(tex, ti.w, ti.h, p, mirror(p.crop_x0 + cx0 + lx, p.rw), mirror(p.crop_y0 + cy0 + ly, p.rh));
+      const int rx = inside ? bx + lx : mirror(bx + lx, p.rw), ry = inside ? by + ly : mirror(by + ly, p.rh);
+      sA[ly][lx] = rotated_px(tex, ti.w, ti.h, p, rx, ry);
       lx += step_x; ly += step_y;
       if (lx >= cw) { lx -= cw; ++ly; }
     }
@@ -1062,13 +1076,13 @@ __global__ void __launch_bounds__(PREP_THREADS) bg_prep_kernel(RenderArgs a) {
   // B: resize along x (one column per lane: its taps are computed once)
   if (lane_x < tw) {
     const ResizeTaps tx = make_taps(p.crop_w, W2, X0 + lane_x, pos_x, alpha_x);
-    for (int ly = lane_y; ly < ch; ly += PREP_THREADS / 32) sB[ly][lane_x] = apply_taps(&sA[ly][0], 1, cx0, p.crop_w, tx);
+    for (int ly = lane_y; ly < ch; ly += PREP_THREADS / 32) sB[ly][lane_x] = apply_taps(&sA[ly][0], 1, cx0, p.crop_w, magic_x, tx);
   }
   __syncthreads();
   // P: resize along y
   if (lane_x < tw)
     for (int ly = lane_y; ly < th; ly += PREP_THREADS / 32) {
-      const uint32_t v = apply_taps(&sB[0][lane_x], PT, cy0, p.crop_h, sTy[ly]);
+      const uint32_t v = apply_taps(&sB[0][lane_x], PT, cy0, p.crop_h, magic_y, sTy[ly]);
       *reinterpret_cast<uint32_t*>(out + (size_t)(Y0 + ly) * W2 + X0 + lane_x) = v;
     }
 }
