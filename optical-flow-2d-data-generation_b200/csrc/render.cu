@@ -943,10 +943,15 @@ __device__ __forceinline__ uint32_t apply_taps(const uint32_t* src, int stride, 
     return out;
   }
   const uint32_t p1 = p0[0], p2 = r.first < len - 1 ? p0[stride] : p1;
+  // byte -> double and double -> byte without the conversion unit: 2^52 + b has b in its low mantissa bits (exact), and
+  // adding 2^52 with round-towards-zero leaves floor(v) there (0 <= v < 256)
+  const double two52 = 4503599627370496.0, na = 1 - r.alpha;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const double v = (1 - r.alpha) * (double)(int)((p1 >> (8 * c)) & 255u) + r.alpha * (double)(int)((p2 >> (8 * c)) & 255u);
-    out |= ((uint32_t)(unsigned char)v) << (8 * c);
+    const double b1 = __hiloint2double(0x43300000, (int)__byte_perm(p1, 0u, 0x4440u + (unsigned)c)) - two52;
+    const double b2 = __hiloint2double(0x43300000, (int)__byte_perm(p2, 0u, 0x4440u + (unsigned)c)) - two52;
+    const double v = na * b1 + r.alpha * b2;
+    out |= ((uint32_t)__double2loint(__dadd_rz(v, two52)) & 255u) << (8 * c);
   }
   return out;
 }
