@@ -169,7 +169,8 @@ int ofdg_generate_host(ofdg_generator* g, ofdg_params* p, int32_t batch, float* 
 /* Production mode: scene parameters are drawn ON THE DEVICE with counter-based Philox4x32-10
  * from the same mode tables and branch structure as the host stream, flattened on the device and rendered --
  * no host work, no upload. Sample i of the stream is a pure function of (mode, seed, first_sample + i), so any
- * GPU reproduces any sample. Statistically, not bitwise, equivalent to the host stream; modes 1-8, 10-13. */
+ * GPU reproduces any sample. Statistically, not bitwise, equivalent to the host stream. All 13 modes; in mode 9 the
+ * warp fields come from the generator's pool (ofdg_set_fields / ofdg_generate_fields), picked by one more counter-based draw. */
 int ofdg_generate_philox(ofdg_generator* g, uint64_t seed, uint64_t first_sample, int32_t batch, int32_t augment,
                          float* d_img0, float* d_img1, float* d_flow, void* stream);
 /* The blueprints the device stream draws for those samples, downloaded into an ordinary task batch

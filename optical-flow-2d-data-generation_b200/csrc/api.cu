@@ -139,6 +139,8 @@ struct ofdg_generator {
   DevBuf ph_slots;
   struct PhiloxSet {
     DevBuf bp, seg_type, seg_x, seg_y, obj_nbp, obj_nseg, ntop;
+    DevBuf n_deform;             // mode 9: device counter of warped outlines ...
+    PinnedBuf n_deform_host;     //   ... and where it lands on the host
     DeviceScene scene;
     cudaEvent_t ready = nullptr, consumed = nullptr;
     bool used = false;
@@ -154,7 +156,7 @@ struct ofdg_generator {
   std::vector<ofdg::TexInfo> tex_info;   // host copy of the table
   DevBuf tex_info_dev;
   // mode 9 fields
-  DevBuf fields, fpos_x, falpha_x, fpos_y, falpha_y, mask_raw, mask_warp;
+  DevBuf fields, fpos_x, falpha_x, fpos_y, falpha_y, mask_raw, mask_warp, field_reach_dev;
   int n_fields = 0;
   std::vector<int> field_reach;
   // per-call scene staging + scratch
@@ -558,12 +560,13 @@ void ofdg_destroy(ofdg_generator* g) {
   for (int i = 0; i < 2; ++i) {
     ofdg_generator::PhiloxSet& q = g->ph[i];
     q.scene.release();
-    DevBuf* qb[] = {&q.bp, &q.seg_type, &q.seg_x, &q.seg_y, &q.obj_nbp, &q.obj_nseg, &q.ntop};
+    DevBuf* qb[] = {&q.bp, &q.seg_type, &q.seg_x, &q.seg_y, &q.obj_nbp, &q.obj_nseg, &q.ntop, &q.n_deform};
+    q.n_deform_host.release();
     for (DevBuf* b : qb) b->release();
     if (q.ready) cudaEventDestroy(q.ready);
     if (q.consumed) cudaEventDestroy(q.consumed);
   }
-  DevBuf* bufs[] = {&g->ph_slots, &g->pool, &g->tex_info_dev, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->bg, &g->tile_hits, &g->rtab_pos_x, &g->rtab_alpha_x, &g->rtab_pos_y, &g->rtab_alpha_y, &g->out0, &g->out1,
+  DevBuf* bufs[] = {&g->ph_slots, &g->pool, &g->tex_info_dev, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->field_reach_dev, &g->bg, &g->tile_hits, &g->rtab_pos_x, &g->rtab_alpha_x, &g->rtab_pos_y, &g->rtab_alpha_y, &g->out0, &g->out1,
                     &g->outf, &g->ids8, &g->dbg_masks, &g->dbg_id0, &g->dbg_id1, &g->dbg_frames8, &g->dbg_planar};
   for (DevBuf* b : bufs) b->release();
   g->scene.release();
@@ -769,6 +772,9 @@ int ofdg_set_fields(ofdg_generator* g, const float* fields, int32_t n) {
         if (std::isfinite(ifl[k])) mx = std::max(mx, std::fabs(ifl[k]));
       g->field_reach[i] = (int)std::ceil(std::min(mx, 1.0e6f));
     }
+    g->field_reach_dev.reserve(n * sizeof(int));  // the device-side stream widens the boxes itself
+    CK(cudaMemcpy(g->field_reach_dev.p, g->field_reach.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    g->ph_next.valid = false;
     // CImg linear-resize tables (W+1 -> 2W, H+1 -> 2H) used when the background carries a field
     auto table = [](int len, int nout, std::vector<int>& pos, std::vector<double>& alpha) {
       pos.resize(nout); alpha.resize(nout);
@@ -1131,7 +1137,10 @@ void philox_run(ofdg_generator* g, int set, uint64_t seed, uint64_t first_sample
   a.slots = (const PhiloxSlot*)g->ph_slots.p;
   a.mode = g->cfg.mode; a.W = g->cfg.width; a.H = g->cfg.height;
   a.seed = seed; a.first_sample = first_sample;
-  a.batch = batch; a.n_fields = 0; a.fg_override = fg_override; a.augment = augment;
+  a.batch = batch; a.n_fields = g->cfg.mode == 9 ? g->n_fields : 0; a.fg_override = fg_override; a.augment = augment;
+  a.field_reach = (const int*)g->field_reach_dev.p;
+  a.deform_shape = (int*)q.scene.deform_shape.p; a.deform_field = (int*)q.scene.deform_field.p; a.n_deform = (int*)q.n_deform.p;
+  CK(cudaMemsetAsync(q.n_deform.p, 0, sizeof(int), s));
   a.n_tex = g->n_tex; a.tex_info = (const ofdg::TexInfo*)g->tex_info_dev.p;
   a.bp = (ofdg_blueprint*)q.bp.p;
   a.seg_type = (int32_t*)q.seg_type.p; a.seg_x = (float*)q.seg_x.p; a.seg_y = (float*)q.seg_y.p;
@@ -1139,13 +1148,20 @@ void philox_run(ofdg_generator* g, int set, uint64_t seed, uint64_t first_sample
   a.samples = (FlatSample*)q.scene.samples.p; a.objects = (FlatObject*)q.scene.objects.p;
   a.shapes = (FlatShape*)q.scene.shapes.p; a.verts = (FlatVertex*)q.scene.verts.p;
   g->launches += launch_philox(a, s);
+  CK(cudaMemcpyAsync(q.n_deform_host.p, q.n_deform.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   q.scene.batch = batch;
-  q.scene.n_deform = 0;
+  q.scene.n_deform = 0;  // mode 9: read back by philox_collect once the set is complete
+}
+
+// Mode 9: the number of warped outlines of a finished set sizes the deformation pre-pass of its render.
+void philox_collect(ofdg_generator* g, int set, cudaStream_t producer) {
+  if (g->cfg.mode != 9) return;
+  CK(cudaStreamSynchronize(producer));
+  g->ph[set].scene.n_deform = *(const int*)g->ph[set].n_deform_host.p;
 }
 
 void philox_check(ofdg_generator* g, int batch) {
   using namespace ofdg;
-  if (g->cfg.mode == 9) throw ArgError("the device-side parameter stream does not cover mode 9 (warp fields are injected through the host stream)");
   if (g->n_tex <= 0) throw StateError("no textures uploaded (ofdg_upload_textures / ofdg_synth_textures)");
   if (batch <= 0 || batch > g->cfg.max_batch) throw ArgError("bad batch size");
   if (batch > g->ph_batch) {
@@ -1159,6 +1175,9 @@ void philox_check(ofdg_generator* g, int batch) {
       q.seg_y.reserve(n * kPhiloxMaxSeg * sizeof(float));
       q.obj_nbp.reserve(n * kPhiloxMaxObj * sizeof(int)); q.obj_nseg.reserve(n * kPhiloxMaxObj * sizeof(int));
       q.ntop.reserve(n * sizeof(int));
+      q.n_deform.reserve(sizeof(int)); q.n_deform_host.reserve(sizeof(int));
+      q.scene.deform_shape.reserve(n * kPhiloxMaxObj * kPhiloxMaxShapes * sizeof(int));
+      q.scene.deform_field.reserve(n * kPhiloxMaxObj * kPhiloxMaxShapes * sizeof(int));
       q.scene.samples.reserve(n * sizeof(FlatSample));
       q.scene.objects.reserve(n * kPhiloxMaxObj * sizeof(FlatObject));
       q.scene.shapes.reserve(n * kPhiloxMaxObj * kPhiloxMaxShapes * sizeof(FlatShape));
@@ -1182,11 +1201,13 @@ int ofdg_generate_philox(ofdg_generator* g, uint64_t seed, uint64_t first_sample
         g->ph_next.augment == augment) {
       set = g->ph_next.set;  // drawn and flattened on the side stream while the previous batch rendered
       CK(cudaStreamWaitEvent(s, g->ph[set].ready, 0));
+      philox_collect(g, set, g->ph_stream);
     } else {
       set = g->ph_next.valid ? (g->ph_next.set ^ 1) : 0;
       if (g->ph_next.valid) CK(cudaStreamSynchronize(g->ph_stream));  // a speculative batch nobody asked for is still being written
       if (g->ph[set].used) CK(cudaStreamWaitEvent(s, g->ph[set].consumed, 0));
       philox_run(g, set, seed, first_sample, batch, augment, 0, s);
+      philox_collect(g, set, s);
     }
     ensure_scratch(g, batch);
     run_kernels(g, with_extra_tops(g, make_args(g, g->ph[set].scene, d_img0, d_img1, d_flow)), s);

@@ -235,7 +235,12 @@ DataGenerationLayer<Dtype>::DataGenerationLayer(const LayerParameter& param) : L
       OFDG_CHECK(ofdg_add_textures(generator_, t.planar_bgr.data(), 1, t.w, t.h));
     }
   }
-  OFDG_CHECK(ofdg_params_create(gp.mode(), cfg.width, cfg.height, 45 * solver_rank_, 0, 0, &params_));
+  // Mode 9: the reference owns a WarpFields::CropGenerator that keeps producing (flow, iflow) crops on 10 CPU threads,
+  // seeded from std::random_device (DataGenerator.cpp:1016-1019, WarpFields.cpp:540-641). Here the GPU producer fills a
+  // pool of kFieldPool crops once, from a reproducible seed; objects walk the pool in commission order.
+  const int n_fields = gp.mode() == 9 ? kFieldPool : 0;
+  if (n_fields) OFDG_CHECK(ofdg_generate_fields(generator_, (uint32_t)(gp.seed() + 7919u * (unsigned)solver_rank_ + 1u), n_fields, nullptr));
+  OFDG_CHECK(ofdg_params_create(gp.mode(), cfg.width, cfg.height, 45 * solver_rank_, n_fields, 0, &params_));
   OFDG_CHECK(ofdg_tasks_create(&tasks_));
 }
 

@@ -51,6 +51,7 @@ class DataGenerationLayer : public Layer<Dtype> {
   void BindExtraTops(const std::vector<Blob<Dtype>*>& top);  // top[3..6]: backward flow, occlusion, index images
 
   static int solver_rank_;
+  static constexpr int kFieldPool = 40;   // mode 9: (flow, iflow) crops generated at set-up
   int device_ = 0;
   ofdg_generator* generator_ = nullptr;   // DataGenerator::DataGenerator data_generator_
   ofdg_params* params_ = nullptr;         // DataGenerator::ObjectParametersGenerator obj_params_generator_

@@ -95,7 +95,7 @@ enum {  // slot indices, DataGenerator.h:524-587
   ObjRot, ObjInitScale, ObjScaleTrigger, ObjScale, ObjTexShiftX, ObjTexShiftY, ObjTexRot, ObjTexZoom, ElliObj_ScaleX,
   ElliObj_ScaleY, PolyObj_spokes, PolyObj_dphi, PolyObj_r, PolyObj_ScaleX, PolyObj_ScaleY, PolyObj_CurveTrigger,
   CompObjInitTransX, CompObjInitTransY, CompObiNumberOfComponents, ComponentIsAdditive, ComponentOffset, ObjIsExtraThin,
-  ObjDeformsNonrigidly, GenericUniform, GenericTrigger, AugGain, AugBrightness, AugContrast, AugSigma, AugSeed
+  ObjDeformsNonrigidly, GenericUniform, GenericTrigger, AugGain, AugBrightness, AugContrast, AugSigma, AugSeed, FieldPick
 };
 
 struct SampleOut {  // this sample's slice of the blueprint arrays
@@ -171,7 +171,14 @@ __device__ void gen_simple(Gen& g, SampleOut& o, int idx, bool is_component, int
   b.tex_id = g.integer(ObjTexID);
   if (g.mode == 9) {
     b.do_warpfield_deformation = g.trigger(ObjDeformsNonrigidly);
-    if (!is_component && b.do_warpfield_deformation && n_fields > 0) b.field_id = (field_draws++ / 3) % n_fields;
+    // the host stream walks the injected pool in commission order; a sample of the device stream must not depend on
+    // the samples before it, so the pick is one more counter-based draw
+    if (!is_component && b.do_warpfield_deformation && n_fields > 0) {
+      uint32_t r0, r1;
+      g.rng.raw(FieldPick, r0, r1);
+      b.field_id = (int)(r0 % (uint32_t)n_fields);
+      ++field_draws;
+    }
   }
   if (b.obj_type == OFDG_OBJ_ELLIPSE) {
     b.ellipse_scale_x = g.real(ElliObj_ScaleX) * 50;
@@ -284,6 +291,11 @@ __global__ void philox_params_kernel(PhiloxArgs a) {
     bg.tex_shift_x = g.integer(BgInitTransX);
     bg.tex_shift_y = g.integer(BgInitTransY);
     bg.do_warpfield_deformation = g.trigger(ObjDeformsNonrigidly);
+    if (a.mode == 9 && bg.do_warpfield_deformation && a.n_fields > 0) {
+      uint32_t r0, r1;
+      g.rng.raw(FieldPick, r0, r1);
+      bg.field_id = (int)(r0 % (uint32_t)a.n_fields);
+    }
     a.bp[s * kPhiloxMaxBp] = bg;
     a.n_top[s] = fg;
     if (a.augment) {
@@ -310,7 +322,7 @@ __global__ void philox_params_kernel(PhiloxArgs a) {
   o.nbp = 1; o.nseg = 0;
   o.bp[0] = blank_bp();
   o.bp[0].obj_id = 10 + k;
-  gen_object(g, o, 0, 0, field_draws);
+  gen_object(g, o, 0, a.n_fields, field_draws);
   a.obj_nbp[s * kPhiloxMaxObj + k] = o.nbp;
   a.obj_nseg[s * kPhiloxMaxObj + k] = o.nseg;
 }
@@ -475,8 +487,8 @@ __global__ void __launch_bounds__(kFlatObjPerBlock * kFlatLanes) philox_flatten_
     tex_inv.store(smp.bg_tex_inv);
     bgM.store(smp.bg_motion);
     bgM.inverse().store(smp.bg_motion_inv);
-    smp.bg_field = -1;  // warp fields (mode 9) are host-driven: the device stream rejects mode 9
-    prepare_bg(a, bg, tex_inv, false, smp.prep);
+    smp.bg_field = (a.mode == 9 && bg.do_warpfield_deformation && bg.field_id >= 0) ? bg.field_id : -1;
+    prepare_bg(a, bg, tex_inv, smp.bg_field >= 0, smp.prep);
     smp.obj_begin = s * kPhiloxMaxObj;
     smp.obj_count = a.n_top[s];
     a.samples[s] = smp;
@@ -516,8 +528,24 @@ __global__ void __launch_bounds__(kFlatObjPerBlock * kFlatLanes) philox_flatten_
     int bx[4] = {0x7FFFFFF0, 0x7FFFFFF0, -0x7FFFFFF0, -0x7FFFFFF0};
     if (out.n) { bx[0] = out.x0 >> 8; bx[1] = out.y0 >> 8; bx[2] = out.x1 >> 8; bx[3] = out.y1 >> 8; }
     for (int i = 0; i < 4; ++i) sh.bbox[f][i] = bx[i];
-    if (f) { for (int i = 0; i < 4; ++i) sh.raw1[i] = bx[i]; }
-    else { sh.additive = c.is_additive_component ? 1 : 0; sh.deform = -1; }
+    if (f) {
+      for (int i = 0; i < 4; ++i) sh.raw1[i] = bx[i];
+      // MovingObjectBase::renderMasks warps this outline's frame-1 masks by the inverse field (DG.cpp:370-386); components
+      // carry their parent's field (DG.cpp:1157-1163). The slot order is arbitrary: slots only name scratch planes.
+      const int field = (a.mode == 9 && b.do_warpfield_deformation && b.field_id >= 0) ? b.field_id : -1;
+      int slot = -1;
+      if (field >= 0) {
+        slot = atomicAdd(a.n_deform, 1);
+        a.deform_shape[slot] = obj_slot * kPhiloxMaxShapes + si;
+        a.deform_field[slot] = field;
+        const int reach = a.field_reach[field] + 2;
+        bx[0] -= reach; bx[1] -= reach; bx[2] += reach; bx[3] += reach;
+        for (int i = 0; i < 4; ++i) sh.bbox[1][i] = bx[i];
+      }
+      sh.deform = slot;
+    } else {
+      sh.additive = c.is_additive_component ? 1 : 0;
+    }
     atomicMin(&s_box[lo][f][0], bx[0]); atomicMin(&s_box[lo][f][1], bx[1]);
     atomicMax(&s_box[lo][f][2], bx[2]); atomicMax(&s_box[lo][f][3], bx[3]);
   }
@@ -527,7 +555,7 @@ __global__ void __launch_bounds__(kFlatObjPerBlock * kFlatLanes) philox_flatten_
     memset(&o, 0, sizeof(o));
     o.obj_id = b.obj_id;
     o.tex = (int)((unsigned)b.tex_id % (unsigned)a.n_tex);
-    o.field = -1;
+    o.field = (a.mode == 9 && b.do_warpfield_deformation && b.field_id >= 0) ? b.field_id : -1;
     o.composite = composite;
     o.shape_begin = obj_slot * kPhiloxMaxShapes;
     o.shape_count = nshape;

@@ -8,7 +8,7 @@
 
 namespace ofdg {
 
-constexpr int kPhiloxSlots = 50;        // the 45 engines of a data mode + 5 augmentation engines
+constexpr int kPhiloxSlots = 51;        // the 45 engines of a data mode + 5 augmentation engines + the field pick of mode 9
 constexpr int kPhiloxMaxObj = 32;       // top-level foreground objects per sample
 constexpr int kPhiloxMaxShapes = 8;     // blueprints per object (itself + up to 7 components) = outlines per object
 constexpr int kPhiloxMaxBp = 1 + kPhiloxMaxObj * kPhiloxMaxShapes;    // background, then 8 slots per object
@@ -30,6 +30,11 @@ struct PhiloxArgs {
   int batch, n_fields, fg_override, augment;
   int n_tex;
   const TexInfo* tex_info;  // device: pool texture sizes
+  // mode 9 (n_fields > 0): outlines whose frame-1 masks go through a warp field get a slot of the deformation scratch
+  const int* field_reach;   // device [n_fields]: ceil(max |iflow|), how far a warped mask can move
+  int* deform_shape;        // [batch * kPhiloxMaxObj * kPhiloxMaxShapes] shape index per slot
+  int* deform_field;        //   field id per slot
+  int* n_deform;            // device counter (zeroed before the launch)
   // blueprints in the ABI layout, fixed strides per sample (downloadable for inspection / the oracle)
   ofdg_blueprint* bp;   // [batch][kPhiloxMaxBp]: background, then kPhiloxMaxShapes slots per object
   int32_t* seg_type;    // [batch][kPhiloxMaxSeg]: 160 per object

@@ -86,7 +86,7 @@ def test_statistics_match_the_host_stream(ofdg, textures8):
     g.close()
 
 
-def test_device_stream_with_augmentation_and_mode9_rejection(ofdg, textures8):
+def test_device_stream_with_augmentation(ofdg, textures8):
     g = _gen(ofdg, 7)
     g.upload_textures(textures8)
     a, b = _blobs(4), _blobs(4)
@@ -94,8 +94,39 @@ def test_device_stream_with_augmentation_and_mode9_rejection(ofdg, textures8):
     g.generate_philox(5, 0, 4, *b, augment=True)
     assert (a[0] - b[0]).abs().mean().item() > 2 and (a[2] - b[2]).abs().max().item() == 0
     g.close()
-    g9 = _gen(ofdg, 9)
-    g9.upload_textures(textures8)
-    with pytest.raises(ofdg.OfdgError, match="mode 9"):
-        g9.generate_philox(5, 0, 4, *a)
-    g9.close()
+
+
+def test_device_stream_mode9_warp_fields(ofdg, oracle, textures8):
+    """Mode 9 through the device stream: field picks are counter-based draws, the flatten kernel hands out the deformation
+    slots, and the render equals the host path's render of the very same blueprints."""
+    import torch
+    fields = oracle.generate_fields(512, 384, seed=3, n_fields=4)
+    g = _gen(ofdg, 9)
+    g.upload_textures(textures8)
+    g.set_fields(fields)
+    n = 12
+    tasks = g.philox_tasks(77, 40, n)
+    bp = tasks.arrays()["blueprints"]
+    flagged = bp[(bp["do_warpfield_deformation"] != 0) & (bp["parent"] < 0)]
+    assert len(flagged) >= 3 and set(np.unique(flagged["field_id"])) <= {0, 1, 2, 3} and len(np.unique(flagged["field_id"])) >= 2
+    assert (flagged["obj_id"] == 1).any(), "a deformed background must be part of the batch"
+    host = g.render_host(tasks)
+    cpu = oracle.render(tasks.struct(), textures8, mode=9, fields=fields)
+    ok = np.isfinite(cpu["flow"])
+    assert np.abs(host[0] - cpu["img0"]).max() <= 1 and np.abs(host[2][ok] - cpu["flow"][ok]).max() <= 1e-3
+    for rep in range(2):          # the second call is served by the look-ahead set
+        i0, i1, fl = _blobs(n)
+        g.generate_philox(77, 40 + rep * n, n, i0, i1, fl)
+        torch.cuda.synchronize()
+        if rep == 0:
+            dev = [t.cpu().numpy() for t in (i0, i1, fl)]
+            for d, h in zip(dev, host):
+                with np.errstate(invalid="ignore"):
+                    bad = np.abs(d - h) > (1e-3 if d.shape[1] == 2 else 1)
+                assert bad.mean() < 3e-3, bad.mean()
+        else:
+            nxt = g.render_host(g.philox_tasks(77, 40 + n, n))
+            with np.errstate(invalid="ignore"):
+                bad = np.abs(i0.cpu().numpy() - nxt[0]) > 1
+            assert bad.mean() < 3e-3
+    g.close()

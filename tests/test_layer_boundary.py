@@ -192,3 +192,26 @@ def test_texture_file_decoders(ofdg, tmp_path):
     (tmp_path / "t.ppm").write_bytes(b"P6\n53 37\n255\n" + rgb.tobytes()[:100])
     with pytest.raises(ofdg.OfdgError, match="truncated"):
         ofdg.decode_texture_file(tmp_path / "t.ppm")
+
+
+@pytest.mark.gpu
+def test_layer_mode9_uses_a_generated_field_pool(ofdg, oracle):
+    """Mode 9 through the layer: the GPU field producer fills a pool of 40 crops at set-up (the reference runs a CropGenerator,
+    DataGenerator.cpp:1016-1019); the batches equal the oracle's render with the same pool and parameter stream."""
+    proto = ('layer { type: "DataGeneration" top: "a" top: "b" top: "c" data_param { batch_size: 6 prefetch: 2 } '
+             'data_generation_param { mode: 9 texture_dbases: "synthetic:8:1" } }')
+    layer = ofdg.DataGenerationLayer(proto)
+    layer.LayerSetUp()
+    layer.Forward_gpu()
+    got = [layer.top_cpu(i) for i in range(3)]
+    g = ofdg.Generator(device=0, mode=9, max_batch=6)
+    fields = g.generate_fields(1, 40)          # the layer's seed for seed = 0, rank 0
+    g.close()
+    tasks = ofdg.ParamStream(9, n_fields=40).generate(6)
+    bp = tasks.arrays()["blueprints"]
+    assert ((bp["do_warpfield_deformation"] != 0) & (bp["field_id"] >= 0)).any()
+    ref = oracle.render(tasks.struct(), ofdg.synth_textures(8, 1024, 768, seed=1), mode=9, fields=fields)
+    ok = np.isfinite(ref["flow"])
+    assert np.abs(got[0] - ref["img0"]).max() <= 1 and np.abs(got[1] - ref["img1"]).max() <= 1
+    assert np.array_equal(ok, np.isfinite(got[2])) and np.abs(got[2][ok] - ref["flow"][ok]).max() <= 1e-3
+    layer.close()
