@@ -62,3 +62,56 @@ def test_remaining_modes_parity(ofdg, oracle, textures8, mode):
     assert np.abs(gpu["frames8"].astype(int) - cpu["frames8"].astype(int)).max() <= 1
     assert np.abs(gpu["flow"] - cpu["flow"]).max() <= 1e-3
     g.close()
+
+
+def test_ten_thousand_texture_pool(ofdg, oracle):
+    """Stress config: 10,000 textures of 1024 x 768 resident in HBM (31 GB, pixel offsets beyond 2^32).
+    The textures a batch uses are regenerated on the host for the oracle; everything else about the batch is untouched."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs 40 GB of free device memory")
+    n_tex = 10000
+    g = ofdg.Generator(device=0, mode=7, max_batch=4)
+    g.synth_textures(n_tex, 1024, 768, seed=4)
+    assert g.texture_size(n_tex - 1) == (1024, 768)
+    assert np.array_equal(g.download_texture(n_tex - 1), ofdg.synth_textures(1, 1024, 768, seed=4, first_index=n_tex - 1)[0])
+    tasks = ofdg.ParamStream(7).generate(4)
+    a = tasks.arrays()
+    ids = a["blueprints"]["tex_id"].astype(np.int64) % n_tex
+    used = np.unique(ids[a["blueprints"]["parent"] < 0])
+    assert used.max() > 5600, "a texture beyond the 2^32-pixel offset must be in use"   # 2^32 / (1024 * 768) = 5461.3
+    compact = {int(t): i for i, t in enumerate(used)}
+    pool = [ofdg.synth_textures(1, 1024, 768, seed=4, first_index=int(t))[0] for t in used]
+    b = {k: (v.copy() if v is not None else None) for k, v in a.items()}
+    b["blueprints"]["tex_id"] = np.array([compact.get(int(t), 0) for t in ids], np.int32)
+    gpu = g.render_debug(tasks)
+    cpu = oracle.render(ofdg.Tasks.from_arrays(b).struct(), pool, mode=7, debug=True)
+    assert np.array_equal(gpu["id0"], cpu["id0"]) and np.array_equal(gpu["masks"], cpu["masks"])
+    assert np.abs(gpu["frames8"].astype(int) - cpu["frames8"].astype(int)).max() <= 1
+    assert np.abs(gpu["flow"] - cpu["flow"]).max() <= 1e-3
+    g.close()
+
+
+def test_config3_mode9_fields_augmentation_batch64(ofdg, oracle, textures8):
+    """mode 9 with a pool of 40 generated warp fields and the colour/noise augmentation at batch 64.
+    Three samples of the batch against the oracle; the whole batch against its own parts."""
+    g = ofdg.Generator(device=0, mode=9, max_batch=64)
+    g.upload_textures(textures8)
+    fields = g.generate_fields(5, 40)
+    ps = ofdg.ParamStream(9, n_fields=40)
+    ps.enable_augmentation(True)
+    tasks = ps.generate(64)
+    full = g.render_host(tasks)
+    pick = [0, 31, 63]
+    sub = tasks.select(pick)
+    part = g.render_host(sub)
+    for a, b in zip(full, part):
+        assert np.array_equal(a[pick], b, equal_nan=True)
+    cpu = oracle.render(sub.struct(), textures8, mode=9, fields=fields)
+    assert np.array_equal(part[0], cpu["img0"]) and np.array_equal(part[1], cpu["img1"])   # augmentation is bit-exact
+    ok = np.isfinite(cpu["flow"])
+    assert np.array_equal(ok, np.isfinite(part[2])) and np.abs(part[2][ok] - cpu["flow"][ok]).max() <= 1e-3
+    bp = tasks.arrays()["blueprints"]
+    assert len(np.unique(bp["field_id"][bp["field_id"] >= 0])) > 20
+    g.close()
