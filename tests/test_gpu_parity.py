@@ -365,3 +365,90 @@ def test_mixed_size_pool_render_parity(ofdg, oracle):
     cpu = oracle.render(tasks.struct(), pool, mode=7, debug=True)
     assert _compare(gpu, cpu) <= IMG_TOL
     g.close()
+
+
+def _ellipse(obj_id, x, y, rx, ry, tex_id=3, rot=0.1, trans=(5.0, -3.0)):
+    return dict(obj_id=obj_id, obj_type=1, init_rot=0.3, init_scale=0.0, init_trans_x=x, init_trans_y=y, rot=rot, scale=1.02,
+                trans_x=trans[0], trans_y=trans[1], tex_id=tex_id, tex_rot=0.0, tex_scale=0.0, tex_shift_x=0, tex_shift_y=0,
+                ellipse_scale_x=rx, ellipse_scale_y=ry, seg_begin=0, seg_count=0, comp_begin=0, comp_count=0, parent=-1,
+                is_additive_component=0, do_warpfield_deformation=0, field_id=-1)
+
+
+def test_edge_case_scenes(ofdg, oracle, textures8):
+    """Hand-made scenes at the corners of the input space: a sample with no foreground at all, objects entirely outside the
+    frame, objects hanging over every border (negative coordinates feed the carry-in of the tile rasteriser), one ellipse
+    larger than the frame, a sliver thinner than a pixel, and a degenerate polygon with zero area."""
+    base = ofdg.ParamStream(5).generate(1).arrays()
+    bg = base["blueprints"][0]
+    dt = base["blueprints"].dtype
+
+    def rec(d):
+        r = np.zeros(1, dt)
+        for k, v in d.items():
+            r[k] = v
+        return r[0]
+
+    scenes = [
+        [],                                                                     # background only
+        [_ellipse(10, -400.0, -300.0, 40, 30), _ellipse(11, 2000.0, 900.0, 50, 50)],  # everything off-frame
+        [_ellipse(10, 0.0, 100.0, 60, 40), _ellipse(11, 511.0, 200.0, 70, 30), _ellipse(12, 250.0, 0.0, 30, 80),
+         _ellipse(13, 300.0, 383.0, 90, 25), _ellipse(14, -20.0, -10.0, 45, 45)],      # over every border and the corner
+        [_ellipse(10, 256.0, 192.0, 900, 700)],                                 # larger than the frame
+        [_ellipse(10, 200.0, 150.0, 120, 0.2), _ellipse(11, 300.0, 250.0, 0.3, 90)],  # slivers
+    ]
+    bps, task_begin = [], [0]
+    seg_type, seg_x, seg_y = [], [], []
+    for sc in scenes:
+        bps.append(bg)
+        bps += [rec(d) for d in sc]
+        task_begin.append(len(bps))
+    # a degenerate polygon (all vertices on one line) next to a proper triangle that leaves the frame on the left
+    bps.append(bg)
+    for k, pts in enumerate([[(-40, -40), (0, 0), (40, 40), (80, 80)], [(-300, -60), (90, 0), (-300, 60)]]):
+        d = _ellipse(10 + k, 260.0, 190.0, 0, 0)
+        d.update(obj_type=2, seg_begin=len(seg_type), seg_count=len(pts))
+        bps.append(rec(d))
+        for (x, y) in pts:
+            seg_type.append(1); seg_x.append(float(x)); seg_y.append(float(y))   # OFDG_SEG_LINE
+    task_begin.append(len(bps))
+    arrs = {"task_begin": np.array(task_begin, np.int32), "blueprints": np.array(bps, dt), "seg_type": np.array(seg_type, np.int32),
+            "seg_x": np.array(seg_x, np.float32), "seg_y": np.array(seg_y, np.float32), "augment": None}
+    tasks = ofdg.Tasks.from_arrays(arrs)
+    g = _gen(ofdg, 5)
+    g.upload_textures(textures8)
+    gpu = g.render_debug(tasks)
+    cpu = oracle.render(tasks.struct(), textures8, mode=5, debug=True)
+    _compare(gpu, cpu)
+    assert (gpu["id0"][0] == 1).all() and (gpu["id0"][1] == 1).all()          # nothing but background
+    assert (gpu["id0"][3] == 10).mean() > 0.95                                # the giant ellipse hides it
+    assert (gpu["id0"][2] != 1).any() and (gpu["masks"][4, :2] > 0).any()     # border objects and slivers leave a trace
+    # the collinear polygon is at most a hairline once its vertices are snapped to 1/256 px; the triangle covers an area
+    assert (gpu["masks"][5, 0, 0] > 0).sum() < 600 and (gpu["masks"][5, 1, 0] > 0).sum() > 2000
+    g.close()
+
+
+def test_argument_and_state_errors(ofdg, textures8):
+    import torch
+    g = _gen(ofdg, 7, max_batch=4)
+    tasks = ofdg.ParamStream(7).generate(2)
+    with pytest.raises(ofdg.OfdgError, match="no textures"):
+        g.render_host(tasks)
+    g.upload_textures(textures8)
+    with pytest.raises(ofdg.OfdgError, match="max_batch"):
+        g.render_host(ofdg.ParamStream(7).generate(5))
+    with pytest.raises(ofdg.OfdgError, match="empty"):
+        g.render_host(ofdg.Tasks())
+    many = ofdg.ParamStream(7, fg_override=300).generate(1)
+    with pytest.raises(ofdg.OfdgError, match="254"):
+        g.render_host(many)
+    a = tasks.arrays()
+    a["blueprints"]["tex_scale"][0] = 1e-6          # a background crop thousands of times the prepared size
+    with pytest.raises(ofdg.OfdgError, match="40x"):
+        g.render_host(ofdg.Tasks.from_arrays(a))
+    out = g.render_host(tasks)                       # the generator survives all of the above
+    assert out[0].std() > 10
+    g.close()
+    with pytest.raises(ofdg.OfdgError, match="BAD MODE"):
+        ofdg.Generator(device=0, mode=14)
+    with pytest.raises(ofdg.OfdgError, match="multiple of 4"):
+        ofdg.Generator(device=0, mode=1, width=510)
