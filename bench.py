@@ -335,7 +335,7 @@ def main():
     ap.add_argument("--height", type=int, default=384)
     ap.add_argument("--textures", type=int, default=1000)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture (profiles/)")
     args = ap.parse_args()

@@ -878,8 +878,12 @@ static void render_host_pipelined(ofdg_generator* g, ofdg_params* params, const 
   g->outf.reserve((size_t)n * 2 * P * sizeof(float));
   if (!g->workers) {
     // widening is bound by host memory bandwidth, not by cores: more threads than this only slow the DMA down
-    int threads = std::min((int)std::thread::hardware_concurrency() / 2, 16);
-    if (const char* lw = std::getenv("LOCAL_WORLD_SIZE")) threads /= std::max(1, std::atoi(lw));  // one process per GPU shares the host
+    const int hw = (int)std::thread::hardware_concurrency();
+    int threads = std::min(hw / 2, 16);
+    if (const char* lw = std::getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU shares the host: an equal share of the cores
+      const int local = std::max(1, std::atoi(lw));
+      if (local > 1) threads = hw / local - 1;
+    }
     if (const char* t = std::getenv("OFDG_HOST_THREADS")) threads = std::atoi(t);
     g->workers.reset(new ofdg::HostPool(std::max(2, std::min(threads, 64)), g->cfg.device));
   }
