@@ -157,6 +157,8 @@ int ofdg_prepare(ofdg_generator* g, const ofdg_task_batch* tasks, ofdg_prepared*
 void ofdg_prepared_destroy(ofdg_prepared* p);
 int ofdg_render_prepared(ofdg_generator* g, const ofdg_prepared* p, float* d_img0, float* d_img1, float* d_flow,
                          void* stream);
+/* The same into HOST blobs, through the pipelined host-blob path (what Forward_cpu uses). */
+int ofdg_render_prepared_host(ofdg_generator* g, const ofdg_prepared* p, float* h_img0, float* h_img1, float* h_flow);
 
 /* One-call producer used by the layer: draws `batch` tasks from `p` and renders them into device blobs. */
 int ofdg_generate(ofdg_generator* g, ofdg_params* p, int32_t batch, float* d_img0, float* d_img1, float* d_flow,

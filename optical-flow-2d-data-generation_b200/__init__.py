@@ -68,7 +68,7 @@ EXPORTS = [
     "ofdg_flatten_ellipse", "ofdg_flatten_polygon", "ofdg_debug_raster_host", "ofdg_debug_expand_host", "ofdg_create", "ofdg_destroy", "ofdg_upload_textures", "ofdg_add_textures", "ofdg_clear_textures", "ofdg_texture_size", "ofdg_download_foreground_view",
     "ofdg_synth_textures", "ofdg_download_texture", "ofdg_set_fields", "ofdg_generate_fields", "ofdg_render", "ofdg_render_host",
     "ofdg_render_debug", "ofdg_debug_background", "ofdg_debug_composite_luts", "ofdg_prepare", "ofdg_prepared_destroy",
-    "ofdg_render_prepared", "ofdg_generate", "ofdg_generate_host", "ofdg_generate_philox", "ofdg_philox_tasks", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_upload_bytes", "ofdg_last_download_bytes", "ofdg_set_extra_tops",
+    "ofdg_render_prepared", "ofdg_render_prepared_host", "ofdg_generate", "ofdg_generate_host", "ofdg_generate_philox", "ofdg_philox_tasks", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_upload_bytes", "ofdg_last_download_bytes", "ofdg_set_extra_tops",
 ]
 # include/ofdg/layer.h
 LAYER_EXPORTS = [
@@ -133,6 +133,7 @@ def lib():
         L.ofdg_prepare.argtypes = [C.c_void_p, C.POINTER(TaskBatchStruct), C.POINTER(C.c_void_p)]
         L.ofdg_prepared_destroy.argtypes = [C.c_void_p]
         L.ofdg_render_prepared.argtypes = [C.c_void_p] * 6
+        L.ofdg_render_prepared_host.argtypes = [C.c_void_p] * 5
         L.ofdg_generate_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 3
         L.ofdg_generate_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32] + [C.c_void_p] * 4
         L.ofdg_philox_tasks.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]
@@ -466,6 +467,16 @@ class Generator:
 
     def render_prepared(self, prepared, img0, img1, flow, stream=None):
         _check(lib().ofdg_render_prepared(self._h, prepared._h, img0.data_ptr(), img1.data_ptr(), flow.data_ptr(), stream))
+
+    def render_prepared_host(self, prepared, img0=None, img1=None, flow=None):
+        """A prepared batch into HOST blobs (numpy arrays or pinned torch tensors) through the pipelined host-blob path."""
+        n = prepared.n
+        img0 = np.empty((n, 3, self.H, self.W), np.float32) if img0 is None else img0
+        img1 = np.empty((n, 3, self.H, self.W), np.float32) if img1 is None else img1
+        flow = np.empty((n, 2, self.H, self.W), np.float32) if flow is None else flow
+        p = lambda a: a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+        _check(lib().ofdg_render_prepared_host(self._h, prepared._h, p(img0), p(img1), p(flow)))
+        return img0, img1, flow
 
     def generate(self, params, batch, img0, img1, flow, stream=None):
         _check(lib().ofdg_generate(self._h, params._h, batch, img0.data_ptr(), img1.data_ptr(), flow.data_ptr(), stream))

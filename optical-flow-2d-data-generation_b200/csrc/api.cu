@@ -121,6 +121,7 @@ struct ofdg_tasks {
 struct ofdg_prepared {
   DeviceScene scene;
   int device = 0;
+  bool augmented = false;  // some sample carries the float augmentation: its frames are not byte-valued
 };
 
 struct ofdg_generator {
@@ -352,9 +353,9 @@ cudaEvent_t timing_event(ofdg_generator* g) {
 // (Running the preparation of the next chunk on a second stream next to the render kernel was
 // measured and is slower: both kernels are issue-bound and the extra launches cost more than the
 // overlap gains -- profiles/README.md.)
-void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s) {
+void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s, bool deform_prepass = true) {
   if (g->spans.size() > 60000) { g->spans.clear(); g->ev_next = 0; g->timed_calls = 0; }  // nobody is reading the timings
-  g->launches += ofdg::launch_deform_prepass(a, s);
+  if (deform_prepass) g->launches += ofdg::launch_deform_prepass(a, s);
   ofdg_generator::Span sp{timing_event(g), timing_event(g), 0};
   CK(cudaEventRecord(sp.a, s));
   g->launches += ofdg::launch_bin(a, s);
@@ -859,11 +860,12 @@ int ofdg_render(ofdg_generator* g, const ofdg_task_batch* tasks, float* d_img0, 
 // per sample than three float blobs) and host threads widen them -- what the reference does on the host as the
 // last step of Process_TaskBucket (/root/reference/src/caffe/DataGenerator.cpp:1228-1244). The flow blob is
 // float all the way.
-static void render_host_pipelined(ofdg_generator* g, ofdg_params* params, const ofdg_task_batch* tasks, int n,
+static void render_host_pipelined(ofdg_generator* g, ofdg_params* params, const ofdg_task_batch* tasks, const ofdg_prepared* prepared, int n,
                                   float* h_img0, float* h_img1, float* h_flow) {
   const size_t P = (size_t)g->cfg.width * g->cfg.height;
   bool bytes = g->transport_u8;
   if (params && params->ps->augmentation_enabled()) bytes = false;
+  if (prepared && prepared->augmented) bytes = false;
   if (tasks && tasks->augment)
     for (int i = 0; i < n && bytes; ++i) bytes = tasks->augment[i].enabled == 0;
   // 4 samples per chunk: short chunks keep the pipeline's fill and drain short (measured: profiles/README.md)
@@ -928,7 +930,9 @@ static void render_host_pipelined(ofdg_generator* g, ofdg_params* params, const 
     if (v.augment) v.augment += i;
     return v;
   };
-  if (params) {
+  if (prepared) {
+    // the scene is already flattened and resident: chunks are windows of its sample array
+  } else if (params) {
     ofdg::ParamStream* ps = params->ps.get();
     g->workers->submit([g, ps, nchunk, chunk_of, submit_flatten, one_task, fail] {
       try {
@@ -953,22 +957,25 @@ static void render_host_pipelined(ofdg_generator* g, ofdg_params* params, const 
   try {
     for (int k = 0; k < nchunk; ++k) {
       const int t0 = chunk_of(k), t1 = chunk_of(k + 1), set = k & 1;
-      {
-        std::unique_lock<std::mutex> lk(sync.mu);
-        sync.cv.wait(lk, [&] { return sync.done[k] == t1 - t0 || !sync.error.empty(); });
-        if (!sync.error.empty()) throw ArgError(sync.error);
+      if (!prepared) {
+        {
+          std::unique_lock<std::mutex> lk(sync.mu);
+          sync.cv.wait(lk, [&] { return sync.done[k] == t1 - t0 || !sync.error.empty(); });
+          if (!sync.error.empty()) throw ArgError(sync.error);
+        }
+        t_ready[k] = now_ms();
+        if (k >= 2) CK(cudaEventSynchronize(g->pipe_uploaded[set]));  // the pinned staging area of this set is free again
+        upload_scene_parts(g, g->sample_flat.data() + t0, t1 - t0, g->pipe_scene[set], g->pipe_staging[set], A);
+        uploaded += g->last_upload_bytes;
+        CK(cudaEventRecord(g->pipe_uploaded[set], A));
       }
-      t_ready[k] = now_ms();
-      if (k >= 2) CK(cudaEventSynchronize(g->pipe_uploaded[set]));  // the pinned staging area of this set is free again
-      upload_scene_parts(g, g->sample_flat.data() + t0, t1 - t0, g->pipe_scene[set], g->pipe_staging[set], A);
-      uploaded += g->last_upload_bytes;
-      CK(cudaEventRecord(g->pipe_uploaded[set], A));
       float* d0 = bytes ? nullptr : (float*)g->out0.p + (size_t)t0 * 3 * P;
       float* d1 = bytes ? nullptr : (float*)g->out1.p + (size_t)t0 * 3 * P;
       float* df = (float*)g->outf.p + (size_t)t0 * 2 * P;
-      ofdg::RenderArgs a = make_args(g, g->pipe_scene[set], d0, d1, df);
+      ofdg::RenderArgs a = make_args(g, prepared ? prepared->scene : g->pipe_scene[set], d0, d1, df);
+      if (prepared) { a.samples += t0; a.batch = t1 - t0; }  // object / shape / vertex indices are absolute within the scene
       if (bytes) a.frames8 = (uint8_t*)g->out8.p + (size_t)t0 * 6 * P;
-      run_kernels(g, a, A);
+      run_kernels(g, a, A, !prepared || k == 0);  // a prepared scene's warped masks (mode 9) are made once, by the first chunk
       CK(cudaEventRecord(g->pipe_rendered[set], A));
       CK(cudaStreamWaitEvent(B, g->pipe_rendered[set], 0));
       const size_t c = (size_t)(t1 - t0);
@@ -1020,7 +1027,7 @@ int ofdg_render_host(ofdg_generator* g, const ofdg_task_batch* tasks, float* h_i
     if (!g || !tasks || !h_img0 || !h_img1 || !h_flow) throw ArgError("null pointer");
     check_batch(g, tasks->n_tasks);
     g->use();
-    render_host_pipelined(g, nullptr, tasks, tasks->n_tasks, h_img0, h_img1, h_flow);
+    render_host_pipelined(g, nullptr, tasks, nullptr, tasks->n_tasks, h_img0, h_img1, h_flow);
   });
 }
 
@@ -1029,7 +1036,7 @@ int ofdg_generate_host(ofdg_generator* g, ofdg_params* p, int32_t batch, float* 
     if (!g || !p || !h_img0 || !h_img1 || !h_flow) throw ArgError("null pointer");
     check_batch(g, batch);
     g->use();
-    render_host_pipelined(g, p, nullptr, batch, h_img0, h_img1, h_flow);
+    render_host_pipelined(g, p, nullptr, nullptr, batch, h_img0, h_img1, h_flow);
   });
 }
 
@@ -1282,6 +1289,8 @@ int ofdg_prepare(ofdg_generator* g, const ofdg_task_batch* tasks, ofdg_prepared*
     flatten_tasks(g, tasks);
     std::unique_ptr<ofdg_prepared> p(new ofdg_prepared);
     p->device = g->cfg.device;
+    if (tasks->augment)
+      for (int i = 0; i < tasks->n_tasks; ++i) p->augmented = p->augmented || tasks->augment[i].enabled != 0;
     upload_scene(g, g->flat, p->scene, g->staging, g->stream);
     CK(cudaStreamSynchronize(g->stream));
     *out = p.release();
@@ -1302,6 +1311,15 @@ int ofdg_render_prepared(ofdg_generator* g, const ofdg_prepared* p, float* d_img
     ensure_scratch(g, p->scene.batch);
     run_kernels(g, with_extra_tops(g, make_args(g, p->scene, d_img0, d_img1, d_flow)), s);
     if (!stream) CK(cudaStreamSynchronize(s));
+  });
+}
+
+int ofdg_render_prepared_host(ofdg_generator* g, const ofdg_prepared* p, float* h_img0, float* h_img1, float* h_flow) {
+  return guarded([&] {
+    if (!g || !p || !h_img0 || !h_img1 || !h_flow) throw ArgError("null pointer");
+    check_batch(g, p->scene.batch);
+    g->use();
+    render_host_pipelined(g, nullptr, nullptr, p, p->scene.batch, h_img0, h_img1, h_flow);
   });
 }
 

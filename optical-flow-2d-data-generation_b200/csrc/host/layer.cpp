@@ -343,6 +343,22 @@ void DataGenerationLayer<Dtype>::InternalThreadEntry() {
   }
 }
 
+// prefetch_full_.pop("Data layer prefetch queue empty"), data_generation_layer.cpp:270
+template <typename Dtype>
+ofdg_prepared* DataGenerationLayer<Dtype>::PopPrefetched() {
+  ofdg_prepared* p = nullptr;
+  {
+    std::unique_lock<std::mutex> l(mutex_);
+    cv_full_.wait(l, [this] { return !prefetch_full_.empty() || !producer_error_.empty() || must_stop_; });
+    if (!producer_error_.empty()) throw std::runtime_error(producer_error_);
+    if (prefetch_full_.empty()) throw std::runtime_error("Data layer prefetch queue empty");
+    p = prefetch_full_.front();
+    prefetch_full_.pop_front();
+  }
+  cv_free_.notify_one();
+  return p;
+}
+
 template <typename Dtype>
 void DataGenerationLayer<Dtype>::Forward_gpu(const std::vector<Blob<Dtype>*>& bottom, const std::vector<Blob<Dtype>*>& top) {
   const DataGenerationParameter& gp = this->layer_param_.data_generation_param();
@@ -360,16 +376,7 @@ void DataGenerationLayer<Dtype>::Forward_gpu(const std::vector<Blob<Dtype>*>& bo
     ++device_batches_;
     return;
   }
-  ofdg_prepared* p = nullptr;
-  {
-    std::unique_lock<std::mutex> l(mutex_);  // prefetch_full_.pop("Data layer prefetch queue empty")
-    cv_full_.wait(l, [this] { return !prefetch_full_.empty() || !producer_error_.empty() || must_stop_; });
-    if (!producer_error_.empty()) throw std::runtime_error(producer_error_);
-    if (prefetch_full_.empty()) throw std::runtime_error("Data layer prefetch queue empty");
-    p = prefetch_full_.front();
-    prefetch_full_.pop_front();
-  }
-  cv_free_.notify_one();
+  ofdg_prepared* p = PopPrefetched();
   const int batch_size = this->layer_param_.data_param().batch_size();
   top[0]->Reshape({batch_size, 3, 384, 512});
   top[1]->Reshape({batch_size, 3, 384, 512});
@@ -386,10 +393,28 @@ void DataGenerationLayer<Dtype>::Forward_gpu(const std::vector<Blob<Dtype>*>& bo
 
 template <typename Dtype>
 void DataGenerationLayer<Dtype>::Forward_cpu(const std::vector<Blob<Dtype>*>& bottom, const std::vector<Blob<Dtype>*>& top) {
-  // There is no CPU generator any more: the blobs are produced on the device and become visible to
-  // cpu_data() through the usual synced-memory copy.
-  Forward_gpu(bottom, top);
-  for (size_t i = 0; i < top.size(); ++i) top[i]->cpu_data();
+  // There is no CPU generator any more. With the reference's three tops and the host parameter stream the blobs are
+  // produced straight into cpu_data() by the pipelined host-blob path (frames cross PCIe as bytes, host threads widen them:
+  // the copy-out of Process_TaskBucket, DataGenerator.cpp:1228-1244). Otherwise (extra tops, device-side stream) they are
+  // produced on the device and become visible through the usual synced-memory copy.
+  const DataGenerationParameter& gp = this->layer_param_.data_generation_param();
+  if (top.size() != 3 || gp.device_params()) {
+    Forward_gpu(bottom, top);
+    for (size_t i = 0; i < top.size(); ++i) top[i]->cpu_data();
+    return;
+  }
+  ofdg_prepared* p = PopPrefetched();
+  const int batch_size = this->layer_param_.data_param().batch_size();
+  top[0]->Reshape({batch_size, 3, 384, 512});
+  top[1]->Reshape({batch_size, 3, 384, 512});
+  top[2]->Reshape({batch_size, 2, 384, 512});
+  int rc;
+  {
+    std::lock_guard<std::mutex> g(generator_mutex_);
+    rc = ofdg_render_prepared_host(generator_, p, top[0]->mutable_cpu_data(), top[1]->mutable_cpu_data(), top[2]->mutable_cpu_data());
+  }
+  ofdg_prepared_destroy(p);
+  if (rc != OFDG_OK) throw std::runtime_error(ofdg_last_error());
 }
 
 template <typename Dtype>

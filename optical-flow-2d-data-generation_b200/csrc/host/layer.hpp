@@ -48,6 +48,7 @@ class DataGenerationLayer : public Layer<Dtype> {
   virtual void load_batch(ofdg_prepared** out);       // draw + flatten + upload one batch
   void StartInternalThread();
   void StopInternalThread();
+  ofdg_prepared* PopPrefetched();                      // blocks until the producer has a batch
   void BindExtraTops(const std::vector<Blob<Dtype>*>& top);  // top[3..6]: backward flow, occlusion, index images
 
   static int solver_rank_;

@@ -452,3 +452,25 @@ def test_argument_and_state_errors(ofdg, textures8):
         ofdg.Generator(device=0, mode=14)
     with pytest.raises(ofdg.OfdgError, match="multiple of 4"):
         ofdg.Generator(device=0, mode=1, width=510)
+
+
+@pytest.mark.parametrize("mode", [7, 9])
+def test_prepared_batches_into_host_blobs(ofdg, oracle, textures8, fields4, mode):
+    """ofdg_render_prepared_host (the layer's Forward_cpu): chunked windows over a resident scene, uint8 transport,
+    mode 9's warped masks made once -- identical to rendering the prepared batch into device blobs."""
+    import torch
+    n = 12
+    g = _gen(ofdg, mode)
+    g.upload_textures(textures8)
+    if mode == 9:
+        g.set_fields(fields4)
+    tasks = ofdg.ParamStream(mode, n_fields=4 if mode == 9 else 0).generate(n)
+    p = g.prepare(tasks)
+    dev = [torch.empty((n, c, 384, 512), device="cuda") for c in (3, 3, 2)]
+    g.render_prepared(p, *dev)
+    torch.cuda.synchronize()
+    host = g.render_prepared_host(p)
+    for d, h in zip(dev, host):
+        assert np.array_equal(d.cpu().numpy(), h, equal_nan=True)
+    assert g.last_download_bytes() == n * (6 + 8) * 384 * 512
+    g.close()
