@@ -892,6 +892,39 @@ __device__ __forceinline__ uint32_t rotated_px(const uchar4* tex, int w, int h, 
   return out;
 }
 
+// Fast form of rotated_px for source tiles that provably stay clear of every boundary rule: the rotated sample positions
+// lie strictly inside the texture (cimg::mod, the mirror fold and the Neumann clamp of get_rotate are identities) and the
+// taps fall into one affine piece of get_shift's mirror boundary, column = cx0 + cs * X, row = ry0 + rs * Y.
+struct TapMap { int cx0, cs, ry0, rs; };
+__device__ __forceinline__ bool tap_axis(int lo, int hi, int shift, int n, int& c0, int& sg) {
+  if (lo - shift >= 0 && hi - shift < n) { c0 = -shift; sg = 1; return true; }        // mirror(i, n) = i
+  if (hi - shift < 0 && lo - shift >= -n) { c0 = shift - 1; sg = -1; return true; }   // mirror(i, n) = -i - 1
+  return false;
+}
+__device__ __forceinline__ void rotated_pos(const BgPrep& p, int x, int y, float& fx, float& fy) {
+  const float xc = x - p.rw2, yc = y - p.rh2;
+  fx = p.w2 + xc * p.ca + yc * p.sa;
+  fy = p.h2 - xc * p.sa + yc * p.ca;
+}
+__device__ __forceinline__ uint32_t rotated_px_fast(const uchar4* tex, int w, const BgPrep& p, const TapMap& m, int x, int y) {
+  float fx, fy;
+  rotated_pos(p, x, y, fx, fy);
+  const unsigned int ix = (unsigned int)fx, iy = (unsigned int)fy;
+  const float dx = fx - ix, dy = fy - iy;
+  const uchar4* t00 = tex + (ptrdiff_t)(m.ry0 + m.rs * (int)iy) * w + (m.cx0 + m.cs * (int)ix);
+  const ptrdiff_t ox = dx > 0 ? m.cs : 0, oy = dy > 0 ? (ptrdiff_t)m.rs * w : 0;
+  const uint32_t pcc = ld_px(t00) & 0xFFFFFFu, pnc = ld_px(t00 + ox) & 0xFFFFFFu, pcn = ld_px(t00 + oy) & 0xFFFFFFu,
+                 pnn = ld_px(t00 + ox + oy) & 0xFFFFFFu;
+  uint32_t out = 0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float Icc = byte_to_float(pcc, c), Inc = byte_to_float(pnc, c), Icn = byte_to_float(pcn, c), Inn = byte_to_float(pnn, c);
+    const float v = Icc + dx * (Inc - Icc + dy * (Icc + Inn - Icn - Inc)) + dy * (Icn - Icc);
+    out |= ((uint32_t)(unsigned char)v) << (8 * c);
+  }
+  return out;
+}
+
 // One resize pass (CImg get_resize interpolation 3; shrinking axes use the moving average)
 // evaluated at output index t from a line of source pixels src[(s - s0) * stride].
 // One output index of a resize pass (CImg get_resize interpolation 3; shrinking axes use the moving average)
@@ -1070,11 +1103,30 @@ __global__ void __launch_bounds__(PREP_THREADS) bg_prep_kernel(RenderArgs a) {
     int lx = (int)threadIdx.x % cw, ly = (int)threadIdx.x / cw;
     const int bx = p.crop_x0 + cx0, by = p.crop_y0 + cy0;
     const bool inside = bx >= 0 && by >= 0 && bx + cw <= p.rw && by + ch <= p.rh;  // the crop's mirror boundary is not in play for this tile
-    while (ly < ch) {
-      const int rx = inside ? bx + lx : mirror(bx + lx, p.rw), ry = inside ? by + ly : mirror(by + ly, p.rh);
-      sA[ly][lx] = rotated_px(tex, ti.w, ti.h, p, rx, ry);
-      lx += step_x; ly += step_y;
-      if (lx >= cw) { lx -= cw; ++ly; }
+    TapMap tm;
+    bool fast = false;
+    if (inside && !p.rot_identity) {  // the sample positions are affine in (x, y): their extremes sit at the tile's corners
+      float x0f, y0f, x1f, y1f, x2f, y2f, x3f, y3f;
+      rotated_pos(p, bx, by, x0f, y0f); rotated_pos(p, bx + cw - 1, by, x1f, y1f);
+      rotated_pos(p, bx, by + ch - 1, x2f, y2f); rotated_pos(p, bx + cw - 1, by + ch - 1, x3f, y3f);
+      const float xl = fminf(fminf(x0f, x1f), fminf(x2f, x3f)), xh = fmaxf(fmaxf(x0f, x1f), fmaxf(x2f, x3f));
+      const float yl = fminf(fminf(y0f, y1f), fminf(y2f, y3f)), yh = fmaxf(fmaxf(y0f, y1f), fmaxf(y2f, y3f));
+      if (xl >= 2.f && xh <= (float)(ti.w - 3) && yl >= 2.f && yh <= (float)(ti.h - 3))  // one texel of slack for rounding inside the tile
+        fast = tap_axis((int)xl - 1, (int)xh + 2, p.shift_x, ti.w, tm.cx0, tm.cs) && tap_axis((int)yl - 1, (int)yh + 2, p.shift_y, ti.h, tm.ry0, tm.rs);
+    }
+    if (fast) {
+      while (ly < ch) {
+        sA[ly][lx] = rotated_px_fast(tex, ti.w, p, tm, bx + lx, by + ly);
+        lx += step_x; ly += step_y;
+        if (lx >= cw) { lx -= cw; ++ly; }
+      }
+    } else {
+      while (ly < ch) {
+        const int rx = inside ? bx + lx : mirror(bx + lx, p.rw), ry = inside ? by + ly : mirror(by + ly, p.rh);
+        sA[ly][lx] = rotated_px(tex, ti.w, ti.h, p, rx, ry);
+        lx += step_x; ly += step_y;
+        if (lx >= cw) { lx -= cw; ++ly; }
+      }
     }
   }
   __syncthreads();
