@@ -906,11 +906,19 @@ __device__ __forceinline__ void rotated_pos(const BgPrep& p, int x, int y, float
   fx = p.w2 + xc * p.ca + yc * p.sa;
   fy = p.h2 - xc * p.sa + yc * p.ca;
 }
-__device__ __forceinline__ uint32_t rotated_px_fast(const uchar4* tex, int w, const BgPrep& p, const TapMap& m, int x, int y) {
-  float fx, fy;
-  rotated_pos(p, x, y, fx, fy);
-  const unsigned int ix = (unsigned int)fx, iy = (unsigned int)fy;
-  const float dx = fx - ix, dy = fy - iy;
+// floor of 0 <= v < 2^22 without the conversion unit: adding 2^23 rounding down leaves floor(v) in the low mantissa bits,
+// and subtracting 2^23 again gives it back as a float (both exact)
+__device__ __forceinline__ unsigned floor_bits(float v, float& as_float) {
+  const float t = __fadd_rd(v, 8388608.0f);
+  as_float = t - 8388608.0f;
+  return __float_as_uint(t) & 0x7FFFFFu;
+}
+__device__ __forceinline__ uint32_t rotated_px_fast(const uchar4* tex, int w, const BgPrep& p, const TapMap& m, float xf, float yf) {
+  const float xc = xf - p.rw2, yc = yf - p.rh2;  // xf, yf: the pixel coordinates as floats (exact)
+  const float fx = p.w2 + xc * p.ca + yc * p.sa, fy = p.h2 - xc * p.sa + yc * p.ca;
+  float fix, fiy;
+  const unsigned int ix = floor_bits(fx, fix), iy = floor_bits(fy, fiy);  // == (unsigned int)fx: fx, fy > 0
+  const float dx = fx - fix, dy = fy - fiy;
   const uchar4* t00 = tex + (ptrdiff_t)(m.ry0 + m.rs * (int)iy) * w + (m.cx0 + m.cs * (int)ix);
   const ptrdiff_t ox = dx > 0 ? m.cs : 0, oy = dy > 0 ? (ptrdiff_t)m.rs * w : 0;
   const uint32_t pcc = ld_px(t00) & 0xFFFFFFu, pnc = ld_px(t00 + ox) & 0xFFFFFFu, pcn = ld_px(t00 + oy) & 0xFFFFFFu,
@@ -920,7 +928,8 @@ __device__ __forceinline__ uint32_t rotated_px_fast(const uchar4* tex, int w, co
   for (int c = 0; c < 3; ++c) {
     const float Icc = byte_to_float(pcc, c), Inc = byte_to_float(pnc, c), Icn = byte_to_float(pcn, c), Inn = byte_to_float(pnn, c);
     const float v = Icc + dx * (Inc - Icc + dy * (Icc + Inn - Icn - Inc)) + dy * (Icn - Icc);
-    out |= ((uint32_t)(unsigned char)v) << (8 * c);
+    // (unsigned char)v for 0 <= v <= 255: truncate through the same mantissa trick (round towards zero)
+    out |= (__float_as_uint(__fadd_rz(fmaxf(v, 0.f), 8388608.0f)) & 255u) << (8 * c);  // (a rounding residue below zero also truncates to 0)
   }
   return out;
 }
@@ -1115,10 +1124,12 @@ __global__ void __launch_bounds__(PREP_THREADS) bg_prep_kernel(RenderArgs a) {
         fast = tap_axis((int)xl - 1, (int)xh + 2, p.shift_x, ti.w, tm.cx0, tm.cs) && tap_axis((int)yl - 1, (int)yh + 2, p.shift_y, ti.h, tm.ry0, tm.rs);
     }
     if (fast) {
+      float xf = (float)(bx + lx), yf = (float)(by + ly);  // float twins of the walk (small integers: exact)
+      const float fstep_x = (float)step_x, fstep_y = (float)step_y, fcw = (float)cw;
       while (ly < ch) {
-        sA[ly][lx] = rotated_px_fast(tex, ti.w, p, tm, bx + lx, by + ly);
-        lx += step_x; ly += step_y;
-        if (lx >= cw) { lx -= cw; ++ly; }
+        sA[ly][lx] = rotated_px_fast(tex, ti.w, p, tm, xf, yf);
+        lx += step_x; ly += step_y; xf += fstep_x; yf += fstep_y;
+        if (lx >= cw) { lx -= cw; ++ly; xf -= fcw; yf += 1.f; }
       }
     } else {
       while (ly < ch) {
