@@ -1098,31 +1098,52 @@ __global__ void __launch_bounds__(PREP_THREADS) bg_prep_kernel(RenderArgs a) {
     bg_prep_general(a, p, tex, ti.w, ti.h, X0, Y0, X1, Y1, pos_x, alpha_x, pos_y, alpha_y, sA, sB, out);
     return;
   }
-  int cx0, cx1, cy0, cy1;
-  source_range32(p.crop_w, W2, X0, X1, pos_x, cx0, cx1);
-  source_range32(p.crop_h, H2, Y0, Y1, pos_y, cy0, cy1);
-  const int cw = cx1 - cx0 + 1, ch = cy1 - cy0 + 1;  // <= PS by construction
-  const int tw = X1 - X0 + 1, th = Y1 - Y0 + 1;
-  const unsigned magic_x = 0xFFFFFFFFu / (unsigned)p.crop_w + 1u, magic_y = 0xFFFFFFFFu / (unsigned)p.crop_h + 1u;
-  if ((int)threadIdx.x < th) sTy[threadIdx.x] = make_taps(p.crop_h, H2, Y0 + (int)threadIdx.x, pos_y, alpha_y);  // visible after the barriers below
-  // A: crop(x0, y0, .., mirror) of the rotated image
-  const int lane_x = threadIdx.x & 31, lane_y = threadIdx.x >> 5;
-  {  // all lanes busy: walk the cw x ch source tile linearly, stepping (x, y) by 256 items without a divide per item
-    const int step_y = PREP_THREADS / cw, step_x = PREP_THREADS % cw;
-    int lx = (int)threadIdx.x % cw, ly = (int)threadIdx.x / cw;
-    const int bx = p.crop_x0 + cx0, by = p.crop_y0 + cy0;
-    const bool inside = bx >= 0 && by >= 0 && bx + cw <= p.rw && by + ch <= p.rh;  // the crop's mirror boundary is not in play for this tile
+  // Per-tile constants (source ranges, multiply-high constants, the walk's steps, the fast-path test): a dozen integer
+  // divisions and four corner evaluations that are the same for all 256 threads -- warp 0 works them out, the others
+  // pick them up from shared memory (the kernel is issue-bound: seven warps' worth of redundant instructions saved).
+  __shared__ struct TileConst {
+    int cx0, cy0, cw, ch, step_x, step_y, inv_cw, bx, by, inside, fast;
+    unsigned magic_x, magic_y;
     TapMap tm;
-    bool fast = false;
-    if (inside && !p.rot_identity) {  // the sample positions are affine in (x, y): their extremes sit at the tile's corners
+  } sC;
+  const int tw = X1 - X0 + 1, th = Y1 - Y0 + 1;
+  if (threadIdx.x < 32) {
+    TileConst c;
+    int cx1, cy1;
+    source_range32(p.crop_w, W2, X0, X1, pos_x, c.cx0, cx1);
+    source_range32(p.crop_h, H2, Y0, Y1, pos_y, c.cy0, cy1);
+    c.cw = cx1 - c.cx0 + 1; c.ch = cy1 - c.cy0 + 1;  // <= PS by construction
+    c.magic_x = 0xFFFFFFFFu / (unsigned)p.crop_w + 1u; c.magic_y = 0xFFFFFFFFu / (unsigned)p.crop_h + 1u;
+    c.step_y = PREP_THREADS / c.cw; c.step_x = PREP_THREADS % c.cw;
+    c.inv_cw = 65536 / c.cw + 1;  // t / cw == (t * inv_cw) >> 16 for t < 256, cw <= 46
+    c.bx = p.crop_x0 + c.cx0; c.by = p.crop_y0 + c.cy0;
+    c.inside = c.bx >= 0 && c.by >= 0 && c.bx + c.cw <= p.rw && c.by + c.ch <= p.rh;  // the crop's mirror boundary is not in play for this tile
+    c.fast = 0;
+    c.tm = TapMap{0, 0, 0, 0};
+    if (c.inside && !p.rot_identity) {  // the sample positions are affine in (x, y): their extremes sit at the tile's corners
       float x0f, y0f, x1f, y1f, x2f, y2f, x3f, y3f;
-      rotated_pos(p, bx, by, x0f, y0f); rotated_pos(p, bx + cw - 1, by, x1f, y1f);
-      rotated_pos(p, bx, by + ch - 1, x2f, y2f); rotated_pos(p, bx + cw - 1, by + ch - 1, x3f, y3f);
+      rotated_pos(p, c.bx, c.by, x0f, y0f); rotated_pos(p, c.bx + c.cw - 1, c.by, x1f, y1f);
+      rotated_pos(p, c.bx, c.by + c.ch - 1, x2f, y2f); rotated_pos(p, c.bx + c.cw - 1, c.by + c.ch - 1, x3f, y3f);
       const float xl = fminf(fminf(x0f, x1f), fminf(x2f, x3f)), xh = fmaxf(fmaxf(x0f, x1f), fmaxf(x2f, x3f));
       const float yl = fminf(fminf(y0f, y1f), fminf(y2f, y3f)), yh = fmaxf(fmaxf(y0f, y1f), fmaxf(y2f, y3f));
       if (xl >= 2.f && xh <= (float)(ti.w - 3) && yl >= 2.f && yh <= (float)(ti.h - 3))  // one texel of slack for rounding inside the tile
-        fast = tap_axis((int)xl - 1, (int)xh + 2, p.shift_x, ti.w, tm.cx0, tm.cs) && tap_axis((int)yl - 1, (int)yh + 2, p.shift_y, ti.h, tm.ry0, tm.rs);
+        c.fast = tap_axis((int)xl - 1, (int)xh + 2, p.shift_x, ti.w, c.tm.cx0, c.tm.cs) && tap_axis((int)yl - 1, (int)yh + 2, p.shift_y, ti.h, c.tm.ry0, c.tm.rs);
     }
+    if (threadIdx.x == 0) sC = c;
+  }
+  if ((int)threadIdx.x >= 32 && (int)threadIdx.x < 32 + th)   // taps of the tile's output rows (warp 1; visible after the barriers below)
+    sTy[threadIdx.x - 32] = make_taps(p.crop_h, H2, Y0 + (int)threadIdx.x - 32, pos_y, alpha_y);
+  __syncthreads();
+  const int cx0 = sC.cx0, cy0 = sC.cy0, cw = sC.cw, ch = sC.ch;
+  const unsigned magic_x = sC.magic_x, magic_y = sC.magic_y;
+  // A: crop(x0, y0, .., mirror) of the rotated image
+  const int lane_x = threadIdx.x & 31, lane_y = threadIdx.x >> 5;
+  {  // all lanes busy: walk the cw x ch source tile linearly, stepping (x, y) by 256 items without a divide per item
+    const int step_y = sC.step_y, step_x = sC.step_x;
+    int ly = ((int)threadIdx.x * sC.inv_cw) >> 16, lx = (int)threadIdx.x - ly * cw;
+    const int bx = sC.bx, by = sC.by;
+    const bool inside = sC.inside != 0, fast = sC.fast != 0;
+    const TapMap tm = sC.tm;
     if (fast) {
       float xf = (float)(bx + lx), yf = (float)(by + ly);  // float twins of the walk (small integers: exact)
       const float fstep_x = (float)step_x, fstep_y = (float)step_y, fcw = (float)cw;
