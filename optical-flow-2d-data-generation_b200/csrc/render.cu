@@ -326,7 +326,8 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
   const uint8_t* bins = a.tile_hits + ((size_t)sample * gridDim.x + blockIdx.x) * TILE_HIT_STRIDE;
   const int binned = bins[0];  // objects touching this tile (255: more than a bin entry lists)
 
-  for (int i = tid; i < 256; i += RENDER_THREADS) s_q255[i] = (float)i / 255.f;
+  if (binned)  // the composite rules' quotient table: only tiles with objects can need it
+    for (int i = tid; i < 256; i += RENDER_THREADS) s_q255[i] = (float)i / 255.f;
 
   // ---- pass set-up, entirely inside warp 0 (the other warps fetch the background meanwhile):
   //      hit table -> outline jobs -> accumulator layers and chunk boundaries
