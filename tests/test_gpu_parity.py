@@ -474,3 +474,18 @@ def test_prepared_batches_into_host_blobs(ofdg, oracle, textures8, fields4, mode
         assert np.array_equal(d.cpu().numpy(), h, equal_nan=True)
     assert g.last_download_bytes() == n * (6 + 8) * 384 * 512
     g.close()
+
+
+@pytest.mark.parametrize("W,H", [(260, 150), (132, 84)])
+def test_frame_sizes_off_the_tile_grid(ofdg, oracle, textures8, W, H):
+    """Runtime frame sizes that are no multiple of the 128 x 8 render tile or the 32 x 32 preparation tile (the reference
+    fixes 512 x 384 at compile time, DataGenerator.h:55-56): partial tiles at the right and bottom borders."""
+    g = ofdg.Generator(device=0, width=W, height=H, mode=7, max_batch=3)
+    g.upload_textures(textures8)
+    tasks = ofdg.ParamStream(7, W, H).generate(3)
+    gpu = g.render_debug(tasks)
+    cpu = oracle.render(tasks.struct(), textures8, W=W, H=H, mode=7, debug=True)
+    _compare(gpu, cpu)
+    host = g.render_host(tasks)          # chunked uint8 transport with planes that are not 64-byte multiples
+    assert np.array_equal(host[0], gpu["img0"]) and np.array_equal(host[2], gpu["flow"])
+    g.close()
