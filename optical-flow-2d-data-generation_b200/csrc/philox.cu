@@ -265,8 +265,13 @@ __device__ void gen_object(Gen& g, SampleOut& o, int idx, int n_fields, int& fie
   o.bp[idx] = b;
 }
 
-__global__ void philox_params_kernel(PhiloxArgs a) {
-  const int s = blockIdx.x, k = threadIdx.x;  // sample, object (thread kPhiloxMaxObj: background and sample-level draws)
+// One WARP per (sample, role), lane 0 working: the roles of a sample (its objects, its background) run through very
+// different branches and loop counts, so as threads of one warp they would execute one after the other.
+constexpr int kParamWarps = (kPhiloxMaxObj + 2) / 2;  // roles per block; two blocks per sample
+__global__ void __launch_bounds__(32 * kParamWarps) philox_params_kernel(PhiloxArgs a) {
+  if (threadIdx.x & 31) return;
+  const int s = blockIdx.x, k = blockIdx.y * kParamWarps + (threadIdx.x >> 5);  // sample, role: object k, or kPhiloxMaxObj = background and sample-level draws
+  if (k > kPhiloxMaxObj) return;
   Gen g;
   g.slots = a.slots;
   g.mode = a.mode;
@@ -577,7 +582,7 @@ void philox_upload_circle(const double* c, const double* s) {
 }
 
 int launch_philox(const PhiloxArgs& a, cudaStream_t s) {
-  philox_params_kernel<<<a.batch, kPhiloxMaxObj + 1, 0, s>>>(a);
+  philox_params_kernel<<<dim3(a.batch, 2), 32 * kParamWarps, 0, s>>>(a);
   philox_flatten_kernel<<<dim3(a.batch, kPhiloxMaxObj / kFlatObjPerBlock + 1), kFlatObjPerBlock * kFlatLanes, 0, s>>>(a);
   return 2;
 }
