@@ -205,6 +205,9 @@ uint64_t ofdg_launch_count(const ofdg_generator* g);
  * preparation kernels and in the render kernel over the render calls made since the previous
  * call of this function (synchronises; resets the accumulation). */
 int ofdg_kernel_times(ofdg_generator* g, double* prep_ms, double* render_ms, int32_t* calls);
+/* Of the render time the last ofdg_kernel_times call reported: the part spent in the shade kernel (the kernel that reads the
+ * textures and writes the blobs; the rest is binning and mask rasterisation). 0 with OFDG_RENDER=fused. */
+double ofdg_last_shade_ms(const ofdg_generator* g);
 /* Bytes of flattened scene data the last render/prepare call copied host-to-device. */
 uint64_t ofdg_last_upload_bytes(const ofdg_generator* g);
 /* Bytes the last ofdg_render_host / ofdg_generate_host call copied device-to-host. The frames cross

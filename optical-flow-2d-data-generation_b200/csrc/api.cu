@@ -107,6 +107,7 @@ struct PinnedBuf {  // pinned and mapped: kernels can read it through `dev`
 struct DeviceScene {
   DevBuf samples, objects, shapes, verts, deform_shape, deform_field;
   int batch = 0, n_deform = 0;
+  size_t pair_bound = 0;  // upper bound of the scene's (object, tile) pairs: sizes the split render path's mask buffer
   void release() { samples.release(); objects.release(); shapes.release(); verts.release(); deform_shape.release(); deform_field.release(); }
 };
 
@@ -128,7 +129,7 @@ struct ofdg_generator {
   ofdg_config cfg{};
   cudaStream_t stream = nullptr;
   // CUDA-event spans around every background-preparation / render launch (roofline timing)
-  struct Span { cudaEvent_t a, b; int kind; };  // kind 0 = background preparation, 1 = render
+  struct Span { cudaEvent_t a, b; int kind; };  // kind 0 = background preparation, 1 = render (all of it), 2 = the shade kernel alone
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_next = 0;
   std::vector<Span> spans;
@@ -164,6 +165,10 @@ struct ofdg_generator {
   DeviceScene scene;
   PinnedBuf staging;
   DevBuf bg, tile_hits;
+  // split render path: per-tile pair ranges, the pair list, the pairs' masks, control words (csrc/render.cuh)
+  DevBuf tile_range, pair_list, pair_masks, pair_ctl;
+  int pair_cap = 0;
+  bool split_render = true;  // OFDG_RENDER=fused selects the single-kernel path
   DevBuf out0, out1, outf;  // device blobs for the *_host entry points
   ofdg_extra_tops extra{};  // extra tops of the device-blob calls (ofdg_set_extra_tops)
   DevBuf ids8;              // object ranks per pixel, scratch of the occlusion pass
@@ -197,6 +202,7 @@ struct ofdg_generator {
   uint64_t render_calls = 0;
   uint64_t launches = 0;
   float last_kernel_ms = 0.f;
+  double last_shade_ms = 0.0;  // of the spans ofdg_kernel_times summed last
 
   void use() const { CK(cudaSetDevice(cfg.device)); }
 };
@@ -255,6 +261,18 @@ void upload_scene_parts(ofdg_generator* g, const ofdg::FlatBatch* parts, int n_p
   if (nd) { ds.deform_shape.reserve(bd + 256); ds.deform_field.reserve(bd + 256); }  // mode 9 only
   ds.batch = (int)ns;
   ds.n_deform = (int)nd;
+  {  // (object, tile) pairs: per frame the tile columns x tile rows the object's box overlaps (bin_pairs_kernel counts the union)
+    const int tiles_x = (g->cfg.width + ofdg::TW - 1) / ofdg::TW, tiles_y = (g->cfg.height + ofdg::TH - 1) / ofdg::TH;
+    size_t pairs = 0;
+    for (int i = 0; i < n_parts; ++i)
+      for (const ofdg::FlatObject& o : parts[i].objects)
+        for (int f = 0; f < 2; ++f) {
+          const int c0 = std::max(0, o.bbox[f][0] >= 0 ? o.bbox[f][0] / ofdg::TW : 0), c1 = std::min(tiles_x - 1, o.bbox[f][2] >= 0 ? o.bbox[f][2] / ofdg::TW : -1);
+          const int r0 = std::max(0, o.bbox[f][1] >= 0 ? o.bbox[f][1] / ofdg::TH : 0), r1 = std::min(tiles_y - 1, o.bbox[f][3] >= 0 ? o.bbox[f][3] / ofdg::TH : -1);
+          if (c1 >= c0 && r1 >= r0) pairs += (size_t)(c1 - c0 + 1) * (r1 - r0 + 1);
+        }
+    ds.pair_bound = pairs;
+  }
   ofdg::UploadSegments u{};
   const char* dv = (const char*)staging.dev;
   auto seg = [&u, dv](void* dst, size_t off, size_t bytes) {
@@ -294,6 +312,11 @@ void ensure_scratch(ofdg_generator* g, int batch) {
   const size_t W = g->cfg.width, H = g->cfg.height;
   g->bg.reserve((size_t)batch * 4 * W * H * sizeof(uchar4));
   g->tile_hits.reserve(ofdg::tile_hits_bytes(batch, (int)W, (int)H));
+  if (g->split_render) {
+    const size_t tiles = ofdg::tile_hits_bytes(1, (int)W, (int)H) / ofdg::TILE_HIT_STRIDE;
+    g->tile_range.reserve((size_t)batch * tiles * sizeof(int2));
+    g->pair_ctl.reserve(2 * sizeof(int));
+  }
   g->scratch_batch = batch;
 }
 
@@ -310,6 +333,17 @@ ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, 
   a.tex_info = (const ofdg::TexInfo*)g->tex_info_dev.p;
   a.bg = (uchar4*)g->bg.p;
   a.tile_hits = (uint8_t*)g->tile_hits.p;
+  if (g->split_render) {
+    if (ds.pair_bound > (size_t)g->pair_cap) {  // grow the pair buffers (4 KB of masks per pair); earlier launches may still use the old ones
+      CK(cudaDeviceSynchronize());
+      const size_t cap = std::max<size_t>(ds.pair_bound + ds.pair_bound / 4, 4096);
+      g->pair_list.reserve(cap * sizeof(int2));
+      g->pair_masks.reserve(cap * ofdg::pair_mask_bytes_per_pair());
+      g->pair_cap = (int)cap;
+    }
+    a.tile_range = (int2*)g->tile_range.p; a.pair_list = (int2*)g->pair_list.p; a.pair_masks = (uint32_t*)g->pair_masks.p;
+    a.pair_ctl = (int*)g->pair_ctl.p; a.pair_cap = g->pair_cap;
+  }
   a.pos_x = (const int*)g->rtab_pos_x.p; a.alpha_x = (const double*)g->rtab_alpha_x.p;
   a.pos_y = (const int*)g->rtab_pos_y.p; a.alpha_y = (const double*)g->rtab_alpha_y.p;
   a.fields = (const float*)g->fields.p;
@@ -358,15 +392,22 @@ void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s, b
   if (deform_prepass) g->launches += ofdg::launch_deform_prepass(a, s);
   ofdg_generator::Span sp{timing_event(g), timing_event(g), 0};
   CK(cudaEventRecord(sp.a, s));
-  g->launches += ofdg::launch_bin(a, s);
+  if (!a.pair_ctl || !a.flow) g->launches += ofdg::launch_bin(a, s);  // (the split path bins inside launch_render_split)
   g->launches += ofdg::launch_background_prep(a, s);
   CK(cudaEventRecord(sp.b, s));
   g->spans.push_back(sp);
   if (a.flow) {
     ofdg_generator::Span sr{timing_event(g), timing_event(g), 1};
     CK(cudaEventRecord(sr.a, s));
-    g->launches += ofdg::launch_render(a, s);
-    CK(cudaEventRecord(sr.b, s));
+    if (a.pair_ctl) {
+      cudaEvent_t mid = timing_event(g);
+      g->launches += ofdg::launch_render_split(a, s, mid);
+      CK(cudaEventRecord(sr.b, s));
+      g->spans.push_back(ofdg_generator::Span{mid, sr.b, 2});
+    } else {
+      g->launches += ofdg::launch_render(a, s);
+      CK(cudaEventRecord(sr.b, s));
+    }
     g->spans.push_back(sr);
   }
   ++g->timed_calls;
@@ -549,6 +590,7 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
     }
     for (cudaEvent_t& e2 : g->chunk_copied) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming | cudaEventBlockingSync));
     if (const char* t = std::getenv("OFDG_TRANSPORT")) g->transport_u8 = std::string(t) != "f32";  // "f32": float blobs cross PCIe as they are
+    if (const char* t = std::getenv("OFDG_RENDER")) g->split_render = std::string(t) != "fused";
     *out = g.release();
   });
 }
@@ -567,7 +609,7 @@ void ofdg_destroy(ofdg_generator* g) {
     if (q.ready) cudaEventDestroy(q.ready);
     if (q.consumed) cudaEventDestroy(q.consumed);
   }
-  DevBuf* bufs[] = {&g->ph_slots, &g->pool, &g->tex_info_dev, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->field_reach_dev, &g->bg, &g->tile_hits, &g->rtab_pos_x, &g->rtab_alpha_x, &g->rtab_pos_y, &g->rtab_alpha_y, &g->out0, &g->out1,
+  DevBuf* bufs[] = {&g->ph_slots, &g->pool, &g->tex_info_dev, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->field_reach_dev, &g->bg, &g->tile_hits, &g->tile_range, &g->pair_list, &g->pair_masks, &g->pair_ctl, &g->rtab_pos_x, &g->rtab_alpha_x, &g->rtab_pos_y, &g->rtab_alpha_y, &g->out0, &g->out1,
                     &g->outf, &g->ids8, &g->dbg_masks, &g->dbg_id0, &g->dbg_id1, &g->dbg_frames8, &g->dbg_planar};
   for (DevBuf* b : bufs) b->release();
   g->scene.release();
@@ -1162,6 +1204,7 @@ void philox_run(ofdg_generator* g, int set, uint64_t seed, uint64_t first_sample
   CK(cudaMemcpyAsync(q.n_deform_host.p, q.n_deform.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   q.scene.batch = batch;
   q.scene.n_deform = 0;  // mode 9: read back by philox_collect once the set is complete
+  q.scene.pair_bound = (size_t)batch * kPhiloxMaxObj * (ofdg::tile_hits_bytes(1, g->cfg.width, g->cfg.height) / ofdg::TILE_HIT_STRIDE);  // the host never sees the boxes
 }
 
 // Mode 9: the number of warped outlines of a finished set sizes the deformation pre-pass of its render.
@@ -1340,7 +1383,7 @@ int ofdg_kernel_times(ofdg_generator* g, double* prep_ms, double* render_ms, int
     if (!g) throw ArgError("null pointer");
     g->use();
     CK(cudaDeviceSynchronize());
-    double t[2] = {0, 0};
+    double t[3] = {0, 0, 0};
     for (const ofdg_generator::Span& sp : g->spans) {
       float ms = 0.f;
       CK(cudaEventElapsedTime(&ms, sp.a, sp.b));
@@ -1349,11 +1392,13 @@ int ofdg_kernel_times(ofdg_generator* g, double* prep_ms, double* render_ms, int
     if (prep_ms) *prep_ms = t[0];
     if (render_ms) *render_ms = t[1];
     if (calls) *calls = (int32_t)g->timed_calls;
+    g->last_shade_ms = t[2];
     g->spans.clear();
     g->ev_next = 0;
     g->timed_calls = 0;
   });
 }
+double ofdg_last_shade_ms(const ofdg_generator* g) { return g ? g->last_shade_ms : 0.0; }
 uint64_t ofdg_last_upload_bytes(const ofdg_generator* g) { return g ? g->last_upload_bytes : 0; }
 uint64_t ofdg_last_download_bytes(const ofdg_generator* g) { return g ? g->last_download_bytes : 0; }
 

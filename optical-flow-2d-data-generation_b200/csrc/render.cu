@@ -760,6 +760,463 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// split render path: bin -> raster (masks per (object, tile) pair) -> shade (background, blits, flow, blobs)
+// ------------------------------------------------------------------------------------------------
+// The fused kernel above keeps the colours of a tile in registers while it rasterises: 80 registers, 44 KB of shared
+// memory and block-wide barriers for the whole tile. Here the two halves are separate kernels. The raster kernel works on
+// one (object, tile) pair per block turn -- no z-order between pairs, so every pair of the batch is independent work -- and
+// leaves the object's four masks (AA / non-AA, both frames; composites already combined) in HBM: 4 KB per pair, a few
+// hundred pairs per sample. The shade kernel is barrier-free: each warp owns a tile row and blends the tile's pairs in
+// z-order straight from those masks.
+struct PairOutline {   // one outline of the pair's object, staged in shared memory
+  int vbegin[2], vcount[2];
+  signed char layer[2];  // accumulator layer per frame, -1: the outline misses the tile
+  unsigned char additive;
+  int deform;
+};
+
+__global__ void __launch_bounds__(256) bin_pairs_kernel(RenderArgs a) {
+  __shared__ int s_box[256][8];
+  __shared__ int s_scan[256];
+  __shared__ int s_base;
+  const int sample = blockIdx.x, tid = threadIdx.x;
+  const FlatSample& smp = a.samples[sample];
+  const int n_obj = min(smp.obj_count, 255);
+  const int tiles_x = (a.W + TW - 1) / TW, tiles_y = (a.H + TH - 1) / TH, n_tiles = tiles_x * tiles_y;
+  for (int i = tid; i < n_obj * 8; i += blockDim.x) s_box[i >> 3][i & 7] = (&a.objects[smp.obj_begin + (i >> 3)].bbox[0][0])[i & 7];
+  __syncthreads();
+  int mine = 0;  // pairs of this thread's tiles
+  for (int t = tid; t < n_tiles; t += blockDim.x) {
+    const int tx0 = (t % tiles_x) * TW, ty0 = (t / tiles_x) * TH;
+    uint8_t* out = a.tile_hits + ((size_t)sample * n_tiles + t) * TILE_HIT_STRIDE;  // the fused kernel's bin entry (its overflow fallback)
+    int cnt = 0;
+    for (int o = 0; o < n_obj; ++o)
+      if (box_hits_tile(&s_box[o][0], tx0, ty0) || box_hits_tile(&s_box[o][4], tx0, ty0)) {
+        if (cnt < TILE_HIT_STRIDE - 1) out[1 + cnt] = (uint8_t)o;
+        ++cnt;
+      }
+    out[0] = (uint8_t)(cnt <= TILE_HIT_STRIDE - 1 ? cnt : 255);
+    mine += cnt;
+  }
+  // exclusive scan of the threads' counts, then one atomic per sample claims the sample's slice of the pair list
+  s_scan[tid] = mine;
+  __syncthreads();
+  for (int d = 1; d < 256; d <<= 1) {
+    const int v = tid >= d ? s_scan[tid - d] : 0;
+    __syncthreads();
+    s_scan[tid] += v;
+    __syncthreads();
+  }
+  if (tid == 255) {
+    const int total = s_scan[255];
+    const int base = atomicAdd(&a.pair_ctl[0], total);
+    if (base + total > a.pair_cap) a.pair_ctl[1] = 1;  // more pairs than the mask buffer holds: the fused kernel renders this batch
+    s_base = base;
+  }
+  __syncthreads();
+  int off = s_base + s_scan[tid] - mine;
+  const bool fits = s_base + s_scan[255] <= a.pair_cap;
+  for (int t = tid; t < n_tiles; t += blockDim.x) {
+    const int tx0 = (t % tiles_x) * TW, ty0 = (t / tiles_x) * TH;
+    const int first = off;
+    if (fits)
+      for (int o = 0; o < n_obj; ++o)
+        if (box_hits_tile(&s_box[o][0], tx0, ty0) || box_hits_tile(&s_box[o][4], tx0, ty0)) a.pair_list[off++] = make_int2(sample * 256 + o, t);
+    a.tile_range[(size_t)sample * n_tiles + t] = make_int2(first, off - first);  // (count 0 if the list is full: the host sizes it from the boxes, so it never is)
+  }
+}
+
+template <bool kDeform>
+__global__ void __launch_bounds__(RENDER_THREADS, 4) raster_pairs_kernel(RenderArgs a) {
+  __shared__ int s_cover[NLAYER][TH][TW];
+  __shared__ int s_area[NLAYER][TH][TW];
+  __shared__ int s_carry[NLAYER][TH];
+  __shared__ float s_q255[256];
+  __shared__ PairOutline s_out[NLAYER / 2];
+  __shared__ int s_seg_begin[NLAYER], s_seg_count[NLAYER];
+  __shared__ unsigned s_pairs[MAX_PAIRS];
+  __shared__ int s_npairs;
+  if (a.pair_ctl[1]) return;
+  const int total = a.pair_ctl[0];
+  const int W = a.W, H = a.H;
+  const size_t P = (size_t)W * H;
+  const int tiles_x = (W + TW - 1) / TW;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 256; i += RENDER_THREADS) s_q255[i] = (float)i / 255.f;
+  for (int pr = blockIdx.x; pr < total; pr += gridDim.x) {
+    const int2 pe = a.pair_list[pr];
+    const int sample = pe.x >> 8, obj = pe.x & 255, tile = pe.y;
+    const int tx0 = (tile % tiles_x) * TW, ty0 = (tile / tiles_x) * TH;
+    const int y = ty0 + warp, x0 = tx0 + lane * 4;
+    const bool live = (y < H) && (x0 < W);
+    const FlatObject& ob = a.objects[a.samples[sample].obj_begin + obj];
+    const int n_shapes = ob.shape_count, composite = ob.composite;
+    uint32_t uaa[2] = {0, 0}, una[2] = {0, 0};
+    for (int s0 = 0; s0 < n_shapes; s0 += NLAYER / 2) {
+      const int ns = min(NLAYER / 2, n_shapes - s0);
+      __syncthreads();  // the previous chunk (or pair) is done with the staging and the accumulators
+      if (tid < ns) {   // outline tid of this chunk: which of its frames touch the tile, which layers they get
+        const FlatShape& sh = a.shapes[ob.shape_begin + s0 + tid];
+        PairOutline po;
+        const bool h0 = box_hits_tile(sh.bbox[0], tx0, ty0), h1 = box_hits_tile(sh.bbox[1], tx0, ty0);
+        po.deform = (kDeform && h1) ? sh.deform : -1;  // a warped outline's frame-1 masks were materialised by the pre-pass
+        const bool r1 = h1 && po.deform < 0;
+        po.vbegin[0] = sh.vbegin[0]; po.vbegin[1] = sh.vbegin[1];
+        po.vcount[0] = h0 ? sh.vcount[0] : 0; po.vcount[1] = r1 ? sh.vcount[1] : 0;
+        po.layer[0] = h0 ? (signed char)(2 * tid) : (signed char)-1;
+        po.layer[1] = r1 ? (signed char)(2 * tid + 1) : (signed char)-1;
+        po.additive = sh.additive ? 1 : 0;
+        s_out[tid] = po;
+        s_seg_begin[2 * tid] = po.vbegin[0]; s_seg_count[2 * tid] = po.vcount[0];
+        s_seg_begin[2 * tid + 1] = po.vbegin[1]; s_seg_count[2 * tid + 1] = po.vcount[1];
+      } else if (tid < NLAYER / 2) {
+        s_seg_count[2 * tid] = 0; s_seg_count[2 * tid + 1] = 0;
+      }
+      for (int i = tid; i < 2 * ns * (TH * TW / 4); i += RENDER_THREADS) {  // outline k owns layers 2k and 2k + 1
+        reinterpret_cast<int4*>(&s_cover[0][0][0])[i] = make_int4(0, 0, 0, 0);
+        reinterpret_cast<int4*>(&s_area[0][0][0])[i] = make_int4(0, 0, 0, 0);
+      }
+      if (tid < NLAYER * TH) (&s_carry[0][0])[tid] = 0;
+      if (tid == 0) s_npairs = 0;
+      __syncthreads();
+      {
+        // (a) threads over edges: which tile rows does the edge cross? One work item per (edge, row).
+        const int c0 = s_seg_count[0], c1 = c0 + s_seg_count[1], c2 = c1 + s_seg_count[2], c3 = c2 + s_seg_count[3];
+        for (int e = tid; e < c3; e += RENDER_THREADS) {
+          const int l = e < c0 ? 0 : (e < c1 ? 1 : (e < c2 ? 2 : 3));
+          const int ei = e - (l == 0 ? 0 : (l == 1 ? c0 : (l == 2 ? c1 : c2)));
+          const int n = s_seg_count[l];
+          const FlatVertex* v = a.verts + s_seg_begin[l];
+          const FlatVertex p = v[ei], q = v[ei + 1 == n ? 0 : ei + 1];
+          int rlo, rhi;
+          bool left;
+          if (!tile_edge_rows(tx0, ty0, p.x, p.y, q.x, q.y, rlo, rhi, left)) continue;
+          const int nrows = rhi - rlo + 1;
+          const int base = left ? MAX_PAIRS : atomicAdd(&s_npairs, nrows);
+          for (int k = 0; k < nrows; ++k) {
+            if (base + k < MAX_PAIRS) s_pairs[base + k] = ((unsigned)l << 28) | ((unsigned)(rlo + k - ty0) << 24) | (unsigned)ei;
+            else tile_edge_row<true>(&s_cover[l][0][0], &s_area[l][0][0], &s_carry[l][0], tx0, ty0, rlo + k, p.x, p.y, q.x, q.y);  // cheap (left of the tile) or list full
+          }
+        }
+      }
+      __syncthreads();
+      {
+        // (b) threads over (edge, row) items: closed-form row segment -> cells
+        const int np = min(s_npairs, MAX_PAIRS);
+        for (int i = tid; i < np; i += RENDER_THREADS) {
+          const unsigned w = s_pairs[i];
+          const int l = (int)(w >> 28), r = ty0 + (int)((w >> 24) & 15u), ei = (int)(w & 0xFFFFFFu);
+          const int n = s_seg_count[l];
+          const FlatVertex* v = a.verts + s_seg_begin[l];
+          const FlatVertex p = v[ei], q = v[ei + 1 == n ? 0 : ei + 1];
+          tile_edge_row<true>(&s_cover[l][0][0], &s_area[l][0][0], &s_carry[l][0], tx0, ty0, r, p.x, p.y, q.x, q.y);
+        }
+      }
+      __syncthreads();
+
+      for (int k = 0; k < ns; ++k) {
+        uint32_t vaa[2] = {0, 0}, vna[2] = {0, 0};
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          const int l = s_out[k].layer[f];
+          if (l < 0) {
+            if (kDeform && f == 1 && s_out[k].deform >= 0 && live) {
+              const uint8_t* mw = a.mask_warp + (size_t)s_out[k].deform * 2 * P + (size_t)y * W + x0;
+              vaa[1] = *reinterpret_cast<const uint32_t*>(mw);
+              vna[1] = *reinterpret_cast<const uint32_t*>(mw + P);
+            }
+            continue;
+          }
+          const int4 c4 = *reinterpret_cast<const int4*>(&s_cover[l][warp][lane * 4]);
+          const int4 a4 = *reinterpret_cast<const int4*>(&s_area[l][warp][lane * 4]);
+          const int carry = s_carry[l][warp];
+          const bool cells = (c4.x | c4.y | c4.z | c4.w | a4.x | a4.y | a4.z | a4.w) != 0;
+          if (!__any_sync(0xffffffffu, cells)) {
+            // no outline crosses this row inside the tile: coverage is constant along it
+            if (carry == 0) continue;
+            const int cv = coverage_alpha(carry, 0);
+            vaa[f] = graylut((unsigned)cv) * 0x01010101u;
+            vna[f] = cv >= 128 ? 0xFFFFFFFFu : 0u;
+            continue;
+          }
+          int c[4] = {c4.x, c4.y, c4.z, c4.w}, ar[4] = {a4.x, a4.y, a4.z, a4.w};
+          c[1] += c[0]; c[2] += c[1]; c[3] += c[2];
+          int tot = c[3];  // warp-level inclusive prefix sum over the lanes' cover totals
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            int o = __shfl_up_sync(0xffffffffu, tot, d);
+            if (lane >= d) tot += o;
+          }
+          const int base = tot - c[3] + carry;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int cv = coverage_alpha(base + c[i], ar[i]);
+            vaa[f] |= graylut((unsigned)cv) << (8 * i);        // gamma_none
+            vna[f] |= (cv >= 128 ? 255u : 0u) << (8 * i);      // gamma_threshold(0.5), then graylut(255) = 255
+          }
+        }
+
+        if (composite) {
+          if (s0 + k == 0) { uaa[0] = uaa[1] = una[0] = una[1] = 0; }
+          const bool add = s_out[k].additive != 0;
+#pragma unroll
+          for (int f = 0; f < 2; ++f) {
+            uaa[f] = comp4(uaa[f], vaa[f], add, s_q255);
+            // non-AA masks stay in {0, 255} (the rules are closed on it) unless a warp field resampled them
+            if (kDeform) una[f] = comp4(una[f], vna[f], add, s_q255);
+            else una[f] = add ? (una[f] | vna[f]) : (una[f] & ~vna[f]);
+          }
+        } else {
+          uaa[0] = vaa[0]; uaa[1] = vaa[1]; una[0] = vna[0]; una[1] = vna[1];
+        }
+      }
+    }
+    // the object's four masks over this tile: [AA 0, AA 1, non-AA 0, non-AA 1][tile row][lane], one word = four pixels
+    uint32_t* pm = a.pair_masks + (size_t)pr * (4 * TH * 32) + warp * 32 + lane;
+    pm[0 * TH * 32] = uaa[0]; pm[1 * TH * 32] = uaa[1]; pm[2 * TH * 32] = una[0]; pm[3 * TH * 32] = una[1];
+  }
+}
+
+template <bool kDeform, bool kExtra>
+__global__ void __launch_bounds__(RENDER_THREADS, 4) shade_kernel(RenderArgs a) {
+  if (a.pair_ctl[1]) return;
+  const int W = a.W, H = a.H;
+  const int tiles_x = (W + TW - 1) / TW;
+  const int tx0 = (blockIdx.x % tiles_x) * TW, ty0 = (blockIdx.x / tiles_x) * TH;
+  const int sample = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int y = ty0 + warp, x0 = tx0 + lane * 4;
+  const bool live = (y < H) && (x0 < W);
+  const FlatSample& smp = a.samples[sample];
+  const size_t P = (size_t)W * H;
+  const int obj_begin = smp.obj_begin;
+  uint32_t col0[4], col1[4];
+  uint32_t id0 = 0, id1 = 0;  // four pixels, one byte each: 0 = background, k+1 = k-th foreground object (k < 255)
+
+  // ---- background: masks are all 255 (DG.cpp:684-690); frame 0 = centre window of the prepared
+  //      texture, frame 1 = that texture warped by I^-1*M*I on the 2W x 2H canvas (DG.cpp:665-682)
+  {
+    const uchar4* bg = a.bg + (size_t)sample * (4 * P);
+    const int W2 = 2 * W, H2 = 2 * H;
+    if (live) {
+      const uchar4* row = bg + (size_t)(y + H / 2) * W2 + (x0 + W / 2);
+      RowWarp rw;
+      rw.init(smp.bg_tex_inv, (double)(y + H / 2), W2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) col0[i] = ld_px(row + i) & 0xFFFFFFu;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) col1[i] = bilinear_rgbx_call(bg, W2, W2, H2, W2, rw.dx.v1, rw.dx.lft, rw.dx.rem, rw.dy.v1, rw.dy.lft, rw.dy.rem, x0 + i + W / 2);
+      if (kDeform && smp.bg_field >= 0) {
+        // background with a warp field: the warped 2W x 2H texture is resampled through the resized,
+        // doubled inverse field before the centre crop (DG.cpp:670-681, 1194-1201)
+        const int fw = W + 1, fh = H + 1;
+        const float* ifl = a.fields + ((size_t)smp.bg_field * 2 + 1) * 2 * fw * fh;
+        const double* tinv = smp.bg_tex_inv;
+        auto tap = [&](int px, int py) -> uint32_t {
+          if (px < 0 || py < 0 || px >= W2 || py >= H2) return 0u;
+          RowWarp r2;
+          r2.init(tinv, (double)py, W2);
+          return bilinear_rgbx(bg, W2, 0, 0, W2, H2, r2, px);
+        };
+        for (int i = 0; i < 4; ++i) {
+          const int X = x0 + i + W / 2, Y = y + H / 2;
+          const float sx = X + resized_field2(ifl, fw, fh, X, Y, a), sy = Y + resized_field2(ifl + (size_t)fw * fh, fw, fh, X, Y, a);
+          col1[i] = dirichlet_rgbx(tap, sx, sy);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) col0[i] = col1[i] = 0;
+    }
+  }
+
+
+  // ---- the tile's (object, tile) pairs in z-order: masks from the raster kernel, blits as in the fused kernel
+  const int2 range = a.tile_range[(size_t)sample * gridDim.x + blockIdx.x];
+  for (int pr = range.x; pr < range.x + range.y; ++pr) {
+    const int k = a.pair_list[pr].x & 255;
+    uint32_t uaa[2], una[2];
+    {
+      const uint32_t* pm = a.pair_masks + (size_t)pr * (4 * TH * 32) + warp * 32 + lane;
+      uaa[0] = pm[0 * TH * 32]; uaa[1] = pm[1 * TH * 32]; una[0] = pm[2 * TH * 32]; una[1] = pm[3 * TH * 32];
+    }
+    const bool row_hit = __any_sync(0xffffffffu, (uaa[0] | uaa[1] | una[0] | una[1]) != 0u);  // (every lane takes part)
+    if (!live || (!row_hit && !a.dbg_masks)) continue;  // outside the frame, or the row is clear of this object
+    const FlatObject& ob = a.objects[obj_begin + k];
+    const TexInfo ti = a.tex_info[ob.tex];
+    {
+        // the object's masks are complete: ids from the non-AA masks, colour through the AA (or non-AA) masks
+        
+        if (a.dbg_masks && k < a.dbg_max_objs) {
+          uint8_t* mb = a.dbg_masks + ((size_t)sample * a.dbg_max_objs + k) * 4 * P + (size_t)y * W + x0;
+          *reinterpret_cast<uint32_t*>(mb + 0 * P) = uaa[0]; *reinterpret_cast<uint32_t*>(mb + 1 * P) = uaa[1];
+          *reinterpret_cast<uint32_t*>(mb + 2 * P) = una[0]; *reinterpret_cast<uint32_t*>(mb + 3 * P) = una[1];
+        }
+        const uint32_t kk = (uint32_t)(k + 1) * 0x01010101u;
+        const uint32_t e0 = __vcmpeq4(una[0], 0xFFFFFFFFu), e1 = __vcmpeq4(una[1], 0xFFFFFFFFu);
+        id0 = (id0 & ~e0) | (kk & e0);
+        id1 = (id1 & ~e1) | (kk & e1);
+        const uint32_t m0w = a.use_aa ? uaa[0] : una[0], m1w = a.use_aa ? uaa[1] : una[1];
+        if ((m0w | m1w) == 0u) continue;
+        const uchar4* tex = a.pool + ti.fg_base;  // the W x H foreground view (centre crop, DG.cpp:99-102 with defaults, or the resized copy)
+        if (m0w) {
+          const uchar4* trow = tex + (size_t)y * ti.fg_pitch + x0;  // identity warp == copy
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const unsigned m0 = (m0w >> (8 * i)) & 255u;
+            if (m0) col0[i] = blend_rgbx(col0[i], ld_px(trow + i) & 0xFFFFFFu, m0);
+          }
+        }
+        if (m1w && (!kDeform || ob.field < 0)) {
+          RowWarp rw;
+          rw.init(a.objects[obj_begin + k].tex_inv, (double)y, W);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const unsigned m1 = (m1w >> (8 * i)) & 255u;
+            if (m1) col1[i] = blend_rgbx(col1[i], bilinear_rgbx_call(tex, ti.fg_pitch, W, H, W, rw.dx.v1, rw.dx.lft, rw.dx.rem, rw.dy.v1, rw.dy.lft, rw.dy.rem, x0 + i), m1);
+          }
+        } else if (kDeform && m1w) {
+          // applyWarpFieldToTexture(getTransformedTexture(tex0, M), iflow) evaluated where the mask is set:
+          // each of the 4 float-bilinear taps is itself one AGG span-bilinear pixel (DG.cpp:341-345)
+          const double* tinv = a.objects[obj_begin + k].tex_inv;
+          const int fw = W + 1, fh = H + 1;
+          const float* ifl = a.fields + ((size_t)ob.field * 2 + 1) * 2 * fw * fh;
+          auto tap = [&](int px, int py) -> uint32_t {
+            if (px < 0 || py < 0 || px >= W || py >= H) return 0u;
+            RowWarp rw;
+            rw.init(tinv, (double)py, W);
+            return bilinear_rgbx(tex, ti.fg_pitch, 0, 0, W, H, rw, px);
+          };
+          for (int i = 0; i < 4; ++i) {
+            const unsigned m1 = (m1w >> (8 * i)) & 255u;
+            if (!m1) continue;
+            const int x = x0 + i;
+            const float sx = x + ifl[(size_t)y * fw + x], sy = y + ifl[(size_t)fw * fh + (size_t)y * fw + x];
+            col1[i] = blend_rgbx(col1[i], dirichlet_rgbx(tap, sx, sy), m1);
+          }
+        }
+    }
+  }
+
+  if (!live) return;
+
+  // ---- flow of the top-most object, f64 -> f32 (DG.cpp:388-401, 692-712). Forward: frame 0's ids through the motions;
+  //      backward (extra top, computeFlowImage(inverse = true)): frame 1's ids through the inverse motions.
+  auto point_flow = [&](unsigned oid, bool inverse, int i, float& fx, float& fy) {
+    const float xf = (float)(x0 + i), yf = (float)y;
+    // background: the point goes through I^-1 = T(-W,-H), M, I = T(W,H) (DG.cpp:697-712); objects: through M alone.
+    // One code path: the translations are exact no-ops (+-0.0) for objects.
+    const FlatObject* fo = oid ? a.objects + obj_begin + oid - 1 : nullptr;
+    const double* m = oid ? (inverse ? fo->tex_inv : fo->motion) : (inverse ? smp.bg_motion_inv : smp.bg_motion);
+    const double pre_x = oid ? 0.0 : (double)W, pre_y = oid ? 0.0 : (double)H;
+    const float save_x = oid ? xf : xf + (float)(W / 2), save_y = oid ? yf : yf + (float)(H / 2);
+    double ix = (double)save_x - pre_x, iy = (double)save_y - pre_y;
+    const double tmp = ix;
+    ix = tmp * m[0] + iy * m[2] + m[4];
+    iy = tmp * m[1] + iy * m[3] + m[5];
+    ix = ix + pre_x; iy = iy + pre_y;
+    fx = (float)(ix - save_x);
+    fy = (float)(iy - save_y);
+    if (kDeform) {  // the forward field is added in both directions (DG.cpp:403-406, 714-717)
+      const int fw = W + 1, fh = H + 1;
+      if (oid == 0) {
+        if (smp.bg_field >= 0 && ix >= 0 && ix < 2 * W && iy >= 0 && iy < 2 * H) {  // DG.cpp:714-717
+          const float* fl = a.fields + ((size_t)smp.bg_field * 2 + 0) * 2 * fw * fh;
+          auto at0 = [&](unsigned X, unsigned Y) { return resized_field2(fl, fw, fh, (int)X, (int)Y, a); };
+          auto at1 = [&](unsigned X, unsigned Y) { return resized_field2(fl + (size_t)fw * fh, fw, fh, (int)X, (int)Y, a); };
+          fx += neumann_f(at0, 2 * W, 2 * H, (float)ix, (float)iy);
+          fy += neumann_f(at1, 2 * W, 2 * H, (float)ix, (float)iy);
+        }
+      } else if (fo->field >= 0 && ix >= 0 && ix < W && iy >= 0 && iy < H) {  // DG.cpp:403-406
+        const float* fl = a.fields + ((size_t)fo->field * 2 + 0) * 2 * fw * fh;
+        auto at0 = [&](unsigned X, unsigned Y) { return fl[(size_t)Y * fw + X]; };
+        auto at1 = [&](unsigned X, unsigned Y) { return fl[(size_t)fw * fh + (size_t)Y * fw + X]; };
+        fx += neumann_f(at0, fw, fh, (float)ix, (float)iy);
+        fy += neumann_f(at1, fw, fh, (float)ix, (float)iy);
+      }
+    }
+  };
+  float fxv[4], fyv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) point_flow((id0 >> (8 * i)) & 255u, false, i, fxv[i], fyv[i]);
+
+  // ---- write the three blobs (NCHW float): 8 planes x one 128-bit store per lane
+  const size_t pix = (size_t)y * W + x0;
+  float* of = a.flow + (size_t)sample * 2 * P + pix;
+  if (a.img0) {
+    float* o0 = a.img0 + (size_t)sample * 3 * P + pix;
+    float* o1 = a.img1 + (size_t)sample * 3 * P + pix;
+    const bool augment = smp.aug.enabled != 0;  // this repository's own colour/noise augmentation (ofdg/augment.h); never set by the reference path
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float4 v0 = make_float4(byte_to_float(col0[0], c), byte_to_float(col0[1], c), byte_to_float(col0[2], c), byte_to_float(col0[3], c));
+      float4 v1 = make_float4(byte_to_float(col1[0], c), byte_to_float(col1[1], c), byte_to_float(col1[2], c), byte_to_float(col1[3], c));
+      if (augment) {
+        const uint32_t p = (uint32_t)pix;
+        v0.x = ofdg_augment_value(&smp.aug, v0.x, c, 0, p); v0.y = ofdg_augment_value(&smp.aug, v0.y, c, 0, p + 1);
+        v0.z = ofdg_augment_value(&smp.aug, v0.z, c, 0, p + 2); v0.w = ofdg_augment_value(&smp.aug, v0.w, c, 0, p + 3);
+        v1.x = ofdg_augment_value(&smp.aug, v1.x, c, 1, p); v1.y = ofdg_augment_value(&smp.aug, v1.y, c, 1, p + 1);
+        v1.z = ofdg_augment_value(&smp.aug, v1.z, c, 1, p + 2); v1.w = ofdg_augment_value(&smp.aug, v1.w, c, 1, p + 3);
+      }
+      __stcs(reinterpret_cast<float4*>(o0 + c * P), v0);
+      __stcs(reinterpret_cast<float4*>(o1 + c * P), v1);
+    }
+  }
+  __stcs(reinterpret_cast<float4*>(of), make_float4(fxv[0], fxv[1], fxv[2], fxv[3]));
+  __stcs(reinterpret_cast<float4*>(of + P), make_float4(fyv[0], fyv[1], fyv[2], fyv[3]));
+
+  if (kExtra) {
+    if (a.flow_bw) {
+      float bx[4], by[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) point_flow((id1 >> (8 * i)) & 255u, true, i, bx[i], by[i]);
+      float* ob = a.flow_bw + (size_t)sample * 2 * P + pix;
+      __stcs(reinterpret_cast<float4*>(ob), make_float4(bx[0], bx[1], bx[2], bx[3]));
+      __stcs(reinterpret_cast<float4*>(ob + P), make_float4(by[0], by[1], by[2], by[3]));
+    }
+    if (a.top_id0 || a.top_id1) {
+      float v0[4], v1[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const unsigned b0 = (id0 >> (8 * i)) & 255u, b1 = (id1 >> (8 * i)) & 255u;
+        v0[i] = (float)(b0 ? a.objects[obj_begin + b0 - 1].obj_id : 1);  // the background's ID is 1 (data_generation_layer.cpp:199)
+        v1[i] = (float)(b1 ? a.objects[obj_begin + b1 - 1].obj_id : 1);
+      }
+      if (a.top_id0) __stcs(reinterpret_cast<float4*>(a.top_id0 + (size_t)sample * P + pix), make_float4(v0[0], v0[1], v0[2], v0[3]));
+      if (a.top_id1) __stcs(reinterpret_cast<float4*>(a.top_id1 + (size_t)sample * P + pix), make_float4(v1[0], v1[1], v1[2], v1[3]));
+    }
+    if (a.ids8) {
+      *reinterpret_cast<uint32_t*>(a.ids8 + (size_t)sample * 2 * P + pix) = id0;
+      *reinterpret_cast<uint32_t*>(a.ids8 + (size_t)sample * 2 * P + P + pix) = id1;
+    }
+  }
+
+  if (a.dbg_id0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const unsigned b0 = (id0 >> (8 * i)) & 255u, b1 = (id1 >> (8 * i)) & 255u;
+      const unsigned o0id = b0 ? (unsigned)a.objects[obj_begin + b0 - 1].obj_id : 1u;
+      const unsigned o1id = b1 ? (unsigned)a.objects[obj_begin + b1 - 1].obj_id : 1u;
+      a.dbg_id0[(size_t)sample * P + pix + i] = o0id;
+      if (a.dbg_id1) a.dbg_id1[(size_t)sample * P + pix + i] = o1id;
+    }
+  }
+  if (a.frames8) {  // byte planes: channel c of the lane's four pixels is one 32-bit store
+    uint8_t* fb = a.frames8 + (size_t)sample * 6 * P + pix;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const unsigned sel = 0x40u + (unsigned)c * 0x11u;  // byte c of the first operand, byte c of the second
+      const uint32_t w0 = __byte_perm(__byte_perm(col0[0], col0[1], sel), __byte_perm(col0[2], col0[3], sel), 0x5410u);
+      const uint32_t w1 = __byte_perm(__byte_perm(col1[0], col1[1], sel), __byte_perm(col1[2], col1[3], sel), 0x5410u);
+      __stcs(reinterpret_cast<uint32_t*>(fb + c * P), w0);
+      __stcs(reinterpret_cast<uint32_t*>(fb + (3 + c) * P), w1);
+    }
+  }
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // mode 9 pre-pass: frame-1 masks of warped outlines (MovingObjectBase::renderMasks, DG.cpp:370-386)
 // ------------------------------------------------------------------------------------------------
@@ -1366,6 +1823,39 @@ int launch_render(const RenderArgs& a, cudaStream_t s) {
   const size_t P = (size_t)a.W * a.H;
   occlusion_kernel<<<dim3((unsigned)((P + 255) / 256), a.batch), 256, 0, s>>>(a);
   return 2;
+}
+
+size_t pair_mask_bytes_per_pair() { return (size_t)4 * TH * 32 * sizeof(uint32_t); }
+
+int launch_render_split(const RenderArgs& a, cudaStream_t s, cudaEvent_t before_shade) {
+  const int tiles_x = (a.W + TW - 1) / TW, tiles_y = (a.H + TH - 1) / TH;
+  dim3 grid(tiles_x * tiles_y, a.batch);
+  const bool extra = a.flow_bw || a.top_id0 || a.top_id1 || a.ids8;
+  static int raster_blocks = 0;  // resident blocks of the device for the persistent raster kernel
+  if (!raster_blocks) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_pairs_kernel<false>, RENDER_THREADS, 0);
+    raster_blocks = max(1, sms * max(1, per_sm));
+  }
+  cudaMemsetAsync(a.pair_ctl, 0, 2 * sizeof(int), s);
+  bin_pairs_kernel<<<a.batch, 256, 0, s>>>(a);
+  if (a.n_fields > 0) {
+    raster_pairs_kernel<true><<<raster_blocks, RENDER_THREADS, 0, s>>>(a);
+    if (before_shade) cudaEventRecord(before_shade, s);
+    if (extra) shade_kernel<true, true><<<grid, RENDER_THREADS, 0, s>>>(a);
+    else shade_kernel<true, false><<<grid, RENDER_THREADS, 0, s>>>(a);
+  } else {
+    raster_pairs_kernel<false><<<raster_blocks, RENDER_THREADS, 0, s>>>(a);
+    if (before_shade) cudaEventRecord(before_shade, s);
+    if (extra) shade_kernel<false, true><<<grid, RENDER_THREADS, 0, s>>>(a);
+    else shade_kernel<false, false><<<grid, RENDER_THREADS, 0, s>>>(a);
+  }
+  if (!a.occlusion) return 3;
+  const size_t P = (size_t)a.W * a.H;
+  occlusion_kernel<<<dim3((unsigned)((P + 255) / 256), a.batch), 256, 0, s>>>(a);
+  return 4;
 }
 
 void launch_planar_to_rgbx(const uint8_t* planar, uchar4* out, int n, int w, int h, cudaStream_t s) {

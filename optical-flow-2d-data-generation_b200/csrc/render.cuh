@@ -28,6 +28,12 @@ struct RenderArgs {
   const double* alpha_y;
   // per-sample, per-tile lists of the objects whose boxes touch the tile (bin_kernel -> render_kernel)
   uint8_t* tile_hits;         // [batch][tiles][TILE_HIT_STRIDE]: byte 0 = count (255: too many, rescan), then object indices in z-order
+  // split render path: (object, tile) pairs (bin_pairs_kernel -> raster_pairs_kernel -> shade_kernel)
+  int2* tile_range;           // [batch][tiles] {first pair, pair count}, pairs of a tile in z-order
+  int2* pair_list;            // [pair_cap] {sample * 256 + object, tile}
+  uint32_t* pair_masks;       // [pair_cap][AA 0 | AA 1 | non-AA 0 | non-AA 1][TH][32] four pixels per word
+  int* pair_ctl;              // [0] pairs claimed (atomic), [1] set when they exceed pair_cap (the fused kernel renders the batch)
+  int pair_cap;
   // mode 9
   const float* fields;        // [n][flow|iflow][channel][H+1][W+1]
   int n_fields;
@@ -65,6 +71,10 @@ int launch_bin(const RenderArgs& a, cudaStream_t s);
 size_t tile_hits_bytes(int batch, int W, int H);
 int launch_background_prep(const RenderArgs& a, cudaStream_t s);
 int launch_render(const RenderArgs& a, cudaStream_t s);  // + the occlusion pass when a.occlusion is set
+// Split path: bin + raster + shade (+ the fused kernel, which only does work when the pair buffer overflowed).
+// Replaces launch_bin + launch_render; a.pair_* must be set.
+int launch_render_split(const RenderArgs& a, cudaStream_t s, cudaEvent_t before_shade = nullptr);  // the event, if given, is recorded between raster and shade
+size_t pair_mask_bytes_per_pair();
 int launch_deform_prepass(const RenderArgs& a, cudaStream_t s);  // mode 9 only; no-op when n_deform == 0
 
 // Foreground view (W x H) of a texture smaller than W x H, CImg linear resize; tmp holds W x h pixels, pos / alpha max(W, H) entries.
