@@ -337,11 +337,11 @@ ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, 
     if (ds.pair_bound > (size_t)g->pair_cap) {  // grow the pair buffers (4 KB of masks per pair); earlier launches may still use the old ones
       CK(cudaDeviceSynchronize());
       const size_t cap = std::max<size_t>(ds.pair_bound + ds.pair_bound / 4, 4096);
-      g->pair_list.reserve(cap * sizeof(int2));
+      g->pair_list.reserve(cap * sizeof(int4));
       g->pair_masks.reserve(cap * ofdg::pair_mask_bytes_per_pair());
       g->pair_cap = (int)cap;
     }
-    a.tile_range = (int2*)g->tile_range.p; a.pair_list = (int2*)g->pair_list.p; a.pair_masks = (uint32_t*)g->pair_masks.p;
+    a.tile_range = (int2*)g->tile_range.p; a.pair_list = (int4*)g->pair_list.p; a.pair_masks = (uint32_t*)g->pair_masks.p;
     a.pair_ctl = (int*)g->pair_ctl.p; a.pair_cap = g->pair_cap;
   }
   a.pos_x = (const int*)g->rtab_pos_x.p; a.alpha_x = (const double*)g->rtab_alpha_x.p;

@@ -770,6 +770,12 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
 // leaves the object's four masks (AA / non-AA, both frames; composites already combined) in HBM: 4 KB per pair, a few
 // hundred pairs per sample. The shade kernel is barrier-free: each warp owns a tile row and blends the tile's pairs in
 // z-order straight from those masks.
+#ifndef OFDG_RASTER_MIN_BLOCKS
+#define OFDG_RASTER_MIN_BLOCKS 5  // measured: 3 / 4 / 5 / 6 blocks per SM -> 0.225 / 0.195 / 0.179 / 0.188 ms (occupancy beats the spills up to 5)
+#endif
+#ifndef OFDG_SHADE_MIN_BLOCKS
+#define OFDG_SHADE_MIN_BLOCKS 4
+#endif
 struct PairOutline {   // one outline of the pair's object, staged in shared memory
   int vbegin[2], vcount[2];
   signed char layer[2];  // accumulator layer per frame, -1: the outline misses the tile
@@ -779,6 +785,7 @@ struct PairOutline {   // one outline of the pair's object, staged in shared mem
 
 __global__ void __launch_bounds__(256) bin_pairs_kernel(RenderArgs a) {
   __shared__ int s_box[256][8];
+  __shared__ int2 s_shapes[256];  // per object: first outline, outline count | composite << 16 (saves the raster kernel two dependent loads per pair)
   __shared__ int s_scan[256];
   __shared__ int s_base;
   const int sample = blockIdx.x, tid = threadIdx.x;
@@ -786,6 +793,10 @@ __global__ void __launch_bounds__(256) bin_pairs_kernel(RenderArgs a) {
   const int n_obj = min(smp.obj_count, 255);
   const int tiles_x = (a.W + TW - 1) / TW, tiles_y = (a.H + TH - 1) / TH, n_tiles = tiles_x * tiles_y;
   for (int i = tid; i < n_obj * 8; i += blockDim.x) s_box[i >> 3][i & 7] = (&a.objects[smp.obj_begin + (i >> 3)].bbox[0][0])[i & 7];
+  for (int o = tid; o < n_obj; o += blockDim.x) {
+    const FlatObject& ob = a.objects[smp.obj_begin + o];
+    s_shapes[o] = make_int2(ob.shape_begin, ob.shape_count | (ob.composite ? 1 << 16 : 0));
+  }
   __syncthreads();
   int mine = 0;  // pairs of this thread's tiles
   for (int t = tid; t < n_tiles; t += blockDim.x) {
@@ -823,13 +834,13 @@ __global__ void __launch_bounds__(256) bin_pairs_kernel(RenderArgs a) {
     const int first = off;
     if (fits)
       for (int o = 0; o < n_obj; ++o)
-        if (box_hits_tile(&s_box[o][0], tx0, ty0) || box_hits_tile(&s_box[o][4], tx0, ty0)) a.pair_list[off++] = make_int2(sample * 256 + o, t);
+        if (box_hits_tile(&s_box[o][0], tx0, ty0) || box_hits_tile(&s_box[o][4], tx0, ty0)) a.pair_list[off++] = make_int4(sample * 256 + o, t, s_shapes[o].x, s_shapes[o].y);
     a.tile_range[(size_t)sample * n_tiles + t] = make_int2(first, off - first);  // (count 0 if the list is full: the host sizes it from the boxes, so it never is)
   }
 }
 
 template <bool kDeform>
-__global__ void __launch_bounds__(RENDER_THREADS, 4) raster_pairs_kernel(RenderArgs a) {
+__global__ void __launch_bounds__(RENDER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster_pairs_kernel(RenderArgs a) {
   __shared__ int s_cover[NLAYER][TH][TW];
   __shared__ int s_area[NLAYER][TH][TW];
   __shared__ int s_carry[NLAYER][TH];
@@ -845,20 +856,21 @@ __global__ void __launch_bounds__(RENDER_THREADS, 4) raster_pairs_kernel(RenderA
   const int tiles_x = (W + TW - 1) / TW;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < 256; i += RENDER_THREADS) s_q255[i] = (float)i / 255.f;
+  int4 pe_next = blockIdx.x < total ? a.pair_list[blockIdx.x] : make_int4(0, 0, 0, 0);
   for (int pr = blockIdx.x; pr < total; pr += gridDim.x) {
-    const int2 pe = a.pair_list[pr];
-    const int sample = pe.x >> 8, obj = pe.x & 255, tile = pe.y;
+    const int4 pe = pe_next;
+    if (pr + (int)gridDim.x < total) pe_next = a.pair_list[pr + gridDim.x];  // in flight while this pair is rasterised
+    const int tile = pe.y, shape_begin = pe.z;
     const int tx0 = (tile % tiles_x) * TW, ty0 = (tile / tiles_x) * TH;
     const int y = ty0 + warp, x0 = tx0 + lane * 4;
     const bool live = (y < H) && (x0 < W);
-    const FlatObject& ob = a.objects[a.samples[sample].obj_begin + obj];
-    const int n_shapes = ob.shape_count, composite = ob.composite;
+    const int n_shapes = pe.w & 0xFFFF, composite = pe.w >> 16;
     uint32_t uaa[2] = {0, 0}, una[2] = {0, 0};
     for (int s0 = 0; s0 < n_shapes; s0 += NLAYER / 2) {
       const int ns = min(NLAYER / 2, n_shapes - s0);
       __syncthreads();  // the previous chunk (or pair) is done with the staging and the accumulators
       if (tid < ns) {   // outline tid of this chunk: which of its frames touch the tile, which layers they get
-        const FlatShape& sh = a.shapes[ob.shape_begin + s0 + tid];
+        const FlatShape& sh = a.shapes[shape_begin + s0 + tid];
         PairOutline po;
         const bool h0 = box_hits_tile(sh.bbox[0], tx0, ty0), h1 = box_hits_tile(sh.bbox[1], tx0, ty0);
         po.deform = (kDeform && h1) ? sh.deform : -1;  // a warped outline's frame-1 masks were materialised by the pre-pass
@@ -980,7 +992,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 4) raster_pairs_kernel(RenderA
 }
 
 template <bool kDeform, bool kExtra>
-__global__ void __launch_bounds__(RENDER_THREADS, 4) shade_kernel(RenderArgs a) {
+__global__ void __launch_bounds__(RENDER_THREADS, OFDG_SHADE_MIN_BLOCKS) shade_kernel(RenderArgs a) {
   if (a.pair_ctl[1]) return;
   const int W = a.W, H = a.H;
   const int tiles_x = (W + TW - 1) / TW;

@@ -30,7 +30,7 @@ struct RenderArgs {
   uint8_t* tile_hits;         // [batch][tiles][TILE_HIT_STRIDE]: byte 0 = count (255: too many, rescan), then object indices in z-order
   // split render path: (object, tile) pairs (bin_pairs_kernel -> raster_pairs_kernel -> shade_kernel)
   int2* tile_range;           // [batch][tiles] {first pair, pair count}, pairs of a tile in z-order
-  int2* pair_list;            // [pair_cap] {sample * 256 + object, tile}
+  int4* pair_list;            // [pair_cap] {sample * 256 + object, tile, first outline (absolute), outline count | composite << 16}
   uint32_t* pair_masks;       // [pair_cap][AA 0 | AA 1 | non-AA 0 | non-AA 1][TH][32] four pixels per word
   int* pair_ctl;              // [0] pairs claimed (atomic), [1] set when they exceed pair_cap (the fused kernel renders the batch)
   int pair_cap;
