@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
 #define OFDG_RASTER_MIN_BLOCKS 5  // measured: 3 / 4 / 5 / 6 blocks per SM -> 0.225 / 0.195 / 0.179 / 0.188 ms (occupancy beats the spills up to 5)
 #endif
 #ifndef OFDG_SHADE_MIN_BLOCKS
-#define OFDG_SHADE_MIN_BLOCKS 4
+#define OFDG_SHADE_MIN_BLOCKS 6  // measured: 4 / 5 / 6 / 8 blocks per SM -> 0.192 / 0.182 / 0.177 / 0.186 ms
 #endif
 struct PairOutline {   // one outline of the pair's object, staged in shared memory
   int vbegin[2], vcount[2];
