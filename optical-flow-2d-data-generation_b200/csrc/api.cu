@@ -108,6 +108,7 @@ struct DeviceScene {
   DevBuf samples, objects, shapes, verts, deform_shape, deform_field;
   int batch = 0, n_deform = 0;
   size_t pair_bound = 0;  // upper bound of the scene's (object, tile) pairs: sizes the split render path's mask buffer
+  int prep_w = 0, prep_h = 0;  // largest part of a prepared background any sample needs (pixels; 0: unknown, the whole 2W x 2H)
   void release() { samples.release(); objects.release(); shapes.release(); verts.release(); deform_shape.release(); deform_field.release(); }
 };
 
@@ -273,6 +274,12 @@ void upload_scene_parts(ofdg_generator* g, const ofdg::FlatBatch* parts, int n_p
         }
     ds.pair_bound = pairs;
   }
+  ds.prep_w = ds.prep_h = 0;  // the preparation kernel's grid covers the largest needed region, not the whole 2W x 2H canvas
+  for (int i = 0; i < n_parts; ++i)
+    for (const ofdg::FlatSample& fs : parts[i].samples) {
+      ds.prep_w = std::max(ds.prep_w, fs.prep.need[2] - fs.prep.need[0] + 1);
+      ds.prep_h = std::max(ds.prep_h, fs.prep.need[3] - fs.prep.need[1] + 1);
+    }
   ofdg::UploadSegments u{};
   const char* dv = (const char*)staging.dev;
   auto seg = [&u, dv](void* dst, size_t off, size_t bytes) {
@@ -315,7 +322,7 @@ void ensure_scratch(ofdg_generator* g, int batch) {
   if (g->split_render) {
     const size_t tiles = ofdg::tile_hits_bytes(1, (int)W, (int)H) / ofdg::TILE_HIT_STRIDE;
     g->tile_range.reserve((size_t)batch * tiles * sizeof(int2));
-    g->pair_ctl.reserve(2 * sizeof(int));
+    g->pair_ctl.reserve(4 * sizeof(int));
   }
   g->scratch_batch = batch;
 }
@@ -328,6 +335,7 @@ ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, 
   a.verts = (const ofdg::FlatVertex*)ds.verts.p;
   a.batch = ds.batch;
   a.W = g->cfg.width; a.H = g->cfg.height;
+  a.prep_w = ds.prep_w; a.prep_h = ds.prep_h;
   a.use_aa = g->cfg.use_antialiasing;
   a.pool = (const uchar4*)g->pool.p;
   a.tex_info = (const ofdg::TexInfo*)g->tex_info_dev.p;

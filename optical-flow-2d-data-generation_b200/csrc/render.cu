@@ -849,6 +849,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster
   __shared__ int s_seg_begin[NLAYER], s_seg_count[NLAYER];
   __shared__ unsigned s_pairs[MAX_PAIRS];
   __shared__ int s_npairs;
+  __shared__ int s_next;
   if (a.pair_ctl[1]) return;
   const int total = a.pair_ctl[0];
   const int W = a.W, H = a.H;
@@ -857,9 +858,13 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < 256; i += RENDER_THREADS) s_q255[i] = (float)i / 255.f;
   int4 pe_next = blockIdx.x < total ? a.pair_list[blockIdx.x] : make_int4(0, 0, 0, 0);
-  for (int pr = blockIdx.x; pr < total; pr += gridDim.x) {
+  // Pairs differ a lot in cost (1 to 7 outlines, a few to hundreds of edges): after its first pair a block claims the next
+  // one from a queue (pair_ctl[2]) instead of striding over the list, so no block is left with a long tail of heavy pairs.
+  int pr = blockIdx.x;
+  while (pr < total) {
     const int4 pe = pe_next;
-    if (pr + (int)gridDim.x < total) pe_next = a.pair_list[pr + gridDim.x];  // in flight while this pair is rasterised
+    int pr_next = total;
+    if (tid == 0) s_next = (int)gridDim.x + atomicAdd(&a.pair_ctl[2], 1);
     const int tile = pe.y, shape_begin = pe.z;
     const int tx0 = (tile % tiles_x) * TW, ty0 = (tile / tiles_x) * TH;
     const int y = ty0 + warp, x0 = tx0 + lane * 4;
@@ -893,6 +898,10 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster
       if (tid < NLAYER * TH) (&s_carry[0][0])[tid] = 0;
       if (tid == 0) s_npairs = 0;
       __syncthreads();
+      if (s0 == 0) {  // the claimed pair's record is in flight while this pair is rasterised
+        pr_next = s_next;
+        if (pr_next < total) pe_next = a.pair_list[pr_next];
+      }
       {
         // (a) threads over edges: which tile rows does the edge cross? One work item per (edge, row).
         const int c0 = s_seg_count[0], c1 = c0 + s_seg_count[1], c2 = c1 + s_seg_count[2], c3 = c2 + s_seg_count[3];
@@ -988,6 +997,13 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster
     // the object's four masks over this tile: [AA 0, AA 1, non-AA 0, non-AA 1][tile row][lane], one word = four pixels
     uint32_t* pm = a.pair_masks + (size_t)pr * (4 * TH * 32) + warp * 32 + lane;
     pm[0 * TH * 32] = uaa[0]; pm[1 * TH * 32] = uaa[1]; pm[2 * TH * 32] = una[0]; pm[3 * TH * 32] = una[1];
+    if (n_shapes <= 0) {  // (an object without outlines: no barrier has published the claim yet)
+      __syncthreads();
+      pr_next = s_next;
+      if (pr_next < total) pe_next = a.pair_list[pr_next];
+      __syncthreads();
+    }
+    pr = pr_next;
   }
 }
 
@@ -1788,7 +1804,9 @@ int launch_bin(const RenderArgs& a, cudaStream_t s) {
 }
 
 int launch_background_prep(const RenderArgs& a, cudaStream_t s) {
-  dim3 grid((2 * a.W + PT - 1) / PT, (2 * a.H + PT - 1) / PT, a.batch);
+  // blocks are placed relative to each sample's needed region (BgPrep::need): no block beyond the largest one has work
+  const int pw = a.prep_w > 0 ? min(a.prep_w, 2 * a.W) : 2 * a.W, ph = a.prep_h > 0 ? min(a.prep_h, 2 * a.H) : 2 * a.H;
+  dim3 grid((pw + PT - 1) / PT, (ph + PT - 1) / PT, a.batch);
   bg_prep_kernel<<<grid, PREP_THREADS, 0, s>>>(a);
   return 1;
 }
@@ -1854,7 +1872,7 @@ int launch_render_split(const RenderArgs& a, cudaStream_t s, cudaEvent_t before_
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_pairs_kernel<false>, RENDER_THREADS, 0);
     raster_blocks = max(1, sms * max(1, per_sm));
   }
-  cudaMemsetAsync(a.pair_ctl, 0, 2 * sizeof(int), s);
+  cudaMemsetAsync(a.pair_ctl, 0, 3 * sizeof(int), s);
   bin_pairs_kernel<<<a.batch, 256, 0, s>>>(a);
   if (a.n_fields > 0) {
     raster_pairs_kernel<true><<<raster_blocks, RENDER_THREADS, 0, s>>>(a);
