@@ -130,13 +130,13 @@ OFDG_HD_NOINLINE void tile_hline(int* cover, int* area, int* carry, int tx0, int
   if (incr < 0 && ex2 < tx0) Acc<kDevice>::add(carry, dyv - prev);  // the cells left of the tile (walk goes left)
 }
 
-// Row range of edge (xa,ya)-(xb,yb) inside the tile: returns false when the edge cannot touch the tile's
+// Row range of edge (xa,ya)-(xb,yb) inside the tile (or its first `rows` rows): returns false when the edge cannot touch the tile's
 // accumulators at all; `left` is set when it lies entirely left of the tile (carry-in only, no divisions).
-OFDG_HD bool tile_edge_rows(int tx0, int ty0, int xa, int ya, int xb, int yb, int& rlo, int& rhi, bool& left) {
+OFDG_HD bool tile_edge_rows(int tx0, int ty0, int xa, int ya, int xb, int yb, int& rlo, int& rhi, bool& left, int rows = TH) {
   if (ya == yb) return false;
   const int ey1 = ya >> 8, ey2 = yb >> 8;
   rlo = rt_max(rt_min(ey1, ey2), ty0);
-  rhi = rt_min(rt_max(ey1, ey2), ty0 + TH - 1);
+  rhi = rt_min(rt_max(ey1, ey2), ty0 + rows - 1);
   if (rlo > rhi) return false;
   if ((rt_min(xa, xb) >> 8) >= tx0 + TW) return false;
   left = (rt_max(xa, xb) >> 8) < tx0;

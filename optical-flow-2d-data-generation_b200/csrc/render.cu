@@ -770,9 +770,23 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
 // leaves the object's four masks (AA / non-AA, both frames; composites already combined) in HBM: 4 KB per pair, a few
 // hundred pairs per sample. The shade kernel is barrier-free: each warp owns a tile row and blends the tile's pairs in
 // z-order straight from those masks.
-#ifndef OFDG_RASTER_MIN_BLOCKS
-#define OFDG_RASTER_MIN_BLOCKS 5  // measured: 3 / 4 / 5 / 6 blocks per SM -> 0.225 / 0.195 / 0.179 / 0.188 ms (occupancy beats the spills up to 5)
+// The raster kernel's work unit is a horizontal slice of a pair's tile: RTH rows, one warp per row. Slices of a pair are
+// independent (every (edge, row) contribution is closed-form), and smaller blocks mean more of them per SM: the phases of one
+// unit are separated by block-wide barriers whose wait is set by the slowest thread, so many small blocks hide it better.
+#ifndef OFDG_RASTER_ROWS
+#define OFDG_RASTER_ROWS 8  // measured: 8 / 4 / 2 rows (5 / 10 / 20 blocks per SM) -> 0.160 / 0.167 / 0.191 ms
 #endif
+constexpr int RTH = OFDG_RASTER_ROWS;
+constexpr int RSUB = TH / RTH;              // slices per pair
+constexpr int RASTER_THREADS = 32 * RTH;
+constexpr int RASTER_ITEMS = MAX_PAIRS * RTH / TH;  // (edge, row) work items listed per chunk
+static_assert(TH % RTH == 0, "a raster slice must divide the tile");
+#ifndef OFDG_RASTER_MIN_BLOCKS
+#define OFDG_RASTER_MIN_BLOCKS (40 / OFDG_RASTER_ROWS)  // 8 rows, measured: 3 / 4 / 5 / 6 blocks per SM -> 0.225 / 0.195 / 0.179 / 0.188 ms
+#endif
+__device__ __forceinline__ bool box_hits_rows(const int32_t* b, int tx0, int ty0, int rows) {
+  return b[1] <= ty0 + rows - 1 && b[3] >= ty0 && b[0] <= tx0 + TW - 1 && b[2] >= tx0;
+}
 #ifndef OFDG_SHADE_MIN_BLOCKS
 #define OFDG_SHADE_MIN_BLOCKS 6  // measured: 4 / 5 / 6 / 8 blocks per SM -> 0.192 / 0.182 / 0.177 / 0.186 ms
 #endif
@@ -840,33 +854,34 @@ __global__ void __launch_bounds__(256) bin_pairs_kernel(RenderArgs a) {
 }
 
 template <bool kDeform>
-__global__ void __launch_bounds__(RENDER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster_pairs_kernel(RenderArgs a) {
-  __shared__ int s_cover[NLAYER][TH][TW];
-  __shared__ int s_area[NLAYER][TH][TW];
-  __shared__ int s_carry[NLAYER][TH];
+__global__ void __launch_bounds__(RASTER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster_pairs_kernel(RenderArgs a) {
+  __shared__ int s_cover[NLAYER][RTH][TW];
+  __shared__ int s_area[NLAYER][RTH][TW];
+  __shared__ int s_carry[NLAYER][RTH];
   __shared__ float s_q255[256];
   __shared__ PairOutline s_out[NLAYER / 2];
   __shared__ int s_seg_begin[NLAYER], s_seg_count[NLAYER];
-  __shared__ unsigned s_pairs[MAX_PAIRS];
+  __shared__ unsigned s_pairs[RASTER_ITEMS];
   __shared__ int s_npairs;
   __shared__ int s_next;
   if (a.pair_ctl[1]) return;
-  const int total = a.pair_ctl[0];
+  const int total = a.pair_ctl[0] * RSUB;  // work units: RSUB slices per pair
   const int W = a.W, H = a.H;
   const size_t P = (size_t)W * H;
   const int tiles_x = (W + TW - 1) / TW;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < 256; i += RENDER_THREADS) s_q255[i] = (float)i / 255.f;
-  int4 pe_next = blockIdx.x < total ? a.pair_list[blockIdx.x] : make_int4(0, 0, 0, 0);
-  // Pairs differ a lot in cost (1 to 7 outlines, a few to hundreds of edges): after its first pair a block claims the next
-  // one from a queue (pair_ctl[2]) instead of striding over the list, so no block is left with a long tail of heavy pairs.
-  int pr = blockIdx.x;
-  while (pr < total) {
+  for (int i = tid; i < 256; i += RASTER_THREADS) s_q255[i] = (float)i / 255.f;
+  int4 pe_next = blockIdx.x < total ? a.pair_list[blockIdx.x / RSUB] : make_int4(0, 0, 0, 0);
+  // Units differ a lot in cost (1 to 7 outlines, a few to hundreds of edges): after its first unit a block claims the next
+  // one from a queue (pair_ctl[2]) instead of striding over the list, so no block is left with a long tail of heavy units.
+  int unit = blockIdx.x;
+  while (unit < total) {
     const int4 pe = pe_next;
+    const int pr = unit / RSUB, slice = unit % RSUB;
     int pr_next = total;
     if (tid == 0) s_next = (int)gridDim.x + atomicAdd(&a.pair_ctl[2], 1);
     const int tile = pe.y, shape_begin = pe.z;
-    const int tx0 = (tile % tiles_x) * TW, ty0 = (tile / tiles_x) * TH;
+    const int tx0 = (tile % tiles_x) * TW, ty0 = (tile / tiles_x) * TH + slice * RTH;
     const int y = ty0 + warp, x0 = tx0 + lane * 4;
     const bool live = (y < H) && (x0 < W);
     const int n_shapes = pe.w & 0xFFFF, composite = pe.w >> 16;
@@ -877,7 +892,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster
       if (tid < ns) {   // outline tid of this chunk: which of its frames touch the tile, which layers they get
         const FlatShape& sh = a.shapes[shape_begin + s0 + tid];
         PairOutline po;
-        const bool h0 = box_hits_tile(sh.bbox[0], tx0, ty0), h1 = box_hits_tile(sh.bbox[1], tx0, ty0);
+        const bool h0 = box_hits_rows(sh.bbox[0], tx0, ty0, RTH), h1 = box_hits_rows(sh.bbox[1], tx0, ty0, RTH);
         po.deform = (kDeform && h1) ? sh.deform : -1;  // a warped outline's frame-1 masks were materialised by the pre-pass
         const bool r1 = h1 && po.deform < 0;
         po.vbegin[0] = sh.vbegin[0]; po.vbegin[1] = sh.vbegin[1];
@@ -891,21 +906,21 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster
       } else if (tid < NLAYER / 2) {
         s_seg_count[2 * tid] = 0; s_seg_count[2 * tid + 1] = 0;
       }
-      for (int i = tid; i < 2 * ns * (TH * TW / 4); i += RENDER_THREADS) {  // outline k owns layers 2k and 2k + 1
+      for (int i = tid; i < 2 * ns * (RTH * TW / 4); i += RASTER_THREADS) {  // outline k owns layers 2k and 2k + 1
         reinterpret_cast<int4*>(&s_cover[0][0][0])[i] = make_int4(0, 0, 0, 0);
         reinterpret_cast<int4*>(&s_area[0][0][0])[i] = make_int4(0, 0, 0, 0);
       }
-      if (tid < NLAYER * TH) (&s_carry[0][0])[tid] = 0;
+      if (tid < NLAYER * RTH) (&s_carry[0][0])[tid] = 0;
       if (tid == 0) s_npairs = 0;
       __syncthreads();
       if (s0 == 0) {  // the claimed pair's record is in flight while this pair is rasterised
         pr_next = s_next;
-        if (pr_next < total) pe_next = a.pair_list[pr_next];
+        if (pr_next < total) pe_next = a.pair_list[pr_next / RSUB];
       }
       {
         // (a) threads over edges: which tile rows does the edge cross? One work item per (edge, row).
         const int c0 = s_seg_count[0], c1 = c0 + s_seg_count[1], c2 = c1 + s_seg_count[2], c3 = c2 + s_seg_count[3];
-        for (int e = tid; e < c3; e += RENDER_THREADS) {
+        for (int e = tid; e < c3; e += RASTER_THREADS) {
           const int l = e < c0 ? 0 : (e < c1 ? 1 : (e < c2 ? 2 : 3));
           const int ei = e - (l == 0 ? 0 : (l == 1 ? c0 : (l == 2 ? c1 : c2)));
           const int n = s_seg_count[l];
@@ -913,11 +928,11 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster
           const FlatVertex p = v[ei], q = v[ei + 1 == n ? 0 : ei + 1];
           int rlo, rhi;
           bool left;
-          if (!tile_edge_rows(tx0, ty0, p.x, p.y, q.x, q.y, rlo, rhi, left)) continue;
+          if (!tile_edge_rows(tx0, ty0, p.x, p.y, q.x, q.y, rlo, rhi, left, RTH)) continue;
           const int nrows = rhi - rlo + 1;
-          const int base = left ? MAX_PAIRS : atomicAdd(&s_npairs, nrows);
+          const int base = left ? RASTER_ITEMS : atomicAdd(&s_npairs, nrows);
           for (int k = 0; k < nrows; ++k) {
-            if (base + k < MAX_PAIRS) s_pairs[base + k] = ((unsigned)l << 28) | ((unsigned)(rlo + k - ty0) << 24) | (unsigned)ei;
+            if (base + k < RASTER_ITEMS) s_pairs[base + k] = ((unsigned)l << 28) | ((unsigned)(rlo + k - ty0) << 24) | (unsigned)ei;
             else tile_edge_row<true>(&s_cover[l][0][0], &s_area[l][0][0], &s_carry[l][0], tx0, ty0, rlo + k, p.x, p.y, q.x, q.y);  // cheap (left of the tile) or list full
           }
         }
@@ -925,8 +940,10 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster
       __syncthreads();
       {
         // (b) threads over (edge, row) items: closed-form row segment -> cells
-        const int np = min(s_npairs, MAX_PAIRS);
-        for (int i = tid; i < np; i += RENDER_THREADS) {
+        const int np = min(s_npairs, RASTER_ITEMS);
+        // (items stay packed in the first warps: spread over all warps, lane * RTH + warp, the same few dozen divergent items
+        // issue from eight half-empty warps instead of two -- measured 0.160 -> 0.171 ms)
+        for (int i = tid; i < np; i += RASTER_THREADS) {
           const unsigned w = s_pairs[i];
           const int l = (int)(w >> 28), r = ty0 + (int)((w >> 24) & 15u), ei = (int)(w & 0xFFFFFFu);
           const int n = s_seg_count[l];
@@ -995,15 +1012,15 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster
       }
     }
     // the object's four masks over this tile: [AA 0, AA 1, non-AA 0, non-AA 1][tile row][lane], one word = four pixels
-    uint32_t* pm = a.pair_masks + (size_t)pr * (4 * TH * 32) + warp * 32 + lane;
+    uint32_t* pm = a.pair_masks + (size_t)pr * (4 * TH * 32) + (slice * RTH + warp) * 32 + lane;
     pm[0 * TH * 32] = uaa[0]; pm[1 * TH * 32] = uaa[1]; pm[2 * TH * 32] = una[0]; pm[3 * TH * 32] = una[1];
     if (n_shapes <= 0) {  // (an object without outlines: no barrier has published the claim yet)
       __syncthreads();
       pr_next = s_next;
-      if (pr_next < total) pe_next = a.pair_list[pr_next];
+      if (pr_next < total) pe_next = a.pair_list[pr_next / RSUB];
       __syncthreads();
     }
-    pr = pr_next;
+    unit = pr_next;
   }
 }
 
@@ -1869,18 +1886,18 @@ int launch_render_split(const RenderArgs& a, cudaStream_t s, cudaEvent_t before_
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_pairs_kernel<false>, RENDER_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_pairs_kernel<false>, RASTER_THREADS, 0);
     raster_blocks = max(1, sms * max(1, per_sm));
   }
   cudaMemsetAsync(a.pair_ctl, 0, 3 * sizeof(int), s);
   bin_pairs_kernel<<<a.batch, 256, 0, s>>>(a);
   if (a.n_fields > 0) {
-    raster_pairs_kernel<true><<<raster_blocks, RENDER_THREADS, 0, s>>>(a);
+    raster_pairs_kernel<true><<<raster_blocks, RASTER_THREADS, 0, s>>>(a);
     if (before_shade) cudaEventRecord(before_shade, s);
     if (extra) shade_kernel<true, true><<<grid, RENDER_THREADS, 0, s>>>(a);
     else shade_kernel<true, false><<<grid, RENDER_THREADS, 0, s>>>(a);
   } else {
-    raster_pairs_kernel<false><<<raster_blocks, RENDER_THREADS, 0, s>>>(a);
+    raster_pairs_kernel<false><<<raster_blocks, RASTER_THREADS, 0, s>>>(a);
     if (before_shade) cudaEventRecord(before_shade, s);
     if (extra) shade_kernel<false, true><<<grid, RENDER_THREADS, 0, s>>>(a);
     else shade_kernel<false, false><<<grid, RENDER_THREADS, 0, s>>>(a);
