@@ -168,6 +168,7 @@ struct ofdg_generator {
   DevBuf bg, tile_hits;
   // split render path: per-tile pair ranges, the pair list, the pairs' masks, control words (csrc/render.cuh)
   DevBuf tile_range, pair_list, pair_masks, pair_ctl;
+  PinnedBuf pair_overflow;  // one int the binning kernel raises if a batch ever had more pairs than the host-computed bound
   int pair_cap = 0;
   bool split_render = true;  // OFDG_RENDER=fused selects the single-kernel path
   DevBuf out0, out1, outf;  // device blobs for the *_host entry points
@@ -323,6 +324,10 @@ void ensure_scratch(ofdg_generator* g, int batch) {
     const size_t tiles = ofdg::tile_hits_bytes(1, (int)W, (int)H) / ofdg::TILE_HIT_STRIDE;
     g->tile_range.reserve((size_t)batch * tiles * sizeof(int2));
     g->pair_ctl.reserve(4 * sizeof(int));
+    if (!g->pair_overflow.p) {
+      g->pair_overflow.reserve(sizeof(int));
+      *(volatile int*)g->pair_overflow.p = 0;
+    }
   }
   g->scratch_batch = batch;
 }
@@ -351,6 +356,7 @@ ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, 
     }
     a.tile_range = (int2*)g->tile_range.p; a.pair_list = (int4*)g->pair_list.p; a.pair_masks = (uint32_t*)g->pair_masks.p;
     a.pair_ctl = (int*)g->pair_ctl.p; a.pair_cap = g->pair_cap;
+    a.pair_overflow = (int*)g->pair_overflow.dev;
   }
   a.pos_x = (const int*)g->rtab_pos_x.p; a.alpha_x = (const double*)g->rtab_alpha_x.p;
   a.pos_y = (const int*)g->rtab_pos_y.p; a.alpha_y = (const double*)g->rtab_alpha_y.p;
@@ -380,6 +386,17 @@ ofdg::RenderArgs with_extra_tops(ofdg_generator* g, ofdg::RenderArgs a) {
     a.ids8 = (uint8_t*)g->ids8.p;
   }
   return a;
+}
+
+// After a synchronisation: the pair buffers are sized from an upper bound of the batch's (object, tile) pairs, so the
+// binning kernel can never run out of room; if it ever did (its kernels then skip the batch instead of writing out of
+// bounds) the call that notices fails loudly rather than handing back blobs that were not rendered.
+void check_pair_overflow(ofdg_generator* g) {
+  volatile int* f = (volatile int*)g->pair_overflow.p;
+  if (f && *f) {
+    *f = 0;
+    throw StateError("internal: more (object, tile) pairs than the mask buffer was sized for; the batch was not rendered");
+  }
 }
 
 cudaEvent_t timing_event(ofdg_generator* g) {
@@ -622,6 +639,7 @@ void ofdg_destroy(ofdg_generator* g) {
   for (DevBuf* b : bufs) b->release();
   g->scene.release();
   g->staging.release();
+  g->pair_overflow.release();
   for (int i = 0; i < 2; ++i) {
     g->pipe_scene[i].release();
     g->pipe_staging[i].release();
@@ -898,7 +916,7 @@ int ofdg_render(ofdg_generator* g, const ofdg_task_batch* tasks, float* d_img0, 
     run_kernels(g, with_extra_tops(g, make_args(g, g->pipe_scene[set], d_img0, d_img1, d_flow)), s);
     CK(cudaEventRecord(g->render_done[set], s));
     g->render_set_used[set] = true;
-    if (!stream) CK(cudaStreamSynchronize(s));
+    if (!stream) { CK(cudaStreamSynchronize(s)); check_pair_overflow(g); }
   });
 }
 
@@ -1058,6 +1076,7 @@ static void render_host_pipelined(ofdg_generator* g, ofdg_params* params, const 
   }
   CK(cudaStreamSynchronize(B));
   CK(cudaStreamSynchronize(A));
+  check_pair_overflow(g);
   const double t_copied = now_ms();
   g->workers->wait();
   if (trace) {
@@ -1282,7 +1301,7 @@ int ofdg_generate_philox(ofdg_generator* g, uint64_t seed, uint64_t first_sample
     CK(cudaEventRecord(g->ph[nset].ready, g->ph_stream));
     g->ph_next.valid = true; g->ph_next.seed = seed; g->ph_next.first = first_sample + (uint64_t)batch;
     g->ph_next.batch = batch; g->ph_next.augment = augment; g->ph_next.set = nset;
-    if (!stream) CK(cudaStreamSynchronize(s));
+    if (!stream) { CK(cudaStreamSynchronize(s)); check_pair_overflow(g); }
   });
 }
 
@@ -1361,7 +1380,7 @@ int ofdg_render_prepared(ofdg_generator* g, const ofdg_prepared* p, float* d_img
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
     ensure_scratch(g, p->scene.batch);
     run_kernels(g, with_extra_tops(g, make_args(g, p->scene, d_img0, d_img1, d_flow)), s);
-    if (!stream) CK(cudaStreamSynchronize(s));
+    if (!stream) { CK(cudaStreamSynchronize(s)); check_pair_overflow(g); }
   });
 }
 
@@ -1391,6 +1410,7 @@ int ofdg_kernel_times(ofdg_generator* g, double* prep_ms, double* render_ms, int
     if (!g) throw ArgError("null pointer");
     g->use();
     CK(cudaDeviceSynchronize());
+    check_pair_overflow(g);
     double t[3] = {0, 0, 0};
     for (const ofdg_generator::Span& sp : g->spans) {
       float ms = 0.f;

@@ -837,7 +837,10 @@ __global__ void __launch_bounds__(256) bin_pairs_kernel(RenderArgs a) {
   if (tid == 255) {
     const int total = s_scan[255];
     const int base = atomicAdd(&a.pair_ctl[0], total);
-    if (base + total > a.pair_cap) a.pair_ctl[1] = 1;  // more pairs than the mask buffer holds: the fused kernel renders this batch
+    if (base + total > a.pair_cap) {  // more pairs than the mask buffer holds (the host sizes it from an upper bound, so this is a bug trap):
+      a.pair_ctl[1] = 1;              // the raster and shade kernels skip the batch, and the host reports it after its next synchronisation
+      if (a.pair_overflow) *a.pair_overflow = 1;
+    }
     s_base = base;
   }
   __syncthreads();

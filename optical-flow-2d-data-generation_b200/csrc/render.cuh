@@ -33,8 +33,9 @@ struct RenderArgs {
   int4* pair_list;            // [pair_cap] {sample * 256 + object, tile, first outline (absolute), outline count | composite << 16}
   int prep_w, prep_h;         // extent of the largest needed part of a prepared background (0: the whole canvas): bg_prep_kernel's grid
   uint32_t* pair_masks;       // [pair_cap][AA 0 | AA 1 | non-AA 0 | non-AA 1][TH][32] four pixels per word
-  int* pair_ctl;              // [0] pairs claimed (atomic), [1] set when they exceed pair_cap (the fused kernel renders the batch), [2] the raster kernel's work queue
+  int* pair_ctl;              // [0] pairs claimed (atomic), [1] set when they exceed pair_cap (cannot happen: pair_cap is an upper bound; the kernels then skip the batch), [2] the raster kernel's work queue
   int pair_cap;
+  int* pair_overflow;         // mapped host int, raised together with pair_ctl[1] (the host reports it after its next synchronisation)
   // mode 9
   const float* fields;        // [n][flow|iflow][channel][H+1][W+1]
   int n_fields;
