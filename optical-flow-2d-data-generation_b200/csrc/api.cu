@@ -171,6 +171,7 @@ struct ofdg_generator {
   PinnedBuf pair_overflow;  // one int the binning kernel raises if a batch ever had more pairs than the host-computed bound
   int pair_cap = 0;
   bool split_render = true;  // OFDG_RENDER=fused selects the single-kernel path
+  int pair_cap_limit = 0;    // OFDG_TEST_PAIR_CAP: pretend the pair buffers are this small (tests of the overflow trap)
   DevBuf out0, out1, outf;  // device blobs for the *_host entry points
   ofdg_extra_tops extra{};  // extra tops of the device-blob calls (ofdg_set_extra_tops)
   DevBuf ids8;              // object ranks per pixel, scratch of the occlusion pass
@@ -355,7 +356,7 @@ ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, 
       g->pair_cap = (int)cap;
     }
     a.tile_range = (int2*)g->tile_range.p; a.pair_list = (int4*)g->pair_list.p; a.pair_masks = (uint32_t*)g->pair_masks.p;
-    a.pair_ctl = (int*)g->pair_ctl.p; a.pair_cap = g->pair_cap;
+    a.pair_ctl = (int*)g->pair_ctl.p; a.pair_cap = g->pair_cap_limit > 0 ? std::min(g->pair_cap, g->pair_cap_limit) : g->pair_cap;
     a.pair_overflow = (int*)g->pair_overflow.dev;
   }
   a.pos_x = (const int*)g->rtab_pos_x.p; a.alpha_x = (const double*)g->rtab_alpha_x.p;
@@ -616,6 +617,7 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
     for (cudaEvent_t& e2 : g->chunk_copied) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming | cudaEventBlockingSync));
     if (const char* t = std::getenv("OFDG_TRANSPORT")) g->transport_u8 = std::string(t) != "f32";  // "f32": float blobs cross PCIe as they are
     if (const char* t = std::getenv("OFDG_RENDER")) g->split_render = std::string(t) != "fused";
+    if (const char* t = std::getenv("OFDG_TEST_PAIR_CAP")) g->pair_cap_limit = std::atoi(t);
     *out = g.release();
   });
 }
@@ -1076,9 +1078,9 @@ static void render_host_pipelined(ofdg_generator* g, ofdg_params* params, const 
   }
   CK(cudaStreamSynchronize(B));
   CK(cudaStreamSynchronize(A));
-  check_pair_overflow(g);
   const double t_copied = now_ms();
   g->workers->wait();
+  check_pair_overflow(g);
   if (trace) {
     std::string line = "[ofdg host pipeline] scenes ready / chunk issued (ms):";
     char buf[64];

@@ -454,6 +454,24 @@ def test_argument_and_state_errors(ofdg, textures8):
         ofdg.Generator(device=0, mode=1, width=510)
 
 
+def test_pair_buffer_overflow_is_reported(ofdg, textures8, monkeypatch):
+    """The (object, tile) pair buffers are sized from an upper bound, so the binning kernel cannot run out of room; if it
+    ever did, the raster and shade kernels skip the batch and the call fails instead of returning blobs nobody rendered.
+    OFDG_TEST_PAIR_CAP makes the kernels believe the buffers hold 8 pairs."""
+    monkeypatch.setenv("OFDG_TEST_PAIR_CAP", "8")
+    g = _gen(ofdg, 7, max_batch=4)
+    monkeypatch.delenv("OFDG_TEST_PAIR_CAP")
+    g.upload_textures(textures8)
+    tasks = ofdg.ParamStream(7).generate(2)
+    with pytest.raises(ofdg.OfdgError, match="pairs"):
+        g.render_host(tasks)
+    g.close()
+    g = _gen(ofdg, 7, max_batch=4)   # without the limit the same batch renders
+    g.upload_textures(textures8)
+    assert g.render_host(tasks)[0].std() > 10
+    g.close()
+
+
 @pytest.mark.parametrize("mode", [7, 9])
 def test_prepared_batches_into_host_blobs(ofdg, oracle, textures8, fields4, mode):
     """ofdg_render_prepared_host (the layer's Forward_cpu): chunked windows over a resident scene, uint8 transport,
