@@ -102,6 +102,9 @@ __device__ __forceinline__ float byte_to_float(uint32_t px, int c) {
   return __uint_as_float(__byte_perm(px, 0x4B000000u, 0x7440u + (unsigned)c)) - 8388608.0f;
 }
 
+__device__ __forceinline__ float byte_to_biased(uint32_t px, int c) {  // 2^23 + byte c (exact)
+  return __uint_as_float(__byte_perm(px, 0x4B000000u, 0x7440u + (unsigned)c));
+}
 __device__ __forceinline__ uint32_t ld_px(const uchar4* p) { return *reinterpret_cast<const uint32_t*>(p); }
 
 __device__ __forceinline__ uint32_t bilinear_rgbx(const uchar4* img, int pitch, int ox, int oy, int sw, int sh,
@@ -1427,13 +1430,15 @@ __device__ __forceinline__ uint32_t rotated_px_fast(const uchar4* tex, int w, co
   const float dx = fx - fix, dy = fy - fiy;
   const uchar4* t00 = tex + (ptrdiff_t)(m.ry0 + m.rs * (int)iy) * w + (m.cx0 + m.cs * (int)ix);
   const ptrdiff_t ox = dx > 0 ? m.cs : 0, oy = dy > 0 ? (ptrdiff_t)m.rs * w : 0;
-  const uint32_t pcc = ld_px(t00) & 0xFFFFFFu, pnc = ld_px(t00 + ox) & 0xFFFFFFu, pcn = ld_px(t00 + oy) & 0xFFFFFFu,
-                 pnn = ld_px(t00 + ox + oy) & 0xFFFFFFu;
+  const uint32_t pcc = ld_px(t00), pnc = ld_px(t00 + ox), pcn = ld_px(t00 + oy), pnn = ld_px(t00 + ox + oy);  // (the X byte is never selected)
   uint32_t out = 0;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float Icc = byte_to_float(pcc, c), Inc = byte_to_float(pnc, c), Icn = byte_to_float(pcn, c), Inn = byte_to_float(pnn, c);
-    const float v = Icc + dx * (Inc - Icc + dy * (Icc + Inn - Icn - Inc)) + dy * (Icn - Icc);
+    // CImg: v = Icc + dx * (Inc - Icc + dy * (Icc + Inn - Icn - Inc)) + dy * (Icn - Icc). The byte differences are small
+    // integers, exact in float in any order -- so they are taken between the biased values 2^23 + byte directly (the
+    // bias cancels exactly) and only the leading Icc is un-biased: three additions per channel less, same roundings.
+    const float Mcc = byte_to_biased(pcc, c), Mnc = byte_to_biased(pnc, c), Mcn = byte_to_biased(pcn, c), Mnn = byte_to_biased(pnn, c);
+    const float v = (Mcc - 8388608.0f) + dx * ((Mnc - Mcc) + dy * ((Mcc - Mcn) + (Mnn - Mnc))) + dy * (Mcn - Mcc);
     // (unsigned char)v for 0 <= v <= 255: truncate through the same mantissa trick (round towards zero)
     out |= (__float_as_uint(__fadd_rz(fmaxf(v, 0.f), 8388608.0f)) & 255u) << (8 * c);  // (a rounding residue below zero also truncates to 0)
   }
