@@ -1431,7 +1431,7 @@ __device__ __forceinline__ uint32_t rotated_px_fast(const uchar4* tex, int w, co
   const uchar4* t00 = tex + (ptrdiff_t)(m.ry0 + m.rs * (int)iy) * w + (m.cx0 + m.cs * (int)ix);
   const ptrdiff_t ox = dx > 0 ? m.cs : 0, oy = dy > 0 ? (ptrdiff_t)m.rs * w : 0;
   const uint32_t pcc = ld_px(t00), pnc = ld_px(t00 + ox), pcn = ld_px(t00 + oy), pnn = ld_px(t00 + ox + oy);  // (the X byte is never selected)
-  uint32_t out = 0;
+  uint32_t t[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     // CImg: v = Icc + dx * (Inc - Icc + dy * (Icc + Inn - Icn - Inc)) + dy * (Icn - Icc). The byte differences are small
@@ -1440,9 +1440,9 @@ __device__ __forceinline__ uint32_t rotated_px_fast(const uchar4* tex, int w, co
     const float Mcc = byte_to_biased(pcc, c), Mnc = byte_to_biased(pnc, c), Mcn = byte_to_biased(pcn, c), Mnn = byte_to_biased(pnn, c);
     const float v = (Mcc - 8388608.0f) + dx * ((Mnc - Mcc) + dy * ((Mcc - Mcn) + (Mnn - Mnc))) + dy * (Mcn - Mcc);
     // (unsigned char)v for 0 <= v <= 255: truncate through the same mantissa trick (round towards zero)
-    out |= (__float_as_uint(__fadd_rz(fmaxf(v, 0.f), 8388608.0f)) & 255u) << (8 * c);  // (a rounding residue below zero also truncates to 0)
+    t[c] = __float_as_uint(__fadd_rz(fmaxf(v, 0.f), 8388608.0f));  // 0x4B0000vv (a rounding residue below zero also truncates to 0)
   }
-  return out;
+  return __byte_perm(__byte_perm(t[0], t[1], 0x0040u), t[2], 0x5410u);  // {t0.b0, t1.b0, t2.b0, t2.b1 = 0}
 }
 
 // One resize pass (CImg get_resize interpolation 3; shrinking axes use the moving average)
@@ -1480,7 +1480,7 @@ __device__ __forceinline__ ResizeTaps make_taps(int len, int n, int t, const int
 __device__ __forceinline__ uint32_t apply_taps(const uint32_t* src, int stride, int s0, int len, unsigned magic, const ResizeTaps& r) {
   const uint32_t* p0 = src + (r.first - s0) * stride;
   if (r.count == 0) return p0[0];
-  uint32_t out = 0;
+  uint32_t t[3];  // the three channels' results, each below 256: packed by two byte permutes (t[2]'s byte 1 supplies the zero)
   if (r.count > 0) {
     unsigned acc[3] = {0u, 0u, 0u};
 #pragma unroll
@@ -1492,8 +1492,8 @@ __device__ __forceinline__ uint32_t apply_taps(const uint32_t* src, int stride, 
       }
     }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) out |= __umulhi(acc[c], magic) << (8 * c);
-    return out;
+    for (int c = 0; c < 3; ++c) t[c] = __umulhi(acc[c], magic);
+    return __byte_perm(__byte_perm(t[0], t[1], 0x0040u), t[2], 0x5410u);
   }
   const uint32_t p1 = p0[0], p2 = r.first < len - 1 ? p0[stride] : p1;
   // byte -> double and double -> byte without the conversion unit: 2^52 + b has b in its low mantissa bits (exact), and
@@ -1504,9 +1504,9 @@ __device__ __forceinline__ uint32_t apply_taps(const uint32_t* src, int stride, 
     const double b1 = __hiloint2double(0x43300000, (int)__byte_perm(p1, 0u, 0x4440u + (unsigned)c)) - two52;
     const double b2 = __hiloint2double(0x43300000, (int)__byte_perm(p2, 0u, 0x4440u + (unsigned)c)) - two52;
     const double v = na * b1 + r.alpha * b2;
-    out |= ((uint32_t)__double2loint(__dadd_rz(v, two52)) & 255u) << (8 * c);
+    t[c] = (uint32_t)__double2loint(__dadd_rz(v, two52));  // low word of 2^52 + floor(v): 0x000000vv
   }
-  return out;
+  return __byte_perm(__byte_perm(t[0], t[1], 0x0040u), t[2], 0x5410u);
 }
 
 // fast path only (len <= 1.3 n): every product below 2^31
