@@ -119,16 +119,15 @@ __device__ __forceinline__ uint32_t bilinear_rgbx(const uchar4* img, int pitch, 
   // sum w_k p_k = [p00 (256-fx) + p10 fx] (256-fy) + [p01 (256-fx) + p11 fx] fy, exact in integers;
   // the horizontal pair is one dp4a: bytes {p00_c, p10_c, p00_c, 0} . {255-fx, fx, 1, 0}
   const unsigned wx = (255u - fx) | (fx << 8) | (1u << 16);
-  uint32_t out = 0;
+  unsigned sacc[3];  // below 2^24: byte 2 is the channel's result, byte 3 is zero
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const unsigned sel = (unsigned)c | ((4u + c) << 4) | ((unsigned)c << 8) | (3u << 12);
     const unsigned top = __dp4a(__byte_perm(p00, p10, sel), wx, 0u);
     const unsigned bot = __dp4a(__byte_perm(p01, p11, sel), wx, 0u);
-    const unsigned sacc = 32768u + top * (256u - fy) + bot * fy;
-    out |= (sacc >> 16) << (8 * c);
+    sacc[c] = 32768u + top * (256u - fy) + bot * fy;
   }
-  return out;
+  return __byte_perm(__byte_perm(sacc[0], sacc[1], 0x0062u), sacc[2], 0x7610u);
 }
 
 // Out-of-line copy for the render kernel's eight call sites (keeps its code inside the instruction cache);
@@ -144,13 +143,12 @@ __device__ __noinline__ uint32_t bilinear_rgbx_call(const uchar4* base, int pitc
 
 // CImg draw_image(sprite, mask, 1, 255) per channel == floor((m*t + f*(255-m)) / 255)  
 __device__ __forceinline__ uint32_t blend_rgbx(uint32_t f, uint32_t t, unsigned m) {
-  uint32_t out = 0;
+  const unsigned w = m | ((255u - m) << 8);  // one dp4a per channel: bytes {t_c, f_c, 0, 0} . {m, 255 - m, 0, 0}
+  unsigned q[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    unsigned fv = (f >> (8 * c)) & 255u, tv = (t >> (8 * c)) & 255u;
-    out |= ((m * tv + fv * (255u - m)) / 255u) << (8 * c);
-  }
-  return out;
+  for (int c = 0; c < 3; ++c)
+    q[c] = __umulhi(__dp4a(__byte_perm(t, f, (unsigned)c | ((4u + c) << 4)), w, 0u), 16843010u);  // floor(x / 255), x <= 65025
+  return __byte_perm(__byte_perm(q[0], q[1], 0x0040u), q[2], 0x5410u);  // q <= 255: q[2]'s byte 1 supplies the zero
 }
 
 // ------------------------------------------------------------------------------------------------
