@@ -200,6 +200,8 @@ struct ofdg_generator {
   PinnedBuf pipe_staging[2];
   ofdg::FlatBatch pipe_flat[2];
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t bin_stream = nullptr;  // pair binning of a batch beside its background preparation (OFDG_BIN_OVERLAP=0: same stream)
+  cudaEvent_t bin_fork = nullptr, bin_join = nullptr;
   cudaEvent_t pipe_uploaded[2] = {nullptr, nullptr}, pipe_rendered[2] = {nullptr, nullptr}, render_done[2] = {nullptr, nullptr};
   bool render_set_used[2] = {false, false};
   uint64_t render_calls = 0;
@@ -418,6 +420,13 @@ void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s, b
   if (deform_prepass) g->launches += ofdg::launch_deform_prepass(a, s);
   ofdg_generator::Span sp{timing_event(g), timing_event(g), 0};
   CK(cudaEventRecord(sp.a, s));
+  const bool fork_bin = g->bin_stream && a.pair_ctl && a.flow;
+  if (fork_bin) {  // everything queued on s so far (scene upload, the previous batch's kernels) precedes the binning
+    CK(cudaEventRecord(g->bin_fork, s));
+    CK(cudaStreamWaitEvent(g->bin_stream, g->bin_fork, 0));
+    g->launches += ofdg::launch_bin_pairs(a, g->bin_stream);  // queued ahead of the preparation's blocks: runs beside them
+    CK(cudaEventRecord(g->bin_join, g->bin_stream));
+  }
   if (!a.pair_ctl || !a.flow) g->launches += ofdg::launch_bin(a, s);  // (the split path bins inside launch_render_split)
   g->launches += ofdg::launch_background_prep(a, s);
   CK(cudaEventRecord(sp.b, s));
@@ -427,7 +436,8 @@ void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s, b
     CK(cudaEventRecord(sr.a, s));
     if (a.pair_ctl) {
       cudaEvent_t mid = timing_event(g);
-      g->launches += ofdg::launch_render_split(a, s, mid);
+      if (fork_bin) CK(cudaStreamWaitEvent(s, g->bin_join, 0));
+      g->launches += ofdg::launch_render_split(a, s, mid, fork_bin);
       CK(cudaEventRecord(sr.b, s));
       g->spans.push_back(ofdg_generator::Span{mid, sr.b, 2});
     } else {
@@ -618,6 +628,12 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
     if (const char* t = std::getenv("OFDG_TRANSPORT")) g->transport_u8 = std::string(t) != "f32";  // "f32": float blobs cross PCIe as they are
     if (const char* t = std::getenv("OFDG_RENDER")) g->split_render = std::string(t) != "fused";
     if (const char* t = std::getenv("OFDG_TEST_PAIR_CAP")) g->pair_cap_limit = std::atoi(t);
+    const char* ov = std::getenv("OFDG_BIN_OVERLAP");
+    if (g->split_render && !(ov && std::string(ov) == "0")) {
+      CK(cudaStreamCreateWithFlags(&g->bin_stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&g->bin_fork, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&g->bin_join, cudaEventDisableTiming));
+    }
     *out = g.release();
   });
 }
@@ -654,6 +670,9 @@ void ofdg_destroy(ofdg_generator* g) {
   g->out8.release();
   g->host8.release();
   if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
+  if (g->bin_stream) { cudaStreamSynchronize(g->bin_stream); cudaStreamDestroy(g->bin_stream); }
+  if (g->bin_fork) cudaEventDestroy(g->bin_fork);
+  if (g->bin_join) cudaEventDestroy(g->bin_join);
   for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;

@@ -1883,7 +1883,13 @@ int launch_render(const RenderArgs& a, cudaStream_t s) {
 
 size_t pair_mask_bytes_per_pair() { return (size_t)4 * TH * 32 * sizeof(uint32_t); }
 
-int launch_render_split(const RenderArgs& a, cudaStream_t s, cudaEvent_t before_shade) {
+int launch_bin_pairs(const RenderArgs& a, cudaStream_t s) {
+  cudaMemsetAsync(a.pair_ctl, 0, 3 * sizeof(int), s);
+  bin_pairs_kernel<<<a.batch, 256, 0, s>>>(a);
+  return 1;
+}
+
+int launch_render_split(const RenderArgs& a, cudaStream_t s, cudaEvent_t before_shade, bool binned) {
   const int tiles_x = (a.W + TW - 1) / TW, tiles_y = (a.H + TH - 1) / TH;
   dim3 grid(tiles_x * tiles_y, a.batch);
   const bool extra = a.flow_bw || a.top_id0 || a.top_id1 || a.ids8;
@@ -1895,8 +1901,7 @@ int launch_render_split(const RenderArgs& a, cudaStream_t s, cudaEvent_t before_
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_pairs_kernel<false>, RASTER_THREADS, 0);
     raster_blocks = max(1, sms * max(1, per_sm));
   }
-  cudaMemsetAsync(a.pair_ctl, 0, 3 * sizeof(int), s);
-  bin_pairs_kernel<<<a.batch, 256, 0, s>>>(a);
+  if (!binned) launch_bin_pairs(a, s);
   if (a.n_fields > 0) {
     raster_pairs_kernel<true><<<raster_blocks, RASTER_THREADS, 0, s>>>(a);
     if (before_shade) cudaEventRecord(before_shade, s);
@@ -1908,10 +1913,10 @@ int launch_render_split(const RenderArgs& a, cudaStream_t s, cudaEvent_t before_
     if (extra) shade_kernel<false, true><<<grid, RENDER_THREADS, 0, s>>>(a);
     else shade_kernel<false, false><<<grid, RENDER_THREADS, 0, s>>>(a);
   }
-  if (!a.occlusion) return 3;
+  if (!a.occlusion) return binned ? 2 : 3;
   const size_t P = (size_t)a.W * a.H;
   occlusion_kernel<<<dim3((unsigned)((P + 255) / 256), a.batch), 256, 0, s>>>(a);
-  return 4;
+  return binned ? 3 : 4;
 }
 
 void launch_planar_to_rgbx(const uint8_t* planar, uchar4* out, int n, int w, int h, cudaStream_t s) {

@@ -75,7 +75,11 @@ int launch_background_prep(const RenderArgs& a, cudaStream_t s);
 int launch_render(const RenderArgs& a, cudaStream_t s);  // + the occlusion pass when a.occlusion is set
 // Split path: bin + raster + shade (+ the fused kernel, which only does work when the pair buffer overflowed).
 // Replaces launch_bin + launch_render; a.pair_* must be set.
-int launch_render_split(const RenderArgs& a, cudaStream_t s, cudaEvent_t before_shade = nullptr);  // the event, if given, is recorded between raster and shade
+// before_shade, if given, is recorded between raster and shade. binned: the caller has already queued launch_bin_pairs for this
+// batch (on a forked stream, beside the background preparation: one block per sample, a 12 us latency-bound launch) and made
+// s wait for it.
+int launch_bin_pairs(const RenderArgs& a, cudaStream_t s);
+int launch_render_split(const RenderArgs& a, cudaStream_t s, cudaEvent_t before_shade = nullptr, bool binned = false);
 size_t pair_mask_bytes_per_pair();
 int launch_deform_prepass(const RenderArgs& a, cudaStream_t s);  // mode 9 only; no-op when n_deform == 0
 
