@@ -202,6 +202,7 @@ struct ofdg_generator {
   cudaStream_t copy_stream = nullptr;
   cudaStream_t bin_stream = nullptr;  // pair binning of a batch beside its background preparation (OFDG_BIN_OVERLAP=0: same stream)
   cudaEvent_t bin_fork = nullptr, bin_join = nullptr;
+  bool raster_overlap = false, philox_raster_overlap = false;
   cudaEvent_t pipe_uploaded[2] = {nullptr, nullptr}, pipe_rendered[2] = {nullptr, nullptr}, render_done[2] = {nullptr, nullptr};
   bool render_set_used[2] = {false, false};
   uint64_t render_calls = 0;
@@ -415,16 +416,18 @@ cudaEvent_t timing_event(ofdg_generator* g) {
 // (Running the preparation of the next chunk on a second stream next to the render kernel was
 // measured and is slower: both kernels are issue-bound and the extra launches cost more than the
 // overlap gains -- profiles/README.md.)
-void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s, bool deform_prepass = true) {
+void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s, bool deform_prepass = true, bool side_raster = true) {
   if (g->spans.size() > 60000) { g->spans.clear(); g->ev_next = 0; g->timed_calls = 0; }  // nobody is reading the timings
   if (deform_prepass) g->launches += ofdg::launch_deform_prepass(a, s);
   ofdg_generator::Span sp{timing_event(g), timing_event(g), 0};
   CK(cudaEventRecord(sp.a, s));
   const bool fork_bin = g->bin_stream && a.pair_ctl && a.flow;
+  const bool fork_raster = fork_bin && g->raster_overlap && side_raster;
   if (fork_bin) {  // everything queued on s so far (scene upload, the previous batch's kernels) precedes the binning
     CK(cudaEventRecord(g->bin_fork, s));
     CK(cudaStreamWaitEvent(g->bin_stream, g->bin_fork, 0));
     g->launches += ofdg::launch_bin_pairs(a, g->bin_stream);  // queued ahead of the preparation's blocks: runs beside them
+    if (fork_raster) g->launches += ofdg::launch_raster_pairs(a, g->bin_stream);  // masks need the scene + pair list only
     CK(cudaEventRecord(g->bin_join, g->bin_stream));
   }
   if (!a.pair_ctl || !a.flow) g->launches += ofdg::launch_bin(a, s);  // (the split path bins inside launch_render_split)
@@ -437,7 +440,7 @@ void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s, b
     if (a.pair_ctl) {
       cudaEvent_t mid = timing_event(g);
       if (fork_bin) CK(cudaStreamWaitEvent(s, g->bin_join, 0));
-      g->launches += ofdg::launch_render_split(a, s, mid, fork_bin);
+      g->launches += ofdg::launch_render_split(a, s, mid, fork_raster ? 2 : fork_bin ? 1 : 0);
       CK(cudaEventRecord(sr.b, s));
       g->spans.push_back(ofdg_generator::Span{mid, sr.b, 2});
     } else {
@@ -604,7 +607,12 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
     g->cfg = *cfg;
     CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&g->ph_stream, cudaStreamNonBlocking));
+    {
+      const char* pp = std::getenv("OFDG_PHILOX_PRIORITY");  // 1: the look-ahead parameter kernels are placed ahead of the render's
+      int lo = 0, hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CK(cudaStreamCreateWithPriority(&g->ph_stream, cudaStreamNonBlocking, (pp && std::string(pp) == "1") ? hi : 0));
+    }
     for (int i = 0; i < 2; ++i) {
       CK(cudaEventCreateWithFlags(&g->ph[i].ready, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&g->ph[i].consumed, cudaEventDisableTiming));
@@ -630,7 +638,19 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
     if (const char* t = std::getenv("OFDG_TEST_PAIR_CAP")) g->pair_cap_limit = std::atoi(t);
     const char* ov = std::getenv("OFDG_BIN_OVERLAP");
     if (g->split_render && !(ov && std::string(ov) == "0")) {
-      CK(cudaStreamCreateWithFlags(&g->bin_stream, cudaStreamNonBlocking));
+      // The mask rasterisation of a batch runs on the side stream too, beside the background preparation: it needs the scene
+      // and the pair list only, and the two kernels stall on different things (OFDG_RASTER_OVERLAP=0: in line; the per-kernel
+      // spans of ofdg_kernel_times then do not overlap). The side stream has the higher priority: the persistent raster
+      // blocks must be placed ahead of the preparation's ~20,000 short blocks, or they only start when those have drained.
+      // The device-side parameter stream keeps the raster in line (OFDG_PHILOX_RASTER_OVERLAP=1 forks it there as well): its
+      // look-ahead kernels already fill the preparation's idle issue slots and are starved by a third concurrent kernel.
+      const char* ro = std::getenv("OFDG_RASTER_OVERLAP");
+      g->raster_overlap = !(ro && std::string(ro) == "0");
+      const char* po = std::getenv("OFDG_PHILOX_RASTER_OVERLAP");
+      g->philox_raster_overlap = po && std::string(po) == "1";
+      int lo = 0, hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CK(cudaStreamCreateWithPriority(&g->bin_stream, cudaStreamNonBlocking, hi));
       CK(cudaEventCreateWithFlags(&g->bin_fork, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&g->bin_join, cudaEventDisableTiming));
     }
@@ -1312,7 +1332,7 @@ int ofdg_generate_philox(ofdg_generator* g, uint64_t seed, uint64_t first_sample
       philox_collect(g, set, s);
     }
     ensure_scratch(g, batch);
-    run_kernels(g, with_extra_tops(g, make_args(g, g->ph[set].scene, d_img0, d_img1, d_flow)), s);
+    run_kernels(g, with_extra_tops(g, make_args(g, g->ph[set].scene, d_img0, d_img1, d_flow)), s, true, g->philox_raster_overlap);
     CK(cudaEventRecord(g->ph[set].consumed, s));
     g->ph[set].used = true;
     // look ahead: the next batch of the same stream, on the side stream, into the other set

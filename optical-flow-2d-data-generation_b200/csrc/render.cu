@@ -1889,34 +1889,45 @@ int launch_bin_pairs(const RenderArgs& a, cudaStream_t s) {
   return 1;
 }
 
-int launch_render_split(const RenderArgs& a, cudaStream_t s, cudaEvent_t before_shade, bool binned) {
-  const int tiles_x = (a.W + TW - 1) / TW, tiles_y = (a.H + TH - 1) / TH;
-  dim3 grid(tiles_x * tiles_y, a.batch);
-  const bool extra = a.flow_bw || a.top_id0 || a.top_id1 || a.ids8;
-  static int raster_blocks = 0;  // resident blocks of the device for the persistent raster kernel
+static int raster_grid() {  // resident blocks of the device for the persistent raster kernel (OFDG_RASTER_BLOCKS_PER_SM: fewer)
+  static int raster_blocks = 0;
   if (!raster_blocks) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_pairs_kernel<false>, RASTER_THREADS, 0);
+    if (const char* t = std::getenv("OFDG_RASTER_BLOCKS_PER_SM")) per_sm = min(per_sm, max(1, std::atoi(t)));
     raster_blocks = max(1, sms * max(1, per_sm));
   }
-  if (!binned) launch_bin_pairs(a, s);
+  return raster_blocks;
+}
+
+int launch_raster_pairs(const RenderArgs& a, cudaStream_t s) {
+  if (a.n_fields > 0) raster_pairs_kernel<true><<<raster_grid(), RASTER_THREADS, 0, s>>>(a);
+  else raster_pairs_kernel<false><<<raster_grid(), RASTER_THREADS, 0, s>>>(a);
+  return 1;
+}
+
+int launch_render_split(const RenderArgs& a, cudaStream_t s, cudaEvent_t before_shade, int done) {
+  const int tiles_x = (a.W + TW - 1) / TW, tiles_y = (a.H + TH - 1) / TH;
+  dim3 grid(tiles_x * tiles_y, a.batch);
+  const bool extra = a.flow_bw || a.top_id0 || a.top_id1 || a.ids8;
+  int n = 0;
+  if (done < 1) n += launch_bin_pairs(a, s);
+  if (done < 2) n += launch_raster_pairs(a, s);
+  if (before_shade) cudaEventRecord(before_shade, s);
   if (a.n_fields > 0) {
-    raster_pairs_kernel<true><<<raster_blocks, RASTER_THREADS, 0, s>>>(a);
-    if (before_shade) cudaEventRecord(before_shade, s);
     if (extra) shade_kernel<true, true><<<grid, RENDER_THREADS, 0, s>>>(a);
     else shade_kernel<true, false><<<grid, RENDER_THREADS, 0, s>>>(a);
   } else {
-    raster_pairs_kernel<false><<<raster_blocks, RASTER_THREADS, 0, s>>>(a);
-    if (before_shade) cudaEventRecord(before_shade, s);
     if (extra) shade_kernel<false, true><<<grid, RENDER_THREADS, 0, s>>>(a);
     else shade_kernel<false, false><<<grid, RENDER_THREADS, 0, s>>>(a);
   }
-  if (!a.occlusion) return binned ? 2 : 3;
+  ++n;
+  if (!a.occlusion) return n;
   const size_t P = (size_t)a.W * a.H;
   occlusion_kernel<<<dim3((unsigned)((P + 255) / 256), a.batch), 256, 0, s>>>(a);
-  return binned ? 3 : 4;
+  return n + 1;
 }
 
 void launch_planar_to_rgbx(const uint8_t* planar, uchar4* out, int n, int w, int h, cudaStream_t s) {

@@ -75,11 +75,12 @@ int launch_background_prep(const RenderArgs& a, cudaStream_t s);
 int launch_render(const RenderArgs& a, cudaStream_t s);  // + the occlusion pass when a.occlusion is set
 // Split path: bin + raster + shade (+ the fused kernel, which only does work when the pair buffer overflowed).
 // Replaces launch_bin + launch_render; a.pair_* must be set.
-// before_shade, if given, is recorded between raster and shade. binned: the caller has already queued launch_bin_pairs for this
-// batch (on a forked stream, beside the background preparation: one block per sample, a 12 us latency-bound launch) and made
-// s wait for it.
+// before_shade, if given, is recorded just before the shade kernel. done: how much of the step the caller has already queued
+// for this batch on a forked stream and made s wait for -- 1: launch_bin_pairs (one block per sample, a 12 us latency-bound
+// launch, beside the background preparation), 2: launch_raster_pairs as well (the masks need the scene and the pair list only).
 int launch_bin_pairs(const RenderArgs& a, cudaStream_t s);
-int launch_render_split(const RenderArgs& a, cudaStream_t s, cudaEvent_t before_shade = nullptr, bool binned = false);
+int launch_raster_pairs(const RenderArgs& a, cudaStream_t s);
+int launch_render_split(const RenderArgs& a, cudaStream_t s, cudaEvent_t before_shade = nullptr, int done = 0);
 size_t pair_mask_bytes_per_pair();
 int launch_deform_prepass(const RenderArgs& a, cudaStream_t s);  // mode 9 only; no-op when n_deform == 0
 
