@@ -284,6 +284,7 @@ def run_ours(args):
     # SURVEY 8d's per-sample figure, and it is the longest kernel of the step: the roofline entry is about it. The whole
     # render step (render_ms) and the mask rasterisation on its own (raster_ms) are reported next to it.
     ab = algo_bytes(W, H) * B
+    overlapped = split and os.environ.get("OFDG_RASTER_OVERLAP") != "0" and os.environ.get("OFDG_BIN_OVERLAP") != "0"
     render_step_ms = render_ms / max(calls, 1)
     kern_ms = (shade_ms if split else render_ms) / max(calls, 1)
     achieved = ab / (kern_ms * 1e-3) / 1e9
@@ -304,6 +305,9 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": ab, "kernel_ms": kern_ms,
                      "render_ms": render_step_ms, "raster_ms": (render_step_ms - kern_ms) if split else None,
                      "bg_prep_ms": prep_ms / max(calls, 1),
+                     "spans": ("raster_pairs runs on a side stream beside bg_prep: bg_prep_ms is the span of both together, "
+                               "raster_ms the raster's tail after it, render_ms = that tail + shade_kernel (OFDG_RASTER_OVERLAP=0 "
+                               "serialises them: 0.164 + 0.145 ms, profiles/r01_bench_v12.json)") if overlapped else "serial",
                      "step_share": kern_ms * max(calls, 1) / max(render_ms + prep_ms, 1e-9),
                      "whole_step_achieved": ab / ((render_ms + prep_ms) / max(calls, 1) * 1e-3) / 1e9},
     }

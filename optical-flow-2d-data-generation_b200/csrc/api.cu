@@ -412,10 +412,10 @@ cudaEvent_t timing_event(ofdg_generator* g) {
   return g->ev_pool[g->ev_next++];
 }
 
-// Background preparation + render of one batch on stream s, every launch bracketed by events.
-// (Running the preparation of the next chunk on a second stream next to the render kernel was
-// measured and is slower: both kernels are issue-bound and the extra launches cost more than the
-// overlap gains -- profiles/README.md.)
+// Background preparation + render of one batch on stream s, bracketed by events. The pair binning and (side_raster) the mask
+// rasterisation are forked onto the high-priority side stream beside the preparation and joined before the shade kernel.
+// (Running the preparation of the NEXT chunk on a second stream next to the render kernels was measured and is slower: the
+// extra launches cost more than the overlap gains -- profiles/README.md.)
 void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s, bool deform_prepass = true, bool side_raster = true) {
   if (g->spans.size() > 60000) { g->spans.clear(); g->ev_next = 0; g->timed_calls = 0; }  // nobody is reading the timings
   if (deform_prepass) g->launches += ofdg::launch_deform_prepass(a, s);
@@ -608,10 +608,10 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
     CK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
     {
-      const char* pp = std::getenv("OFDG_PHILOX_PRIORITY");  // 1: the look-ahead parameter kernels are placed ahead of the render's
+      const char* pp = std::getenv("OFDG_PHILOX_PRIORITY");  // the look-ahead parameter kernels are placed ahead of the render's (0: not)
       int lo = 0, hi = 0;
       CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-      CK(cudaStreamCreateWithPriority(&g->ph_stream, cudaStreamNonBlocking, (pp && std::string(pp) == "1") ? hi : 0));
+      CK(cudaStreamCreateWithPriority(&g->ph_stream, cudaStreamNonBlocking, (pp && std::string(pp) == "0") ? 0 : hi));
     }
     for (int i = 0; i < 2; ++i) {
       CK(cudaEventCreateWithFlags(&g->ph[i].ready, cudaEventDisableTiming));
@@ -642,12 +642,13 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
       // and the pair list only, and the two kernels stall on different things (OFDG_RASTER_OVERLAP=0: in line; the per-kernel
       // spans of ofdg_kernel_times then do not overlap). The side stream has the higher priority: the persistent raster
       // blocks must be placed ahead of the preparation's ~20,000 short blocks, or they only start when those have drained.
-      // The device-side parameter stream keeps the raster in line (OFDG_PHILOX_RASTER_OVERLAP=1 forks it there as well): its
-      // look-ahead kernels already fill the preparation's idle issue slots and are starved by a third concurrent kernel.
+      // The device-side parameter stream forks it as well (OFDG_PHILOX_RASTER_OVERLAP=0: in line); its look-ahead kernels run on
+      // a high-priority stream of their own, or the third concurrent kernel starves them (measured: 109.7k in line, 103.2k
+      // forked with the look-ahead at normal priority, 114.3k forked with it at high priority).
       const char* ro = std::getenv("OFDG_RASTER_OVERLAP");
       g->raster_overlap = !(ro && std::string(ro) == "0");
       const char* po = std::getenv("OFDG_PHILOX_RASTER_OVERLAP");
-      g->philox_raster_overlap = po && std::string(po) == "1";
+      g->philox_raster_overlap = !(po && std::string(po) == "0");
       int lo = 0, hi = 0;
       CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
       CK(cudaStreamCreateWithPriority(&g->bin_stream, cudaStreamNonBlocking, hi));
