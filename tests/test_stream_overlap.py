@@ -1,0 +1,53 @@
+"""The pair binning and the mask rasterisation of a batch run on a high-priority side stream beside the background
+preparation (csrc/api.cu:run_kernels). Where a kernel runs must not change a single bit of the blobs: batches queued back to back
+on a caller's stream without any host synchronisation in between (the side stream of batch k+1 must wait for the shade kernel
+of batch k, which still reads the pair masks) are compared with the same batches rendered with everything in line on one stream
+(OFDG_BIN_OVERLAP=0)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N_BATCHES, BATCH = 6, 16
+
+
+def _blobs(n):
+    import torch
+    return (torch.empty((n, 3, 384, 512), device="cuda"), torch.empty((n, 3, 384, 512), device="cuda"),
+            torch.empty((n, 2, 384, 512), device="cuda"))
+
+
+def _run(ofdg, textures8, mode, philox):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    g = ofdg.Generator(device=0, mode=mode, max_batch=BATCH)
+    g.upload_textures(textures8)
+    ts = torch.cuda.Stream()
+    outs = [_blobs(BATCH) for _ in range(N_BATCHES)]
+    if philox:
+        for k, (i0, i1, fl) in enumerate(outs):
+            g.generate_philox(77, k * BATCH, BATCH, i0, i1, fl, stream=ts.cuda_stream)
+    else:
+        ps = ofdg.ParamStream(mode)
+        prepared = [g.prepare(ps.generate(BATCH)) for _ in range(N_BATCHES)]
+        for p, (i0, i1, fl) in zip(prepared, outs):
+            g.render_prepared(p, i0, i1, fl, ts.cuda_stream)
+    ts.synchronize()
+    torch.cuda.synchronize()
+    host = [[t.cpu().numpy() for t in o] for o in outs]
+    g.close()
+    return host
+
+
+@pytest.mark.parametrize("philox", [False, True])
+@pytest.mark.parametrize("mode", [7, 2])
+def test_side_stream_changes_no_bit(ofdg, textures8, mode, philox, monkeypatch):
+    monkeypatch.setenv("OFDG_BIN_OVERLAP", "0")
+    inline = _run(ofdg, textures8, mode, philox)
+    monkeypatch.delenv("OFDG_BIN_OVERLAP")
+    forked = _run(ofdg, textures8, mode, philox)
+    assert inline[0][0].std() > 10
+    assert not np.array_equal(inline[0][2], inline[1][2]), "the batches are supposed to differ"
+    for k, (a, b) in enumerate(zip(inline, forked)):
+        for name, x, y in zip(("img0", "img1", "flow"), a, b):
+            assert np.array_equal(x, y), f"batch {k}: {name} differs between the in-line and the forked step"
