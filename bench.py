@@ -9,8 +9,9 @@ A step = one batch of `--batch` (default 64) samples per GPU rendered by the hot
 `value` is whole-job samples/s over all ranks (weak scaling: per-GPU batch fixed, per-GPU seed
 offset 45*rank). `e2e` is the same metric through the C-ABI call with HOST blobs: host parameter
 draw + geometry flattening + scene upload + kernels + device-to-host copy of the three blobs, all
-inside the timed region. `--impl reference` times the CPU generator (the oracle port of the
-reference, all host threads) on bounded samples of the same workload.
+inside the timed region. `--impl reference` times the reference's own CPU generator (oracle/_ref: its
+untouched sources compiled here; the oracle port when that library is absent) on all host threads, on
+bounded samples of the same workload.
 
 Prints ONE JSON line (rank 0).
 """
@@ -88,7 +89,8 @@ class ClockSampler:
 
 
 def cpu_generator_rate(mode, W, H, n_samples, threads, tex, seed_offset=0, faithful=True):
-    """samples/s of the CPU generator (oracle port, reference structure: one worker thread per task)."""
+    """samples/s of the CPU restatement (oracle port, reference structure: one worker thread per task). Used only when the
+    reference build is not available (or for sizes other than the reference's compile-time 512 x 384)."""
     import ofdg_b200 as o
     from oracle import binding as ob
     tasks = o.ParamStream(mode, W, H, seed_offset).generate(n_samples)
@@ -98,45 +100,112 @@ def cpu_generator_rate(mode, W, H, n_samples, threads, tex, seed_offset=0, faith
     return n_samples / dt, dt
 
 
+def reference_available(W, H):
+    """The reference's own code (oracle/_ref, built from /root/reference by oracle/ref_build.sh) serves its compile-time size only."""
+    try:
+        from oracle import ref_binding as rb
+        return (W, H) == (rb.W, rb.H) and rb.available()
+    except Exception:
+        return False
+
+
+class ReferenceLayerRun:
+    """The reference's DataGenerationLayer on this box's host cores: texture list of PPM files -> TextureCollection ->
+    first_level_threads worker threads (DataGenerator::WorkerThreadLoop) -> load_batch -> Forward_cpu. One step = one Forward."""
+
+    def __init__(self, mode, batch, threads, seed):
+        import tempfile
+        import ofdg_b200 as o
+        from oracle import ref_binding as rb
+        self.rb = rb
+        self.dir = tempfile.mkdtemp(prefix="ofdg_ref_pool_")
+        tex = o.synth_textures(16, 1024, 768, seed=seed)  # a small pool: the pool size does not change the CPU cost per sample
+        lst = rb.write_ppm_pool(self.dir, tex)
+        self.batch, self.threads = batch, threads
+        # second_level_threads = 1 is the proto default (caffe.proto:10); prefetch 2 lets generation overlap the consumer
+        self.layer = rb.Layer(mode, lst, batch=batch, prefetch=2, first_level_threads=threads, second_level_threads=1)
+
+    def forward(self):
+        self.layer.forward(copy=False)
+
+    def close(self):
+        import shutil
+        self.layer.close()
+        shutil.rmtree(self.dir, ignore_errors=True)
+
+
+def reference_layer_rate(mode, cores, seconds, seed=0):
+    """Bounded sample: forwards of `cores` samples until `seconds` of wall clock have passed (after one warm-up forward)."""
+    run = ReferenceLayerRun(mode, batch=max(cores, 4), threads=cores, seed=seed)
+    run.forward()
+    n, t0 = 0, time.time()
+    while True:
+        run.forward()
+        n += run.batch
+        dt = time.time() - t0
+        if dt >= seconds:
+            break
+    run.close()
+    return n / dt, dt, n
+
+
 def run_reference(args):
-    """The reference arm: the CPU generator on this box's host cores, same workload/metric."""
+    """The reference arm: the reference's own CPU generator on this box's host cores, same workload/metric. Its own code
+    (oracle/_ref) when that library is present, else the oracle port of it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
-    import ofdg_b200 as o
-    from oracle import binding as ob
-    ob.build()
     cores = os.cpu_count() or 1
     W, H, mode = args.width, args.height, args.mode
-    tex = o.synth_textures(16, 2 * W, 2 * H, seed=args.seed)  # a small pool: pool size does not change CPU cost
-    # calibrate, then size the per-step sample so the whole run stays within ~3 minutes
-    rate, _ = cpu_generator_rate(mode, W, H, min(cores, 16), min(cores, 16), tex)
-    per_step = int(max(1, min(2 * cores, rate * 150.0 / (args.steps + args.warmup))))
-    threads = min(cores, per_step)
-    ps = o.ParamStream(mode, W, H, 0)
-    tasks = o.Tasks()
+    if reference_available(W, H):
+        from oracle import ref_binding as rb
+        # calibrate, then size the per-step batch so that the whole run stays within ~3 minutes
+        rate, _, _ = reference_layer_rate(mode, cores, 4.0, args.seed)
+        per_step = int(max(4, min(4 * cores, rate * 150.0 / (args.steps + args.warmup))))
+        run = ReferenceLayerRun(mode, per_step, cores, args.seed)
+        for _ in range(max(args.warmup, 1)):
+            run.forward()
+        t0 = time.time()
+        for _ in range(args.steps):
+            run.forward()
+        dt = time.time() - t0
+        run.close()
+        kind, threads = "reference", cores
+        sample = (f"{per_step} samples per step x {args.steps} steps through the reference's own DataGenerationLayer::Forward_cpu "
+                  f"(oracle/_ref: {rb.describe()}), mode {mode}, {W}x{H}, first_level_threads={cores}, second_level_threads=1, prefetch=2, "
+                  f"16-texture PPM pool, {cores} host cores")
+    else:
+        import ofdg_b200 as o
+        from oracle import binding as ob
+        ob.build()
+        tex = o.synth_textures(16, 2 * W, 2 * H, seed=args.seed)
+        rate, _ = cpu_generator_rate(mode, W, H, min(cores, 16), min(cores, 16), tex)
+        per_step = int(max(1, min(2 * cores, rate * 150.0 / (args.steps + args.warmup))))
+        threads = min(cores, per_step)
+        ps = o.ParamStream(mode, W, H, 0)
+        tasks = o.Tasks()
 
-    def step():
-        tasks.clear()
-        ps.generate(per_step, tasks)  # parameter draws are part of the reference's per-batch work too
-        ob.render(tasks.struct(), tex, W=W, H=H, mode=mode, n_threads=threads, faithful=True)
+        def step():
+            tasks.clear()
+            ps.generate(per_step, tasks)  # parameter draws are part of the reference's per-batch work too
+            ob.render(tasks.struct(), tex, W=W, H=H, mode=mode, n_threads=threads, faithful=True)
 
-    for _ in range(args.warmup):
-        step()
-    t0 = time.time()
-    for _ in range(args.steps):
-        step()
-    dt = time.time() - t0
+        for _ in range(args.warmup):
+            step()
+        t0 = time.time()
+        for _ in range(args.steps):
+            step()
+        dt = time.time() - t0
+        kind = "port"
+        sample = (f"{per_step} samples per step x {args.steps} steps, mode {mode}, {W}x{H}, oracle/liboracle.so with the reference's "
+                  f"whole-image copies, {threads} worker threads of {cores} host cores")
     v = per_step * args.steps / dt
     line = {
         "impl": "reference", "metric": "img-pair+flow samples/sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-                         "sample": f"{per_step} samples per step x {args.steps} steps, mode {mode}, {W}x{H}, oracle/liboracle.so "
-                                   f"with the reference's whole-image copies, {threads} worker threads of {cores} host cores"},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -313,15 +382,22 @@ def run_ours(args):
     }
     # CPU generator next to it (N=1 only): bounded sample on this box's host cores
     if world == 1 and not args.no_cpu:
-        from oracle import binding as ob
-        ob.build()
         cores = os.cpu_count() or 1
-        tex = o.synth_textures(16, 2 * W, 2 * H, seed=args.seed)
-        n = int(max(8, min(128, 6 * cores)))  # ~5 s of wall clock on every core of the bench box (16 cores: 96 samples)
-        rate, dt_cpu = cpu_generator_rate(mode, W, H, n, min(cores, n), tex)
-        line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": min(cores, n), "kind": "port",
-                                "sample": f"{n} samples of the same workload in {dt_cpu:.1f} s (oracle/liboracle.so, reference structure "
-                                          f"with its whole-image copies), {min(cores, n)} worker threads of {cores} host cores"}
+        if reference_available(W, H):
+            from oracle import ref_binding as rb
+            rate, dt_cpu, n = reference_layer_rate(mode, cores, 12.0, args.seed)
+            line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": cores, "kind": "reference",
+                                    "sample": f"{n} samples of the same workload in {dt_cpu:.1f} s through the reference's own DataGenerationLayer::Forward_cpu "
+                                              f"(oracle/_ref: {rb.describe()}), first_level_threads={cores}, second_level_threads=1, {cores} host cores"}
+        else:
+            from oracle import binding as ob
+            ob.build()
+            tex = o.synth_textures(16, 2 * W, 2 * H, seed=args.seed)
+            n = int(max(8, min(128, 6 * cores)))  # ~5 s of wall clock on every core of the bench box (16 cores: 96 samples)
+            rate, dt_cpu = cpu_generator_rate(mode, W, H, n, min(cores, n), tex)
+            line["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": min(cores, n), "kind": "port",
+                                    "sample": f"{n} samples of the same workload in {dt_cpu:.1f} s (oracle/liboracle.so, reference structure "
+                                              f"with its whole-image copies), {min(cores, n)} worker threads of {cores} host cores"}
     emit(line)
     if dist is not None:
         dist.barrier()

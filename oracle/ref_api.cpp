@@ -18,6 +18,7 @@
 #include <map>
 #include <memory>
 #include <new>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -176,6 +177,7 @@ CImg<float> field_image(const RefGenerator& g, int id, int which) {
 void queue_crops(RefGenerator& g, const ofdg_task_batch& t, int task, int policy, uint64_t* cursor) {
   WarpFields::CropGenerator* cg = g.gen->m_crop_generator_ptr;
   std::queue<std::pair<CImg<float>, CImg<float>>> empty;
+  const_cast<int&>(cg->m_reuse_same) = policy == 0 ? 0 : 2;  // (a const member; set at construction in the reference, DataGenerator.cpp:1018)
   if (policy == 0) {
     cg->m_finalized_crops_queue.swap(empty);
     cg->m_reuse_counter = 0;
@@ -367,7 +369,6 @@ int ref_render(void* h, const ofdg_task_batch* tasks, float* img0, float* img1, 
       for (int i = b0 + 1; i < b1; ++i)
         if (tasks->blueprints[i].parent < 0) task.object_blueprints.push_back(make_blueprint(*tasks, i));
 
-      uint64_t cursor_before = cursor;
       if (g->mode == 9) queue_crops(*g, *tasks, t, field_policy, &cursor);
       std::queue<std::pair<CImg<float>, CImg<float>>> saved_queue;
       int saved_counter = 0;
@@ -380,7 +381,6 @@ int ref_render(void* h, const ofdg_task_batch* tasks, float* img0, float* img1, 
       if (flow) std::memcpy(flow + (size_t)t * 2 * P, task.result_flow0_ptr->data(), 2 * P * sizeof(float));
 
       if (dbg) {
-        (void)cursor_before;
         if (g->mode == 9) { g->gen->m_crop_generator_ptr->m_finalized_crops_queue = saved_queue; g->gen->m_crop_generator_ptr->m_reuse_counter = saved_counter; }
         DG::RenderCore core;
         std::map<size_t, DG::MovingObjectBase*> objects_map;
@@ -440,6 +440,64 @@ int ref_render(void* h, const ofdg_task_batch* tasks, float* img0, float* img1, 
       delete task.result_flow0_ptr;
       delete task.background_blueprint;
       for (DG::ObjectBlueprint* b : task.object_blueprints) delete b;
+    }
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+
+// ---- the reference's warp-field producer with an explicit seed ---------------------------------------------------------
+// CropGenerator::worker_thread_loop (WarpFields.cpp:540-641) seeds its std::mt19937 from std::random_device and runs on ten
+// threads, so its output cannot be reproduced. This is the body of that loop, statement for statement, with the engine
+// seeded by the caller and the crops written to `out` (n x 2 x 2 x (H+1) x (W+1)) instead of the queue; the displacer scene,
+// DisplacementComposer, FlowField::init_from_DisplacementComposer and clamp_near_zeros are the reference's own code.
+int ref_generate_fields(uint32_t seed, int n_fields, float* out) {
+  try {
+    std::mt19937 mersenne(seed);
+    std::uniform_int_distribution<> displacer_type(0, 2);
+    std::uniform_real_distribution<> generic_param(-1, 1);
+    const int big_size{std::max(W, H) * 3};
+    const size_t plane = (size_t)(W + 1) * (H + 1);
+    int produced = 0;
+    while (produced < n_fields) {
+      WarpFields::DisplacementComposer dc(big_size, big_size);
+      const int spacing{200};
+      const int isosceles_spacing{(int)(spacing / 2. * std::sqrt(3.))};
+      const int rows{(dc.get_H() + isosceles_spacing - 1) / isosceles_spacing};
+      const int cols{(dc.get_W()) / spacing};
+      for (int yidx = 0; yidx < rows; ++yidx) {
+        for (int xidx = 0; xidx < cols; ++xidx) {
+          const int x = xidx * spacing + (yidx % 2 == 1 ? spacing / 2 : 0) + spacing / 2;
+          const int y = yidx * isosceles_spacing + spacing / 2;
+          // The reference draws these inside constructor argument lists (WarpFields.cpp:579-601), whose evaluation order C++
+          // leaves unspecified; the draws are i.i.d., so any order is "the reference". Fixed here to left-to-right so that the
+          // restatement (oracle/warpfields.cpp) can be compared value for value.
+          auto g = [&]() { return generic_param(mersenne); };
+          WarpFields::Displacers::DisplacerBase* displacer_ptr{nullptr};
+          switch (displacer_type(mersenne)) {
+            case 0: { const double a = g() * 3e-4, b = g() * 3e-4; displacer_ptr = new WarpFields::Displacers::Translation(a, b); break; }
+            case 1: { const double a = x + g() * 10, b = y + g() * 10, c = g() * M_PI * 2e-6; displacer_ptr = new WarpFields::Displacers::Rotation(a, b, c); break; }
+            case 2: { const double a = x + g() * 10, b = y + g() * 10, c = 1 + g() * 2e-6; displacer_ptr = new WarpFields::Displacers::Zoom(a, b, c); break; }
+          }
+          const double s0 = x + g() * 10, s1 = y + g() * 10, s2 = 50 + g() * 20, s3 = 50 + g() * 20, s4 = g() * M_PI;
+          WarpFields::Supports::SupportBase* support_ptr = new WarpFields::Supports::Gaussian2D(s0, s1, s2, s3, s4);
+          dc.add_displacer(displacer_ptr).with_support(support_ptr);
+        }
+      }
+      WarpFields::FlowField ff;
+      ff.init_from_DisplacementComposer(dc).clamp_near_zeros();
+      const CImg<float> flow = ff.get_flow();
+      const CImg<float> iflow = ff.get_iflow();
+      for (int y = H / 4; y < big_size - 5 * H / 4 && produced < n_fields; y += H / 3) {
+        for (int x = W / 4; x < big_size - 5 * W / 4 && produced < n_fields; x += W / 3) {
+          CImg<float> crop = flow.get_crop(x, y, x + W, y + H);
+          CImg<float> icrop = iflow.get_crop(x, y, x + W, y + H);
+          float* dst = out + (size_t)produced * 4 * plane;
+          std::memcpy(dst, crop.data(), 2 * plane * sizeof(float));
+          std::memcpy(dst + 2 * plane, icrop.data(), 2 * plane * sizeof(float));
+          ++produced;
+        }
+      }
     }
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return 1; }

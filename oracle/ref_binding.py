@@ -87,6 +87,7 @@ def lib():
         L.ref_generator_set_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ref_randomized_crop.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p]
         L.ref_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_generate_fields.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
         L.ref_layer_create.restype = C.c_void_p
         L.ref_layer_create.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.ref_layer_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -243,6 +244,15 @@ class Layer:
         if lib().ref_layer_forward(self._h, _p(out[0]), _p(out[1]), _p(out[2])):
             raise _err()
         return out
+
+
+def generate_fields(seed=1, n_fields=8):
+    """(n, 2, 2, H+1, W+1) float32 pool of (flow, iflow) crops from the reference's own DisplacementComposer / FlowField, with
+    the displacer scene drawn as CropGenerator::worker_thread_loop draws it but from std::mt19937(seed)."""
+    out = np.empty((n_fields, 2, 2, H + 1, W + 1), np.float32)
+    if lib().ref_generate_fields(seed, n_fields, _p(out)):
+        raise _err()
+    return out
 
 
 def write_ppm_pool(directory, textures_bgr):

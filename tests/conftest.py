@@ -36,5 +36,17 @@ def oracle():
 
 
 @pytest.fixture(scope="session")
+def refimpl():
+    """oracle/_ref/libofdg_ref.so: the reference's own sources compiled against oracle/shim (oracle/ref_build.sh). Built here
+    from /root/reference; on the GPU box the prebuilt library that travelled with the snapshot is used."""
+    from oracle import ref_binding
+    if not ref_binding.available():
+        pytest.skip("oracle/_ref is not built and /root/reference is not present to build it from")
+    ref_binding.build()
+    ref_binding.lib()
+    return ref_binding
+
+
+@pytest.fixture(scope="session")
 def textures8(ofdg):
     return ofdg.synth_textures(8, 1024, 768, seed=1)

@@ -1,8 +1,10 @@
-"""Generates tests/golden/render_golden.npz: outputs of the CPU oracle (oracle/, the restatement of the reference's
-render path) for fixed parameter streams and procedural textures. The reference ships no fixtures of its own
- and cannot be built here, so these vectors pin the *restatement*: any later change to the oracle, to the
-host parameter stream or to the texture synthesis that alters a pixel shows up as a diff against this file, and the
-sm_100a path is checked against the same vectors on the GPU box.
+"""Generates tests/golden/render_golden.npz for fixed parameter streams and procedural textures. The reference ships no
+fixtures of its own. The vectors are computed by the CPU oracle (oracle/, the restatement of the reference's
+render path); tests/test_reference_build.py::test_golden_vectors_are_reference_outputs shows that the reference's own code
+(oracle/_ref: its untouched sources compiled against stand-in AGG / CImg headers) renders the very same bytes, so the file
+pins reference outputs -- up to the third-party arithmetic both sides restate. Any later change to the oracle, to the host
+parameter stream or to the texture synthesis that alters a pixel shows up as a diff against this file, and the sm_100a path
+is checked against the same vectors on the GPU box. `--ref` computes them with the reference build instead.
 
     python tests/golden/make_golden.py        # rewrites render_golden.npz
 
@@ -22,12 +24,15 @@ CASES = [(1, 2), (2, 2), (5, 2), (7, 2), (12, 2)]  # (mode, samples)
 PROBES = np.random.default_rng(7).integers(0, 384 * 512, 64)
 
 
-def compute(mode, n):
+def compute(mode, n, use_ref=False):
     import ofdg_b200 as ofdg
-    from oracle import binding as oracle
-    oracle.build()
     tex = ofdg.synth_textures(8, 1024, 768, seed=1)
     tasks = ofdg.ParamStream(mode).generate(n)
+    if use_ref:
+        from oracle import ref_binding
+        return summarise(ref_binding.Generator(mode, textures=tex).render(tasks.struct(), debug=True))
+    from oracle import binding as oracle
+    oracle.build()
     out = oracle.render(tasks.struct(), tex, mode=mode, debug=True)
     return summarise(out)
 
@@ -47,7 +52,7 @@ def summarise(out):
 if __name__ == "__main__":
     blob = {}
     for mode, n in CASES:
-        s = compute(mode, n)
+        s = compute(mode, n, use_ref="--ref" in sys.argv)
         for k, v in s.items():
             blob[f"m{mode}_{k}"] = np.array(v) if isinstance(v, str) else v
         print("mode", mode, s["frames_sha"][:16], s["id0_sha"][:16])
