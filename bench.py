@@ -219,6 +219,76 @@ def workload_config(args):
             "parallelism": f"sample-sharded x{args.gpus}, seed offset 45*rank, no collective"}
 
 
+def traffic_table():
+    """DRAM bytes per launch of each kernel from the committed ncu --set full capture (batch 64, 512x384, mode 7)."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name))), name
+        except Exception:
+            pass
+    return {}, None
+
+
+def attribution_pass(o, args, device, task_sets, img0, img1, flow, stream, steps):
+    """Per-kernel times of the step: a second generator created with the overlaps switched off (the switches are read at
+    ofdg_create), so that bg_prep, bin_pairs, raster_pairs and shade run one after the other on one stream and the CUDA-event
+    spans around each launch do not overlap. Returns {kernel: {ms, bytes (the kernel's own mandatory traffic), achieved GB/s,
+    frac of the measured HBM peak, traffic (dram bytes per launch from the committed ncu capture)}}."""
+    import torch
+    W, H, B = args.width, args.height, args.batch
+    keys = ("OFDG_PIPELINE", "OFDG_RASTER_OVERLAP", "OFDG_BIN_OVERLAP")
+    saved = {k: os.environ.get(k) for k in keys}
+    for k in keys:
+        os.environ[k] = "0"
+    try:
+        g2 = o.Generator(device=device, width=W, height=H, mode=args.mode, max_batch=B)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    g2.synth_textures(args.textures, 2 * W, 2 * H, seed=args.seed)
+    prepared = [g2.prepare(t) for t in task_sets]
+    for i in range(8):
+        g2.render_prepared(prepared[i % len(prepared)], img0, img1, flow, stream)
+    g2.kernel_times()
+    pairs = prep_px = src_px = 0
+    for i in range(steps):
+        g2.render_prepared(prepared[i % len(prepared)], img0, img1, flow, stream)
+        if i < len(prepared):  # sizes of each distinct scene batch (synchronises; the spans are per launch, so this does not disturb them)
+            a, b, c = g2.last_render_stats()
+            pairs += a; prep_px += b; src_px += c
+    prep_ms, render_ms, calls = g2.kernel_times()
+    shade_ms = g2.last_shade_ms()
+    bin_ms, raster_ms = g2.last_bin_raster_ms()
+    n = min(steps, len(prepared))
+    pairs, prep_px, src_px = pairs / n, prep_px / n, src_px / n
+    peak, _ = measured_peak()
+    traffic, traffic_src = traffic_table()
+    own = {
+        # prepared pixels written (RGBX) + the source texels under them read once (RGBX)
+        "bg_prep_kernel": (prep_ms, 4 * prep_px + 4 * src_px),
+        # reads the objects' boxes, writes the pair list and the tiles' ranges
+        "bin_pairs_kernel": (bin_ms, 16 * pairs + 8 * B * ((W + 127) // 128) * ((H + 7) // 8)),
+        # four 128x8 coverage masks per (object, tile) pair
+        "raster_pairs_kernel": (raster_ms, 4096 * pairs),
+        # SURVEY 8(d): blobs written + texels read
+        "shade_kernel": (shade_ms, algo_bytes(W, H) * B),
+    }
+    out = {}
+    for name, (tot_ms, nbytes) in own.items():
+        ms = tot_ms / max(calls, 1)
+        ach = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None
+        t = traffic.get(name, {}).get("traffic_bytes") if (B == 64 and W == 512 and H == 384 and args.mode == 7) else None
+        out[name] = {"ms": ms, "bytes": int(nbytes), "achieved": ach, "frac": (ach / peak) if ach else None, "traffic": t}
+    out["shade_kernel"]["note"] = "moves every algorithmic byte of the step (SURVEY 8d)"
+    out["bg_prep_kernel"]["note"] = "own bytes: prepared RGBX pixels written + source RGBX texels read once; instruction-bound (CImg float/double chain)"
+    out["raster_pairs_kernel"]["note"] = "own bytes: 4 KB of masks per (object, tile) pair, which stay in L2 for the shade kernel"
+    del g2
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -237,7 +307,8 @@ def run_ours(args):
     g.synth_textures(args.textures, 2 * W, 2 * H, seed=args.seed)
     ps = o.ParamStream(mode, W, H, seed_offset=45 * rank)
     n_sets = 4
-    prepared = [g.prepare(ps.generate(B)) for _ in range(n_sets)]
+    prepared_tasks = [ps.generate(B) for _ in range(n_sets)]
+    prepared = [g.prepare(t) for t in prepared_tasks]
     img0 = torch.empty((B, 3, H, W), device="cuda", dtype=torch.float32)
     img1 = torch.empty_like(img0)
     flow = torch.empty((B, 2, H, W), device="cuda", dtype=torch.float32)
@@ -285,6 +356,11 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- attribution pass (rank 0): the same scenes with every kernel in line on one stream, per-kernel CUDA-event spans
+    attribution = None
+    if rank == 0 and not args.no_attribution and os.environ.get("OFDG_RENDER") != "fused":
+        attribution = attribution_pass(o, args, local, prepared_tasks, img0, img1, flow, stream, min(args.steps, 200))
 
     # ---- production mode: parameters drawn + flattened on the device (Philox), nothing crosses PCIe
     production = None
@@ -338,28 +414,23 @@ def run_ours(args):
         return
 
     peak, peak_src = measured_peak()
-    traffic = args.traffic
     split = shade_ms > 0
     dominant = "shade_kernel" if split else "render_kernel"
-    if traffic is None:  # dram bytes per launch of the dominant kernel from the committed ncu --set full capture (batch 64 only)
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if B == 64 and W == 512 and H == 384:
-                traffic = tj[dominant]["traffic_bytes"]
-        except Exception:
-            traffic = None
-    # The render step is bin_pairs_kernel + raster_pairs_kernel (coverage masks of every (object, tile) pair) + shade_kernel.
-    # shade_kernel reads the prepared background and the textures and writes the three blobs, i.e. it moves every byte of
-    # SURVEY 8d's per-sample figure, and it is the longest kernel of the step: the roofline entry is about it. The whole
-    # render step (render_ms) and the mask rasterisation on its own (raster_ms) are reported next to it.
     ab = algo_bytes(W, H) * B
-    overlapped = split and os.environ.get("OFDG_RASTER_OVERLAP") != "0" and os.environ.get("OFDG_BIN_OVERLAP") != "0"
-    render_step_ms = render_ms / max(calls, 1)
-    kern_ms = (shade_ms if split else render_ms) / max(calls, 1)
+    step_ms = ms / args.steps
+    # The step is bg_prep_kernel + bin_pairs_kernel + raster_pairs_kernel (coverage masks of every (object, tile) pair) +
+    # shade_kernel. shade_kernel reads the prepared background and the textures and writes the three blobs, i.e. it moves every
+    # byte of SURVEY 8d's per-sample figure: the roofline entry is about it. In the timed region the kernels of consecutive
+    # batches overlap (front end of batch k+1 beside the shade kernel of batch k), so per-kernel durations come from the
+    # attribution pass above: the same scenes, same process, every kernel in line on one stream, CUDA events around each launch.
+    kern_ms = attribution["shade_kernel"]["ms"] if attribution else (shade_ms if split else render_ms) / max(calls, 1)
     achieved = ab / (kern_ms * 1e-3) / 1e9
+    traffic = args.traffic
+    if traffic is None and attribution and B == 64 and W == 512 and H == 384:
+        traffic = attribution["shade_kernel"].get("traffic")
     line = {
         "metric": "img-pair+flow samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args),
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": h2d // e2e_steps,
@@ -372,13 +443,13 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ab, "kernel_ms": kern_ms,
-                     "render_ms": render_step_ms, "raster_ms": (render_step_ms - kern_ms) if split else None,
-                     "bg_prep_ms": prep_ms / max(calls, 1),
-                     "spans": ("raster_pairs runs on a side stream beside bg_prep: bg_prep_ms is the span of both together, "
-                               "raster_ms the raster's tail after it, render_ms = that tail + shade_kernel (OFDG_RASTER_OVERLAP=0 "
-                               "serialises them: 0.164 + 0.145 ms, profiles/r01_bench_v12.json)") if overlapped else "serial",
-                     "step_share": kern_ms * max(calls, 1) / max(render_ms + prep_ms, 1e-9),
-                     "whole_step_achieved": ab / ((render_ms + prep_ms) / max(calls, 1) * 1e-3) / 1e9},
+                     "timed": ("attribution pass: OFDG_PIPELINE=0 OFDG_RASTER_OVERLAP=0 OFDG_BIN_OVERLAP=0, every kernel in line, CUDA events "
+                               "around each launch" if attribution else "CUDA events around the launches of the timed region"),
+                     "kernels": attribution,
+                     "serial_step_ms": sum(k["ms"] for k in attribution.values()) if attribution else None,
+                     "shade_ms_in_step": (shade_ms / max(calls, 1)) if split else None,
+                     "whole_step": {"ms": step_ms, "achieved": ab / (step_ms * 1e-3) / 1e9, "frac": ab / (step_ms * 1e-3) / 1e9 / peak,
+                                    "what": "algorithmic bytes of the batch / ms_per_step of the timed region (kernels of consecutive batches overlap)"}},
     }
     # CPU generator next to it (N=1 only): bounded sample on this box's host cores
     if world == 1 and not args.no_cpu:
@@ -428,6 +499,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-attribution", action="store_true", help="skip the per-kernel attribution pass")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture (profiles/)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -208,6 +208,14 @@ int ofdg_kernel_times(ofdg_generator* g, double* prep_ms, double* render_ms, int
 /* Of the render time the last ofdg_kernel_times call reported: the part spent in the shade kernel (the kernel that reads the
  * textures and writes the blobs; the rest is binning and mask rasterisation). 0 with OFDG_RENDER=fused. */
 double ofdg_last_shade_ms(const ofdg_generator* g);
+/* Same, for the pair binning and the mask rasterisation kernels; measured only when they run in line with the rest
+ * (OFDG_PIPELINE=0 OFDG_RASTER_OVERLAP=0 OFDG_BIN_OVERLAP=0: the attribution pass of bench.py), else 0. */
+/* Sizes of the batch rendered last, for per-kernel roofline accounting (synchronises): (object, tile) pairs whose masks the
+ * raster kernel wrote (4 KB each), prepared background pixels written and the source texels under them (0 when the scene was
+ * drawn on the device). */
+int ofdg_last_render_stats(ofdg_generator* g, uint64_t* pairs, uint64_t* prepared_px, uint64_t* source_px);
+double ofdg_last_bin_ms(const ofdg_generator* g);
+double ofdg_last_raster_ms(const ofdg_generator* g);
 /* Bytes of flattened scene data the last render/prepare call copied host-to-device. */
 uint64_t ofdg_last_upload_bytes(const ofdg_generator* g);
 /* Bytes the last ofdg_render_host / ofdg_generate_host call copied device-to-host. The frames cross

@@ -68,7 +68,7 @@ EXPORTS = [
     "ofdg_flatten_ellipse", "ofdg_flatten_polygon", "ofdg_debug_raster_host", "ofdg_debug_expand_host", "ofdg_create", "ofdg_destroy", "ofdg_upload_textures", "ofdg_add_textures", "ofdg_clear_textures", "ofdg_texture_size", "ofdg_download_foreground_view",
     "ofdg_synth_textures", "ofdg_download_texture", "ofdg_set_fields", "ofdg_generate_fields", "ofdg_render", "ofdg_render_host",
     "ofdg_render_debug", "ofdg_debug_background", "ofdg_debug_composite_luts", "ofdg_prepare", "ofdg_prepared_destroy",
-    "ofdg_render_prepared", "ofdg_render_prepared_host", "ofdg_generate", "ofdg_generate_host", "ofdg_generate_philox", "ofdg_philox_tasks", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_shade_ms", "ofdg_last_upload_bytes", "ofdg_last_download_bytes", "ofdg_set_extra_tops",
+    "ofdg_render_prepared", "ofdg_render_prepared_host", "ofdg_generate", "ofdg_generate_host", "ofdg_generate_philox", "ofdg_philox_tasks", "ofdg_launch_count", "ofdg_kernel_times", "ofdg_last_shade_ms", "ofdg_last_bin_ms", "ofdg_last_render_stats", "ofdg_last_raster_ms", "ofdg_last_upload_bytes", "ofdg_last_download_bytes", "ofdg_set_extra_tops",
 ]
 # include/ofdg/layer.h
 LAYER_EXPORTS = [
@@ -101,6 +101,10 @@ def lib():
         L.ofdg_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         L.ofdg_last_shade_ms.argtypes = [C.c_void_p]
         L.ofdg_last_shade_ms.restype = C.c_double
+        L.ofdg_last_render_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        for f in (L.ofdg_last_bin_ms, L.ofdg_last_raster_ms):
+            f.argtypes = [C.c_void_p]
+            f.restype = C.c_double
         L.ofdg_params_create.argtypes = [C.c_int32] * 6 + [C.POINTER(C.c_void_p)]
         L.ofdg_params_destroy.argtypes = [C.c_void_p]
         L.ofdg_params_generate.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
@@ -507,6 +511,16 @@ class Generator:
         p, r, n = C.c_double(), C.c_double(), C.c_int32()
         _check(lib().ofdg_kernel_times(self._h, C.byref(p), C.byref(r), C.byref(n)))
         return p.value, r.value, n.value
+
+    def last_render_stats(self):
+        """(pairs, prepared_px, source_px) of the batch rendered last (ofdg_last_render_stats)."""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(lib().ofdg_last_render_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def last_bin_raster_ms(self):
+        """Pair binning / mask rasterisation parts of the last kernel_times() call (in-line runs only, else 0)."""
+        return float(lib().ofdg_last_bin_ms(self._h)), float(lib().ofdg_last_raster_ms(self._h))
 
     def last_shade_ms(self):
         """Part of the render time of the last kernel_times() call spent in the shade kernel (0 with OFDG_RENDER=fused)."""

@@ -109,6 +109,7 @@ struct DeviceScene {
   int batch = 0, n_deform = 0;
   size_t pair_bound = 0;  // upper bound of the scene's (object, tile) pairs: sizes the split render path's mask buffer
   int prep_w = 0, prep_h = 0;  // largest part of a prepared background any sample needs (pixels; 0: unknown, the whole 2W x 2H)
+  uint64_t prep_px = 0, prep_src_px = 0;  // prepared pixels written / source texels under them, summed over the samples (0: unknown)
   void release() { samples.release(); objects.release(); shapes.release(); verts.release(); deform_shape.release(); deform_field.release(); }
 };
 
@@ -130,7 +131,7 @@ struct ofdg_generator {
   ofdg_config cfg{};
   cudaStream_t stream = nullptr;
   // CUDA-event spans around every background-preparation / render launch (roofline timing)
-  struct Span { cudaEvent_t a, b; int kind; };  // kind 0 = background preparation, 1 = render (all of it), 2 = the shade kernel alone
+  struct Span { cudaEvent_t a, b; int kind; };  // kind 0 = background preparation, 1 = render (all of it), 2 = the shade kernel alone, 3 / 4 = pair binning / mask rasterisation (in-line runs only)
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_next = 0;
   std::vector<Span> spans;
@@ -167,7 +168,7 @@ struct ofdg_generator {
   PinnedBuf staging;
   DevBuf bg, tile_hits;
   // split render path: per-tile pair ranges, the pair list, the pairs' masks, control words (csrc/render.cuh)
-  DevBuf tile_range, pair_list, pair_masks, pair_ctl;
+  DevBuf tile_range, pair_list, pair_masks, pair_ctl, bg_rows, pair_rows;
   PinnedBuf pair_overflow;  // one int the binning kernel raises if a batch ever had more pairs than the host-computed bound
   int pair_cap = 0;
   bool split_render = true;  // OFDG_RENDER=fused selects the single-kernel path
@@ -201,6 +202,15 @@ struct ofdg_generator {
   ofdg::FlatBatch pipe_flat[2];
   cudaStream_t copy_stream = nullptr;
   cudaStream_t bin_stream = nullptr;  // pair binning of a batch beside its background preparation (OFDG_BIN_OVERLAP=0: same stream)
+  // Cross-batch software pipeline (OFDG_PIPELINE=0: off): a second scratch set and a preparation stream, so that the background
+  // preparation and the mask rasterisation of batch k+1 run beside the shade kernel of batch k. Set 0 is the members above
+  // (bg, tile_range, pair_list, pair_masks, pair_ctl), set 1 is `alt`. Every render call records set_shade_done for the set it used.
+  struct { DevBuf bg, tile_range, pair_list, pair_masks, pair_ctl, bg_rows, pair_rows; } alt;
+  cudaStream_t prep_stream = nullptr;
+  cudaEvent_t set_prep_done[2] = {nullptr, nullptr}, set_raster_done[2] = {nullptr, nullptr}, set_shade_done[2] = {nullptr, nullptr};
+  bool set_used[2] = {false, false};
+  bool pipeline = false;
+  uint64_t pipe_calls = 0;
   cudaEvent_t bin_fork = nullptr, bin_join = nullptr;
   bool raster_overlap = false, philox_raster_overlap = false;
   cudaEvent_t pipe_uploaded[2] = {nullptr, nullptr}, pipe_rendered[2] = {nullptr, nullptr}, render_done[2] = {nullptr, nullptr};
@@ -208,7 +218,9 @@ struct ofdg_generator {
   uint64_t render_calls = 0;
   uint64_t launches = 0;
   float last_kernel_ms = 0.f;
-  double last_shade_ms = 0.0;  // of the spans ofdg_kernel_times summed last
+  double last_shade_ms = 0.0, last_bin_ms = 0.0, last_raster_ms = 0.0;  // of the spans ofdg_kernel_times summed last
+  uint64_t last_prep_px = 0, last_prep_src_px = 0;  // of the scene rendered last (ofdg_last_render_stats)
+  int last_set = 0;
 
   void use() const { CK(cudaSetDevice(cfg.device)); }
 };
@@ -280,10 +292,16 @@ void upload_scene_parts(ofdg_generator* g, const ofdg::FlatBatch* parts, int n_p
     ds.pair_bound = pairs;
   }
   ds.prep_w = ds.prep_h = 0;  // the preparation kernel's grid covers the largest needed region, not the whole 2W x 2H canvas
+  ds.prep_px = ds.prep_src_px = 0;
   for (int i = 0; i < n_parts; ++i)
     for (const ofdg::FlatSample& fs : parts[i].samples) {
-      ds.prep_w = std::max(ds.prep_w, fs.prep.need[2] - fs.prep.need[0] + 1);
-      ds.prep_h = std::max(ds.prep_h, fs.prep.need[3] - fs.prep.need[1] + 1);
+      const int nw = fs.prep.need[2] - fs.prep.need[0] + 1, nh = fs.prep.need[3] - fs.prep.need[1] + 1;
+      ds.prep_w = std::max(ds.prep_w, nw);
+      ds.prep_h = std::max(ds.prep_h, nh);
+      if (nw > 0 && nh > 0) {
+        ds.prep_px += (uint64_t)nw * nh;
+        ds.prep_src_px += (uint64_t)((double)nw * nh * ((double)fs.prep.crop_w / (2.0 * g->cfg.width)) * ((double)fs.prep.crop_h / (2.0 * g->cfg.height)));
+      }
     }
   ofdg::UploadSegments u{};
   const char* dv = (const char*)staging.dev;
@@ -328,6 +346,13 @@ void ensure_scratch(ofdg_generator* g, int batch) {
     const size_t tiles = ofdg::tile_hits_bytes(1, (int)W, (int)H) / ofdg::TILE_HIT_STRIDE;
     g->tile_range.reserve((size_t)batch * tiles * sizeof(int2));
     g->pair_ctl.reserve(4 * sizeof(int));
+    g->bg_rows.reserve((size_t)batch * H * 2 * sizeof(int4));
+    if (g->pipeline) {
+      g->alt.bg_rows.reserve((size_t)batch * H * 2 * sizeof(int4));
+      g->alt.bg.reserve((size_t)batch * 4 * W * H * sizeof(uchar4));
+      g->alt.tile_range.reserve((size_t)batch * tiles * sizeof(int2));
+      g->alt.pair_ctl.reserve(4 * sizeof(int));
+    }
     if (!g->pair_overflow.p) {
       g->pair_overflow.reserve(sizeof(int));
       *(volatile int*)g->pair_overflow.p = 0;
@@ -336,8 +361,9 @@ void ensure_scratch(ofdg_generator* g, int batch) {
   g->scratch_batch = batch;
 }
 
-ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, float* d1, float* df) {
+ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, float* d1, float* df, int set = 0) {
   ofdg::RenderArgs a{};
+  g->last_prep_px = ds.prep_px; g->last_prep_src_px = ds.prep_src_px; g->last_set = set;
   a.samples = (const ofdg::FlatSample*)ds.samples.p;
   a.objects = (const ofdg::FlatObject*)ds.objects.p;
   a.shapes = (const ofdg::FlatShape*)ds.shapes.p;
@@ -348,7 +374,7 @@ ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, 
   a.use_aa = g->cfg.use_antialiasing;
   a.pool = (const uchar4*)g->pool.p;
   a.tex_info = (const ofdg::TexInfo*)g->tex_info_dev.p;
-  a.bg = (uchar4*)g->bg.p;
+  a.bg = (uchar4*)(set ? g->alt.bg.p : g->bg.p);
   a.tile_hits = (uint8_t*)g->tile_hits.p;
   if (g->split_render) {
     if (ds.pair_bound > (size_t)g->pair_cap) {  // grow the pair buffers (4 KB of masks per pair); earlier launches may still use the old ones
@@ -356,10 +382,22 @@ ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, 
       const size_t cap = std::max<size_t>(ds.pair_bound + ds.pair_bound / 4, 4096);
       g->pair_list.reserve(cap * sizeof(int4));
       g->pair_masks.reserve(cap * ofdg::pair_mask_bytes_per_pair());
+      g->pair_rows.reserve(cap * ofdg::pair_row_bytes_per_pair());
+      if (g->pipeline) {
+        g->alt.pair_rows.reserve(cap * ofdg::pair_row_bytes_per_pair());
+        g->alt.pair_list.reserve(cap * sizeof(int4));
+        g->alt.pair_masks.reserve(cap * ofdg::pair_mask_bytes_per_pair());
+      }
       g->pair_cap = (int)cap;
     }
-    a.tile_range = (int2*)g->tile_range.p; a.pair_list = (int4*)g->pair_list.p; a.pair_masks = (uint32_t*)g->pair_masks.p;
-    a.pair_ctl = (int*)g->pair_ctl.p; a.pair_cap = g->pair_cap_limit > 0 ? std::min(g->pair_cap, g->pair_cap_limit) : g->pair_cap;
+    if (set) {
+      a.tile_range = (int2*)g->alt.tile_range.p; a.pair_list = (int4*)g->alt.pair_list.p; a.pair_masks = (uint32_t*)g->alt.pair_masks.p;
+      a.pair_ctl = (int*)g->alt.pair_ctl.p; a.bg_rows = (int4*)g->alt.bg_rows.p; a.pair_rows = (int4*)g->alt.pair_rows.p;
+    } else {
+      a.tile_range = (int2*)g->tile_range.p; a.pair_list = (int4*)g->pair_list.p; a.pair_masks = (uint32_t*)g->pair_masks.p;
+      a.pair_ctl = (int*)g->pair_ctl.p; a.bg_rows = (int4*)g->bg_rows.p; a.pair_rows = (int4*)g->pair_rows.p;
+    }
+    a.pair_cap = g->pair_cap_limit > 0 ? std::min(g->pair_cap, g->pair_cap_limit) : g->pair_cap;
     a.pair_overflow = (int*)g->pair_overflow.dev;
   }
   a.pos_x = (const int*)g->rtab_pos_x.p; a.alpha_x = (const double*)g->rtab_alpha_x.p;
@@ -416,8 +454,51 @@ cudaEvent_t timing_event(ofdg_generator* g) {
 // rasterisation are forked onto the high-priority side stream beside the preparation and joined before the shade kernel.
 // (Running the preparation of the NEXT chunk on a second stream next to the render kernels was measured and is slower: the
 // extra launches cost more than the overlap gains -- profiles/README.md.)
+// Pipelined form (pipe_set >= 0; the caller built `a` with make_args(.., pipe_set)): the scene is already resident (scene_ready, if
+// given, says when), so nothing of this batch's front end depends on what is queued on s. The pair binning + mask rasterisation
+// go to the high-priority side stream and the background preparation to the preparation stream, both gated only by the shade
+// kernel that last read this scratch set (two calls ago); s waits for both and runs the shade kernel. Queued back to back, the
+// front end of batch k+1 therefore runs beside the shade kernel of batch k.
+void run_kernels_pipelined(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s, int set, cudaEvent_t scene_ready) {
+  if (g->spans.size() > 60000) { g->spans.clear(); g->ev_next = 0; g->timed_calls = 0; }
+  cudaStream_t front[2] = {g->bin_stream, g->prep_stream};
+  for (cudaStream_t f : front) {
+    if (scene_ready) CK(cudaStreamWaitEvent(f, scene_ready, 0));
+    if (g->set_used[set]) CK(cudaStreamWaitEvent(f, g->set_shade_done[set], 0));
+  }
+  g->launches += ofdg::launch_bin_pairs(a, g->bin_stream);
+  g->launches += ofdg::launch_raster_pairs(a, g->bin_stream);
+  CK(cudaEventRecord(g->set_raster_done[set], g->bin_stream));
+  ofdg_generator::Span sp{timing_event(g), timing_event(g), 0};
+  CK(cudaEventRecord(sp.a, g->prep_stream));
+  g->launches += ofdg::launch_background_prep(a, g->prep_stream);
+  CK(cudaEventRecord(sp.b, g->prep_stream));
+  CK(cudaEventRecord(g->set_prep_done[set], g->prep_stream));
+  g->spans.push_back(sp);
+  CK(cudaStreamWaitEvent(s, g->set_raster_done[set], 0));
+  CK(cudaStreamWaitEvent(s, g->set_prep_done[set], 0));
+  ofdg_generator::Span sr{timing_event(g), timing_event(g), 1};
+  CK(cudaEventRecord(sr.a, s));  // completes once both waits are satisfied: the span is the shade kernel (+ the occlusion pass)
+  g->launches += ofdg::launch_render_split(a, s, nullptr, 2);
+  CK(cudaEventRecord(sr.b, s));
+  g->spans.push_back(ofdg_generator::Span{sr.a, sr.b, 2});
+  g->spans.push_back(sr);
+  CK(cudaEventRecord(g->set_shade_done[set], s));
+  g->set_used[set] = true;
+  ++g->timed_calls;
+  CK(cudaGetLastError());
+}
+
+// Whether a render call can take the pipelined form, and with which scratch set (-1: no). Warped outlines (mode 9) keep the
+// in-order form: their pre-pass scratch is single-buffered.
+int pipeline_set(ofdg_generator* g, const DeviceScene& ds) {
+  if (!g->pipeline || ds.n_deform) return -1;
+  return (int)(g->pipe_calls++ & 1);
+}
+
 void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s, bool deform_prepass = true, bool side_raster = true) {
   if (g->spans.size() > 60000) { g->spans.clear(); g->ev_next = 0; g->timed_calls = 0; }  // nobody is reading the timings
+  if (g->pipeline && g->set_used[0]) CK(cudaStreamWaitEvent(s, g->set_shade_done[0], 0));  // in-order calls use scratch set 0
   if (deform_prepass) g->launches += ofdg::launch_deform_prepass(a, s);
   ofdg_generator::Span sp{timing_event(g), timing_event(g), 0};
   CK(cudaEventRecord(sp.a, s));
@@ -440,7 +521,17 @@ void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s, b
     if (a.pair_ctl) {
       cudaEvent_t mid = timing_event(g);
       if (fork_bin) CK(cudaStreamWaitEvent(s, g->bin_join, 0));
-      g->launches += ofdg::launch_render_split(a, s, mid, fork_raster ? 2 : fork_bin ? 1 : 0);
+      int done = fork_raster ? 2 : fork_bin ? 1 : 0;
+      if (done == 0) {  // everything in line (OFDG_BIN_OVERLAP=0): the binning and the rasterisation get spans of their own
+        cudaEvent_t e1 = timing_event(g);
+        g->launches += ofdg::launch_bin_pairs(a, s);
+        CK(cudaEventRecord(e1, s));
+        g->launches += ofdg::launch_raster_pairs(a, s);
+        g->spans.push_back(ofdg_generator::Span{sr.a, e1, 3});
+        g->spans.push_back(ofdg_generator::Span{e1, mid, 4});
+        done = 2;
+      }
+      g->launches += ofdg::launch_render_split(a, s, mid, done);
       CK(cudaEventRecord(sr.b, s));
       g->spans.push_back(ofdg_generator::Span{mid, sr.b, 2});
     } else {
@@ -448,6 +539,10 @@ void run_kernels(ofdg_generator* g, const ofdg::RenderArgs& a, cudaStream_t s, b
       CK(cudaEventRecord(sr.b, s));
     }
     g->spans.push_back(sr);
+  }
+  if (g->pipeline) {  // a later pipelined call that picks set 0 must not start its front end before this call is done with it
+    CK(cudaEventRecord(g->set_shade_done[0], s));
+    g->set_used[0] = true;
   }
   ++g->timed_calls;
   CK(cudaGetLastError());
@@ -654,6 +749,19 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
       CK(cudaStreamCreateWithPriority(&g->bin_stream, cudaStreamNonBlocking, hi));
       CK(cudaEventCreateWithFlags(&g->bin_fork, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&g->bin_join, cudaEventDisableTiming));
+      // cross-batch pipeline (see run_kernels_pipelined): needs the forked raster; OFDG_PIPELINE=0 keeps every batch in line,
+      // which is also how per-kernel times are measured (the spans of ofdg_kernel_times then do not overlap)
+      const char* pl = std::getenv("OFDG_PIPELINE");
+      g->pipeline = g->raster_overlap && !(pl && std::string(pl) == "0");
+      if (g->pipeline) {
+        const char* pr = std::getenv("OFDG_PREP_PRIORITY");  // "hi": the preparation stream shares the raster's priority
+        CK(cudaStreamCreateWithPriority(&g->prep_stream, cudaStreamNonBlocking, (pr && std::string(pr) == "hi") ? hi : 0));
+        for (int i = 0; i < 2; ++i) {
+          CK(cudaEventCreateWithFlags(&g->set_prep_done[i], cudaEventDisableTiming));
+          CK(cudaEventCreateWithFlags(&g->set_raster_done[i], cudaEventDisableTiming));
+          CK(cudaEventCreateWithFlags(&g->set_shade_done[i], cudaEventDisableTiming));
+        }
+      }
     }
     *out = g.release();
   });
@@ -673,7 +781,7 @@ void ofdg_destroy(ofdg_generator* g) {
     if (q.ready) cudaEventDestroy(q.ready);
     if (q.consumed) cudaEventDestroy(q.consumed);
   }
-  DevBuf* bufs[] = {&g->ph_slots, &g->pool, &g->tex_info_dev, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->field_reach_dev, &g->bg, &g->tile_hits, &g->tile_range, &g->pair_list, &g->pair_masks, &g->pair_ctl, &g->rtab_pos_x, &g->rtab_alpha_x, &g->rtab_pos_y, &g->rtab_alpha_y, &g->out0, &g->out1,
+  DevBuf* bufs[] = {&g->ph_slots, &g->pool, &g->tex_info_dev, &g->fields, &g->fpos_x, &g->falpha_x, &g->fpos_y, &g->falpha_y, &g->mask_raw, &g->mask_warp, &g->field_reach_dev, &g->bg, &g->tile_hits, &g->tile_range, &g->pair_list, &g->pair_masks, &g->pair_ctl, &g->bg_rows, &g->pair_rows, &g->rtab_pos_x, &g->rtab_alpha_x, &g->rtab_pos_y, &g->rtab_alpha_y, &g->out0, &g->out1,
                     &g->outf, &g->ids8, &g->dbg_masks, &g->dbg_id0, &g->dbg_id1, &g->dbg_frames8, &g->dbg_planar};
   for (DevBuf* b : bufs) b->release();
   g->scene.release();
@@ -692,6 +800,16 @@ void ofdg_destroy(ofdg_generator* g) {
   g->host8.release();
   if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
   if (g->bin_stream) { cudaStreamSynchronize(g->bin_stream); cudaStreamDestroy(g->bin_stream); }
+  if (g->prep_stream) { cudaStreamSynchronize(g->prep_stream); cudaStreamDestroy(g->prep_stream); }
+  for (int i = 0; i < 2; ++i) {
+    if (g->set_prep_done[i]) cudaEventDestroy(g->set_prep_done[i]);
+    if (g->set_raster_done[i]) cudaEventDestroy(g->set_raster_done[i]);
+    if (g->set_shade_done[i]) cudaEventDestroy(g->set_shade_done[i]);
+  }
+  {
+    DevBuf* ab[] = {&g->alt.bg, &g->alt.tile_range, &g->alt.pair_list, &g->alt.pair_masks, &g->alt.pair_ctl, &g->alt.bg_rows, &g->alt.pair_rows};
+    for (DevBuf* b : ab) b->release();
+  }
   if (g->bin_fork) cudaEventDestroy(g->bin_fork);
   if (g->bin_join) cudaEventDestroy(g->bin_join);
   for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
@@ -1320,11 +1438,13 @@ int ofdg_generate_philox(ofdg_generator* g, uint64_t seed, uint64_t first_sample
     philox_check(g, batch);
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
     int set;
+    bool looked_ahead = false;
     if (g->ph_next.valid && g->ph_next.seed == seed && g->ph_next.first == first_sample && g->ph_next.batch == batch &&
         g->ph_next.augment == augment) {
       set = g->ph_next.set;  // drawn and flattened on the side stream while the previous batch rendered
       CK(cudaStreamWaitEvent(s, g->ph[set].ready, 0));
       philox_collect(g, set, g->ph_stream);
+      looked_ahead = true;
     } else {
       set = g->ph_next.valid ? (g->ph_next.set ^ 1) : 0;
       if (g->ph_next.valid) CK(cudaStreamSynchronize(g->ph_stream));  // a speculative batch nobody asked for is still being written
@@ -1333,7 +1453,11 @@ int ofdg_generate_philox(ofdg_generator* g, uint64_t seed, uint64_t first_sample
       philox_collect(g, set, s);
     }
     ensure_scratch(g, batch);
-    run_kernels(g, with_extra_tops(g, make_args(g, g->ph[set].scene, d_img0, d_img1, d_flow)), s, true, g->philox_raster_overlap);
+    const int pset = (looked_ahead && g->philox_raster_overlap) ? pipeline_set(g, g->ph[set].scene) : -1;
+    if (pset >= 0)  // the scene was written on the look-ahead stream: the front end only waits for that, not for the previous batch on s
+      run_kernels_pipelined(g, with_extra_tops(g, make_args(g, g->ph[set].scene, d_img0, d_img1, d_flow, pset)), s, pset, g->ph[set].ready);
+    else
+      run_kernels(g, with_extra_tops(g, make_args(g, g->ph[set].scene, d_img0, d_img1, d_flow)), s, true, g->philox_raster_overlap);
     CK(cudaEventRecord(g->ph[set].consumed, s));
     g->ph[set].used = true;
     // look ahead: the next batch of the same stream, on the side stream, into the other set
@@ -1421,7 +1545,9 @@ int ofdg_render_prepared(ofdg_generator* g, const ofdg_prepared* p, float* d_img
     g->use();
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
     ensure_scratch(g, p->scene.batch);
-    run_kernels(g, with_extra_tops(g, make_args(g, p->scene, d_img0, d_img1, d_flow)), s);
+    const int set = pipeline_set(g, p->scene);  // the scene has been resident since ofdg_prepare returned
+    if (set >= 0) run_kernels_pipelined(g, with_extra_tops(g, make_args(g, p->scene, d_img0, d_img1, d_flow, set)), s, set, nullptr);
+    else run_kernels(g, with_extra_tops(g, make_args(g, p->scene, d_img0, d_img1, d_flow)), s);
     if (!stream) { CK(cudaStreamSynchronize(s)); check_pair_overflow(g); }
   });
 }
@@ -1453,12 +1579,13 @@ int ofdg_kernel_times(ofdg_generator* g, double* prep_ms, double* render_ms, int
     g->use();
     CK(cudaDeviceSynchronize());
     check_pair_overflow(g);
-    double t[3] = {0, 0, 0};
+    double t[5] = {0, 0, 0, 0, 0};
     for (const ofdg_generator::Span& sp : g->spans) {
       float ms = 0.f;
       CK(cudaEventElapsedTime(&ms, sp.a, sp.b));
       t[sp.kind] += ms;
     }
+    g->last_bin_ms = t[3]; g->last_raster_ms = t[4];
     if (prep_ms) *prep_ms = t[0];
     if (render_ms) *render_ms = t[1];
     if (calls) *calls = (int32_t)g->timed_calls;
@@ -1469,6 +1596,21 @@ int ofdg_kernel_times(ofdg_generator* g, double* prep_ms, double* render_ms, int
   });
 }
 double ofdg_last_shade_ms(const ofdg_generator* g) { return g ? g->last_shade_ms : 0.0; }
+int ofdg_last_render_stats(ofdg_generator* g, uint64_t* pairs, uint64_t* prepared_px, uint64_t* source_px) {
+  return guarded([&] {
+    if (!g) throw ArgError("null pointer");
+    g->use();
+    CK(cudaDeviceSynchronize());
+    int n = 0;
+    const void* ctl = g->last_set ? g->alt.pair_ctl.p : g->pair_ctl.p;
+    if (ctl) CK(cudaMemcpy(&n, ctl, sizeof(int), cudaMemcpyDeviceToHost));
+    if (pairs) *pairs = (uint64_t)n;
+    if (prepared_px) *prepared_px = g->last_prep_px;
+    if (source_px) *source_px = g->last_prep_src_px;
+  });
+}
+double ofdg_last_bin_ms(const ofdg_generator* g) { return g ? g->last_bin_ms : 0.0; }
+double ofdg_last_raster_ms(const ofdg_generator* g) { return g ? g->last_raster_ms : 0.0; }
 uint64_t ofdg_last_upload_bytes(const ofdg_generator* g) { return g ? g->last_upload_bytes : 0; }
 uint64_t ofdg_last_download_bytes(const ofdg_generator* g) { return g ? g->last_download_bytes : 0; }
 

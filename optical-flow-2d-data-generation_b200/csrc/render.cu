@@ -141,6 +141,45 @@ __device__ __noinline__ uint32_t bilinear_rgbx_call(const uchar4* base, int pitc
   return bilinear_rgbx(base, pitch, 0, 0, sw, sh, rw, i);
 }
 
+// The same filter for a lane's four consecutive span pixels when (a) the span length is a power of two, so the closed-form
+// dda2 value (Dda2::at) advances by an add and a shift per pixel, and (b) every tap of every lane of the warp lies inside
+// the image, so wrap_mode_reflect is the identity (checked by the caller: span positions are monotone along the row, the
+// lane's first and last pixel bound the rest). The rows' interpolator constants come from a table (RenderArgs::bg_rows /
+// pair_rows) instead of being worked out by every warp.
+struct SpanLane {
+  int xb, yb, tx, ty, lx, ly, rx, ry, sh;  // x_hr(k) = xb + k * lx + ((tx + k * rx) >> sh), k = 0..3 (the -128 of the filter offset is in xb)
+  __device__ __forceinline__ void init(const int4 r0, const int4 r1, int i0, int n, int shift) {
+    lx = r0.y; rx = r0.z; ly = r1.x; ry = r1.y; sh = shift;
+    tx = (i0 + 1) * rx + n - 1; ty = (i0 + 1) * ry + n - 1;
+    xb = r0.x + i0 * lx - 129; yb = r0.w + i0 * ly - 129;
+  }
+  __device__ __forceinline__ int x_hr(int k) const { return xb + k * lx + ((tx + k * rx) >> sh); }
+  __device__ __forceinline__ int y_hr(int k) const { return yb + k * ly + ((ty + k * ry) >> sh); }
+  // every tap of pixels 0..3 inside [0, sw - 1] x [0, sh_img - 1]?
+  __device__ __forceinline__ bool inside(int sw, int sh_img) const {
+    const int xa = x_hr(0) >> 8, xz = x_hr(3) >> 8, ya = y_hr(0) >> 8, yz = y_hr(3) >> 8;
+    return (unsigned)xa < (unsigned)(sw - 1) && (unsigned)xz < (unsigned)(sw - 1) && (unsigned)ya < (unsigned)(sh_img - 1) && (unsigned)yz < (unsigned)(sh_img - 1);
+  }
+};
+__device__ __forceinline__ uint32_t bilinear_inside(const uint32_t* img, int pitch, int x_hr, int y_hr) {
+  const int x_lr = x_hr >> 8, y_lr = y_hr >> 8;
+  const unsigned fx = x_hr & 255, fy = y_hr & 255;
+  const uint32_t* r0 = img + (y_lr * pitch + x_lr);  // one texture (or one prepared background): the index fits 32 bits
+  const uint32_t* r1 = r0 + pitch;
+  const uint32_t p00 = r0[0], p10 = r0[1], p01 = r1[0], p11 = r1[1];
+  const unsigned wx = (255u - fx) | (fx << 8) | (1u << 16);
+  unsigned sacc[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const unsigned sel = (unsigned)c | ((4u + c) << 4) | ((unsigned)c << 8) | (3u << 12);
+    const unsigned top = __dp4a(__byte_perm(p00, p10, sel), wx, 0u);
+    const unsigned bot = __dp4a(__byte_perm(p01, p11, sel), wx, 0u);
+    sacc[c] = 32768u + top * (256u - fy) + bot * fy;
+  }
+  return __byte_perm(__byte_perm(sacc[0], sacc[1], 0x0062u), sacc[2], 0x7610u);
+}
+__device__ __forceinline__ int pow2_shift(int n) { return (n & (n - 1)) == 0 ? 31 - __clz(n) : -1; }
+
 // CImg draw_image(sprite, mask, 1, 255) per channel == floor((m*t + f*(255-m)) / 255)  
 __device__ __forceinline__ uint32_t blend_rgbx(uint32_t f, uint32_t t, unsigned m) {
   const unsigned w = m | ((255u - m) << 8);  // one dp4a per channel: bytes {t_c, f_c, 0, 0} . {m, 255 - m, 0, 0}
@@ -813,6 +852,15 @@ __global__ void __launch_bounds__(256) bin_pairs_kernel(RenderArgs a) {
     s_shapes[o] = make_int2(ob.shape_begin, ob.shape_count | (ob.composite ? 1 << 16 : 0));
   }
   __syncthreads();
+  if (a.bg_rows) {  // the background's span-interpolator rows (frame 1 = the prepared texture under I^-1 * M * I, DG.cpp:665-682)
+    for (int y = tid; y < a.H; y += blockDim.x) {
+      RowWarp rw;
+      rw.init(smp.bg_tex_inv, (double)(y + a.H / 2), 2 * a.W);
+      int4* r = a.bg_rows + ((size_t)sample * a.H + y) * 2;
+      r[0] = make_int4(rw.dx.v1, rw.dx.lft, rw.dx.rem, rw.dy.v1);
+      r[1] = make_int4(rw.dy.lft, rw.dy.rem, 0, 0);
+    }
+  }
   int mine = 0;  // pairs of this thread's tiles
   for (int t = tid; t < n_tiles; t += blockDim.x) {
     const int tx0 = (t % tiles_x) * TW, ty0 = (t / tiles_x) * TH;
@@ -890,6 +938,17 @@ __global__ void __launch_bounds__(RASTER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster
     const bool live = (y < H) && (x0 < W);
     const int n_shapes = pe.w & 0xFFFF, composite = pe.w >> 16;
     uint32_t uaa[2] = {0, 0}, una[2] = {0, 0};
+    if (a.pair_rows && tid >= RASTER_THREADS - 32 && lane < RTH) {
+      // the object's span-interpolator rows over this tile (frame 1 = its texture under the inverse motion, DG.cpp:203-221),
+      // one row per lane of the last warp (the (edge, row) items keep the first warps busy): the shade kernel's eight warps
+      // pick them up instead of each working out its own
+      const FlatObject& ob = a.objects[a.samples[pe.x >> 8].obj_begin + (pe.x & 255)];
+      RowWarp rw;
+      rw.init(ob.tex_inv, (double)(ty0 + lane), W);
+      int4* r = a.pair_rows + ((size_t)pr * TH + slice * RTH + lane) * 2;
+      r[0] = make_int4(rw.dx.v1, rw.dx.lft, rw.dx.rem, rw.dy.v1);
+      r[1] = make_int4(rw.dy.lft, rw.dy.rem, 0, 0);
+    }
     for (int s0 = 0; s0 < n_shapes; s0 += NLAYER / 2) {
       const int ns = min(NLAYER / 2, n_shapes - s0);
       __syncthreads();  // the previous chunk (or pair) is done with the staging and the accumulators
@@ -1046,17 +1105,33 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_SHADE_MIN_BLOCKS) shade_k
 
   // ---- background: masks are all 255 (DG.cpp:684-690); frame 0 = centre window of the prepared
   //      texture, frame 1 = that texture warped by I^-1*M*I on the 2W x 2H canvas (DG.cpp:665-682)
+  const unsigned full = 0xffffffffu;
   {
     const uchar4* bg = a.bg + (size_t)sample * (4 * P);
     const int W2 = 2 * W, H2 = 2 * H;
-    if (live) {
-      const uchar4* row = bg + (size_t)(y + H / 2) * W2 + (x0 + W / 2);
-      RowWarp rw;
-      rw.init(smp.bg_tex_inv, (double)(y + H / 2), W2);
+    // (lanes outside the frame take part in the votes with neutral values)
+    const int yy = live ? y : 0, xx = live ? x0 : 0;
+    const uchar4* row = bg + (size_t)(yy + H / 2) * W2 + (xx + W / 2);
+    if ((W & 7) == 0) {  // the lane's four pixels are one aligned 128-bit load
+      const uint4 c4 = *reinterpret_cast<const uint4*>(row);
+      col0[0] = c4.x & 0xFFFFFFu; col0[1] = c4.y & 0xFFFFFFu; col0[2] = c4.z & 0xFFFFFFu; col0[3] = c4.w & 0xFFFFFFu;
+    } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i) col0[i] = ld_px(row + i) & 0xFFFFFFu;
+    }
+    const int4* br = a.bg_rows + ((size_t)sample * H + yy) * 2;
+    const int4 r0 = br[0], r1 = br[1];
+    const int shift = pow2_shift(W2);
+    SpanLane sl;
+    sl.init(r0, r1, xx + W / 2, W2, shift < 0 ? 0 : shift);
+    if (shift >= 0 && __all_sync(full, sl.inside(W2, H2))) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) col1[i] = bilinear_rgbx_call(bg, W2, W2, H2, W2, rw.dx.v1, rw.dx.lft, rw.dx.rem, rw.dy.v1, rw.dy.lft, rw.dy.rem, x0 + i + W / 2);
+      for (int i = 0; i < 4; ++i) col1[i] = bilinear_inside(reinterpret_cast<const uint32_t*>(bg), W2, sl.x_hr(i), sl.y_hr(i));
+    } else {
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) col1[i] = bilinear_rgbx_call(bg, W2, W2, H2, W2, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, xx + i + W / 2);
+    }
+    if (live) {
       if (kDeform && smp.bg_field >= 0) {
         // background with a warp field: the warped 2W x 2H texture is resampled through the resized,
         // doubled inverse field before the centre crop (DG.cpp:670-681, 1194-1201)
@@ -1082,114 +1157,136 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_SHADE_MIN_BLOCKS) shade_k
   }
 
 
-  // ---- the tile's (object, tile) pairs in z-order: masks from the raster kernel, blits as in the fused kernel
+  // ---- the tile's (object, tile) pairs in z-order: masks from the raster kernel, blits as in the fused kernel.
+  //      Control flow around the votes is warp-uniform: lanes outside the frame carry empty masks instead of leaving.
   const int2 range = a.tile_range[(size_t)sample * gridDim.x + blockIdx.x];
+  const int shift_fg = pow2_shift(W);
   for (int pr = range.x; pr < range.x + range.y; ++pr) {
     const int k = a.pair_list[pr].x & 255;
-    uint32_t uaa[2], una[2];
-    {
+    uint32_t uaa[2] = {0u, 0u}, una[2] = {0u, 0u};
+    if (live) {
       const uint32_t* pm = a.pair_masks + (size_t)pr * (4 * TH * 32) + warp * 32 + lane;
       uaa[0] = pm[0 * TH * 32]; uaa[1] = pm[1 * TH * 32]; una[0] = pm[2 * TH * 32]; una[1] = pm[3 * TH * 32];
     }
-    const bool row_hit = __any_sync(0xffffffffu, (uaa[0] | uaa[1] | una[0] | una[1]) != 0u);  // (every lane takes part)
-    if (!live || (!row_hit && !a.dbg_masks)) continue;  // outside the frame, or the row is clear of this object
+    const bool row_hit = __any_sync(full, (uaa[0] | uaa[1] | una[0] | una[1]) != 0u);
+    if (!row_hit && !a.dbg_masks) continue;  // the row is clear of this object
     const FlatObject& ob = a.objects[obj_begin + k];
     const TexInfo ti = a.tex_info[ob.tex];
-    {
-        // the object's masks are complete: ids from the non-AA masks, colour through the AA (or non-AA) masks
-        
-        if (a.dbg_masks && k < a.dbg_max_objs) {
-          uint8_t* mb = a.dbg_masks + ((size_t)sample * a.dbg_max_objs + k) * 4 * P + (size_t)y * W + x0;
-          *reinterpret_cast<uint32_t*>(mb + 0 * P) = uaa[0]; *reinterpret_cast<uint32_t*>(mb + 1 * P) = uaa[1];
-          *reinterpret_cast<uint32_t*>(mb + 2 * P) = una[0]; *reinterpret_cast<uint32_t*>(mb + 3 * P) = una[1];
-        }
-        const uint32_t kk = (uint32_t)(k + 1) * 0x01010101u;
-        const uint32_t e0 = __vcmpeq4(una[0], 0xFFFFFFFFu), e1 = __vcmpeq4(una[1], 0xFFFFFFFFu);
-        id0 = (id0 & ~e0) | (kk & e0);
-        id1 = (id1 & ~e1) | (kk & e1);
-        const uint32_t m0w = a.use_aa ? uaa[0] : una[0], m1w = a.use_aa ? uaa[1] : una[1];
-        if ((m0w | m1w) == 0u) continue;
-        const uchar4* tex = a.pool + ti.fg_base;  // the W x H foreground view (centre crop, DG.cpp:99-102 with defaults, or the resized copy)
-        if (m0w) {
-          const uchar4* trow = tex + (size_t)y * ti.fg_pitch + x0;  // identity warp == copy
+    // the object's masks are complete: ids from the non-AA masks, colour through the AA (or non-AA) masks
+    if (a.dbg_masks && k < a.dbg_max_objs && live) {
+      uint8_t* mb = a.dbg_masks + ((size_t)sample * a.dbg_max_objs + k) * 4 * P + (size_t)y * W + x0;
+      *reinterpret_cast<uint32_t*>(mb + 0 * P) = uaa[0]; *reinterpret_cast<uint32_t*>(mb + 1 * P) = uaa[1];
+      *reinterpret_cast<uint32_t*>(mb + 2 * P) = una[0]; *reinterpret_cast<uint32_t*>(mb + 3 * P) = una[1];
+    }
+    const uint32_t kk = (uint32_t)(k + 1) * 0x01010101u;
+    const uint32_t e0 = __vcmpeq4(una[0], 0xFFFFFFFFu), e1 = __vcmpeq4(una[1], 0xFFFFFFFFu);
+    id0 = (id0 & ~e0) | (kk & e0);
+    id1 = (id1 & ~e1) | (kk & e1);
+    const uint32_t m0w = a.use_aa ? uaa[0] : una[0], m1w = a.use_aa ? uaa[1] : una[1];
+    const uchar4* tex = a.pool + ti.fg_base;  // the W x H foreground view (centre crop, DG.cpp:99-102 with defaults, or the resized copy)
+    if (m0w) {
+      const uchar4* trow = tex + (size_t)y * ti.fg_pitch + x0;  // identity warp == copy
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const unsigned m0 = (m0w >> (8 * i)) & 255u;
-            if (m0) col0[i] = blend_rgbx(col0[i], ld_px(trow + i) & 0xFFFFFFu, m0);
+      for (int i = 0; i < 4; ++i) {
+        const unsigned m0 = (m0w >> (8 * i)) & 255u;
+        if (m0) col0[i] = blend_rgbx(col0[i], ld_px(trow + i) & 0xFFFFFFu, m0);
+      }
+    }
+    if (!kDeform || ob.field < 0) {
+      if (__any_sync(full, m1w != 0u)) {
+        const int4* prow = a.pair_rows + ((size_t)pr * TH + warp) * 2;
+        const int4 r0 = prow[0], r1 = prow[1];
+        SpanLane sl;
+        sl.init(r0, r1, live ? x0 : 0, W, shift_fg < 0 ? 0 : shift_fg);
+        if (shift_fg >= 0 && __all_sync(full, m1w == 0u || sl.inside(W, H))) {
+          if (m1w) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const unsigned m1 = (m1w >> (8 * i)) & 255u;
+              if (m1) col1[i] = blend_rgbx(col1[i], bilinear_inside(reinterpret_cast<const uint32_t*>(tex), ti.fg_pitch, sl.x_hr(i), sl.y_hr(i)), m1);
+            }
           }
-        }
-        if (m1w && (!kDeform || ob.field < 0)) {
-          RowWarp rw;
-          rw.init(a.objects[obj_begin + k].tex_inv, (double)y, W);
-#pragma unroll
+        } else if (m1w) {
+#pragma unroll 1
           for (int i = 0; i < 4; ++i) {
             const unsigned m1 = (m1w >> (8 * i)) & 255u;
-            if (m1) col1[i] = blend_rgbx(col1[i], bilinear_rgbx_call(tex, ti.fg_pitch, W, H, W, rw.dx.v1, rw.dx.lft, rw.dx.rem, rw.dy.v1, rw.dy.lft, rw.dy.rem, x0 + i), m1);
-          }
-        } else if (kDeform && m1w) {
-          // applyWarpFieldToTexture(getTransformedTexture(tex0, M), iflow) evaluated where the mask is set:
-          // each of the 4 float-bilinear taps is itself one AGG span-bilinear pixel (DG.cpp:341-345)
-          const double* tinv = a.objects[obj_begin + k].tex_inv;
-          const int fw = W + 1, fh = H + 1;
-          const float* ifl = a.fields + ((size_t)ob.field * 2 + 1) * 2 * fw * fh;
-          auto tap = [&](int px, int py) -> uint32_t {
-            if (px < 0 || py < 0 || px >= W || py >= H) return 0u;
-            RowWarp rw;
-            rw.init(tinv, (double)py, W);
-            return bilinear_rgbx(tex, ti.fg_pitch, 0, 0, W, H, rw, px);
-          };
-          for (int i = 0; i < 4; ++i) {
-            const unsigned m1 = (m1w >> (8 * i)) & 255u;
-            if (!m1) continue;
-            const int x = x0 + i;
-            const float sx = x + ifl[(size_t)y * fw + x], sy = y + ifl[(size_t)fw * fh + (size_t)y * fw + x];
-            col1[i] = blend_rgbx(col1[i], dirichlet_rgbx(tap, sx, sy), m1);
+            if (m1) col1[i] = blend_rgbx(col1[i], bilinear_rgbx_call(tex, ti.fg_pitch, W, H, W, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, x0 + i), m1);
           }
         }
+      }
+    } else if (kDeform && m1w) {
+      // applyWarpFieldToTexture(getTransformedTexture(tex0, M), iflow) evaluated where the mask is set:
+      // each of the 4 float-bilinear taps is itself one AGG span-bilinear pixel (DG.cpp:341-345)
+      const double* tinv = a.objects[obj_begin + k].tex_inv;
+      const int fw = W + 1, fh = H + 1;
+      const float* ifl = a.fields + ((size_t)ob.field * 2 + 1) * 2 * fw * fh;
+      auto tap = [&](int px, int py) -> uint32_t {
+        if (px < 0 || py < 0 || px >= W || py >= H) return 0u;
+        RowWarp rw;
+        rw.init(tinv, (double)py, W);
+        return bilinear_rgbx(tex, ti.fg_pitch, 0, 0, W, H, rw, px);
+      };
+      for (int i = 0; i < 4; ++i) {
+        const unsigned m1 = (m1w >> (8 * i)) & 255u;
+        if (!m1) continue;
+        const int x = x0 + i;
+        const float sx = x + ifl[(size_t)y * fw + x], sy = y + ifl[(size_t)fw * fh + (size_t)y * fw + x];
+        col1[i] = blend_rgbx(col1[i], dirichlet_rgbx(tap, sx, sy), m1);
+      }
     }
   }
 
   if (!live) return;
 
-  // ---- flow of the top-most object, f64 -> f32 (DG.cpp:388-401, 692-712). Forward: frame 0's ids through the motions;
-  //      backward (extra top, computeFlowImage(inverse = true)): frame 1's ids through the inverse motions.
-  auto point_flow = [&](unsigned oid, bool inverse, int i, float& fx, float& fy) {
-    const float xf = (float)(x0 + i), yf = (float)y;
-    // background: the point goes through I^-1 = T(-W,-H), M, I = T(W,H) (DG.cpp:697-712); objects: through M alone.
-    // One code path: the translations are exact no-ops (+-0.0) for objects.
-    const FlatObject* fo = oid ? a.objects + obj_begin + oid - 1 : nullptr;
-    const double* m = oid ? (inverse ? fo->tex_inv : fo->motion) : (inverse ? smp.bg_motion_inv : smp.bg_motion);
-    const double pre_x = oid ? 0.0 : (double)W, pre_y = oid ? 0.0 : (double)H;
-    const float save_x = oid ? xf : xf + (float)(W / 2), save_y = oid ? yf : yf + (float)(H / 2);
-    double ix = (double)save_x - pre_x, iy = (double)save_y - pre_y;
-    const double tmp = ix;
-    ix = tmp * m[0] + iy * m[2] + m[4];
-    iy = tmp * m[1] + iy * m[3] + m[5];
-    ix = ix + pre_x; iy = iy + pre_y;
-    fx = (float)(ix - save_x);
-    fy = (float)(iy - save_y);
-    if (kDeform) {  // the forward field is added in both directions (DG.cpp:403-406, 714-717)
-      const int fw = W + 1, fh = H + 1;
-      if (oid == 0) {
-        if (smp.bg_field >= 0 && ix >= 0 && ix < 2 * W && iy >= 0 && iy < 2 * H) {  // DG.cpp:714-717
-          const float* fl = a.fields + ((size_t)smp.bg_field * 2 + 0) * 2 * fw * fh;
-          auto at0 = [&](unsigned X, unsigned Y) { return resized_field2(fl, fw, fh, (int)X, (int)Y, a); };
-          auto at1 = [&](unsigned X, unsigned Y) { return resized_field2(fl + (size_t)fw * fh, fw, fh, (int)X, (int)Y, a); };
-          fx += neumann_f(at0, 2 * W, 2 * H, (float)ix, (float)iy);
-          fy += neumann_f(at1, 2 * W, 2 * H, (float)ix, (float)iy);
+  // Forward flow of the lane's four pixels. The motion of the top-most object is loaded once and kept while the id stays the
+  // same (it changes at object borders only); the row terms y * shx, y * sy are shared by the four pixels. Every product and
+  // sum is the one getPointFlow forms, in its order: ((x * sx + y * shx) + tx) + W, minus the saved x (DG.cpp:390-401, 697-712).
+  float fxv[4], fyv[4];
+  {
+    unsigned cur = 0xFFFFFFFFu;
+    double m0 = 0, m1 = 0, m4 = 0, m5 = 0, t2 = 0, t3 = 0, pre_x = 0, pre_y = 0, ixb = 0, sxb = 0, syd = 0;
+    const FlatObject* fo = nullptr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const unsigned oid = (id0 >> (8 * i)) & 255u;
+      if (oid != cur) {
+        cur = oid;
+        fo = oid ? a.objects + obj_begin + oid - 1 : nullptr;
+        const double* m = oid ? fo->motion : smp.bg_motion;
+        pre_x = oid ? 0.0 : (double)W; pre_y = oid ? 0.0 : (double)H;
+        sxb = (double)(oid ? x0 : x0 + W / 2); syd = (double)(oid ? y : y + H / 2);  // (double)(float)(integer): exact
+        ixb = sxb - pre_x;
+        const double iy0 = syd - pre_y;
+        m0 = m[0]; m1 = m[1]; m4 = m[4]; m5 = m[5];
+        t2 = iy0 * m[2]; t3 = iy0 * m[3];
+      }
+      const double di = (double)i;
+      const double ix0 = ixb + di, sx = sxb + di;  // small integers: exact
+      double ix = ix0 * m0 + t2 + m4, iy = ix0 * m1 + t3 + m5;
+      ix = ix + pre_x; iy = iy + pre_y;
+      fxv[i] = (float)(ix - sx);
+      fyv[i] = (float)(iy - syd);
+      if (kDeform) {  // the forward field is added (DG.cpp:403-406, 714-717)
+        const int fw = W + 1, fh = H + 1;
+        if (oid == 0) {
+          if (smp.bg_field >= 0 && ix >= 0 && ix < 2 * W && iy >= 0 && iy < 2 * H) {  // DG.cpp:714-717
+            const float* fl = a.fields + ((size_t)smp.bg_field * 2 + 0) * 2 * fw * fh;
+            auto at0 = [&](unsigned X, unsigned Y) { return resized_field2(fl, fw, fh, (int)X, (int)Y, a); };
+            auto at1 = [&](unsigned X, unsigned Y) { return resized_field2(fl + (size_t)fw * fh, fw, fh, (int)X, (int)Y, a); };
+            fxv[i] += neumann_f(at0, 2 * W, 2 * H, (float)ix, (float)iy);
+            fyv[i] += neumann_f(at1, 2 * W, 2 * H, (float)ix, (float)iy);
+          }
+        } else if (fo->field >= 0 && ix >= 0 && ix < W && iy >= 0 && iy < H) {  // DG.cpp:403-406
+          const float* fl = a.fields + ((size_t)fo->field * 2 + 0) * 2 * fw * fh;
+          auto at0 = [&](unsigned X, unsigned Y) { return fl[(size_t)Y * fw + X]; };
+          auto at1 = [&](unsigned X, unsigned Y) { return fl[(size_t)fw * fh + (size_t)Y * fw + X]; };
+          fxv[i] += neumann_f(at0, fw, fh, (float)ix, (float)iy);
+          fyv[i] += neumann_f(at1, fw, fh, (float)ix, (float)iy);
         }
-      } else if (fo->field >= 0 && ix >= 0 && ix < W && iy >= 0 && iy < H) {  // DG.cpp:403-406
-        const float* fl = a.fields + ((size_t)fo->field * 2 + 0) * 2 * fw * fh;
-        auto at0 = [&](unsigned X, unsigned Y) { return fl[(size_t)Y * fw + X]; };
-        auto at1 = [&](unsigned X, unsigned Y) { return fl[(size_t)fw * fh + (size_t)Y * fw + X]; };
-        fx += neumann_f(at0, fw, fh, (float)ix, (float)iy);
-        fy += neumann_f(at1, fw, fh, (float)ix, (float)iy);
       }
     }
-  };
-  float fxv[4], fyv[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) point_flow((id0 >> (8 * i)) & 255u, false, i, fxv[i], fyv[i]);
+  }
+
 
   // ---- write the three blobs (NCHW float): 8 planes x one 128-bit store per lane
   const size_t pix = (size_t)y * W + x0;
@@ -1218,6 +1315,42 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_SHADE_MIN_BLOCKS) shade_k
 
   if (kExtra) {
     if (a.flow_bw) {
+  // ---- flow of the top-most object, f64 -> f32 (DG.cpp:388-401, 692-712). Forward: frame 0's ids through the motions;
+      //      backward (extra top, computeFlowImage(inverse = true)): frame 1's ids through the inverse motions.
+      auto point_flow = [&](unsigned oid, bool inverse, int i, float& fx, float& fy) {
+        const float xf = (float)(x0 + i), yf = (float)y;
+        // background: the point goes through I^-1 = T(-W,-H), M, I = T(W,H) (DG.cpp:697-712); objects: through M alone.
+        // One code path: the translations are exact no-ops (+-0.0) for objects.
+        const FlatObject* fo = oid ? a.objects + obj_begin + oid - 1 : nullptr;
+        const double* m = oid ? (inverse ? fo->tex_inv : fo->motion) : (inverse ? smp.bg_motion_inv : smp.bg_motion);
+        const double pre_x = oid ? 0.0 : (double)W, pre_y = oid ? 0.0 : (double)H;
+        const float save_x = oid ? xf : xf + (float)(W / 2), save_y = oid ? yf : yf + (float)(H / 2);
+        double ix = (double)save_x - pre_x, iy = (double)save_y - pre_y;
+        const double tmp = ix;
+        ix = tmp * m[0] + iy * m[2] + m[4];
+        iy = tmp * m[1] + iy * m[3] + m[5];
+        ix = ix + pre_x; iy = iy + pre_y;
+        fx = (float)(ix - save_x);
+        fy = (float)(iy - save_y);
+        if (kDeform) {  // the forward field is added in both directions (DG.cpp:403-406, 714-717)
+          const int fw = W + 1, fh = H + 1;
+          if (oid == 0) {
+            if (smp.bg_field >= 0 && ix >= 0 && ix < 2 * W && iy >= 0 && iy < 2 * H) {  // DG.cpp:714-717
+              const float* fl = a.fields + ((size_t)smp.bg_field * 2 + 0) * 2 * fw * fh;
+              auto at0 = [&](unsigned X, unsigned Y) { return resized_field2(fl, fw, fh, (int)X, (int)Y, a); };
+              auto at1 = [&](unsigned X, unsigned Y) { return resized_field2(fl + (size_t)fw * fh, fw, fh, (int)X, (int)Y, a); };
+              fx += neumann_f(at0, 2 * W, 2 * H, (float)ix, (float)iy);
+              fy += neumann_f(at1, 2 * W, 2 * H, (float)ix, (float)iy);
+            }
+          } else if (fo->field >= 0 && ix >= 0 && ix < W && iy >= 0 && iy < H) {  // DG.cpp:403-406
+            const float* fl = a.fields + ((size_t)fo->field * 2 + 0) * 2 * fw * fh;
+            auto at0 = [&](unsigned X, unsigned Y) { return fl[(size_t)Y * fw + X]; };
+            auto at1 = [&](unsigned X, unsigned Y) { return fl[(size_t)fw * fh + (size_t)Y * fw + X]; };
+            fx += neumann_f(at0, fw, fh, (float)ix, (float)iy);
+            fy += neumann_f(at1, fw, fh, (float)ix, (float)iy);
+          }
+        }
+      };
       float bx[4], by[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) point_flow((id1 >> (8 * i)) & 255u, true, i, bx[i], by[i]);
@@ -1882,6 +2015,7 @@ int launch_render(const RenderArgs& a, cudaStream_t s) {
 }
 
 size_t pair_mask_bytes_per_pair() { return (size_t)4 * TH * 32 * sizeof(uint32_t); }
+size_t pair_row_bytes_per_pair() { return (size_t)TH * 2 * sizeof(int4); }
 
 int launch_bin_pairs(const RenderArgs& a, cudaStream_t s) {
   cudaMemsetAsync(a.pair_ctl, 0, 3 * sizeof(int), s);

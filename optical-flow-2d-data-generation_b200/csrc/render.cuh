@@ -33,6 +33,10 @@ struct RenderArgs {
   int4* pair_list;            // [pair_cap] {sample * 256 + object, tile, first outline (absolute), outline count | composite << 16}
   int prep_w, prep_h;         // extent of the largest needed part of a prepared background (0: the whole canvas): bg_prep_kernel's grid
   uint32_t* pair_masks;       // [pair_cap][AA 0 | AA 1 | non-AA 0 | non-AA 1][TH][32] four pixels per word
+  // span-interpolator rows (agg::span_interpolator_linear::begin, DataGenerator.cpp:203-221) hoisted out of the shade kernel:
+  // two int4 per row = {x1, lft_x, rem_x, y1} {lft_y, rem_y, -, -} of dda2_line_interpolator over the row's span
+  int4* bg_rows;              // [batch][H][2] background rows (written by bin_pairs_kernel), span length 2W
+  int4* pair_rows;            // [pair_cap][TH][2] the pair's object over the tile's rows (written by raster_pairs_kernel), span length W
   int* pair_ctl;              // [0] pairs claimed (atomic), [1] set when they exceed pair_cap (cannot happen: pair_cap is an upper bound; the kernels then skip the batch), [2] the raster kernel's work queue
   int pair_cap;
   int* pair_overflow;         // mapped host int, raised together with pair_ctl[1] (the host reports it after its next synchronisation)
@@ -82,6 +86,7 @@ int launch_bin_pairs(const RenderArgs& a, cudaStream_t s);
 int launch_raster_pairs(const RenderArgs& a, cudaStream_t s);
 int launch_render_split(const RenderArgs& a, cudaStream_t s, cudaEvent_t before_shade = nullptr, int done = 0);
 size_t pair_mask_bytes_per_pair();
+size_t pair_row_bytes_per_pair();
 int launch_deform_prepass(const RenderArgs& a, cudaStream_t s);  // mode 9 only; no-op when n_deform == 0
 
 // Foreground view (W x H) of a texture smaller than W x H, CImg linear resize; tmp holds W x h pixels, pos / alpha max(W, H) entries.
