@@ -13,6 +13,9 @@
 //       write    uint8 -> float conversion into the output blobs                      (DG.cpp:1229-1245)
 #include "render.cuh"
 
+#include <cstdlib>
+#include <string>
+
 #include "ofdg/augment.h"
 #include "raster_tile.h"
 
@@ -828,8 +831,42 @@ __device__ __forceinline__ bool box_hits_rows(const int32_t* b, int tx0, int ty0
   return b[1] <= ty0 + rows - 1 && b[3] >= ty0 && b[0] <= tx0 + TW - 1 && b[2] >= tx0;
 }
 #ifndef OFDG_SHADE_MIN_BLOCKS
-#define OFDG_SHADE_MIN_BLOCKS 6  // measured: 4 / 5 / 6 / 8 blocks per SM -> 0.192 / 0.182 / 0.177 / 0.186 ms
+#define OFDG_SHADE_MIN_BLOCKS 5  // measured (round 2 kernel): 4 / 5 / 6 blocks per SM -> 0.152 / 0.142 / 0.153 ms
 #endif
+// ---- bulk asynchronous copies global -> shared (cp.async.bulk, completion counted on an mbarrier), sm_90+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {  // 16-byte aligned, size a multiple of 16
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE;\n"
+      "bra MBAR_WAIT;\n"
+      "MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+#ifndef OFDG_SHADE_STAGE
+#define OFDG_SHADE_STAGE 0  // > 0: that many (object, tile) pairs' masks and records are brought into shared memory by one bulk copy (cp.async.bulk +
+                            // mbarrier) while the background is filtered. Measured with 6: shade 0.142 -> 0.160 ms (5 blocks/SM), 0.153 -> 0.176 ms (6):
+                            // the 26 KB per block come out of the L1 the bilinear taps live in. 0: per-pair global loads + L1 prefetch of the next pair.
+#endif
+
+constexpr int PAIR_ROW_STRIDE = 2 + 2 * TH;  // RenderArgs::pair_rows per pair: a two-word header {foreground view base (2 x 32 bits), pitch, object} {field}, then two words per tile row
 struct PairOutline {   // one outline of the pair's object, staged in shared memory
   int vbegin[2], vcount[2];
   signed char layer[2];  // accumulator layer per frame, -1: the outline misses the tile
@@ -945,9 +982,14 @@ __global__ void __launch_bounds__(RASTER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster
       const FlatObject& ob = a.objects[a.samples[pe.x >> 8].obj_begin + (pe.x & 255)];
       RowWarp rw;
       rw.init(ob.tex_inv, (double)(ty0 + lane), W);
-      int4* r = a.pair_rows + ((size_t)pr * TH + slice * RTH + lane) * 2;
-      r[0] = make_int4(rw.dx.v1, rw.dx.lft, rw.dx.rem, rw.dy.v1);
-      r[1] = make_int4(rw.dy.lft, rw.dy.rem, 0, 0);
+      int4* r = a.pair_rows + (size_t)pr * PAIR_ROW_STRIDE;
+      r[2 + (slice * RTH + lane) * 2] = make_int4(rw.dx.v1, rw.dx.lft, rw.dx.rem, rw.dy.v1);
+      r[3 + (slice * RTH + lane) * 2] = make_int4(rw.dy.lft, rw.dy.rem, 0, 0);
+      if (lane == 0 && slice == 0) {  // what the shade kernel needs of the object, in one record (instead of pair -> object -> texture table)
+        const TexInfo ti = a.tex_info[ob.tex];
+        r[0] = make_int4((int)(uint32_t)(ti.fg_base & 0xFFFFFFFFu), (int)(uint32_t)(ti.fg_base >> 32), ti.fg_pitch, pe.x & 255);
+        r[1] = make_int4(ob.field, 0, 0, 0);
+      }
     }
     for (int s0 = 0; s0 < n_shapes; s0 += NLAYER / 2) {
       const int ns = min(NLAYER / 2, n_shapes - s0);
@@ -1102,10 +1144,29 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_SHADE_MIN_BLOCKS) shade_k
   const int obj_begin = smp.obj_begin;
   uint32_t col0[4], col1[4];
   uint32_t id0 = 0, id1 = 0;  // four pixels, one byte each: 0 = background, k+1 = k-th foreground object (k < 255)
+  const unsigned full = 0xffffffffu;
+  const int2 range = a.tile_range[(size_t)sample * gridDim.x + blockIdx.x];
+#if OFDG_SHADE_STAGE > 0
+  // The tile's pairs are consecutive in the pair list, so their masks (4 KB each) and records are two contiguous runs: one thread
+  // starts bulk copies of the first OFDG_SHADE_STAGE pairs into shared memory now, and they land while the background is filtered --
+  // the pair loop then finds everything on chip instead of paying a global round trip per pair.
+  __shared__ __align__(128) uint32_t s_masks[OFDG_SHADE_STAGE][4 * TH * 32];
+  __shared__ __align__(16) int4 s_rows[OFDG_SHADE_STAGE][PAIR_ROW_STRIDE];
+  __shared__ __align__(8) unsigned long long s_bar;
+  if (range.y > 0) {  // (block-uniform)
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t n = (uint32_t)min(range.y, OFDG_SHADE_STAGE);
+      mbar_expect_tx(&s_bar, n * (uint32_t)(4 * TH * 32 * 4 + PAIR_ROW_STRIDE * 16));
+      bulk_g2s(&s_masks[0][0], a.pair_masks + (size_t)range.x * (4 * TH * 32), n * (uint32_t)(4 * TH * 32 * 4), &s_bar);
+      bulk_g2s(&s_rows[0][0], a.pair_rows + (size_t)range.x * PAIR_ROW_STRIDE, n * (uint32_t)(PAIR_ROW_STRIDE * 16), &s_bar);
+    }
+  }
+#endif
 
   // ---- background: masks are all 255 (DG.cpp:684-690); frame 0 = centre window of the prepared
   //      texture, frame 1 = that texture warped by I^-1*M*I on the 2W x 2H canvas (DG.cpp:665-682)
-  const unsigned full = 0xffffffffu;
   {
     const uchar4* bg = a.bg + (size_t)sample * (4 * P);
     const int W2 = 2 * W, H2 = 2 * H;
@@ -1121,6 +1182,15 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_SHADE_MIN_BLOCKS) shade_k
     }
     const int4* br = a.bg_rows + ((size_t)sample * H + yy) * 2;
     const int4 r0 = br[0], r1 = br[1];
+#if OFDG_SHADE_STAGE == 0
+    if (range.y > 0) {  // the first pair's record and mask rows: on their way while the background is filtered
+      const char* nm = reinterpret_cast<const char*>(a.pair_masks + (size_t)range.x * (4 * TH * 32) + warp * 32);
+      const int4* prow = a.pair_rows + (size_t)range.x * PAIR_ROW_STRIDE;
+      if (lane < 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(nm + lane * (TH * 32 * 4)));
+      else if (lane == 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(prow));
+      else if (lane == 5) asm volatile("prefetch.global.L1 [%0];" ::"l"(prow + 2 + warp * 2));
+    }
+#endif
     const int shift = pow2_shift(W2);
     SpanLane sl;
     sl.init(r0, r1, xx + W / 2, W2, shift < 0 ? 0 : shift);
@@ -1159,19 +1229,56 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_SHADE_MIN_BLOCKS) shade_k
 
   // ---- the tile's (object, tile) pairs in z-order: masks from the raster kernel, blits as in the fused kernel.
   //      Control flow around the votes is warp-uniform: lanes outside the frame carry empty masks instead of leaving.
-  const int2 range = a.tile_range[(size_t)sample * gridDim.x + blockIdx.x];
   const int shift_fg = pow2_shift(W);
+#if OFDG_SHADE_STAGE > 0
+  uint32_t stage_parity = 0;
+#endif
   for (int pr = range.x; pr < range.x + range.y; ++pr) {
-    const int k = a.pair_list[pr].x & 255;
     uint32_t uaa[2] = {0u, 0u}, una[2] = {0u, 0u};
+#if OFDG_SHADE_STAGE > 0
+    const int slot = (pr - range.x) % OFDG_SHADE_STAGE;
+    if (slot == 0) {
+      if (pr > range.x) {  // the next run of pairs: every warp is done with the staged ones
+        __syncthreads();
+        if (tid == 0) {
+          const uint32_t n = (uint32_t)min(range.x + range.y - pr, OFDG_SHADE_STAGE);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_expect_tx(&s_bar, n * (uint32_t)(4 * TH * 32 * 4 + PAIR_ROW_STRIDE * 16));
+          bulk_g2s(&s_masks[0][0], a.pair_masks + (size_t)pr * (4 * TH * 32), n * (uint32_t)(4 * TH * 32 * 4), &s_bar);
+          bulk_g2s(&s_rows[0][0], a.pair_rows + (size_t)pr * PAIR_ROW_STRIDE, n * (uint32_t)(PAIR_ROW_STRIDE * 16), &s_bar);
+        }
+      }
+      mbar_wait(&s_bar, stage_parity);
+      stage_parity ^= 1u;
+    }
+    const int4* prow = &s_rows[slot][0];
+    if (live) {
+      const uint32_t* pm = &s_masks[slot][warp * 32 + lane];
+      uaa[0] = pm[0 * TH * 32]; uaa[1] = pm[1 * TH * 32]; una[0] = pm[2 * TH * 32]; una[1] = pm[3 * TH * 32];
+    }
+    const int4 hdr = prow[0];  // {foreground view base, pitch, object}
+#else
+    const int4* prow = a.pair_rows + (size_t)pr * PAIR_ROW_STRIDE;
     if (live) {
       const uint32_t* pm = a.pair_masks + (size_t)pr * (4 * TH * 32) + warp * 32 + lane;
       uaa[0] = pm[0 * TH * 32]; uaa[1] = pm[1 * TH * 32]; una[0] = pm[2 * TH * 32]; una[1] = pm[3 * TH * 32];
     }
+    const int4 hdr = prow[0];  // {foreground view base, pitch, object}: in flight together with the masks
+    if (pr + 1 < range.x + range.y) {  // the next pair's record and mask rows: on their way while this pair is blended
+      const char* nm = reinterpret_cast<const char*>(a.pair_masks + (size_t)(pr + 1) * (4 * TH * 32) + warp * 32);
+      if (lane < 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(nm + lane * (TH * 32 * 4)));
+      else if (lane == 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(prow + PAIR_ROW_STRIDE));
+      else if (lane == 5) asm volatile("prefetch.global.L1 [%0];" ::"l"(prow + PAIR_ROW_STRIDE + 2 + warp * 2));
+    }
+#endif
     const bool row_hit = __any_sync(full, (uaa[0] | uaa[1] | una[0] | una[1]) != 0u);
     if (!row_hit && !a.dbg_masks) continue;  // the row is clear of this object
-    const FlatObject& ob = a.objects[obj_begin + k];
-    const TexInfo ti = a.tex_info[ob.tex];
+    const int k = hdr.w;
+    struct { unsigned long long fg_base; int fg_pitch; } ti;
+    ti.fg_base = (unsigned long long)(uint32_t)hdr.x | ((unsigned long long)(uint32_t)hdr.y << 32);
+    ti.fg_pitch = hdr.z;
+    struct { int field; } ob;
+    ob.field = kDeform ? prow[1].x : -1;
     // the object's masks are complete: ids from the non-AA masks, colour through the AA (or non-AA) masks
     if (a.dbg_masks && k < a.dbg_max_objs && live) {
       uint8_t* mb = a.dbg_masks + ((size_t)sample * a.dbg_max_objs + k) * 4 * P + (size_t)y * W + x0;
@@ -1194,8 +1301,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_SHADE_MIN_BLOCKS) shade_k
     }
     if (!kDeform || ob.field < 0) {
       if (__any_sync(full, m1w != 0u)) {
-        const int4* prow = a.pair_rows + ((size_t)pr * TH + warp) * 2;
-        const int4 r0 = prow[0], r1 = prow[1];
+        const int4 r0 = prow[2 + warp * 2], r1 = prow[3 + warp * 2];
         SpanLane sl;
         sl.init(r0, r1, live ? x0 : 0, W, shift_fg < 0 ? 0 : shift_fg);
         if (shift_fg >= 0 && __all_sync(full, m1w == 0u || sl.inside(W, H))) {
@@ -2015,7 +2121,7 @@ int launch_render(const RenderArgs& a, cudaStream_t s) {
 }
 
 size_t pair_mask_bytes_per_pair() { return (size_t)4 * TH * 32 * sizeof(uint32_t); }
-size_t pair_row_bytes_per_pair() { return (size_t)TH * 2 * sizeof(int4); }
+size_t pair_row_bytes_per_pair() { return (size_t)PAIR_ROW_STRIDE * sizeof(int4); }
 
 int launch_bin_pairs(const RenderArgs& a, cudaStream_t s) {
   cudaMemsetAsync(a.pair_ctl, 0, 3 * sizeof(int), s);
