@@ -407,6 +407,32 @@ def run_ours(args):
     checksum = float(h0.mean()) + float(h1.mean()) + float(hf.mean())  # every blob element was delivered to the host
     g.kernel_times()
 
+    # ---- the Caffe-style layer, the actual drop-in: prototxt -> LayerRegistry -> LayerSetUp -> Forward_gpu x steps
+    layer_leg = None
+    if world == 1 and not args.no_layer and (W, H) == (512, 384):
+        layer_leg = {}
+        for name, extra in (("host_rng", ""), ("device_params", " device_params: true seed: %d" % args.seed)):
+            if name == "device_params" and mode == 9:
+                continue
+            proto = ('layer { name: "gen" type: "DataGeneration" top: "img0" top: "img1" top: "flow" data_param { batch_size: %d prefetch: 4 } '
+                     'data_generation_param { mode: %d texture_dbases: "synthetic:%d:%d"%s } }' % (B, mode, args.textures, args.seed, extra))
+            layer = o.DataGenerationLayer(proto)
+            layer.LayerSetUp()
+            for _ in range(6):
+                layer.Forward_gpu()
+            torch.cuda.synchronize()
+            n_fw = max(20, min(args.steps, 300))
+            t0 = time.time()
+            for _ in range(n_fw):
+                layer.Forward_gpu()  # non-blocking: queues the batch on the layer's stream, the default stream waits by event
+            torch.cuda.synchronize()
+            dt = time.time() - t0
+            layer_leg[name] = {"value": B * n_fw / dt, "unit": "samples/s", "ms_per_forward": 1e3 * dt / n_fw, "forwards": n_fw}
+            layer.close()
+        layer_leg["what"] = ("DataGenerationLayer::Forward_gpu into the top blobs' device memory, wall clock over back-to-back forwards incl. the "
+                             "prefetch thread's parameter draw + flatten (host pool) + scene upload; host_rng = the reference's RNG stream, "
+                             "device_params = the Philox production stream")
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -440,6 +466,7 @@ def run_ours(args):
                 "steps": e2e_steps, "checksum": checksum},
         "gpu_launches": launches,
         "production_mode": production,
+        "layer_forward_gpu": layer_leg,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ab, "kernel_ms": kern_ms,
@@ -500,6 +527,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-attribution", action="store_true", help="skip the per-kernel attribution pass")
+    ap.add_argument("--no-layer", action="store_true", help="skip the DataGenerationLayer::Forward_gpu leg")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture (profiles/)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -26,6 +26,10 @@ int ofdg_layer_top_shape(void* layer, int32_t i, int32_t* shape4);
 int ofdg_layer_forward(void* layer, int32_t gpu);                /* Forward_gpu (1) / Forward_cpu (0) */
 const float* ofdg_layer_top_data(void* layer, int32_t i, int32_t gpu); /* top[i]->gpu_data() / cpu_data() */
 const char* ofdg_layer_type(void* layer);                        /* "DataGeneration" */
+/* Comma-separated type strings in the shim's caffe::LayerRegistry<float> (REGISTER_LAYER_CLASS(DataGeneration),
+ * /root/reference/src/caffe/layers/data_generation_layer.cpp:298-299): ofdg_layer_create builds the layer through
+ * LayerRegistry<float>::CreateLayer(param), the way Net::Init does. Returns the number of types. */
+int ofdg_layer_registered_types(char* out, int32_t cap);
 /* The texture-file decoder the layer uses (TextureCollection ctor, DataGenerator.cpp:128-133): size of the image,
  * and, when `planar_bgr` is non-NULL and `cap` >= 3*w*h, its pixels as 3 x h x w planes in B,G,R order. No GPU needed. */
 int ofdg_decode_texture_file(const char* path, int32_t* w, int32_t* h, uint8_t* planar_bgr, uint64_t cap);

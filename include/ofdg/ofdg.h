@@ -65,6 +65,8 @@ int ofdg_params_generate(ofdg_params* p, int32_t n_tasks, ofdg_tasks* out);
 int ofdg_params_enable_augmentation(ofdg_params* p, int32_t enable);
 int ofdg_params_skip(ofdg_params* p, uint64_t n_tasks);          /* checkpoint/resume: fast-forward */
 uint64_t ofdg_params_tasks_generated(const ofdg_params* p);
+/* Mode 9: warp-field picks made so far (pool slot of pick k = (k / 3) % n_fields). */
+uint64_t ofdg_params_field_draws(const ofdg_params* p);
 uint64_t ofdg_params_draws(const ofdg_params* p, int32_t slot);  /* draws made by engine `slot` so far */
 const char* ofdg_params_slot_name(int32_t slot);
 
@@ -126,6 +128,15 @@ int ofdg_set_fields(ofdg_generator* g, const float* fields, int32_t n);
  * 3*max(W,H) canvas with 17 self-compositions each and installs n crops as the generator's pool
  * (like ofdg_set_fields). fields_out, if not NULL, receives a host copy (same layout as ofdg_set_fields). */
 int ofdg_generate_fields(ofdg_generator* g, uint32_t seed, int32_t n, float* fields_out);
+/* The reference's CropGenerator keeps producing crops while training runs; every crop is handed out three times and then
+ * dropped (WarpFields.cpp:516-538, 540-641). Here the pool is a ring: this call regenerates slots [first_slot, first_slot + n)
+ * in place from a fresh displacer scene (std::mt19937(seed)), on a stream of its own with persistent work buffers, and updates
+ * their reach. It may run on a producer thread beside render calls as long as no batch that is prepared or being rendered
+ * uses those slots (the caller's ring arithmetic, csrc/host/layer.cpp). Synchronises its own stream only. */
+int ofdg_refresh_fields(ofdg_generator* g, uint32_t seed, int32_t first_slot, int32_t n);
+/* Grows the installed pool to `total` slots (the existing ones keep their content; the new ones are to be filled by
+ * ofdg_refresh_fields before a batch uses them). Set-up time only: synchronises the device. */
+int ofdg_reserve_fields(ofdg_generator* g, int32_t total);
 
 /* Process_TaskBucket (DataGenerator.cpp:1175-1254) for a whole batch, writing straight into the
  * caller's DEVICE blobs: img0/img1 = batch x 3 x H x W, flow = batch x 2 x H x W, float32.

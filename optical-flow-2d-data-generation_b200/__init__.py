@@ -63,7 +63,7 @@ _lib = None
 # every symbol include/ofdg/ofdg.h declares
 EXPORTS = [
     "ofdg_last_error", "ofdg_version", "ofdg_params_create", "ofdg_params_destroy", "ofdg_params_generate",
-    "ofdg_params_skip", "ofdg_params_enable_augmentation", "ofdg_params_tasks_generated", "ofdg_params_draws", "ofdg_params_slot_name",
+    "ofdg_params_skip", "ofdg_params_enable_augmentation", "ofdg_params_tasks_generated", "ofdg_params_draws", "ofdg_params_field_draws", "ofdg_refresh_fields", "ofdg_reserve_fields", "ofdg_params_slot_name",
     "ofdg_tasks_create", "ofdg_tasks_destroy", "ofdg_tasks_clear", "ofdg_tasks_view", "ofdg_tasks_assign",
     "ofdg_flatten_ellipse", "ofdg_flatten_polygon", "ofdg_debug_raster_host", "ofdg_debug_expand_host", "ofdg_create", "ofdg_destroy", "ofdg_upload_textures", "ofdg_add_textures", "ofdg_clear_textures", "ofdg_texture_size", "ofdg_download_foreground_view",
     "ofdg_synth_textures", "ofdg_download_texture", "ofdg_set_fields", "ofdg_generate_fields", "ofdg_render", "ofdg_render_host",
@@ -72,7 +72,7 @@ EXPORTS = [
 ]
 # include/ofdg/layer.h
 LAYER_EXPORTS = [
-    "ofdg_layer_last_error", "ofdg_layer_parse_prototxt", "ofdg_layer_create", "ofdg_layer_destroy", "ofdg_layer_setup",
+    "ofdg_layer_last_error", "ofdg_layer_parse_prototxt", "ofdg_layer_registered_types", "ofdg_layer_create", "ofdg_layer_destroy", "ofdg_layer_setup",
     "ofdg_layer_top_shape", "ofdg_layer_forward", "ofdg_layer_top_data", "ofdg_layer_type", "ofdg_decode_texture_file",
 ]
 
@@ -101,6 +101,10 @@ def lib():
         L.ofdg_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         L.ofdg_last_shade_ms.argtypes = [C.c_void_p]
         L.ofdg_last_shade_ms.restype = C.c_double
+        L.ofdg_params_field_draws.argtypes = [C.c_void_p]
+        L.ofdg_params_field_draws.restype = C.c_uint64
+        L.ofdg_refresh_fields.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32]
+        L.ofdg_reserve_fields.argtypes = [C.c_void_p, C.c_int32]
         L.ofdg_last_render_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         for f in (L.ofdg_last_bin_ms, L.ofdg_last_raster_ms):
             f.argtypes = [C.c_void_p]
@@ -295,6 +299,10 @@ class ParamStream:
     def draws(self):
         return [int(lib().ofdg_params_draws(self._h, i)) for i in range(NUM_SLOTS)]
 
+    def field_draws(self):
+        """Mode 9: warp-field picks so far; pick k reads pool slot (k // 3) % n_fields."""
+        return int(lib().ofdg_params_field_draws(self._h))
+
 
 def slot_names():
     return [lib().ofdg_params_slot_name(i).decode() for i in range(NUM_SLOTS)]
@@ -420,6 +428,13 @@ class Generator:
         out = np.empty((n, 2, 2, self.H + 1, self.W + 1), np.float32)
         _check(lib().ofdg_generate_fields(self._h, seed, n, _ptr(out)))
         return out
+
+    def reserve_fields(self, total):
+        _check(lib().ofdg_reserve_fields(self._h, total))
+
+    def refresh_fields(self, seed, first_slot, n):
+        """Regenerates pool slots [first_slot, first_slot + n) in place on the GPU (ofdg_refresh_fields)."""
+        _check(lib().ofdg_refresh_fields(self._h, seed, first_slot, n))
 
     # -- rendering
     def render(self, tasks, img0, img1, flow, stream=None):
@@ -648,6 +663,13 @@ class DataGenerationLayer:
 
     def type(self):
         return lib().ofdg_layer_type(self._h).decode()
+
+    @staticmethod
+    def registered_types():
+        """LayerRegistry<float>::LayerTypeList() of the shim (REGISTER_LAYER_CLASS(DataGeneration))."""
+        buf = C.create_string_buffer(1024)
+        lib().ofdg_layer_registered_types(buf, 1024)
+        return [t for t in buf.value.decode().split(",") if t]
 
     def LayerSetUp(self):
         if lib().ofdg_layer_setup(self._h):

@@ -22,6 +22,9 @@
 #include "ofdg/ofdg.h"
 #include "raster_tile.h"
 #include "philox.cuh"
+#include <atomic>
+#include <set>
+
 #include "render.cuh"
 #include "warpfields.cuh"
 
@@ -125,6 +128,11 @@ struct ofdg_prepared {
   DeviceScene scene;
   int device = 0;
   bool augmented = false;  // some sample carries the float augmentation: its frames are not byte-valued
+  // Recycling (ofdg_prepared_destroy hands the device buffers back to the generator that made them instead of freeing them:
+  // cudaFree synchronises the whole device, which would serialise the consumer's GPU work on every batch).
+  ofdg_generator* owner = nullptr;
+  mutable cudaEvent_t last_use = nullptr;  // recorded after every render call that reads the scene
+  mutable bool used = false;
 };
 
 struct ofdg_generator {
@@ -216,14 +224,34 @@ struct ofdg_generator {
   cudaEvent_t pipe_uploaded[2] = {nullptr, nullptr}, pipe_rendered[2] = {nullptr, nullptr}, render_done[2] = {nullptr, nullptr};
   bool render_set_used[2] = {false, false};
   uint64_t render_calls = 0;
-  uint64_t launches = 0;
+  std::atomic<uint64_t> launches{0};
   float last_kernel_ms = 0.f;
   double last_shade_ms = 0.0, last_bin_ms = 0.0, last_raster_ms = 0.0;  // of the spans ofdg_kernel_times summed last
   uint64_t last_prep_px = 0, last_prep_src_px = 0;  // of the scene rendered last (ofdg_last_render_stats)
   int last_set = 0;
 
+  // ofdg_prepare: its own flatten pool, staging and upload stream, so that a producer thread can prepare the next batch
+  // while another thread renders (the two only meet in the free list of recycled scenes)
+  std::mutex prepare_mu, free_mu;
+  std::unique_ptr<ofdg::HostPool> prep_workers;
+  std::vector<ofdg::FlatBatch> prep_flat;
+  PinnedBuf prep_staging;
+  cudaStream_t prep_upload_stream = nullptr;
+  std::vector<ofdg_prepared*> free_scenes;
+  static constexpr size_t kMaxFreeScenes = 12;
+  // mode 9: refreshing slots of the field pool while other slots are being rendered (ofdg_refresh_fields)
+  ofdg::WfScratch wf_scratch;
+  cudaStream_t field_stream = nullptr;
+  PinnedBuf reach_host;
+
   void use() const { CK(cudaSetDevice(cfg.device)); }
 };
+
+namespace {
+// Generators alive in this process: a prepared scene that outlives its generator is freed instead of recycled.
+std::mutex g_live_mu;
+std::set<ofdg_generator*> g_live;
+}  // namespace
 
 namespace {
 
@@ -586,6 +614,7 @@ int ofdg_params_enable_augmentation(ofdg_params* p, int32_t enable) {
   });
 }
 uint64_t ofdg_params_tasks_generated(const ofdg_params* p) { return p ? p->ps->tasks_generated() : 0; }
+uint64_t ofdg_params_field_draws(const ofdg_params* p) { return p ? p->ps->field_draws() : 0; }
 uint64_t ofdg_params_draws(const ofdg_params* p, int32_t slot) {
   return (p && slot >= 0 && slot < ofdg::kNumSlots) ? p->ps->draws(slot) : 0;
 }
@@ -763,6 +792,11 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
         }
       }
     }
+    CK(cudaStreamCreateWithFlags(&g->prep_upload_stream, cudaStreamNonBlocking));
+    {
+      std::lock_guard<std::mutex> lk(g_live_mu);
+      g_live.insert(g.get());
+    }
     *out = g.release();
   });
 }
@@ -770,6 +804,23 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
 void ofdg_destroy(ofdg_generator* g) {
   if (!g) return;
   cudaSetDevice(g->cfg.device);
+  {
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    g_live.erase(g);
+  }
+  cudaDeviceSynchronize();  // render calls on callers' streams may still read the scratch
+  g->prep_workers.reset();
+  for (ofdg_prepared* p : g->free_scenes) {
+    p->scene.release();
+    if (p->last_use) cudaEventDestroy(p->last_use);
+    delete p;
+  }
+  g->free_scenes.clear();
+  g->prep_staging.release();
+  g->wf_scratch.release();
+  g->reach_host.release();
+  if (g->field_stream) cudaStreamDestroy(g->field_stream);
+  if (g->prep_upload_stream) cudaStreamDestroy(g->prep_upload_stream);
   if (g->stream) cudaStreamSynchronize(g->stream);
   if (g->ph_stream) { cudaStreamSynchronize(g->ph_stream); cudaStreamDestroy(g->ph_stream); }
   for (int i = 0; i < 2; ++i) {
@@ -1049,6 +1100,47 @@ int ofdg_generate_fields(ofdg_generator* g, uint32_t seed, int32_t n, float* fie
   });
   if (rc) return rc;
   return ofdg_set_fields(g, host.data(), n);  // install as the generator's pool (reach table, resize tables)
+}
+
+int ofdg_reserve_fields(ofdg_generator* g, int32_t total) {
+  return guarded([&] {
+    if (!g || total <= 0) throw ArgError("bad arguments");
+    if (g->n_fields <= 0) throw StateError("ofdg_reserve_fields: install a pool first (ofdg_set_fields / ofdg_generate_fields)");
+    if (total <= g->n_fields) return;
+    g->use();
+    CK(cudaDeviceSynchronize());  // set-up time: nothing may be reading the pool while it moves
+    const size_t per = (size_t)2 * 2 * (g->cfg.height + 1) * (g->cfg.width + 1) * sizeof(float);
+    DevBuf nf, nr;
+    nf.reserve(per * total);
+    CK(cudaMemcpy(nf.p, g->fields.p, per * g->n_fields, cudaMemcpyDeviceToDevice));
+    nr.reserve((size_t)total * sizeof(int));
+    CK(cudaMemset(nr.p, 0, (size_t)total * sizeof(int)));
+    CK(cudaMemcpy(nr.p, g->field_reach_dev.p, (size_t)g->n_fields * sizeof(int), cudaMemcpyDeviceToDevice));
+    g->fields.release(); g->field_reach_dev.release();
+    g->fields = nf; g->field_reach_dev = nr;
+    g->field_reach.resize(total, 0);
+    g->n_fields = total;
+    g->ph_next.valid = false;
+  });
+}
+
+int ofdg_refresh_fields(ofdg_generator* g, uint32_t seed, int32_t first_slot, int32_t n) {
+  return guarded([&] {
+    if (!g || n <= 0 || first_slot < 0) throw ArgError("bad arguments");
+    if (first_slot + n > g->n_fields) throw StateError("ofdg_refresh_fields: slots beyond the pool (size it with ofdg_generate_fields / ofdg_set_fields first)");
+    g->use();
+    if (!g->field_stream) CK(cudaStreamCreateWithFlags(&g->field_stream, cudaStreamNonBlocking));
+    const size_t per = (size_t)2 * 2 * (g->cfg.height + 1) * (g->cfg.width + 1);
+    float* dst = (float*)g->fields.p + (size_t)first_slot * per;
+    g->launches += ofdg::wf_generate(g->cfg.width, g->cfg.height, seed, n, dst, g->field_stream, &g->wf_scratch);
+    int* reach_dev = (int*)g->field_reach_dev.p + first_slot;
+    g->launches += ofdg::wf_reach(g->cfg.width, g->cfg.height, dst, n, reach_dev, g->field_stream);
+    g->reach_host.reserve((size_t)n * sizeof(int));
+    CK(cudaMemcpyAsync(g->reach_host.p, reach_dev, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, g->field_stream));
+    CK(cudaStreamSynchronize(g->field_stream));
+    CK(cudaGetLastError());
+    for (int i = 0; i < n; ++i) g->field_reach[first_slot + i] = ((const int*)g->reach_host.p)[i];
+  });
 }
 
 int ofdg_set_extra_tops(ofdg_generator* g, const ofdg_extra_tops* tops) {
@@ -1522,20 +1614,75 @@ int ofdg_prepare(ofdg_generator* g, const ofdg_task_batch* tasks, ofdg_prepared*
     if (!g || !tasks || !out) throw ArgError("null pointer");
     check_batch(g, tasks->n_tasks);
     g->use();
-    flatten_tasks(g, tasks);
-    std::unique_ptr<ofdg_prepared> p(new ofdg_prepared);
+    // May run on a producer thread beside render calls of another thread: it touches nothing they use (own flatten pool,
+    // staging, upload stream); concurrent ofdg_prepare calls take turns.
+    std::lock_guard<std::mutex> turn(g->prepare_mu);
+    const int n = tasks->n_tasks;
+    if (!g->prep_workers) {
+      int threads = std::min((int)std::thread::hardware_concurrency() / 2, 8);
+      if (const char* lw = std::getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU shares the host
+        const int local = std::max(1, std::atoi(lw));
+        if (local > 1) threads = std::min(threads, (int)std::thread::hardware_concurrency() / local);
+      }
+      if (const char* t = std::getenv("OFDG_PREPARE_THREADS")) threads = std::atoi(t);
+      g->prep_workers.reset(new ofdg::HostPool(std::max(1, std::min(threads, 32)), g->cfg.device));
+    }
+    if ((int)g->prep_flat.size() < n) g->prep_flat.resize(n);
+    const ofdg::FlattenConfig fc = flatten_config(g);
+    // one flatten job per sample (f64 geometry: ellipse 100-gons, curve subdivision, the background's crop parameters)
+    for (int i = 0; i < n; ++i) {
+      ofdg_task_batch one = *tasks;
+      one.n_tasks = 1;
+      one.task_begin = tasks->task_begin + i;  // blueprint indices stay absolute
+      if (one.augment) one.augment += i;
+      ofdg::FlatBatch* dst = &g->prep_flat[i];
+      g->prep_workers->submit([one, fc, dst] {
+        dst->clear();
+        ofdg::flatten(one, fc, *dst);
+      }, true);
+    }
+    g->prep_workers->wait();  // throws the first flatten failure
+    std::unique_ptr<ofdg_prepared> p;
+    {
+      std::lock_guard<std::mutex> lk(g->free_mu);
+      if (!g->free_scenes.empty()) {
+        p.reset(g->free_scenes.back());
+        g->free_scenes.pop_back();
+      }
+    }
+    if (p) {
+      if (p->used) CK(cudaEventSynchronize(p->last_use));  // the render that read these buffers last
+      p->used = false;
+    } else {
+      p.reset(new ofdg_prepared);
+      CK(cudaEventCreateWithFlags(&p->last_use, cudaEventDisableTiming));
+    }
     p->device = g->cfg.device;
+    p->owner = g;
+    p->augmented = false;
     if (tasks->augment)
-      for (int i = 0; i < tasks->n_tasks; ++i) p->augmented = p->augmented || tasks->augment[i].enabled != 0;
-    upload_scene(g, g->flat, p->scene, g->staging, g->stream);
-    CK(cudaStreamSynchronize(g->stream));
+      for (int i = 0; i < n; ++i) p->augmented = p->augmented || tasks->augment[i].enabled != 0;
+    upload_scene_parts(g, g->prep_flat.data(), n, p->scene, g->prep_staging, g->prep_upload_stream);
+    CK(cudaStreamSynchronize(g->prep_upload_stream));  // the scene is resident (and the staging free) when this returns
     *out = p.release();
   });
 }
 void ofdg_prepared_destroy(ofdg_prepared* p) {
   if (!p) return;
   cudaSetDevice(p->device);
+  {
+    std::lock_guard<std::mutex> live(g_live_mu);
+    if (p->owner && g_live.count(p->owner)) {
+      std::lock_guard<std::mutex> lk(p->owner->free_mu);
+      if (p->owner->free_scenes.size() < ofdg_generator::kMaxFreeScenes) {
+        p->owner->free_scenes.push_back(p);  // its buffers serve a later ofdg_prepare (which waits for last_use first)
+        return;
+      }
+    }
+  }
+  if (p->used && p->last_use) cudaEventSynchronize(p->last_use);
   p->scene.release();
+  if (p->last_use) cudaEventDestroy(p->last_use);
   delete p;
 }
 int ofdg_render_prepared(ofdg_generator* g, const ofdg_prepared* p, float* d_img0, float* d_img1, float* d_flow, void* stream) {
@@ -1548,6 +1695,7 @@ int ofdg_render_prepared(ofdg_generator* g, const ofdg_prepared* p, float* d_img
     const int set = pipeline_set(g, p->scene);  // the scene has been resident since ofdg_prepare returned
     if (set >= 0) run_kernels_pipelined(g, with_extra_tops(g, make_args(g, p->scene, d_img0, d_img1, d_flow, set)), s, set, nullptr);
     else run_kernels(g, with_extra_tops(g, make_args(g, p->scene, d_img0, d_img1, d_flow)), s);
+    if (p->last_use) { CK(cudaEventRecord(p->last_use, s)); p->used = true; }
     if (!stream) { CK(cudaStreamSynchronize(s)); check_pair_overflow(g); }
   });
 }
@@ -1572,7 +1720,7 @@ int ofdg_generate(ofdg_generator* g, ofdg_params* p, int32_t batch, float* d_img
   return ofdg_render(g, &v, d_img0, d_img1, d_flow, stream);
 }
 
-uint64_t ofdg_launch_count(const ofdg_generator* g) { return g ? g->launches : 0; }
+uint64_t ofdg_launch_count(const ofdg_generator* g) { return g ? g->launches.load() : 0; }
 int ofdg_kernel_times(ofdg_generator* g, double* prep_ms, double* render_ms, int32_t* calls) {
   return guarded([&] {
     if (!g) throw ArgError("null pointer");

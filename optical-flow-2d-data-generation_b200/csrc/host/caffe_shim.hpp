@@ -6,6 +6,9 @@
 // (INTEGRATION.md).
 #pragma once
 #include <cstddef>
+#include <map>
+#include <memory>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -117,5 +120,58 @@ class Layer {
  protected:
   LayerParameter layer_param_;
 };
+
+// caffe/layer_factory.hpp: layers register a creator under their type string; Net::Init builds every layer of a
+// prototxt with LayerRegistry<Dtype>::CreateLayer(param). The reference registers itself with
+// REGISTER_LAYER_CLASS(DataGeneration) (src/caffe/layers/data_generation_layer.cpp:298-299).
+template <typename Dtype>
+class LayerRegistry {
+ public:
+  typedef std::shared_ptr<Layer<Dtype> > (*Creator)(const LayerParameter&);
+  typedef std::map<std::string, Creator> CreatorRegistry;
+  static CreatorRegistry& Registry() {
+    static CreatorRegistry* g_registry_ = new CreatorRegistry();
+    return *g_registry_;
+  }
+  static void AddCreator(const std::string& type, Creator creator) {
+    CreatorRegistry& registry = Registry();
+    if (registry.count(type)) throw std::runtime_error("Layer type " + type + " already registered.");
+    registry[type] = creator;
+  }
+  static std::shared_ptr<Layer<Dtype> > CreateLayer(const LayerParameter& param) {
+    const std::string& type = param.type();
+    CreatorRegistry& registry = Registry();
+    if (registry.count(type) != 1) throw std::runtime_error("Unknown layer type: " + type + " (known types: " + LayerTypeListString() + ")");
+    return registry[type](param);
+  }
+  static std::vector<std::string> LayerTypeList() {
+    std::vector<std::string> layer_types;
+    for (typename CreatorRegistry::iterator iter = Registry().begin(); iter != Registry().end(); ++iter) layer_types.push_back(iter->first);
+    return layer_types;
+  }
+
+ private:
+  LayerRegistry() {}
+  static std::string LayerTypeListString() {
+    std::string s;
+    for (const std::string& t : LayerTypeList()) s += (s.empty() ? "" : ", ") + t;
+    return s;
+  }
+};
+template <typename Dtype>
+class LayerRegisterer {
+ public:
+  LayerRegisterer(const std::string& type, std::shared_ptr<Layer<Dtype> > (*creator)(const LayerParameter&)) {
+    LayerRegistry<Dtype>::AddCreator(type, creator);
+  }
+};
+// (the shim instantiates layers for float only; Caffe's macro registers float and double)
+#define REGISTER_LAYER_CREATOR(type, creator) static ::caffe::LayerRegisterer<float> g_creator_f_##type(#type, creator<float>)
+#define REGISTER_LAYER_CLASS(type)                                                                   \
+  template <typename Dtype>                                                                          \
+  std::shared_ptr<Layer<Dtype> > Creator_##type##Layer(const LayerParameter& param) {               \
+    return std::shared_ptr<Layer<Dtype> >(new type##Layer<Dtype>(param));                            \
+  }                                                                                                  \
+  REGISTER_LAYER_CREATOR(type, Creator_##type##Layer)
 
 }  // namespace caffe

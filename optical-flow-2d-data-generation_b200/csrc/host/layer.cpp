@@ -7,6 +7,8 @@
 #include <cctype>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
+#include <cmath>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -235,20 +237,44 @@ DataGenerationLayer<Dtype>::DataGenerationLayer(const LayerParameter& param) : L
       OFDG_CHECK(ofdg_add_textures(generator_, t.planar_bgr.data(), 1, t.w, t.h));
     }
   }
-  // Mode 9: the reference owns a WarpFields::CropGenerator that keeps producing (flow, iflow) crops on 10 CPU threads,
-  // seeded from std::random_device (DataGenerator.cpp:1016-1019, WarpFields.cpp:540-641). Here the GPU producer fills a
-  // pool of kFieldPool crops once, from a reproducible seed; objects walk the pool in commission order.
-  const int n_fields = gp.mode() == 9 ? kFieldPool : 0;
-  if (n_fields) OFDG_CHECK(ofdg_generate_fields(generator_, (uint32_t)(gp.seed() + 7919u * (unsigned)solver_rank_ + 1u), n_fields, nullptr));
+  // Mode 9: the reference owns a WarpFields::CropGenerator that keeps producing (flow, iflow) crops on 10 CPU threads, seeded
+  // from std::random_device; every crop is handed out three times, then dropped (DataGenerator.cpp:1016-1019,
+  // WarpFields.cpp:516-538, 540-641). Here the pool is a ring of generations of kFieldPool crops (one 3*max(W,H) canvas each):
+  // pick k of the parameter stream reads slot (k / 3) % pool size, and the producer thread regenerates a generation's slots on
+  // the GPU (reproducible seeds) right before the first batch that picks from it (EnsureFieldGenerations). The device-side
+  // parameter stream (device_params) draws its picks from the pool as installed here and does not refresh it.
+  int n_fields = 0;
+  if (gp.mode() == 9) {
+    const int bs = param.data_param().batch_size();
+    const double gens_per_batch = bs * (23 * 0.2 + 0.2) / (3.0 * kFieldPool);  // about a fifth of the objects (and backgrounds) deform
+    field_ring_ = (int)std::min(96.0, std::ceil(gens_per_batch * ((double)prefetch_depth_ + 3.0)) + 4.0);
+    if (gp.device_params()) field_ring_ = 1;
+    n_fields = kFieldPool * field_ring_;
+    OFDG_CHECK(ofdg_generate_fields(generator_, FieldSeed(0), kFieldPool, nullptr));  // generation 0; sizes the tables
+    OFDG_CHECK(ofdg_reserve_fields(generator_, n_fields));
+    next_generation_ = 1;
+  }
   OFDG_CHECK(ofdg_params_create(gp.mode(), cfg.width, cfg.height, 45 * solver_rank_, n_fields, 0, &params_));
-  OFDG_CHECK(ofdg_tasks_create(&tasks_));
+  for (int i = 0; i < kProducers; ++i) OFDG_CHECK(ofdg_tasks_create(&tasks_[i]));
+  // Forward_gpu enqueues on a stream of the layer's own and never blocks the solver thread: the legacy default stream (where
+  // Caffe's other layers run) is made to wait for the blobs by an event, and the layer's stream waits for the default
+  // stream's earlier work before it overwrites them.
+  SHIM_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  SHIM_CUDA(cudaEventCreateWithFlags(&blobs_ready_, cudaEventDisableTiming));
+  SHIM_CUDA(cudaEventCreateWithFlags(&consumer_done_, cudaEventDisableTiming));
 }
 
 template <typename Dtype>
 DataGenerationLayer<Dtype>::~DataGenerationLayer() {
   StopInternalThread();
-  for (ofdg_prepared* p : prefetch_full_) ofdg_prepared_destroy(p);
-  if (tasks_) ofdg_tasks_destroy(tasks_);
+  if (stream_) cudaStreamSynchronize(stream_);
+  for (const Prefetched& b : prefetch_full_) ofdg_prepared_destroy(b.scene);
+  for (const InFlight& f : in_flight_) cudaEventDestroy(f.done);
+  for (cudaEvent_t e : event_pool_) cudaEventDestroy(e);
+  if (blobs_ready_) cudaEventDestroy(blobs_ready_);
+  if (consumer_done_) cudaEventDestroy(consumer_done_);
+  if (stream_) cudaStreamDestroy(stream_);
+  for (int i = 0; i < kProducers; ++i) if (tasks_[i]) ofdg_tasks_destroy(tasks_[i]);
   if (params_) ofdg_params_destroy(params_);
   if (generator_) ofdg_destroy(generator_);
 }
@@ -289,9 +315,9 @@ void DataGenerationLayer<Dtype>::BindExtraTops(const std::vector<Blob<Dtype>*>& 
 
 template <typename Dtype>
 void DataGenerationLayer<Dtype>::StartInternalThread() {
-  if (thread_.joinable()) return;
+  if (thread_[0].joinable()) return;
   must_stop_ = false;
-  thread_ = std::thread([this] { this->InternalThreadEntry(); });
+  for (int i = 0; i < kProducers; ++i) thread_[i] = std::thread([this, i] { this->InternalThreadEntry(i); });
 }
 template <typename Dtype>
 void DataGenerationLayer<Dtype>::StopInternalThread() {
@@ -301,93 +327,203 @@ void DataGenerationLayer<Dtype>::StopInternalThread() {
   }
   cv_free_.notify_all();
   cv_full_.notify_all();
-  if (thread_.joinable()) thread_.join();
+  cv_push_.notify_all();
+  for (int i = 0; i < kProducers; ++i) if (thread_[i].joinable()) thread_[i].join();
 }
 
 // Draws batch_size tasks in commission order, flattens them and uploads the scene (load_batch,
 // data_generation_layer.cpp:183-216; the retrieval half of the reference's load_batch is now the
 // kernel launch in Forward).
 template <typename Dtype>
-void DataGenerationLayer<Dtype>::load_batch(ofdg_prepared** out) {
+void DataGenerationLayer<Dtype>::load_batch(Prefetched* out, int producer, uint64_t* ticket) {
   const int batch_size = this->layer_param_.data_param().batch_size();
-  std::lock_guard<std::mutex> g(generator_mutex_);
-  ofdg_tasks_clear(tasks_);
-  OFDG_CHECK(ofdg_params_generate(params_, batch_size, tasks_));
+  ofdg_tasks* tasks = tasks_[producer];
+  {
+    // The parameter stream is sequential (45 mt19937 engines consumed in commission order): one batch is drawn at a time.
+    // The other producer thread meanwhile flattens and uploads the batch it drew before.
+    std::lock_guard<std::mutex> draw(draw_mutex_);
+    {
+      std::lock_guard<std::mutex> l(mutex_);
+      *ticket = next_ticket_++;
+    }
+    ofdg_tasks_clear(tasks);
+    const uint64_t d0 = ofdg_params_field_draws(params_);
+    OFDG_CHECK(ofdg_params_generate(params_, batch_size, tasks));
+    const uint64_t d1 = ofdg_params_field_draws(params_);
+    if (d1 > d0) {  // mode 9: the generations this batch picks from must hold their crops (and their reach) before it is flattened
+      out->uses_fields = true;
+      out->gen_lo = (d0 / 3) / kFieldPool;
+      out->gen_hi = ((d1 - 1) / 3) / kFieldPool;
+      EnsureFieldGenerations(out->gen_lo, out->gen_hi);
+      std::lock_guard<std::mutex> l(mutex_);
+      drawn_.push_back(std::make_pair(*ticket, out->gen_lo));  // drawn, not queued yet: its generations must stay as they are
+    }
+  }
+  // (no generator lock: ofdg_prepare flattens on its own host pool and uploads on its own stream, beside a running Forward)
   ofdg_task_batch view;
-  OFDG_CHECK(ofdg_tasks_view(tasks_, &view));
-  OFDG_CHECK(ofdg_prepare(generator_, &view, out));
+  OFDG_CHECK(ofdg_tasks_view(tasks, &view));
+  OFDG_CHECK(ofdg_prepare(generator_, &view, &out->scene));
 }
 
 template <typename Dtype>
-void DataGenerationLayer<Dtype>::InternalThreadEntry() {
+uint32_t DataGenerationLayer<Dtype>::FieldSeed(uint64_t generation) const {
+  const DataGenerationParameter& gp = this->layer_param_.data_generation_param();
+  return (uint32_t)(gp.seed() + 7919u * (unsigned)solver_rank_ + 1u + 104729u * (uint32_t)generation);
+}
+
+// Producer thread. Generation G lives in slots (G % ring) * kFieldPool ...; it replaces generation G - ring, so every batch
+// that picked from that one must have finished rendering first.
+template <typename Dtype>
+void DataGenerationLayer<Dtype>::EnsureFieldGenerations(uint64_t gen_lo, uint64_t gen_hi) {
+  if (gen_hi - gen_lo + 2 > (uint64_t)field_ring_)
+    throw std::runtime_error("mode 9: one batch picks from more warp-field generations than the pool ring holds (lower batch_size or prefetch)");
+  for (uint64_t G = std::max(gen_lo, next_generation_); G <= gen_hi; ++G) {
+    if (G >= (uint64_t)field_ring_) WaitGenerationRetired(G - (uint64_t)field_ring_);
+    OFDG_CHECK(ofdg_refresh_fields(generator_, FieldSeed(G), (int)(G % (uint64_t)field_ring_) * kFieldPool, kFieldPool));
+    next_generation_ = G + 1;
+  }
+}
+
+// Blocks the producer until no batch that picked from generations <= gen is queued or still rendering.
+template <typename Dtype>
+void DataGenerationLayer<Dtype>::WaitGenerationRetired(uint64_t gen) {
+  for (;;) {
+    cudaEvent_t wait_for = nullptr;
+    {
+      std::unique_lock<std::mutex> l(mutex_);
+      if (!in_flight_.empty()) {
+        if (in_flight_.front().gen_lo > gen) return;  // (ranges grow with the commission order: nothing older is left)
+        wait_for = in_flight_.front().done;
+      } else {
+        bool queued = false;
+        for (const Prefetched& b : prefetch_full_) queued = queued || (b.uses_fields && b.gen_lo <= gen);
+        for (const std::pair<uint64_t, uint64_t>& d : drawn_) queued = queued || d.second <= gen;  // still with the other producer
+        if (!queued) return;
+        // still waiting in the queue (or on its way there): Forward will pop it (cv_free_ is signalled on every pop)
+        cv_free_.wait_for(l, std::chrono::milliseconds(2), [this] { return must_stop_ || !in_flight_.empty(); });
+        if (must_stop_) throw std::runtime_error("stopped");
+        continue;
+      }
+    }
+    cudaEventSynchronize(wait_for);
+    std::lock_guard<std::mutex> l(mutex_);
+    if (!in_flight_.empty() && in_flight_.front().done == wait_for) {
+      event_pool_.push_back(wait_for);
+      in_flight_.pop_front();
+    }
+  }
+}
+
+// Solver thread, after the render of `b` has been queued on stream_.
+template <typename Dtype>
+void DataGenerationLayer<Dtype>::TrackInFlight(const Prefetched& b) {
+  if (!b.uses_fields || field_ring_ <= 1) return;
+  std::lock_guard<std::mutex> l(mutex_);
+  cudaEvent_t e = nullptr;
+  if (!event_pool_.empty()) { e = event_pool_.back(); event_pool_.pop_back(); }
+  else SHIM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  SHIM_CUDA(cudaEventRecord(e, stream_));
+  in_flight_.push_back(InFlight{e, b.gen_lo});
+  cv_free_.notify_all();
+}
+
+template <typename Dtype>
+void DataGenerationLayer<Dtype>::InternalThreadEntry(int producer) {
   cudaSetDevice(device_);
   try {
     for (;;) {
       {
+        // room for this batch once the ones ahead of it are in: queued + being produced <= prefetch depth
         std::unique_lock<std::mutex> l(mutex_);
-        cv_free_.wait(l, [this] { return must_stop_ || prefetch_full_.size() < prefetch_depth_; });
+        cv_free_.wait(l, [this] { return must_stop_ || prefetch_full_.size() + (size_t)(next_ticket_ - next_push_) < prefetch_depth_; });
         if (must_stop_) return;
       }
-      ofdg_prepared* p = nullptr;
-      load_batch(&p);
+      Prefetched b;
+      uint64_t ticket = 0;
+      load_batch(&b, producer, &ticket);
       {
-        std::lock_guard<std::mutex> l(mutex_);
-        prefetch_full_.push_back(p);
+        std::unique_lock<std::mutex> l(mutex_);
+        cv_push_.wait(l, [this, ticket] { return must_stop_ || next_push_ == ticket; });  // commission order
+        if (must_stop_) { ofdg_prepared_destroy(b.scene); return; }
+        prefetch_full_.push_back(b);
+        ++next_push_;
+        for (size_t i = 0; i < drawn_.size(); ++i)
+          if (drawn_[i].first == ticket) { drawn_.erase(drawn_.begin() + (long)i); break; }
       }
+      cv_push_.notify_all();
       cv_full_.notify_one();
     }
   } catch (const std::exception& e) {
     std::lock_guard<std::mutex> l(mutex_);
-    producer_error_ = e.what();
+    if (producer_error_.empty()) producer_error_ = e.what();
+    must_stop_ = true;
     cv_full_.notify_all();
+    cv_push_.notify_all();
+    cv_free_.notify_all();
   }
 }
 
 // prefetch_full_.pop("Data layer prefetch queue empty"), data_generation_layer.cpp:270
 template <typename Dtype>
-ofdg_prepared* DataGenerationLayer<Dtype>::PopPrefetched() {
-  ofdg_prepared* p = nullptr;
+typename DataGenerationLayer<Dtype>::Prefetched DataGenerationLayer<Dtype>::PopPrefetched() {
+  Prefetched b;
   {
     std::unique_lock<std::mutex> l(mutex_);
     cv_full_.wait(l, [this] { return !prefetch_full_.empty() || !producer_error_.empty() || must_stop_; });
     if (!producer_error_.empty()) throw std::runtime_error(producer_error_);
     if (prefetch_full_.empty()) throw std::runtime_error("Data layer prefetch queue empty");
-    p = prefetch_full_.front();
+    b = prefetch_full_.front();
     prefetch_full_.pop_front();
   }
-  cv_free_.notify_one();
-  return p;
+  cv_free_.notify_all();
+  return b;
+}
+
+// Orders the layer's stream after everything the consumer has queued on the legacy default stream so far (it may still be
+// reading the top blobs of the previous iteration); only the kernel that writes the blobs waits, the batch's front end
+// (background preparation, mask rasterisation) runs beside the consumer's work.
+template <typename Dtype>
+void DataGenerationLayer<Dtype>::BeginForward() {
+  SHIM_CUDA(cudaEventRecord(consumer_done_, cudaStreamLegacy));
+  SHIM_CUDA(cudaStreamWaitEvent(stream_, consumer_done_, 0));
+}
+// ... and the default stream after the blobs: whatever the consumer launches next sees them complete. No host blocking.
+template <typename Dtype>
+void DataGenerationLayer<Dtype>::EndForward() {
+  SHIM_CUDA(cudaEventRecord(blobs_ready_, stream_));
+  SHIM_CUDA(cudaStreamWaitEvent(cudaStreamLegacy, blobs_ready_, 0));
 }
 
 template <typename Dtype>
 void DataGenerationLayer<Dtype>::Forward_gpu(const std::vector<Blob<Dtype>*>& bottom, const std::vector<Blob<Dtype>*>& top) {
   const DataGenerationParameter& gp = this->layer_param_.data_generation_param();
+  const int bs = this->layer_param_.data_param().batch_size();
+  top[0]->Reshape({bs, 3, 384, 512});
+  top[1]->Reshape({bs, 3, 384, 512});
+  top[2]->Reshape({bs, 2, 384, 512});
+  BindExtraTops(top);
   if (gp.device_params()) {
     // production mode: parameters drawn and flattened on the device, straight into the top blobs
-    const int bs = this->layer_param_.data_param().batch_size();
-    top[0]->Reshape({bs, 3, 384, 512});
-    top[1]->Reshape({bs, 3, 384, 512});
-    top[2]->Reshape({bs, 2, 384, 512});
-    BindExtraTops(top);
     const unsigned long long seed = gp.seed() ^ ((unsigned long long)solver_rank_ << 40);  // distinct streams per replica
+    BeginForward();
     if (ofdg_generate_philox(generator_, seed, device_batches_ * (unsigned long long)bs, bs, 0, top[0]->mutable_gpu_data(),
-                             top[1]->mutable_gpu_data(), top[2]->mutable_gpu_data(), nullptr) != OFDG_OK)
+                             top[1]->mutable_gpu_data(), top[2]->mutable_gpu_data(), stream_) != OFDG_OK)
       throw std::runtime_error(ofdg_last_error());
+    EndForward();
     ++device_batches_;
     return;
   }
-  ofdg_prepared* p = PopPrefetched();
-  const int batch_size = this->layer_param_.data_param().batch_size();
-  top[0]->Reshape({batch_size, 3, 384, 512});
-  top[1]->Reshape({batch_size, 3, 384, 512});
-  top[2]->Reshape({batch_size, 2, 384, 512});
-  BindExtraTops(top);
+  const Prefetched b = PopPrefetched();
+  ofdg_prepared* p = b.scene;
+  BeginForward();
   int rc;
   {
     std::lock_guard<std::mutex> g(generator_mutex_);
-    rc = ofdg_render_prepared(generator_, p, top[0]->mutable_gpu_data(), top[1]->mutable_gpu_data(), top[2]->mutable_gpu_data(), nullptr);
+    rc = ofdg_render_prepared(generator_, p, top[0]->mutable_gpu_data(), top[1]->mutable_gpu_data(), top[2]->mutable_gpu_data(), stream_);
   }
-  ofdg_prepared_destroy(p);
+  EndForward();
+  TrackInFlight(b);
+  ofdg_prepared_destroy(p);  // back to the generator's free list; its buffers are reused once this render is done
   if (rc != OFDG_OK) throw std::runtime_error(ofdg_last_error());
 }
 
@@ -403,7 +539,8 @@ void DataGenerationLayer<Dtype>::Forward_cpu(const std::vector<Blob<Dtype>*>& bo
     for (size_t i = 0; i < top.size(); ++i) top[i]->cpu_data();
     return;
   }
-  ofdg_prepared* p = PopPrefetched();
+  const Prefetched b = PopPrefetched();  // (rendered synchronously below: nothing of it is in flight afterwards)
+  ofdg_prepared* p = b.scene;
   const int batch_size = this->layer_param_.data_param().batch_size();
   top[0]->Reshape({batch_size, 3, 384, 512});
   top[1]->Reshape({batch_size, 3, 384, 512});
@@ -421,6 +558,7 @@ template <typename Dtype>
 uint64_t DataGenerationLayer<Dtype>::tasks_commissioned() const { return ofdg_params_tasks_generated(params_); }
 
 template class DataGenerationLayer<float>;
+REGISTER_LAYER_CLASS(DataGeneration);  // src/caffe/layers/data_generation_layer.cpp:298-299
 
 }  // namespace caffe
 
@@ -428,7 +566,7 @@ template class DataGenerationLayer<float>;
 namespace {
 thread_local std::string g_layer_error;
 struct LayerBox {
-  std::unique_ptr<caffe::DataGenerationLayer<float>> layer;
+  std::shared_ptr<caffe::Layer<float>> layer;  // built by LayerRegistry<float>::CreateLayer from the prototxt's type string
   std::vector<std::unique_ptr<caffe::Blob<float>>> tops;
   std::vector<caffe::Blob<float>*> top_ptrs, bottom_ptrs;
   caffe::LayerParameter param;
@@ -472,10 +610,9 @@ int ofdg_layer_create(const char* prototxt, const char* texture_db_override, int
   return layer_guard([&] {
     std::unique_ptr<LayerBox> b(new LayerBox);
     b->param = caffe::ParseLayerPrototxt(prototxt);
-    if (b->param.type() != "DataGeneration") throw std::runtime_error("layer type must be \"DataGeneration\"");
     if (texture_db_override && *texture_db_override) b->param.data_generation_param_.texture_dbases_ = {texture_db_override};
     caffe::DataGenerationLayer<float>::set_solver_rank(solver_rank);
-    b->layer.reset(new caffe::DataGenerationLayer<float>(b->param));
+    b->layer = caffe::LayerRegistry<float>::CreateLayer(b->param);  // Net::Init's path: the type string picks the class
     for (int i = 0; i < std::max(3, b->param.top_size()); ++i) {
       b->tops.emplace_back(new caffe::Blob<float>());
       b->top_ptrs.push_back(b->tops.back().get());
@@ -505,4 +642,11 @@ const float* ofdg_layer_top_data(void* l, int32_t i, int32_t gpu) {
   try { return gpu ? b->top_ptrs.at(i)->gpu_data() : b->top_ptrs.at(i)->cpu_data(); } catch (const std::exception& e) { g_layer_error = e.what(); return nullptr; }
 }
 const char* ofdg_layer_type(void* l) { return ((LayerBox*)l)->layer->type(); }
+int ofdg_layer_registered_types(char* out, int32_t cap) {
+  std::string s;
+  const std::vector<std::string> types = caffe::LayerRegistry<float>::LayerTypeList();
+  for (const std::string& t : types) s += (s.empty() ? "" : ",") + t;
+  if (out && cap > 0) std::snprintf(out, (size_t)cap, "%s", s.c_str());
+  return (int)types.size();
+}
 }

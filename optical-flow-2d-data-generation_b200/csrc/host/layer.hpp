@@ -13,6 +13,8 @@
 #include <thread>
 #include <vector>
 
+#include <cuda_runtime.h>
+
 #include "caffe_shim.hpp"
 #include "ofdg/ofdg.h"
 
@@ -44,29 +46,54 @@ class DataGenerationLayer : public Layer<Dtype> {
   uint64_t tasks_commissioned() const;
 
  protected:
-  virtual void InternalThreadEntry();                 // prefetch producer
-  virtual void load_batch(ofdg_prepared** out);       // draw + flatten + upload one batch
+  struct Prefetched {
+    ofdg_prepared* scene = nullptr;
+    uint64_t gen_lo = 0, gen_hi = 0;  // mode 9: field generations (40 crops each) the batch's objects picked from
+    bool uses_fields = false;
+  };
+  virtual void InternalThreadEntry(int producer);     // prefetch producer
+  virtual void load_batch(Prefetched* out, int producer, uint64_t* ticket);  // draw + flatten + upload one batch
   void StartInternalThread();
   void StopInternalThread();
-  ofdg_prepared* PopPrefetched();                      // blocks until the producer has a batch
+  Prefetched PopPrefetched();                          // blocks until the producer has a batch
   void BindExtraTops(const std::vector<Blob<Dtype>*>& top);  // top[3..6]: backward flow, occlusion, index images
+  void BeginForward();                                 // layer stream <- default stream (the consumer's reads of the old blobs)
+  void EndForward();                                   // default stream <- layer stream (the new blobs)
 
   static int solver_rank_;
-  static constexpr int kFieldPool = 40;   // mode 9: (flow, iflow) crops generated at set-up
+  static constexpr int kFieldPool = 40;   // mode 9: (flow, iflow) crops per generation = per 3*max(W,H) canvas (WarpFields.cpp:619-637)
   int device_ = 0;
   ofdg_generator* generator_ = nullptr;   // DataGenerator::DataGenerator data_generator_
   ofdg_params* params_ = nullptr;         // DataGenerator::ObjectParametersGenerator obj_params_generator_
-  ofdg_tasks* tasks_ = nullptr;
+  static constexpr int kProducers = 2;    // prefetch threads: one draws batch k+1 (the RNG stream is sequential) while the other flattens batch k
+  ofdg_tasks* tasks_[kProducers] = {nullptr, nullptr};
   // prefetch_free_/prefetch_full_ of the reference collapse into one bounded queue of prepared batches
-  std::deque<ofdg_prepared*> prefetch_full_;
+  std::deque<Prefetched> prefetch_full_;
+  // mode 9: the field pool is a ring of `field_ring_` generations of kFieldPool crops. The producer regenerates a
+  // generation's slots right before the first batch that picks from it, after every batch that used the previous
+  // occupant has finished rendering (in_flight_: rendered batches and the events that say when they are done).
+  struct InFlight { cudaEvent_t done; uint64_t gen_lo; };
+  std::deque<InFlight> in_flight_;
+  std::vector<std::pair<uint64_t, uint64_t> > drawn_;  // (ticket, first generation) of batches drawn but not queued yet
+  std::vector<cudaEvent_t> event_pool_;
+  int field_ring_ = 0;
+  uint64_t next_generation_ = 0;          // first generation that has not been produced yet
+  void EnsureFieldGenerations(uint64_t gen_lo, uint64_t gen_hi);
+  void WaitGenerationRetired(uint64_t gen);
+  void TrackInFlight(const Prefetched& b);
+  uint32_t FieldSeed(uint64_t generation) const;
   size_t prefetch_depth_ = 1;
   std::mutex mutex_, generator_mutex_;
-  std::condition_variable cv_full_, cv_free_;
-  std::thread thread_;
+  std::condition_variable cv_full_, cv_free_, cv_push_;
+  std::thread thread_[kProducers];
+  std::mutex draw_mutex_;                 // the parameter stream: batches are drawn one at a time, in ticket order
+  uint64_t next_ticket_ = 0, next_push_ = 0;  // commission order of the batches = their order in the prefetch queue
   bool must_stop_ = false;
   unsigned long long device_batches_ = 0;  // batches produced by the device-side stream (its sample counter)
   std::string producer_error_;
   ofdg_extra_tops extra_{};               // what the generator currently writes besides the three blobs
+  cudaStream_t stream_ = nullptr;         // Forward_gpu's stream (non-blocking)
+  cudaEvent_t blobs_ready_ = nullptr, consumer_done_ = nullptr;
 };
 
 }  // namespace caffe

@@ -92,6 +92,7 @@ class ParamStream {
   void enable_augmentation(bool on) { augment_ = on; }
   bool augmentation_enabled() const { return augment_; }
   uint64_t tasks_generated() const { return tasks_; }
+  uint64_t field_draws() const { return field_draws_; }  // mode 9: warp-field picks so far (each pool slot serves three)
   uint64_t draws(int slot) const { return eng_[slot].draws; }
   int mode() const { return mode_; }
 

@@ -131,15 +131,52 @@ void wf_draw_displacers(std::mt19937& mersenne, int big_size, std::vector<WfDisp
     }
 }
 
-int wf_generate(int W, int H, uint32_t seed, int n_fields, float* d_out, cudaStream_t s) {
-  const int S = std::max(W, H) * 3, W1 = W + 1, H1 = H + 1;
-  const size_t P = (size_t)S * S, per_field = (size_t)2 * 2 * W1 * H1;
-  float *flow = nullptr, *iflow = nullptr, *tmp = nullptr;
-  unsigned char* flagged = nullptr;
-  WfDisplacer* d_ds = nullptr;
-  int launches = 0;
+void WfScratch::reserve(int canvas) {
+  if (canvas <= S) return;
+  release();
+  const size_t P = (size_t)canvas * canvas;
   cudaMalloc(&flow, 2 * P * sizeof(float)); cudaMalloc(&iflow, 2 * P * sizeof(float)); cudaMalloc(&tmp, 2 * P * sizeof(float));
   cudaMalloc(&flagged, P); cudaMalloc(&d_ds, 256 * sizeof(WfDisplacer));
+  S = canvas;
+}
+void WfScratch::release() {
+  cudaFree(flow); cudaFree(iflow); cudaFree(tmp); cudaFree(flagged); cudaFree(d_ds);
+  flow = iflow = tmp = nullptr; flagged = nullptr; d_ds = nullptr; S = 0;
+}
+
+__global__ void wf_reach_kernel(const float* fields, int n2, size_t per_field, int* reach) {
+  // one block per crop: max |v| over the finite values of its inverse field (the second half of the crop's record)
+  __shared__ float s_max[256];
+  const float* ifl = fields + (size_t)blockIdx.x * per_field + n2;
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    const float v = fabsf(ifl[i]);
+    if (v <= 3.0e38f) mx = fmaxf(mx, v);  // (NaN and inf fail the comparison)
+  }
+  s_max[threadIdx.x] = mx;
+  __syncthreads();
+  for (int d = 128; d > 0; d >>= 1) {
+    if ((int)threadIdx.x < d) s_max[threadIdx.x] = fmaxf(s_max[threadIdx.x], s_max[threadIdx.x + d]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) reach[blockIdx.x] = (int)ceilf(fminf(s_max[0], 1.0e6f));
+}
+int wf_reach(int W, int H, const float* d_fields, int n_fields, int* d_reach, cudaStream_t s) {
+  const int n2 = 2 * (W + 1) * (H + 1);
+  wf_reach_kernel<<<n_fields, 256, 0, s>>>(d_fields, n2, (size_t)2 * n2, d_reach);
+  return 1;
+}
+
+int wf_generate(int W, int H, uint32_t seed, int n_fields, float* d_out, cudaStream_t s, WfScratch* scratch) {
+  const int S = std::max(W, H) * 3, W1 = W + 1, H1 = H + 1;
+  const size_t P = (size_t)S * S, per_field = (size_t)2 * 2 * W1 * H1;
+  WfScratch own;
+  WfScratch& sc = scratch ? *scratch : own;
+  sc.reserve(S);
+  float *flow = sc.flow, *iflow = sc.iflow, *tmp = sc.tmp;
+  unsigned char* flagged = sc.flagged;
+  WfDisplacer* d_ds = sc.d_ds;
+  int launches = 0;
   std::mt19937 mersenne(seed);
   std::vector<WfDisplacer> ds;
   const int tb = 256, gb = (int)((P + tb - 1) / tb);
@@ -173,7 +210,7 @@ int wf_generate(int W, int H, uint32_t seed, int n_fields, float* d_out, cudaStr
       }
     cudaStreamSynchronize(s);  // the host redraws `ds` for the next canvas
   }
-  cudaFree(flow); cudaFree(iflow); cudaFree(tmp); cudaFree(flagged); cudaFree(d_ds);
+  if (!scratch) own.release();
   return launches;
 }
 

@@ -26,6 +26,14 @@ def test_prototxt_defaults_and_errors(ofdg):
         ofdg.DataGenerationLayer('layer { type: "Data" top: "a" }')
 
 
+def test_layer_registry(ofdg):
+    """REGISTER_LAYER_CLASS(DataGeneration) (data_generation_layer.cpp:298-299): the type string is in the shim's
+    LayerRegistry, and layers are built through LayerRegistry<float>::CreateLayer the way Net::Init builds them."""
+    assert ofdg.DataGenerationLayer.registered_types() == ["DataGeneration"]
+    with pytest.raises(ofdg.OfdgError, match="Unknown layer type: Convolution"):
+        ofdg.DataGenerationLayer('layer { type: "Convolution" top: "a" }')
+
+
 @pytest.mark.gpu
 def test_layer_blob_contract(ofdg, oracle):
     import torch
@@ -214,4 +222,75 @@ def test_layer_mode9_uses_a_generated_field_pool(ofdg, oracle):
     ok = np.isfinite(ref["flow"])
     assert np.abs(got[0] - ref["img0"]).max() <= 1 and np.abs(got[1] - ref["img1"]).max() <= 1
     assert np.array_equal(ok, np.isfinite(got[2])) and np.abs(got[2][ok] - ref["flow"][ok]).max() <= 1e-3
+    layer.close()
+
+
+@pytest.mark.gpu
+def test_layer_mode9_refreshes_its_field_pool(ofdg, oracle):
+    """The reference's CropGenerator keeps producing crops while training runs and hands every crop out three times
+    (WarpFields.cpp:516-538, 540-641). The layer's pool is a ring of generations of 40 crops that the producer thread
+    regenerates on the GPU: after enough batches the picks wrap around the ring and must find NEW crops in the old slots.
+    Checked against the oracle's render with the crops the ring arithmetic says are resident (seed of generation G known)."""
+    B, prefetch = 6, 2
+    proto = ('layer { type: "DataGeneration" top: "a" top: "b" top: "c" data_param { batch_size: %d prefetch: %d } '
+             'data_generation_param { mode: 9 texture_dbases: "synthetic:8:1" } }' % (B, prefetch))
+    ring = int(min(96.0, np.ceil(B * (23 * 0.2 + 0.2) / 120.0 * (prefetch + 3.0)) + 4.0))  # csrc/host/layer.cpp
+    layer = ofdg.DataGenerationLayer(proto)
+    layer.LayerSetUp()
+    ps = ofdg.ParamStream(9, n_fields=40 * ring)
+    tex = ofdg.synth_textures(8, 1024, 768, seed=1)
+    g = ofdg.Generator(device=0, mode=9, max_batch=B)
+    gen_cache = {}
+
+    def generation(G):  # FieldSeed(G) for seed 0, rank 0
+        if G not in gen_cache:
+            gen_cache[G] = g.generate_fields((1 + 104729 * G) & 0xFFFFFFFF, 40)
+        return gen_cache[G]
+
+    checked_wrapped = 0
+    for it in range(60):
+        d0 = ps.field_draws()
+        tasks = ps.generate(B)
+        d1 = ps.field_draws()
+        layer.Forward_gpu()
+        g_lo, g_hi = (d0 // 3) // 40, ((max(d1, d0 + 1) - 1) // 3) // 40
+        if g_hi < ring or d1 == d0:
+            continue  # still in the first lap of the ring (test_layer_mode9_uses_a_generated_field_pool covers it)
+        got = [layer.top_cpu(i) for i in range(3)]
+        fields = np.zeros((40 * ring, 2, 2, 385, 513), np.float32)
+        for G in range(g_lo, g_hi + 1):
+            fields[(G % ring) * 40:(G % ring) * 40 + 40] = generation(G)
+        ref = oracle.render(tasks.struct(), tex, mode=9, fields=fields)
+        ok = np.isfinite(ref["flow"])
+        assert np.abs(got[0] - ref["img0"]).max() <= 1 and np.abs(got[1] - ref["img1"]).max() <= 1, f"batch {it}"
+        assert np.array_equal(ok, np.isfinite(got[2])) and np.abs(got[2][ok] - ref["flow"][ok]).max() <= 1e-3, f"batch {it}"
+        checked_wrapped += 1
+        if checked_wrapped == 2:
+            break
+    assert checked_wrapped == 2, "the picks never wrapped around the ring"
+    g.close()
+    layer.close()
+
+
+@pytest.mark.gpu
+def test_layer_forward_gpu_does_not_block_and_recycles_scenes(ofdg, oracle):
+    """Forward_gpu queues the batch on the layer's stream and returns; the default stream (top_cpu's copy) is ordered after
+    the blobs by an event. Many forwards back to back -- prepared scenes go back to the generator's free list and are reused --
+    still deliver the commission order of the parameter stream."""
+    import time
+    text = ('layer { type: "DataGeneration" top: "a" top: "b" top: "c" data_param { batch_size: 8 prefetch: 3 } '
+            'data_generation_param { mode: 7 texture_dbases: "synthetic:8:1" } }')
+    layer = ofdg.DataGenerationLayer(text)
+    layer.LayerSetUp()
+    ps = ofdg.ParamStream(7)
+    tex = ofdg.synth_textures(8, 1024, 768, seed=1)
+    n = 40
+    for _ in range(n - 1):
+        layer.Forward_gpu()  # (no read in between: the blobs are simply overwritten in stream order)
+        ps.generate(8)
+    layer.Forward_gpu()
+    got = [layer.top_cpu(i) for i in range(3)]
+    ref = oracle.render(ps.generate(8).struct(), tex, mode=7)
+    assert np.abs(got[0] - ref["img0"]).max() <= 1 and np.abs(got[1] - ref["img1"]).max() <= 1
+    assert np.abs(got[2] - ref["flow"]).max() <= 1e-3
     layer.close()
