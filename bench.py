@@ -289,6 +289,84 @@ def attribution_pass(o, args, device, task_sets, img0, img1, flow, stream, steps
     return out
 
 
+def timed_render_leg(o, torch, g, task_sets, B, W, H, stream, steps):
+    """samples/s and ms per step of render_prepared over the given scene batches (CUDA events on the launching stream)."""
+    prepared = [g.prepare(t) for t in task_sets]
+    img0 = torch.empty((B, 3, H, W), device="cuda", dtype=torch.float32)
+    img1 = torch.empty_like(img0)
+    flow = torch.empty((B, 2, H, W), device="cuda", dtype=torch.float32)
+    for i in range(6):
+        g.render_prepared(prepared[i % len(prepared)], img0, img1, flow, stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        g.render_prepared(prepared[i % len(prepared)], img0, img1, flow, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    peak, _ = measured_peak()
+    ab = algo_bytes(W, H) * B
+    del prepared, img0, img1, flow
+    return {"value": B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "batch": B, "steps": steps,
+            "algorithmic_bytes_per_step": ab, "whole_step_achieved_gbs": ab / (ms * 1e-3) / 1e9, "whole_step_frac": ab / (ms * 1e-3) / 1e9 / peak}
+
+
+def other_config_legs(o, torch, args, device, stream):
+    """BASELINE.json configs 3 and 5, device-resident scenes like the headline `value`:
+    config 3 = mode 9 (all shapes, composites, thin objects, non-rigid motion) with a pool of 40 GPU-generated warp fields and the
+    colour/noise augmentation, batch 64; config 5 = 1024 x 768 output, 64 and 128 forced foreground objects per sample,
+    10,000-texture pool (31 GB) resident in HBM, batch 16 (the same 403 MB of blobs per step)."""
+    out = {}
+    steps = max(10, min(args.steps, 100))
+    # ---- config 3
+    g = o.Generator(device=device, width=512, height=384, mode=9, max_batch=64)
+    g.synth_textures(args.textures, 1024, 768, seed=args.seed)
+    g.generate_fields(5, 40)
+    ps = o.ParamStream(9, 512, 384, n_fields=40)
+    ps.enable_augmentation(True)
+    leg = timed_render_leg(o, torch, g, [ps.generate(64) for _ in range(3)], 64, 512, 384, stream, steps)
+    leg["workload"] = f"mode 9 + 40 generated warp fields + colour/noise augmentation, 512x384, batch 64, {args.textures}-texture pool"
+    out["config3"] = leg
+    g.close()
+    # ---- config 5
+    free, _ = torch.cuda.mem_get_info()
+    n_tex = 10000 if free > 60e9 else 1000
+    W5, H5, B5 = 1024, 768, 16
+    g = o.Generator(device=device, width=W5, height=H5, mode=7, max_batch=B5)
+    g.synth_textures(n_tex, 1024, 768, seed=args.seed)
+    for n_obj in (64, 128):
+        ps = o.ParamStream(7, W5, H5, fg_override=n_obj)
+        leg = timed_render_leg(o, torch, g, [ps.generate(B5) for _ in range(3)], B5, W5, H5, stream, max(10, steps // 2))
+        leg["workload"] = (f"mode 7, 1024x768 output, {n_obj} forced foreground objects per sample, batch {B5}, {n_tex} textures of 1024x768 "
+                           f"({n_tex * 1024 * 768 * 4 / 1e9:.1f} GB as RGBX in HBM; smaller than 2W x 2H: the background takes getRandomizedCrop's resize-whole branch)")
+        out[f"config5_{n_obj}_objects"] = leg
+    g.close()
+    return out
+
+
+def host_memory_probe(o, threads=8, mb=96, reps=3):
+    """What the host's memory system sustains for the host-blob path's last stage: `threads` threads widening uint8 -> float32 with
+    non-temporal stores (csrc/host/expand.cpp), GB/s of DRAM traffic (1 byte read + 4 written per element)."""
+    import numpy as np
+    n = mb << 20
+    src = [np.full(n, 7, np.uint8) for _ in range(threads)]
+    dst = [np.empty(n, np.float32) for _ in range(threads)]
+    for i in range(threads):
+        o.expand_host(src[i], dst[i])  # touch the pages
+    best = 0.0
+    for _ in range(reps):
+        ts = [threading.Thread(target=o.expand_host, args=(src[i], dst[i])) for i in range(threads)]
+        t0 = time.time()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        dt = time.time() - t0
+        best = max(best, threads * n * 5 / dt / 1e9)
+    return {"threads": threads, "gbs": best, "what": "uint8 -> float32 widening with non-temporal stores, read + written bytes per second"}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -407,6 +485,10 @@ def run_ours(args):
     checksum = float(h0.mean()) + float(h1.mean()) + float(hf.mean())  # every blob element was delivered to the host
     g.kernel_times()
 
+    other = None
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        other = other_config_legs(o, torch, args, local, stream)
+
     # ---- the Caffe-style layer, the actual drop-in: prototxt -> LayerRegistry -> LayerSetUp -> Forward_gpu x steps
     layer_leg = None
     if world == 1 and not args.no_layer and (W, H) == (512, 384):
@@ -438,6 +520,7 @@ def run_ours(args):
             dist.barrier()
             dist.destroy_process_group()
         return
+    host_probe = host_memory_probe(o) if not args.no_cpu else None
 
     peak, peak_src = measured_peak()
     split = shade_ms > 0
@@ -463,10 +546,16 @@ def run_ours(args):
                 "d2h_bytes_per_step": d2h, "host_blob_bytes_per_step": B * (2 * 3 + 2) * H * W * 4,
                 "transport": ("uint8 frames + float32 flow over PCIe, widened to the float blobs by host threads inside the timed region"
                               if d2h < B * 8 * H * W * 4 else "float32 blobs over PCIe"),
-                "steps": e2e_steps, "checksum": checksum},
+                "steps": e2e_steps, "checksum": checksum,
+                # host DRAM traffic the path implies per step: the DMA writes (d2h), the byte frames read back by the widening
+                # threads, the float frames they write (the flow lands in the caller's blob directly)
+                "host_dram_bytes_per_step": (d2h + B * 6 * H * W + B * 6 * H * W * 4) if d2h < B * 8 * H * W * 4 else d2h,
+                "host_dram_gbs_implied": ((d2h + B * 6 * H * W + B * 6 * H * W * 4) if d2h < B * 8 * H * W * 4 else d2h) * (e2e / (world * B)) * world / 1e9,
+                "host_probe": host_probe},
         "gpu_launches": launches,
         "production_mode": production,
         "layer_forward_gpu": layer_leg,
+        "other_configs": other,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ab, "kernel_ms": kern_ms,
@@ -528,6 +617,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-attribution", action="store_true", help="skip the per-kernel attribution pass")
     ap.add_argument("--no-layer", action="store_true", help="skip the DataGenerationLayer::Forward_gpu leg")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the config 3 / config 5 legs")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture (profiles/)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -17,7 +17,7 @@ const char* ofdg_layer_last_error(void);
  * ints[7] = {batch_size, prefetch, mode, first_level_threads, second_level_threads, use_antialiasing, top_size}. */
 int ofdg_layer_parse_prototxt(const char* text, int32_t* ints, char* texture_db, int32_t cap, char* type, int32_t type_cap);
 /* DataGenerationLayer(const LayerParameter&) on the current CUDA device. texture_db_override (may be NULL)
- * replaces texture_dbases(0): either a list file of image paths (binary PPM, uncompressed BMP, 8-bit PNG; any
+ * replaces texture_dbases(0): either a list file of image paths (binary PPM, uncompressed BMP, 8-bit PNG, JPEG; any
  * mix of sizes) or "synthetic:<count>[:<seed>]". */
 int ofdg_layer_create(const char* prototxt, const char* texture_db_override, int32_t solver_rank, void** out);
 void ofdg_layer_destroy(void* layer);
@@ -31,8 +31,12 @@ const char* ofdg_layer_type(void* layer);                        /* "DataGenerat
  * LayerRegistry<float>::CreateLayer(param), the way Net::Init does. Returns the number of types. */
 int ofdg_layer_registered_types(char* out, int32_t cap);
 /* The texture-file decoder the layer uses (TextureCollection ctor, DataGenerator.cpp:128-133): size of the image,
- * and, when `planar_bgr` is non-NULL and `cap` >= 3*w*h, its pixels as 3 x h x w planes in B,G,R order. No GPU needed. */
+ * and, when `planar_bgr` is non-NULL and `cap` >= 3*w*h, its pixels as 3 x h x w planes in B,G,R order. PPM, BMP and PNG
+ * need no GPU; JPEG is decoded by nvJPEG on the current CUDA device. */
 int ofdg_decode_texture_file(const char* path, int32_t* w, int32_t* h, uint8_t* planar_bgr, uint64_t cap);
+/* The paths a texture list names, with the reference's getline / eof semantics (TextureCollection ctor,
+ * DataGenerator.cpp:123-126: a last line without a trailing newline is not read). `out` receives them newline-separated. */
+int ofdg_read_texture_list(const char* listfile, char* out, int32_t cap, int32_t* count);
 
 #ifdef __cplusplus
 }

@@ -61,9 +61,12 @@ void ofdg_params_destroy(ofdg_params* p);
  * appends n_tasks freshly drawn tasks to `out`. */
 int ofdg_params_generate(ofdg_params* p, int32_t n_tasks, ofdg_tasks* out);
 /* Colour/noise augmentation records for subsequently generated tasks (not in the reference; specification in
- * ofdg/scene.h; drawn from five extra engines seeded seed_offset+45..49). Off by default. */
+ * ofdg/scene.h; drawn from five extra engines seeded 0x40000000 + seed_offset + 0..4, away from every rank's 45 reference seeds). Off by default. */
 int ofdg_params_enable_augmentation(ofdg_params* p, int32_t enable);
 int ofdg_params_skip(ofdg_params* p, uint64_t n_tasks);          /* checkpoint/resume: fast-forward */
+/* Helper threads that produce the engines' values ahead of ofdg_params_generate's sequential walk (one job per engine and
+ * batch; the k-th value of an engine depends on its seed and k only, so the stream is unchanged). 0 = off (default). */
+int ofdg_params_set_threads(ofdg_params* p, int32_t threads);
 uint64_t ofdg_params_tasks_generated(const ofdg_params* p);
 /* Mode 9: warp-field picks made so far (pool slot of pick k = (k / 3) % n_fields). */
 uint64_t ofdg_params_field_draws(const ofdg_params* p);

@@ -63,7 +63,7 @@ _lib = None
 # every symbol include/ofdg/ofdg.h declares
 EXPORTS = [
     "ofdg_last_error", "ofdg_version", "ofdg_params_create", "ofdg_params_destroy", "ofdg_params_generate",
-    "ofdg_params_skip", "ofdg_params_enable_augmentation", "ofdg_params_tasks_generated", "ofdg_params_draws", "ofdg_params_field_draws", "ofdg_refresh_fields", "ofdg_reserve_fields", "ofdg_params_slot_name",
+    "ofdg_params_skip", "ofdg_params_set_threads", "ofdg_params_enable_augmentation", "ofdg_params_tasks_generated", "ofdg_params_draws", "ofdg_params_field_draws", "ofdg_refresh_fields", "ofdg_reserve_fields", "ofdg_params_slot_name",
     "ofdg_tasks_create", "ofdg_tasks_destroy", "ofdg_tasks_clear", "ofdg_tasks_view", "ofdg_tasks_assign",
     "ofdg_flatten_ellipse", "ofdg_flatten_polygon", "ofdg_debug_raster_host", "ofdg_debug_expand_host", "ofdg_create", "ofdg_destroy", "ofdg_upload_textures", "ofdg_add_textures", "ofdg_clear_textures", "ofdg_texture_size", "ofdg_download_foreground_view",
     "ofdg_synth_textures", "ofdg_download_texture", "ofdg_set_fields", "ofdg_generate_fields", "ofdg_render", "ofdg_render_host",
@@ -73,7 +73,7 @@ EXPORTS = [
 # include/ofdg/layer.h
 LAYER_EXPORTS = [
     "ofdg_layer_last_error", "ofdg_layer_parse_prototxt", "ofdg_layer_registered_types", "ofdg_layer_create", "ofdg_layer_destroy", "ofdg_layer_setup",
-    "ofdg_layer_top_shape", "ofdg_layer_forward", "ofdg_layer_top_data", "ofdg_layer_type", "ofdg_decode_texture_file",
+    "ofdg_layer_top_shape", "ofdg_layer_forward", "ofdg_layer_top_data", "ofdg_layer_type", "ofdg_decode_texture_file", "ofdg_read_texture_list",
 ]
 
 
@@ -101,6 +101,7 @@ def lib():
         L.ofdg_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]
         L.ofdg_last_shade_ms.argtypes = [C.c_void_p]
         L.ofdg_last_shade_ms.restype = C.c_double
+        L.ofdg_params_set_threads.argtypes = [C.c_void_p, C.c_int32]
         L.ofdg_params_field_draws.argtypes = [C.c_void_p]
         L.ofdg_params_field_draws.restype = C.c_uint64
         L.ofdg_refresh_fields.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_int32]
@@ -290,6 +291,10 @@ class ParamStream:
     def skip(self, n):
         _check(lib().ofdg_params_skip(self._h, n))
 
+    def set_threads(self, n):
+        """Look-ahead helper threads of generate() (ofdg_params_set_threads); the stream itself does not change."""
+        _check(lib().ofdg_params_set_threads(self._h, n))
+
     def enable_augmentation(self, on=True):
         _check(lib().ofdg_params_enable_augmentation(self._h, int(bool(on))))
 
@@ -347,6 +352,19 @@ def decode_texture_file(path):
     out = np.empty((3, h.value, w.value), np.uint8)
     if L.ofdg_decode_texture_file(str(path).encode(), C.byref(w), C.byref(h), _ptr(out), out.size):
         raise OfdgError(L.ofdg_layer_last_error().decode())
+    return out
+
+
+def read_texture_list(path):
+    """Paths of a texture list file as the layer reads it (reference semantics: an unterminated last line is dropped)."""
+    buf = C.create_string_buffer(1 << 20)
+    n = C.c_int32()
+    L = lib()
+    L.ofdg_read_texture_list.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(C.c_int32)]
+    if L.ofdg_read_texture_list(str(path).encode(), buf, 1 << 20, C.byref(n)):
+        raise OfdgError(L.ofdg_layer_last_error().decode())
+    out = [p for p in buf.value.decode().split("\n") if p]
+    assert len(out) == n.value
     return out
 
 

@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "--fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off,-O2,-pthread", "-shared",
-           "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB + ".tmp"] + srcs + ["-lz"]
+           "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB + ".tmp"] + srcs + ["-lz", "-lnvjpeg"]
     cmd += [f for f in os.environ.get("OFDG_NVCC_FLAGS", "").split() if f]  # experiments: -DOFDG_TILE_ROWS=4 ...
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

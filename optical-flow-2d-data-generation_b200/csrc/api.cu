@@ -181,6 +181,7 @@ struct ofdg_generator {
   int pair_cap = 0;
   bool split_render = true;  // OFDG_RENDER=fused selects the single-kernel path
   int pair_cap_limit = 0;    // OFDG_TEST_PAIR_CAP: pretend the pair buffers are this small (tests of the overflow trap)
+  int philox_fg_override = 0;  // OFDG_TEST_PHILOX_FG: forced object count of the device stream (tests of its truncation flag)
   DevBuf out0, out1, outf;  // device blobs for the *_host entry points
   ofdg_extra_tops extra{};  // extra tops of the device-blob calls (ofdg_set_extra_tops)
   DevBuf ids8;              // object ranks per pixel, scratch of the occlusion pass
@@ -382,8 +383,9 @@ void ensure_scratch(ofdg_generator* g, int batch) {
       g->alt.pair_ctl.reserve(4 * sizeof(int));
     }
     if (!g->pair_overflow.p) {
-      g->pair_overflow.reserve(sizeof(int));
-      *(volatile int*)g->pair_overflow.p = 0;
+      g->pair_overflow.reserve(2 * sizeof(int));  // [0] pair buffer overflow, [1] a device-drawn scene did not fit its fixed strides
+      ((volatile int*)g->pair_overflow.p)[0] = 0;
+      ((volatile int*)g->pair_overflow.p)[1] = 0;
     }
   }
   g->scratch_batch = batch;
@@ -463,8 +465,13 @@ ofdg::RenderArgs with_extra_tops(ofdg_generator* g, ofdg::RenderArgs a) {
 // bounds) the call that notices fails loudly rather than handing back blobs that were not rendered.
 void check_pair_overflow(ofdg_generator* g) {
   volatile int* f = (volatile int*)g->pair_overflow.p;
-  if (f && *f) {
-    *f = 0;
+  if (f && f[1]) {
+    f[1] = 0;
+    throw StateError("device parameter stream: a sample asked for more than 32 foreground objects or an outline for more than 512 "
+                     "vertices per frame; it was rendered without them (use the host parameter stream for such scenes)");
+  }
+  if (f && f[0]) {
+    f[0] = 0;
     throw StateError("internal: more (object, tile) pairs than the mask buffer was sized for; the batch was not rendered");
   }
 }
@@ -598,7 +605,13 @@ void ofdg_params_destroy(ofdg_params* p) { delete p; }
 int ofdg_params_generate(ofdg_params* p, int32_t n_tasks, ofdg_tasks* out) {
   return guarded([&] {
     if (!p || !out || n_tasks < 0) throw ArgError("bad arguments");
-    for (int i = 0; i < n_tasks; ++i) p->ps->next_task(out->tb);
+    p->ps->next_tasks(out->tb, n_tasks);
+  });
+}
+int ofdg_params_set_threads(ofdg_params* p, int32_t threads) {
+  return guarded([&] {
+    if (!p || threads < 0) throw ArgError("bad arguments");
+    p->ps->set_lookahead_threads(threads);
   });
 }
 int ofdg_params_skip(ofdg_params* p, uint64_t n_tasks) {
@@ -760,6 +773,7 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
     if (const char* t = std::getenv("OFDG_TRANSPORT")) g->transport_u8 = std::string(t) != "f32";  // "f32": float blobs cross PCIe as they are
     if (const char* t = std::getenv("OFDG_RENDER")) g->split_render = std::string(t) != "fused";
     if (const char* t = std::getenv("OFDG_TEST_PAIR_CAP")) g->pair_cap_limit = std::atoi(t);
+    if (const char* t = std::getenv("OFDG_TEST_PHILOX_FG")) g->philox_fg_override = std::atoi(t);
     const char* ov = std::getenv("OFDG_BIN_OVERLAP");
     if (g->split_render && !(ov && std::string(ov) == "0")) {
       // The mask rasterisation of a batch runs on the side stream too, beside the background preparation: it needs the scene
@@ -1471,6 +1485,12 @@ void philox_run(ofdg_generator* g, int set, uint64_t seed, uint64_t first_sample
   a.seed = seed; a.first_sample = first_sample;
   a.batch = batch; a.n_fields = g->cfg.mode == 9 ? g->n_fields : 0; a.fg_override = fg_override; a.augment = augment;
   a.field_reach = (const int*)g->field_reach_dev.p;
+  if (!g->pair_overflow.p) {
+    g->pair_overflow.reserve(2 * sizeof(int));
+    ((volatile int*)g->pair_overflow.p)[0] = 0;
+    ((volatile int*)g->pair_overflow.p)[1] = 0;
+  }
+  a.truncated = (int*)g->pair_overflow.dev + 1;
   a.deform_shape = (int*)q.scene.deform_shape.p; a.deform_field = (int*)q.scene.deform_field.p; a.n_deform = (int*)q.n_deform.p;
   CK(cudaMemsetAsync(q.n_deform.p, 0, sizeof(int), s));
   a.n_tex = g->n_tex; a.tex_info = (const ofdg::TexInfo*)g->tex_info_dev.p;
@@ -1483,7 +1503,15 @@ void philox_run(ofdg_generator* g, int set, uint64_t seed, uint64_t first_sample
   CK(cudaMemcpyAsync(q.n_deform_host.p, q.n_deform.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   q.scene.batch = batch;
   q.scene.n_deform = 0;  // mode 9: read back by philox_collect once the set is complete
-  q.scene.pair_bound = (size_t)batch * kPhiloxMaxObj * (ofdg::tile_hits_bytes(1, g->cfg.width, g->cfg.height) / ofdg::TILE_HIT_STRIDE);  // the host never sees the boxes
+  {
+    // The host never sees the boxes of a device-drawn scene. Every object on every tile would be batch * 32 * tiles pairs of
+    // 4.4 KB (1.9 GB at batch 64); the modes' scenes have about 300 pairs per 512 x 384 sample, so large batches get 1536 pairs
+    // per sample (scaled with the tile count) -- five times the average of a whole batch -- and small ones the full bound.
+    // bin_pairs_kernel counts the real pairs: a batch beyond the buffer raises the overflow flag and the call fails loudly.
+    const size_t tiles = ofdg::tile_hits_bytes(1, g->cfg.width, g->cfg.height) / ofdg::TILE_HIT_STRIDE;
+    const size_t full = (size_t)batch * kPhiloxMaxObj * tiles;
+    q.scene.pair_bound = std::min(full, std::max<size_t>((size_t)batch * 1536 * tiles / 192, 16384));
+  }
 }
 
 // Mode 9: the number of warped outlines of a finished set sizes the deformation pre-pass of its render.
@@ -1541,7 +1569,7 @@ int ofdg_generate_philox(ofdg_generator* g, uint64_t seed, uint64_t first_sample
       set = g->ph_next.valid ? (g->ph_next.set ^ 1) : 0;
       if (g->ph_next.valid) CK(cudaStreamSynchronize(g->ph_stream));  // a speculative batch nobody asked for is still being written
       if (g->ph[set].used) CK(cudaStreamWaitEvent(s, g->ph[set].consumed, 0));
-      philox_run(g, set, seed, first_sample, batch, augment, 0, s);
+      philox_run(g, set, seed, first_sample, batch, augment, g->philox_fg_override, s);
       philox_collect(g, set, s);
     }
     ensure_scratch(g, batch);
@@ -1555,7 +1583,7 @@ int ofdg_generate_philox(ofdg_generator* g, uint64_t seed, uint64_t first_sample
     // look ahead: the next batch of the same stream, on the side stream, into the other set
     const int nset = set ^ 1;
     if (g->ph[nset].used) CK(cudaStreamWaitEvent(g->ph_stream, g->ph[nset].consumed, 0));
-    philox_run(g, nset, seed, first_sample + (uint64_t)batch, batch, augment, 0, g->ph_stream);
+    philox_run(g, nset, seed, first_sample + (uint64_t)batch, batch, augment, g->philox_fg_override, g->ph_stream);
     CK(cudaEventRecord(g->ph[nset].ready, g->ph_stream));
     g->ph_next.valid = true; g->ph_next.seed = seed; g->ph_next.first = first_sample + (uint64_t)batch;
     g->ph_next.batch = batch; g->ph_next.augment = augment; g->ph_next.set = nset;

@@ -113,7 +113,12 @@ void prepare_background(const ofdg_blueprint& b, const FlattenConfig& cfg, const
   p.shift_y = b.tex_shift_y;
   // CImg get_rotate(angle, 1, 3): SURVEY App. B.5
   const float nangle = cimg_modf(b.tex_rot, 360.0f);
-  p.rot_identity = (cimg_modf(nangle, 90.0f) == 0) ? 1 : 0;
+  p.rot_identity = (nangle == 0.f) ? 1 : 0;
+  // CImg rotates by exact multiples of 90 degrees without interpolation (axis swaps / flips). The parameter streams cannot
+  // reach them (tex_rot stays within +-pi, taken as degrees); blueprints supplied from outside that ask for one are refused,
+  // as the oracle refuses them, instead of being rendered with the unrotated texture.
+  if (!p.rot_identity && cimg_modf(nangle, 90.0f) == 0)
+    throw std::runtime_error("background tex_rot of exactly 90 / 180 / 270 degrees (CImg's orthogonal rotations) is not implemented");
   if (p.rot_identity) {
     p.ca = 1.f; p.sa = 0.f;
     p.rw = w; p.rh = h;

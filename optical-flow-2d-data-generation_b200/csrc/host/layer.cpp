@@ -154,6 +154,8 @@ LayerParameter ParseLayerPrototxt(const std::string& text) {
   Lexer lx(text);
   bool seen_layer = false, seen_mode = false;
   auto layer_fields = [&](const std::string& n, const Tok* v, Lexer& l) {
+    if (!v && (n == "name" || n == "type" || n == "top" || n == "bottom"))  // e.g. `top { }`: a scalar field written as a message
+      throw std::runtime_error("prototxt: field '" + n + "' takes a value, not a message");
     if (n == "name") p.name_ = to_str(*v, n);
     else if (n == "type") p.type_ = to_str(*v, n);
     else if (n == "top") p.top_.push_back(to_str(*v, n));
@@ -255,6 +257,14 @@ DataGenerationLayer<Dtype>::DataGenerationLayer(const LayerParameter& param) : L
     next_generation_ = 1;
   }
   OFDG_CHECK(ofdg_params_create(gp.mode(), cfg.width, cfg.height, 45 * solver_rank_, n_fields, 0, &params_));
+  {
+    // look-ahead threads of the parameter stream: the engines' values for the batch after next are produced while the
+    // prefetch threads walk / flatten the current ones (the stream itself is unchanged)
+    int helpers = std::min(6, (int)std::thread::hardware_concurrency() / 3);
+    if (const char* lw = std::getenv("LOCAL_WORLD_SIZE")) helpers = std::min(helpers, (int)std::thread::hardware_concurrency() / (3 * std::max(1, std::atoi(lw))));
+    if (const char* t = std::getenv("OFDG_PARAM_THREADS")) helpers = std::atoi(t);
+    if (helpers > 0 && !gp.device_params()) OFDG_CHECK(ofdg_params_set_threads(params_, helpers));
+  }
   for (int i = 0; i < kProducers; ++i) OFDG_CHECK(ofdg_tasks_create(&tasks_[i]));
   // Forward_gpu enqueues on a stream of the layer's own and never blocks the solver thread: the legacy default stream (where
   // Caffe's other layers run) is made to wait for the blobs by an event, and the layer's stream waits for the default
@@ -589,6 +599,17 @@ int ofdg_decode_texture_file(const char* path, int32_t* w, int32_t* h, uint8_t* 
       if (cap < t.planar_bgr.size()) throw std::runtime_error("buffer too small");
       std::memcpy(planar_bgr, t.planar_bgr.data(), t.planar_bgr.size());
     }
+  });
+}
+
+int ofdg_read_texture_list(const char* listfile, char* out, int32_t cap, int32_t* count) {
+  return layer_guard([&] {
+    if (!listfile || !count) throw std::runtime_error("null pointer");
+    const std::vector<std::string> paths = ofdg::read_texture_list(listfile);
+    *count = (int32_t)paths.size();
+    std::string joined;
+    for (const std::string& p : paths) joined += p + "\n";
+    if (out && cap > 0) std::snprintf(out, (size_t)cap, "%s", joined.c_str());
   });
 }
 

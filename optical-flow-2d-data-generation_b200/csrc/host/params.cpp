@@ -2,6 +2,8 @@
 // /root/reference/include/caffe/data_generation/SimpleRandom.h (SR.h).
 #include "params.hpp"
 
+#include <algorithm>
+
 #include <cmath>
 #include <limits>
 #include <stdexcept>
@@ -44,7 +46,15 @@ const char* slot_name(int slot) {
 }
 
 // ---------------------------------------------------------------------------------------------
-Engine::Engine(const SlotSpec& spec, int seed) : spec_(spec), mt_((uint32_t)seed) {
+Engine& Engine::operator=(Engine&& o) noexcept {
+  draws = o.draws; spec_ = o.spec_; mt_ = o.mt_; int_ = o.int_; real_ = o.real_; normal_ = o.normal_;
+  fa_ = o.fa_; fb_ = o.fb_; fc_ = o.fc_; fd_ = o.fd_;
+  cur_ = std::move(o.cur_); pos_ = o.pos_; ready_ = std::move(o.ready_); mu_ = std::move(o.mu_);
+  produced_.store(o.produced_.load()); consumed_ = o.consumed_; shared_ = o.shared_;
+  return *this;
+}
+
+Engine::Engine(const SlotSpec& spec, int seed) : spec_(spec), mt_((uint32_t)seed), mu_(new std::mutex) {
   // The reference's constructors take float a/b (DG.h:301-363); narrow here, widen where
   // the std:: distribution wants double (SR.h:98-102).
   fa_ = (float)spec.a; fb_ = (float)spec.b; fc_ = (float)spec.c; fd_ = (float)spec.d;
@@ -72,52 +82,128 @@ static inline float base_gauss(float a, float b, float input, float normalize) {
   return ((a <= sample && sample <= b) ? sample : (b + a) / 2.);
 }
 
-float Engine::real() {
-  ++draws;
+Engine::Value Engine::produce() {
+  Value v;
   switch (spec_.kind) {
     case UREAL:
-      return (float)real_(mt_);  // SR.h:104-105 (double narrowed by the float return type)
+      v.f = (float)real_(mt_);  // SR.h:104-105 (double narrowed by the float return type)
+      return v;
     case GAUSS_SQ: {             // DG.cpp:886-890
       float tmp = normal01();
       tmp = ((tmp > 0) ? std::pow(tmp, 2) : -std::pow(tmp, 2));
-      return base_gauss(fa_, fb_, tmp, 6);
+      v.f = base_gauss(fa_, fb_, tmp, 6);
+      return v;
     }
     case GAUSS_3: {              // DG.cpp:897-900
       float tmp = std::pow(normal01(), 3);
-      return base_gauss(fa_, fb_, tmp, 10);
+      v.f = base_gauss(fa_, fb_, tmp, 10);
+      return v;
     }
     case GAUSS_4: {              // DG.cpp:907-911
       float tmp = normal01();
       tmp = ((tmp > 0) ? std::pow(tmp, 4) : -std::pow(tmp, 4));
-      return base_gauss(fa_, fb_, tmp, 15);
+      v.f = base_gauss(fa_, fb_, tmp, 15);
+      return v;
     }
     case GAUSS_MSR: {            // DG.cpp:918-921: a, b, mean = c, sigma = d
       float tmp = normal01() * fd_ + fc_;
-      return (((fa_ <= tmp) && (tmp <= fb_)) ? tmp : fc_);
+      v.f = (((fa_ <= tmp) && (tmp <= fb_)) ? tmp : fc_);
+      return v;
     }
-    default:
-      throw std::logic_error("Engine::real on a non-real slot");
+    case UINT:
+      v.i = int_(mt_);
+      return v;
+    case CHOICE_INT:
+    case CHOICE_TYPE:
+      v.i = spec_.opts[int_(mt_)];  // DG.cpp:859-861
+      return v;
+    default: {                   // TRIGGER, DG.cpp:846-849
+      float u = (float)real_(mt_);
+      v.i = u < fc_ ? 1 : 0;
+      return v;
+    }
   }
+}
+
+void Engine::fill(size_t count) {
+  std::lock_guard<std::mutex> l(*mu_);
+  std::vector<Value> chunk;
+  chunk.reserve(count);
+  for (size_t i = 0; i < count; ++i) chunk.push_back(produce());
+  ready_.push_back(std::move(chunk));
+  produced_.fetch_add(count, std::memory_order_relaxed);
+}
+
+Engine::Value Engine::next_slow() {
+  std::lock_guard<std::mutex> l(*mu_);  // (waits for a fill in progress: the engine's state is its alone)
+  while (!ready_.empty()) {
+    cur_ = std::move(ready_.front());
+    ready_.pop_front();
+    pos_ = 0;
+    if (!cur_.empty()) { ++consumed_; return cur_[pos_++]; }
+  }
+  cur_.clear();
+  pos_ = 0;
+  return produce();
+}
+
+float Engine::real() {
+  ++draws;
+  if (spec_.kind != UREAL && spec_.kind < GAUSS_SQ) throw std::logic_error("Engine::real on a non-real slot");
+  return next().f;
 }
 
 int Engine::integer() {
   ++draws;
-  switch (spec_.kind) {
-    case UINT:
-      return int_(mt_);
-    case CHOICE_INT:
-    case CHOICE_TYPE:
-      return spec_.opts[int_(mt_)];  // DG.cpp:859-861
-    default:
-      throw std::logic_error("Engine::integer on a non-integer slot");
-  }
+  if (spec_.kind != UINT && spec_.kind != CHOICE_INT && spec_.kind != CHOICE_TYPE) throw std::logic_error("Engine::integer on a non-integer slot");
+  return next().i;
 }
 
 bool Engine::trigger() {  // DG.cpp:846-849
   ++draws;
   if (spec_.kind != TRIGGER) throw std::logic_error("Engine::trigger on a non-trigger slot");
-  float v = (float)real_(mt_);
-  return v < fc_;
+  return next().i != 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+MiniPool::MiniPool(int threads) {
+  for (int i = 0; i < threads; ++i) workers_.emplace_back([this] { loop(); });
+}
+MiniPool::~MiniPool() {
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    stop_ = true;
+  }
+  cv_work_.notify_all();
+  for (std::thread& t : workers_) t.join();
+}
+void MiniPool::loop() {
+  for (;;) {
+    std::function<void()> job;
+    {
+      std::unique_lock<std::mutex> l(mu_);
+      cv_work_.wait(l, [this] { return stop_ || !queue_.empty(); });
+      if (queue_.empty()) return;
+      job = std::move(queue_.front());
+      queue_.pop_front();
+    }
+    job();
+    std::lock_guard<std::mutex> l(mu_);
+    if (--pending_ == 0) cv_done_.notify_all();
+  }
+}
+void MiniPool::start(std::vector<std::function<void()> > jobs) {
+  if (jobs.empty()) return;
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    pending_ += jobs.size();
+    for (std::function<void()>& j : jobs) queue_.push_back(std::move(j));
+  }
+  cv_work_.notify_all();
+}
+void MiniPool::wait() {
+  std::unique_lock<std::mutex> l(mu_);
+  cv_done_.wait(l, [this] { return pending_ == 0; });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -156,8 +242,10 @@ ParamStream::ParamStream(int mode, int W, int H, int seed_offset, int n_fields, 
     : mode_(mode), W_(W), H_(H), n_fields_(n_fields), fg_override_(fg_override) {
   SlotSpec specs[kNumSlots];
   fill_mode_table(mode, W, H, specs);
-  for (int i = 0; i < kNumSlots; ++i) eng_[i] = Engine(specs[i], seed_offset + i);  // RNG_SEED++, DG.cpp:1360
-  for (int i = 0; i < 5; ++i) aug_eng_[i] = std::mt19937((uint32_t)(seed_offset + kNumSlots + i));
+  for (int i = 0; i < kNumSlots; ++i) eng_[i] = Engine(specs[i], seed_offset + i);  // RNG_SEED++, DG.cpp:1360 (move-assigned)
+  // augmentation engines (this repository's own spec): seeded far away from every rank's 45 reference seeds (ranks are strided by
+  // 45: seeds seed_offset + 45.. would be the next rank's first engines, and the streams of neighbouring GPUs would be correlated)
+  for (int i = 0; i < 5; ++i) aug_eng_[i] = std::mt19937(0x40000000u + (uint32_t)seed_offset + (uint32_t)i);
 }
 
 // CropGenerator::get_crop serves every crop reuse_same+1 = 3 times before popping it
@@ -409,7 +497,9 @@ void ParamStream::foreground(TaskBatch& out, size_t idx, bool is_component) {  /
   }
 }
 
-void ParamStream::next_task(TaskBatch& out) {  // data_generation_layer.cpp:197-214
+void ParamStream::next_task(TaskBatch& out) { next_task_unsynced(out); }
+
+void ParamStream::next_task_unsynced(TaskBatch& out) {  // data_generation_layer.cpp:197-214
   ofdg_blueprint bg = blank_blueprint();
   bg.obj_id = 1;
   bg.obj_type = OFDG_OBJ_POLYGON;
@@ -438,6 +528,57 @@ void ParamStream::next_task(TaskBatch& out) {  // data_generation_layer.cpp:197-
     out.augment.push_back(a);
   }
   ++tasks_;
+}
+
+void ParamStream::set_lookahead_threads(int threads) {
+  finish_lookahead();
+  pool_.reset();
+  if (threads > 0) {
+    for (int i = 0; i < kNumSlots; ++i) eng_[i].share();
+    pool_.reset(new MiniPool(std::min(threads, 16)));
+  }
+}
+
+ParamStream::~ParamStream() { finish_lookahead(); }
+
+void ParamStream::finish_lookahead() {
+  if (pool_) pool_->wait();
+}
+
+// The values of the next n tasks, engine by engine, on the helper threads; busiest engines first. An engine that runs dry
+// during the walk simply produces the rest in place, so the estimate only has to be good, not safe.
+void ParamStream::start_lookahead(int n) {
+  if (!pool_ || !have_rate_ || n < 8) return;
+  // keep about two batches' worth of values buffered per engine: the helpers work on the batch after next while the
+  // caller walks the next one
+  std::vector<std::pair<size_t, int> > want;
+  for (int i = 0; i < kNumSlots; ++i) {
+    if (rate_[i] <= 0) continue;
+    const size_t target = (size_t)(rate_[i] * n * 2.3) + 32, have = eng_[i].buffered();
+    if (have + (size_t)(rate_[i] * n * 0.5) < target) want.push_back(std::make_pair(target - have, i));
+  }
+  std::sort(want.begin(), want.end(), [](const std::pair<size_t, int>& a, const std::pair<size_t, int>& b) { return a.first > b.first; });
+  std::vector<std::function<void()> > jobs;
+  for (const std::pair<size_t, int>& w : want) {
+    Engine* e = &eng_[w.second];
+    const size_t cnt = w.first;
+    jobs.push_back([e, cnt] { e->fill(cnt); });
+  }
+  pool_->start(std::move(jobs));
+}
+
+void ParamStream::next_tasks(TaskBatch& out, int n) {
+  uint64_t before[kNumSlots];
+  for (int i = 0; i < kNumSlots; ++i) before[i] = eng_[i].draws;
+  for (int i = 0; i < n; ++i) next_task_unsynced(out);
+  if (n > 0) {
+    for (int i = 0; i < kNumSlots; ++i) {
+      const double r = (double)(eng_[i].draws - before[i]) / n;
+      rate_[i] = have_rate_ ? 0.5 * rate_[i] + 0.5 * r : r;
+    }
+    have_rate_ = true;
+  }
+  start_lookahead(n);  // for the next batch, beside whatever the caller does with this one
 }
 
 void ParamStream::skip(uint64_t n_tasks) {

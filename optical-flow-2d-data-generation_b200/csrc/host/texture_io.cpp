@@ -1,6 +1,8 @@
 // See texture_io.hpp.
 #include "texture_io.hpp"
 
+#include <cuda_runtime.h>
+#include <nvjpeg.h>
 #include <zlib.h>
 
 #include <cctype>
@@ -157,6 +159,42 @@ TextureImage decode_png(const std::string& path, const std::vector<unsigned char
   return from_interleaved(px.data(), w, h, ch, stride, false, false);
 }
 
+// JPEG (baseline and progressive) through nvJPEG, the decoder that ships with the CUDA toolkit: straight to planar B,G,R on
+// the current device, then to the host. The reference decodes JPEG through CImg -> libjpeg; decoders agree on the bitstream
+// but may round the inverse DCT / chroma upsampling differently by an LSB -- a property of the texture database, not of the
+// render path (whose parity is defined on the pixels the pool holds).
+TextureImage decode_jpeg(const std::string& path, const std::vector<unsigned char>& d) {
+  struct Nv {
+    nvjpegHandle_t h = nullptr;
+    nvjpegJpegState_t st = nullptr;
+    ~Nv() {
+      if (st) nvjpegJpegStateDestroy(st);
+      if (h) nvjpegDestroy(h);
+    }
+  } nv;
+  if (nvjpegCreateSimple(&nv.h) != NVJPEG_STATUS_SUCCESS) fail(path, "nvjpegCreateSimple failed (JPEG textures need a CUDA device)");
+  if (nvjpegJpegStateCreate(nv.h, &nv.st) != NVJPEG_STATUS_SUCCESS) fail(path, "nvjpegJpegStateCreate failed");
+  int comps = 0, ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
+  nvjpegChromaSubsampling_t sub;
+  if (nvjpegGetImageInfo(nv.h, d.data(), d.size(), &comps, &sub, ws, hs) != NVJPEG_STATUS_SUCCESS) fail(path, "not a JPEG image nvJPEG can parse");
+  const int w = ws[0], h = hs[0];
+  if (w <= 0 || h <= 0) fail(path, "bad JPEG size");
+  const size_t plane = (size_t)w * h;
+  unsigned char* dev = nullptr;
+  if (cudaMalloc(&dev, 3 * plane) != cudaSuccess) fail(path, "cudaMalloc failed while decoding a JPEG");
+  nvjpegImage_t out{};
+  for (int c = 0; c < 3; ++c) { out.channel[c] = dev + (size_t)c * plane; out.pitch[c] = (size_t)w; }
+  const nvjpegStatus_t rc = nvjpegDecode(nv.h, nv.st, d.data(), d.size(), NVJPEG_OUTPUT_BGR, &out, nullptr);  // planar B, G, R
+  TextureImage t;
+  t.w = w; t.h = h;
+  t.planar_bgr.resize(3 * plane);
+  const cudaError_t ce = rc == NVJPEG_STATUS_SUCCESS ? cudaMemcpy(t.planar_bgr.data(), dev, 3 * plane, cudaMemcpyDeviceToHost) : cudaSuccess;
+  cudaFree(dev);
+  if (rc != NVJPEG_STATUS_SUCCESS) fail(path, "nvjpegDecode failed (status " + std::to_string((int)rc) + ")");
+  if (ce != cudaSuccess) fail(path, "copying the decoded JPEG to the host failed");
+  return t;
+}
+
 }  // namespace
 
 TextureImage load_texture_file(const std::string& path) {
@@ -164,19 +202,27 @@ TextureImage load_texture_file(const std::string& path) {
   if (d.size() >= 2 && d[0] == 'P' && d[1] == '6') return decode_ppm(path, d);
   if (d.size() >= 2 && d[0] == 'B' && d[1] == 'M') return decode_bmp(path, d);
   if (d.size() >= 4 && d[0] == 0x89 && d[1] == 'P' && d[2] == 'N' && d[3] == 'G') return decode_png(path, d);
-  fail(path, "unsupported image format (decoders: binary PPM, uncompressed BMP, 8-bit PNG)");
+  if (d.size() >= 3 && d[0] == 0xFF && d[1] == 0xD8 && d[2] == 0xFF) return decode_jpeg(path, d);
+  fail(path, "unsupported image format (decoders: binary PPM, uncompressed BMP, 8-bit PNG, JPEG)");
 }
 
 std::vector<std::string> read_texture_list(const std::string& listfile) {
   std::ifstream infile(listfile);
   if (infile.bad() || !infile.is_open()) throw std::runtime_error("Could not open texture collection");  // DataGenerator.cpp:121
+  // The reference's loop, DataGenerator.cpp:123-126:  while (!eof) { getline(path); if (eof) break; load(path); }
+  // A last line that is not terminated by a newline sets eof inside getline and is therefore NOT loaded; pool slot k is
+  // tex_id % pool size, so the pool must have exactly the reference's size for the k-th task to pick the same texture.
+  // An empty line would make CImg::load("") throw in the reference; here it is an error as well.
   std::vector<std::string> paths;
   std::string path;
-  while (std::getline(infile, path)) {
-    while (!path.empty() && (path.back() == '\r' || path.back() == ' ')) path.pop_back();
-    if (!path.empty()) paths.push_back(path);
+  while (!infile.eof()) {
+    std::getline(infile, path);
+    if (infile.eof()) break;
+    while (!path.empty() && path.back() == '\r') path.pop_back();  // (lists written on Windows)
+    if (path.empty()) throw std::runtime_error("texture collection " + listfile + ": empty line (the reference's CImg::load(\"\") fails there too)");
+    paths.push_back(path);
   }
-  if (paths.empty()) throw std::runtime_error("texture collection is empty");
+  if (paths.empty()) throw std::runtime_error("texture collection is empty (note: a last line without a trailing newline is not read, like the reference)");
   return paths;
 }
 

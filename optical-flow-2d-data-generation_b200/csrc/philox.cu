@@ -278,7 +278,10 @@ __global__ void __launch_bounds__(32 * kParamWarps) philox_params_kernel(PhiloxA
   // the number of objects is a sample-level draw every thread of the sample repeats
   g.rng.init(a.seed, a.first_sample + (uint64_t)s, kPhiloxMaxObj);
   int fg = a.fg_override > 0 ? a.fg_override : (int)g.real(NumberOfFgObjects);
-  if (fg > kPhiloxMaxObj) fg = kPhiloxMaxObj;
+  if (fg > kPhiloxMaxObj) {  // more objects than the fixed strides hold: rendered without the rest, and the host is told
+    if (a.truncated && k == kPhiloxMaxObj && (threadIdx.x & 31) == 0) *a.truncated = 1;
+    fg = kPhiloxMaxObj;
+  }
   int field_draws = 0;
   if (k == kPhiloxMaxObj) {
     // generateBackground, DG.cpp:2105-2143
@@ -526,7 +529,10 @@ __global__ void __launch_bounds__(kFlatObjPerBlock * kFlatLanes) philox_flatten_
     const size_t vb = (size_t)obj_slot * kPhiloxMaxVerts + (size_t)sf * cap;
     out.begin(a.verts + vb, cap);
     outline(a, c, T, out);
-    if (out.n > out.cap) out.n = 0;  // out of room: drop the outline rather than corrupt memory (never seen in practice)
+    if (out.n > out.cap) {  // out of room: drop the outline rather than corrupt memory, and tell the host (never seen with the modes' shapes)
+      out.n = 0;
+      if (a.truncated) *a.truncated = 1;
+    }
     FlatShape& sh = a.shapes[obj_slot * kPhiloxMaxShapes + si];
     sh.vbegin[f] = (int)vb;
     sh.vcount[f] = out.n;

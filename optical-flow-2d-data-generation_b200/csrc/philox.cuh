@@ -35,6 +35,7 @@ struct PhiloxArgs {
   int* deform_shape;        // [batch * kPhiloxMaxObj * kPhiloxMaxShapes] shape index per slot
   int* deform_field;        //   field id per slot
   int* n_deform;            // device counter (zeroed before the launch)
+  int* truncated;           // mapped host int (may be null): raised when a scene does not fit the fixed strides below and loses objects / outlines
   // blueprints in the ABI layout, fixed strides per sample (downloadable for inspection / the oracle)
   ofdg_blueprint* bp;   // [batch][kPhiloxMaxBp]: background, then kPhiloxMaxShapes slots per object
   int32_t* seg_type;    // [batch][kPhiloxMaxSeg]: 160 per object

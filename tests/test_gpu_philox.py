@@ -130,3 +130,24 @@ def test_device_stream_mode9_warp_fields(ofdg, oracle, textures8):
                 bad = np.abs(i0.cpu().numpy() - nxt[0]) > 1
             assert bad.mean() < 3e-3
     g.close()
+
+
+def test_device_stream_reports_truncated_scenes(ofdg, textures8, monkeypatch):
+    """The device stream works in fixed strides (32 objects per sample, 512 vertices per outline and frame). A scene beyond them
+    used to lose objects silently; now the call that notices fails loudly (OFDG_TEST_PHILOX_FG forces 40 objects)."""
+    import torch
+    monkeypatch.setenv("OFDG_TEST_PHILOX_FG", "40")
+    g = ofdg.Generator(device=0, mode=7, max_batch=4)
+    g.upload_textures(textures8)
+    i0 = torch.empty((4, 3, 384, 512), device="cuda")
+    i1 = torch.empty_like(i0)
+    fl = torch.empty((4, 2, 384, 512), device="cuda")
+    with pytest.raises(ofdg.OfdgError, match="more than 32 foreground objects"):
+        g.generate_philox(1, 0, 4, i0, i1, fl)
+    monkeypatch.delenv("OFDG_TEST_PHILOX_FG")
+    g.close()
+    g = ofdg.Generator(device=0, mode=7, max_batch=4)
+    g.upload_textures(textures8)
+    g.generate_philox(1, 0, 4, i0, i1, fl)  # the ordinary stream: fine
+    assert float(i0.std()) > 5
+    g.close()

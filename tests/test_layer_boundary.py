@@ -22,6 +22,8 @@ def test_prototxt_defaults_and_errors(ofdg):
         ofdg.parse_prototxt('layer { type: "DataGeneration" data_generation_param { modee: 3 } }')
     with pytest.raises(ofdg.OfdgError):
         ofdg.parse_prototxt('layer { type: "DataGeneration" ')
+    with pytest.raises(ofdg.OfdgError, match="takes a value"):  # used to dereference a null token
+        ofdg.parse_prototxt('layer { type: "DataGeneration" top { } }')
     with pytest.raises(ofdg.OfdgError, match="DataGeneration"):
         ofdg.DataGenerationLayer('layer { type: "Data" top: "a" }')
 
@@ -192,8 +194,11 @@ def test_texture_file_decoders(ofdg, tmp_path):
     for name in ("a.ppm", "a.bmp", "a.png", "b.png"):
         assert np.array_equal(ofdg.decode_texture_file(tmp_path / name), want), name
     assert np.array_equal(ofdg.decode_texture_file(tmp_path / "c.png"), np.ascontiguousarray(few[:, :, ::-1].transpose(2, 0, 1)))
-    (tmp_path / "x.jpg").write_bytes(b"\xff\xd8\xff\xe0" + b"\0" * 64)
+    (tmp_path / "x.gif").write_bytes(b"GIF89a" + b"\0" * 64)
     with pytest.raises(ofdg.OfdgError, match="unsupported image format"):
+        ofdg.decode_texture_file(tmp_path / "x.gif")
+    (tmp_path / "x.jpg").write_bytes(b"\xff\xd8\xff\xe0" + b"\0" * 64)  # a JPEG signature goes to nvJPEG (needs a device; garbage is rejected)
+    with pytest.raises(ofdg.OfdgError, match="nvjpeg|JPEG"):
         ofdg.decode_texture_file(tmp_path / "x.jpg")
     with pytest.raises(ofdg.OfdgError, match="Could not open"):
         ofdg.decode_texture_file(tmp_path / "missing.png")
@@ -293,4 +298,53 @@ def test_layer_forward_gpu_does_not_block_and_recycles_scenes(ofdg, oracle):
     ref = oracle.render(ps.generate(8).struct(), tex, mode=7)
     assert np.abs(got[0] - ref["img0"]).max() <= 1 and np.abs(got[1] - ref["img1"]).max() <= 1
     assert np.abs(got[2] - ref["flow"]).max() <= 1e-3
+    layer.close()
+
+
+def test_texture_list_follows_the_reference_loop(ofdg, tmp_path):
+    """TextureCollection's loop (DataGenerator.cpp:123-126) is `while (!eof) { getline; if (eof) break; load; }`: a last line
+    without a trailing newline is NOT loaded, so the pool size -- and with it tex_id % pool size -- must follow the same rule."""
+    f = tmp_path / "db.txt"
+    f.write_text("a.ppm\nb.ppm\nc.ppm\n")
+    assert ofdg.read_texture_list(f) == ["a.ppm", "b.ppm", "c.ppm"]
+    f.write_text("a.ppm\nb.ppm\nc.ppm")           # unterminated last line: dropped, like the reference
+    assert ofdg.read_texture_list(f) == ["a.ppm", "b.ppm"]
+    f.write_text("a.ppm\r\nb.ppm\r\n")
+    assert ofdg.read_texture_list(f) == ["a.ppm", "b.ppm"]
+    f.write_text("a.ppm\n\nb.ppm\n")              # CImg::load("") throws in the reference
+    with pytest.raises(ofdg.OfdgError, match="empty line"):
+        ofdg.read_texture_list(f)
+    f.write_text("only-line-without-newline")
+    with pytest.raises(ofdg.OfdgError, match="empty"):
+        ofdg.read_texture_list(f)
+    with pytest.raises(ofdg.OfdgError, match="Could not open texture collection"):
+        ofdg.read_texture_list(tmp_path / "missing.txt")
+
+
+@pytest.mark.gpu
+def test_jpeg_textures_through_nvjpeg(ofdg, tmp_path):
+    """JPEG textures (the authors' database format; CImg::load -> libjpeg in the reference, DataGenerator.cpp:128) are decoded by
+    nvJPEG. Checked against Pillow's libjpeg decode of the same files: baseline 4:2:0, progressive 4:4:4 and grayscale."""
+    from PIL import Image
+    tex = ofdg.synth_textures(1, 640, 480, seed=21)[0]               # planes in file order R, G, B
+    rgb = np.ascontiguousarray(tex.transpose(1, 2, 0))
+    Image.fromarray(rgb).save(tmp_path / "a.jpg", quality=92, subsampling=2)
+    Image.fromarray(rgb).save(tmp_path / "b.jpg", quality=95, subsampling=0, progressive=True)
+    Image.fromarray(rgb[:, :, 1]).save(tmp_path / "c.jpg", quality=90)
+    for name in ("a.jpg", "b.jpg", "c.jpg"):
+        w, h, planar = ofdg.decode_texture_file(tmp_path / name)
+        want = np.asarray(Image.open(tmp_path / name).convert("RGB")).astype(int)
+        assert (w, h) == (640, 480)
+        got = planar[::-1].transpose(1, 2, 0).astype(int)            # planar B,G,R -> interleaved R,G,B
+        d = np.abs(got - want)
+        assert d.max() <= 3 and d.mean() < 0.6, (name, d.max(), d.mean())  # decoders differ in IDCT / upsampling rounding only
+        assert np.abs(got - rgb.astype(int) if name != "c.jpg" else 0).mean() < 8
+    # and through the layer's list loader
+    (tmp_path / "db.txt").write_text(str(tmp_path / "a.jpg") + "\n" + str(tmp_path / "b.jpg") + "\n")
+    proto = ('layer { type: "DataGeneration" top: "a" top: "b" top: "c" data_param { batch_size: 2 prefetch: 1 } '
+             'data_generation_param { mode: 5 texture_dbases: "%s" } }' % (tmp_path / "db.txt"))
+    layer = ofdg.DataGenerationLayer(proto)
+    layer.LayerSetUp()
+    layer.Forward_gpu()
+    assert layer.top_cpu(0).std() > 5
     layer.close()

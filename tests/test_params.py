@@ -184,3 +184,28 @@ def test_augmentation_noise_statistics(ofdg, oracle, textures8):
     assert np.corrcoef(d[0].ravel()[:50000], d[1].ravel()[:50000])[0, 1] < 0.02  # channels independent
     assert not np.array_equal(d[0], d1[0])
     assert np.array_equal(noisy["flow"], clean["flow"])
+
+
+@pytest.mark.parametrize("mode", [1, 7, 9])
+def test_lookahead_threads_leave_the_stream_unchanged(ofdg, mode):
+    """ofdg_params_set_threads: helper threads produce the engines' values ahead of the sequential walk. The k-th value of an
+    engine depends on its seed and k only, so blueprints, segments, per-engine draw counts and resume points are the same
+    with and without them -- for batches of changing size, single tasks and a skip in between."""
+    def run(threads):
+        ps = ofdg.ParamStream(mode, n_fields=40 if mode == 9 else 0)
+        if threads:
+            ps.set_threads(threads)
+        out = []
+        for n in (64, 64, 3, 64, 17, 64, 64):
+            a = ps.generate(n).arrays()
+            out.append((a["blueprints"].tobytes(), a["seg_type"].tobytes(), a["seg_x"].tobytes(), a["seg_y"].tobytes()))
+        ps.skip(5)
+        a = ps.generate(64).arrays()
+        out.append((a["blueprints"].tobytes(), a["seg_x"].tobytes()))
+        return out, ps.draws(), ps.tasks_generated()
+    base = run(0)
+    for threads in (1, 3):
+        got = run(threads)
+        assert got[1] == base[1] and got[2] == base[2]
+        for k, (x, y) in enumerate(zip(base[0], got[0])):
+            assert x == y, f"batch {k} differs with {threads} look-ahead threads"

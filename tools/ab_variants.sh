@@ -7,7 +7,7 @@ cp $LIB /tmp/libofdg_current.so
 for v in "$@" /tmp/libofdg_current.so; do
   cp "$v" $LIB
   for rep in $(seq 1 ${REPS:-2}); do
-    python bench.py --no-cpu --no-layer --e2e-steps 3 --steps ${STEPS:-600} 2>/dev/null | python -c "
+    python bench.py --no-cpu --no-layer --no-other-configs --e2e-steps 3 --steps ${STEPS:-600} 2>/dev/null | python -c "
 import json, sys
 d = json.loads(sys.stdin.read().strip().splitlines()[-1]); r = d['roofline']; k = r.get('kernels') or {}
 print('$v', 'samples/s %.0f' % d['value'], 'step %.4f ms' % d['ms_per_step'], 'prod %.0f' % d['production_mode']['value'],
