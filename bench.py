@@ -503,6 +503,8 @@ def run_ours(args):
             for _ in range(6):
                 layer.Forward_gpu()
             torch.cuda.synchronize()
+            if name == "host_rng":
+                layer.producer_stats()
             n_fw = max(20, min(args.steps, 300))
             t0 = time.time()
             for _ in range(n_fw):
@@ -510,6 +512,10 @@ def run_ours(args):
             torch.cuda.synchronize()
             dt = time.time() - t0
             layer_leg[name] = {"value": B * n_fw / dt, "unit": "samples/s", "ms_per_forward": 1e3 * dt / n_fw, "forwards": n_fw}
+            if name == "host_rng":
+                draw_ms, prep_ms_l, nb = layer.producer_stats()
+                layer_leg[name]["producer"] = {"draw_ms_per_batch": draw_ms, "prepare_ms_per_batch": prep_ms_l, "batches": nb,
+                                               "threads": "2 prefetch threads (draw of batch k+1 beside prepare of batch k) + look-ahead helpers + flatten pool"}
             layer.close()
         layer_leg["what"] = ("DataGenerationLayer::Forward_gpu into the top blobs' device memory, wall clock over back-to-back forwards incl. the "
                              "prefetch thread's parameter draw + flatten (host pool) + scene upload; host_rng = the reference's RNG stream, "

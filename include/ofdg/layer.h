@@ -30,6 +30,9 @@ const char* ofdg_layer_type(void* layer);                        /* "DataGenerat
  * /root/reference/src/caffe/layers/data_generation_layer.cpp:298-299): ofdg_layer_create builds the layer through
  * LayerRegistry<float>::CreateLayer(param), the way Net::Init does. Returns the number of types. */
 int ofdg_layer_registered_types(char* out, int32_t cap);
+/* Prefetch-side timing since the last call: out3 = {ms drawing parameters (incl. waiting for the sequential stream), ms in
+ * ofdg_prepare (flatten + upload), batches produced}. */
+int ofdg_layer_producer_stats(void* layer, double* out3);
 /* The texture-file decoder the layer uses (TextureCollection ctor, DataGenerator.cpp:128-133): size of the image,
  * and, when `planar_bgr` is non-NULL and `cap` >= 3*w*h, its pixels as 3 x h x w planes in B,G,R order. PPM, BMP and PNG
  * need no GPU; JPEG is decoded by nvJPEG on the current CUDA device. */

@@ -72,7 +72,7 @@ EXPORTS = [
 ]
 # include/ofdg/layer.h
 LAYER_EXPORTS = [
-    "ofdg_layer_last_error", "ofdg_layer_parse_prototxt", "ofdg_layer_registered_types", "ofdg_layer_create", "ofdg_layer_destroy", "ofdg_layer_setup",
+    "ofdg_layer_last_error", "ofdg_layer_parse_prototxt", "ofdg_layer_registered_types", "ofdg_layer_producer_stats", "ofdg_layer_create", "ofdg_layer_destroy", "ofdg_layer_setup",
     "ofdg_layer_top_shape", "ofdg_layer_forward", "ofdg_layer_top_data", "ofdg_layer_type", "ofdg_decode_texture_file", "ofdg_read_texture_list",
 ]
 
@@ -681,6 +681,15 @@ class DataGenerationLayer:
 
     def type(self):
         return lib().ofdg_layer_type(self._h).decode()
+
+    def producer_stats(self):
+        """(ms drawing per batch, ms in ofdg_prepare per batch, batches) of the prefetch threads since the last call."""
+        a = (C.c_double * 3)()
+        lib().ofdg_layer_producer_stats.argtypes = [C.c_void_p, C.c_void_p]
+        if lib().ofdg_layer_producer_stats(self._h, a):
+            raise OfdgError(lib().ofdg_layer_last_error().decode())
+        n = max(a[2], 1.0)
+        return a[0] / n, a[1] / n, int(a[2])
 
     @staticmethod
     def registered_types():

@@ -234,10 +234,20 @@ struct ofdg_generator {
   // ofdg_prepare: its own flatten pool, staging and upload stream, so that a producer thread can prepare the next batch
   // while another thread renders (the two only meet in the free list of recycled scenes)
   std::mutex prepare_mu, free_mu;
+  std::condition_variable prepare_cv;
   std::unique_ptr<ofdg::HostPool> prep_workers;
-  std::vector<ofdg::FlatBatch> prep_flat;
-  PinnedBuf prep_staging;
-  cudaStream_t prep_upload_stream = nullptr;
+  struct PrepCtx {  // what one ofdg_prepare call works with; a few of them, so that calls of different threads overlap
+    std::vector<ofdg::FlatBatch> flat;
+    PinnedBuf staging;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::condition_variable cv;
+    int remaining = 0;
+    std::string error;
+    bool busy = false;
+  };
+  static constexpr int kPrepCtx = 3;
+  PrepCtx prep_ctx[kPrepCtx];
   std::vector<ofdg_prepared*> free_scenes;
   static constexpr size_t kMaxFreeScenes = 12;
   // mode 9: refreshing slots of the field pool while other slots are being rendered (ofdg_refresh_fields)
@@ -806,7 +816,7 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
         }
       }
     }
-    CK(cudaStreamCreateWithFlags(&g->prep_upload_stream, cudaStreamNonBlocking));
+    for (ofdg_generator::PrepCtx& c : g->prep_ctx) CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     {
       std::lock_guard<std::mutex> lk(g_live_mu);
       g_live.insert(g.get());
@@ -830,11 +840,13 @@ void ofdg_destroy(ofdg_generator* g) {
     delete p;
   }
   g->free_scenes.clear();
-  g->prep_staging.release();
+  for (ofdg_generator::PrepCtx& c : g->prep_ctx) {
+    c.staging.release();
+    if (c.stream) cudaStreamDestroy(c.stream);
+  }
   g->wf_scratch.release();
   g->reach_host.release();
   if (g->field_stream) cudaStreamDestroy(g->field_stream);
-  if (g->prep_upload_stream) cudaStreamDestroy(g->prep_upload_stream);
   if (g->stream) cudaStreamSynchronize(g->stream);
   if (g->ph_stream) { cudaStreamSynchronize(g->ph_stream); cudaStreamDestroy(g->ph_stream); }
   for (int i = 0; i < 2; ++i) {
@@ -1642,34 +1654,59 @@ int ofdg_prepare(ofdg_generator* g, const ofdg_task_batch* tasks, ofdg_prepared*
     if (!g || !tasks || !out) throw ArgError("null pointer");
     check_batch(g, tasks->n_tasks);
     g->use();
-    // May run on a producer thread beside render calls of another thread: it touches nothing they use (own flatten pool,
-    // staging, upload stream); concurrent ofdg_prepare calls take turns.
-    std::lock_guard<std::mutex> turn(g->prepare_mu);
+    // May run on producer threads beside render calls of another thread: it touches nothing they use (own flatten pool,
+    // staging, upload streams), and up to kPrepCtx calls run side by side, each with a context of its own.
     const int n = tasks->n_tasks;
-    if (!g->prep_workers) {
-      int threads = std::min((int)std::thread::hardware_concurrency() / 2, 8);
-      if (const char* lw = std::getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU shares the host
-        const int local = std::max(1, std::atoi(lw));
-        if (local > 1) threads = std::min(threads, (int)std::thread::hardware_concurrency() / local);
+    ofdg_generator::PrepCtx* ctx = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(g->prepare_mu);
+      if (!g->prep_workers) {
+        int threads = std::min((int)std::thread::hardware_concurrency() / 2, 8);
+        if (const char* lw = std::getenv("LOCAL_WORLD_SIZE")) {  // one process per GPU shares the host
+          const int local = std::max(1, std::atoi(lw));
+          if (local > 1) threads = std::min(threads, (int)std::thread::hardware_concurrency() / local);
+        }
+        if (const char* t = std::getenv("OFDG_PREPARE_THREADS")) threads = std::atoi(t);
+        g->prep_workers.reset(new ofdg::HostPool(std::max(1, std::min(threads, 32)), g->cfg.device));
       }
-      if (const char* t = std::getenv("OFDG_PREPARE_THREADS")) threads = std::atoi(t);
-      g->prep_workers.reset(new ofdg::HostPool(std::max(1, std::min(threads, 32)), g->cfg.device));
+      g->prepare_cv.wait(lk, [g] { for (ofdg_generator::PrepCtx& c : g->prep_ctx) if (!c.busy) return true; return false; });
+      for (ofdg_generator::PrepCtx& c : g->prep_ctx) if (!c.busy) { ctx = &c; break; }
+      ctx->busy = true;
     }
-    if ((int)g->prep_flat.size() < n) g->prep_flat.resize(n);
+    struct Release {
+      ofdg_generator* g; ofdg_generator::PrepCtx* c;
+      ~Release() { { std::lock_guard<std::mutex> lk(g->prepare_mu); c->busy = false; } g->prepare_cv.notify_one(); }
+    } release{g, ctx};
+    if ((int)ctx->flat.size() < n) ctx->flat.resize(n);
     const ofdg::FlattenConfig fc = flatten_config(g);
     // one flatten job per sample (f64 geometry: ellipse 100-gons, curve subdivision, the background's crop parameters)
+    ctx->remaining = n;
+    ctx->error.clear();
     for (int i = 0; i < n; ++i) {
       ofdg_task_batch one = *tasks;
       one.n_tasks = 1;
       one.task_begin = tasks->task_begin + i;  // blueprint indices stay absolute
       if (one.augment) one.augment += i;
-      ofdg::FlatBatch* dst = &g->prep_flat[i];
-      g->prep_workers->submit([one, fc, dst] {
-        dst->clear();
-        ofdg::flatten(one, fc, *dst);
+      ofdg::FlatBatch* dst = &ctx->flat[i];
+      g->prep_workers->submit([one, fc, dst, ctx] {
+        std::string err;
+        try {
+          dst->clear();
+          ofdg::flatten(one, fc, *dst);
+        } catch (const std::exception& e) {
+          err = e.what();
+          if (err.empty()) err = "flatten failed";
+        }
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (!err.empty() && ctx->error.empty()) ctx->error = err;
+        if (--ctx->remaining == 0) ctx->cv.notify_all();
       }, true);
     }
-    g->prep_workers->wait();  // throws the first flatten failure
+    {
+      std::unique_lock<std::mutex> lk(ctx->mu);
+      ctx->cv.wait(lk, [ctx] { return ctx->remaining == 0; });
+      if (!ctx->error.empty()) throw ArgError(ctx->error);
+    }
     std::unique_ptr<ofdg_prepared> p;
     {
       std::lock_guard<std::mutex> lk(g->free_mu);
@@ -1690,8 +1727,8 @@ int ofdg_prepare(ofdg_generator* g, const ofdg_task_batch* tasks, ofdg_prepared*
     p->augmented = false;
     if (tasks->augment)
       for (int i = 0; i < n; ++i) p->augmented = p->augmented || tasks->augment[i].enabled != 0;
-    upload_scene_parts(g, g->prep_flat.data(), n, p->scene, g->prep_staging, g->prep_upload_stream);
-    CK(cudaStreamSynchronize(g->prep_upload_stream));  // the scene is resident (and the staging free) when this returns
+    upload_scene_parts(g, ctx->flat.data(), n, p->scene, ctx->staging, ctx->stream);
+    CK(cudaStreamSynchronize(ctx->stream));  // the scene is resident (and the staging free) when this returns
     *out = p.release();
   });
 }

@@ -348,6 +348,8 @@ template <typename Dtype>
 void DataGenerationLayer<Dtype>::load_batch(Prefetched* out, int producer, uint64_t* ticket) {
   const int batch_size = this->layer_param_.data_param().batch_size();
   ofdg_tasks* tasks = tasks_[producer];
+  const auto t0 = std::chrono::steady_clock::now();
+  auto t1 = t0;
   {
     // The parameter stream is sequential (45 mt19937 engines consumed in commission order): one batch is drawn at a time.
     // The other producer thread meanwhile flattens and uploads the batch it drew before.
@@ -368,11 +370,24 @@ void DataGenerationLayer<Dtype>::load_batch(Prefetched* out, int producer, uint6
       std::lock_guard<std::mutex> l(mutex_);
       drawn_.push_back(std::make_pair(*ticket, out->gen_lo));  // drawn, not queued yet: its generations must stay as they are
     }
+    t1 = std::chrono::steady_clock::now();
   }
   // (no generator lock: ofdg_prepare flattens on its own host pool and uploads on its own stream, beside a running Forward)
   ofdg_task_batch view;
   OFDG_CHECK(ofdg_tasks_view(tasks, &view));
+  const auto t2 = std::chrono::steady_clock::now();
   OFDG_CHECK(ofdg_prepare(generator_, &view, &out->scene));
+  const auto t3 = std::chrono::steady_clock::now();
+  std::lock_guard<std::mutex> l(mutex_);
+  stats_[0] += std::chrono::duration<double, std::milli>(t1 - t0).count();  // waiting for the stream + drawing
+  stats_[1] += std::chrono::duration<double, std::milli>(t3 - t2).count();  // flatten + upload (incl. waiting for its turn)
+  stats_[2] += 1.0;
+}
+
+template <typename Dtype>
+void DataGenerationLayer<Dtype>::producer_stats(double* out3) {
+  std::lock_guard<std::mutex> l(mutex_);
+  for (int i = 0; i < 3; ++i) { out3[i] = stats_[i]; stats_[i] = 0; }
 }
 
 template <typename Dtype>
@@ -663,6 +678,13 @@ const float* ofdg_layer_top_data(void* l, int32_t i, int32_t gpu) {
   try { return gpu ? b->top_ptrs.at(i)->gpu_data() : b->top_ptrs.at(i)->cpu_data(); } catch (const std::exception& e) { g_layer_error = e.what(); return nullptr; }
 }
 const char* ofdg_layer_type(void* l) { return ((LayerBox*)l)->layer->type(); }
+int ofdg_layer_producer_stats(void* l, double* out3) {
+  return layer_guard([&] {
+    caffe::DataGenerationLayer<float>* dl = dynamic_cast<caffe::DataGenerationLayer<float>*>(((LayerBox*)l)->layer.get());
+    if (!dl || !out3) throw std::runtime_error("not a DataGeneration layer");
+    dl->producer_stats(out3);
+  });
+}
 int ofdg_layer_registered_types(char* out, int32_t cap) {
   std::string s;
   const std::vector<std::string> types = caffe::LayerRegistry<float>::LayerTypeList();

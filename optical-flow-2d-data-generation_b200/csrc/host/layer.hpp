@@ -44,6 +44,8 @@ class DataGenerationLayer : public Layer<Dtype> {
   static void set_solver_rank(int rank) { solver_rank_ = rank; }
   // Checkpoint/resume: tasks commissioned so far; fast-forward a fresh layer to that point.
   uint64_t tasks_commissioned() const;
+  // Prefetch-side timing since the last call: {ms spent drawing (incl. waiting for the stream), ms in ofdg_prepare, batches}.
+  void producer_stats(double* out3);
 
  protected:
   struct Prefetched {
@@ -85,6 +87,7 @@ class DataGenerationLayer : public Layer<Dtype> {
   size_t prefetch_depth_ = 1;
   std::mutex mutex_, generator_mutex_;
   std::condition_variable cv_full_, cv_free_, cv_push_;
+  double stats_[3] = {0, 0, 0};
   std::thread thread_[kProducers];
   std::mutex draw_mutex_;                 // the parameter stream: batches are drawn one at a time, in ticket order
   uint64_t next_ticket_ = 0, next_push_ = 0;  // commission order of the batches = their order in the prefetch queue

@@ -259,6 +259,28 @@ __device__ __forceinline__ bool box_hits_tile(const int32_t* b, int tx0, int ty0
   return b[1] <= ty0 + TH - 1 && b[3] >= ty0 && b[0] <= tx0 + TW - 1 && b[2] >= tx0;
 }
 
+// Mode 9: the pre-pass materialises a warped outline's frame-1 masks only where they can be non-zero -- the outline's
+// frame-1 box (already widened by the field's reach, flatten.cpp) clipped to the frame, columns rounded outwards to whole
+// four-pixel words. Everything outside reads as 0.
+struct WarpRegion {
+  int x0, y0, x1, y1;  // inclusive; x0 % 4 == 0, (x1 + 1) % 4 == 0 or x1 == W - 1
+  __device__ __forceinline__ bool empty() const { return x1 < x0 || y1 < y0; }
+};
+__device__ __forceinline__ WarpRegion warp_region(const int32_t* b, int W, int H) {
+  WarpRegion r;
+  r.x0 = max(b[0], 0) & ~3; r.y0 = max(b[1], 0);
+  r.x1 = min(min(b[2], W - 1) | 3, W - 1); r.y1 = min(b[3], H - 1);
+  return r;
+}
+__device__ __forceinline__ void warped_mask_words(const RenderArgs& a, int slot, int x0, int y, uint32_t& aa, uint32_t& na) {
+  const WarpRegion r = warp_region(a.shapes[a.deform_shape[slot]].bbox[1], a.W, a.H);
+  if (x0 < r.x0 || x0 > r.x1 || y < r.y0 || y > r.y1) { aa = 0u; na = 0u; return; }
+  const size_t P = (size_t)a.W * a.H;
+  const uint8_t* mw = a.mask_warp + (size_t)slot * 2 * P + (size_t)y * a.W + x0;
+  aa = *reinterpret_cast<const uint32_t*>(mw);
+  na = *reinterpret_cast<const uint32_t*>(mw + P);
+}
+
 // ------------------------------------------------------------------------------------------------
 // binning: which objects touch which tile (so that background-only tiles never enter the object path)
 // ------------------------------------------------------------------------------------------------
@@ -576,11 +598,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
         for (int f = 0; f < 2; ++f) {
           const int l = jb.slot[f];
           if (l < 0) {
-            if (kDeform && f == 1 && jb.deform >= 0 && live) {
-              const uint8_t* mw = a.mask_warp + (size_t)jb.deform * 2 * P + (size_t)y * W + x0;
-              vaa[1] = *reinterpret_cast<const uint32_t*>(mw);
-              vna[1] = *reinterpret_cast<const uint32_t*>(mw + P);
-            }
+            if (kDeform && f == 1 && jb.deform >= 0 && live) warped_mask_words(a, jb.deform, x0, y, vaa[1], vna[1]);
             continue;
           }
           const int4 c4 = *reinterpret_cast<const int4*>(&s_cover[l][warp][lane * 4]);
@@ -1065,11 +1083,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster
         for (int f = 0; f < 2; ++f) {
           const int l = s_out[k].layer[f];
           if (l < 0) {
-            if (kDeform && f == 1 && s_out[k].deform >= 0 && live) {
-              const uint8_t* mw = a.mask_warp + (size_t)s_out[k].deform * 2 * P + (size_t)y * W + x0;
-              vaa[1] = *reinterpret_cast<const uint32_t*>(mw);
-              vna[1] = *reinterpret_cast<const uint32_t*>(mw + P);
-            }
+            if (kDeform && f == 1 && s_out[k].deform >= 0 && live) warped_mask_words(a, s_out[k].deform, x0, y, vaa[1], vna[1]);
             continue;
           }
           const int4 c4 = *reinterpret_cast<const int4*>(&s_cover[l][warp][lane * 4]);
@@ -1524,7 +1538,8 @@ __global__ void __launch_bounds__(RENDER_THREADS) deform_raster_kernel(RenderArg
   const FlatShape& sh = a.shapes[a.deform_shape[slot]];
   uint8_t* out = a.mask_raw + (size_t)slot * 2 * P + (size_t)y * W + x0;
   uint32_t paa = 0, pna = 0;
-  if (box_hits_tile(sh.raw1, tx0, ty0)) {
+  if (!box_hits_tile(sh.raw1, tx0, ty0)) return;  // the warp pass reads nothing outside the outline's box (block-uniform)
+  {
     for (int i = tid; i < TH * TW; i += RENDER_THREADS) { (&s_cover[0][0])[i] = 0; (&s_area[0][0])[i] = 0; }
     if (tid < TH) s_carry[tid] = 0;
     __syncthreads();
@@ -1558,19 +1573,40 @@ __global__ void __launch_bounds__(RENDER_THREADS) deform_raster_kernel(RenderArg
     *reinterpret_cast<uint32_t*>(out + P) = pna;
   }
 }
-// (b) applyWarpFieldToTexture(mask, iflow): out(x,y) = trunc(bilinear_0(mask, (x,y) + iflow(x,y)))
+// (b) applyWarpFieldToTexture(mask, iflow): out(x,y) = trunc(bilinear_0(mask, (x,y) + iflow(x,y))), evaluated over the
+// outline's warp region only (one thread = one four-pixel word of it; the raw mask is 0 outside the outline's own box, where
+// pass (a) wrote nothing)
 __global__ void deform_warp_kernel(RenderArgs a) {
   const int W = a.W, H = a.H;
   const size_t P = (size_t)W * H;
   const int slot = blockIdx.y >> 1, which = blockIdx.y & 1;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  const int x = (int)(i % W), y = (int)(i / W);
+  const FlatShape& sh = a.shapes[a.deform_shape[slot]];
+  const WarpRegion r = warp_region(sh.bbox[1], W, H);
+  if (r.empty()) return;
+  const int wpr = (r.x1 - r.x0 + 4) >> 2;  // words per region row
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int row = i / wpr;
+  if (row > r.y1 - r.y0) return;
+  const int y = r.y0 + row, xw = r.x0 + 4 * (i - row * wpr);
+  const int bx0 = max(sh.raw1[0], 0), by0 = max(sh.raw1[1], 0), bx1 = min(sh.raw1[2], W - 1), by1 = min(sh.raw1[3], H - 1);
   const int fw = W + 1, fh = H + 1;
   const float* ifl = a.fields + ((size_t)a.deform_field[slot] * 2 + 1) * 2 * fw * fh;
-  const float sx = x + ifl[(size_t)y * fw + x], sy = y + ifl[(size_t)fw * fh + (size_t)y * fw + x];
   const uint8_t* src = a.mask_raw + ((size_t)slot * 2 + which) * P;
-  a.mask_warp[((size_t)slot * 2 + which) * P + i] = (uint8_t)dirichlet_u8(src, W, H, sx, sy);
+  uint32_t out = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = xw + k;
+    if (x >= W) break;
+    const float fx = x + ifl[(size_t)y * fw + x], fy = y + ifl[(size_t)fw * fh + (size_t)y * fw + x];
+    int ix, iy;
+    float dx, dy;
+    if (!dirichlet_setup(fx, fy, ix, iy, dx, dy)) continue;
+    auto tap = [&](int px, int py) -> float { return (px < bx0 || py < by0 || px > bx1 || py > by1) ? 0.f : (float)src[(size_t)py * W + px]; };
+    const float v = cimg_lerp2(tap(ix, iy), tap(ix + 1, iy), tap(ix, iy + 1), tap(ix + 1, iy + 1), dx, dy);
+    out |= (uint32_t)(unsigned char)v << (8 * k);
+  }
+  if (xw + 3 < W) *reinterpret_cast<uint32_t*>(a.mask_warp + ((size_t)slot * 2 + which) * P + (size_t)y * W + xw) = out;
+  else for (int k = 0; xw + k < W; ++k) a.mask_warp[((size_t)slot * 2 + which) * P + (size_t)y * W + xw + k] = (uint8_t)(out >> (8 * k));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2078,7 +2114,7 @@ int launch_deform_prepass(const RenderArgs& a, cudaStream_t s) {
   const int tiles_x = (a.W + TW - 1) / TW, tiles_y = (a.H + TH - 1) / TH;
   deform_raster_kernel<<<dim3(tiles_x * tiles_y, a.n_deform), RENDER_THREADS, 0, s>>>(a);
   const size_t P = (size_t)a.W * a.H;
-  deform_warp_kernel<<<dim3((unsigned)((P + 255) / 256), 2 * a.n_deform), 256, 0, s>>>(a);
+  deform_warp_kernel<<<dim3((unsigned)((P / 4 + 255) / 256 + 1), 2 * a.n_deform), 256, 0, s>>>(a);  // (blocks beyond an outline's region leave at once)
   return 2;
 }
 

@@ -332,13 +332,17 @@ def test_jpeg_textures_through_nvjpeg(ofdg, tmp_path):
     Image.fromarray(rgb).save(tmp_path / "b.jpg", quality=95, subsampling=0, progressive=True)
     Image.fromarray(rgb[:, :, 1]).save(tmp_path / "c.jpg", quality=90)
     for name in ("a.jpg", "b.jpg", "c.jpg"):
-        w, h, planar = ofdg.decode_texture_file(tmp_path / name)
+        planar = ofdg.decode_texture_file(tmp_path / name)
         want = np.asarray(Image.open(tmp_path / name).convert("RGB")).astype(int)
-        assert (w, h) == (640, 480)
+        assert planar.shape == (3, 480, 640)
         got = planar[::-1].transpose(1, 2, 0).astype(int)            # planar B,G,R -> interleaved R,G,B
         d = np.abs(got - want)
-        assert d.max() <= 3 and d.mean() < 0.6, (name, d.max(), d.mean())  # decoders differ in IDCT / upsampling rounding only
-        assert np.abs(got - rgb.astype(int) if name != "c.jpg" else 0).mean() < 8
+        # decoders differ in IDCT rounding and, for subsampled chroma (a.jpg, 4:2:0), in the upsampling filter: libjpeg's "fancy"
+        # triangle filter against nvJPEG's (measured: max 6, mean 0.77 on 4:2:0; <= 3 / < 0.6 on 4:4:4 and grayscale)
+        lim_max, lim_mean = (12, 1.5) if name == "a.jpg" else (3, 0.6)
+        assert d.max() <= lim_max and d.mean() < lim_mean, (name, d.max(), d.mean())
+        if name != "c.jpg":
+            assert np.abs(got - rgb.astype(int)).mean() < 8  # and it is the picture that was encoded
     # and through the layer's list loader
     (tmp_path / "db.txt").write_text(str(tmp_path / "a.jpg") + "\n" + str(tmp_path / "b.jpg") + "\n")
     proto = ('layer { type: "DataGeneration" top: "a" top: "b" top: "c" data_param { batch_size: 2 prefetch: 1 } '
