@@ -489,6 +489,36 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_other_configs:
         other = other_config_legs(o, torch, args, local, stream)
 
+    # ---- optional epilogue at N > 1: the ranks' finished blobs gathered to a training rank over NVLink (NCCL gather = send / recv)
+    gather_leg = None
+    if dist is not None and not args.no_gather:
+        outs = None
+        if rank == 0:
+            outs = [torch.empty((world * B, 3, H, W), device="cuda"), torch.empty((world * B, 3, H, W), device="cuda"),
+                    torch.empty((world * B, 2, H, W), device="cuda")]
+        torch.cuda.set_stream(torch.cuda.default_stream())
+        for _ in range(3):
+            o.gather_blobs([img0, img1, flow], dst=0, out=outs)
+        barrier()
+        n_g = 20
+        ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ga.record()
+        for _ in range(n_g):
+            o.gather_blobs([img0, img1, flow], dst=0, out=outs)
+        gb.record()
+        barrier()
+        gms = ga.elapsed_time(gb) / n_g
+        t = torch.tensor([gms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gms = float(t.item())
+        recv = (world - 1) * B * 8 * H * W * 4
+        gather_leg = {"ms_per_gather": gms, "bytes_into_rank0": recv, "gbs_into_rank0": recv / (gms * 1e-3) / 1e9,
+                      "samples_per_s": world * B / (gms * 1e-3),
+                      "what": f"ofdg_b200.gather_blobs: {world} x {B} samples of float blobs gathered to rank 0 with torch.distributed (NCCL) over NVLink; "
+                              "not part of `value` (no collective on the generation path)"}
+        torch.cuda.set_stream(tstream)
+        del outs
+
     # ---- the Caffe-style layer, the actual drop-in: prototxt -> LayerRegistry -> LayerSetUp -> Forward_gpu x steps
     layer_leg = None
     if world == 1 and not args.no_layer and (W, H) == (512, 384):
@@ -562,6 +592,7 @@ def run_ours(args):
         "production_mode": production,
         "layer_forward_gpu": layer_leg,
         "other_configs": other,
+        "gather_to_training_rank": gather_leg,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ab, "kernel_ms": kern_ms,
@@ -624,6 +655,7 @@ def main():
     ap.add_argument("--no-attribution", action="store_true", help="skip the per-kernel attribution pass")
     ap.add_argument("--no-layer", action="store_true", help="skip the DataGenerationLayer::Forward_gpu leg")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the config 3 / config 5 legs")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the gather-to-rank-0 leg")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from an ncu --set full capture (profiles/)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

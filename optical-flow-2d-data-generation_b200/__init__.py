@@ -645,6 +645,27 @@ def synth_textures(n, w=1024, h=768, seed=0, first_index=0):
 # ---------------------------------------------------------------------------------------------------
 # Caffe-style layer surface (csrc/host/layer.hpp): prototxt in, three top blobs out.
 # ---------------------------------------------------------------------------------------------------
+def gather_blobs(blobs, dst=0, group=None, out=None):
+    """The optional epilogue of sharded generation (BASELINE north_star): every rank's finished blobs
+    (img0, img1, flow -- device tensors under NCCL, host tensors under gloo) are gathered to the training rank `dst`,
+    which receives them stacked along the batch axis in rank order: [(world * N, 3, H, W), (world * N, 3, H, W),
+    (world * N, 2, H, W)]; the other ranks get None. No collective sits on the generation path itself. `out`, on the
+    destination rank, is an optional list of preallocated stacked tensors to receive into."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    res = []
+    for i, b in enumerate(blobs):
+        if rank == dst:
+            stacked = out[i] if out is not None else torch.empty((world * b.shape[0],) + tuple(b.shape[1:]), dtype=b.dtype, device=b.device)
+            parts = list(stacked.split(b.shape[0], dim=0))  # views: the gather lands in place
+            dist.gather(b, parts, dst=dst, group=group)
+            res.append(stacked)
+        else:
+            dist.gather(b, None, dst=dst, group=group)
+    return res if rank == dst else None
+
+
 def parse_prototxt(text):
     """Fields of a prototxt `layer { ... }` block as the layer sees them."""
     ints = (C.c_int32 * 7)()

@@ -411,6 +411,7 @@ ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, 
   a.batch = ds.batch;
   a.W = g->cfg.width; a.H = g->cfg.height;
   a.prep_w = ds.prep_w; a.prep_h = ds.prep_h;
+  a.float_bias = 0x4B000000u;
   a.use_aa = g->cfg.use_antialiasing;
   a.pool = (const uchar4*)g->pool.p;
   a.tex_info = (const ofdg::TexInfo*)g->tex_info_dev.p;
@@ -780,7 +781,12 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
       CK(cudaEventCreateWithFlags(&g->render_done[i], cudaEventDisableTiming));
     }
     for (cudaEvent_t& e2 : g->chunk_copied) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming | cudaEventBlockingSync));
-    if (const char* t = std::getenv("OFDG_TRANSPORT")) g->transport_u8 = std::string(t) != "f32";  // "f32": float blobs cross PCIe as they are
+    // Host-blob transport. Bytes + host widening move 176 MB over PCIe and 553 MB through host DRAM per 64-sample step, plain
+    // float blobs 403 MB over both. One GPU per host is PCIe-bound (bytes win: 20.7k against 9k samples/s at 57 GB/s); with
+    // three or more ranks sharing one host the host's DRAM bandwidth (~155 GB/s measured) is the bound and the plain float
+    // transfer needs 27 % less of it. OFDG_TRANSPORT=u8|f32 overrides.
+    if (const char* lw = std::getenv("LOCAL_WORLD_SIZE")) g->transport_u8 = std::atoi(lw) < 3;
+    if (const char* t = std::getenv("OFDG_TRANSPORT")) g->transport_u8 = std::string(t) != "f32";
     if (const char* t = std::getenv("OFDG_RENDER")) g->split_render = std::string(t) != "fused";
     if (const char* t = std::getenv("OFDG_TEST_PAIR_CAP")) g->pair_cap_limit = std::atoi(t);
     if (const char* t = std::getenv("OFDG_TEST_PHILOX_FG")) g->philox_fg_override = std::atoi(t);

@@ -892,12 +892,15 @@ struct PairOutline {   // one outline of the pair's object, staged in shared mem
   int deform;
 };
 
-__global__ void __launch_bounds__(256) bin_pairs_kernel(RenderArgs a) {
+constexpr int BIN_THREADS = 64;  // one tile per thread; a sample's tiles are split over gridDim.y blocks
+__global__ void __launch_bounds__(BIN_THREADS) bin_pairs_kernel(RenderArgs a) {
   __shared__ int s_box[256][8];
   __shared__ int2 s_shapes[256];  // per object: first outline, outline count | composite << 16 (saves the raster kernel two dependent loads per pair)
-  __shared__ int s_scan[256];
+  __shared__ int s_scan[BIN_THREADS];
   __shared__ int s_base;
-  const int sample = blockIdx.x, tid = threadIdx.x;
+  // grid = (sample, part): the parts of a sample split its tiles (and its background rows) among them; each part claims its
+  // own slice of the pair list, so the pairs of a tile stay consecutive, which is all the raster and shade kernels rely on
+  const int sample = blockIdx.x, tid = threadIdx.x, part = blockIdx.y, n_parts = gridDim.y;
   const FlatSample& smp = a.samples[sample];
   const int n_obj = min(smp.obj_count, 255);
   const int tiles_x = (a.W + TW - 1) / TW, tiles_y = (a.H + TH - 1) / TH, n_tiles = tiles_x * tiles_y;
@@ -908,7 +911,7 @@ __global__ void __launch_bounds__(256) bin_pairs_kernel(RenderArgs a) {
   }
   __syncthreads();
   if (a.bg_rows) {  // the background's span-interpolator rows (frame 1 = the prepared texture under I^-1 * M * I, DG.cpp:665-682)
-    for (int y = tid; y < a.H; y += blockDim.x) {
+    for (int y = tid + part * blockDim.x; y < a.H; y += blockDim.x * n_parts) {
       RowWarp rw;
       rw.init(smp.bg_tex_inv, (double)(y + a.H / 2), 2 * a.W);
       int4* r = a.bg_rows + ((size_t)sample * a.H + y) * 2;
@@ -917,7 +920,7 @@ __global__ void __launch_bounds__(256) bin_pairs_kernel(RenderArgs a) {
     }
   }
   int mine = 0;  // pairs of this thread's tiles
-  for (int t = tid; t < n_tiles; t += blockDim.x) {
+  for (int t = tid + part * blockDim.x; t < n_tiles; t += blockDim.x * n_parts) {
     const int tx0 = (t % tiles_x) * TW, ty0 = (t / tiles_x) * TH;
     uint8_t* out = a.tile_hits + ((size_t)sample * n_tiles + t) * TILE_HIT_STRIDE;  // the fused kernel's bin entry (its overflow fallback)
     int cnt = 0;
@@ -932,14 +935,14 @@ __global__ void __launch_bounds__(256) bin_pairs_kernel(RenderArgs a) {
   // exclusive scan of the threads' counts, then one atomic per sample claims the sample's slice of the pair list
   s_scan[tid] = mine;
   __syncthreads();
-  for (int d = 1; d < 256; d <<= 1) {
+  for (int d = 1; d < BIN_THREADS; d <<= 1) {
     const int v = tid >= d ? s_scan[tid - d] : 0;
     __syncthreads();
     s_scan[tid] += v;
     __syncthreads();
   }
-  if (tid == 255) {
-    const int total = s_scan[255];
+  if (tid == BIN_THREADS - 1) {
+    const int total = s_scan[BIN_THREADS - 1];
     const int base = atomicAdd(&a.pair_ctl[0], total);
     if (base + total > a.pair_cap) {  // more pairs than the mask buffer holds (the host sizes it from an upper bound, so this is a bug trap):
       a.pair_ctl[1] = 1;              // the raster and shade kernels skip the batch, and the host reports it after its next synchronisation
@@ -949,8 +952,8 @@ __global__ void __launch_bounds__(256) bin_pairs_kernel(RenderArgs a) {
   }
   __syncthreads();
   int off = s_base + s_scan[tid] - mine;
-  const bool fits = s_base + s_scan[255] <= a.pair_cap;
-  for (int t = tid; t < n_tiles; t += blockDim.x) {
+  const bool fits = s_base + s_scan[BIN_THREADS - 1] <= a.pair_cap;
+  for (int t = tid + part * blockDim.x; t < n_tiles; t += blockDim.x * n_parts) {
     const int tx0 = (t % tiles_x) * TW, ty0 = (t / tiles_x) * TH;
     const int first = off;
     if (fits)
@@ -1874,6 +1877,27 @@ __global__ void __launch_bounds__(PREP_THREADS, OFDG_PREP_MIN_BLOCKS) bg_prep_ke
   const int X0 = p.need[0] + blockIdx.x * PT, Y0 = p.need[1] + blockIdx.y * PT;
   if (X0 > p.need[2] || Y0 > p.need[3]) return;
   const int X1 = min(X0 + PT - 1, p.need[2]), Y1 = min(Y0 + PT - 1, p.need[3]);
+  // `need` is the bounding box of what the renderer reads: the centre W x H window (frame 0) and the footprint of the frame-1
+  // warp, a parallelogram. A tile in a corner of that box that touches neither is skipped: its corners (three pixels of margin
+  // for the filter taps and roundings), taken back through the forward transform, must bound a rectangle that meets the output
+  // window. Not applied when the footprint left the canvas (reflect wrap: `need` then spans a whole axis), to backgrounds
+  // with a warp field (they read anywhere) and to the parity instrumentation (a.flow == nullptr: the whole box is compared).
+  if (a.flow && a.samples[sample].bg_field < 0 && !(p.need[0] == 0 && p.need[2] == W2 - 1) && !(p.need[1] == 0 && p.need[3] == H2 - 1)) {
+    const bool frame0 = X0 <= a.W / 2 + a.W - 1 && X1 >= a.W / 2 && Y0 <= a.H / 2 + a.H - 1 && Y1 >= a.H / 2;
+    if (!frame0) {
+      const double* m = a.samples[sample].bg_tex_inv;  // prepared = m * output
+      const double det = m[0] * m[3] - m[1] * m[2];
+      double ux0 = 1e300, ux1 = -1e300, uy0 = 1e300, uy1 = -1e300;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double px = ((c & 1) ? X1 + 4 : X0 - 4) - m[4], py = ((c & 2) ? Y1 + 4 : Y0 - 4) - m[5];
+        const double ox = (px * m[3] - py * m[2]) / det, oy = (py * m[0] - px * m[1]) / det;
+        ux0 = fmin(ux0, ox); ux1 = fmax(ux1, ox); uy0 = fmin(uy0, oy); uy1 = fmax(uy1, oy);
+      }
+      // the output pixels whose centres (+0.5) the span interpolator maps: columns W/2 .. W/2 + W, rows H/2 .. H/2 + H
+      if (ux1 < a.W / 2 - 1.0 || ux0 > a.W / 2 + a.W + 2.0 || uy1 < a.H / 2 - 1.0 || uy0 > a.H / 2 + a.H + 2.0) return;
+    }
+  }
   const int* pos_x = a.pos_x + (size_t)min(p.crop_w, W2 - 1) * W2;  // rows >= n are never read (no table needed when shrinking)
   const double* alpha_x = a.alpha_x + (size_t)min(p.crop_w, W2 - 1) * W2;
   const int* pos_y = a.pos_y + (size_t)min(p.crop_h, H2 - 1) * H2;
@@ -1932,12 +1956,39 @@ __global__ void __launch_bounds__(PREP_THREADS, OFDG_PREP_MIN_BLOCKS) bg_prep_ke
     const bool inside = sC.inside != 0, fast = sC.fast != 0;
     const TapMap tm = sC.tm;
     if (fast) {
+      // The hot loop of the kernel (about 40 % of its instructions), written for the instruction count: everything that does not
+      // change stays in registers, texels are addressed by a 32-bit index from the texture's base, the staging row is a running
+      // shared-memory address, and the 2^23 bias the byte -> float permutes insert lives in a register so that their selectors
+      // stay immediates. Arithmetic and roundings are those of rotated_px_fast (CImg's _linear_atXY formula).
       float xf = (float)(bx + lx), yf = (float)(by + ly);  // float twins of the walk (small integers: exact)
       const float fstep_x = (float)step_x, fstep_y = (float)step_y, fcw = (float)cw;
+      const float ca = p.ca, sa = p.sa, w2 = p.w2, h2 = p.h2, rw2 = p.rw2, rh2 = p.rh2;
+      const uint32_t* tex32 = reinterpret_cast<const uint32_t*>(tex);
+      const int cs = tm.cs, rsw = tm.rs * ti.w, idx0 = tm.ry0 * ti.w + tm.cx0;  // texel index = idx0 + rsw * iy + cs * ix
+      const uint32_t bias = a.float_bias;  // 0x4B000000
+      uint32_t saddr = smem_u32(&sA[0][0]) + (uint32_t)(ly * PS + lx) * 4u;
+      const uint32_t sstep = (uint32_t)(step_y * PS + step_x) * 4u, swrap = (uint32_t)(PS - cw) * 4u;
       while (ly < ch) {
-        sA[ly][lx] = rotated_px_fast(tex, ti.w, p, tm, xf, yf);
-        lx += step_x; ly += step_y; xf += fstep_x; yf += fstep_y;
-        if (lx >= cw) { lx -= cw; ++ly; xf -= fcw; yf += 1.f; }
+        const float xc = xf - rw2, yc = yf - rh2;
+        const float fx = w2 + xc * ca + yc * sa, fy = h2 - xc * sa + yc * ca;
+        float fix, fiy;
+        const unsigned int ix = floor_bits(fx, fix), iy = floor_bits(fy, fiy);  // == (unsigned int)fx: fx, fy > 0
+        const float dx = fx - fix, dy = fy - fiy;
+        const int i00 = idx0 + rsw * (int)iy + cs * (int)ix;
+        const int ox = dx > 0 ? cs : 0, oy = dy > 0 ? rsw : 0;
+        const uint32_t pcc = tex32[i00], pnc = tex32[i00 + ox], pcn = tex32[i00 + oy], pnn = tex32[i00 + ox + oy];
+        uint32_t t[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float Mcc = __uint_as_float(__byte_perm(pcc, bias, 0x7440u + c)), Mnc = __uint_as_float(__byte_perm(pnc, bias, 0x7440u + c)),
+                      Mcn = __uint_as_float(__byte_perm(pcn, bias, 0x7440u + c)), Mnn = __uint_as_float(__byte_perm(pnn, bias, 0x7440u + c));
+          const float v = (Mcc - 8388608.0f) + dx * ((Mnc - Mcc) + dy * ((Mcc - Mcn) + (Mnn - Mnc))) + dy * (Mcn - Mcc);
+          t[c] = __float_as_uint(__fadd_rz(fmaxf(v, 0.f), 8388608.0f));
+        }
+        const uint32_t px = __byte_perm(__byte_perm(t[0], t[1], 0x0040u), t[2], 0x5410u);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(px) : "memory");
+        lx += step_x; ly += step_y; xf += fstep_x; yf += fstep_y; saddr += sstep;
+        if (lx >= cw) { lx -= cw; ++ly; xf -= fcw; yf += 1.f; saddr += swrap; }
       }
     } else {
       while (ly < ch) {
@@ -2161,7 +2212,10 @@ size_t pair_row_bytes_per_pair() { return (size_t)PAIR_ROW_STRIDE * sizeof(int4)
 
 int launch_bin_pairs(const RenderArgs& a, cudaStream_t s) {
   cudaMemsetAsync(a.pair_ctl, 0, 3 * sizeof(int), s);
-  bin_pairs_kernel<<<a.batch, 256, 0, s>>>(a);
+  {
+    const int tiles = ((a.W + TW - 1) / TW) * ((a.H + TH - 1) / TH);
+    bin_pairs_kernel<<<dim3(a.batch, max(1, min(16, (tiles + BIN_THREADS - 1) / BIN_THREADS))), BIN_THREADS, 0, s>>>(a);  // 64 tiles (and their share of the background rows) per block
+  }
   return 1;
 }
 

@@ -31,6 +31,7 @@ struct RenderArgs {
   // split render path: (object, tile) pairs (bin_pairs_kernel -> raster_pairs_kernel -> shade_kernel)
   int2* tile_range;           // [batch][tiles] {first pair, pair count}, pairs of a tile in z-order
   int4* pair_list;            // [pair_cap] {sample * 256 + object, tile, first outline (absolute), outline count | composite << 16}
+  uint32_t float_bias;        // 0x4B000000 (2^23 as float bits), handed in as a parameter: the byte -> float permutes that insert it keep immediate selectors
   int prep_w, prep_h;         // extent of the largest needed part of a prepared background (0: the whole canvas): bg_prep_kernel's grid
   uint32_t* pair_masks;       // [pair_cap][AA 0 | AA 1 | non-AA 0 | non-AA 1][TH][32] four pixels per word
   // span-interpolator rows (agg::span_interpolator_linear::begin, DataGenerator.cpp:203-221) hoisted out of the shade kernel:

@@ -31,12 +31,15 @@ def _worker(rank, world, port, out):
     # whole-job time = max over ranks (bench.py)
     t = torch.tensor([1.0 + rank], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    # optional gather of a (tiny stand-in for a) finished blob to the training rank
-    blob = torch.full((2, 3), float(rank))
-    gathered = [torch.zeros(2, 3) for _ in range(world)] if rank == 0 else None
-    dist.gather(blob, gathered, dst=0)
+    # optional gather of the finished blobs to the training rank (ofdg_b200.gather_blobs; small stand-ins for the three blobs here)
+    blobs = [torch.full((2, 3, 4, 5), float(rank)), torch.full((2, 3, 4, 5), 10.0 + rank), torch.full((2, 2, 4, 5), 20.0 + rank)]
+    got = o.gather_blobs(blobs, dst=0)
     if rank == 0:
-        out.put(([int(v.item()) for v in allv], float(t.item()), [float(g[0, 0]) for g in gathered]))
+        assert [tuple(g.shape) for g in got] == [(2 * world, 3, 4, 5), (2 * world, 3, 4, 5), (2 * world, 2, 4, 5)]
+        assert float(got[2][2 * (world - 1), 0, 0, 0]) == 20.0 + world - 1
+        out.put(([int(v.item()) for v in allv], float(t.item()), [float(got[0][2 * r, 0, 0, 0]) for r in range(world)]))
+    else:
+        assert got is None
     dist.barrier()
     dist.destroy_process_group()
 
