@@ -218,7 +218,7 @@ struct ofdg_generator {
   cudaStream_t prep_stream = nullptr;
   cudaEvent_t set_prep_done[2] = {nullptr, nullptr}, set_raster_done[2] = {nullptr, nullptr}, set_shade_done[2] = {nullptr, nullptr};
   bool set_used[2] = {false, false};
-  bool pipeline = false;
+  bool pipeline = false, philox_pipeline = false;
   uint64_t pipe_calls = 0;
   cudaEvent_t bin_fork = nullptr, bin_join = nullptr;
   bool raster_overlap = false, philox_raster_overlap = false;
@@ -812,6 +812,7 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
       // which is also how per-kernel times are measured (the spans of ofdg_kernel_times then do not overlap)
       const char* pl = std::getenv("OFDG_PIPELINE");
       g->pipeline = g->raster_overlap && !(pl && std::string(pl) == "0");
+      if (const char* pp = std::getenv("OFDG_PHILOX_PIPELINE")) g->philox_pipeline = std::string(pp) == "1";
       if (g->pipeline) {
         const char* pr = std::getenv("OFDG_PREP_PRIORITY");  // "hi": the preparation stream shares the raster's priority
         CK(cudaStreamCreateWithPriority(&g->prep_stream, cudaStreamNonBlocking, (pr && std::string(pr) == "hi") ? hi : 0));
@@ -1591,7 +1592,10 @@ int ofdg_generate_philox(ofdg_generator* g, uint64_t seed, uint64_t first_sample
       philox_collect(g, set, s);
     }
     ensure_scratch(g, batch);
-    const int pset = (looked_ahead && g->philox_raster_overlap) ? pipeline_set(g, g->ph[set].scene) : -1;
+    // The cross-batch pipeline is off for the device-side stream unless OFDG_PHILOX_PIPELINE=1: its look-ahead parameter kernels
+    // already run beside the previous batch's render, and a third and fourth concurrent kernel cost more than they gain
+    // (measured at batch 64: 118.6k samples/s in line, 111.1k pipelined).
+    const int pset = (g->philox_pipeline && looked_ahead && g->philox_raster_overlap) ? pipeline_set(g, g->ph[set].scene) : -1;
     if (pset >= 0)  // the scene was written on the look-ahead stream: the front end only waits for that, not for the previous batch on s
       run_kernels_pipelined(g, with_extra_tops(g, make_args(g, g->ph[set].scene, d_img0, d_img1, d_flow, pset)), s, pset, g->ph[set].ready);
     else

@@ -58,6 +58,7 @@ def test_side_stream_changes_no_bit(ofdg, textures8, mode, philox, monkeypatch):
     inline = _run(ofdg, textures8, mode, philox)
     monkeypatch.delenv("OFDG_BIN_OVERLAP")
     monkeypatch.delenv("OFDG_PIPELINE")
+    monkeypatch.setenv("OFDG_PHILOX_PIPELINE", "1")  # (off by default for the device stream; its pipelined form stays covered)
     forked = _run(ofdg, textures8, mode, philox)
     assert inline[0][0].std() > 10
     assert not np.array_equal(inline[0][2], inline[1][2]), "the batches are supposed to differ"
