@@ -345,10 +345,12 @@ def other_config_legs(o, torch, args, device, stream):
     return out
 
 
-def host_memory_probe(o, threads=8, mb=96, reps=3):
+def host_memory_probe(o, threads=None, mb=96, reps=3):
     """What the host's memory system sustains for the host-blob path's last stage: `threads` threads widening uint8 -> float32 with
     non-temporal stores (csrc/host/expand.cpp), GB/s of DRAM traffic (1 byte read + 4 written per element)."""
     import numpy as np
+    if threads is None:
+        threads = max(4, min(32, (os.cpu_count() or 8) // 2))
     n = mb << 20
     src = [np.full(n, 7, np.uint8) for _ in range(threads)]
     dst = [np.empty(n, np.float32) for _ in range(threads)]

@@ -781,11 +781,11 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
       CK(cudaEventCreateWithFlags(&g->render_done[i], cudaEventDisableTiming));
     }
     for (cudaEvent_t& e2 : g->chunk_copied) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming | cudaEventBlockingSync));
-    // Host-blob transport. Bytes + host widening move 176 MB over PCIe and 553 MB through host DRAM per 64-sample step, plain
-    // float blobs 403 MB over both. One GPU per host is PCIe-bound (bytes win: 20.7k against 9k samples/s at 57 GB/s); with
-    // three or more ranks sharing one host the host's DRAM bandwidth (~155 GB/s measured) is the bound and the plain float
-    // transfer needs 27 % less of it. OFDG_TRANSPORT=u8|f32 overrides.
-    if (const char* lw = std::getenv("LOCAL_WORLD_SIZE")) g->transport_u8 = std::atoi(lw) < 3;
+    // Host-blob transport: bytes + host widening (176 MB over PCIe, 553 MB through host DRAM per 64-sample step) unless
+    // OFDG_TRANSPORT=f32 asks for plain float blobs (403 MB over both). Measured with 8 ranks on one 32-core host
+    // (tools/exp_transport_n.sh, profiles/r02_transport_n8.log): bytes 18.6k samples/s for the 8 GPUs together (161 GB/s of host
+    // DRAM traffic: the bound), float 15.0k (94 GB/s of inbound PCIe writes: the host's PCIe ingest saturates first) -- bytes
+    // win at every rank count.
     if (const char* t = std::getenv("OFDG_TRANSPORT")) g->transport_u8 = std::string(t) != "f32";
     if (const char* t = std::getenv("OFDG_RENDER")) g->split_render = std::string(t) != "fused";
     if (const char* t = std::getenv("OFDG_TEST_PAIR_CAP")) g->pair_cap_limit = std::atoi(t);
