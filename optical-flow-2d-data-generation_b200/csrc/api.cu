@@ -318,16 +318,26 @@ void upload_scene_parts(ofdg_generator* g, const ofdg::FlatBatch* parts, int n_p
   if (nd) { ds.deform_shape.reserve(bd + 256); ds.deform_field.reserve(bd + 256); }  // mode 9 only
   ds.batch = (int)ns;
   ds.n_deform = (int)nd;
-  {  // (object, tile) pairs: per frame the tile columns x tile rows the object's box overlaps (bin_pairs_kernel counts the union)
+  {  // (object, tile) pairs: the tiles an object's box overlaps in frame 0 or in frame 1 -- two rectangles of tiles, counted as
+     // |A| + |B| - |A and B|, which is exactly what bin_pairs_kernel's box tests count (the pair buffers are sized from it)
     const int tiles_x = (g->cfg.width + ofdg::TW - 1) / ofdg::TW, tiles_y = (g->cfg.height + ofdg::TH - 1) / ofdg::TH;
     size_t pairs = 0;
     for (int i = 0; i < n_parts; ++i)
-      for (const ofdg::FlatObject& o : parts[i].objects)
+      for (const ofdg::FlatObject& o : parts[i].objects) {
+        int c0[2], c1[2], r0[2], r1[2];
+        size_t n[2];
         for (int f = 0; f < 2; ++f) {
-          const int c0 = std::max(0, o.bbox[f][0] >= 0 ? o.bbox[f][0] / ofdg::TW : 0), c1 = std::min(tiles_x - 1, o.bbox[f][2] >= 0 ? o.bbox[f][2] / ofdg::TW : -1);
-          const int r0 = std::max(0, o.bbox[f][1] >= 0 ? o.bbox[f][1] / ofdg::TH : 0), r1 = std::min(tiles_y - 1, o.bbox[f][3] >= 0 ? o.bbox[f][3] / ofdg::TH : -1);
-          if (c1 >= c0 && r1 >= r0) pairs += (size_t)(c1 - c0 + 1) * (r1 - r0 + 1);
+          c0[f] = std::max(0, o.bbox[f][0] >= 0 ? o.bbox[f][0] / ofdg::TW : 0); c1[f] = std::min(tiles_x - 1, o.bbox[f][2] >= 0 ? o.bbox[f][2] / ofdg::TW : -1);
+          r0[f] = std::max(0, o.bbox[f][1] >= 0 ? o.bbox[f][1] / ofdg::TH : 0); r1[f] = std::min(tiles_y - 1, o.bbox[f][3] >= 0 ? o.bbox[f][3] / ofdg::TH : -1);
+          n[f] = (c1[f] >= c0[f] && r1[f] >= r0[f]) ? (size_t)(c1[f] - c0[f] + 1) * (r1[f] - r0[f] + 1) : 0;
         }
+        size_t both = 0;
+        if (n[0] && n[1]) {
+          const int ca = std::max(c0[0], c0[1]), cb = std::min(c1[0], c1[1]), ra = std::max(r0[0], r0[1]), rb = std::min(r1[0], r1[1]);
+          if (cb >= ca && rb >= ra) both = (size_t)(cb - ca + 1) * (rb - ra + 1);
+        }
+        pairs += n[0] + n[1] - both;
+      }
     ds.pair_bound = pairs;
   }
   ds.prep_w = ds.prep_h = 0;  // the preparation kernel's grid covers the largest needed region, not the whole 2W x 2H canvas

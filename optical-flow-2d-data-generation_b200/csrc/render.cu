@@ -963,185 +963,196 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_pairs_kernel(RenderArgs a) {
   }
 }
 
-template <bool kDeform>
-__global__ void __launch_bounds__(RASTER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster_pairs_kernel(RenderArgs a) {
-  __shared__ int s_cover[NLAYER][RTH][TW];
-  __shared__ int s_area[NLAYER][RTH][TW];
-  __shared__ int s_carry[NLAYER][RTH];
-  __shared__ float s_q255[256];
-  __shared__ PairOutline s_out[NLAYER / 2];
-  __shared__ int s_seg_begin[NLAYER], s_seg_count[NLAYER];
-  __shared__ unsigned s_pairs[RASTER_ITEMS];
-  __shared__ int s_npairs;
-  __shared__ int s_next;
-  if (a.pair_ctl[1]) return;
-  const int total = a.pair_ctl[0] * RSUB;  // work units: RSUB slices per pair
+struct RasterSmem {  // shared memory of one block rasterising (object, tile) pairs
+  int cover[NLAYER][RTH][TW];
+  int area[NLAYER][RTH][TW];
+  int carry[NLAYER][RTH];
+  float q255[256];
+  PairOutline out[NLAYER / 2];
+  int seg_begin[NLAYER], seg_count[NLAYER];
+  unsigned pairs[RASTER_ITEMS];
+  int npairs;
+  int next;
+};
+
+// One work unit (a pair, or a slice of RTH rows of it) by the whole block. kQueue: the block is persistent and claims its next
+// unit from the queue a.pair_ctl[2] while it works on this one (pr_next / pe_next: the claimed unit and its record).
+template <bool kDeform, bool kQueue>
+__device__ __forceinline__ void raster_unit(const RenderArgs& a, RasterSmem& sm, int unit, int total, const int4 pe, int queue_base, int& pr_next,
+                                            int4& pe_next) {
   const int W = a.W, H = a.H;
-  const size_t P = (size_t)W * H;
   const int tiles_x = (W + TW - 1) / TW;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < 256; i += RASTER_THREADS) s_q255[i] = (float)i / 255.f;
-  int4 pe_next = blockIdx.x < total ? a.pair_list[blockIdx.x / RSUB] : make_int4(0, 0, 0, 0);
+  const int pr = unit / RSUB, slice = unit % RSUB;
+  if (kQueue && tid == 0) sm.next = queue_base + atomicAdd(&a.pair_ctl[2], 1);
+  const int tile = pe.y, shape_begin = pe.z;
+  const int tx0 = (tile % tiles_x) * TW, ty0 = (tile / tiles_x) * TH + slice * RTH;
+  const int y = ty0 + warp, x0 = tx0 + lane * 4;
+  const bool live = (y < H) && (x0 < W);
+  const int n_shapes = pe.w & 0xFFFF, composite = pe.w >> 16;
+  uint32_t uaa[2] = {0, 0}, una[2] = {0, 0};
+  if (a.pair_rows && tid >= RASTER_THREADS - 32 && lane < RTH) {
+    // the object's span-interpolator rows over this tile (frame 1 = its texture under the inverse motion, DG.cpp:203-221),
+    // one row per lane of the last warp (the (edge, row) items keep the first warps busy): the shade kernel's eight warps
+    // pick them up instead of each working out its own
+    const FlatObject& ob = a.objects[a.samples[pe.x >> 8].obj_begin + (pe.x & 255)];
+    RowWarp rw;
+    rw.init(ob.tex_inv, (double)(ty0 + lane), W);
+    int4* r = a.pair_rows + (size_t)pr * PAIR_ROW_STRIDE;
+    r[2 + (slice * RTH + lane) * 2] = make_int4(rw.dx.v1, rw.dx.lft, rw.dx.rem, rw.dy.v1);
+    r[3 + (slice * RTH + lane) * 2] = make_int4(rw.dy.lft, rw.dy.rem, 0, 0);
+    if (lane == 0 && slice == 0) {  // what the shade kernel needs of the object, in one record (instead of pair -> object -> texture table)
+      const TexInfo ti = a.tex_info[ob.tex];
+      r[0] = make_int4((int)(uint32_t)(ti.fg_base & 0xFFFFFFFFu), (int)(uint32_t)(ti.fg_base >> 32), ti.fg_pitch, pe.x & 255);
+      r[1] = make_int4(ob.field, 0, 0, 0);
+    }
+  }
+  for (int s0 = 0; s0 < n_shapes; s0 += NLAYER / 2) {
+    const int ns = min(NLAYER / 2, n_shapes - s0);
+    __syncthreads();  // the previous chunk (or pair) is done with the staging and the accumulators
+    if (tid < ns) {   // outline tid of this chunk: which of its frames touch the tile, which layers they get
+      const FlatShape& sh = a.shapes[shape_begin + s0 + tid];
+      PairOutline po;
+      const bool h0 = box_hits_rows(sh.bbox[0], tx0, ty0, RTH), h1 = box_hits_rows(sh.bbox[1], tx0, ty0, RTH);
+      po.deform = (kDeform && h1) ? sh.deform : -1;  // a warped outline's frame-1 masks were materialised by the pre-pass
+      const bool r1 = h1 && po.deform < 0;
+      po.vbegin[0] = sh.vbegin[0]; po.vbegin[1] = sh.vbegin[1];
+      po.vcount[0] = h0 ? sh.vcount[0] : 0; po.vcount[1] = r1 ? sh.vcount[1] : 0;
+      po.layer[0] = h0 ? (signed char)(2 * tid) : (signed char)-1;
+      po.layer[1] = r1 ? (signed char)(2 * tid + 1) : (signed char)-1;
+      po.additive = sh.additive ? 1 : 0;
+      sm.out[tid] = po;
+      sm.seg_begin[2 * tid] = po.vbegin[0]; sm.seg_count[2 * tid] = po.vcount[0];
+      sm.seg_begin[2 * tid + 1] = po.vbegin[1]; sm.seg_count[2 * tid + 1] = po.vcount[1];
+    } else if (tid < NLAYER / 2) {
+      sm.seg_count[2 * tid] = 0; sm.seg_count[2 * tid + 1] = 0;
+    }
+    for (int i = tid; i < 2 * ns * (RTH * TW / 4); i += RASTER_THREADS) {  // outline k owns layers 2k and 2k + 1
+      reinterpret_cast<int4*>(&sm.cover[0][0][0])[i] = make_int4(0, 0, 0, 0);
+      reinterpret_cast<int4*>(&sm.area[0][0][0])[i] = make_int4(0, 0, 0, 0);
+    }
+    if (tid < NLAYER * RTH) (&sm.carry[0][0])[tid] = 0;
+    if (tid == 0) sm.npairs = 0;
+    __syncthreads();
+    if (kQueue && s0 == 0) {  // the claimed pair's record is in flight while this pair is rasterised
+      pr_next = sm.next;
+      if (pr_next < total) pe_next = a.pair_list[pr_next / RSUB];
+    }
+    {
+      // (a) threads over edges: which tile rows does the edge cross? One work item per (edge, row).
+      const int c0 = sm.seg_count[0], c1 = c0 + sm.seg_count[1], c2 = c1 + sm.seg_count[2], c3 = c2 + sm.seg_count[3];
+      for (int e = tid; e < c3; e += RASTER_THREADS) {
+        const int l = e < c0 ? 0 : (e < c1 ? 1 : (e < c2 ? 2 : 3));
+        const int ei = e - (l == 0 ? 0 : (l == 1 ? c0 : (l == 2 ? c1 : c2)));
+        const int n = sm.seg_count[l];
+        const FlatVertex* v = a.verts + sm.seg_begin[l];
+        const FlatVertex p = v[ei], q = v[ei + 1 == n ? 0 : ei + 1];
+        int rlo, rhi;
+        bool left;
+        if (!tile_edge_rows(tx0, ty0, p.x, p.y, q.x, q.y, rlo, rhi, left, RTH)) continue;
+        const int nrows = rhi - rlo + 1;
+        const int base = left ? RASTER_ITEMS : atomicAdd(&sm.npairs, nrows);
+        for (int k = 0; k < nrows; ++k) {
+          if (base + k < RASTER_ITEMS) sm.pairs[base + k] = ((unsigned)l << 28) | ((unsigned)(rlo + k - ty0) << 24) | (unsigned)ei;
+          else tile_edge_row<true>(&sm.cover[l][0][0], &sm.area[l][0][0], &sm.carry[l][0], tx0, ty0, rlo + k, p.x, p.y, q.x, q.y);  // cheap (left of the tile) or list full
+        }
+      }
+    }
+    __syncthreads();
+    {
+      // (b) threads over (edge, row) items: closed-form row segment -> cells
+      const int np = min(sm.npairs, RASTER_ITEMS);
+      // (items stay packed in the first warps: spread over all warps, lane * RTH + warp, the same few dozen divergent items
+      // issue from eight half-empty warps instead of two -- measured 0.160 -> 0.171 ms)
+      for (int i = tid; i < np; i += RASTER_THREADS) {
+        const unsigned w = sm.pairs[i];
+        const int l = (int)(w >> 28), r = ty0 + (int)((w >> 24) & 15u), ei = (int)(w & 0xFFFFFFu);
+        const int n = sm.seg_count[l];
+        const FlatVertex* v = a.verts + sm.seg_begin[l];
+        const FlatVertex p = v[ei], q = v[ei + 1 == n ? 0 : ei + 1];
+        tile_edge_row<true>(&sm.cover[l][0][0], &sm.area[l][0][0], &sm.carry[l][0], tx0, ty0, r, p.x, p.y, q.x, q.y);
+      }
+    }
+    __syncthreads();
+
+    for (int k = 0; k < ns; ++k) {
+      uint32_t vaa[2] = {0, 0}, vna[2] = {0, 0};
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        const int l = sm.out[k].layer[f];
+        if (l < 0) {
+          if (kDeform && f == 1 && sm.out[k].deform >= 0 && live) warped_mask_words(a, sm.out[k].deform, x0, y, vaa[1], vna[1]);
+          continue;
+        }
+        const int4 c4 = *reinterpret_cast<const int4*>(&sm.cover[l][warp][lane * 4]);
+        const int4 a4 = *reinterpret_cast<const int4*>(&sm.area[l][warp][lane * 4]);
+        const int carry = sm.carry[l][warp];
+        const bool cells = (c4.x | c4.y | c4.z | c4.w | a4.x | a4.y | a4.z | a4.w) != 0;
+        if (!__any_sync(0xffffffffu, cells)) {
+          // no outline crosses this row inside the tile: coverage is constant along it
+          if (carry == 0) continue;
+          const int cv = coverage_alpha(carry, 0);
+          vaa[f] = graylut((unsigned)cv) * 0x01010101u;
+          vna[f] = cv >= 128 ? 0xFFFFFFFFu : 0u;
+          continue;
+        }
+        int c[4] = {c4.x, c4.y, c4.z, c4.w}, ar[4] = {a4.x, a4.y, a4.z, a4.w};
+        c[1] += c[0]; c[2] += c[1]; c[3] += c[2];
+        int tot = c[3];  // warp-level inclusive prefix sum over the lanes' cover totals
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          int o = __shfl_up_sync(0xffffffffu, tot, d);
+          if (lane >= d) tot += o;
+        }
+        const int base = tot - c[3] + carry;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cv = coverage_alpha(base + c[i], ar[i]);
+          vaa[f] |= graylut((unsigned)cv) << (8 * i);        // gamma_none
+          vna[f] |= (cv >= 128 ? 255u : 0u) << (8 * i);      // gamma_threshold(0.5), then graylut(255) = 255
+        }
+      }
+
+      if (composite) {
+        if (s0 + k == 0) { uaa[0] = uaa[1] = una[0] = una[1] = 0; }
+        const bool add = sm.out[k].additive != 0;
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          uaa[f] = comp4(uaa[f], vaa[f], add, sm.q255);
+          // non-AA masks stay in {0, 255} (the rules are closed on it) unless a warp field resampled them
+          if (kDeform) una[f] = comp4(una[f], vna[f], add, sm.q255);
+          else una[f] = add ? (una[f] | vna[f]) : (una[f] & ~vna[f]);
+        }
+      } else {
+        uaa[0] = vaa[0]; uaa[1] = vaa[1]; una[0] = vna[0]; una[1] = vna[1];
+      }
+    }
+  }
+  // the object's four masks over this tile: [AA 0, AA 1, non-AA 0, non-AA 1][tile row][lane], one word = four pixels
+  uint32_t* pm = a.pair_masks + (size_t)pr * (4 * TH * 32) + (slice * RTH + warp) * 32 + lane;
+  pm[0 * TH * 32] = uaa[0]; pm[1 * TH * 32] = uaa[1]; pm[2 * TH * 32] = una[0]; pm[3 * TH * 32] = una[1];
+  if (kQueue && n_shapes <= 0) {  // (an object without outlines: no barrier has published the claim yet)
+    __syncthreads();
+    pr_next = sm.next;
+    if (pr_next < total) pe_next = a.pair_list[pr_next / RSUB];
+    __syncthreads();
+  }
+}
+
+template <bool kDeform>
+__global__ void __launch_bounds__(RASTER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster_pairs_kernel(RenderArgs a) {
+  __shared__ RasterSmem sm;
+  if (a.pair_ctl[1]) return;
+  const int total = a.pair_ctl[0] * RSUB;  // work units: RSUB slices per pair
+  for (int i = threadIdx.x; i < 256; i += RASTER_THREADS) sm.q255[i] = (float)i / 255.f;
+  int4 pe_next = (int)blockIdx.x < total ? a.pair_list[blockIdx.x / RSUB] : make_int4(0, 0, 0, 0);
   // Units differ a lot in cost (1 to 7 outlines, a few to hundreds of edges): after its first unit a block claims the next
   // one from a queue (pair_ctl[2]) instead of striding over the list, so no block is left with a long tail of heavy units.
   int unit = blockIdx.x;
   while (unit < total) {
     const int4 pe = pe_next;
-    const int pr = unit / RSUB, slice = unit % RSUB;
     int pr_next = total;
-    if (tid == 0) s_next = (int)gridDim.x + atomicAdd(&a.pair_ctl[2], 1);
-    const int tile = pe.y, shape_begin = pe.z;
-    const int tx0 = (tile % tiles_x) * TW, ty0 = (tile / tiles_x) * TH + slice * RTH;
-    const int y = ty0 + warp, x0 = tx0 + lane * 4;
-    const bool live = (y < H) && (x0 < W);
-    const int n_shapes = pe.w & 0xFFFF, composite = pe.w >> 16;
-    uint32_t uaa[2] = {0, 0}, una[2] = {0, 0};
-    if (a.pair_rows && tid >= RASTER_THREADS - 32 && lane < RTH) {
-      // the object's span-interpolator rows over this tile (frame 1 = its texture under the inverse motion, DG.cpp:203-221),
-      // one row per lane of the last warp (the (edge, row) items keep the first warps busy): the shade kernel's eight warps
-      // pick them up instead of each working out its own
-      const FlatObject& ob = a.objects[a.samples[pe.x >> 8].obj_begin + (pe.x & 255)];
-      RowWarp rw;
-      rw.init(ob.tex_inv, (double)(ty0 + lane), W);
-      int4* r = a.pair_rows + (size_t)pr * PAIR_ROW_STRIDE;
-      r[2 + (slice * RTH + lane) * 2] = make_int4(rw.dx.v1, rw.dx.lft, rw.dx.rem, rw.dy.v1);
-      r[3 + (slice * RTH + lane) * 2] = make_int4(rw.dy.lft, rw.dy.rem, 0, 0);
-      if (lane == 0 && slice == 0) {  // what the shade kernel needs of the object, in one record (instead of pair -> object -> texture table)
-        const TexInfo ti = a.tex_info[ob.tex];
-        r[0] = make_int4((int)(uint32_t)(ti.fg_base & 0xFFFFFFFFu), (int)(uint32_t)(ti.fg_base >> 32), ti.fg_pitch, pe.x & 255);
-        r[1] = make_int4(ob.field, 0, 0, 0);
-      }
-    }
-    for (int s0 = 0; s0 < n_shapes; s0 += NLAYER / 2) {
-      const int ns = min(NLAYER / 2, n_shapes - s0);
-      __syncthreads();  // the previous chunk (or pair) is done with the staging and the accumulators
-      if (tid < ns) {   // outline tid of this chunk: which of its frames touch the tile, which layers they get
-        const FlatShape& sh = a.shapes[shape_begin + s0 + tid];
-        PairOutline po;
-        const bool h0 = box_hits_rows(sh.bbox[0], tx0, ty0, RTH), h1 = box_hits_rows(sh.bbox[1], tx0, ty0, RTH);
-        po.deform = (kDeform && h1) ? sh.deform : -1;  // a warped outline's frame-1 masks were materialised by the pre-pass
-        const bool r1 = h1 && po.deform < 0;
-        po.vbegin[0] = sh.vbegin[0]; po.vbegin[1] = sh.vbegin[1];
-        po.vcount[0] = h0 ? sh.vcount[0] : 0; po.vcount[1] = r1 ? sh.vcount[1] : 0;
-        po.layer[0] = h0 ? (signed char)(2 * tid) : (signed char)-1;
-        po.layer[1] = r1 ? (signed char)(2 * tid + 1) : (signed char)-1;
-        po.additive = sh.additive ? 1 : 0;
-        s_out[tid] = po;
-        s_seg_begin[2 * tid] = po.vbegin[0]; s_seg_count[2 * tid] = po.vcount[0];
-        s_seg_begin[2 * tid + 1] = po.vbegin[1]; s_seg_count[2 * tid + 1] = po.vcount[1];
-      } else if (tid < NLAYER / 2) {
-        s_seg_count[2 * tid] = 0; s_seg_count[2 * tid + 1] = 0;
-      }
-      for (int i = tid; i < 2 * ns * (RTH * TW / 4); i += RASTER_THREADS) {  // outline k owns layers 2k and 2k + 1
-        reinterpret_cast<int4*>(&s_cover[0][0][0])[i] = make_int4(0, 0, 0, 0);
-        reinterpret_cast<int4*>(&s_area[0][0][0])[i] = make_int4(0, 0, 0, 0);
-      }
-      if (tid < NLAYER * RTH) (&s_carry[0][0])[tid] = 0;
-      if (tid == 0) s_npairs = 0;
-      __syncthreads();
-      if (s0 == 0) {  // the claimed pair's record is in flight while this pair is rasterised
-        pr_next = s_next;
-        if (pr_next < total) pe_next = a.pair_list[pr_next / RSUB];
-      }
-      {
-        // (a) threads over edges: which tile rows does the edge cross? One work item per (edge, row).
-        const int c0 = s_seg_count[0], c1 = c0 + s_seg_count[1], c2 = c1 + s_seg_count[2], c3 = c2 + s_seg_count[3];
-        for (int e = tid; e < c3; e += RASTER_THREADS) {
-          const int l = e < c0 ? 0 : (e < c1 ? 1 : (e < c2 ? 2 : 3));
-          const int ei = e - (l == 0 ? 0 : (l == 1 ? c0 : (l == 2 ? c1 : c2)));
-          const int n = s_seg_count[l];
-          const FlatVertex* v = a.verts + s_seg_begin[l];
-          const FlatVertex p = v[ei], q = v[ei + 1 == n ? 0 : ei + 1];
-          int rlo, rhi;
-          bool left;
-          if (!tile_edge_rows(tx0, ty0, p.x, p.y, q.x, q.y, rlo, rhi, left, RTH)) continue;
-          const int nrows = rhi - rlo + 1;
-          const int base = left ? RASTER_ITEMS : atomicAdd(&s_npairs, nrows);
-          for (int k = 0; k < nrows; ++k) {
-            if (base + k < RASTER_ITEMS) s_pairs[base + k] = ((unsigned)l << 28) | ((unsigned)(rlo + k - ty0) << 24) | (unsigned)ei;
-            else tile_edge_row<true>(&s_cover[l][0][0], &s_area[l][0][0], &s_carry[l][0], tx0, ty0, rlo + k, p.x, p.y, q.x, q.y);  // cheap (left of the tile) or list full
-          }
-        }
-      }
-      __syncthreads();
-      {
-        // (b) threads over (edge, row) items: closed-form row segment -> cells
-        const int np = min(s_npairs, RASTER_ITEMS);
-        // (items stay packed in the first warps: spread over all warps, lane * RTH + warp, the same few dozen divergent items
-        // issue from eight half-empty warps instead of two -- measured 0.160 -> 0.171 ms)
-        for (int i = tid; i < np; i += RASTER_THREADS) {
-          const unsigned w = s_pairs[i];
-          const int l = (int)(w >> 28), r = ty0 + (int)((w >> 24) & 15u), ei = (int)(w & 0xFFFFFFu);
-          const int n = s_seg_count[l];
-          const FlatVertex* v = a.verts + s_seg_begin[l];
-          const FlatVertex p = v[ei], q = v[ei + 1 == n ? 0 : ei + 1];
-          tile_edge_row<true>(&s_cover[l][0][0], &s_area[l][0][0], &s_carry[l][0], tx0, ty0, r, p.x, p.y, q.x, q.y);
-        }
-      }
-      __syncthreads();
-
-      for (int k = 0; k < ns; ++k) {
-        uint32_t vaa[2] = {0, 0}, vna[2] = {0, 0};
-#pragma unroll
-        for (int f = 0; f < 2; ++f) {
-          const int l = s_out[k].layer[f];
-          if (l < 0) {
-            if (kDeform && f == 1 && s_out[k].deform >= 0 && live) warped_mask_words(a, s_out[k].deform, x0, y, vaa[1], vna[1]);
-            continue;
-          }
-          const int4 c4 = *reinterpret_cast<const int4*>(&s_cover[l][warp][lane * 4]);
-          const int4 a4 = *reinterpret_cast<const int4*>(&s_area[l][warp][lane * 4]);
-          const int carry = s_carry[l][warp];
-          const bool cells = (c4.x | c4.y | c4.z | c4.w | a4.x | a4.y | a4.z | a4.w) != 0;
-          if (!__any_sync(0xffffffffu, cells)) {
-            // no outline crosses this row inside the tile: coverage is constant along it
-            if (carry == 0) continue;
-            const int cv = coverage_alpha(carry, 0);
-            vaa[f] = graylut((unsigned)cv) * 0x01010101u;
-            vna[f] = cv >= 128 ? 0xFFFFFFFFu : 0u;
-            continue;
-          }
-          int c[4] = {c4.x, c4.y, c4.z, c4.w}, ar[4] = {a4.x, a4.y, a4.z, a4.w};
-          c[1] += c[0]; c[2] += c[1]; c[3] += c[2];
-          int tot = c[3];  // warp-level inclusive prefix sum over the lanes' cover totals
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            int o = __shfl_up_sync(0xffffffffu, tot, d);
-            if (lane >= d) tot += o;
-          }
-          const int base = tot - c[3] + carry;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int cv = coverage_alpha(base + c[i], ar[i]);
-            vaa[f] |= graylut((unsigned)cv) << (8 * i);        // gamma_none
-            vna[f] |= (cv >= 128 ? 255u : 0u) << (8 * i);      // gamma_threshold(0.5), then graylut(255) = 255
-          }
-        }
-
-        if (composite) {
-          if (s0 + k == 0) { uaa[0] = uaa[1] = una[0] = una[1] = 0; }
-          const bool add = s_out[k].additive != 0;
-#pragma unroll
-          for (int f = 0; f < 2; ++f) {
-            uaa[f] = comp4(uaa[f], vaa[f], add, s_q255);
-            // non-AA masks stay in {0, 255} (the rules are closed on it) unless a warp field resampled them
-            if (kDeform) una[f] = comp4(una[f], vna[f], add, s_q255);
-            else una[f] = add ? (una[f] | vna[f]) : (una[f] & ~vna[f]);
-          }
-        } else {
-          uaa[0] = vaa[0]; uaa[1] = vaa[1]; una[0] = vna[0]; una[1] = vna[1];
-        }
-      }
-    }
-    // the object's four masks over this tile: [AA 0, AA 1, non-AA 0, non-AA 1][tile row][lane], one word = four pixels
-    uint32_t* pm = a.pair_masks + (size_t)pr * (4 * TH * 32) + (slice * RTH + warp) * 32 + lane;
-    pm[0 * TH * 32] = uaa[0]; pm[1 * TH * 32] = uaa[1]; pm[2 * TH * 32] = una[0]; pm[3 * TH * 32] = una[1];
-    if (n_shapes <= 0) {  // (an object without outlines: no barrier has published the claim yet)
-      __syncthreads();
-      pr_next = s_next;
-      if (pr_next < total) pe_next = a.pair_list[pr_next / RSUB];
-      __syncthreads();
-    }
+    raster_unit<kDeform, true>(a, sm, unit, total, pe, (int)gridDim.x, pr_next, pe_next);
     unit = pr_next;
   }
 }
@@ -1867,14 +1878,28 @@ __device__ __noinline__ void bg_prep_general(const RenderArgs& a, const BgPrep& 
 #ifndef OFDG_PREP_MIN_BLOCKS
 #define OFDG_PREP_MIN_BLOCKS 8  // measured: 4 / 5 / 6 / 8 blocks per SM -> 0.208 / 0.194 / 0.190 / 0.186 ms
 #endif
-__global__ void __launch_bounds__(PREP_THREADS, OFDG_PREP_MIN_BLOCKS) bg_prep_kernel(RenderArgs a) {
-  __shared__ uint32_t sA[PS][PS];  // rotated + cropped source pixels
-  __shared__ uint32_t sB[PS][PT];  // after the x pass
-  __shared__ ResizeTaps sTy[PT];   // taps of the tile's output rows
-  const int sample = blockIdx.z;
+struct PrepTileConst {
+    int cx0, cy0, cw, ch, step_x, step_y, inv_cw, bx, by, inside, fast;
+    unsigned magic_x, magic_y;
+    TapMap tm;
+};
+struct PrepSmem {  // shared memory of one block preparing a 32 x 32 tile of a background
+  uint32_t sA[PS][PS];  // rotated + cropped source pixels
+  uint32_t sB[PS][PT];  // after the x pass
+  ResizeTaps sTy[PT];   // taps of the tile's output rows
+  PrepTileConst sC;
+};
+
+// One 32 x 32 tile (bx, by) of sample `sample`'s prepared background, by the whole block.
+__device__ __forceinline__ void bg_prep_tile(const RenderArgs& a, PrepSmem& sm, int bx, int by, int sample) {
+  uint32_t (*sA)[PS] = sm.sA;
+  uint32_t (*sB)[PT] = sm.sB;
+  ResizeTaps* sTy = sm.sTy;
+  PrepTileConst& sC = sm.sC;
+  typedef PrepTileConst TileConst;
   const BgPrep& p = a.samples[sample].prep;
   const int W2 = 2 * a.W, H2 = 2 * a.H;
-  const int X0 = p.need[0] + blockIdx.x * PT, Y0 = p.need[1] + blockIdx.y * PT;
+  const int X0 = p.need[0] + bx * PT, Y0 = p.need[1] + by * PT;
   if (X0 > p.need[2] || Y0 > p.need[3]) return;
   const int X1 = min(X0 + PT - 1, p.need[2]), Y1 = min(Y0 + PT - 1, p.need[3]);
   // `need` is the bounding box of what the renderer reads: the centre W x H window (frame 0) and the footprint of the frame-1
@@ -1912,11 +1937,6 @@ __global__ void __launch_bounds__(PREP_THREADS, OFDG_PREP_MIN_BLOCKS) bg_prep_ke
   // Per-tile constants (source ranges, multiply-high constants, the walk's steps, the fast-path test): a dozen integer
   // divisions and four corner evaluations that are the same for all 256 threads -- warp 0 works them out, the others
   // pick them up from shared memory (the kernel is issue-bound: seven warps' worth of redundant instructions saved).
-  __shared__ struct TileConst {
-    int cx0, cy0, cw, ch, step_x, step_y, inv_cw, bx, by, inside, fast;
-    unsigned magic_x, magic_y;
-    TapMap tm;
-  } sC;
   const int tw = X1 - X0 + 1, th = Y1 - Y0 + 1;
   if (threadIdx.x < 32) {
     TileConst c;
@@ -2012,6 +2032,11 @@ __global__ void __launch_bounds__(PREP_THREADS, OFDG_PREP_MIN_BLOCKS) bg_prep_ke
       const uint32_t v = apply_taps(&sB[0][lane_x], PT, cy0, p.crop_h, magic_y, sTy[ly]);
       *reinterpret_cast<uint32_t*>(out + (size_t)(Y0 + ly) * W2 + X0 + lane_x) = v;
     }
+}
+
+__global__ void __launch_bounds__(PREP_THREADS, OFDG_PREP_MIN_BLOCKS) bg_prep_kernel(RenderArgs a) {
+  __shared__ PrepSmem sm;
+  bg_prep_tile(a, sm, (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z);
 }
 
 // Foreground view of a texture smaller than W x H: the whole texture resized (getRandomizedCrop's else branch with
