@@ -1155,6 +1155,7 @@ int ofdg_reserve_fields(ofdg_generator* g, int32_t total) {
     const size_t per = (size_t)2 * 2 * (g->cfg.height + 1) * (g->cfg.width + 1) * sizeof(float);
     DevBuf nf, nr;
     nf.reserve(per * total);
+    CK(cudaMemset(nf.p, 0, per * total));  // (new slots read as zero displacement until they are filled)
     CK(cudaMemcpy(nf.p, g->fields.p, per * g->n_fields, cudaMemcpyDeviceToDevice));
     nr.reserve((size_t)total * sizeof(int));
     CK(cudaMemset(nr.p, 0, (size_t)total * sizeof(int)));

@@ -423,6 +423,7 @@ void DataGenerationLayer<Dtype>::WaitGenerationRetired(uint64_t gen) {
         bool queued = false;
         for (const Prefetched& b : prefetch_full_) queued = queued || (b.uses_fields && b.gen_lo <= gen);
         for (const std::pair<uint64_t, uint64_t>& d : drawn_) queued = queued || d.second <= gen;  // still with the other producer
+        queued = queued || (popped_active_ && popped_gen_lo_ <= gen);                              // popped by Forward, render not queued / done yet
         if (!queued) return;
         // still waiting in the queue (or on its way there): Forward will pop it (cv_free_ is signalled on every pop)
         cv_free_.wait_for(l, std::chrono::milliseconds(2), [this] { return must_stop_ || !in_flight_.empty(); });
@@ -442,8 +443,10 @@ void DataGenerationLayer<Dtype>::WaitGenerationRetired(uint64_t gen) {
 // Solver thread, after the render of `b` has been queued on stream_.
 template <typename Dtype>
 void DataGenerationLayer<Dtype>::TrackInFlight(const Prefetched& b) {
-  if (!b.uses_fields || field_ring_ <= 1) return;
+  if (!b.uses_fields) return;
   std::lock_guard<std::mutex> l(mutex_);
+  popped_active_ = false;
+  if (field_ring_ <= 1) return;
   cudaEvent_t e = nullptr;
   if (!event_pool_.empty()) { e = event_pool_.back(); event_pool_.pop_back(); }
   else SHIM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -499,6 +502,7 @@ typename DataGenerationLayer<Dtype>::Prefetched DataGenerationLayer<Dtype>::PopP
     if (prefetch_full_.empty()) throw std::runtime_error("Data layer prefetch queue empty");
     b = prefetch_full_.front();
     prefetch_full_.pop_front();
+    if (b.uses_fields) { popped_active_ = true; popped_gen_lo_ = b.gen_lo; }  // neither queued nor in flight yet, but its generations are in use
   }
   cv_free_.notify_all();
   return b;
@@ -576,6 +580,11 @@ void DataGenerationLayer<Dtype>::Forward_cpu(const std::vector<Blob<Dtype>*>& bo
     rc = ofdg_render_prepared_host(generator_, p, top[0]->mutable_cpu_data(), top[1]->mutable_cpu_data(), top[2]->mutable_cpu_data());
   }
   ofdg_prepared_destroy(p);
+  if (b.uses_fields) {  // rendered synchronously: its field generations are free again
+    std::lock_guard<std::mutex> l(mutex_);
+    popped_active_ = false;
+  }
+  cv_free_.notify_all();
   if (rc != OFDG_OK) throw std::runtime_error(ofdg_last_error());
 }
 

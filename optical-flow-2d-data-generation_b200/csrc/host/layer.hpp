@@ -76,6 +76,8 @@ class DataGenerationLayer : public Layer<Dtype> {
   // occupant has finished rendering (in_flight_: rendered batches and the events that say when they are done).
   struct InFlight { cudaEvent_t done; uint64_t gen_lo; };
   std::deque<InFlight> in_flight_;
+  bool popped_active_ = false;            // a batch Forward has popped and not yet queued (gpu) / finished (cpu) rendering
+  uint64_t popped_gen_lo_ = 0;
   std::vector<std::pair<uint64_t, uint64_t> > drawn_;  // (ticket, first generation) of batches drawn but not queued yet
   std::vector<cudaEvent_t> event_pool_;
   int field_ring_ = 0;

@@ -115,3 +115,59 @@ def test_config3_mode9_fields_augmentation_batch64(ofdg, oracle, textures8):
     bp = tasks.arrays()["blueprints"]
     assert len(np.unique(bp["field_id"][bp["field_id"] >= 0])) > 20
     g.close()
+
+
+def test_field_pool_slots_can_be_refreshed_in_place(ofdg):
+    """ofdg_reserve_fields / ofdg_refresh_fields: the pool grows without losing its crops, and regenerating a range of slots
+    from a seed gives exactly the crops ofdg_generate_fields makes from that seed (same producer, persistent work buffers)."""
+    g = ofdg.Generator(device=0, mode=9, max_batch=2)
+    g.synth_textures(2, 1024, 768, seed=1)
+    first = g.generate_fields(11, 40)
+    with pytest.raises(ofdg.OfdgError):
+        g.refresh_fields(12, 40, 40)            # beyond the pool
+    g.reserve_fields(120)
+    g.refresh_fields(12, 40, 40)
+    g.refresh_fields(13, 80, 40)
+    g.refresh_fields(14, 40, 40)                # ... and again over the same slots
+    g.close()
+    g2 = ofdg.Generator(device=0, mode=9, max_batch=2)
+    g2.synth_textures(2, 1024, 768, seed=1)
+    want14 = g2.generate_fields(14, 40)
+    g2.close()
+    # render one mode-9 sample whose objects pick from slots 40..79 on both generators' pools: same blobs
+    ga = ofdg.Generator(device=0, mode=9, max_batch=2)
+    ga.synth_textures(2, 1024, 768, seed=1)
+    ga.generate_fields(11, 40)
+    ga.reserve_fields(120)
+    ga.refresh_fields(14, 40, 40)
+    gb = ofdg.Generator(device=0, mode=9, max_batch=2)
+    gb.synth_textures(2, 1024, 768, seed=1)
+    import numpy as np
+    pool = np.concatenate([first, want14, np.zeros_like(first)])
+    gb.set_fields(pool)
+    ps = ofdg.ParamStream(9, n_fields=120)
+    ps.skip(7)                                   # (move the picks past the first 40 slots: 3 picks per slot)
+    while ps.field_draws() < 125:
+        ps.generate(2)
+    tasks = ps.generate(2)
+    assert (tasks.arrays()["blueprints"]["field_id"] >= 40).any()
+    a = ga.render_host(tasks)
+    b = gb.render_host(tasks)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y, equal_nan=True)
+    ga.close(); gb.close()
+
+
+def test_last_render_stats(ofdg, textures8):
+    """ofdg_last_render_stats: the pair count the host sizes its buffers from is exactly what bin_pairs_kernel counts."""
+    import torch
+    g = ofdg.Generator(device=0, mode=7, max_batch=8)
+    g.upload_textures(textures8)
+    p = g.prepare(ofdg.ParamStream(7).generate(8))
+    i0 = torch.empty((8, 3, 384, 512), device="cuda"); i1 = torch.empty_like(i0); fl = torch.empty((8, 2, 384, 512), device="cuda")
+    g.render_prepared(p, i0, i1, fl)
+    pairs, prepared_px, source_px = g.last_render_stats()
+    assert 8 * 50 < pairs < 8 * 2000
+    assert 8 * 512 * 384 <= prepared_px <= 8 * 1024 * 768 and source_px > 0
+    del p
+    g.close()
