@@ -161,6 +161,7 @@ struct ofdg_generator {
   struct { bool valid = false; uint64_t seed = 0, first = 0; int batch = 0, augment = 0, set = 0; } ph_next;
   int ph_batch = 0;
   DevBuf rtab_pos_x, rtab_alpha_x, rtab_pos_y, rtab_alpha_y;  // CImg linear-resize tables for every source length
+  DevBuf comp_lut;  // [2][256][256] composite-mask rules (additive, subtractive), filled once by composite_lut_kernel
   // texture pool
   DevBuf pool;
   int n_tex = 0;
@@ -450,6 +451,7 @@ ofdg::RenderArgs make_args(ofdg_generator* g, const DeviceScene& ds, float* d0, 
     }
     a.pair_cap = g->pair_cap_limit > 0 ? std::min(g->pair_cap, g->pair_cap_limit) : g->pair_cap;
     a.pair_overflow = (int*)g->pair_overflow.dev;
+    a.comp_lut = (const uint8_t*)g->comp_lut.p;
   }
   a.pos_x = (const int*)g->rtab_pos_x.p; a.alpha_x = (const double*)g->rtab_alpha_x.p;
   a.pos_y = (const int*)g->rtab_pos_y.p; a.alpha_y = (const double*)g->rtab_alpha_y.p;
@@ -782,6 +784,13 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
       ofdg::launch_resize_tables((int*)g->rtab_pos_x.p, (double*)g->rtab_alpha_x.p, (int)W2, g->stream);
       ofdg::launch_resize_tables((int*)g->rtab_pos_y.p, (double*)g->rtab_alpha_y.p, (int)H2, g->stream);
       g->launches += 2;
+      CK(cudaStreamSynchronize(g->stream));
+      CK(cudaGetLastError());
+    }
+    {  // one-time: the composite rules' table for the raster kernel
+      g->comp_lut.reserve(2 * 65536);
+      ofdg::launch_composite_luts((uint8_t*)g->comp_lut.p, (uint8_t*)g->comp_lut.p + 65536, g->stream);
+      g->launches += 1;
       CK(cudaStreamSynchronize(g->stream));
       CK(cudaGetLastError());
     }

@@ -265,74 +265,110 @@ __device__ void gen_object(Gen& g, SampleOut& o, int idx, int n_fields, int& fie
   o.bp[idx] = b;
 }
 
-// One WARP per (sample, role), lane 0 working: the roles of a sample (its objects, its background) run through very
-// different branches and loop counts, so as threads of one warp they would execute one after the other.
-constexpr int kParamWarps = (kPhiloxMaxObj + 2) / 2;  // roles per block; two blocks per sample
+// One WARP per (sample, role), lane 0 drawing: the roles of a sample (its objects, its background) run through very
+// different branches and loop counts, so as threads of one warp they would execute one after the other. An object's
+// blueprints and polygon segments are read, scaled and rewritten several times while they are drawn (components copy and
+// shrink their parent's outline, thin objects rescale theirs): they live in shared memory until the object is complete and
+// leave in one coalesced copy by the whole warp -- as global read-modify-write chains they were most of the kernel's 169 us,
+// during which its blocks (17 warps at 56 registers for one working lane each) held half an SM's registers away from the
+// render kernels of the batch before.
+constexpr int kParamWarps = 12;                                          // roles per block
+constexpr int kParamBlocks = (kPhiloxMaxObj + 1 + kParamWarps - 1) / kParamWarps;  // blocks per sample
+constexpr int kSegPerObj = kPhiloxMaxShapes * 20;
+struct ParamStage {
+  ofdg_blueprint bp[kPhiloxMaxShapes];
+  int32_t seg_type[kSegPerObj];
+  float seg_x[kSegPerObj];
+  float seg_y[kSegPerObj];
+};
 __global__ void __launch_bounds__(32 * kParamWarps) philox_params_kernel(PhiloxArgs a) {
-  if (threadIdx.x & 31) return;
-  const int s = blockIdx.x, k = blockIdx.y * kParamWarps + (threadIdx.x >> 5);  // sample, role: object k, or kPhiloxMaxObj = background and sample-level draws
+  __shared__ ParamStage s_stage[kParamWarps];
+  __shared__ PhiloxSlot s_slots[kPhiloxSlots];
+  for (int i = threadIdx.x; i < (int)(kPhiloxSlots * sizeof(PhiloxSlot) / 4); i += blockDim.x)
+    reinterpret_cast<int*>(s_slots)[i] = reinterpret_cast<const int*>(a.slots)[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int s = blockIdx.x, k = blockIdx.y * kParamWarps + w;  // sample, role: object k, or kPhiloxMaxObj = background and sample-level draws
   if (k > kPhiloxMaxObj) return;
-  Gen g;
-  g.slots = a.slots;
-  g.mode = a.mode;
-  // the number of objects is a sample-level draw every thread of the sample repeats
-  g.rng.init(a.seed, a.first_sample + (uint64_t)s, kPhiloxMaxObj);
-  int fg = a.fg_override > 0 ? a.fg_override : (int)g.real(NumberOfFgObjects);
-  if (fg > kPhiloxMaxObj) {  // more objects than the fixed strides hold: rendered without the rest, and the host is told
-    if (a.truncated && k == kPhiloxMaxObj && (threadIdx.x & 31) == 0) *a.truncated = 1;
-    fg = kPhiloxMaxObj;
-  }
-  int field_draws = 0;
-  if (k == kPhiloxMaxObj) {
-    // generateBackground, DG.cpp:2105-2143
-    ofdg_blueprint bg = blank_bp();
-    bg.obj_id = 1;
-    bg.obj_type = OFDG_OBJ_POLYGON;
-    bg.rot = g.trigger(BgRotTrigger) ? g.real(BgRot) : 0.f;
-    bg.scale = g.trigger(BgScaleTrigger) ? g.real(BgScale) : 1.f;
-    const float ptx = g.real(BgTransX), pty = g.real(BgTransY);
-    bg.trans_x = cosf(-bg.rot) * ptx - sinf(-bg.rot) * pty;
-    bg.trans_y = sinf(-bg.rot) * ptx + cosf(-bg.rot) * pty;
-    bg.tex_id = g.integer(BgTexID);
-    bg.tex_rot = g.real(BgInitRot);
-    bg.tex_scale = g.real(BgInitScale);
-    bg.tex_shift_x = g.integer(BgInitTransX);
-    bg.tex_shift_y = g.integer(BgInitTransY);
-    bg.do_warpfield_deformation = g.trigger(ObjDeformsNonrigidly);
-    if (a.mode == 9 && bg.do_warpfield_deformation && a.n_fields > 0) {
-      uint32_t r0, r1;
-      g.rng.raw(FieldPick, r0, r1);
-      bg.field_id = (int)(r0 % (uint32_t)a.n_fields);
+  ParamStage& st = s_stage[w];
+  const int bp_base = s * kPhiloxMaxBp + 1 + k * kPhiloxMaxShapes, seg_base = s * kPhiloxMaxSeg + k * kSegPerObj;
+  int nbp = 0, nseg = 0;
+  if (lane == 0) {
+    Gen g;
+    g.slots = s_slots;
+    g.mode = a.mode;
+    // the number of objects is a sample-level draw every role of the sample repeats
+    g.rng.init(a.seed, a.first_sample + (uint64_t)s, kPhiloxMaxObj);
+    int fg = a.fg_override > 0 ? a.fg_override : (int)g.real(NumberOfFgObjects);
+    if (fg > kPhiloxMaxObj) {  // more objects than the fixed strides hold: rendered without the rest, and the host is told
+      if (a.truncated && k == kPhiloxMaxObj) *a.truncated = 1;
+      fg = kPhiloxMaxObj;
     }
-    a.bp[s * kPhiloxMaxBp] = bg;
-    a.n_top[s] = fg;
-    if (a.augment) {
-      ofdg_augment au;
-      au.enabled = 1;
-      for (int c = 0; c < 3; ++c) au.gain[c] = 0.8f + 0.4f * g.rng.unit(AugGain);
-      au.brightness = -20.f + 40.f * g.rng.unit(AugBrightness);
-      au.contrast = 0.7f + 0.6f * g.rng.unit(AugContrast);
-      au.noise_sigma = 10.f * g.rng.unit(AugSigma);
-      g.rng.raw(AugSeed, au.noise_seed[0], au.noise_seed[1]);
-      a.samples[s].aug = au;
-    } else {
-      a.samples[s].aug.enabled = 0;
+    int field_draws = 0;
+    if (k == kPhiloxMaxObj) {
+      // generateBackground, DG.cpp:2105-2143
+      ofdg_blueprint bg = blank_bp();
+      bg.obj_id = 1;
+      bg.obj_type = OFDG_OBJ_POLYGON;
+      bg.rot = g.trigger(BgRotTrigger) ? g.real(BgRot) : 0.f;
+      bg.scale = g.trigger(BgScaleTrigger) ? g.real(BgScale) : 1.f;
+      const float ptx = g.real(BgTransX), pty = g.real(BgTransY);
+      bg.trans_x = cosf(-bg.rot) * ptx - sinf(-bg.rot) * pty;
+      bg.trans_y = sinf(-bg.rot) * ptx + cosf(-bg.rot) * pty;
+      bg.tex_id = g.integer(BgTexID);
+      bg.tex_rot = g.real(BgInitRot);
+      bg.tex_scale = g.real(BgInitScale);
+      bg.tex_shift_x = g.integer(BgInitTransX);
+      bg.tex_shift_y = g.integer(BgInitTransY);
+      bg.do_warpfield_deformation = g.trigger(ObjDeformsNonrigidly);
+      if (a.mode == 9 && bg.do_warpfield_deformation && a.n_fields > 0) {
+        uint32_t r0, r1;
+        g.rng.raw(FieldPick, r0, r1);
+        bg.field_id = (int)(r0 % (uint32_t)a.n_fields);
+      }
+      a.bp[s * kPhiloxMaxBp] = bg;
+      a.n_top[s] = fg;
+      if (a.augment) {
+        ofdg_augment au;
+        au.enabled = 1;
+        for (int c = 0; c < 3; ++c) au.gain[c] = 0.8f + 0.4f * g.rng.unit(AugGain);
+        au.brightness = -20.f + 40.f * g.rng.unit(AugBrightness);
+        au.contrast = 0.7f + 0.6f * g.rng.unit(AugContrast);
+        au.noise_sigma = 10.f * g.rng.unit(AugSigma);
+        g.rng.raw(AugSeed, au.noise_seed[0], au.noise_seed[1]);
+        a.samples[s].aug = au;
+      } else {
+        a.samples[s].aug.enabled = 0;
+      }
+    } else if (k < fg) {
+      // generateForegroundObject for object k: its own engines, its own slice of the arrays (staged in shared memory;
+      // seg_begin / comp_begin / parent hold the absolute positions the slice will have in the batch's arrays)
+      g.rng.init(a.seed, a.first_sample + (uint64_t)s, k);
+      SampleOut o;
+      o.bp_base = bp_base;
+      o.seg_base = seg_base;
+      o.bp = st.bp; o.seg_type = st.seg_type; o.seg_x = st.seg_x; o.seg_y = st.seg_y;
+      o.nbp = 1; o.nseg = 0;
+      o.bp[0] = blank_bp();
+      o.bp[0].obj_id = 10 + k;
+      gen_object(g, o, 0, a.n_fields, field_draws);
+      nbp = o.nbp; nseg = o.nseg;
     }
-    return;
+    if (k < kPhiloxMaxObj) { a.obj_nbp[s * kPhiloxMaxObj + k] = nbp; a.obj_nseg[s * kPhiloxMaxObj + k] = nseg; }
   }
-  if (k >= fg) { a.obj_nbp[s * kPhiloxMaxObj + k] = 0; a.obj_nseg[s * kPhiloxMaxObj + k] = 0; return; }
-  // generateForegroundObject for object k: its own engines, its own slice of the arrays
-  g.rng.init(a.seed, a.first_sample + (uint64_t)s, k);
-  SampleOut o;
-  o.bp_base = s * kPhiloxMaxBp + 1 + k * kPhiloxMaxShapes;
-  o.seg_base = s * kPhiloxMaxSeg + k * (kPhiloxMaxShapes * 20);
-  o.bp = a.bp + o.bp_base; o.seg_type = a.seg_type + o.seg_base; o.seg_x = a.seg_x + o.seg_base; o.seg_y = a.seg_y + o.seg_base;
-  o.nbp = 1; o.nseg = 0;
-  o.bp[0] = blank_bp();
-  o.bp[0].obj_id = 10 + k;
-  gen_object(g, o, 0, a.n_fields, field_draws);
-  a.obj_nbp[s * kPhiloxMaxObj + k] = o.nbp;
-  a.obj_nseg[s * kPhiloxMaxObj + k] = o.nseg;
+  __syncwarp();
+  nbp = __shfl_sync(0xffffffffu, nbp, 0);
+  nseg = __shfl_sync(0xffffffffu, nseg, 0);
+  {
+    int* dst = reinterpret_cast<int*>(a.bp + bp_base);
+    const int* src = reinterpret_cast<const int*>(st.bp);
+    for (int i = lane; i < nbp * (int)(sizeof(ofdg_blueprint) / 4); i += 32) dst[i] = src[i];
+    for (int i = lane; i < nseg; i += 32) {
+      a.seg_type[seg_base + i] = st.seg_type[i];
+      a.seg_x[seg_base + i] = st.seg_x[i];
+      a.seg_y[seg_base + i] = st.seg_y[i];
+    }
+  }
 }
 
 // ---- device flatten (host/flatten.cpp restated for one thread per object) ------------------------------
@@ -588,7 +624,7 @@ void philox_upload_circle(const double* c, const double* s) {
 }
 
 int launch_philox(const PhiloxArgs& a, cudaStream_t s) {
-  philox_params_kernel<<<dim3(a.batch, 2), 32 * kParamWarps, 0, s>>>(a);
+  philox_params_kernel<<<dim3(a.batch, kParamBlocks), 32 * kParamWarps, 0, s>>>(a);
   philox_flatten_kernel<<<dim3(a.batch, kPhiloxMaxObj / kFlatObjPerBlock + 1), kFlatObjPerBlock * kFlatLanes, 0, s>>>(a);
   return 2;
 }

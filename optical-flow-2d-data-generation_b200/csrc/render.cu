@@ -362,6 +362,22 @@ __device__ __forceinline__ uint32_t comp4(uint32_t u, uint32_t v, bool additive,
   return comp4_bytes(u, v, additive, q255);
 }
 
+// The same rules through the table composite_lut_kernel fills once per generator with exactly these float expressions
+// (RenderArgs::comp_lut): four byte loads instead of four float evaluations behind per-byte branches. The raster kernel
+// spent a fifth of its instructions in comp4_bytes, at nine active lanes per instruction.
+__device__ __forceinline__ uint32_t comp4_lut(uint32_t u, uint32_t v, bool additive, const uint8_t* lut) {
+  if (additive) {
+    if (v == 0xFFFFFFFFu) return 0xFFFFFFFFu;
+    if ((u | v) == 0u) return 0u;
+  } else {
+    if (v == 0xFFFFFFFFu || u == 0u) return 0u;
+  }
+  const uint8_t* t = lut + (additive ? 0 : 65536);
+  const uint32_t lo = __byte_perm(v, u, 0x5140u), hi = __byte_perm(v, u, 0x7362u);  // {v0, u0, v1, u1}, {v2, u2, v3, u3}: index = u * 256 + v
+  const uint32_t r0 = __ldg(t + (lo & 0xFFFFu)), r1 = __ldg(t + (lo >> 16)), r2 = __ldg(t + (hi & 0xFFFFu)), r3 = __ldg(t + (hi >> 16));
+  return __byte_perm(__byte_perm(r0, r1, 0x0040u), __byte_perm(r2, r3, 0x0040u), 0x5410u);
+}
+
 // kDeform = false compiles the mode-9 (warp field) branches out; kExtra = false the extra tops (backward flow, ids).
 template <bool kDeform, bool kExtra>
 __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render_kernel(RenderArgs a) {
@@ -839,11 +855,29 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
 #endif
 constexpr int RTH = OFDG_RASTER_ROWS;
 constexpr int RSUB = TH / RTH;              // slices per pair
-constexpr int RASTER_THREADS = 32 * RTH;
-constexpr int RASTER_ITEMS = MAX_PAIRS * RTH / TH;  // (edge, row) work items listed per chunk
+// Warps per raster block and accumulator layers per chunk. A unit's phases are dependent chains separated by block barriers
+// (shape records -> vertices -> row crossings -> shared atomics -> sweep), and only the sweep has work for every thread. Four
+// warps (each sweeping two rows) and one outline per chunk (two layers, 19 KB of shared memory) put eight units on an SM at 64
+// registers instead of five at 48. Measured (same box, kernel in line / whole pipelined step): 8 warps x 4 layers x 5 blocks
+// 0.153 / 0.4255 ms; 8 x 2 x 5: 0.171 / 0.435; 4 x 2 x 10 (48 registers, spills): 0.173 / 0.432; 4 x 2 x 8: 0.151 / 0.407;
+// 4 x 2 x 6: 0.166 / 0.424; 4 x 4 x 5: 0.166 / 0.430; 2 x 2 x 11: 0.242 / 0.487. (Starting the packed item loops at a warp that
+// changes from unit to unit, so that they do not all issue from the same scheduler: no gain, 0.153 vs 0.151.)
+#ifndef OFDG_RASTER_WARPS
+#define OFDG_RASTER_WARPS 4
+#endif
+#ifndef OFDG_RASTER_LAYERS
+#define OFDG_RASTER_LAYERS 2
+#endif
+
+constexpr int RWARPS = OFDG_RASTER_WARPS;
+constexpr int RPW = RTH / RWARPS;           // tile rows swept per warp
+constexpr int RLAYER = OFDG_RASTER_LAYERS;  // accumulator layers of the raster kernel: RLAYER / 2 outlines per chunk
+constexpr int RASTER_THREADS = 32 * RWARPS;
+constexpr int RASTER_ITEMS = MAX_PAIRS * RTH * RLAYER / (TH * NLAYER);  // (edge, row) work items listed per chunk
 static_assert(TH % RTH == 0, "a raster slice must divide the tile");
+static_assert(RTH % RWARPS == 0 && RLAYER % 2 == 0 && RLAYER <= NLAYER && RLAYER * RTH <= RASTER_THREADS, "raster block shape");
 #ifndef OFDG_RASTER_MIN_BLOCKS
-#define OFDG_RASTER_MIN_BLOCKS (40 / OFDG_RASTER_ROWS)  // 8 rows, measured: 3 / 4 / 5 / 6 blocks per SM -> 0.225 / 0.195 / 0.179 / 0.188 ms
+#define OFDG_RASTER_MIN_BLOCKS (OFDG_RASTER_WARPS == 4 ? 8 : 1280 / (32 * OFDG_RASTER_WARPS))  // 8 warps, measured: 3 / 4 / 5 / 6 blocks per SM -> 0.225 / 0.195 / 0.179 / 0.188 ms
 #endif
 __device__ __forceinline__ bool box_hits_rows(const int32_t* b, int tx0, int ty0, int rows) {
   return b[1] <= ty0 + rows - 1 && b[3] >= ty0 && b[0] <= tx0 + TW - 1 && b[2] >= tx0;
@@ -964,10 +998,9 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_pairs_kernel(RenderArgs a) {
 }
 
 struct RasterSmem {  // shared memory of one block rasterising (object, tile) pairs
-  int cover[NLAYER][RTH][TW];
-  int area[NLAYER][RTH][TW];
-  int carry[NLAYER][RTH];
-  float q255[256];
+  int cover[RLAYER][RTH][TW];
+  int area[RLAYER][RTH][TW];
+  int carry[RLAYER][RTH];
   PairOutline out[NLAYER / 2];
   int seg_begin[NLAYER], seg_count[NLAYER];
   unsigned pairs[RASTER_ITEMS];
@@ -987,10 +1020,11 @@ __device__ __forceinline__ void raster_unit(const RenderArgs& a, RasterSmem& sm,
   if (kQueue && tid == 0) sm.next = queue_base + atomicAdd(&a.pair_ctl[2], 1);
   const int tile = pe.y, shape_begin = pe.z;
   const int tx0 = (tile % tiles_x) * TW, ty0 = (tile / tiles_x) * TH + slice * RTH;
-  const int y = ty0 + warp, x0 = tx0 + lane * 4;
-  const bool live = (y < H) && (x0 < W);
+  const int x0 = tx0 + lane * 4;  // the warp sweeps tile rows warp, warp + RWARPS, ..
   const int n_shapes = pe.w & 0xFFFF, composite = pe.w >> 16;
-  uint32_t uaa[2] = {0, 0}, una[2] = {0, 0};
+  uint32_t uaa[RPW][2], una[RPW][2];
+#pragma unroll
+  for (int j = 0; j < RPW; ++j) uaa[j][0] = uaa[j][1] = una[j][0] = una[j][1] = 0u;
   if (a.pair_rows && tid >= RASTER_THREADS - 32 && lane < RTH) {
     // the object's span-interpolator rows over this tile (frame 1 = its texture under the inverse motion, DG.cpp:203-221),
     // one row per lane of the last warp (the (edge, row) items keep the first warps busy): the shade kernel's eight warps
@@ -1007,8 +1041,8 @@ __device__ __forceinline__ void raster_unit(const RenderArgs& a, RasterSmem& sm,
       r[1] = make_int4(ob.field, 0, 0, 0);
     }
   }
-  for (int s0 = 0; s0 < n_shapes; s0 += NLAYER / 2) {
-    const int ns = min(NLAYER / 2, n_shapes - s0);
+  for (int s0 = 0; s0 < n_shapes; s0 += RLAYER / 2) {
+    const int ns = min(RLAYER / 2, n_shapes - s0);
     __syncthreads();  // the previous chunk (or pair) is done with the staging and the accumulators
     if (tid < ns) {   // outline tid of this chunk: which of its frames touch the tile, which layers they get
       const FlatShape& sh = a.shapes[shape_begin + s0 + tid];
@@ -1031,7 +1065,7 @@ __device__ __forceinline__ void raster_unit(const RenderArgs& a, RasterSmem& sm,
       reinterpret_cast<int4*>(&sm.cover[0][0][0])[i] = make_int4(0, 0, 0, 0);
       reinterpret_cast<int4*>(&sm.area[0][0][0])[i] = make_int4(0, 0, 0, 0);
     }
-    if (tid < NLAYER * RTH) (&sm.carry[0][0])[tid] = 0;
+    if (tid < RLAYER * RTH) (&sm.carry[0][0])[tid] = 0;
     if (tid == 0) sm.npairs = 0;
     __syncthreads();
     if (kQueue && s0 == 0) {  // the claimed pair's record is in flight while this pair is rasterised
@@ -1075,7 +1109,11 @@ __device__ __forceinline__ void raster_unit(const RenderArgs& a, RasterSmem& sm,
     }
     __syncthreads();
 
-    for (int k = 0; k < ns; ++k) {
+    for (int k = 0; k < ns; ++k)
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) {
+      const int row = warp + j * RWARPS, y = ty0 + row;
+      const bool live = (y < H) && (x0 < W);
       uint32_t vaa[2] = {0, 0}, vna[2] = {0, 0};
 #pragma unroll
       for (int f = 0; f < 2; ++f) {
@@ -1084,9 +1122,9 @@ __device__ __forceinline__ void raster_unit(const RenderArgs& a, RasterSmem& sm,
           if (kDeform && f == 1 && sm.out[k].deform >= 0 && live) warped_mask_words(a, sm.out[k].deform, x0, y, vaa[1], vna[1]);
           continue;
         }
-        const int4 c4 = *reinterpret_cast<const int4*>(&sm.cover[l][warp][lane * 4]);
-        const int4 a4 = *reinterpret_cast<const int4*>(&sm.area[l][warp][lane * 4]);
-        const int carry = sm.carry[l][warp];
+        const int4 c4 = *reinterpret_cast<const int4*>(&sm.cover[l][row][lane * 4]);
+        const int4 a4 = *reinterpret_cast<const int4*>(&sm.area[l][row][lane * 4]);
+        const int carry = sm.carry[l][row];
         const bool cells = (c4.x | c4.y | c4.z | c4.w | a4.x | a4.y | a4.z | a4.w) != 0;
         if (!__any_sync(0xffffffffu, cells)) {
           // no outline crosses this row inside the tile: coverage is constant along it
@@ -1114,23 +1152,26 @@ __device__ __forceinline__ void raster_unit(const RenderArgs& a, RasterSmem& sm,
       }
 
       if (composite) {
-        if (s0 + k == 0) { uaa[0] = uaa[1] = una[0] = una[1] = 0; }
+        if (s0 + k == 0) { uaa[j][0] = uaa[j][1] = una[j][0] = una[j][1] = 0; }
         const bool add = sm.out[k].additive != 0;
 #pragma unroll
         for (int f = 0; f < 2; ++f) {
-          uaa[f] = comp4(uaa[f], vaa[f], add, sm.q255);
+          uaa[j][f] = comp4_lut(uaa[j][f], vaa[f], add, a.comp_lut);
           // non-AA masks stay in {0, 255} (the rules are closed on it) unless a warp field resampled them
-          if (kDeform) una[f] = comp4(una[f], vna[f], add, sm.q255);
-          else una[f] = add ? (una[f] | vna[f]) : (una[f] & ~vna[f]);
+          if (kDeform) una[j][f] = comp4_lut(una[j][f], vna[f], add, a.comp_lut);
+          else una[j][f] = add ? (una[j][f] | vna[f]) : (una[j][f] & ~vna[f]);
         }
       } else {
-        uaa[0] = vaa[0]; uaa[1] = vaa[1]; una[0] = vna[0]; una[1] = vna[1];
+        uaa[j][0] = vaa[0]; uaa[j][1] = vaa[1]; una[j][0] = vna[0]; una[j][1] = vna[1];
       }
     }
   }
   // the object's four masks over this tile: [AA 0, AA 1, non-AA 0, non-AA 1][tile row][lane], one word = four pixels
-  uint32_t* pm = a.pair_masks + (size_t)pr * (4 * TH * 32) + (slice * RTH + warp) * 32 + lane;
-  pm[0 * TH * 32] = uaa[0]; pm[1 * TH * 32] = uaa[1]; pm[2 * TH * 32] = una[0]; pm[3 * TH * 32] = una[1];
+#pragma unroll
+  for (int j = 0; j < RPW; ++j) {
+    uint32_t* pm = a.pair_masks + (size_t)pr * (4 * TH * 32) + (slice * RTH + warp + j * RWARPS) * 32 + lane;
+    pm[0 * TH * 32] = uaa[j][0]; pm[1 * TH * 32] = uaa[j][1]; pm[2 * TH * 32] = una[j][0]; pm[3 * TH * 32] = una[j][1];
+  }
   if (kQueue && n_shapes <= 0) {  // (an object without outlines: no barrier has published the claim yet)
     __syncthreads();
     pr_next = sm.next;
@@ -1144,7 +1185,6 @@ __global__ void __launch_bounds__(RASTER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster
   __shared__ RasterSmem sm;
   if (a.pair_ctl[1]) return;
   const int total = a.pair_ctl[0] * RSUB;  // work units: RSUB slices per pair
-  for (int i = threadIdx.x; i < 256; i += RASTER_THREADS) sm.q255[i] = (float)i / 255.f;
   int4 pe_next = (int)blockIdx.x < total ? a.pair_list[blockIdx.x / RSUB] : make_int4(0, 0, 0, 0);
   // Units differ a lot in cost (1 to 7 outlines, a few to hundreds of edges): after its first unit a block claims the next
   // one from a queue (pair_ctl[2]) instead of striding over the list, so no block is left with a long tail of heavy units.

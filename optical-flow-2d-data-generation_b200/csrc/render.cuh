@@ -41,6 +41,7 @@ struct RenderArgs {
   int* pair_ctl;              // [0] pairs claimed (atomic), [1] set when they exceed pair_cap (cannot happen: pair_cap is an upper bound; the kernels then skip the batch), [2] the raster kernel's work queue
   int pair_cap;
   int* pair_overflow;         // mapped host int, raised together with pair_ctl[1] (the host reports it after its next synchronisation)
+  const uint8_t* comp_lut;    // [2][256][256] MovingObjectComposite::renderMasks' rules tabulated (composite_lut_kernel): additive, then subtractive; index u * 256 + v
   // mode 9
   const float* fields;        // [n][flow|iflow][channel][H+1][W+1]
   int n_fields;
