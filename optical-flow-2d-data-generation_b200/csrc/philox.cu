@@ -31,8 +31,10 @@ struct Rng {
     obj = (uint32_t)object << 8;
     for (int i = 0; i < kPhiloxSlots; ++i) ctr[i] = 0;
   }
-  __device__ void raw(int slot, uint32_t& a, uint32_t& b) {
-    uint32_t x0 = s0, x1 = s1, x2 = (uint32_t)slot | obj, x3 = ctr[slot]++;
+  __device__ void raw(int slot, uint32_t& a, uint32_t& b) { raw_at(slot, 0, a, b); ++ctr[slot]; }
+  // the draw `ahead` positions further down the slot's stream, without consuming anything (see Gen::lanes)
+  __device__ void raw_at(int slot, int ahead, uint32_t& a, uint32_t& b) const {
+    uint32_t x0 = s0, x1 = s1, x2 = (uint32_t)slot | obj, x3 = (uint32_t)(unsigned char)(ctr[slot] + ahead);
     uint32_t ka = k0, kb = k1;
     for (int r = 0; r < 10; ++r) {
       const uint64_t p0 = (uint64_t)0xD2511F53u * x0, p1 = (uint64_t)0xCD9E8D57u * x2;
@@ -42,17 +44,18 @@ struct Rng {
     }
     a = x0; b = x1;
   }
-  __device__ float unit(int slot) {  // [0, 1)
+  __device__ float unit(int slot, int ahead = -1) {  // [0, 1); ahead >= 0: that draw of the stream, nothing consumed
     uint32_t a, b;
-    raw(slot, a, b);
+    if (ahead < 0) raw(slot, a, b); else raw_at(slot, ahead, a, b);
     return (float)(a >> 8) * (1.0f / 16777216.0f);
   }
-  __device__ float normal(int slot) {  // Box-Muller
+  __device__ float normal(int slot, int ahead = -1) {  // Box-Muller
     uint32_t a, b;
-    raw(slot, a, b);
+    if (ahead < 0) raw(slot, a, b); else raw_at(slot, ahead, a, b);
     const float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f), u2 = (float)(b >> 8) * (1.0f / 16777216.0f);
     return sqrtf(-2.0f * logf(u1)) * cosf(6.28318530717958647692f * u2);
   }
+  __device__ void skip(int slot, int n) { ctr[slot] = (unsigned char)(ctr[slot] + n); }
 };
 
 struct Gen {
@@ -63,14 +66,17 @@ struct Gen {
     const float sample = input * ((b + a) / 2.f - a) / normalize + (b + a) / 2.f;
     return (a <= sample && sample <= b) ? sample : (b + a) / 2.f;
   }
-  __device__ float real(int slot) {
+  // ahead >= 0 (here and in trigger): the value the ahead-th next call would return, without consuming a draw. Every draw is
+  // a pure function of (seed, sample, object, slot, draw number), so the lanes of the warp can each take one of a run of
+  // consecutive draws of a slot (a polygon's spokes) instead of one lane walking the run; rng.skip then consumes the run.
+  __device__ float real(int slot, int ahead = -1) {
     const PhiloxSlot& s = slots[slot];
     switch (s.kind) {
-      case 1: return s.a + (s.b - s.a) * rng.unit(slot);                                     // UREAL
-      case 5: { float t = rng.normal(slot); t = t > 0 ? t * t : -(t * t); return base_gauss(s.a, s.b, t, 6); }   // GAUSS_SQ
-      case 6: { float t = rng.normal(slot); return base_gauss(s.a, s.b, t * t * t, 10); }      // GAUSS_3
-      case 7: { float t = rng.normal(slot); const float q = t * t * t * t; return base_gauss(s.a, s.b, t > 0 ? q : -q, 15); }  // GAUSS_4
-      default: { float t = rng.normal(slot) * s.d + s.c; return (s.a <= t && t <= s.b) ? t : s.c; }  // GAUSS_MSR
+      case 1: return s.a + (s.b - s.a) * rng.unit(slot, ahead);                                     // UREAL
+      case 5: { float t = rng.normal(slot, ahead); t = t > 0 ? t * t : -(t * t); return base_gauss(s.a, s.b, t, 6); }   // GAUSS_SQ
+      case 6: { float t = rng.normal(slot, ahead); return base_gauss(s.a, s.b, t * t * t, 10); }      // GAUSS_3
+      case 7: { float t = rng.normal(slot, ahead); const float q = t * t * t * t; return base_gauss(s.a, s.b, t > 0 ? q : -q, 15); }  // GAUSS_4
+      default: { float t = rng.normal(slot, ahead) * s.d + s.c; return (s.a <= t && t <= s.b) ? t : s.c; }  // GAUSS_MSR
     }
   }
   __device__ int integer(int slot) {
@@ -83,9 +89,9 @@ struct Gen {
     }
     return s.opts[(int)(((uint64_t)a * (uint64_t)s.n_opts) >> 32)];  // CHOICE_*
   }
-  __device__ bool trigger(int slot) {
+  __device__ bool trigger(int slot, int ahead = -1) {
     const PhiloxSlot& s = slots[slot];
-    return s.a + (s.b - s.a) * rng.unit(slot) < s.c;
+    return s.a + (s.b - s.a) * rng.unit(slot, ahead) < s.c;
   }
 };
 
@@ -130,30 +136,44 @@ __device__ void gen_polygon(Gen& g, SampleOut& o, ofdg_blueprint& b, bool curves
     o.nseg += 4;
     return;
   }
-  const int spokes = g.integer(PolyObj_spokes);  // DG.cpp:2469-2495
-  for (int i = 0; i < spokes; ++i) {
-    const float phi = (float)((i * 360. / spokes + g.real(PolyObj_dphi)) * 3.14159265358979323846 / 180.);
-    const float r = g.real(PolyObj_r);
-    sx[i] = r * cosf(phi);  // scaled below, once ScaleX / ScaleY are drawn (same draw order as the reference)
-    sy[i] = r * sinf(phi);
+  // The whole warp runs this code with identical state; where the reference loops over the spokes, lane i takes spoke i
+  // (its draws are the i-th next ones of their slots) and writes its own segment.
+  const int lane = threadIdx.x & 31;
+  const int spokes = g.integer(PolyObj_spokes);  // DG.cpp:2469-2495 (at most 20: the mode tables' choices)
+  float px = 0.f, py = 0.f;
+  for (int i = lane; i < spokes; i += 32) {
+    const float phi = (float)((i * 360. / spokes + g.real(PolyObj_dphi, i)) * 3.14159265358979323846 / 180.);
+    const float r = g.real(PolyObj_r, i);
+    px = r * cosf(phi);  // scaled below, once ScaleX / ScaleY are drawn (same draw order as the reference)
+    py = r * sinf(phi);
   }
+  g.rng.skip(PolyObj_dphi, spokes);
+  g.rng.skip(PolyObj_r, spokes);
   const float xscale = g.real(PolyObj_ScaleX), yscale = g.real(PolyObj_ScaleY);
-  for (int i = 0; i < spokes; ++i) { sx[i] *= xscale; sy[i] *= yscale; st[i] = OFDG_SEG_LINE; }
-  st[0] = OFDG_SEG_DUMMY;
+  // the curve triggers: the n-th one asked for is the n-th next draw, whichever spoke asks; lane n draws it, every lane replays the walk
+  const unsigned fired = __ballot_sync(0xffffffffu, curves && lane < spokes && g.trigger(PolyObj_CurveTrigger, lane));
+  int asked = 0, mine = OFDG_SEG_LINE;
   for (int i = 1; i < spokes; ++i) {
-    if (curves && (i < spokes - 1) && g.trigger(PolyObj_CurveTrigger)) {
-      st[i] = OFDG_SEG_CURVE3;
-      st[i + 1] = OFDG_SEG_DUMMY;
+    if (curves && (i < spokes - 1) && ((fired >> asked++) & 1u)) {
+      if (lane == i) mine = OFDG_SEG_CURVE3;
+      if (lane == i + 1) mine = OFDG_SEG_DUMMY;
       ++i;
     }
   }
+  g.rng.skip(PolyObj_CurveTrigger, asked);
+  if (lane == 0) mine = OFDG_SEG_DUMMY;
+  if (lane < spokes) { sx[lane] = px * xscale; sy[lane] = py * yscale; st[lane] = mine; }
+  __syncwarp();
   b.seg_count = spokes;
   o.nseg += spokes;
 }
 
-__device__ void shrink(SampleOut& o, ofdg_blueprint& c, float f) {
+__device__ void shrink(SampleOut& o, ofdg_blueprint& c, float f) {  // (whole warp: lanes over the segments)
   if (c.obj_type == OFDG_OBJ_ELLIPSE) { c.ellipse_scale_x *= f; c.ellipse_scale_y *= f; }
-  else for (int i = 0; i < c.seg_count; ++i) { o.seg_x[c.seg_begin - o.seg_base + i] *= f; o.seg_y[c.seg_begin - o.seg_base + i] *= f; }
+  else {
+    for (int i = threadIdx.x & 31; i < c.seg_count; i += 32) { o.seg_x[c.seg_begin - o.seg_base + i] *= f; o.seg_y[c.seg_begin - o.seg_base + i] *= f; }
+    __syncwarp();
+  }
 }
 
 // generateForegroundObject (DG.cpp:2145-2830); components are never composite, so one level of nesting suffices
@@ -186,8 +206,10 @@ __device__ void gen_simple(Gen& g, SampleOut& o, int idx, bool is_component, int
     if (thin_modes && !is_component && g.trigger(ObjIsExtraThin)) b.ellipse_scale_x *= 0.05f;
   } else if (b.obj_type == OFDG_OBJ_POLYGON) {
     gen_polygon(g, o, b, g.mode >= 4);
-    if (thin_modes && !is_component && g.trigger(ObjIsExtraThin))
-      for (int i = 0; i < b.seg_count; ++i) o.seg_x[b.seg_begin - o.seg_base + i] *= 0.05f;
+    if (thin_modes && !is_component && g.trigger(ObjIsExtraThin)) {
+      for (int i = threadIdx.x & 31; i < b.seg_count; i += 32) o.seg_x[b.seg_begin - o.seg_base + i] *= 0.05f;
+      __syncwarp();
+    }
   }
   o.bp[idx] = b;
 }
@@ -218,11 +240,12 @@ __device__ void gen_object(Gen& g, SampleOut& o, int idx, int n_fields, int& fie
     ofdg_blueprint c2 = c1;
     if (c1.obj_type == OFDG_OBJ_POLYGON) {
       c2.seg_begin = o.seg_base + o.nseg;
-      for (int i = 0; i < c1.seg_count; ++i) {
+      for (int i = threadIdx.x & 31; i < c1.seg_count; i += 32) {
         o.seg_type[o.nseg + i] = o.seg_type[c1.seg_begin - o.seg_base + i];
         o.seg_x[o.nseg + i] = o.seg_x[c1.seg_begin - o.seg_base + i];
         o.seg_y[o.nseg + i] = o.seg_y[c1.seg_begin - o.seg_base + i];
       }
+      __syncwarp();
       o.nseg += c1.seg_count;
     }
     if (c1.obj_type == OFDG_OBJ_ELLIPSE) {
@@ -265,8 +288,11 @@ __device__ void gen_object(Gen& g, SampleOut& o, int idx, int n_fields, int& fie
   o.bp[idx] = b;
 }
 
-// One WARP per (sample, role), lane 0 drawing: the roles of a sample (its objects, its background) run through very
-// different branches and loop counts, so as threads of one warp they would execute one after the other. An object's
+// One WARP per (sample, role): the roles of a sample (its objects, its background) run through very different branches and
+// loop counts, so as threads of one warp they would execute one after the other. All 32 lanes of the role's warp run its code
+// with identical state (no divergence, nothing wasted that lane 0 alone would not idle away), and split the loops over a
+// polygon's spokes / segments among them: the longest role (a composite of seven 20-spoke polygons) drops from ~500 draws in a
+// row to ~100. An object's
 // blueprints and polygon segments are read, scaled and rewritten several times while they are drawn (components copy and
 // shrink their parent's outline, thin objects rescale theirs): they live in shared memory until the object is complete and
 // leave in one coalesced copy by the whole warp -- as global read-modify-write chains they were most of the kernel's 169 us,
@@ -281,7 +307,7 @@ struct ParamStage {
   float seg_x[kSegPerObj];
   float seg_y[kSegPerObj];
 };
-__global__ void __launch_bounds__(32 * kParamWarps) philox_params_kernel(PhiloxArgs a) {
+__global__ void __launch_bounds__(32 * kParamWarps, 3) philox_params_kernel(PhiloxArgs a) {
   __shared__ ParamStage s_stage[kParamWarps];
   __shared__ PhiloxSlot s_slots[kPhiloxSlots];
   for (int i = threadIdx.x; i < (int)(kPhiloxSlots * sizeof(PhiloxSlot) / 4); i += blockDim.x)
@@ -293,7 +319,7 @@ __global__ void __launch_bounds__(32 * kParamWarps) philox_params_kernel(PhiloxA
   ParamStage& st = s_stage[w];
   const int bp_base = s * kPhiloxMaxBp + 1 + k * kPhiloxMaxShapes, seg_base = s * kPhiloxMaxSeg + k * kSegPerObj;
   int nbp = 0, nseg = 0;
-  if (lane == 0) {
+  {  // every lane runs the role's code with identical state (same draws, same branches); the lanes only differ inside the loops over a polygon's segments
     Gen g;
     g.slots = s_slots;
     g.mode = a.mode;
@@ -301,7 +327,7 @@ __global__ void __launch_bounds__(32 * kParamWarps) philox_params_kernel(PhiloxA
     g.rng.init(a.seed, a.first_sample + (uint64_t)s, kPhiloxMaxObj);
     int fg = a.fg_override > 0 ? a.fg_override : (int)g.real(NumberOfFgObjects);
     if (fg > kPhiloxMaxObj) {  // more objects than the fixed strides hold: rendered without the rest, and the host is told
-      if (a.truncated && k == kPhiloxMaxObj) *a.truncated = 1;
+      if (a.truncated && k == kPhiloxMaxObj && lane == 0) *a.truncated = 1;
       fg = kPhiloxMaxObj;
     }
     int field_draws = 0;
@@ -326,8 +352,10 @@ __global__ void __launch_bounds__(32 * kParamWarps) philox_params_kernel(PhiloxA
         g.rng.raw(FieldPick, r0, r1);
         bg.field_id = (int)(r0 % (uint32_t)a.n_fields);
       }
-      a.bp[s * kPhiloxMaxBp] = bg;
-      a.n_top[s] = fg;
+      if (lane == 0) {
+        a.bp[s * kPhiloxMaxBp] = bg;
+        a.n_top[s] = fg;
+      }
       if (a.augment) {
         ofdg_augment au;
         au.enabled = 1;
@@ -336,8 +364,8 @@ __global__ void __launch_bounds__(32 * kParamWarps) philox_params_kernel(PhiloxA
         au.contrast = 0.7f + 0.6f * g.rng.unit(AugContrast);
         au.noise_sigma = 10.f * g.rng.unit(AugSigma);
         g.rng.raw(AugSeed, au.noise_seed[0], au.noise_seed[1]);
-        a.samples[s].aug = au;
-      } else {
+        if (lane == 0) a.samples[s].aug = au;
+      } else if (lane == 0) {
         a.samples[s].aug.enabled = 0;
       }
     } else if (k < fg) {
@@ -354,11 +382,9 @@ __global__ void __launch_bounds__(32 * kParamWarps) philox_params_kernel(PhiloxA
       gen_object(g, o, 0, a.n_fields, field_draws);
       nbp = o.nbp; nseg = o.nseg;
     }
-    if (k < kPhiloxMaxObj) { a.obj_nbp[s * kPhiloxMaxObj + k] = nbp; a.obj_nseg[s * kPhiloxMaxObj + k] = nseg; }
+    if (k < kPhiloxMaxObj && lane == 0) { a.obj_nbp[s * kPhiloxMaxObj + k] = nbp; a.obj_nseg[s * kPhiloxMaxObj + k] = nseg; }
   }
   __syncwarp();
-  nbp = __shfl_sync(0xffffffffu, nbp, 0);
-  nseg = __shfl_sync(0xffffffffu, nseg, 0);
   {
     int* dst = reinterpret_cast<int*>(a.bp + bp_base);
     const int* src = reinterpret_cast<const int*>(st.bp);
