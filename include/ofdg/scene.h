@@ -52,8 +52,9 @@ typedef struct ofdg_blueprint {
  * the oracle reproduces it bit for bit: for frame f, channel c, pixel p with 8-bit value v,
  *   y = contrast * (gain[c] * v - 127.5f) + 127.5f + brightness + noise_sigma * n(f, c, p)
  *   out = min(max(y, 0), 255)                       (float32, one rounding per operation, no FMA)
- * n = ((sum of the eight 16-bit halves of Philox4x32-10(key = noise_seed, counter = {p, 2*c + f, 0, 0}))
- *      - 262140) * (1 / 53510.1f)                   (Irwin-Hall, approximately N(0,1), integer-exact)
+ * n = ((sum of the four bytes of word c of Philox4x32-10(key = noise_seed, counter = {p, f, 0, 0}))
+ *      - 510) * (1 / 147.80f)                       (Irwin-Hall of four bytes, approximately N(0,1), integer-exact;
+ *                                                     one Philox call serves the three channels of a pixel: ofdg/augment.h)
  * The flow is not touched. enabled == 0 leaves the sample exactly as the reference would produce it. */
 typedef struct ofdg_augment {
   int32_t  enabled;

@@ -193,6 +193,26 @@ __device__ __forceinline__ uint32_t blend_rgbx(uint32_t f, uint32_t t, unsigned 
   return __byte_perm(__byte_perm(q[0], q[1], 0x0040u), q[2], 0x5410u);  // q <= 255: q[2]'s byte 1 supplies the zero
 }
 
+// The blob write of a lane's four pixels with the augmentation applied (both frames, three channels). Out of line: the
+// reference path never takes it, and inlined its Philox rounds were most of the render kernels' static code. One Philox call
+// per pixel and frame yields the three channels' noise sums (ofdg_noise3).
+__device__ __noinline__ void store_augmented(const ofdg_augment* au, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1,
+                                             uint32_t b2, uint32_t b3, float* o0, float* o1, size_t P, uint32_t p) {
+  const uint32_t k0 = au->noise_seed[0], k1 = au->noise_seed[1];
+  const uint32_t n00 = ofdg_noise3(k0, k1, p, 0u), n01 = ofdg_noise3(k0, k1, p + 1, 0u), n02 = ofdg_noise3(k0, k1, p + 2, 0u), n03 = ofdg_noise3(k0, k1, p + 3, 0u);
+  const uint32_t n10 = ofdg_noise3(k0, k1, p, 1u), n11 = ofdg_noise3(k0, k1, p + 1, 1u), n12 = ofdg_noise3(k0, k1, p + 2, 1u), n13 = ofdg_noise3(k0, k1, p + 3, 1u);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float4 v0, v1;
+    v0.x = ofdg_augment_apply(au, byte_to_float(a0, c), c, n00); v0.y = ofdg_augment_apply(au, byte_to_float(a1, c), c, n01);
+    v0.z = ofdg_augment_apply(au, byte_to_float(a2, c), c, n02); v0.w = ofdg_augment_apply(au, byte_to_float(a3, c), c, n03);
+    v1.x = ofdg_augment_apply(au, byte_to_float(b0, c), c, n10); v1.y = ofdg_augment_apply(au, byte_to_float(b1, c), c, n11);
+    v1.z = ofdg_augment_apply(au, byte_to_float(b2, c), c, n12); v1.w = ofdg_augment_apply(au, byte_to_float(b3, c), c, n13);
+    __stcs(reinterpret_cast<float4*>(o0 + c * P), v0);
+    __stcs(reinterpret_cast<float4*>(o1 + c * P), v1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // mode 9: non-rigid warp fields (consumer side, DG.cpp:237-252, 370-386, 403-406, 714-717)
 // ------------------------------------------------------------------------------------------------
@@ -229,6 +249,32 @@ __device__ __forceinline__ uint32_t dirichlet_rgbx(Tap tap, float fx, float fy) 
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const float v = cimg_lerp2(byte_to_float(pcc, c), byte_to_float(pnc, c), byte_to_float(pcn, c), byte_to_float(pnn, c), dx, dy);
+    out |= ((uint32_t)(unsigned char)v) << (8 * c);
+  }
+  return out;
+}
+// applyWarpFieldToTexture over getTransformedTexture (DG.cpp:341-345, 670-681): the Dirichlet-bilinear sample at (fx, fy) of the
+// sw x sh image that AGG's span filter would produce from `img` under the inverse matrix tinv -- each of its four taps is one
+// span-bilinear pixel. The two taps of a row share the row's span interpolator (its set-up is two matrix products and four
+// roundings in double), so it is built once per row, not once per tap.
+__device__ __forceinline__ uint32_t warped_dirichlet_rgbx(const uchar4* img, int pitch, int sw, int sh, const double* tinv, float fx, float fy) {
+  int ix, iy;
+  float dx, dy;
+  if (!dirichlet_setup(fx, fy, ix, iy, dx, dy)) return 0u;
+  uint32_t px[4] = {0u, 0u, 0u, 0u};  // cc, nc, cn, nn; 0 outside
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int py = iy + r;
+    if (py < 0 || py >= sh || ix + 1 < 0 || ix >= sw) continue;
+    RowWarp rw;
+    rw.init(tinv, (double)py, sw);
+    if (ix >= 0) px[2 * r] = bilinear_rgbx(img, pitch, 0, 0, sw, sh, rw, ix);
+    if (ix + 1 < sw) px[2 * r + 1] = bilinear_rgbx(img, pitch, 0, 0, sw, sh, rw, ix + 1);
+  }
+  uint32_t out = 0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = cimg_lerp2(byte_to_float(px[0], c), byte_to_float(px[1], c), byte_to_float(px[2], c), byte_to_float(px[3], c), dx, dy);
     out |= ((uint32_t)(unsigned char)v) << (8 * c);
   }
   return out;
@@ -526,17 +572,10 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
         // doubled inverse field before the centre crop (DG.cpp:670-681, 1194-1201)
         const int fw = W + 1, fh = H + 1;
         const float* ifl = a.fields + ((size_t)smp.bg_field * 2 + 1) * 2 * fw * fh;
-        const double* tinv = smp.bg_tex_inv;
-        auto tap = [&](int px, int py) -> uint32_t {
-          if (px < 0 || py < 0 || px >= W2 || py >= H2) return 0u;
-          RowWarp r2;
-          r2.init(tinv, (double)py, W2);
-          return bilinear_rgbx(bg, W2, 0, 0, W2, H2, r2, px);
-        };
         for (int i = 0; i < 4; ++i) {
           const int X = x0 + i + W / 2, Y = y + H / 2;
           const float sx = X + resized_field2(ifl, fw, fh, X, Y, a), sy = Y + resized_field2(ifl + (size_t)fw * fh, fw, fh, X, Y, a);
-          col1[i] = dirichlet_rgbx(tap, sx, sy);
+          col1[i] = warped_dirichlet_rgbx(bg, W2, W2, H2, smp.bg_tex_inv, sx, sy);
         }
       }
     } else {
@@ -769,20 +808,16 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_RENDER_MIN_BLOCKS) render
   if (a.img0) {
     float* o0 = a.img0 + (size_t)sample * 3 * P + pix;
     float* o1 = a.img1 + (size_t)sample * 3 * P + pix;
-    const bool augment = smp.aug.enabled != 0;  // this repository's own colour/noise augmentation (ofdg/augment.h); never set by the reference path
+    if (smp.aug.enabled != 0) {  // this repository's own colour/noise augmentation (ofdg/augment.h); never set by the reference path
+      store_augmented(&smp.aug, col0[0], col0[1], col0[2], col0[3], col1[0], col1[1], col1[2], col1[3], o0, o1, P, (uint32_t)pix);
+    } else {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float4 v0 = make_float4(byte_to_float(col0[0], c), byte_to_float(col0[1], c), byte_to_float(col0[2], c), byte_to_float(col0[3], c));
-      float4 v1 = make_float4(byte_to_float(col1[0], c), byte_to_float(col1[1], c), byte_to_float(col1[2], c), byte_to_float(col1[3], c));
-      if (augment) {
-        const uint32_t p = (uint32_t)pix;
-        v0.x = ofdg_augment_value(&smp.aug, v0.x, c, 0, p); v0.y = ofdg_augment_value(&smp.aug, v0.y, c, 0, p + 1);
-        v0.z = ofdg_augment_value(&smp.aug, v0.z, c, 0, p + 2); v0.w = ofdg_augment_value(&smp.aug, v0.w, c, 0, p + 3);
-        v1.x = ofdg_augment_value(&smp.aug, v1.x, c, 1, p); v1.y = ofdg_augment_value(&smp.aug, v1.y, c, 1, p + 1);
-        v1.z = ofdg_augment_value(&smp.aug, v1.z, c, 1, p + 2); v1.w = ofdg_augment_value(&smp.aug, v1.w, c, 1, p + 3);
+      for (int c = 0; c < 3; ++c) {
+        const float4 v0 = make_float4(byte_to_float(col0[0], c), byte_to_float(col0[1], c), byte_to_float(col0[2], c), byte_to_float(col0[3], c));
+        const float4 v1 = make_float4(byte_to_float(col1[0], c), byte_to_float(col1[1], c), byte_to_float(col1[2], c), byte_to_float(col1[3], c));
+        __stcs(reinterpret_cast<float4*>(o0 + c * P), v0);
+        __stcs(reinterpret_cast<float4*>(o1 + c * P), v1);
       }
-      __stcs(reinterpret_cast<float4*>(o0 + c * P), v0);
-      __stcs(reinterpret_cast<float4*>(o1 + c * P), v1);
     }
   }
   __stcs(reinterpret_cast<float4*>(of), make_float4(fxv[0], fxv[1], fxv[2], fxv[3]));
@@ -882,6 +917,9 @@ static_assert(RTH % RWARPS == 0 && RLAYER % 2 == 0 && RLAYER <= NLAYER && RLAYER
 __device__ __forceinline__ bool box_hits_rows(const int32_t* b, int tx0, int ty0, int rows) {
   return b[1] <= ty0 + rows - 1 && b[3] >= ty0 && b[0] <= tx0 + TW - 1 && b[2] >= tx0;
 }
+#ifndef OFDG_SHADE_DEFORM_MIN_BLOCKS
+#define OFDG_SHADE_DEFORM_MIN_BLOCKS 4  // the mode-9 instances (warp-field branches compiled in): 5 / 4 / 3 blocks per SM (48 / 64 / 80 registers) -> config 3 shade 0.473 / 0.450 / 0.452 ms
+#endif
 #ifndef OFDG_SHADE_MIN_BLOCKS
 #define OFDG_SHADE_MIN_BLOCKS 5  // measured (round 2 kernel): 4 / 5 / 6 blocks per SM -> 0.152 / 0.142 / 0.153 ms
 #endif
@@ -1198,7 +1236,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster
 }
 
 template <bool kDeform, bool kExtra>
-__global__ void __launch_bounds__(RENDER_THREADS, OFDG_SHADE_MIN_BLOCKS) shade_kernel(RenderArgs a) {
+__global__ void __launch_bounds__(RENDER_THREADS, kDeform ? OFDG_SHADE_DEFORM_MIN_BLOCKS : OFDG_SHADE_MIN_BLOCKS) shade_kernel(RenderArgs a) {
   if (a.pair_ctl[1]) return;
   const int W = a.W, H = a.H;
   const int tiles_x = (W + TW - 1) / TW;
@@ -1275,17 +1313,10 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_SHADE_MIN_BLOCKS) shade_k
         // doubled inverse field before the centre crop (DG.cpp:670-681, 1194-1201)
         const int fw = W + 1, fh = H + 1;
         const float* ifl = a.fields + ((size_t)smp.bg_field * 2 + 1) * 2 * fw * fh;
-        const double* tinv = smp.bg_tex_inv;
-        auto tap = [&](int px, int py) -> uint32_t {
-          if (px < 0 || py < 0 || px >= W2 || py >= H2) return 0u;
-          RowWarp r2;
-          r2.init(tinv, (double)py, W2);
-          return bilinear_rgbx(bg, W2, 0, 0, W2, H2, r2, px);
-        };
         for (int i = 0; i < 4; ++i) {
           const int X = x0 + i + W / 2, Y = y + H / 2;
           const float sx = X + resized_field2(ifl, fw, fh, X, Y, a), sy = Y + resized_field2(ifl + (size_t)fw * fh, fw, fh, X, Y, a);
-          col1[i] = dirichlet_rgbx(tap, sx, sy);
+          col1[i] = warped_dirichlet_rgbx(bg, W2, W2, H2, smp.bg_tex_inv, sx, sy);
         }
       }
     } else {
@@ -1394,18 +1425,12 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_SHADE_MIN_BLOCKS) shade_k
       const double* tinv = a.objects[obj_begin + k].tex_inv;
       const int fw = W + 1, fh = H + 1;
       const float* ifl = a.fields + ((size_t)ob.field * 2 + 1) * 2 * fw * fh;
-      auto tap = [&](int px, int py) -> uint32_t {
-        if (px < 0 || py < 0 || px >= W || py >= H) return 0u;
-        RowWarp rw;
-        rw.init(tinv, (double)py, W);
-        return bilinear_rgbx(tex, ti.fg_pitch, 0, 0, W, H, rw, px);
-      };
       for (int i = 0; i < 4; ++i) {
         const unsigned m1 = (m1w >> (8 * i)) & 255u;
         if (!m1) continue;
         const int x = x0 + i;
         const float sx = x + ifl[(size_t)y * fw + x], sy = y + ifl[(size_t)fw * fh + (size_t)y * fw + x];
-        col1[i] = blend_rgbx(col1[i], dirichlet_rgbx(tap, sx, sy), m1);
+        col1[i] = blend_rgbx(col1[i], warped_dirichlet_rgbx(tex, ti.fg_pitch, W, H, tinv, sx, sy), m1);
       }
     }
   }
@@ -1468,20 +1493,16 @@ __global__ void __launch_bounds__(RENDER_THREADS, OFDG_SHADE_MIN_BLOCKS) shade_k
   if (a.img0) {
     float* o0 = a.img0 + (size_t)sample * 3 * P + pix;
     float* o1 = a.img1 + (size_t)sample * 3 * P + pix;
-    const bool augment = smp.aug.enabled != 0;  // this repository's own colour/noise augmentation (ofdg/augment.h); never set by the reference path
+    if (smp.aug.enabled != 0) {  // this repository's own colour/noise augmentation (ofdg/augment.h); never set by the reference path
+      store_augmented(&smp.aug, col0[0], col0[1], col0[2], col0[3], col1[0], col1[1], col1[2], col1[3], o0, o1, P, (uint32_t)pix);
+    } else {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float4 v0 = make_float4(byte_to_float(col0[0], c), byte_to_float(col0[1], c), byte_to_float(col0[2], c), byte_to_float(col0[3], c));
-      float4 v1 = make_float4(byte_to_float(col1[0], c), byte_to_float(col1[1], c), byte_to_float(col1[2], c), byte_to_float(col1[3], c));
-      if (augment) {
-        const uint32_t p = (uint32_t)pix;
-        v0.x = ofdg_augment_value(&smp.aug, v0.x, c, 0, p); v0.y = ofdg_augment_value(&smp.aug, v0.y, c, 0, p + 1);
-        v0.z = ofdg_augment_value(&smp.aug, v0.z, c, 0, p + 2); v0.w = ofdg_augment_value(&smp.aug, v0.w, c, 0, p + 3);
-        v1.x = ofdg_augment_value(&smp.aug, v1.x, c, 1, p); v1.y = ofdg_augment_value(&smp.aug, v1.y, c, 1, p + 1);
-        v1.z = ofdg_augment_value(&smp.aug, v1.z, c, 1, p + 2); v1.w = ofdg_augment_value(&smp.aug, v1.w, c, 1, p + 3);
+      for (int c = 0; c < 3; ++c) {
+        const float4 v0 = make_float4(byte_to_float(col0[0], c), byte_to_float(col0[1], c), byte_to_float(col0[2], c), byte_to_float(col0[3], c));
+        const float4 v1 = make_float4(byte_to_float(col1[0], c), byte_to_float(col1[1], c), byte_to_float(col1[2], c), byte_to_float(col1[3], c));
+        __stcs(reinterpret_cast<float4*>(o0 + c * P), v0);
+        __stcs(reinterpret_cast<float4*>(o1 + c * P), v1);
       }
-      __stcs(reinterpret_cast<float4*>(o0 + c * P), v0);
-      __stcs(reinterpret_cast<float4*>(o1 + c * P), v1);
     }
   }
   __stcs(reinterpret_cast<float4*>(of), make_float4(fxv[0], fxv[1], fxv[2], fxv[3]));
