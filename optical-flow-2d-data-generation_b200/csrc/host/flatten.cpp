@@ -105,7 +105,7 @@ float cimg_modf(float x, float m) {
 }
 
 void prepare_background(const ofdg_blueprint& b, const FlattenConfig& cfg, const Affine& tex_inv,
-                        bool deformed, BgPrep& p) {
+                        int spread, BgPrep& p) {
   const int W = cfg.W, H = cfg.H, tw = 2 * W, th = 2 * H;
   p.tex = (int32_t)((unsigned)b.tex_id % (unsigned)cfg.n_tex);
   const int w = cfg.tex_info[p.tex].w, h = cfg.tex_info[p.tex].h;
@@ -156,12 +156,15 @@ void prepare_background(const ofdg_blueprint& b, const FlattenConfig& cfg, const
   p.pad = 0;
 
   // Part of the prepared texture the renderer touches: the centre W x H window (frame 0)
-  // plus the footprint of the frame-1 warp (4 taps around tex_inv * pixel centre).
+  // plus the footprint of the frame-1 warp (4 taps around tex_inv * pixel centre). A background with a warp field samples the
+  // warped canvas up to `spread` pixels (twice the inverse field's reach, + 2 for the taps) outside the window -- never
+  // outside the canvas (Dirichlet boundary); spread < 0: reach unknown, the whole canvas.
   int nx0 = W / 2, ny0 = H / 2, nx1 = W / 2 + W - 1, ny1 = H / 2 + H - 1;
-  if (deformed) {
+  if (spread < 0) {
     nx0 = 0; ny0 = 0; nx1 = tw - 1; ny1 = th - 1;
   } else {
-    const double cx[2] = {W / 2 + 0.0, W / 2 + W + 1.0}, cy[2] = {H / 2 + 0.0, H / 2 + H + 1.0};
+    const double cx[2] = {std::max(0.0, W / 2 + 0.0 - spread), std::min((double)tw, W / 2 + W + 1.0 + spread)};
+    const double cy[2] = {std::max(0.0, H / 2 + 0.0 - spread), std::min((double)th, H / 2 + H + 1.0 + spread)};
     double fx0 = 1e300, fy0 = 1e300, fx1 = -1e300, fy1 = -1e300;
     for (int i = 0; i < 2; ++i)
       for (int j = 0; j < 2; ++j) {
@@ -307,7 +310,9 @@ void flatten(const ofdg_task_batch& tb, const FlattenConfig& cfg, FlatBatch& out
     const bool bg_deformed = (cfg.mode == 9 && bg.do_warpfield_deformation && bg.field_id >= 0);
     smp.bg_field = bg_deformed ? bg.field_id : -1;
     if (smp.bg_field >= cfg.n_fields) throw std::runtime_error("background refers to a warp field that was not injected (ofdg_set_fields)");
-    prepare_background(bg, cfg, tex_inv, bg_deformed, smp.prep);
+    // (a reach beyond the canvas is the whole canvas anyway: clamped so that 2 * reach + 2 cannot overflow)
+    const int spread = !bg_deformed ? 0 : (cfg.field_reach ? 2 * std::min(cfg.field_reach[bg.field_id], 4 * (W + H)) + 2 : -1);
+    prepare_background(bg, cfg, tex_inv, spread, smp.prep);
     if (tb.augment) smp.aug = tb.augment[t];
 
     // addBackgroundMotion's bracket T(-W/2,-H/2) * M_bg * T(W/2,H/2), DG.cpp:327-329

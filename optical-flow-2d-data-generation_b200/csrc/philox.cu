@@ -489,7 +489,7 @@ __device__ float cimg_mod_dev(float x, float m) {
   return (float)(dx - dm * floor(dx / dm));
 }
 
-__device__ void prepare_bg(const PhiloxArgs& a, const ofdg_blueprint& b, const Affine& tex_inv, bool deformed, BgPrep& p) {
+__device__ void prepare_bg(const PhiloxArgs& a, const ofdg_blueprint& b, const Affine& tex_inv, int spread, BgPrep& p) {
   const int W = a.W, H = a.H, tw = 2 * W, th = 2 * H;
   p.tex = (int)((unsigned)b.tex_id % (unsigned)a.n_tex);
   const int w = a.tex_info[p.tex].w, h = a.tex_info[p.tex].h;
@@ -519,12 +519,13 @@ __device__ void prepare_bg(const PhiloxArgs& a, const ofdg_blueprint& b, const A
   p.general = (p.crop_w * 10 > tw * 13 || p.crop_h * 10 > th * 13) ? 1 : 0;
   p.pad = 0;
   int nx0 = W / 2, ny0 = H / 2, nx1 = W / 2 + W - 1, ny1 = H / 2 + H - 1;
-  if (deformed) { nx0 = 0; ny0 = 0; nx1 = tw - 1; ny1 = th - 1; }
-  else {
+  if (spread < 0) { nx0 = 0; ny0 = 0; nx1 = tw - 1; ny1 = th - 1; }
+  else {  // (host/flatten.cpp: a background with a warp field samples the warped canvas up to `spread` pixels outside the window)
     double fx0 = 1e300, fy0 = 1e300, fx1 = -1e300, fy1 = -1e300;
     for (int i = 0; i < 2; ++i)
       for (int j = 0; j < 2; ++j) {
-        double x = i ? W / 2 + W + 1.0 : W / 2 + 0.0, y = j ? H / 2 + H + 1.0 : H / 2 + 0.0;
+        double x = i ? fmin((double)tw, W / 2 + W + 1.0 + spread) : fmax(0.0, W / 2 + 0.0 - spread);
+        double y = j ? fmin((double)th, H / 2 + H + 1.0 + spread) : fmax(0.0, H / 2 + 0.0 - spread);
         tex_inv.apply(&x, &y);
         fx0 = fmin(fx0, x); fx1 = fmax(fx1, x); fy0 = fmin(fy0, y); fy1 = fmax(fy1, y);
       }
@@ -558,7 +559,8 @@ __global__ void __launch_bounds__(kFlatObjPerBlock * kFlatLanes) philox_flatten_
     bgM.store(smp.bg_motion);
     bgM.inverse().store(smp.bg_motion_inv);
     smp.bg_field = (a.mode == 9 && bg.do_warpfield_deformation && bg.field_id >= 0) ? bg.field_id : -1;
-    prepare_bg(a, bg, tex_inv, smp.bg_field >= 0, smp.prep);
+    const int spread = smp.bg_field < 0 ? 0 : (a.field_reach ? 2 * min(a.field_reach[smp.bg_field], 4 * (W + H)) + 2 : -1);
+    prepare_bg(a, bg, tex_inv, spread, smp.prep);
     smp.obj_begin = s * kPhiloxMaxObj;
     smp.obj_count = a.n_top[s];
     a.samples[s] = smp;
