@@ -392,7 +392,7 @@ def run_ours(args):
     img0 = torch.empty((B, 3, H, W), device="cuda", dtype=torch.float32)
     img1 = torch.empty_like(img0)
     flow = torch.empty((B, 2, H, W), device="cuda", dtype=torch.float32)
-    tstream = torch.cuda.Stream()  # a non-default stream: torch events and our launches share it
+    tstream = torch.cuda.Stream(priority=int(os.environ.get("OFDG_BENCH_STREAM_PRIORITY", "0")))  # a non-default stream: torch events and our launches share it (experiments: -1 = high priority)
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
 

@@ -121,6 +121,14 @@ __device__ ofdg_blueprint blank_bp() {
   return b;
 }
 
+// Every lane of the role's warp holds the same blueprint; lane 0 writes it to the staging area, and the warp is
+// synchronised so that any lane may read it back.
+__device__ void put_bp(SampleOut& o, int idx, const ofdg_blueprint& b) {
+  __syncwarp();  // (no lane is still reading the slot's previous content)
+  if ((threadIdx.x & 31) == 0) o.bp[idx] = b;
+  __syncwarp();
+}
+
 __device__ void gen_polygon(Gen& g, SampleOut& o, ofdg_blueprint& b, bool curves) {
   b.seg_begin = o.seg_base + o.nseg;
   float* sx = o.seg_x + o.nseg;
@@ -129,9 +137,12 @@ __device__ void gen_polygon(Gen& g, SampleOut& o, ofdg_blueprint& b, bool curves
   if (g.mode == 1) {  // DG.cpp:2163-2183
     const float radius = g.real(PolyObj_r);
     const float xs = radius * g.real(PolyObj_ScaleX), ys = radius * g.real(PolyObj_ScaleY);
-    sx[0] = xs; sx[1] = xs; sx[2] = -xs; sx[3] = -xs;
-    sy[0] = -ys; sy[1] = ys; sy[2] = ys; sy[3] = -ys;
-    st[0] = OFDG_SEG_DUMMY; st[1] = st[2] = st[3] = OFDG_SEG_LINE;
+    if ((threadIdx.x & 31) == 0) {
+      sx[0] = xs; sx[1] = xs; sx[2] = -xs; sx[3] = -xs;
+      sy[0] = -ys; sy[1] = ys; sy[2] = ys; sy[3] = -ys;
+      st[0] = OFDG_SEG_DUMMY; st[1] = st[2] = st[3] = OFDG_SEG_LINE;
+    }
+    __syncwarp();
     b.seg_count = 4;
     o.nseg += 4;
     return;
@@ -211,7 +222,7 @@ __device__ void gen_simple(Gen& g, SampleOut& o, int idx, bool is_component, int
       __syncwarp();
     }
   }
-  o.bp[idx] = b;
+  put_bp(o, idx, b);
 }
 
 __device__ void copy_placement(ofdg_blueprint& c, const ofdg_blueprint& b) {
@@ -227,15 +238,18 @@ __device__ void gen_object(Gen& g, SampleOut& o, int idx, int n_fields, int& fie
   b.comp_begin = o.bp_base + o.nbp;
   if (thin_modes && g.trigger(ObjIsExtraThin)) {  // "outline": a shape minus a slightly smaller copy (DG.cpp:2504-2547)
     const int i1 = o.nbp++;
-    o.bp[i1] = blank_bp();
-    o.bp[i1].obj_type = OFDG_OBJ_COMPOSITE;
+    {
+      ofdg_blueprint nb = blank_bp();
+      nb.obj_type = OFDG_OBJ_COMPOSITE;
+      put_bp(o, i1, nb);
+    }
     gen_simple(g, o, i1, true, n_fields, field_draws);
     ofdg_blueprint c1 = o.bp[i1];
     c1.parent = o.bp_base + idx;
     copy_placement(c1, b);
     c1.is_additive_component = 1;
     c1.do_warpfield_deformation = b.do_warpfield_deformation; c1.field_id = b.field_id;
-    o.bp[i1] = c1;
+    put_bp(o, i1, c1);
     const int i2 = o.nbp++;
     ofdg_blueprint c2 = c1;
     if (c1.obj_type == OFDG_OBJ_POLYGON) {
@@ -259,14 +273,17 @@ __device__ void gen_object(Gen& g, SampleOut& o, int idx, int n_fields, int& fie
       shrink(o, c2, 0.9f);
     }
     c2.is_additive_component = 0;
-    o.bp[i2] = c2;
+    put_bp(o, i2, c2);
     b.comp_count = 2;
   } else {  // DG.cpp:2549-2591
     const int parts = g.integer(CompObiNumberOfComponents);
     for (int part = 0; part < parts; ++part) {
       const int ci = o.nbp++;
-      o.bp[ci] = blank_bp();
-      o.bp[ci].obj_type = OFDG_OBJ_COMPOSITE;
+      {
+        ofdg_blueprint nb = blank_bp();
+        nb.obj_type = OFDG_OBJ_COMPOSITE;
+        put_bp(o, ci, nb);
+      }
       gen_simple(g, o, ci, true, n_fields, field_draws);
       ofdg_blueprint c = o.bp[ci];
       c.parent = o.bp_base + idx;
@@ -281,11 +298,11 @@ __device__ void gen_object(Gen& g, SampleOut& o, int idx, int n_fields, int& fie
         c.is_additive_component = g.trigger(ComponentIsAdditive) ? 1 : 0;
       }
       c.do_warpfield_deformation = b.do_warpfield_deformation; c.field_id = b.field_id;
-      o.bp[ci] = c;
+      put_bp(o, ci, c);
     }
     b.comp_count = parts;
   }
-  o.bp[idx] = b;
+  put_bp(o, idx, b);
 }
 
 // One WARP per (sample, role): the roles of a sample (its objects, its background) run through very different branches and
@@ -377,8 +394,11 @@ __global__ void __launch_bounds__(32 * kParamWarps, 3) philox_params_kernel(Phil
       o.seg_base = seg_base;
       o.bp = st.bp; o.seg_type = st.seg_type; o.seg_x = st.seg_x; o.seg_y = st.seg_y;
       o.nbp = 1; o.nseg = 0;
-      o.bp[0] = blank_bp();
-      o.bp[0].obj_id = 10 + k;
+      {
+        ofdg_blueprint nb = blank_bp();
+        nb.obj_id = 10 + k;
+        put_bp(o, 0, nb);
+      }
       gen_object(g, o, 0, a.n_fields, field_draws);
       nbp = o.nbp; nseg = o.nseg;
     }

@@ -1,5 +1,7 @@
 """Device-side (Philox) parameter stream + device flattening: production mode.
 Statistically equivalent to the host stream, bitwise reproducible from (seed, sample index)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -151,3 +153,19 @@ def test_device_stream_reports_truncated_scenes(ofdg, textures8, monkeypatch):
     g.generate_philox(1, 0, 4, i0, i1, fl)  # the ordinary stream: fine
     assert float(i0.std()) > 5
     g.close()
+
+
+@pytest.mark.gpu
+def test_device_stream_is_pinned(ofdg):
+    """The blueprints of fixed (mode, seed, first sample) cases hash to the committed digests (tests/golden/philox_digest.json,
+    made by tests/golden/make_philox_digest.py): rewriting the generating kernels (lanes over a polygon's spokes, staging in
+    shared memory) must not move the stream."""
+    import importlib.util
+    import json
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_philox_digest", os.path.join(here, "golden", "make_philox_digest.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    want = json.load(open(os.path.join(here, "golden", "philox_digest.json")))
+    got = m.digests()
+    assert got == want
