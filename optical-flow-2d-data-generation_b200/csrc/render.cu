@@ -105,6 +105,15 @@ __device__ __forceinline__ float byte_to_float(uint32_t px, int c) {
   return __uint_as_float(__byte_perm(px, 0x4B000000u, 0x7440u + (unsigned)c)) - 8388608.0f;
 }
 
+// The same through the conversion unit (I2F.U8 with a byte selector: one instruction instead of two, on a pipe the shade
+// kernel otherwise leaves idle -- it is latency-bound since round 2, not issue-bound)
+__device__ __forceinline__ float byte_to_float_cvt(uint32_t px, int c) { return (float)((px >> (8 * c)) & 255u); }
+#ifndef OFDG_SHADE_VEC_FG
+#define OFDG_SHADE_VEC_FG 1  // the lane's four frame-0 texels of an object as one 128-bit load where the view is 16-byte aligned (0.1334 -> 0.1329 ms)
+#endif
+#ifndef OFDG_SHADE_I2F
+#define OFDG_SHADE_I2F 2  // 0: permute + add for both frames, 1: frame 0 through the conversion unit, 2: both frames (0.1334 / 0.1332 / 0.1328 ms)
+#endif
 __device__ __forceinline__ float byte_to_biased(uint32_t px, int c) {  // 2^23 + byte c (exact)
   return __uint_as_float(__byte_perm(px, 0x4B000000u, 0x7440u + (unsigned)c));
 }
@@ -1235,6 +1244,9 @@ __global__ void __launch_bounds__(RASTER_THREADS, OFDG_RASTER_MIN_BLOCKS) raster
   }
 }
 
+// (Blocks of 4 or 2 rows of a tile instead of 8 -- a block's slot is only free again when its slowest warp is done -- were
+// measured: 2 % faster than the same code at 8 rows, but the extra index arithmetic costs the register allocation more than
+// that at the 48-register cap: 0.132 -> 0.134 ms. One block per tile it stays.)
 template <bool kDeform, bool kExtra>
 __global__ void __launch_bounds__(RENDER_THREADS, kDeform ? OFDG_SHADE_DEFORM_MIN_BLOCKS : OFDG_SHADE_MIN_BLOCKS) shade_kernel(RenderArgs a) {
   if (a.pair_ctl[1]) return;
@@ -1392,10 +1404,23 @@ __global__ void __launch_bounds__(RENDER_THREADS, kDeform ? OFDG_SHADE_DEFORM_MI
     const uchar4* tex = a.pool + ti.fg_base;  // the W x H foreground view (centre crop, DG.cpp:99-102 with defaults, or the resized copy)
     if (m0w) {
       const uchar4* trow = tex + (size_t)y * ti.fg_pitch + x0;  // identity warp == copy
+#if OFDG_SHADE_VEC_FG
+      if (((ti.fg_base | (unsigned long long)ti.fg_pitch) & 3ull) == 0ull) {  // the lane's four texels are one aligned 128-bit load
+        const uint4 t4 = *reinterpret_cast<const uint4*>(trow);
+        const uint32_t tt[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const unsigned m0 = (m0w >> (8 * i)) & 255u;
-        if (m0) col0[i] = blend_rgbx(col0[i], ld_px(trow + i) & 0xFFFFFFu, m0);
+        for (int i = 0; i < 4; ++i) {
+          const unsigned m0 = (m0w >> (8 * i)) & 255u;
+          if (m0) col0[i] = blend_rgbx(col0[i], tt[i] & 0xFFFFFFu, m0);
+        }
+      } else
+#endif
+      {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const unsigned m0 = (m0w >> (8 * i)) & 255u;
+          if (m0) col0[i] = blend_rgbx(col0[i], ld_px(trow + i) & 0xFFFFFFu, m0);
+        }
       }
     }
     if (!kDeform || ob.field < 0) {
@@ -1498,8 +1523,16 @@ __global__ void __launch_bounds__(RENDER_THREADS, kDeform ? OFDG_SHADE_DEFORM_MI
     } else {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
+#if OFDG_SHADE_I2F >= 1
+        const float4 v0 = make_float4(byte_to_float_cvt(col0[0], c), byte_to_float_cvt(col0[1], c), byte_to_float_cvt(col0[2], c), byte_to_float_cvt(col0[3], c));
+#else
         const float4 v0 = make_float4(byte_to_float(col0[0], c), byte_to_float(col0[1], c), byte_to_float(col0[2], c), byte_to_float(col0[3], c));
+#endif
+#if OFDG_SHADE_I2F >= 2
+        const float4 v1 = make_float4(byte_to_float_cvt(col1[0], c), byte_to_float_cvt(col1[1], c), byte_to_float_cvt(col1[2], c), byte_to_float_cvt(col1[3], c));
+#else
         const float4 v1 = make_float4(byte_to_float(col1[0], c), byte_to_float(col1[1], c), byte_to_float(col1[2], c), byte_to_float(col1[3], c));
+#endif
         __stcs(reinterpret_cast<float4*>(o0 + c * P), v0);
         __stcs(reinterpret_cast<float4*>(o1 + c * P), v1);
       }
