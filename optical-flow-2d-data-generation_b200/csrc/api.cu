@@ -147,7 +147,7 @@ struct ofdg_generator {
   size_t last_upload_bytes = 0, last_download_bytes = 0;
   int scratch_batch = 0;
   // device-side (Philox) parameter stream
-  // (two sets: while batch k renders, batch k+1 is drawn and flattened on a side stream)
+  // (three sets: while batch k renders, batches k+1 and k+2 are drawn and flattened on a side stream)
   DevBuf ph_slots;
   struct PhiloxSet {
     DevBuf bp, seg_type, seg_x, seg_y, obj_nbp, obj_nseg, ntop;
@@ -156,9 +156,14 @@ struct ofdg_generator {
     DeviceScene scene;
     cudaEvent_t ready = nullptr, consumed = nullptr;
     bool used = false;
-  } ph[2];
+  };
+  static constexpr int kPhSets = 3;
+  PhiloxSet ph[kPhSets];
   cudaStream_t ph_stream = nullptr;
-  struct { bool valid = false; uint64_t seed = 0, first = 0; int batch = 0, augment = 0, set = 0; } ph_next;
+  struct PhNext { uint64_t seed = 0, first = 0; int batch = 0, augment = 0, set = 0; };
+  std::vector<PhNext> ph_queue;  // batches drawn ahead on ph_stream, oldest first (at most ph_depth)
+  bool ph_dirty = false;         // drawn-ahead batches were discarded and may still be running on ph_stream
+  int ph_depth = 2;              // OFDG_PHILOX_DEPTH
   int ph_batch = 0;
   DevBuf rtab_pos_x, rtab_alpha_x, rtab_pos_y, rtab_alpha_y;  // CImg linear-resize tables for every source length
   DevBuf comp_lut;  // [2][256][256] composite-mask rules (additive, subtractive), filled once by composite_lut_kernel
@@ -773,7 +778,8 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
       CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
       CK(cudaStreamCreateWithPriority(&g->ph_stream, cudaStreamNonBlocking, (pp && std::string(pp) == "0") ? 0 : hi));
     }
-    for (int i = 0; i < 2; ++i) {
+    if (const char* t = std::getenv("OFDG_PHILOX_DEPTH")) g->ph_depth = std::max(1, std::min(std::atoi(t), ofdg_generator::kPhSets - 1));
+    for (int i = 0; i < ofdg_generator::kPhSets; ++i) {
       CK(cudaEventCreateWithFlags(&g->ph[i].ready, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&g->ph[i].consumed, cudaEventDisableTiming));
     }
@@ -831,7 +837,8 @@ int ofdg_create(const ofdg_config* cfg, ofdg_generator** out) {
       // which is also how per-kernel times are measured (the spans of ofdg_kernel_times then do not overlap)
       const char* pl = std::getenv("OFDG_PIPELINE");
       g->pipeline = g->raster_overlap && !(pl && std::string(pl) == "0");
-      if (const char* pp = std::getenv("OFDG_PHILOX_PIPELINE")) g->philox_pipeline = std::string(pp) == "1";
+      g->philox_pipeline = g->pipeline;  // (OFDG_PHILOX_PIPELINE=0: the device-side stream's batches in line)
+      if (const char* pp = std::getenv("OFDG_PHILOX_PIPELINE")) g->philox_pipeline = g->pipeline && std::string(pp) != "0";
       if (g->pipeline) {
         const char* pr = std::getenv("OFDG_PREP_PRIORITY");  // "hi": the preparation stream shares the raster's priority
         CK(cudaStreamCreateWithPriority(&g->prep_stream, cudaStreamNonBlocking, (pr && std::string(pr) == "hi") ? hi : 0));
@@ -875,7 +882,7 @@ void ofdg_destroy(ofdg_generator* g) {
   if (g->field_stream) cudaStreamDestroy(g->field_stream);
   if (g->stream) cudaStreamSynchronize(g->stream);
   if (g->ph_stream) { cudaStreamSynchronize(g->ph_stream); cudaStreamDestroy(g->ph_stream); }
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < ofdg_generator::kPhSets; ++i) {
     ofdg_generator::PhiloxSet& q = g->ph[i];
     q.scene.release();
     DevBuf* qb[] = {&q.bp, &q.seg_type, &q.seg_x, &q.seg_y, &q.obj_nbp, &q.obj_nseg, &q.ntop, &q.n_deform};
@@ -926,7 +933,7 @@ namespace {
 // Nothing may still be reading the pool (or the look-ahead batch of the device stream) when it changes.
 void pool_quiesce(ofdg_generator* g) {
   CK(cudaDeviceSynchronize());
-  g->ph_next.valid = false;
+  { g->ph_queue.clear(); g->ph_dirty = true; }
 }
 
 // Room for `extra_px` more pixels; keeps what is there.
@@ -1106,7 +1113,7 @@ int ofdg_set_fields(ofdg_generator* g, const float* fields, int32_t n) {
     }
     g->field_reach_dev.reserve(n * sizeof(int));  // the device-side stream widens the boxes itself
     CK(cudaMemcpy(g->field_reach_dev.p, g->field_reach.data(), n * sizeof(int), cudaMemcpyHostToDevice));
-    g->ph_next.valid = false;
+    { g->ph_queue.clear(); g->ph_dirty = true; }
     // CImg linear-resize tables (W+1 -> 2W, H+1 -> 2H) used when the background carries a field
     auto table = [](int len, int nout, std::vector<int>& pos, std::vector<double>& alpha) {
       pos.resize(nout); alpha.resize(nout);
@@ -1173,7 +1180,7 @@ int ofdg_reserve_fields(ofdg_generator* g, int32_t total) {
     g->fields = nf; g->field_reach_dev = nr;
     g->field_reach.resize(total, 0);
     g->n_fields = total;
-    g->ph_next.valid = false;
+    { g->ph_queue.clear(); g->ph_dirty = true; }
   });
 }
 
@@ -1566,9 +1573,10 @@ void philox_check(ofdg_generator* g, int batch) {
   if (batch <= 0 || batch > g->cfg.max_batch) throw ArgError("bad batch size");
   if (batch > g->ph_batch) {
     CK(cudaDeviceSynchronize());
-    g->ph_next.valid = false;
+    g->ph_queue.clear();
+    g->ph_dirty = false;  // (the device was just synchronised)
     const size_t n = batch;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ofdg_generator::kPhSets; ++i) {
       ofdg_generator::PhiloxSet& q = g->ph[i];
       q.bp.reserve(n * kPhiloxMaxBp * sizeof(ofdg_blueprint));
       q.seg_type.reserve(n * kPhiloxMaxSeg * sizeof(int32_t)); q.seg_x.reserve(n * kPhiloxMaxSeg * sizeof(float));
@@ -1598,23 +1606,26 @@ int ofdg_generate_philox(ofdg_generator* g, uint64_t seed, uint64_t first_sample
     cudaStream_t s = stream ? (cudaStream_t)stream : g->stream;
     int set;
     bool looked_ahead = false;
-    if (g->ph_next.valid && g->ph_next.seed == seed && g->ph_next.first == first_sample && g->ph_next.batch == batch &&
-        g->ph_next.augment == augment) {
-      set = g->ph_next.set;  // drawn and flattened on the side stream while the previous batch rendered
+    std::vector<ofdg_generator::PhNext>& q = g->ph_queue;
+    if (!q.empty() && q.front().seed == seed && q.front().first == first_sample && q.front().batch == batch && q.front().augment == augment) {
+      set = q.front().set;  // drawn and flattened on the side stream while earlier batches rendered
+      q.erase(q.begin());
       CK(cudaStreamWaitEvent(s, g->ph[set].ready, 0));
       philox_collect(g, set, g->ph_stream);
       looked_ahead = true;
     } else {
-      set = g->ph_next.valid ? (g->ph_next.set ^ 1) : 0;
-      if (g->ph_next.valid) CK(cudaStreamSynchronize(g->ph_stream));  // a speculative batch nobody asked for is still being written
+      if (!q.empty() || g->ph_dirty) CK(cudaStreamSynchronize(g->ph_stream));  // batches nobody asked for may still be written
+      q.clear();
+      g->ph_dirty = false;
+      set = 0;
       if (g->ph[set].used) CK(cudaStreamWaitEvent(s, g->ph[set].consumed, 0));
       philox_run(g, set, seed, first_sample, batch, augment, g->philox_fg_override, s);
       philox_collect(g, set, s);
     }
     ensure_scratch(g, batch);
-    // The cross-batch pipeline is off for the device-side stream unless OFDG_PHILOX_PIPELINE=1: its look-ahead parameter kernels
-    // already run beside the previous batch's render, and a third and fourth concurrent kernel cost more than they gain
-    // (measured at batch 64: 118.6k samples/s in line, 111.1k pipelined).
+    // The cross-batch pipeline serves the device-side stream too (OFDG_PHILOX_PIPELINE=0: in line). Measured at batch 64 with the
+    // parameter kernel of round 2 (84 us, all lanes working): in line 138.9k samples/s, pipelined 140.2k, pipelined with batches
+    // drawn two ahead 143.4k. (With round 1's 169 us kernel the pipelined form was the slower one: 111.1k against 118.6k.)
     const int pset = (g->philox_pipeline && looked_ahead && g->philox_raster_overlap) ? pipeline_set(g, g->ph[set].scene) : -1;
     if (pset >= 0)  // the scene was written on the look-ahead stream: the front end only waits for that, not for the previous batch on s
       run_kernels_pipelined(g, with_extra_tops(g, make_args(g, g->ph[set].scene, d_img0, d_img1, d_flow, pset)), s, pset, g->ph[set].ready);
@@ -1622,13 +1633,25 @@ int ofdg_generate_philox(ofdg_generator* g, uint64_t seed, uint64_t first_sample
       run_kernels(g, with_extra_tops(g, make_args(g, g->ph[set].scene, d_img0, d_img1, d_flow)), s, true, g->philox_raster_overlap);
     CK(cudaEventRecord(g->ph[set].consumed, s));
     g->ph[set].used = true;
-    // look ahead: the next batch of the same stream, on the side stream, into the other set
-    const int nset = set ^ 1;
-    if (g->ph[nset].used) CK(cudaStreamWaitEvent(g->ph_stream, g->ph[nset].consumed, 0));
-    philox_run(g, nset, seed, first_sample + (uint64_t)batch, batch, augment, g->philox_fg_override, g->ph_stream);
-    CK(cudaEventRecord(g->ph[nset].ready, g->ph_stream));
-    g->ph_next.valid = true; g->ph_next.seed = seed; g->ph_next.first = first_sample + (uint64_t)batch;
-    g->ph_next.batch = batch; g->ph_next.augment = augment; g->ph_next.set = nset;
+    // look ahead: the next batches of the same stream, on the side stream, into the sets that are neither being rendered nor
+    // waiting in the queue. Two batches ahead (OFDG_PHILOX_DEPTH), a drawn-ahead batch has a whole render step of slack.
+    uint64_t next_first = q.empty() ? first_sample + (uint64_t)batch : q.back().first + (uint64_t)batch;
+    while ((int)q.size() < g->ph_depth) {
+      int nset = -1;
+      for (int i = 0; i < ofdg_generator::kPhSets && nset < 0; ++i) {
+        bool busy = (i == set);
+        for (const ofdg_generator::PhNext& e : q) busy = busy || e.set == i;
+        if (!busy) nset = i;
+      }
+      if (nset < 0) break;
+      if (g->ph[nset].used) CK(cudaStreamWaitEvent(g->ph_stream, g->ph[nset].consumed, 0));
+      philox_run(g, nset, seed, next_first, batch, augment, g->philox_fg_override, g->ph_stream);
+      CK(cudaEventRecord(g->ph[nset].ready, g->ph_stream));
+      ofdg_generator::PhNext e;
+      e.seed = seed; e.first = next_first; e.batch = batch; e.augment = augment; e.set = nset;
+      q.push_back(e);
+      next_first += (uint64_t)batch;
+    }
     if (!stream) { CK(cudaStreamSynchronize(s)); check_pair_overflow(g); }
   });
 }
@@ -1640,7 +1663,7 @@ int ofdg_philox_tasks(ofdg_generator* g, uint64_t seed, uint64_t first_sample, i
     using namespace ofdg;
     philox_check(g, batch);
     CK(cudaDeviceSynchronize());
-    g->ph_next.valid = false;
+    { g->ph_queue.clear(); g->ph_dirty = true; }
     philox_run(g, 0, seed, first_sample, batch, augment, 0, g->stream);
     CK(cudaStreamSynchronize(g->stream));
     std::vector<ofdg_blueprint> bp((size_t)batch * kPhiloxMaxBp);
