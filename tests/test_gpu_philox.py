@@ -57,6 +57,43 @@ def test_sample_is_a_pure_function_of_seed_and_index(ofdg, textures8):
     g.close()
 
 
+def test_batches_drawn_ahead_are_used_or_discarded_correctly(ofdg, textures8):
+    """The generator draws the next two batches of a stream ahead (three scene sets). Consecutive calls consume them in order;
+    a call that asks for anything else (another position, another seed, another batch size) discards them. Either way the
+    blobs equal those of a generator that was asked for that batch first thing."""
+    import torch
+
+    def fresh(seed, first, n):
+        g = _gen(ofdg, 7)
+        g.upload_textures(textures8)
+        out = _blobs(n)
+        g.generate_philox(seed, first, n, *out)
+        torch.cuda.synchronize()
+        g.close()
+        return out
+
+    g = _gen(ofdg, 7)
+    g.upload_textures(textures8)
+    got = {}
+    for call, (seed, first, n) in enumerate([(5, 0, 4), (5, 4, 4), (5, 8, 4), (5, 12, 4),     # in order: the drawn-ahead batches are used
+                                             (5, 4, 4),                                         # back: discarded
+                                             (5, 8, 4),                                         # in order again
+                                             (6, 8, 4), (6, 12, 4),                             # another seed
+                                             (6, 16, 2), (6, 18, 2), (6, 20, 2)]):              # another batch size
+        out = _blobs(n)
+        g.generate_philox(seed, first, n, *out)
+        torch.cuda.synchronize()
+        got[call] = (seed, first, n, [t.clone() for t in out])
+    g.close()
+    want = {}
+    for call, (seed, first, n, out) in got.items():
+        key = (seed, first, n)
+        if key not in want:
+            want[key] = fresh(*key)
+        for x, y in zip(out, want[key]):
+            assert torch.equal(x, y), (call, key)
+
+
 def test_statistics_match_the_host_stream(ofdg, textures8):
     g = _gen(ofdg, 7)
     g.upload_textures(textures8)
