@@ -1858,11 +1858,14 @@ __device__ __forceinline__ ResizeTaps make_taps(int len, int n, int t, const int
 // quotient of two such integers is either an integer (exact in float) or at least 1/len away from the next one, far more
 // than the float rounding error at values <= 255 -- so trunc(float(acc) / float(len)) == acc / len in integers.
 // `magic` = floor(2^32 / len) + 1 turns that division into one multiply-high (exact for acc * len < 2^32).
+// kMode: which of the three forms the pass takes is a property of the sample (crop length against prepared length), so the
+// passes decide it once per block (0 copy, 1 moving average, 2 linear) instead of once per element (-1).
+template <int kMode = -1>
 __device__ __forceinline__ uint32_t apply_taps(const uint32_t* src, int stride, int s0, int len, unsigned magic, const ResizeTaps& r) {
   const uint32_t* p0 = src + (r.first - s0) * stride;
-  if (r.count == 0) return p0[0];
+  if (kMode == 0 || (kMode < 0 && r.count == 0)) return p0[0];
   uint32_t t[3];  // the three channels' results, each below 256: packed by two byte permutes (t[2]'s byte 1 supplies the zero)
-  if (r.count > 0) {
+  if (kMode == 1 || (kMode < 0 && r.count > 0)) {
     unsigned acc[3] = {0u, 0u, 0u};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -2117,15 +2120,26 @@ __device__ __forceinline__ void bg_prep_tile(const RenderArgs& a, PrepSmem& sm, 
   // B: resize along x (one column per lane: its taps are computed once)
   if (lane_x < tw) {
     const ResizeTaps tx = make_taps(p.crop_w, W2, X0 + lane_x, pos_x, alpha_x);
-    for (int ly = lane_y; ly < ch; ly += PREP_THREADS / 32) sB[ly][lane_x] = apply_taps(&sA[ly][0], 1, cx0, p.crop_w, magic_x, tx);
+    if (p.crop_w == W2) {
+      for (int ly = lane_y; ly < ch; ly += PREP_THREADS / 32) sB[ly][lane_x] = apply_taps<0>(&sA[ly][0], 1, cx0, p.crop_w, magic_x, tx);
+    } else if (p.crop_w > W2) {
+      for (int ly = lane_y; ly < ch; ly += PREP_THREADS / 32) sB[ly][lane_x] = apply_taps<1>(&sA[ly][0], 1, cx0, p.crop_w, magic_x, tx);
+    } else {
+      for (int ly = lane_y; ly < ch; ly += PREP_THREADS / 32) sB[ly][lane_x] = apply_taps<2>(&sA[ly][0], 1, cx0, p.crop_w, magic_x, tx);
+    }
   }
   __syncthreads();
   // P: resize along y
-  if (lane_x < tw)
-    for (int ly = lane_y; ly < th; ly += PREP_THREADS / 32) {
-      const uint32_t v = apply_taps(&sB[0][lane_x], PT, cy0, p.crop_h, magic_y, sTy[ly]);
-      *reinterpret_cast<uint32_t*>(out + (size_t)(Y0 + ly) * W2 + X0 + lane_x) = v;
+  if (lane_x < tw) {
+    uint32_t* orow = reinterpret_cast<uint32_t*>(out + (size_t)Y0 * W2 + X0 + lane_x);
+    if (p.crop_h == H2) {
+      for (int ly = lane_y; ly < th; ly += PREP_THREADS / 32) orow[(size_t)ly * W2] = apply_taps<0>(&sB[0][lane_x], PT, cy0, p.crop_h, magic_y, sTy[ly]);
+    } else if (p.crop_h > H2) {
+      for (int ly = lane_y; ly < th; ly += PREP_THREADS / 32) orow[(size_t)ly * W2] = apply_taps<1>(&sB[0][lane_x], PT, cy0, p.crop_h, magic_y, sTy[ly]);
+    } else {
+      for (int ly = lane_y; ly < th; ly += PREP_THREADS / 32) orow[(size_t)ly * W2] = apply_taps<2>(&sB[0][lane_x], PT, cy0, p.crop_h, magic_y, sTy[ly]);
     }
+  }
 }
 
 __global__ void __launch_bounds__(PREP_THREADS, OFDG_PREP_MIN_BLOCKS) bg_prep_kernel(RenderArgs a) {
