@@ -315,6 +315,9 @@ __device__ void gen_object(Gen& g, SampleOut& o, int idx, int n_fields, int& fie
 // leave in one coalesced copy by the whole warp -- as global read-modify-write chains they were most of the kernel's 169 us,
 // during which its blocks (17 warps at 56 registers for one working lane each) held half an SM's registers away from the
 // render kernels of the batch before.
+#ifndef OFDG_PARAMS_MIN_BLOCKS
+#define OFDG_PARAMS_MIN_BLOCKS 5  // 3 / 4 / 5 blocks per SM (56 / 40 / 32 registers, spilling): production mode 142.5k / 143.5k / 146.5k samples/s -- what the kernel costs the render beside it is the registers its blocks hold
+#endif
 constexpr int kParamWarps = 12;                                          // roles per block
 constexpr int kParamBlocks = (kPhiloxMaxObj + 1 + kParamWarps - 1) / kParamWarps;  // blocks per sample
 constexpr int kSegPerObj = kPhiloxMaxShapes * 20;
@@ -324,7 +327,7 @@ struct ParamStage {
   float seg_x[kSegPerObj];
   float seg_y[kSegPerObj];
 };
-__global__ void __launch_bounds__(32 * kParamWarps, 3) philox_params_kernel(PhiloxArgs a) {
+__global__ void __launch_bounds__(32 * kParamWarps, OFDG_PARAMS_MIN_BLOCKS) philox_params_kernel(PhiloxArgs a) {
   __shared__ ParamStage s_stage[kParamWarps];
   __shared__ PhiloxSlot s_slots[kPhiloxSlots];
   for (int i = threadIdx.x; i < (int)(kPhiloxSlots * sizeof(PhiloxSlot) / 4); i += blockDim.x)
