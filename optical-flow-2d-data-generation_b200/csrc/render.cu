@@ -904,7 +904,8 @@ constexpr int RSUB = TH / RTH;              // slices per pair
 // warps (each sweeping two rows) and one outline per chunk (two layers, 19 KB of shared memory) put eight units on an SM at 64
 // registers instead of five at 48. Measured (same box, kernel in line / whole pipelined step): 8 warps x 4 layers x 5 blocks
 // 0.153 / 0.4255 ms; 8 x 2 x 5: 0.171 / 0.435; 4 x 2 x 10 (48 registers, spills): 0.173 / 0.432; 4 x 2 x 8: 0.151 / 0.407;
-// 4 x 2 x 6: 0.166 / 0.424; 4 x 4 x 5: 0.166 / 0.430; 2 x 2 x 11: 0.242 / 0.487. (Starting the packed item loops at a warp that
+// 4 x 2 x 6: 0.166 / 0.424; 4 x 4 x 5: 0.166 / 0.430; 2 x 2 x 11: 0.242 / 0.487. With the composite table (below): 4 x 2 x 7 / 8 / 9 /
+// 10 blocks (72 / 64 / 56 / 48 registers) 0.138 / 0.130 / 0.138 / 0.138 ms. (Starting the packed item loops at a warp that
 // changes from unit to unit, so that they do not all issue from the same scheduler: no gain, 0.153 vs 0.151.)
 #ifndef OFDG_RASTER_WARPS
 #define OFDG_RASTER_WARPS 4
