@@ -6,5 +6,6 @@ for v in "$@"; do
   env $e python bench.py --no-cpu --e2e-steps 3 --steps 600 2>/dev/null | python -c "
 import json, sys
 d = json.loads(sys.stdin.read().strip().splitlines()[-1]); r = d['roofline']
-print('[$v]', 'samples/s %.0f' % d['value'], 'prod %.0f' % d['production_mode']['value'], 'prep %.4f raster %.4f shade %.4f frac %.3f' % (r['bg_prep_ms'], r['raster_ms'] or 0, r['kernel_ms'], r['frac']))"
+k = r.get('kernels') or {}
+print('[$v]', 'samples/s %.0f' % d['value'], 'prod %.0f' % d['production_mode']['value'], ' '.join('%s %.4f' % (n.replace('_kernel', ''), x['ms']) for n, x in k.items()), 'frac %.3f' % r['frac'])"
 done
