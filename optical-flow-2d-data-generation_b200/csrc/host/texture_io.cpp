@@ -108,7 +108,7 @@ TextureImage decode_png(const std::string& path, const std::vector<unsigned char
     i += 12 + (size_t)len;
   }
   if (w <= 0 || h <= 0 || w > 32768 || h > 32768) fail(path, "bad size");
-  if (depth != 8 || interlace != 0) fail(path, "only non-interlaced 8-bit PNG is decoded");
+  if (depth != 8 || interlace > 1) fail(path, "only 8-bit PNG is decoded (16-bit and sub-byte depths are not)");
   int ch;
   switch (ctype) {
     case 0: ch = 1; break;
@@ -118,32 +118,62 @@ TextureImage decode_png(const std::string& path, const std::vector<unsigned char
     case 6: ch = 4; break;
     default: fail(path, "unsupported PNG colour type");
   }
-  const size_t stride = (size_t)w * ch;
-  std::vector<unsigned char> raw((stride + 1) * h);
-  uLongf out_len = (uLongf)raw.size();
-  if (uncompress(raw.data(), &out_len, idat.data(), (uLong)idat.size()) != Z_OK || out_len != raw.size()) fail(path, "inflate failed");
-  std::vector<unsigned char> px(stride * h);
-  for (int y = 0; y < h; ++y) {  // undo the scanline filters
-    const unsigned char* in = raw.data() + (size_t)y * (stride + 1);
-    unsigned char* cur = px.data() + (size_t)y * stride;
-    const unsigned char* up = y ? cur - stride : nullptr;
-    const int ft = in[0];
-    for (size_t x = 0; x < stride; ++x) {
-      const int a = x >= (size_t)ch ? cur[x - ch] : 0, b = up ? up[x] : 0, c = (up && x >= (size_t)ch) ? up[x - ch] : 0;
-      int pred;
-      switch (ft) {
-        case 0: pred = 0; break;
-        case 1: pred = a; break;
-        case 2: pred = b; break;
-        case 3: pred = (a + b) >> 1; break;
-        case 4: {
-          const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
-          pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
-          break;
+  // One image (the whole picture, or one Adam7 pass of it) = ph filtered scanlines of pw pixels: undo the scanline filters.
+  auto unfilter = [&](const unsigned char* raw, int pw, int ph, unsigned char* dst) {
+    const size_t stride = (size_t)pw * ch;
+    for (int y = 0; y < ph; ++y) {
+      const unsigned char* in = raw + (size_t)y * (stride + 1);
+      unsigned char* cur = dst + (size_t)y * stride;
+      const unsigned char* up = y ? cur - stride : nullptr;
+      const int ft = in[0];
+      for (size_t x = 0; x < stride; ++x) {
+        const int a = x >= (size_t)ch ? cur[x - ch] : 0, b = up ? up[x] : 0, c = (up && x >= (size_t)ch) ? up[x - ch] : 0;
+        int pred;
+        switch (ft) {
+          case 0: pred = 0; break;
+          case 1: pred = a; break;
+          case 2: pred = b; break;
+          case 3: pred = (a + b) >> 1; break;
+          case 4: {
+            const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+            pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+            break;
+          }
+          default: fail(path, "bad PNG filter");
         }
-        default: fail(path, "bad PNG filter");
+        cur[x] = (unsigned char)(in[1 + x] + pred);
       }
-      cur[x] = (unsigned char)(in[1 + x] + pred);
+    }
+  };
+  const size_t stride = (size_t)w * ch;
+  std::vector<unsigned char> px(stride * h);
+  if (!interlace) {
+    std::vector<unsigned char> raw((stride + 1) * h);
+    uLongf out_len = (uLongf)raw.size();
+    if (uncompress(raw.data(), &out_len, idat.data(), (uLong)idat.size()) != Z_OK || out_len != raw.size()) fail(path, "inflate failed");
+    unfilter(raw.data(), w, h, px.data());
+  } else {  // Adam7: seven reduced images one after the other in the stream, each filtered on its own
+    static const int xs[7] = {0, 4, 0, 2, 0, 1, 0}, ys[7] = {0, 0, 4, 0, 2, 0, 1}, dx[7] = {8, 8, 4, 4, 2, 2, 1}, dy[7] = {8, 8, 8, 4, 4, 2, 2};
+    int pw[7], ph[7];
+    size_t total = 0;
+    for (int k = 0; k < 7; ++k) {
+      pw[k] = (w - xs[k] + dx[k] - 1) / dx[k];
+      ph[k] = (h - ys[k] + dy[k] - 1) / dy[k];
+      if (pw[k] > 0 && ph[k] > 0) total += ((size_t)pw[k] * ch + 1) * ph[k];
+    }
+    std::vector<unsigned char> raw(total);
+    uLongf out_len = (uLongf)raw.size();
+    if (uncompress(raw.data(), &out_len, idat.data(), (uLong)idat.size()) != Z_OK || out_len != raw.size()) fail(path, "inflate failed");
+    std::vector<unsigned char> pass;
+    size_t off = 0;
+    for (int k = 0; k < 7; ++k) {
+      if (pw[k] <= 0 || ph[k] <= 0) continue;
+      pass.assign((size_t)pw[k] * ch * ph[k], 0);
+      unfilter(raw.data() + off, pw[k], ph[k], pass.data());
+      off += ((size_t)pw[k] * ch + 1) * ph[k];
+      for (int j = 0; j < ph[k]; ++j)
+        for (int i2 = 0; i2 < pw[k]; ++i2)
+          std::memcpy(&px[((size_t)(ys[k] + j * dy[k]) * w + xs[k] + (size_t)i2 * dx[k]) * ch], &pass[((size_t)j * pw[k] + i2) * ch], (size_t)ch);
     }
   }
   if (ctype == 3) {  // palette -> RGB
@@ -203,7 +233,7 @@ TextureImage load_texture_file(const std::string& path) {
   if (d.size() >= 2 && d[0] == 'B' && d[1] == 'M') return decode_bmp(path, d);
   if (d.size() >= 4 && d[0] == 0x89 && d[1] == 'P' && d[2] == 'N' && d[3] == 'G') return decode_png(path, d);
   if (d.size() >= 3 && d[0] == 0xFF && d[1] == 0xD8 && d[2] == 0xFF) return decode_jpeg(path, d);
-  fail(path, "unsupported image format (decoders: binary PPM, uncompressed BMP, 8-bit PNG, JPEG)");
+  fail(path, "unsupported image format (decoders: binary PPM, uncompressed BMP, 8-bit PNG incl. Adam7, JPEG)");
 }
 
 std::vector<std::string> read_texture_list(const std::string& listfile) {

@@ -130,8 +130,8 @@ def test_layer_extra_tops(ofdg, oracle):
         bad.LayerSetUp()
 
 
-def _png_bytes(rgb, filter_types=(0, 1, 2, 3, 4), alpha=False, palette=False):
-    """Minimal PNG writer (zlib + struct) exercising every scanline filter."""
+def _png_bytes(rgb, filter_types=(0, 1, 2, 3, 4), alpha=False, palette=False, interlace=False):
+    """Minimal PNG writer (zlib + struct) exercising every scanline filter; interlace: Adam7."""
     import struct, zlib
     h, w, _ = rgb.shape
     if palette:
@@ -145,8 +145,26 @@ def _png_bytes(rgb, filter_types=(0, 1, 2, 3, 4), alpha=False, palette=False):
     else:
         px, ctype = rgb, 2
     bpp = px.shape[2]
-    rows = px.reshape(h, w * bpp).astype(np.int32)
     raw = bytearray()
+    passes = [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)] if interlace else [(0, 0, 1, 1)]
+    for xs, ys, dx, dy in passes:
+        sub = px[ys::dy, xs::dx]
+        if sub.shape[0] == 0 or sub.shape[1] == 0:
+            continue
+        _png_filter_rows(sub, bpp, filter_types, raw)
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    z = zlib.compress(bytes(raw), 6)
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ctype, 0, 0, 1 if interlace else 0))
+    if palette:
+        out += chunk(b"PLTE", colours.astype(np.uint8).tobytes())
+    out += chunk(b"IDAT", z[: len(z) // 2]) + chunk(b"IDAT", z[len(z) // 2:]) + chunk(b"IEND", b"")
+    return out
+
+
+def _png_filter_rows(px, bpp, filter_types, raw):
+    h, w = px.shape[0], px.shape[1]
+    rows = np.ascontiguousarray(px).reshape(h, w * bpp).astype(np.int32)
     prev = np.zeros(w * bpp, np.int32)
     for y in range(h):
         cur = rows[y]
@@ -165,14 +183,6 @@ def _png_bytes(rgb, filter_types=(0, 1, 2, 3, 4), alpha=False, palette=False):
         raw.append(ft)
         raw += ((cur - pred) & 255).astype(np.uint8).tobytes()
         prev = cur
-    def chunk(t, d):
-        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
-    z = zlib.compress(bytes(raw), 6)
-    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ctype, 0, 0, 0))
-    if palette:
-        out += chunk(b"PLTE", colours.astype(np.uint8).tobytes())
-    out += chunk(b"IDAT", z[: len(z) // 2]) + chunk(b"IDAT", z[len(z) // 2:]) + chunk(b"IEND", b"")
-    return out
 
 
 def test_texture_file_decoders(ofdg, tmp_path):
@@ -191,6 +201,10 @@ def test_texture_file_decoders(ofdg, tmp_path):
     (tmp_path / "b.png").write_bytes(_png_bytes(rgb, alpha=True))
     few = (rgb // 64) * 64
     (tmp_path / "c.png").write_bytes(_png_bytes(few, palette=True))
+    (tmp_path / "d.png").write_bytes(_png_bytes(rgb, interlace=True))               # Adam7 (53 x 37: ragged passes)
+    (tmp_path / "e.png").write_bytes(_png_bytes(rgb[:3, :2], interlace=True))       # passes without pixels
+    assert np.array_equal(ofdg.decode_texture_file(tmp_path / "d.png"), want)
+    assert np.array_equal(ofdg.decode_texture_file(tmp_path / "e.png"), np.ascontiguousarray(rgb[:3, :2, ::-1].transpose(2, 0, 1)))
     for name in ("a.ppm", "a.bmp", "a.png", "b.png"):
         assert np.array_equal(ofdg.decode_texture_file(tmp_path / name), want), name
     assert np.array_equal(ofdg.decode_texture_file(tmp_path / "c.png"), np.ascontiguousarray(few[:, :, ::-1].transpose(2, 0, 1)))
