@@ -108,7 +108,9 @@ TextureImage decode_png(const std::string& path, const std::vector<unsigned char
     i += 12 + (size_t)len;
   }
   if (w <= 0 || h <= 0 || w > 32768 || h > 32768) fail(path, "bad size");
-  if (depth != 8 || interlace > 1) fail(path, "only 8-bit PNG is decoded (16-bit and sub-byte depths are not)");
+  if (interlace > 1) fail(path, "bad PNG interlace method");
+  const bool sub_byte = (depth == 1 || depth == 2 || depth == 4) && (ctype == 0 || ctype == 3);
+  if (depth != 8 && !sub_byte) fail(path, "only PNG of 8 bits per sample (or 1 / 2 / 4-bit grey and palette images) is decoded, not 16-bit");
   int ch;
   switch (ctype) {
     case 0: ch = 1; break;
@@ -118,16 +120,23 @@ TextureImage decode_png(const std::string& path, const std::vector<unsigned char
     case 6: ch = 4; break;
     default: fail(path, "unsupported PNG colour type");
   }
-  // One image (the whole picture, or one Adam7 pass of it) = ph filtered scanlines of pw pixels: undo the scanline filters.
+  // One image (the whole picture, or one Adam7 pass of it) = ph filtered scanlines of pw pixels: undo the scanline filters
+  // (on bytes; the filters' "previous pixel" is one byte back for depths below 8), then unpack sub-byte samples the way
+  // libpng's expansion does (grey: scaled to 0..255; palette: the index).
+  auto row_bytes = [&](int pw) { return ((size_t)pw * ch * depth + 7) / 8; };
+  std::vector<unsigned char> packed;
   auto unfilter = [&](const unsigned char* raw, int pw, int ph, unsigned char* dst) {
-    const size_t stride = (size_t)pw * ch;
+    const size_t stride = row_bytes(pw);
+    const size_t fb = (size_t)std::max(1, ch * depth / 8);
+    unsigned char* base = dst;
+    if (sub_byte) { packed.assign(stride * ph, 0); base = packed.data(); }
     for (int y = 0; y < ph; ++y) {
       const unsigned char* in = raw + (size_t)y * (stride + 1);
-      unsigned char* cur = dst + (size_t)y * stride;
+      unsigned char* cur = base + (size_t)y * stride;
       const unsigned char* up = y ? cur - stride : nullptr;
       const int ft = in[0];
       for (size_t x = 0; x < stride; ++x) {
-        const int a = x >= (size_t)ch ? cur[x - ch] : 0, b = up ? up[x] : 0, c = (up && x >= (size_t)ch) ? up[x - ch] : 0;
+        const int a = x >= fb ? cur[x - fb] : 0, b = up ? up[x] : 0, c = (up && x >= fb) ? up[x - fb] : 0;
         int pred;
         switch (ft) {
           case 0: pred = 0; break;
@@ -144,11 +153,20 @@ TextureImage decode_png(const std::string& path, const std::vector<unsigned char
         cur[x] = (unsigned char)(in[1 + x] + pred);
       }
     }
+    if (sub_byte) {
+      const int scale = ctype == 0 ? 255 / ((1 << depth) - 1) : 1;
+      for (int y = 0; y < ph; ++y)
+        for (int x = 0; x < pw; ++x) {
+          const unsigned char byte = packed[(size_t)y * stride + ((size_t)x * depth) / 8];
+          const int shift = 8 - depth - (int)(((size_t)x * depth) % 8);
+          dst[(size_t)y * pw + x] = (unsigned char)(((byte >> shift) & ((1 << depth) - 1)) * scale);
+        }
+    }
   };
   const size_t stride = (size_t)w * ch;
   std::vector<unsigned char> px(stride * h);
   if (!interlace) {
-    std::vector<unsigned char> raw((stride + 1) * h);
+    std::vector<unsigned char> raw((row_bytes(w) + 1) * h);
     uLongf out_len = (uLongf)raw.size();
     if (uncompress(raw.data(), &out_len, idat.data(), (uLong)idat.size()) != Z_OK || out_len != raw.size()) fail(path, "inflate failed");
     unfilter(raw.data(), w, h, px.data());
@@ -159,7 +177,7 @@ TextureImage decode_png(const std::string& path, const std::vector<unsigned char
     for (int k = 0; k < 7; ++k) {
       pw[k] = (w - xs[k] + dx[k] - 1) / dx[k];
       ph[k] = (h - ys[k] + dy[k] - 1) / dy[k];
-      if (pw[k] > 0 && ph[k] > 0) total += ((size_t)pw[k] * ch + 1) * ph[k];
+      if (pw[k] > 0 && ph[k] > 0) total += (row_bytes(pw[k]) + 1) * ph[k];
     }
     std::vector<unsigned char> raw(total);
     uLongf out_len = (uLongf)raw.size();
@@ -170,7 +188,7 @@ TextureImage decode_png(const std::string& path, const std::vector<unsigned char
       if (pw[k] <= 0 || ph[k] <= 0) continue;
       pass.assign((size_t)pw[k] * ch * ph[k], 0);
       unfilter(raw.data() + off, pw[k], ph[k], pass.data());
-      off += ((size_t)pw[k] * ch + 1) * ph[k];
+      off += (row_bytes(pw[k]) + 1) * ph[k];
       for (int j = 0; j < ph[k]; ++j)
         for (int i2 = 0; i2 < pw[k]; ++i2)
           std::memcpy(&px[((size_t)(ys[k] + j * dy[k]) * w + xs[k] + (size_t)i2 * dx[k]) * ch], &pass[((size_t)j * pw[k] + i2) * ch], (size_t)ch);
@@ -233,7 +251,7 @@ TextureImage load_texture_file(const std::string& path) {
   if (d.size() >= 2 && d[0] == 'B' && d[1] == 'M') return decode_bmp(path, d);
   if (d.size() >= 4 && d[0] == 0x89 && d[1] == 'P' && d[2] == 'N' && d[3] == 'G') return decode_png(path, d);
   if (d.size() >= 3 && d[0] == 0xFF && d[1] == 0xD8 && d[2] == 0xFF) return decode_jpeg(path, d);
-  fail(path, "unsupported image format (decoders: binary PPM, uncompressed BMP, 8-bit PNG incl. Adam7, JPEG)");
+  fail(path, "unsupported image format (decoders: binary PPM, uncompressed BMP, PNG up to 8 bits per sample incl. Adam7, JPEG)");
 }
 
 std::vector<std::string> read_texture_list(const std::string& listfile) {

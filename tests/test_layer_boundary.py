@@ -162,6 +162,38 @@ def _png_bytes(rgb, filter_types=(0, 1, 2, 3, 4), alpha=False, palette=False, in
     return out
 
 
+def _png_packed(idx, depth, ctype, interlace, palette=None):
+    """Grey (ctype 0) or palette (ctype 3) PNG of `depth` bits per sample, samples packed MSB first, filter 0 / 1 / 2 by row."""
+    import struct, zlib
+    h, w = idx.shape
+    raw = bytearray()
+    passes = [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)] if interlace else [(0, 0, 1, 1)]
+    for xs, ys, dx, dy in passes:
+        sub = idx[ys::dy, xs::dx]
+        if sub.shape[0] == 0 or sub.shape[1] == 0:
+            continue
+        ph, pw = sub.shape
+        nbytes = (pw * depth + 7) // 8
+        bits = np.zeros((ph, nbytes * 8), np.uint8)
+        for b in range(depth):
+            bits[:, b:pw * depth:depth] = (sub >> (depth - 1 - b)) & 1
+        rows = np.packbits(bits, axis=1).astype(np.int32)
+        prev = np.zeros(nbytes, np.int32)
+        for y in range(ph):
+            cur = rows[y]
+            ft = y % 3
+            pred = 0 if ft == 0 else (np.concatenate([[0], cur[:-1]]) if ft == 1 else prev)
+            raw.append(ft)
+            raw += ((cur - pred) & 255).astype(np.uint8).tobytes()
+            prev = cur
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 1 if interlace else 0))
+    if palette is not None:
+        out += chunk(b"PLTE", palette.astype(np.uint8).tobytes())
+    return out + chunk(b"IDAT", zlib.compress(bytes(raw), 6)) + chunk(b"IEND", b"")
+
+
 def _png_filter_rows(px, bpp, filter_types, raw):
     h, w = px.shape[0], px.shape[1]
     rows = np.ascontiguousarray(px).reshape(h, w * bpp).astype(np.int32)
@@ -201,6 +233,15 @@ def test_texture_file_decoders(ofdg, tmp_path):
     (tmp_path / "b.png").write_bytes(_png_bytes(rgb, alpha=True))
     few = (rgb // 64) * 64
     (tmp_path / "c.png").write_bytes(_png_bytes(few, palette=True))
+    for depth in (1, 2, 4, 8):                                                       # grey / palette images below 8 bits per sample
+        for interlace in (False, True):
+            g = rng.integers(0, 1 << depth, (37, 53), dtype=np.uint8)
+            (tmp_path / "g.png").write_bytes(_png_packed(g, depth, 0, interlace))
+            grey = (g.astype(np.int32) * (255 // ((1 << depth) - 1))).astype(np.uint8)
+            assert np.array_equal(ofdg.decode_texture_file(tmp_path / "g.png"), np.stack([grey] * 3)), (depth, interlace)
+            pal = rng.integers(0, 256, (1 << depth, 3), dtype=np.uint8)
+            (tmp_path / "p.png").write_bytes(_png_packed(g, depth, 3, interlace, pal))
+            assert np.array_equal(ofdg.decode_texture_file(tmp_path / "p.png"), np.ascontiguousarray(pal[g][:, :, ::-1].transpose(2, 0, 1))), (depth, interlace)
     (tmp_path / "d.png").write_bytes(_png_bytes(rgb, interlace=True))               # Adam7 (53 x 37: ragged passes)
     (tmp_path / "e.png").write_bytes(_png_bytes(rgb[:3, :2], interlace=True))       # passes without pixels
     assert np.array_equal(ofdg.decode_texture_file(tmp_path / "d.png"), want)
