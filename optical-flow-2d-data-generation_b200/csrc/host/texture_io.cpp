@@ -110,7 +110,8 @@ TextureImage decode_png(const std::string& path, const std::vector<unsigned char
   if (w <= 0 || h <= 0 || w > 32768 || h > 32768) fail(path, "bad size");
   if (interlace > 1) fail(path, "bad PNG interlace method");
   const bool sub_byte = (depth == 1 || depth == 2 || depth == 4) && (ctype == 0 || ctype == 3);
-  if (depth != 8 && !sub_byte) fail(path, "only PNG of 8 bits per sample (or 1 / 2 / 4-bit grey and palette images) is decoded, not 16-bit");
+  const bool wide = depth == 16 && ctype != 3;
+  if (depth != 8 && !sub_byte && !wide) fail(path, "bad PNG bit depth for its colour type");
   int ch;
   switch (ctype) {
     case 0: ch = 1; break;
@@ -129,7 +130,7 @@ TextureImage decode_png(const std::string& path, const std::vector<unsigned char
     const size_t stride = row_bytes(pw);
     const size_t fb = (size_t)std::max(1, ch * depth / 8);
     unsigned char* base = dst;
-    if (sub_byte) { packed.assign(stride * ph, 0); base = packed.data(); }
+    if (sub_byte || wide) { packed.assign(stride * ph, 0); base = packed.data(); }
     for (int y = 0; y < ph; ++y) {
       const unsigned char* in = raw + (size_t)y * (stride + 1);
       unsigned char* cur = base + (size_t)y * stride;
@@ -152,6 +153,12 @@ TextureImage decode_png(const std::string& path, const std::vector<unsigned char
         }
         cur[x] = (unsigned char)(in[1 + x] + pred);
       }
+    }
+    if (wide) {
+      // 16-bit samples: the reference reads them into a CImg<unsigned char>, i.e. CImg's loader casts each 16-bit value to
+      // unsigned char -- its LOW byte (big-endian in the file: the second one). Reproduced as it is.
+      for (int y = 0; y < ph; ++y)
+        for (size_t x = 0; x < (size_t)pw * ch; ++x) dst[(size_t)y * pw * ch + x] = packed[(size_t)y * stride + 2 * x + 1];
     }
     if (sub_byte) {
       const int scale = ctype == 0 ? 255 / ((1 << depth) - 1) : 1;

@@ -194,6 +194,26 @@ def _png_packed(idx, depth, ctype, interlace, palette=None):
     return out + chunk(b"IDAT", zlib.compress(bytes(raw), 6)) + chunk(b"IEND", b"")
 
 
+def _png_wide(rgb16):
+    """RGB PNG of 16 bits per sample (big-endian), filters 0 / 1 / 2 by row."""
+    import struct, zlib
+    h, w, _ = rgb16.shape
+    rows = rgb16.astype(">u2").reshape(h, w * 3).view(np.uint8).reshape(h, w * 6).astype(np.int32)
+    raw = bytearray()
+    prev = np.zeros(w * 6, np.int32)
+    for y in range(h):
+        cur = rows[y]
+        ft = y % 3
+        pred = 0 if ft == 0 else (np.concatenate([np.zeros(6, np.int32), cur[:-6]]) if ft == 1 else prev)
+        raw.append(ft)
+        raw += ((cur - pred) & 255).astype(np.uint8).tobytes()
+        prev = cur
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 16, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(bytes(raw), 6)) +
+            chunk(b"IEND", b""))
+
+
 def _png_filter_rows(px, bpp, filter_types, raw):
     h, w = px.shape[0], px.shape[1]
     rows = np.ascontiguousarray(px).reshape(h, w * bpp).astype(np.int32)
@@ -242,6 +262,9 @@ def test_texture_file_decoders(ofdg, tmp_path):
             pal = rng.integers(0, 256, (1 << depth, 3), dtype=np.uint8)
             (tmp_path / "p.png").write_bytes(_png_packed(g, depth, 3, interlace, pal))
             assert np.array_equal(ofdg.decode_texture_file(tmp_path / "p.png"), np.ascontiguousarray(pal[g][:, :, ::-1].transpose(2, 0, 1))), (depth, interlace)
+    wide = rng.integers(0, 65536, (37, 53, 3), dtype=np.uint16)                      # 16 bits per sample: CImg<unsigned char> keeps the low byte
+    (tmp_path / "w.png").write_bytes(_png_wide(wide))
+    assert np.array_equal(ofdg.decode_texture_file(tmp_path / "w.png"), np.ascontiguousarray((wide & 255).astype(np.uint8)[:, :, ::-1].transpose(2, 0, 1)))
     (tmp_path / "d.png").write_bytes(_png_bytes(rgb, interlace=True))               # Adam7 (53 x 37: ragged passes)
     (tmp_path / "e.png").write_bytes(_png_bytes(rgb[:3, :2], interlace=True))       # passes without pixels
     assert np.array_equal(ofdg.decode_texture_file(tmp_path / "d.png"), want)
